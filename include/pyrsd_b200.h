@@ -1,0 +1,109 @@
+/* pyrsd_b200.h -- C-ABI of the B200-native PT hot path of pyRSD.
+ *
+ * This is the drop-in boundary: it replaces the SWIG module `pyRSD._gcl`
+ * (pyRSD/gcl.i:36-56, pyRSD/_gcl/python/*.i) for the perturbation-theory path.
+ * Plain pointers and sizes only; every array is double precision, C-contiguous,
+ * HOST memory unless stated otherwise.  Every function returns 0 on success or a
+ * negative code (PRSD_ERR_*); prsd_last_error() gives the message.  Nothing here
+ * aborts the process (the reference's Common::error does, Common.cpp:67-74) and
+ * nothing falls back to the CPU: without a usable sm_100 device
+ * prsd_ctx_create fails with PRSD_ERR_NO_DEVICE.
+ *
+ * Batch convention: a `prsd_spectra` holds `ncosmo` cosmologies; outputs are
+ * [ncosmo][...] row-major.
+ */
+#ifndef PYRSD_B200_H
+#define PYRSD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRSD_OK              0
+#define PRSD_ERR_INVALID    -1
+#define PRSD_ERR_CUDA       -2
+#define PRSD_ERR_NO_DEVICE  -3
+#define PRSD_ERR_INTERNAL   -4
+
+typedef struct prsd_ctx prsd_ctx;
+typedef struct prsd_spectra prsd_spectra;
+typedef struct prsd_plan prsd_plan;
+typedef struct prsd_result prsd_result;
+
+const char* prsd_last_error(void);
+int prsd_version(void);
+
+/* ---- device context (one per GPU / process rank) */
+int prsd_ctx_create(int device, prsd_ctx** out);
+int prsd_ctx_destroy(prsd_ctx* ctx);
+int prsd_ctx_sync(prsd_ctx* ctx);
+int prsd_ctx_launches(prsd_ctx* ctx, long long* n_kernels);
+int prsd_ctx_stream(prsd_ctx* ctx, void** cuda_stream);
+
+/* ---- tabulation grid shared by every operator (ln q of the knots) */
+int prsd_knot_grid(int* n, double* lnq /* may be NULL */);
+
+/* ---- quadrature configuration: cfg[9] = {qmin, n_outer, n_inner, ln_far, ln_mid,
+ *      bao_lo, bao_hi, bao_dq, reserved}.  Replaces the reference's `epsrel` constructor
+ *      argument (Imn.i:8, Jmn.i:8, Kmn.i:8): accuracy is set by the fixed rule. */
+int prsd_quad_config_default(double* cfg9);
+
+/* ---- linear spectra: replaces Cosmology + LinearPS (LinearPS.i:5-14, LinearPS.cpp:11-15).
+ *   k, T   [ncosmo][nspl]  discrete transfer function (Cosmology.GetDiscreteK/Tk)
+ *   pars   [ncosmo][8]     {n_s, amplitude = delta_H^2 (sigma8_z/sigma8)^2, h, Omega0_m,
+ *                           Omega0_b, T_cmb, 0, 0}                                        */
+int prsd_spectra_create(prsd_ctx* ctx, int ncosmo, int nspl, const double* k, const double* T,
+                        const double* pars, prsd_spectra** out);
+int prsd_spectra_destroy(prsd_spectra* sp);
+int prsd_spectra_rescale(prsd_spectra* sp, const double* fac /*[ncosmo]*/);   /* LinearPS::SetSigma8AtZ */
+int prsd_spectra_plin(prsd_spectra* sp, int nq, const double* q, double* out /*[ncosmo][nq]*/);
+int prsd_spectra_table(prsd_spectra* sp, int kind, double* out /*[ncosmo][n_knots]*/);
+/* one-loop spectra: OneLoopPS(P_L, epsrel, oneloop_power) ctor / Evaluate / EvaluateFull
+ * (OneLoopPS.i:5-63, OneLoopPS.cpp:21-33); which: 0 Pdd, 1 Pdv, 2 Pvv, 3 P22bar */
+int prsd_spectra_set_oneloop(prsd_spectra* sp, const double* tables /*[ncosmo][4][1000]*/);
+int prsd_spectra_oneloop_eval(prsd_spectra* sp, int which, int full, int nq, const double* q,
+                              double* out /*[ncosmo][nq]*/);
+
+/* ---- one-off evaluations with the call shapes of the pygcl drivers ------------------- */
+/* Imn(P_L)(k, m, n)  [Imn.i:8-14, Imn.cpp:142-189] */
+int prsd_eval_imn(prsd_spectra* sp, int m, int n, int nk, const double* k, const double* cfg9,
+                  double* out /*[ncosmo][nk]*/);
+/* Kmn(P_L)(k, m, n, tidal, part)  [Kmn.i:8-14, Kmn.cpp:109-184] */
+int prsd_eval_kmn(prsd_spectra* sp, int m, int n, int tidal, int part, int nk, const double* k,
+                  const double* cfg9, double* out);
+/* Jmn(P_L)(k, m, n)  [Jmn.i:8-14, Jmn.cpp:96-139] */
+int prsd_eval_jmn(prsd_spectra* sp, int m, int n, int nk, const double* k, double* out);
+/* ImnOneLoop(P1[,P2]).EvaluateLinear/Cross/OneLoop(k, m, n)  [ImnOneLoop.i:8-23,
+ * ImnOneLoop.cpp:96-216]; p1, p2: 0 Pdd, 1 Pdv, 2 Pvv (p2 < 0: single-spectrum ctor);
+ * which: 0 linear, 1 cross, 2 one-loop */
+int prsd_eval_imn_oneloop(prsd_spectra* sp, int p1, int p2, int which, int m, int n, int nk,
+                          const double* k, const double* cfg9, double* out);
+/* PowerSpectrum::VelocityDispersion(), VelocityDispersion(k, factor), X_Zel, Y_Zel, Q3_Zel,
+ * Sigma(R), sigma3_squared  [PowerSpectrum.i:5-45, PowerSpectrum.cpp:28-161]
+ * what: 0 sigma_v^2 (n = 1, x ignored), 1 sigma_v^2(k; factor), 2 X_Zel(r), 3 Y_Zel(r), 4 Q3_Zel(k),
+ *       5 Sigma(R), 6 sigma3_squared(k) */
+int prsd_eval_ps_integral(prsd_spectra* sp, int what, int n, const double* x, double factor,
+                          double* out /*[ncosmo][n]*/);
+/* OneLoopP22Bar::VelocityKurtosis  [OneLoopPS.cpp:187-193] */
+int prsd_eval_kurtosis(prsd_spectra* sp, double* out /*[ncosmo]*/);
+
+/* ---- the batched PT stage: everything rsd/pt_integrals.py:42-450 tabulates ------------ */
+/* flags: bit 0 = ImnOneLoop integrals, bit 1 = Zel'dovich X(r), Y(r) */
+int prsd_plan_create(prsd_ctx* ctx, int nk, const double* k_interp, const double* cfg9, int flags,
+                     prsd_plan** out);
+int prsd_plan_destroy(prsd_plan* plan);
+/* info[8] = {total 2-D nodes, device bytes, build seconds, nk, n_knots, nodes(one-loop op),
+ *            nodes(I/K op), nodes(ImnOneLoop op, one half)} */
+int prsd_plan_info(prsd_plan* plan, double* info8);
+/* *res may be NULL on first use (allocated) and is reused afterwards */
+int prsd_plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res);
+int prsd_result_destroy(prsd_result* res);
+/* what: 0 I [c][16][nk], 1 J [c][6][nk], 2 K [c][13][nk], 3 ML [c][7][3][nk],
+ *       4 one-loop tables [c][4][1000], 5 sigmasq_k [c][nk], 6 scalars [c][4] = {sigma_v^2,
+ *       velocity kurtosis, Q3/k^4, 0}, 7 X_Zel [c][1024], 8 Y_Zel [c][1024] */
+int prsd_result_get(prsd_result* res, int what, double* out, long long n_expected);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRSD_B200_H */

@@ -48,6 +48,10 @@ def lib():
             'ref_ps_sigma3sq': (None, [vp, i, _dp, _dp]),
             'ref_ps_xzel_tol': (None, [vp, i, _dp, d, d, _dp]),
             'ref_ps_yzel_tol': (None, [vp, i, _dp, d, d, _dp]),
+            'ref_ps_sigv_tol': (d, [vp, d, d, d]),
+            'ref_ps_q3_tol': (d, [vp, d, d, d]),
+            'ref_p22bar_kurtosis_tol': (d, [vp, d, d]),
+            'ref_ps_sigma_R_tol': (d, [vp, d, d, d]),
             'ref_imn': (None, [vp, d, i, i, i, _dp, _dp]),
             'ref_jmn': (None, [vp, d, i, i, i, _dp, _dp]),
             'ref_kmn': (None, [vp, d, i, i, i, i, i, _dp, _dp]),
@@ -160,6 +164,16 @@ class RefPower(object):
     def Q3_Zel(self, k):
         return self._vec('ref_ps_q3zel', k)
 
+    # tight-tolerance variants (the reference hard-codes 1e-4..1e-5 in these integrals)
+    def sigv_tol(self, qmax=100.0, epsrel=1e-10, epsabs=1e-14):
+        return lib().ref_ps_sigv_tol(self.ptr, qmax, epsrel, epsabs)
+
+    def Q3_tol(self, k, epsrel=1e-10, epsabs=1e-14):
+        return np.array([lib().ref_ps_q3_tol(self.ptr, float(kk), epsrel, epsabs) for kk in _a(k)])
+
+    def Sigma_tol(self, R, epsrel=1e-10, epsabs=1e-14):
+        return np.array([lib().ref_ps_sigma_R_tol(self.ptr, float(r), epsrel, epsabs) for r in _a(R)])
+
     def sigma3_squared(self, k):
         return self._vec('ref_ps_sigma3sq', k)
 
@@ -213,8 +227,10 @@ class RefOneLoop(RefPower):
         lib().ref_oneloop_eval(self.ptr, 1, len(k), k, out)
         return out
 
-    def VelocityKurtosis(self):
-        return lib().ref_p22bar_kurtosis(self.ptr)
+    def VelocityKurtosis(self, epsrel=None, epsabs=1e-14):
+        if epsrel is None:
+            return lib().ref_p22bar_kurtosis(self.ptr)
+        return lib().ref_p22bar_kurtosis_tol(self.ptr, epsrel, epsabs)
 
 
 def ImnOneLoop(P1, P2, k, m, n, which, epsrel=1e-4):

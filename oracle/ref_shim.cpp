@@ -121,6 +121,38 @@ void ref_ps_yzel_tol(void* P, int n, const double* r, double epsrel, double epsa
         out[i] = 1/(2*M_PI*M_PI) * Integrate(std::bind(Yint, std::cref(ps), r[i], _1), 1e-5, 1e2, epsrel, epsabs);
 }
 
+/* Same integrands and the same reference quadrature templates as PowerSpectrum.cpp:53-62,
+ * 129-136 and OneLoopPS.cpp:183-193, with caller-chosen tolerances (hard-coded there). */
+static double Pint(const PowerSpectrum& P, double q) { return P(q); }
+double ref_ps_sigv_tol(void* P, double qmax, double epsrel, double epsabs)
+{
+    const PowerSpectrum& ps = *(PowerSpectrum*)P;
+    return 1/(6*M_PI*M_PI) * Integrate<ExpSub>(std::bind(Pint, std::cref(ps), _1), 1e-5, qmax, epsrel, epsabs);
+}
+static double Q3int(const PowerSpectrum& P, double q) { double p = P(q); return p*p/q/q; }
+double ref_ps_q3_tol(void* P, double k, double epsrel, double epsabs)
+{
+    const PowerSpectrum& ps = *(PowerSpectrum*)P;
+    return 1/(10*M_PI*M_PI) * Common::pow4(k) * Integrate(std::bind(Q3int, std::cref(ps), _1), 1e-5, 1e2, epsrel, epsabs);
+}
+static double Kurtint(const OneLoopPS& P, double q) { return P.EvaluateFull(q)/(q*q); }
+double ref_p22bar_kurtosis_tol(void* L, double epsrel, double epsabs)
+{
+    const OneLoopPS& ps = *(OneLoopPS*)L;
+    return 0.25/(2*M_PI*M_PI) * Integrate<ExpSub>(std::bind(Kurtint, std::cref(ps), _1), 1e-5, 1e1, epsrel, epsabs);
+}
+static double SigRint(const PowerSpectrum& P, double R, double k)
+{
+    double x = k*R;
+    double W = (x < 1e-5) ? 1 - (1./30.)*x*x : 3/Common::pow3(x) * (sin(x) - x*cos(x));
+    return k*k/(2*M_PI*M_PI) * P(k) * W*W;
+}
+double ref_ps_sigma_R_tol(void* P, double R, double epsrel, double epsabs)
+{
+    const PowerSpectrum& ps = *(PowerSpectrum*)P;
+    return sqrt(Integrate<ExpSub>(std::bind(SigRint, std::cref(ps), R, _1), 1e-5, 1e2, epsrel, epsabs));
+}
+
 /* --------------------------------------------------------- Imn/Jmn/Kmn */
 void ref_imn(void* P, double epsrel, int m, int n, int nk, const double* k, double* out)
 {

@@ -1,0 +1,258 @@
+// bilinear.cu -- build and apply the mode-coupling quadrature operators (see bilinear.cuh).
+#include "bilinear.cuh"
+#include "pt_math.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+
+namespace prsd {
+
+size_t NodeGeometry::bytes() const
+{
+    return n_nodes*(sizeof(int)*2 + sizeof(double)*6) + n_outer*(sizeof(int)*2 + sizeof(double)*5);
+}
+
+std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
+                                            const QuadConfig& cfg, const KnotGrid& grid)
+{
+    PRSD_REQUIRE(nk > 0, "make_geometry: empty k list");
+    for (int i = 0; i < nk; i++) PRSD_REQUIRE(k[i] > 0 && std::isfinite(k[i]), "make_geometry: k[%d] = %g must be > 0", i, k[i]);
+    HalfNodes H;
+    build_half_nodes(k, nk, qmax, cfg, grid, H);
+
+    // pad every k's node list to a multiple of 4 (one DMMA k-step) with weightless nodes
+    auto g = std::make_shared<NodeGeometry>();
+    g->nk = nk;
+    g->k.assign(k, k + nk);
+    std::vector<int> b_j0, n_ol;
+    std::vector<double> b, wgt, b_coef;
+    g->h_node_off.assign(1, 0);
+    g->h_outer_off = H.outer_off;
+    for (int ik = 0; ik < nk; ik++) {
+        const int64_t n0 = H.node_off[ik], n1 = H.node_off[ik + 1];
+        const int64_t o0 = H.outer_off[ik];
+        g->max_outer = std::max<int>(g->max_outer, (int)(H.outer_off[ik + 1] - o0));
+        for (int64_t j = n0; j < n1; j++) {
+            b.push_back(H.b[j]);
+            wgt.push_back(H.wgt[j]);
+            b_j0.push_back(H.b_j0[j]);
+            n_ol.push_back((int)(H.n_outer[j] - o0));
+            b_coef.insert(b_coef.end(), &H.b_coef[4*j], &H.b_coef[4*j] + 4);
+        }
+        while ((b.size() & 3) != 0) {
+            b.push_back(k[ik]);
+            wgt.push_back(0.0);
+            b_j0.push_back(0);
+            n_ol.push_back(0);
+            b_coef.insert(b_coef.end(), 4, 0.0);
+        }
+        g->h_node_off.push_back((int64_t)b.size());
+    }
+    g->n_nodes = (int64_t)b.size();
+    g->n_outer = (int64_t)H.a.size();
+    cudaStream_t s = ctx.stream;
+    g->outer_off.upload(g->h_outer_off, s);
+    g->node_off.upload(g->h_node_off, s);
+    g->a_j0.upload(H.a_j0, s);
+    g->o_kid.upload(H.o_kid, s);
+    g->a.upload(H.a, s);
+    g->a_coef.upload(H.a_coef, s);
+    g->b_j0.upload(b_j0, s);
+    g->n_outer_local.upload(n_ol, s);
+    g->b.upload(b, s);
+    g->wgt.upload(wgt, s);
+    g->b_coef.upload(b_coef, s);
+    g->kdev.upload(g->k, s);
+    ctx.sync();   // the host vectors go out of scope
+    return g;
+}
+
+// ------------------------------------------------------------------ W build
+// fragment-major column order: stored index of column c is (c % 8) * NT + c / 8, so that the
+// NT B-fragment values one lane needs (columns 8 j + lane/4) are contiguous.
+__host__ __device__ inline int w_slot(int col, int nt) { return (col & 7)*nt + (col >> 3); }
+
+struct ColSpecDev { int kid; int sign; double fac; };
+
+__global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, const ColSpecDev* __restrict__ cols,
+                          const int64_t* __restrict__ outer_off, const int64_t* __restrict__ node_off, int nk,
+                          const double* __restrict__ kk, const double* __restrict__ a_arr,
+                          const int* __restrict__ n_outer_local, const double* __restrict__ b_arr,
+                          const double* __restrict__ wgt, double* __restrict__ W)
+{
+    const int64_t node = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (node >= n_nodes) return;
+    // binary search of the k this node belongs to
+    int lo = 0, hi = nk - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (node_off[mid] <= node) lo = mid; else hi = mid - 1;
+    }
+    const double k = kk[lo];
+    const double a = a_arr[outer_off[lo] + n_outer_local[node]];
+    const double b = b_arr[node];
+    const double w = wgt[node];
+    const double u = (a + b)/k, vp = (b - a)/k;
+    const double ea = 2.0*a/k, eb = 2.0*b/k;
+    const int nt = ncol >> 3;
+    double* row = W + node*ncol;
+    for (int c = 0; c < ncol; c++) {
+        double val = 0.0;
+        if (c < ncol_used && w != 0.0) {
+            const ColSpecDev cs = cols[c];
+            const double f = cs.sign > 0 ? pt_kernel(cs.kid, u, vp, ea, eb)
+                                         : pt_kernel(cs.kid, u, -vp, eb, ea);
+            val = w*k*cs.fac*f;
+        }
+        row[w_slot(c, nt)] = val;
+    }
+}
+
+void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols)
+{
+    geo = g;
+    ncol_used = (int)cols.size();
+    ncol = (ncol_used + 7)/8*8;
+    PRSD_REQUIRE(ncol_used > 0 && ncol <= 40, "BilinearOp: %d columns unsupported", ncol_used);
+    std::vector<ColSpecDev> hc(ncol_used);
+    for (int i = 0; i < ncol_used; i++) hc[i] = {cols[i].kid, cols[i].sign, cols[i].fac};
+    DevBuf<ColSpecDev> dc;
+    dc.upload(hc, ctx.stream);
+    W.alloc((size_t)g->n_nodes*ncol);
+    const int threads = 128;
+    const int64_t blocks = (g->n_nodes + threads - 1)/threads;
+    k_build_w<<<(unsigned)blocks, threads, 0, ctx.stream>>>(g->n_nodes, ncol, ncol_used, dc.p, g->outer_off.p,
+        g->node_off.p, g->nk, g->kdev.p, g->a.p, g->n_outer_local.p, g->b.p, g->wgt.p, W.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+    ctx.sync();
+}
+
+// -------------------------------------------------------------------- apply
+// One CTA per (k, tile of 8 rows).  Shared memory:
+//   [ nslots tables (TAB_MPAD doubles each) | PaS[8][max_outer] | mbarrier ]
+// and, after the node loop, the table area is reused for the cross-warp reduction.
+static const int BL_THREADS = 512;
+static const int BL_WARPS = BL_THREADS/32;
+
+template <int NT>
+__global__ void __launch_bounds__(BL_THREADS, 1)
+k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, const int64_t* __restrict__ node_off,
+                 const int* __restrict__ a_j0, const double* __restrict__ a_coef,
+                 const int* __restrict__ b_j0, const int* __restrict__ n_outer_local,
+                 const double* __restrict__ b_coef, const double* __restrict__ W,
+                 const double* __restrict__ tables, const int* __restrict__ slot_tab,
+                 const int* __restrict__ rowA, const int* __restrict__ rowB, double* __restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tabs = reinterpret_cast<double*>(smem_raw);
+    double* PaS = tabs + 8*TAB_MPAD;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(PaS + 8*max_outer);
+
+    const int ik = blockIdx.x;
+    const int tile = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- stage the (up to) 8 spectra tables of this row tile with TMA bulk copies
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = TAB_MPAD*sizeof(double);
+        mbar_expect_tx(mbar, 8*bytes);
+        for (int s = 0; s < 8; s++)
+            bulk_copy_g2s(tabs + s*TAB_MPAD, tables + (size_t)slot_tab[tile*8 + s]*TAB_MPAD, bytes, mbar);
+    }
+    mbar_wait(mbar, 0);
+
+    // ---- P_A(a) for every outer node of this k and every row
+    const int64_t o0 = outer_off[ik];
+    const int n_out = (int)(outer_off[ik + 1] - o0);
+    for (int idx = tid; idx < 8*n_out; idx += BL_THREADS) {
+        const int o = idx >> 3, r = idx & 7;
+        const double* t = tabs + rowA[tile*8 + r]*TAB_MPAD + a_j0[o0 + o];
+        const double* c = a_coef + 4*(o0 + o);
+        PaS[r*max_outer + o] = c[0]*t[0] + c[1]*t[1] + c[2]*t[2] + c[3]*t[3];
+    }
+    __syncthreads();
+
+    // ---- node loop: each warp consumes 4 nodes per step; lane = (row = lane/4, node = lane%4)
+    const int row = lane >> 2, sub = lane & 3;
+    const double* tb = tabs + rowB[tile*8 + row]*TAB_MPAD;
+    const double* pa = PaS + row*max_outer;
+    double acc[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = 0.0;
+
+    const int64_t n0 = node_off[ik], n1 = node_off[ik + 1];
+#pragma unroll 2
+    for (int64_t base = n0 + 4*warp; base < n1; base += 4*BL_WARPS) {
+        const int64_t node = base + sub;
+        const int j0 = __ldg(b_j0 + node);
+        const int ol = __ldg(n_outer_local + node);
+        const double2 c01 = __ldg(reinterpret_cast<const double2*>(b_coef + 4*node));
+        const double2 c23 = __ldg(reinterpret_cast<const double2*>(b_coef + 4*node) + 1);
+        double wf[NT];
+        const double* wrow = W + node*(8*NT) + row*NT;
+#pragma unroll
+        for (int j = 0; j < NT; j++) wf[j] = __ldg(wrow + j);
+        const double* t = tb + j0;
+        double pb = c01.x*t[0];
+        pb = fma(c01.y, t[1], pb);
+        pb = fma(c23.x, t[2], pb);
+        pb = fma(c23.y, t[3], pb);
+        const double pp = pa[ol]*pb;
+#pragma unroll
+        for (int j = 0; j < NT; j++) dmma_m8n8k4(acc[j][0], acc[j][1], pp, wf[j]);
+    }
+
+    // ---- reduce the C fragments of the 16 warps and write out[row][k][col]
+    __syncthreads();                       // everyone is done reading the tables
+    double* red = tabs;                    // [warp][NT][64]
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+        red[(warp*NT + j)*64 + row*8 + sub*2 + 0] = acc[j][0];
+        red[(warp*NT + j)*64 + row*8 + sub*2 + 1] = acc[j][1];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NT*64; idx += BL_THREADS) {
+        const int j = idx >> 6, e = idx & 63;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < BL_WARPS; w++) s += red[(w*NT + j)*64 + e];
+        const int r = e >> 3, c = 8*j + (e & 7);
+        out[((size_t)(tile*8 + r)*nk + ik)*(8*NT) + c] = s;
+    }
+}
+
+template <int NT>
+static void launch_apply(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab,
+                         const int* rowA, const int* rowB, int ntiles, double* out)
+{
+    const NodeGeometry& g = *op.geo;
+    const size_t smem = (size_t)(8*TAB_MPAD + 8*g.max_outer)*sizeof(double) + 16;
+    PRSD_REQUIRE(smem <= ctx.smem_optin, "bilinear apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
+    PRSD_CUDA(cudaFuncSetAttribute(k_bilinear_apply<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(g.nk, ntiles);
+    k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, g.max_outer, g.outer_off.p, g.node_off.p,
+        g.a_j0.p, g.a_coef.p, g.b_j0.p, g.n_outer_local.p, g.b_coef.p, op.W.p, tables, slot_tab, rowA, rowB, out);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
+void BilinearOp::apply(Context& ctx, const double* tables, const int* slot_tab, const int* rowA,
+                       const int* rowB, int ntiles, double* out) const
+{
+    switch (ncol/8) {
+        case 1: launch_apply<1>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
+        case 2: launch_apply<2>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
+        case 3: launch_apply<3>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
+        case 4: launch_apply<4>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
+        case 5: launch_apply<5>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
+        default: throw Error(ERR_INTERNAL, "BilinearOp::apply: unsupported column count");
+    }
+}
+
+} // namespace prsd

@@ -1,0 +1,62 @@
+// bilinear.cuh -- the mode-coupling integrals as a precomputed quadrature operator.
+//
+// Every 2-D integral of the reference's Imn / Kmn / ImnOneLoop drivers
+// (Imn.cpp:113-140, Kmn.cpp:109-138, ImnOneLoop.cpp:74-93) has the form
+//     O_c(k) = sum_nodes  W_c[node] * P_1(a_node) * P_2(b_node)
+// once a fixed quadrature is chosen (quad.h).  W (measure x kernel x quadrature weight)
+// depends only on k and the kernel, so it is built ONCE on the device and every cosmology /
+// spectrum pair is then a row of a (rows x nodes) . (nodes x kernels) contraction, executed
+// with FP64 tensor-core MMAs (DMMA m8n8k4) fed from spectra tables staged in shared memory
+// by TMA bulk copies.
+#pragma once
+#include "common.h"
+#include "quad.h"
+
+#include <memory>
+
+namespace prsd {
+
+static const int TAB_M    = 2342;   // knots of make_knot_grid() (checked at start-up)
+static const int TAB_MPAD = 2356;   // row stride of every spectra table: = 4 (mod 16) doubles
+
+struct ColSpec {
+    int kid;        // KernelId
+    int sign;       // +1: f(u, +v') with P_1(a) P_2(b);  -1: f(u, -v') (the r <= q half)
+    double fac;     // coefficient c in the prefactor c * k  (k/(8 pi^2) etc.)
+};
+
+// node geometry on the device, shared between operators on the same k list
+struct NodeGeometry {
+    int nk = 0;
+    int max_outer = 0;
+    int64_t n_nodes = 0, n_outer = 0;
+    std::vector<double> k;
+    std::vector<int64_t> h_node_off, h_outer_off;
+    DevBuf<int64_t> outer_off, node_off;
+    DevBuf<int> a_j0, o_kid;
+    DevBuf<double> a, a_coef;
+    DevBuf<int> b_j0, n_outer_local;
+    DevBuf<double> b, wgt, b_coef;
+    DevBuf<double> kdev;
+    size_t bytes() const;
+};
+
+std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
+                                            const QuadConfig& cfg, const KnotGrid& grid);
+
+struct BilinearOp {
+    std::shared_ptr<NodeGeometry> geo;
+    int ncol = 0;       // padded to a multiple of 8
+    int ncol_used = 0;
+    DevBuf<double> W;   // [n_nodes][ncol] in fragment-major column order
+    void build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols);
+
+    // out[row][k][ncol] (device) = sum_nodes W * TA_row(a) * TB_row(b)
+    //   tables   : device pool [ntab][TAB_MPAD]
+    //   slot_tab : device [ntiles][8] global table index of each local slot
+    //   rowA/rowB: device [ntiles][8] local slot (0..7) of the a-side / b-side table per row
+    void apply(Context& ctx, const double* tables, const int* slot_tab, const int* rowA,
+               const int* rowB, int ntiles, double* out) const;
+};
+
+} // namespace prsd

@@ -1,0 +1,436 @@
+// capi.cu -- extern "C" entry points declared in include/pyrsd_b200.h.
+#include "../../include/pyrsd_b200.h"
+#include "plan.cuh"
+
+#include <cstring>
+#include <list>
+#include <mutex>
+
+using namespace prsd;
+
+struct prsd_ctx { Context c; explicit prsd_ctx(int d) : c(d) {} };
+struct prsd_spectra { SpectraBatch s; prsd_spectra(Context& c, int nc, int ns, const double* k, const double* T, const double* p) : s(c, nc, ns, k, T, p) {} };
+struct prsd_plan { PTPlan p; prsd_plan(Context& c, const double* k, int nk, const QuadConfig& q, bool ml, bool zel) : p(c, k, nk, q, ml, zel) {} };
+struct prsd_result { PTResult r; Context* ctx = nullptr; };
+
+static thread_local std::string g_err;
+
+template <typename F>
+static int guarded(F&& f)
+{
+    try {
+        f();
+        return PRSD_OK;
+    } catch (const Error& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return PRSD_ERR_INTERNAL;
+    } catch (...) {
+        g_err = "unknown exception";
+        return PRSD_ERR_INTERNAL;
+    }
+}
+
+static QuadConfig cfg_from(const double* c9)
+{
+    QuadConfig q;
+    if (c9) {
+        q.qmin = c9[0]; q.n_outer = (int)c9[1]; q.n_inner = (int)c9[2]; q.ln_far = c9[3]; q.ln_mid = c9[4];
+        q.bao_lo = c9[5]; q.bao_hi = c9[6]; q.bao_dq = c9[7];
+        PRSD_REQUIRE(q.qmin >= 1e-8 && q.qmin < 1e-5, "quadrature config: qmin = %g outside [1e-8, 1e-5)", q.qmin);
+        PRSD_REQUIRE(q.n_outer >= 2 && q.n_outer <= 64 && q.n_inner >= 2 && q.n_inner <= 64, "quadrature config: bad point counts");
+        PRSD_REQUIRE(q.ln_far > 0 && q.ln_mid > 0 && q.bao_dq > 0, "quadrature config: widths must be positive");
+    }
+    return q;
+}
+
+// small cache of node geometries for the one-off calls (keyed by device, qmax, config, k)
+struct GeoKey {
+    int device; double qmax; QuadConfig cfg; std::vector<double> k;
+    bool operator==(const GeoKey& o) const
+    {
+        return device == o.device && qmax == o.qmax && k == o.k && std::memcmp(&cfg, &o.cfg, sizeof(QuadConfig)) == 0;
+    }
+};
+static std::mutex g_geo_mu;
+static std::list<std::pair<GeoKey, std::shared_ptr<NodeGeometry>>> g_geo_cache;
+
+static std::shared_ptr<NodeGeometry> cached_geometry(Context& c, const double* k, int nk, double qmax, const QuadConfig& cfg)
+{
+    GeoKey key{c.device, qmax, cfg, std::vector<double>(k, k + nk)};
+    std::lock_guard<std::mutex> lock(g_geo_mu);
+    for (auto it = g_geo_cache.begin(); it != g_geo_cache.end(); ++it)
+        if (it->first == key) {
+            g_geo_cache.splice(g_geo_cache.begin(), g_geo_cache, it);
+            return g_geo_cache.front().second;
+        }
+    auto g = make_geometry(c, k, nk, qmax, cfg, knot_grid());
+    g_geo_cache.emplace_front(std::move(key), g);
+    while (g_geo_cache.size() > 6) g_geo_cache.pop_back();
+    return g;
+}
+
+// apply a small operator with rows = (cosmology) and tables (kindA, kindB); returns [ncosmo][nk][ncol]
+static void apply_rows(SpectraBatch& sp, const BilinearOp& op, int kindA, int kindB, std::vector<double>& host)
+{
+    Context& c = *sp.ctx;
+    const int nc = sp.ncosmo, ntile = (nc + 3)/4;
+    // 4 cosmologies per tile: slots 0..3 = kindA tables, 4..7 = kindB tables
+    std::vector<int> slot(ntile*8), rA(ntile*8), rB(ntile*8);
+    for (int t = 0; t < ntile; t++)
+        for (int r = 0; r < 8; r++) {
+            const int ci = std::min(t*4 + (r & 3), nc - 1);
+            slot[t*8 + r] = sp.table_index(ci, r < 4 ? kindA : kindB);
+            rA[t*8 + r] = r & 3;
+            rB[t*8 + r] = 4 + (r & 3);
+        }
+    DevBuf<int> ds, dA, dB;
+    ds.upload(slot, c.stream);
+    dA.upload(rA, c.stream);
+    dB.upload(rB, c.stream);
+    const int nk = op.geo->nk;
+    DevBuf<double> out((size_t)ntile*8*nk*op.ncol);
+    op.apply(c, sp.tables.p, ds.p, dA.p, dB.p, ntile, out.p);
+    std::vector<double> tmp((size_t)ntile*8*nk*op.ncol);
+    out.download(tmp.data(), tmp.size(), c.stream);
+    c.sync();
+    // rows 0..3 of each tile are the cosmologies (rows 4..7 duplicate them)
+    host.assign((size_t)nc*nk*op.ncol, 0.0);
+    for (int i = 0; i < nc; i++) {
+        const int t = i/4, r = i%4;
+        std::memcpy(&host[(size_t)i*nk*op.ncol], &tmp[((size_t)(t*8 + r))*nk*op.ncol], sizeof(double)*nk*op.ncol);
+    }
+}
+
+static void eval_kernel_generic(SpectraBatch& sp, int kid, int convention, int kindQ, int kindR, double qmax,
+                                int nk, const double* k, const double* cfg9, double* out)
+{
+    // convention 0: Imn, 1: Kmn, 2: ImnOneLoop (see Imn.cpp:120-140, Kmn.cpp:118-138, ImnOneLoop.cpp:82-93)
+    Context& c = *sp.ctx;
+    if (nk <= 0) return;
+    const QuadConfig cfg = cfg_from(cfg9);
+    // the reference returns 0 for k <= 0 (Imn.cpp:122)
+    std::vector<double> kpos;
+    std::vector<int> where;
+    for (int i = 0; i < nk; i++) {
+        PRSD_REQUIRE(std::isfinite(k[i]), "k[%d] is not finite", i);
+        if (k[i] > 0) { kpos.push_back(k[i]); where.push_back(i); }
+    }
+    for (size_t i = 0; i < (size_t)sp.ncosmo*nk; i++) out[i] = 0.0;
+    if (kpos.empty()) return;
+    auto geo = cached_geometry(c, kpos.data(), (int)kpos.size(), qmax, cfg);
+    const bool sym = kernel_is_symmetric(kid);
+    const double V8 = 1.0/(8.0*M_PI*M_PI), V4 = 1.0/(4.0*M_PI*M_PI);
+    const int np = (int)kpos.size();
+    std::vector<double> pos, neg;
+    BilinearOp op;
+    if (convention == 0)      op.build(c, geo, {{kid, +1, sym ? 2*V8 : V8}});
+    else if (convention == 1) op.build(c, geo, {{kid, +1, sym ? V4 : 0.5*V4}});
+    else                      op.build(c, geo, {{kid, +1, V8}});
+    apply_rows(sp, op, kindQ, kindR, pos);
+    const bool need_neg = (convention == 2) || !sym;
+    if (need_neg) {
+        BilinearOp on;
+        on.build(c, geo, {{kid, -1, convention == 1 ? 0.5*V4 : V8}});
+        apply_rows(sp, on, kindR, kindQ, neg);      // a = r, b = q on the v < 0 half
+    }
+    for (int ci = 0; ci < sp.ncosmo; ci++)
+        for (int i = 0; i < np; i++) {
+            double v = pos[((size_t)ci*np + i)*8];
+            if (need_neg) v += neg[((size_t)ci*np + i)*8];
+            out[(size_t)ci*nk + where[i]] = v;
+        }
+}
+
+static void eval_linear_generic(SpectraBatch& sp, const std::vector<LinOutSpec>& outs, int kind, double* out)
+{
+    Context& c = *sp.ctx;
+    LinearOp op;
+    op.build(c, outs);
+    std::vector<int> idx(sp.ncosmo);
+    for (int i = 0; i < sp.ncosmo; i++) idx[i] = sp.table_index(i, kind);
+    DevBuf<int> di;
+    di.upload(idx, c.stream);
+    DevBuf<double> o((size_t)sp.ncosmo*op.nout);
+    op.apply(c, sp.tables.p, di.p, sp.ncosmo, o.p);
+    o.download(out, (size_t)sp.ncosmo*op.nout, c.stream);
+    c.sync();
+}
+
+extern "C" {
+
+const char* prsd_last_error(void) { return g_err.c_str(); }
+int prsd_version(void) { return 100; }
+
+int prsd_ctx_create(int device, prsd_ctx** out)
+{
+    return guarded([&] { PRSD_REQUIRE(out, "null output"); *out = new prsd_ctx(device); });
+}
+int prsd_ctx_destroy(prsd_ctx* ctx) { return guarded([&] { delete ctx; }); }
+int prsd_ctx_sync(prsd_ctx* ctx) { return guarded([&] { PRSD_REQUIRE(ctx, "null context"); ctx->c.sync(); }); }
+int prsd_ctx_launches(prsd_ctx* ctx, long long* n)
+{
+    return guarded([&] { PRSD_REQUIRE(ctx && n, "null argument"); *n = ctx->c.launches; });
+}
+int prsd_ctx_stream(prsd_ctx* ctx, void** s)
+{
+    return guarded([&] { PRSD_REQUIRE(ctx && s, "null argument"); *s = (void*)ctx->c.stream; });
+}
+
+int prsd_knot_grid(int* n, double* lnq)
+{
+    return guarded([&] {
+        const KnotGrid& g = knot_grid();
+        if (n) *n = g.size();
+        if (lnq) std::memcpy(lnq, g.x.data(), sizeof(double)*g.size());
+    });
+}
+
+int prsd_quad_config_default(double* c9)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(c9, "null argument");
+        QuadConfig q;
+        c9[0] = q.qmin; c9[1] = q.n_outer; c9[2] = q.n_inner; c9[3] = q.ln_far; c9[4] = q.ln_mid;
+        c9[5] = q.bao_lo; c9[6] = q.bao_hi; c9[7] = q.bao_dq; c9[8] = 0.0;
+    });
+}
+
+int prsd_spectra_create(prsd_ctx* ctx, int ncosmo, int nspl, const double* k, const double* T,
+                        const double* pars, prsd_spectra** out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && k && T && pars && out, "null argument");
+        *out = new prsd_spectra(ctx->c, ncosmo, nspl, k, T, pars);
+    });
+}
+int prsd_spectra_destroy(prsd_spectra* sp) { return guarded([&] { delete sp; }); }
+int prsd_spectra_rescale(prsd_spectra* sp, const double* fac)
+{
+    return guarded([&] { PRSD_REQUIRE(sp && fac, "null argument"); sp->s.rescale_linear(fac); });
+}
+int prsd_spectra_plin(prsd_spectra* sp, int nq, const double* q, double* out)
+{
+    return guarded([&] { PRSD_REQUIRE(sp && (nq == 0 || (q && out)), "null argument"); sp->s.eval_linear(nq, q, out); });
+}
+int prsd_spectra_table(prsd_spectra* sp, int kind, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && out, "null argument");
+        PRSD_REQUIRE(kind >= 0 && kind < SP_NKIND, "invalid table kind %d", kind);
+        SpectraBatch& s = sp->s;
+        for (int i = 0; i < s.ncosmo; i++)
+            PRSD_CUDA(cudaMemcpyAsync(out + (size_t)i*TAB_M, s.table_ptr(i, kind), TAB_M*sizeof(double), cudaMemcpyDeviceToHost, s.ctx->stream));
+        s.ctx->sync();
+    });
+}
+int prsd_spectra_set_oneloop(prsd_spectra* sp, const double* tables)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && tables, "null argument");
+        SpectraBatch& s = sp->s;
+        DevBuf<double> d;
+        d.upload(tables, (size_t)s.ncosmo*4*ONELOOP_N, s.ctx->stream);
+        s.set_oneloop_tables(d.p);
+        s.ctx->sync();
+    });
+}
+int prsd_spectra_oneloop_eval(prsd_spectra* sp, int which, int full, int nq, const double* q, double* out)
+{
+    return guarded([&] { PRSD_REQUIRE(sp && (nq == 0 || (q && out)), "null argument"); sp->s.eval_oneloop(which, full != 0, nq, q, out); });
+}
+
+int prsd_eval_imn(prsd_spectra* sp, int m, int n, int nk, const double* k, const double* cfg9, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
+        // the reference aborts on invalid indices (Imn.cpp:186); here: error code
+        PRSD_REQUIRE(m >= 0 && m <= 3 && n >= 0 && n <= 3, "Imn: invalid indices, m = %d, n = %d", m, n);
+        eval_kernel_generic(sp->s, 4*m + n, 0, SP_LIN, SP_LIN, 1e5, nk, k, cfg9, out);
+    });
+}
+
+int prsd_eval_kmn(prsd_spectra* sp, int m, int n, int tidal, int part, int nk, const double* k, const double* cfg9, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
+        int kid = -1;
+        // Kmn::Evaluate dispatch on 2 (3 m + tidal) + n (Kmn.cpp:151-183)
+        switch (2*(3*m + (tidal ? 1 : 0)) + n) {
+            case 0: kid = KID_K00; break;   case 1: kid = KID_K01; break;
+            case 2: kid = KID_K00S; break;  case 3: kid = KID_K01S; break;
+            case 4: kid = KID_K02S; break;  case 6: kid = KID_K10; break;
+            case 7: kid = KID_K11; break;   case 8: kid = KID_K10S; break;
+            case 9: kid = KID_K11S; break;
+            case 12: kid = part == 0 ? KID_K20A : KID_K20B; break;
+            case 14: kid = part == 0 ? KID_K20SA : KID_K20SB; break;
+            default: break;
+        }
+        PRSD_REQUIRE(kid >= 0 && m >= 0 && n >= 0, "Kmn: invalid indices, m = %d, n = %d", m, n);
+        eval_kernel_generic(sp->s, kid, 1, SP_LIN, SP_LIN, 1e5, nk, k, cfg9, out);
+    });
+}
+
+int prsd_eval_jmn(prsd_spectra* sp, int m, int n, int nk, const double* k, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
+        const int id = 3*m + n;
+        PRSD_REQUIRE(m >= 0 && n >= 0 && (id == 0 || id == 1 || id == 2 || id == 3 || id == 4 || id == 6) && n <= 2,
+                     "Jmn: invalid indices, m = %d, n = %d", m, n);
+        if (nk == 0) return;
+        std::vector<LinOutSpec> o;
+        std::vector<int> where;
+        for (int i = 0; i < nk; i++) if (k[i] > 0) { o.push_back({LK_JMN, id, k[i], 1e-5, 1e5, 1.0}); where.push_back(i); }
+        for (size_t i = 0; i < (size_t)sp->s.ncosmo*nk; i++) out[i] = 0.0;
+        if (o.empty()) return;
+        std::vector<double> tmp((size_t)sp->s.ncosmo*o.size());
+        eval_linear_generic(sp->s, o, SP_LIN, tmp.data());
+        for (int c = 0; c < sp->s.ncosmo; c++)
+            for (size_t i = 0; i < o.size(); i++) out[(size_t)c*nk + where[i]] = tmp[(size_t)c*o.size() + i];
+    });
+}
+
+int prsd_eval_imn_oneloop(prsd_spectra* sp, int p1, int p2, int which, int m, int n, int nk, const double* k,
+                          const double* cfg9, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
+        PRSD_REQUIRE(sp->s.have_oneloop, "ImnOneLoop: one-loop spectra have not been set for this batch");
+        PRSD_REQUIRE(p1 >= 0 && p1 <= 2 && p2 <= 2, "ImnOneLoop: invalid spectra (%d, %d)", p1, p2);
+        PRSD_REQUIRE(which >= 0 && which <= 2, "ImnOneLoop: invalid part %d", which);
+        const bool equal = p2 < 0;
+        if (equal) p2 = p1;
+        int kid = -1, kid_cross = -1;
+        switch (2*m + n) {          // ImnOneLoop.cpp:97-116
+            case 1: kid = kid_cross = KID_H01; break;
+            case 2: kid = kid_cross = KID_H02; break;
+            case 3: kid = kid_cross = KID_K20A; break;
+            case 4: kid = kid_cross = KID_K20B; break;
+            case 7: kid = kid_cross = KID_F23; break;
+            case 8: kid = KID_F23; kid_cross = KID_F32; break;     // reference quirk (:108-109, :160-165, :199-200)
+            case 9: kid = kid_cross = KID_F33; break;
+            default: break;
+        }
+        PRSD_REQUIRE(kid >= 0 && m >= 0 && n >= 0, "ImnOneLoop: invalid indices, m = %d, n = %d", m, n);
+        const int K1 = SP_DD1 + p1, K2 = SP_DD1 + p2;
+        SpectraBatch& s = sp->s;
+        if (which == 0) eval_kernel_generic(s, kid, 2, SP_LIN, SP_LIN, 10.0, nk, k, cfg9, out);
+        else if (which == 2) eval_kernel_generic(s, kid, 2, K1, K2, 10.0, nk, k, cfg9, out);
+        else {
+            eval_kernel_generic(s, kid_cross, 2, SP_LIN, K2, 10.0, nk, k, cfg9, out);
+            const size_t tot = (size_t)s.ncosmo*nk;
+            if (equal) { for (size_t i = 0; i < tot; i++) out[i] *= 2.0; }
+            else {
+                std::vector<double> part2(tot);
+                eval_kernel_generic(s, kid_cross, 2, K1, SP_LIN, 10.0, nk, k, cfg9, part2.data());
+                for (size_t i = 0; i < tot; i++) out[i] += part2[i];
+            }
+        }
+    });
+}
+
+int prsd_eval_ps_integral(prsd_spectra* sp, int what, int n, const double* x, double factor, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && out, "null argument");
+        std::vector<LinOutSpec> o;
+        int kind = SP_LIN;
+        if (what == 0) { n = 1; o.push_back({LK_SIGV, 0, 0.0, 1e-5, 1e2, 1.0}); }
+        else {
+            PRSD_REQUIRE(n >= 0 && (n == 0 || x), "null argument");
+            if (n == 0) return;
+            for (int i = 0; i < n; i++) {
+                const double v = x[i];
+                PRSD_REQUIRE(std::isfinite(v) && v > 0, "argument %d = %g must be positive", i, v);
+                switch (what) {
+                    case 1: {
+                        const double hi = factor*v;
+                        if (hi >= 1e-5) o.push_back({LK_SIGV, 0, 0.0, 1e-5, hi, 1.0});
+                        else o.push_back({LK_SIGV, 0, 0.0, hi, 1e-5, -1.0});
+                        break;
+                    }
+                    case 2: o.push_back({LK_XZEL, 0, v, 1e-5, 1e2, 1.0}); break;
+                    case 3: o.push_back({LK_YZEL, 0, v, 1e-5, 1e2, 1.0}); break;
+                    case 4: o.push_back({LK_INVQ2, 0, 0.0, 1e-5, 1e2, v*v*v*v/(10.0*M_PI*M_PI)}); kind = SP_LIN_SQ; break;
+                    case 5: o.push_back({LK_SIGMA_R, 0, v, 1e-5, 1e2, 1.0}); break;
+                    case 6: o.push_back({LK_SIGMA3, 0, v, 1e-5*v, 1e2*v, 1.0}); break;
+                    default: PRSD_REQUIRE(false, "unknown integral %d", what);
+                }
+            }
+        }
+        eval_linear_generic(sp->s, o, kind, out);
+        if (what == 5) for (size_t i = 0; i < (size_t)sp->s.ncosmo*n; i++) out[i] = std::sqrt(out[i]);
+    });
+}
+
+int prsd_eval_kurtosis(prsd_spectra* sp, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp && out, "null argument");
+        PRSD_REQUIRE(sp->s.have_oneloop, "VelocityKurtosis: one-loop spectra have not been set for this batch");
+        eval_linear_generic(sp->s, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}}, SP_P22BAR, out);
+    });
+}
+
+int prsd_plan_create(prsd_ctx* ctx, int nk, const double* k, const double* cfg9, int flags, prsd_plan** out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && k && out, "null argument");
+        *out = new prsd_plan(ctx->c, k, nk, cfg_from(cfg9), (flags & 1) != 0, (flags & 2) != 0);
+    });
+}
+int prsd_plan_destroy(prsd_plan* plan) { return guarded([&] { delete plan; }); }
+int prsd_plan_info(prsd_plan* plan, double* info)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(plan && info, "null argument");
+        const PTPlan& p = plan->p;
+        info[0] = (double)p.nodes_total();
+        info[1] = (double)p.device_bytes();
+        info[2] = p.build_seconds;
+        info[3] = p.nk;
+        info[4] = TAB_M;
+        info[5] = p.op_1loop.geo ? (double)p.op_1loop.geo->n_nodes : 0.0;
+        info[6] = p.op_ik.geo ? (double)p.op_ik.geo->n_nodes : 0.0;
+        info[7] = p.op_ml_pos.geo ? (double)p.op_ml_pos.geo->n_nodes : 0.0;
+    });
+}
+int prsd_plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(plan && sp && res, "null argument");
+        if (!*res) { *res = new prsd_result(); (*res)->ctx = plan->p.ctx; }
+        plan->p.run(sp->s, (*res)->r);
+    });
+}
+int prsd_result_destroy(prsd_result* res) { return guarded([&] { delete res; }); }
+int prsd_result_get(prsd_result* res, int what, double* out, long long n_expected)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(res && out, "null argument");
+        PTResult& r = res->r;
+        const size_t c = r.ncosmo, nk = r.nk;
+        const DevBuf<double>* b = nullptr;
+        size_t n = 0;
+        switch (what) {
+            case 0: b = &r.I; n = c*16*nk; break;
+            case 1: b = &r.J; n = c*6*nk; break;
+            case 2: b = &r.K; n = c*13*nk; break;
+            case 3: b = &r.ML; n = c*N_ML*3*nk; break;
+            case 4: b = &r.oneloop; n = c*4*ONELOOP_N; break;
+            case 5: b = &r.sigmasq_k; n = c*nk; break;
+            case 6: b = &r.scalars; n = c*4; break;
+            case 7: b = &r.X0; n = c*ZEL_NR; break;
+            case 8: b = &r.YY; n = c*ZEL_NR; break;
+            default: PRSD_REQUIRE(false, "unknown result id %d", what);
+        }
+        PRSD_REQUIRE((long long)n == n_expected, "result %d has %zu elements, caller expects %lld", what, n, n_expected);
+        b->download(out, n, res->ctx->stream);
+        res->ctx->sync();
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,108 @@
+// common.h -- error plumbing, device context and small RAII helpers shared by the library.
+//
+// Error convention of the C-ABI (replaces the reference's SWIG exception translation,
+// pyRSD/gcl.i:22-30, and its abort()-on-bad-index, Common.cpp:67-74): every entry point
+// returns PRSD_OK (0) or a negative code and never aborts; prsd_last_error() returns the
+// message for the calling thread.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace prsd {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+enum {
+    ERR_OK = 0,
+    ERR_INVALID = -1,     // bad argument (e.g. invalid (m, n) indices)
+    ERR_CUDA = -2,        // CUDA runtime failure
+    ERR_NO_DEVICE = -3,   // no usable GPU: there is no CPU fallback by design
+    ERR_INTERNAL = -4,
+};
+
+inline std::string strprintf(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return std::string(buf);
+}
+
+#define PRSD_CUDA(expr)                                                                     \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            throw ::prsd::Error(::prsd::ERR_CUDA, ::prsd::strprintf("%s failed: %s (%s:%d)", #expr, \
+                                cudaGetErrorString(e_), __FILE__, __LINE__));               \
+    } while (0)
+
+#define PRSD_REQUIRE(cond, ...)                                                             \
+    do {                                                                                    \
+        if (!(cond)) throw ::prsd::Error(::prsd::ERR_INVALID, ::prsd::strprintf(__VA_ARGS__)); \
+    } while (0)
+
+// Device buffer (cudaMallocAsync-free: plain cudaMalloc, freed in dtor).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t n_)
+    {
+        release();
+        n = n_;
+        if (n) PRSD_CUDA(cudaMalloc((void**)&p, n*sizeof(T)));
+    }
+    void ensure(size_t n_) { if (n_ > n) alloc(n_); }
+    void upload(const T* h, size_t cnt, cudaStream_t s)
+    {
+        ensure(cnt);
+        if (cnt) PRSD_CUDA(cudaMemcpyAsync(p, h, cnt*sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+    void download(T* h, size_t cnt, cudaStream_t s) const
+    {
+        if (cnt) PRSD_CUDA(cudaMemcpyAsync(h, p, cnt*sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    void zero(cudaStream_t s) { if (n) PRSD_CUDA(cudaMemsetAsync(p, 0, n*sizeof(T), s)); }
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    long long launches = 0;        // kernels launched through this context (bench bookkeeping)
+    explicit Context(int dev);
+    ~Context();
+    void sync() { PRSD_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+} // namespace prsd

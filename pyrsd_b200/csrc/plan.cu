@@ -1,0 +1,335 @@
+// plan.cu -- PT plan construction and the batched PT stage (see plan.cuh).
+#include "plan.cuh"
+
+#include <chrono>
+#include <cmath>
+
+namespace prsd {
+
+// parray::logspace (pyRSD/_gcl/cpp/parray.cpp:101-121): exp(ln min + i dln), exact end points
+static std::vector<double> logspace_ref(double lo, double hi, int n)
+{
+    std::vector<double> x(n);
+    const double l0 = std::log(lo), l1 = std::log(hi);
+    for (int i = 0; i < n; i++) x[i] = std::exp(l0 + i*(l1 - l0)/(n - 1));
+    x[0] = lo;
+    x[n - 1] = hi;
+    return x;
+}
+
+std::vector<double> oneloop_kgrid() { return logspace_ref(ONELOOP_KMIN, ONELOOP_KMAX, ONELOOP_N); }
+
+// ZeldovichPS::InitializeR (ZeldovichPS.cpp:41-53)
+std::vector<double> zeldovich_rgrid()
+{
+    std::vector<double> r(ZEL_NR);
+    const double nc = 0.5*(ZEL_NR + 1), logrmin = -2.0, logrmax = 5.0;
+    const double logrc = 0.5*(logrmin + logrmax), dlogr = (logrmax - logrmin)/ZEL_NR;
+    for (int i = 1; i <= ZEL_NR; i++) r[i - 1] = std::pow(10.0, logrc + (i - nc)*dlogr);
+    return r;
+}
+
+void PTResult::ensure(int ncosmo_, int nk_)
+{
+    ncosmo = ncosmo_;
+    nk = nk_;
+    const size_t c = ncosmo;
+    I.ensure(c*16*nk);
+    J.ensure(c*6*nk);
+    K.ensure(c*13*nk);
+    ML.ensure(c*N_ML*3*nk);
+    oneloop.ensure(c*4*ONELOOP_N);
+    sigmasq_k.ensure(c*nk);
+    scalars.ensure(c*4);
+    X0.ensure(c*ZEL_NR);
+    YY.ensure(c*ZEL_NR);
+}
+
+static const double INV8PI2 = 1.0/(8.0*M_PI*M_PI);
+static const double INV4PI2 = 1.0/(4.0*M_PI*M_PI);
+static const int J_IDS[6] = {0, 1, 2, 3, 4, 6};                    // J00 J01 J02 J10 J11 J20 -> 3m+n
+static const int NONSYM[8] = {KID_F03, KID_F10, KID_F13, KID_F22, KID_F30, KID_F31, KID_K11, KID_K11S};
+static const int ML_KID[N_ML] = {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33};
+
+PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel)
+    : ctx(&c), cfg(q), nk(nk_), with_ml(ml), with_zel(zel)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    PRSD_REQUIRE(nk > 0, "PTPlan: empty k grid");
+    k_interp.assign(k, k + nk);
+    k_1loop = oneloop_kgrid();
+    r_zel = zeldovich_rgrid();
+    const KnotGrid& grid = knot_grid();
+
+    // ---- one-loop tables: I00 I01 I11 I23 I32 I33 (all symmetric: 2 x the v > 0 half)
+    {
+        auto geo = make_geometry(c, k_1loop.data(), ONELOOP_N, 1e5, cfg, grid);
+        std::vector<ColSpec> cols;
+        for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
+        op_1loop.build(c, geo, cols);
+    }
+    // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
+    {
+        auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid);
+        std::vector<ColSpec> cols;
+        for (int id = 0; id < 16; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
+        for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
+        for (int id : NONSYM) cols.push_back({id, -1, id < 16 ? INV8PI2 : 0.5*INV4PI2});
+        op_ik.build(c, geo, cols);
+    }
+    // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
+    if (with_ml) {
+        auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg, grid);
+        std::vector<ColSpec> pos, neg;
+        for (int id : ML_KID) { pos.push_back({id, +1, INV8PI2}); neg.push_back({id, -1, INV8PI2}); }
+        op_ml_pos.build(c, geo, pos);
+        op_ml_neg.build(c, geo, neg);
+    }
+    // ---- 1-D operators
+    {
+        std::vector<LinOutSpec> o;
+        for (int id : {0, 1, 4})
+            for (int i = 0; i < ONELOOP_N; i++) o.push_back({LK_JMN, id, k_1loop[i], 1e-5, 1e5, 1.0});
+        lin_1loop.build(c, o);
+    }
+    {
+        std::vector<LinOutSpec> o;
+        for (int j = 0; j < 6; j++)
+            for (int i = 0; i < nk; i++) o.push_back({LK_JMN, J_IDS[j], k_interp[i], 1e-5, 1e5, 1.0});
+        // sigma_v^2(k) integrates from 1e-5 up to 0.5 k (PowerSpectrum.cpp:60-62)
+        for (int i = 0; i < nk; i++) {
+            // for 0.5 k < 1e-5 the reference integrates "backwards" and returns a negative number
+            const double hi = 0.5*k_interp[i];
+            if (hi >= 1e-5) o.push_back({LK_SIGV, 0, 0.0, 1e-5, hi, 1.0});
+            else            o.push_back({LK_SIGV, 0, 0.0, hi, 1e-5, -1.0});
+        }
+        o.push_back({LK_SIGV, 0, 0.0, 1e-5, 1e2, 1.0});
+        if (with_zel) {
+            for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_XZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
+            for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_YZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
+        }
+        lin_main.build(c, o);
+    }
+    lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}});
+    lin_kurt.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}});
+    d_k1loop.upload(k_1loop, c.stream);
+    d_kinterp.upload(k_interp, c.stream);
+    c.sync();
+    build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+size_t PTPlan::device_bytes() const
+{
+    size_t b = 0;
+    for (const BilinearOp* op : {&op_1loop, &op_ik, &op_ml_pos, &op_ml_neg}) {
+        if (!op->geo) continue;
+        b += op->W.n*sizeof(double);
+    }
+    if (op_1loop.geo) b += op_1loop.geo->bytes();
+    if (op_ik.geo) b += op_ik.geo->bytes();
+    if (op_ml_pos.geo) b += op_ml_pos.geo->bytes();
+    for (const LinearOp* l : {&lin_1loop, &lin_main, &lin_invq2_100, &lin_kurt}) b += l->Omega.n*sizeof(double);
+    return b;
+}
+
+long long PTPlan::nodes_total() const
+{
+    long long n = 0;
+    if (op_1loop.geo) n += op_1loop.geo->n_nodes;
+    if (op_ik.geo) n += op_ik.geo->n_nodes;
+    if (op_ml_pos.geo) n += 2*op_ml_pos.geo->n_nodes;
+    return n;
+}
+
+// ------------------------------------------------------------------ packing
+__global__ void k_oneloop_combine(int ncosmo, const double* __restrict__ op1 /*[c][1000][8]*/,
+                                  const double* __restrict__ lin1 /*[c][3000]*/, const double* __restrict__ plk /*[c][1000]*/,
+                                  const double* __restrict__ k1, double* __restrict__ ol /*[c][4][1000]*/)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (i >= ONELOOP_N) return;
+    const double* a = op1 + ((size_t)c*ONELOOP_N + i)*8;
+    const double* j = lin1 + (size_t)c*3*ONELOOP_N;
+    const double k = k1[i], P = plk[(size_t)c*ONELOOP_N + i];
+    double* o = ol + (size_t)c*4*ONELOOP_N;
+    // OneLoopPS.cpp:56-132: 2 I_ab + 6 k^2 J_ab P_L ; P22bar = I23 + 2/3 I32 + 1/5 I33 (:164-185)
+    o[i]               = 2.0*a[0] + 6.0*k*k*j[i]*P;
+    o[ONELOOP_N + i]   = 2.0*a[1] + 6.0*k*k*j[ONELOOP_N + i]*P;
+    o[2*ONELOOP_N + i] = 2.0*a[2] + 6.0*k*k*j[2*ONELOOP_N + i]*P;
+    o[3*ONELOOP_N + i] = a[3] + (2.0/3.0)*a[4] + (1.0/5.0)*a[5];
+}
+
+__global__ void k_pack_ik(int nk, const double* __restrict__ s /*[c][nk][40]*/, double* __restrict__ I, double* __restrict__ K)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (i >= nk) return;
+    const double* r = s + ((size_t)c*nk + i)*40;
+    double v[29];
+#pragma unroll
+    for (int j = 0; j < 29; j++) v[j] = r[j];
+    v[KID_F03] += r[29]; v[KID_F10] += r[30]; v[KID_F13] += r[31]; v[KID_F22] += r[32];
+    v[KID_F30] += r[33]; v[KID_F31] += r[34]; v[KID_K11] += r[35]; v[KID_K11S] += r[36];
+#pragma unroll
+    for (int j = 0; j < 16; j++) I[((size_t)c*16 + j)*nk + i] = v[j];
+#pragma unroll
+    for (int j = 0; j < 13; j++) K[((size_t)c*13 + j)*nk + i] = v[16 + j];
+}
+
+// rows of the ImnOneLoop contraction: (P_1(q), P_2(r)) =
+//   0 (L,L)  1 (L,dv)  2 (dv,dv)  3 (L,dd)  4 (vv,L)  5 (vv,dd)  6 (L,vv)  7 (vv,vv)
+// columns: h01 h02 h03 h04 f23 f32 f33
+__global__ void k_pack_ml(int nk, const double* __restrict__ sp, const double* __restrict__ sn, double* __restrict__ ML)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (i >= nk) return;
+    auto at = [&](int row, int col) {
+        const size_t idx = (((size_t)c*8 + row)*nk + i)*8 + col;
+        return sp[idx] + sn[idx];
+    };
+    double* o = ML + (size_t)c*N_ML*3*nk;
+    auto put = [&](int m, double lin, double cross, double one) {
+        o[((size_t)m*3 + 0)*nk + i] = lin;
+        o[((size_t)m*3 + 1)*nk + i] = cross;
+        o[((size_t)m*3 + 2)*nk + i] = one;
+    };
+    // ImnOneLoop(Pvv, Pdd): h01, h02  (cross = \int P_L P_2 + \int P_1 P_L, ImnOneLoop.cpp:130-148)
+    put(0, at(0, 0), at(3, 0) + at(4, 0), at(5, 0));
+    put(1, at(0, 1), at(3, 1) + at(4, 1), at(5, 1));
+    // ImnOneLoop(Pdv): h03, h04  (equal spectra: cross = 2 x part1)
+    put(2, at(0, 2), 2.0*at(1, 2), at(2, 2));
+    put(3, at(0, 3), 2.0*at(1, 3), at(2, 3));
+    // ImnOneLoop(Pvv): f23, f32, f33.  The reference evaluates the LINEAR and ONE-LOOP parts of
+    // (m,n) = (3,2) with the f23 kernel (ImnOneLoop.cpp:108-109, 199-200) and only the cross
+    // part with f32 (:160-165); reproduced as is.
+    put(4, at(0, 4), 2.0*at(6, 4), at(7, 4));
+    put(5, at(0, 4), 2.0*at(6, 5), at(7, 4));
+    put(6, at(0, 6), 2.0*at(6, 6), at(7, 6));
+}
+
+__global__ void k_pack_lin(int nk, int nout, int with_zel, const double* __restrict__ s /*[c][nout]*/,
+                           const double* __restrict__ q3, const double* __restrict__ kurt,
+                           double* __restrict__ J, double* __restrict__ sigk, double* __restrict__ scal,
+                           double* __restrict__ X0, double* __restrict__ YY)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
+    const double* r = s + (size_t)c*nout;
+    if (i < 6*nk) J[(size_t)c*6*nk + i] = r[i];
+    if (i < nk) sigk[(size_t)c*nk + i] = r[6*nk + i];
+    if (i == 0) {
+        scal[c*4 + 0] = r[7*nk];
+        scal[c*4 + 1] = kurt ? kurt[c] : 0.0;
+        scal[c*4 + 2] = q3[c];
+        scal[c*4 + 3] = 0.0;
+    }
+    if (with_zel && i < ZEL_NR) {
+        X0[(size_t)c*ZEL_NR + i] = r[7*nk + 1 + i];
+        YY[(size_t)c*ZEL_NR + i] = r[7*nk + 1 + ZEL_NR + i];
+    }
+}
+
+__global__ void k_plin_at(int nspl, const PlinParams* __restrict__ params, const double* __restrict__ spl,
+                          int nq, const double* __restrict__ q, double* __restrict__ out)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
+}
+
+void PTPlan::run(SpectraBatch& sp, PTResult& res)
+{
+    Context& c = *ctx;
+    cudaStream_t s = c.stream;
+    const int nc = sp.ncosmo;
+    res.ensure(nc, nk);
+    const int ntile = (nc + 7)/8;
+
+    // ---- tile maps
+    std::vector<int> slot(ntile*8), rowI(ntile*8), tabL(nc), tabSq(nc), tab22(nc);
+    for (int t = 0; t < ntile; t++)
+        for (int r = 0; r < 8; r++) {
+            slot[t*8 + r] = sp.table_index(std::min(t*8 + r, nc - 1), SP_LIN);
+            rowI[t*8 + r] = r;
+        }
+    for (int i = 0; i < nc; i++) {
+        tabL[i] = sp.table_index(i, SP_LIN);
+        tabSq[i] = sp.table_index(i, SP_LIN_SQ);
+        tab22[i] = sp.table_index(i, SP_P22BAR);
+    }
+    s_slot.upload(slot, s);
+    s_rowA.upload(rowI, s);
+    DevBuf<int> d_tabL, d_tabSq, d_tab22;
+    d_tabL.upload(tabL, s);
+    d_tabSq.upload(tabSq, s);
+    d_tab22.upload(tab22, s);
+
+    // ---- stage A: one-loop tables
+    s_op1.ensure((size_t)ntile*8*ONELOOP_N*8);
+    op_1loop.apply(c, sp.tables.p, s_slot.p, s_rowA.p, s_rowA.p, ntile, s_op1.p);
+    s_lin1.ensure((size_t)nc*3*ONELOOP_N);
+    lin_1loop.apply(c, sp.tables.p, d_tabL.p, nc, s_lin1.p);
+    s_plk.ensure((size_t)nc*ONELOOP_N);
+    {
+        dim3 g((ONELOOP_N + 255)/256, nc);
+        k_plin_at<<<g, 256, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, ONELOOP_N, d_k1loop.p, s_plk.p);
+        k_oneloop_combine<<<g, 256, 0, s>>>(nc, s_op1.p, s_lin1.p, s_plk.p, d_k1loop.p, res.oneloop.p);
+        PRSD_CUDA(cudaGetLastError());
+        c.launches += 2;
+    }
+    sp.set_oneloop_tables(res.oneloop.p);
+
+    // ---- stage B: I_mn, K_mn
+    s_ik.ensure((size_t)ntile*8*nk*40);
+    op_ik.apply(c, sp.tables.p, s_slot.p, s_rowA.p, s_rowA.p, ntile, s_ik.p);
+    {
+        dim3 g((nk + 127)/128, nc);
+        k_pack_ik<<<g, 128, 0, s>>>(nk, s_ik.p, res.I.p, res.K.p);
+        PRSD_CUDA(cudaGetLastError());
+        c.launches++;
+    }
+    // ---- stage B: ImnOneLoop (one tile = one cosmology, rows = spectrum pairs)
+    if (with_ml) {
+        std::vector<int> mslot(nc*8), mA(nc*8), mB(nc*8);
+        const int a_of[8] = {0, 0, 2, 0, 3, 3, 0, 3};   // slot of P_1: 0 L, 1 dd, 2 dv, 3 vv
+        const int b_of[8] = {0, 2, 2, 1, 0, 1, 3, 3};   // slot of P_2
+        for (int i = 0; i < nc; i++) {
+            const int kinds[8] = {SP_LIN, SP_DD1, SP_DV1, SP_VV1, SP_LIN, SP_LIN, SP_LIN, SP_LIN};
+            for (int r = 0; r < 8; r++) {
+                mslot[i*8 + r] = sp.table_index(i, kinds[r]);
+                mA[i*8 + r] = a_of[r];
+                mB[i*8 + r] = b_of[r];
+            }
+        }
+        DevBuf<int> dslot, dA, dB;
+        dslot.upload(mslot, s);
+        dA.upload(mA, s);
+        dB.upload(mB, s);
+        s_mlp.ensure((size_t)nc*8*nk*8);
+        s_mln.ensure((size_t)nc*8*nk*8);
+        // v > 0 half: a = q, b = r -> (A, B) = (P_1, P_2); v < 0 half: a = r, b = q -> swapped
+        op_ml_pos.apply(c, sp.tables.p, dslot.p, dA.p, dB.p, nc, s_mlp.p);
+        op_ml_neg.apply(c, sp.tables.p, dslot.p, dB.p, dA.p, nc, s_mln.p);
+        dim3 g((nk + 127)/128, nc);
+        k_pack_ml<<<g, 128, 0, s>>>(nk, s_mlp.p, s_mln.p, res.ML.p);
+        PRSD_CUDA(cudaGetLastError());
+        c.launches++;
+        c.sync();    // the index buffers above are locals
+    }
+    // ---- 1-D functionals
+    s_linmain.ensure((size_t)nc*lin_main.nout);
+    lin_main.apply(c, sp.tables.p, d_tabL.p, nc, s_linmain.p);
+    s_small.ensure((size_t)2*nc);
+    lin_invq2_100.apply(c, sp.tables.p, d_tabSq.p, nc, s_small.p);
+    lin_kurt.apply(c, sp.tables.p, d_tab22.p, nc, s_small.p + nc);
+    {
+        const int nmax = std::max(6*nk, ZEL_NR);
+        dim3 g((nmax + 127)/128, nc);
+        k_pack_lin<<<g, 128, 0, s>>>(nk, lin_main.nout, with_zel ? 1 : 0, s_linmain.p, s_small.p, s_small.p + nc,
+                                    res.J.p, res.sigmasq_k.p, res.scalars.p, res.X0.p, res.YY.p);
+        PRSD_CUDA(cudaGetLastError());
+        c.launches++;
+    }
+    c.sync();
+}
+
+} // namespace prsd

@@ -1,0 +1,63 @@
+// plan.cuh -- the cosmology-independent "plan" of the PT stage and its per-batch results.
+//
+// A plan owns, for a given k_interp grid (rsd: 250 log-spaced k in [5e-6, 1],
+// pyRSD/rsd/power/dm/power_dm.py:22) and the reference's fixed one-loop grid
+// (logspace(1e-5, 10, 1000), OneLoopPS.cpp:11-13) and Zel'dovich r grid (ZeldovichPS.cpp:41-53):
+//   * the 2-D quadrature operators (bilinear.cuh) for I_mn, K_mn, the one-loop tables and
+//     the ImnOneLoop convolutions;
+//   * the 1-D operators (linear.cuh) for J_mn, sigma_v^2, sigma_v^2(k), X(r), Y(r), Q3,
+//     velocity kurtosis.
+// run() evaluates everything the reference's PTIntegralsMixin (rsd/pt_integrals.py:42-450)
+// tabulates, for a whole batch of cosmologies, unnormalised (z = 0) exactly as there.
+#pragma once
+#include "bilinear.cuh"
+#include "linear.cuh"
+#include "spectra.cuh"
+
+namespace prsd {
+
+static const int ZEL_NR = 1024;     // NUM_PTS of ZeldovichPS.cpp:7
+static const int N_ML = 7;          // Ivvdd_h01, Ivvdd_h02, Idvdv_h03, Idvdv_h04, Ivvvv_f23, f32, f33
+
+std::vector<double> oneloop_kgrid();
+std::vector<double> zeldovich_rgrid();
+
+struct PTResult {
+    int ncosmo = 0, nk = 0;
+    // all device buffers, layouts [cosmo][...]
+    DevBuf<double> I;          // [c][16][nk]   I_mn, index 4 m + n
+    DevBuf<double> J;          // [c][6][nk]    order J00 J01 J02 J10 J11 J20
+    DevBuf<double> K;          // [c][13][nk]   order K00 K01 K00s K01s K02s K10 K11 K10s K11s K20_a K20_b K20s_a K20s_b
+    DevBuf<double> ML;         // [c][7][3][nk] (linear, cross, one-loop) of the N_ML ImnOneLoop integrals
+    DevBuf<double> oneloop;    // [c][4][1000]  Pdd, Pdv, Pvv, P22bar one-loop tables
+    DevBuf<double> sigmasq_k;  // [c][nk]
+    DevBuf<double> scalars;    // [c][4]  sigma_v^2, velocity kurtosis, Q3/k^4, (unused)
+    DevBuf<double> X0;         // [c][1024]  X_Zel(r)
+    DevBuf<double> YY;         // [c][1024]  Y_Zel(r)
+    void ensure(int ncosmo_, int nk_);
+};
+
+struct PTPlan {
+    Context* ctx;
+    QuadConfig cfg;
+    std::vector<double> k_interp, k_1loop, r_zel;
+    int nk = 0;
+    bool with_ml = true, with_zel = true;
+    BilinearOp op_1loop, op_ik, op_ml_pos, op_ml_neg;
+    LinearOp lin_1loop;        // J00, J01, J11 on k_1loop                      (P_L table)
+    LinearOp lin_main;         // J x6 (nk each), sigmasq_k (nk), sigma_v^2, X (1024), Y (1024)   (P_L table)
+    LinearOp lin_invq2_100;    // \int S/q^2 dq over [1e-5, 100] x 1/(10 pi^2)  (P_L^2 table)  -> Q3 / k^4
+    LinearOp lin_kurt;         // 0.25/(2 pi^2) \int S/q^2 dq over [1e-5, 10]   (P22bar table)
+    DevBuf<double> d_k1loop, d_kinterp;
+    // scratch
+    DevBuf<double> s_op1, s_lin1, s_ik, s_mlp, s_mln, s_linmain, s_small, s_ol, s_plk;
+    DevBuf<int> s_slot, s_rowA, s_rowB, s_tabidx;
+    double build_seconds = 0.0;
+
+    PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel);
+    void run(SpectraBatch& sp, PTResult& res);
+    size_t device_bytes() const;
+    long long nodes_total() const;
+};
+
+} // namespace prsd

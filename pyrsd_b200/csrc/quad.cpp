@@ -1,0 +1,198 @@
+// quad.cpp -- host-side quadrature geometry (see quad.h).
+#include "quad.h"
+#include "pt_math.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace prsd {
+
+// ------------------------------------------------------------------ knots
+KnotGrid make_knot_grid()
+{
+    // (lo, hi, target spacing in ln q).  The BAO zone must resolve the wiggles of P_L with a
+    // cubic read (<~ 4e-7), the smooth zones only power laws.
+    struct Z { double lo, hi, h; };
+    const Z zs[] = {
+        {1e-8, 1e-5, 0.03}, {1e-5, 5e-3, 0.02}, {5e-3, 1.0, 0.004},
+        {1.0, 10.0, 0.02},  {10.0, 100.0, 0.02}, {100.0, 1.2e5, 0.03},
+    };
+    KnotGrid g;
+    for (const Z& z : zs) {
+        const double L = std::log(z.hi/z.lo);
+        int n = (int)std::ceil(L/z.h - 1e-9);
+        if (n < 3) n = 3;
+        KnotZone kz;
+        kz.x0 = std::log(z.lo);
+        kz.h = L/n;
+        kz.n = n;
+        kz.start = (int)g.x.size();
+        for (int i = 0; i <= n; i++) g.x.push_back(kz.x0 + kz.h*i);
+        g.x.back() = std::log(z.hi);
+        g.zones.push_back(kz);
+    }
+    return g;
+}
+
+int KnotGrid::stencil_start(int z, int c) const
+{
+    const KnotZone& kz = zones[z];
+    int j = c - 1;
+    if (j < 0) j = 0;
+    if (j > kz.n - 3) j = kz.n - 3;
+    return kz.start + j;
+}
+
+void KnotGrid::locate(double lnq, int& j0, double& s) const
+{
+    int z = 0;
+    const int nz = (int)zones.size();
+    while (z < nz - 1 && lnq >= zones[z + 1].x0) ++z;
+    const KnotZone& kz = zones[z];
+    int c = (int)std::floor((lnq - kz.x0)/kz.h);
+    if (c < 0) c = 0;
+    if (c > kz.n - 1) c = kz.n - 1;
+    j0 = stencil_start(z, c);
+    s = (lnq - kz.x0)/kz.h - (double)(j0 - kz.start);
+}
+
+// ------------------------------------------------------- Gauss-Legendre
+void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w)
+{
+    x.assign(n, 0.0);
+    w.assign(n, 0.0);
+    for (int i = 0; i < (n + 1)/2; i++) {
+        double z = std::cos(M_PI*(i + 0.75)/(n + 0.5));
+        double pp = 1.0;
+        for (int it = 0; it < 100; it++) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 1; j <= n; j++) {
+                double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0*j - 1.0)*z*p2 - (j - 1.0)*p3)/j;
+            }
+            pp = n*(z*p1 - p2)/(z*z - 1.0);
+            double dz = p1/pp;
+            z -= dz;
+            if (std::fabs(dz) < 1e-16) break;
+        }
+        x[i] = -z;
+        x[n - 1 - i] = z;
+        w[i] = w[n - 1 - i] = 2.0/((1.0 - z*z)*pp*pp);
+    }
+}
+
+// --------------------------------------------------------------- panels
+static double local_width(double q, const QuadConfig& c)
+{
+    double w = c.ln_far;
+    if (q >= c.mid_lo && q <= c.mid_hi) w = std::min(w, c.ln_mid);
+    if (q >= c.bao_lo && q <= c.bao_hi) w = std::min(w, c.bao_dq/q);
+    return w;
+}
+
+std::vector<double> panel_edges(double lo, double hi, const std::vector<double>& extra,
+                                const QuadConfig& c)
+{
+    std::vector<double> brk;
+    brk.push_back(lo);
+    brk.push_back(hi);
+    auto add = [&](double e) { if (e > lo*(1 + 1e-12) && e < hi*(1 - 1e-12)) brk.push_back(e); };
+    for (double e : extra) add(e);
+    add(c.mid_lo); add(c.mid_hi); add(c.bao_lo); add(c.bao_hi);
+    std::sort(brk.begin(), brk.end());
+    brk.erase(std::unique(brk.begin(), brk.end()), brk.end());
+
+    std::vector<double> out;
+    out.push_back(brk[0]);
+    std::vector<double> xs;
+    for (size_t i = 0; i + 1 < brk.size(); i++) {
+        const double p0 = brk[i], p1 = brk[i + 1];
+        const double x0 = std::log(p0), x1 = std::log(p1);
+        if (!(x1 > x0)) continue;
+        // march with the local width, then stretch the marks to land exactly on p1
+        xs.clear();
+        xs.push_back(x0);
+        while (xs.back() < x1 - 1e-12) {
+            double q = std::min(std::exp(xs.back())*1.0000001, p1);
+            xs.push_back(xs.back() + local_width(q, c));
+        }
+        const double scale = (x1 - x0)/(xs.back() - x0);
+        for (size_t j = 1; j < xs.size(); j++) {
+            double e = (j + 1 == xs.size()) ? p1 : std::exp(x0 + (xs[j] - x0)*scale);
+            out.push_back(e);
+        }
+    }
+    return out;
+}
+
+// ----------------------------------------------------------- 2-D nodes
+void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cfg,
+                      const KnotGrid& grid, HalfNodes& H)
+{
+    std::vector<double> xo, wo, xi, wi;
+    gauss_legendre(cfg.n_outer, xo, wo);
+    gauss_legendre(cfg.n_inner, xi, wi);
+    const std::vector<double> zone_breaks = {1e-5, 10.0, 100.0};
+
+    H = HalfNodes();
+    H.k.assign(k, k + nk);
+    H.outer_off.push_back(0);
+    H.node_off.push_back(0);
+    std::vector<double> extra;
+    double coef[4];
+    for (int ik = 0; ik < nk; ik++) {
+        const double kk = k[ik];
+        const double umax = 2.0*qmax/kk;
+        // a = min(q, r) <= (q + r)/2 <= qmax
+        extra = zone_breaks;
+        extra.push_back(0.5*kk);
+        extra.push_back(kk);
+        extra.push_back(2.0*kk);
+        std::vector<double> oe = panel_edges(cfg.qmin, qmax, extra, cfg);
+        for (size_t p = 0; p + 1 < oe.size(); p++) {
+            const double l0 = std::log(oe[p]), l1 = std::log(oe[p + 1]);
+            const double hw = 0.5*(l1 - l0), mid = 0.5*(l1 + l0);
+            for (int io = 0; io < cfg.n_outer; io++) {
+                const double x = mid + hw*xo[io];
+                const double wx = hw*wo[io];
+                const double a = std::exp(x);
+                double blo, bhi;
+                if (a < 0.5*kk) { blo = kk - a; bhi = kk + a; }
+                else            { blo = a;      bhi = a + kk; }
+                // u = (a+b)/k <= umax  ->  b <= k umax - a
+                const double bcap = kk*umax - a;
+                if (bcap <= blo) continue;
+                const int32_t oid = (int32_t)H.a.size();
+                int j0; double s;
+                grid.locate(x, j0, s);
+                lagrange4(s, coef);
+                H.a.push_back(a);
+                H.a_j0.push_back(j0);
+                H.a_coef.insert(H.a_coef.end(), coef, coef + 4);
+                H.o_kid.push_back(ik);
+                std::vector<double> ie = panel_edges(blo, bhi, zone_breaks, cfg);
+                for (size_t pb = 0; pb + 1 < ie.size(); pb++) {
+                    const double b0 = ie[pb], b1 = ie[pb + 1];
+                    const double hb = 0.5*(b1 - b0), mb = 0.5*(b1 + b0);
+                    for (int ii = 0; ii < cfg.n_inner; ii++) {
+                        const double b = mb + hb*xi[ii];
+                        double w = wx*(hb*wi[ii]/kk)*(2.0/kk)*a*a*b;
+                        if (b > bcap) w = 0.0;
+                        grid.locate(std::log(b), j0, s);
+                        lagrange4(s, coef);
+                        H.b.push_back(b);
+                        H.wgt.push_back(w);
+                        H.b_j0.push_back(j0);
+                        H.b_coef.insert(H.b_coef.end(), coef, coef + 4);
+                        H.n_outer.push_back(oid);
+                    }
+                }
+            }
+        }
+        H.outer_off.push_back((int64_t)H.a.size());
+        H.node_off.push_back((int64_t)H.b.size());
+    }
+}
+
+} // namespace prsd

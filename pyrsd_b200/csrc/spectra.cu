@@ -1,0 +1,293 @@
+// spectra.cu -- device-resident spectra tables (see spectra.cuh).
+#include "spectra.cuh"
+
+#include <cmath>
+#include <mutex>
+
+namespace prsd {
+
+const KnotGrid& knot_grid()
+{
+    static KnotGrid g = make_knot_grid();
+    if (g.size() != TAB_M) throw Error(ERR_INTERNAL, strprintf("knot grid has %d knots, TAB_M = %d", g.size(), TAB_M));
+    return g;
+}
+
+const double* knot_grid_dev(Context& ctx)
+{
+    static std::mutex mu;
+    static std::vector<std::pair<int, double*>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : cache) if (e.first == ctx.device) return e.second;
+    double* d = nullptr;
+    PRSD_CUDA(cudaMalloc((void**)&d, TAB_M*sizeof(double)));
+    PRSD_CUDA(cudaMemcpy(d, knot_grid().x.data(), TAB_M*sizeof(double), cudaMemcpyHostToDevice));
+    cache.push_back({ctx.device, d});
+    return d;
+}
+
+// ------------------------------------------------------------ spline build
+// One CTA per spline.  The tridiagonal sweeps are inherently serial (thread 0, operands in
+// shared memory); set-up and the final polynomial coefficients are done by the whole CTA.
+// Same arithmetic as cubic_spline_build() in pt_math.cuh (netlib fmm/spline.f).
+__global__ void k_spline_build(int n, const double* __restrict__ X, int x_stride,
+                               const double* __restrict__ Y, double* __restrict__ out)
+{
+    extern __shared__ double sm[];
+    double* x = sm;
+    double* y = sm + n;
+    double* b = sm + 2*n;
+    double* c = sm + 3*n;
+    double* d = sm + 4*n;
+    const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const double* Xs = X + (size_t)s*x_stride;
+    const double* Ys = Y + (size_t)s*n;
+    for (int i = tid; i < n; i += nt) { x[i] = Xs[i]; y[i] = Ys[i]; }
+    __syncthreads();
+    for (int i = tid; i < n - 1; i += nt) d[i] = x[i + 1] - x[i];
+    __syncthreads();
+    // right-hand side: second differences of the slopes
+    for (int i = tid; i < n; i += nt) {
+        if (i >= 1 && i <= n - 2) {
+            b[i] = 2.0*(d[i - 1] + d[i]);
+            c[i] = (y[i + 1] - y[i])/d[i] - (y[i] - y[i - 1])/d[i - 1];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        b[0] = -d[0];
+        b[n - 1] = -d[n - 2];
+        double c0 = 0.0, cn = 0.0;
+        if (n > 3) {
+            c0 = c[2]/(x[3] - x[1]) - c[1]/(x[2] - x[0]);
+            cn = c[n - 2]/(x[n - 1] - x[n - 3]) - c[n - 3]/(x[n - 2] - x[n - 4]);
+            c0 = c0*d[0]*d[0]/(x[3] - x[0]);
+            cn = -cn*d[n - 2]*d[n - 2]/(x[n - 1] - x[n - 4]);
+        }
+        c[0] = c0;
+        c[n - 1] = cn;
+        // forward elimination
+        double bp = b[0], cp = c[0];
+        for (int i = 1; i < n; i++) {
+            const double dm = d[i - 1];
+            const double t = dm/bp;
+            bp = b[i] - t*dm;
+            cp = c[i] - t*cp;
+            b[i] = bp;
+            c[i] = cp;
+        }
+        // back substitution
+        double cn1 = c[n - 1]/b[n - 1];
+        c[n - 1] = cn1;
+        for (int i = n - 2; i >= 0; i--) {
+            cn1 = (c[i] - d[i]*cn1)/b[i];
+            c[i] = cn1;
+        }
+    }
+    __syncthreads();
+    double* o = out + (size_t)s*5*n;
+    for (int i = tid; i < n; i += nt) {
+        double bi, ci, di;
+        if (i < n - 1) {
+            bi = (y[i + 1] - y[i])/d[i] - d[i]*(c[i + 1] + 2.0*c[i]);
+            di = (c[i + 1] - c[i])/d[i];
+        } else {
+            bi = (y[n - 1] - y[n - 2])/d[n - 2] + d[n - 2]*(c[n - 2] + 2.0*c[n - 1]);
+            di = (c[n - 1] - c[n - 2])/d[n - 2];
+        }
+        ci = 3.0*c[i];
+        o[i] = x[i];
+        o[n + i] = y[i];
+        o[2*n + i] = bi;
+        o[3*n + i] = ci;
+        o[4*n + i] = di;
+    }
+}
+
+void spline_build_batched(Context& ctx, int nspline, int n, const double* dX, int x_stride,
+                          const double* dY, double* dspl)
+{
+    PRSD_REQUIRE(n >= 4 && n <= 4096, "spline_build_batched: n = %d out of range [4, 4096]", n);
+    const size_t smem = (size_t)5*n*sizeof(double);
+    if (smem > 48*1024)
+        PRSD_CUDA(cudaFuncSetAttribute(k_spline_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_spline_build<<<nspline, 128, smem, ctx.stream>>>(n, dX, x_stride, dY, dspl);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
+// ------------------------------------------------------------ table builds
+__global__ void k_plin_table(int nspl, const PlinParams* __restrict__ params, const double* __restrict__ spl,
+                             const double* __restrict__ lnq, double* __restrict__ tables)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= TAB_MPAD) return;
+    double* lin = tables + (size_t)(c*SP_NKIND + SP_LIN)*TAB_MPAD;
+    double* sq = tables + (size_t)(c*SP_NKIND + SP_LIN_SQ)*TAB_MPAD;
+    double v = 0.0;
+    if (j < TAB_M) v = plin_eval(params[c], spl + (size_t)c*5*nspl, exp(lnq[j]));
+    lin[j] = v;
+    sq[j] = v*v;
+}
+
+__global__ void k_plin_eval(int nspl, const PlinParams* __restrict__ params, const double* __restrict__ spl,
+                            int nq, const double* __restrict__ q, double* __restrict__ out)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
+}
+
+__global__ void k_scale_linear(const double* __restrict__ fac, PlinParams* __restrict__ params, double* __restrict__ tables)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    const double f = fac[c];
+    if (j == 0) params[c].amp *= f;
+    if (j >= TAB_MPAD) return;
+    tables[(size_t)(c*SP_NKIND + SP_LIN)*TAB_MPAD + j] *= f;
+    tables[(size_t)(c*SP_NKIND + SP_LIN_SQ)*TAB_MPAD + j] *= f*f;
+}
+
+SpectraBatch::SpectraBatch(Context& c, int ncosmo_, int nspl_, const double* k, const double* T, const double* pars)
+    : ctx(&c), ncosmo(ncosmo_), nspl(nspl_)
+{
+    PRSD_REQUIRE(ncosmo > 0, "SpectraBatch: ncosmo must be positive");
+    PRSD_REQUIRE(nspl >= 4 && nspl <= 4096, "SpectraBatch: %d transfer-function samples unsupported", nspl);
+    h_params.resize(ncosmo);
+    for (int i = 0; i < ncosmo; i++) {
+        const double* kk = k + (size_t)i*nspl;
+        const double* TT = T + (size_t)i*nspl;
+        const double* p = pars + (size_t)i*8;
+        for (int j = 0; j < nspl; j++) {
+            PRSD_REQUIRE(kk[j] > 0 && (j == 0 || kk[j] > kk[j - 1]), "SpectraBatch: k must be positive and increasing (cosmology %d, sample %d)", i, j);
+            PRSD_REQUIRE(std::isfinite(TT[j]), "SpectraBatch: non-finite T(k) (cosmology %d, sample %d)", i, j);
+        }
+        // pars = {n_s, amplitude, h, Omega0_m, Omega0_b, T_cmb, -, -}
+        plin_params_init(h_params[i], nspl, kk, TT, p[0], p[1], p[2], p[3], p[4], p[5]);
+    }
+    cudaStream_t s = ctx->stream;
+    params.upload(h_params, s);
+    DevBuf<double> dk, dT;
+    dk.upload(k, (size_t)ncosmo*nspl, s);
+    dT.upload(T, (size_t)ncosmo*nspl, s);
+    spl.alloc((size_t)ncosmo*5*nspl);
+    spline_build_batched(*ctx, ncosmo, nspl, dk.p, nspl, dT.p, spl.p);
+    tables.alloc((size_t)ncosmo*SP_NKIND*TAB_MPAD);
+    tables.zero(s);
+    dim3 grid((TAB_MPAD + 255)/256, ncosmo);
+    k_plin_table<<<grid, 256, 0, s>>>(nspl, params.p, spl.p, knot_grid_dev(*ctx), tables.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->sync();
+}
+
+void SpectraBatch::rescale_linear(const double* fac_host)
+{
+    DevBuf<double> f;
+    f.upload(fac_host, ncosmo, ctx->stream);
+    dim3 grid((TAB_MPAD + 255)/256, ncosmo);
+    k_scale_linear<<<grid, 256, 0, ctx->stream>>>(f.p, params.p, tables.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx->launches++;
+    for (int i = 0; i < ncosmo; i++) h_params[i].amp *= fac_host[i];
+    ctx->sync();
+}
+
+void SpectraBatch::eval_linear(int nq, const double* q_host, double* out_host)
+{
+    if (nq <= 0) return;
+    DevBuf<double> q, o((size_t)ncosmo*nq);
+    q.upload(q_host, nq, ctx->stream);
+    dim3 grid((nq + 255)/256, ncosmo);
+    k_plin_eval<<<grid, 256, 0, ctx->stream>>>(nspl, params.p, spl.p, nq, q.p, o.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx->launches++;
+    o.download(out_host, (size_t)ncosmo*nq, ctx->stream);
+    ctx->sync();
+}
+
+// --------------------------------------------------------- one-loop spectra
+// OneLoopPS::Evaluate returns the spline inside [KMIN, KMAX] and 0 outside
+// (OneLoopPS.cpp:28-33); the tables keep exactly that (zone edges sit on 1e-5 and 10).
+__global__ void k_oneloop_tabulate(const double* __restrict__ ospl, const double* __restrict__ lnq,
+                                   double lnk0, double inv_dlnk, int jlo, int jhi, double* __restrict__ tables)
+{
+    const int c = blockIdx.y, which = blockIdx.z;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= TAB_MPAD) return;
+    double v = 0.0;
+    if (j >= jlo && j <= jhi) {     // knots of the zones inside [KMIN, KMAX]
+        const double q = exp(lnq[j]);
+        const double* s = ospl + (size_t)(c*4 + which)*5*ONELOOP_N;
+        // knots that coincide with the hard limits may differ from them by an ulp
+        double qq = q;
+        if (fabs(q - ONELOOP_KMIN) < 1e-12*ONELOOP_KMIN) qq = ONELOOP_KMIN;
+        if (fabs(q - ONELOOP_KMAX) < 1e-12*ONELOOP_KMAX) qq = ONELOOP_KMAX;
+        v = cubic_spline_eval_log(ONELOOP_N, s, lnk0, inv_dlnk, qq);
+    }
+    tables[(size_t)(c*SP_NKIND + SP_DD1 + which)*TAB_MPAD + j] = v;
+}
+
+__global__ void k_oneloop_eval(const double* __restrict__ ospl, int nspl, const PlinParams* __restrict__ params,
+                               const double* __restrict__ spl, int which, int full, double lnk0, double inv_dlnk,
+                               int nq, const double* __restrict__ q, double* __restrict__ out)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    const double k = q[j];
+    const double* s = ospl + (size_t)(c*4 + which)*5*ONELOOP_N;
+    double v = (k < ONELOOP_KMIN || k > ONELOOP_KMAX) ? 0.0 : cubic_spline_eval_log(ONELOOP_N, s, lnk0, inv_dlnk, k);
+    if (full) {
+        // OneLoopPS::EvaluateFull (OneLoopPS.cpp:21-26); P22bar has no linear part (:150-155)
+        if (k > ONELOOP_KMAX) v = 0.0;
+        else if (which != 3) v += plin_eval(params[c], spl + (size_t)c*5*nspl, k);
+    }
+    out[(size_t)c*nq + j] = v;
+}
+
+std::vector<double> oneloop_kgrid();   // defined in plan.cu
+
+void SpectraBatch::set_oneloop_tables(const double* d_tables)
+{
+    static DevBuf<double> dk;    // shared abscissae
+    static int dk_dev = -1;
+    if (dk_dev != ctx->device) {
+        dk.upload(oneloop_kgrid(), ctx->stream);
+        dk_dev = ctx->device;
+    }
+    oneloop_spl.ensure((size_t)ncosmo*4*5*ONELOOP_N);
+    spline_build_batched(*ctx, ncosmo*4, ONELOOP_N, dk.p, 0, d_tables, oneloop_spl.p);
+    const double lnk0 = std::log(ONELOOP_KMIN);
+    const double inv = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
+    // zones 1..3 of the knot grid span [1e-5, 10] exactly (quad.cpp make_knot_grid)
+    const KnotGrid& kg = knot_grid();
+    const int jlo = kg.zones[1].start, jhi = kg.zones[3].start + kg.zones[3].n;
+    dim3 grid((TAB_MPAD + 255)/256, ncosmo, 4);
+    k_oneloop_tabulate<<<grid, 256, 0, ctx->stream>>>(oneloop_spl.p, knot_grid_dev(*ctx), lnk0, inv, jlo, jhi, tables.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx->launches++;
+    have_oneloop = true;
+}
+
+void SpectraBatch::eval_oneloop(int which, bool full, int nq, const double* q_host, double* out_host)
+{
+    PRSD_REQUIRE(have_oneloop, "one-loop tables have not been computed for this batch");
+    PRSD_REQUIRE(which >= 0 && which < 4, "eval_oneloop: invalid spectrum %d", which);
+    if (nq <= 0) return;
+    DevBuf<double> q, o((size_t)ncosmo*nq);
+    q.upload(q_host, nq, ctx->stream);
+    const double lnk0 = std::log(ONELOOP_KMIN);
+    const double inv = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
+    dim3 grid((nq + 255)/256, ncosmo);
+    k_oneloop_eval<<<grid, 256, 0, ctx->stream>>>(oneloop_spl.p, nspl, params.p, spl.p, which, full ? 1 : 0, lnk0, inv, nq, q.p, o.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx->launches++;
+    o.download(out_host, (size_t)ncosmo*nq, ctx->stream);
+    ctx->sync();
+}
+
+} // namespace prsd
