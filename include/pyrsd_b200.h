@@ -29,6 +29,7 @@ typedef struct prsd_ctx prsd_ctx;
 typedef struct prsd_spectra prsd_spectra;
 typedef struct prsd_plan prsd_plan;
 typedef struct prsd_result prsd_result;
+typedef struct prsd_galaxy prsd_galaxy;
 
 const char* prsd_last_error(void);
 int prsd_version(void);
@@ -102,6 +103,63 @@ int prsd_result_destroy(prsd_result* res);
  *       4 one-loop tables [c][4][1000], 5 sigmasq_k [c][nk], 6 scalars [c][4] = {sigma_v^2,
  *       velocity kurtosis, Q3/k^4, 0}, 7 X_Zel [c][1024], 8 Y_Zel [c][1024] */
 int prsd_result_get(prsd_result* res, int what, double* out, long long n_expected);
+
+/* ---- FFTLog: FortranFFTLog(N, dlnr, mu, q, kr, kropt).Transform(a, dir = 1)
+ *      [FortranFFTLog.cpp:10-33, fftlog.f:233-784]; batch of sequences, kr_out = KR() */
+int prsd_fftlog(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
+                const double* a /*[batch][N]*/, double* out /*[batch][N]*/, double* kr_out);
+/* same with DEVICE pointers (asynchronous on the context's stream) */
+int prsd_fftlog_device(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
+                       const double* d_in, double* d_out, double* kr_out);
+/* ComputeXiLM(l, m, k, pk, r, smoothing, FFTLOG) x scale  [CorrelationFunction.cpp:56-90];
+ * pk_to_xi = (-1)^(l/2) ComputeXiLM(l, 2, ...), xi_to_pk = (-1)^(l/2) 8 pi^3 ComputeXiLM(l, 2, r, xi, k) (:127-141) */
+int prsd_compute_xilm(prsd_ctx* ctx, int batch, int l, int m, int nk, const double* k /*[nk]*/,
+                      const double* pk /*[batch][nk]*/, int nr, const double* r, double smoothing, double scale,
+                      double* out /*[batch][nr]*/);
+/* ComputeXiLM_fftlog(l, m, k, pk, r, xi, q, smoothing)  [CorrelationFunction.cpp:23-54] */
+int prsd_compute_xilm_fftlog(prsd_ctx* ctx, int batch, int l, int m, int N, const double* k, const double* pk,
+                             double q, double smoothing, double* r_out /*[N]*/, double* xi_out /*[batch][N]*/);
+
+/* ---- Zel'dovich spectra: ZeldovichP00/P01/P11(ZeldovichPS state)(k)  [ZeldovichPS.i:5-71,
+ *      ZeldovichPS.cpp:112-300].  Rows = (cosmology) states: X0, XX, YY [nrow][1024] (XX may be NULL:
+ *      X0 + 2 sigma^2), sigmasq [nrow]; ratio [nrow] (may be NULL) = (sigma8_new/sigma8_old)^2 of
+ *      SetSigma8AtZ; lowk != 0 enables the low-k SPT forms below k0_low and then needs plin [nrow][nk]
+ *      (P_L at the new sigma8) and q3 [nrow] (Q3_Zel(k)/k^4 at the OLD sigma8).
+ *      out [nrow][3][nk] = P00, P01, P11. */
+int prsd_zeldovich(prsd_ctx* ctx, int nrow, const double* X0, const double* XX, const double* YY,
+                   const double* sigmasq, const double* ratio, int lowk, double k0_low, const double* plin,
+                   const double* q3, int nk, const double* k, double* out);
+
+/* ---- GalaxySpectrum.power(k, mu)  [rsd/power/gal/power_gal.py:404-425 and everything below it]
+ * cfg64 (NULL = defaults, see prsd_galaxy_config_default):
+ *   [0] max_mu  [1] fog_model (0 modified_lorentzian, 1 lorentzian, 2 gaussian)
+ *   [2..7] use_P00/P01/P11/Pdv/Pvv/Phm_model  [8] use_tidal_bias  [9] use_so_correction  [10] k0_low
+ *   [16..25] HZPT P00/P01 parameters, [26..34] HZPT P11, [35..54] HZPT Phm
+ * kmodel: the model's spline grid self.k (numpy.logspace(log10 kmin, log10 kmax, Nk));
+ * k_interp: the PT interpolation grid of the plan.
+ * Walker parameters par [nw][48]:
+ *   0 sigma8_z, 1 f, 2 alpha_par, 3 alpha_perp, 4 alpha_drag, 5..8 b1_cA b1_cB b1_sA b1_sB, 9 fs, 10 fcB,
+ *   11 fsB, 12 sigma_c, 13 sigma_sA, 14 sigma_sB, 15 NcBs, 16 NsBsB, 17 f_so, 18 sigma_so,
+ *   19 sigma_v (<= 0: sigma_lin), 20 D(z), 21 sigma8 (cosmo.sigma8()),
+ *   22 + 4 kind + bias: nonlinear biases, kind = b2_00_a, b2_00_b, b2_00_c, b2_00_d, b2_01_a, b2_01_b
+ *   evaluated at the four linear biases (host inputs: Gaussian-process fits in the reference).
+ * stoch [nw][10][20]: stochasticity Lambda(k) of the 10 (b1, b1_bar) pairs on 20 log-spaced k between
+ *   the ends of kmodel (power_biased.py:342-366), pair order cAcA cAcB cBcB cAsA cAsB cBsA cBsB sAsA sAsB sBsB.
+ * cmap [nw] (NULL = identity): cosmology (row of sp / res) each walker uses.
+ * k, mu [npts] paired observed coordinates; out [nw][npts]. */
+int prsd_galaxy_config_default(double* cfg64);
+int prsd_galaxy_create(prsd_ctx* ctx, const double* cfg64, int nkm, const double* kmodel, int nk_interp,
+                       const double* k_interp, prsd_galaxy** out);
+int prsd_galaxy_destroy(prsd_galaxy* g);
+int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
+                      const double* par, const double* stoch, int npts, const double* k, const double* mu,
+                      double* out);
+/* k, mu, out are DEVICE pointers; returns after the kernels completed */
+int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
+                             const double* par, const double* stoch, int npts, const double* d_k,
+                             const double* d_mu, double* d_out);
+/* spline knots of P[mu^0], P[mu^2], P[mu^4], P[mu^6] of the last call: out [nw][10][4][nkm] */
+int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
 
 #ifdef __cplusplus
 }

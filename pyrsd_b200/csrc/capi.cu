@@ -1,6 +1,8 @@
 // capi.cu -- extern "C" entry points declared in include/pyrsd_b200.h.
 #include "../../include/pyrsd_b200.h"
 #include "plan.cuh"
+#include "galaxy.cuh"
+#include "xilm.cuh"
 
 #include <cstring>
 #include <list>
@@ -12,6 +14,12 @@ struct prsd_ctx { Context c; explicit prsd_ctx(int d) : c(d) {} };
 struct prsd_spectra { SpectraBatch s; prsd_spectra(Context& c, int nc, int ns, const double* k, const double* T, const double* p) : s(c, nc, ns, k, T, p) {} };
 struct prsd_plan { PTPlan p; prsd_plan(Context& c, const double* k, int nk, const QuadConfig& q, bool ml, bool zel) : p(c, k, nk, q, ml, zel) {} };
 struct prsd_result { PTResult r; Context* ctx = nullptr; };
+struct prsd_galaxy {
+    GalaxyModel g;
+    DevBuf<double> dk, dmu, dout;
+    prsd_galaxy(Context& c, const GalaxyConfig& cfg, const double* km, int nkm, const double* ki, int nki) : g(c, cfg, km, nkm, ki, nki) {}
+};
+struct prsd_zelplan { ZelPlan z; Context* ctx = nullptr; };
 
 static thread_local std::string g_err;
 
@@ -431,6 +439,182 @@ int prsd_result_get(prsd_result* res, int what, double* out, long long n_expecte
         b->download(out, n, res->ctx->stream);
         res->ctx->sync();
     });
+}
+
+
+/* ------------------------------------------------------------------ FFTLog */
+int prsd_fftlog(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
+                const double* a, double* out, double* kr_out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && a && out, "null argument");
+        PRSD_REQUIRE(batch > 0, "FFTLog: empty batch");
+        auto plan = fftlog_plan(ctx->c, N, mu, q, dlnr, kr, kropt);
+        DevBuf<double> din, dout((size_t)batch*N);
+        din.upload(a, (size_t)batch*N, ctx->c.stream);
+        fftlog_apply(ctx->c, *plan, batch, din.p, dout.p);
+        dout.download(out, (size_t)batch*N, ctx->c.stream);
+        ctx->c.sync();
+        if (kr_out) *kr_out = plan->kr;
+    });
+}
+
+int prsd_fftlog_device(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
+                       const double* d_in, double* d_out, double* kr_out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && d_in && d_out, "null argument");
+        auto plan = fftlog_plan(ctx->c, N, mu, q, dlnr, kr, kropt);
+        fftlog_apply(ctx->c, *plan, batch, d_in, d_out);
+        if (kr_out) *kr_out = plan->kr;
+    });
+}
+
+int prsd_compute_xilm(prsd_ctx* ctx, int batch, int l, int m, int nk, const double* k, const double* pk,
+                      int nr, const double* r, double smoothing, double scale, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && k && pk && r && out, "null argument");
+        PRSD_REQUIRE(batch > 0 && nr > 0, "ComputeXiLM: empty request");
+        DevBuf<double> dpk, dout((size_t)batch*nr);
+        dpk.upload(pk, (size_t)batch*nk, ctx->c.stream);
+        compute_xilm_dev(ctx->c, batch, l, m, nk, k, dpk.p, nr, r, smoothing, scale, dout.p);
+        dout.download(out, (size_t)batch*nr, ctx->c.stream);
+        ctx->c.sync();
+    });
+}
+
+int prsd_compute_xilm_fftlog(prsd_ctx* ctx, int batch, int l, int m, int N, const double* k, const double* pk,
+                             double q, double smoothing, double* r_out, double* xi_out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && k && pk && r_out && xi_out, "null argument");
+        PRSD_REQUIRE(batch > 0 && N >= 2, "ComputeXiLM_fftlog: empty request");
+        DevBuf<double> dk, dpk, dxi((size_t)batch*N);
+        dk.upload(k, N, ctx->c.stream);
+        dpk.upload(pk, (size_t)batch*N, ctx->c.stream);
+        std::vector<double> r;
+        compute_xilm_fftlog_dev(ctx->c, batch, l, m, N, dk.p, k, dpk.p, q, smoothing, r, dxi.p, nullptr);
+        std::memcpy(r_out, r.data(), sizeof(double)*N);
+        dxi.download(xi_out, (size_t)batch*N, ctx->c.stream);
+        ctx->c.sync();
+    });
+}
+
+/* -------------------------------------------------------------- Zel'dovich */
+int prsd_zeldovich(prsd_ctx* ctx, int nrow, const double* X0, const double* XX, const double* YY, const double* sigmasq,
+                   const double* ratio, int lowk, double k0_low, const double* plin, const double* q3,
+                   int nk, const double* k, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && X0 && YY && sigmasq && k && out, "null argument");
+        PRSD_REQUIRE(nrow > 0 && nk > 0, "Zeldovich: empty request");
+        Context& c = ctx->c;
+        // stencil plans are cached per k list
+        static std::mutex mu;
+        static std::list<std::pair<std::pair<int, std::vector<double>>, std::shared_ptr<ZelPlan>>> cache;
+        std::shared_ptr<ZelPlan> zp;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            std::pair<int, std::vector<double>> key{c.device, std::vector<double>(k, k + nk)};
+            for (auto& e : cache) if (e.first == key) { zp = e.second; break; }
+            if (!zp) {
+                zp = std::make_shared<ZelPlan>();
+                zp->build(c, k, nk);
+                cache.emplace_front(key, zp);
+                while (cache.size() > 8) cache.pop_back();
+            }
+        }
+        DevBuf<double> dX0, dXX, dYY, dss, drat, dpl, dq3, dout((size_t)nrow*3*nk);
+        dX0.upload(X0, (size_t)nrow*ZEL_N, c.stream);
+        if (XX) dXX.upload(XX, (size_t)nrow*ZEL_N, c.stream);
+        dYY.upload(YY, (size_t)nrow*ZEL_N, c.stream);
+        dss.upload(sigmasq, nrow, c.stream);
+        if (ratio) drat.upload(ratio, nrow, c.stream);
+        if (lowk) {
+            PRSD_REQUIRE(plin && q3, "Zeldovich: the low-k approximation needs P_lin(k) and Q3/k^4");
+            dpl.upload(plin, (size_t)nrow*nk, c.stream);
+            dq3.upload(q3, nrow, c.stream);
+        }
+        zeldovich_eval_map(c, *zp, nrow, nullptr, dX0.p, XX ? dXX.p : nullptr, dYY.p, dss.p, 1, ratio ? drat.p : nullptr,
+                           lowk != 0, k0_low, lowk ? dpl.p : nullptr, lowk ? dq3.p : nullptr, 1, dout.p);
+        dout.download(out, (size_t)nrow*3*nk, c.stream);
+        c.sync();
+    });
+}
+
+/* ------------------------------------------------------------ galaxy model */
+static GalaxyConfig gal_cfg_from(const double* cfg)
+{
+    GalaxyConfig g;
+    galaxy_config_default(g);
+    if (cfg) {
+        g.max_mu = (int)cfg[0]; g.fog_model = (int)cfg[1];
+        g.use_P00_model = cfg[2] != 0; g.use_P01_model = cfg[3] != 0; g.use_P11_model = cfg[4] != 0;
+        g.use_Pdv_model = cfg[5] != 0; g.use_Pvv_model = cfg[6] != 0; g.use_Phm_model = cfg[7] != 0;
+        g.use_tidal_bias = cfg[8] != 0; g.use_so_correction = cfg[9] != 0;
+        g.k0_low = cfg[10];
+        for (int i = 0; i < 10; i++) g.hz00[i] = cfg[16 + i];
+        for (int i = 0; i < 9; i++) g.hz11[i] = cfg[26 + i];
+        for (int i = 0; i < 20; i++) g.hzhm[i] = cfg[35 + i];
+    }
+    return g;
+}
+
+int prsd_galaxy_config_default(double* cfg64)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(cfg64, "null argument");
+        GalaxyConfig g;
+        galaxy_config_default(g);
+        for (int i = 0; i < 64; i++) cfg64[i] = 0.0;
+        cfg64[0] = g.max_mu; cfg64[1] = g.fog_model;
+        cfg64[2] = g.use_P00_model; cfg64[3] = g.use_P01_model; cfg64[4] = g.use_P11_model;
+        cfg64[5] = g.use_Pdv_model; cfg64[6] = g.use_Pvv_model; cfg64[7] = g.use_Phm_model;
+        cfg64[8] = g.use_tidal_bias; cfg64[9] = g.use_so_correction; cfg64[10] = g.k0_low;
+        for (int i = 0; i < 10; i++) cfg64[16 + i] = g.hz00[i];
+        for (int i = 0; i < 9; i++) cfg64[26 + i] = g.hz11[i];
+        for (int i = 0; i < 20; i++) cfg64[35 + i] = g.hzhm[i];
+    });
+}
+
+int prsd_galaxy_create(prsd_ctx* ctx, const double* cfg64, int nkm, const double* kmodel, int nk_interp,
+                       const double* k_interp, prsd_galaxy** out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && kmodel && k_interp && out, "null argument");
+        *out = new prsd_galaxy(ctx->c, gal_cfg_from(cfg64), kmodel, nkm, k_interp, nk_interp);
+    });
+}
+int prsd_galaxy_destroy(prsd_galaxy* g) { return guarded([&] { delete g; }); }
+
+int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
+                      const double* stoch, int npts, const double* k, const double* mu, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && sp && res && par && stoch && k && mu && out, "null argument");
+        Context& c = *g->g.ctx;
+        g->dk.upload(k, npts, c.stream);
+        g->dmu.upload(mu, npts, c.stream);
+        g->dout.ensure((size_t)nw*npts);
+        g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p);
+        g->dout.download(out, (size_t)nw*npts, c.stream);
+        c.sync();
+    });
+}
+
+int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
+                             const double* stoch, int npts, const double* d_k, const double* d_mu, double* d_out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && sp && res && par && stoch && d_k && d_mu && d_out, "null argument");
+        g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, d_k, d_mu, d_out);
+    });
+}
+
+int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
+{
+    return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });
 }
 
 } // extern "C"

@@ -1,0 +1,200 @@
+// fftlog.cu -- batched FFTLog (see fftlog.cuh).
+#include "fftlog.cuh"
+#include "fftlog_host.h"
+
+#include <cmath>
+#include <list>
+#include <mutex>
+
+namespace prsd {
+
+// --------------------------------------------------------------- plan cache
+struct FKey { int dev, N, kropt; double mu, q, dlnr, kr; };
+static bool operator==(const FKey& a, const FKey& b)
+{
+    return a.dev == b.dev && a.N == b.N && a.kropt == b.kropt && a.mu == b.mu && a.q == b.q && a.dlnr == b.dlnr && a.kr == b.kr;
+}
+static std::mutex g_mu;
+static std::list<std::pair<FKey, std::shared_ptr<FFTLogPlan>>> g_cache;
+
+std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt)
+{
+    PRSD_REQUIRE(N >= 2 && N <= 8192, "FFTLog: N = %d outside [2, 8192]", N);
+    PRSD_REQUIRE(dlnr != 0.0 && std::isfinite(dlnr), "FFTLog: dlnr must be non-zero");
+    PRSD_REQUIRE(kr > 0, "FFTLog: kr must be positive");
+    FKey key{ctx.device, N, kropt, mu, q, dlnr, kr};
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto& e : g_cache) if (e.first == key) return e.second;
+    auto p = std::make_shared<FFTLogPlan>();
+    p->N = N; p->mu = mu; p->q = q; p->dlnr = dlnr;
+    p->kr = kropt ? fftlog_krgood(mu, q, dlnr, kr) : kr;
+    p->pow2 = (N & (N - 1)) == 0 && N >= 8;
+    std::vector<double> re, im;
+    fftlog_multipliers(N, mu, q, dlnr, p->kr, re, im);
+    p->ure.upload(re, ctx.stream);
+    p->uim.upload(im, ctx.stream);
+    ctx.sync();
+    g_cache.emplace_front(key, p);
+    while (g_cache.size() > 64) g_cache.pop_back();
+    return p;
+}
+
+// ------------------------------------------------------------ real-space g
+// g[d] = (1/N) sum_{m=0}^{N-1} U_m exp(2 pi i d m / N), U_{N-m} = conj(U_m)
+__global__ void k_fftlog_g(int N, const double* __restrict__ ure, const double* __restrict__ uim, double* __restrict__ g)
+{
+    const int d = blockIdx.x*blockDim.x + threadIdx.x;
+    if (d >= N) return;
+    const int nh = N/2;
+    double s = ure[0];
+    const int mmax = (N % 2 == 0) ? nh - 1 : nh;
+    for (int m = 1; m <= mmax; m++) {
+        const long long dm = ((long long)d*m) % N;
+        double sn, cs;
+        sincospi(2.0*(double)dm/(double)N, &sn, &cs);
+        s += 2.0*(ure[m]*cs - uim[m]*sn);
+    }
+    if (N % 2 == 0) s += ure[nh]*((d & 1) ? -1.0 : 1.0);
+    g[d] = s/N;
+}
+
+void FFTLogPlan::build_g(Context& ctx)
+{
+    if (g.n) return;
+    g.alloc(N);
+    k_fftlog_g<<<(N + 127)/128, 128, 0, ctx.stream>>>(N, ure.p, uim.p, g.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
+// ----------------------------------------------------- power-of-two kernel
+// smem: z[N] (double2) | tw[N/2] (double2)
+__global__ void __launch_bounds__(256)
+k_fftlog_pow2(int N, int logN, int batch, double q, double dlnr, double lnkr,
+              const double* __restrict__ ure, const double* __restrict__ uim,
+              const double* __restrict__ in, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    double2* z = reinterpret_cast<double2*>(smem_raw2);
+    double2* tw = z + N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b0 = 2*blockIdx.x, b1 = b0 + 1;
+    const bool two = b1 < batch;
+    const double jc = 0.5*(N + 1);
+
+    for (int j = tid; j < N/2; j += nt) {
+        double s, c;
+        sincospi(-2.0*(double)j/(double)N, &s, &c);
+        tw[j] = make_double2(c, s);
+    }
+    for (int i = tid; i < N; i += nt) {
+        double a0 = in[(size_t)b0*N + i];
+        double a1 = two ? in[(size_t)b1*N + i] : 0.0;
+        if (q != 0.0) {
+            const double f = exp(-q*((i + 1) - jc)*dlnr);      // fht: a(r) = A(r) (r/rc)^(-q)
+            a0 *= f; a1 *= f;
+        }
+        z[i] = make_double2(a0, a1);
+    }
+    __syncthreads();
+    // forward DIF: natural order in, bit-reversed order out
+    for (int half = N >> 1, shift = 0; half >= 1; half >>= 1, shift++) {
+        for (int t = tid; t < N/2; t += nt) {
+            const int j = t & (half - 1);
+            const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+            const double2 u = z[i0], v = z[i1];
+            const double2 w = tw[j << shift];
+            const double dr = u.x - v.x, di = u.y - v.y;
+            z[i0] = make_double2(u.x + v.x, u.y + v.y);
+            z[i1] = make_double2(dr*w.x - di*w.y, dr*w.y + di*w.x);
+        }
+        __syncthreads();
+    }
+    // multiply by U_m; slot p holds mode m = bitrev(p)
+    for (int p = tid; p < N; p += nt) {
+        const int m = (int)(__brev((unsigned)p) >> (32 - logN));
+        double ur, ui;
+        if (m <= N/2) { ur = ure[m]; ui = uim[m]; }
+        else { ur = ure[N - m]; ui = -uim[N - m]; }
+        const double2 v = z[p];
+        z[p] = make_double2(v.x*ur - v.y*ui, v.x*ui + v.y*ur);
+    }
+    __syncthreads();
+    // inverse DIT: bit-reversed in, natural out (conjugate twiddles)
+    for (int half = 1, shift = logN - 1; half < N; half <<= 1, shift--) {
+        for (int t = tid; t < N/2; t += nt) {
+            const int j = t & (half - 1);
+            const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+            const double2 w = tw[j << shift];
+            const double2 u = z[i0], v0 = z[i1];
+            const double vr = v0.x*w.x + v0.y*w.y, vi = v0.y*w.x - v0.x*w.y;   // v * conj(w)
+            z[i0] = make_double2(u.x + vr, u.y + vi);
+            z[i1] = make_double2(u.x - vr, u.y - vi);
+        }
+        __syncthreads();
+    }
+    // reversal, 1/N, output bias (fhtq :772-782, fht :632-638)
+    const double invN = 1.0/N;
+    for (int i = tid; i < N; i += nt) {
+        const double2 v = z[N - 1 - i];
+        double f = invN;
+        if (q != 0.0) f *= exp(-q*(((i + 1) - jc)*dlnr + lnkr));
+        out[(size_t)b0*N + i] = v.x*f;
+        if (two) out[(size_t)b1*N + i] = v.y*f;
+    }
+}
+
+// ------------------------------------------------------------ generic kernel
+// out[j] = sum_l a_l g[(N-1-j-l) mod N]   (one CTA per sequence, a and g in shared memory)
+__global__ void __launch_bounds__(256)
+k_fftlog_direct(int N, double q, double dlnr, double lnkr, const double* __restrict__ g,
+                const double* __restrict__ in, double* __restrict__ out)
+{
+    extern __shared__ double sm_d[];
+    double* a = sm_d;
+    double* gs = sm_d + N;
+    const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x;
+    const double jc = 0.5*(N + 1);
+    for (int i = tid; i < N; i += nt) {
+        double v = in[(size_t)b*N + i];
+        if (q != 0.0) v *= exp(-q*((i + 1) - jc)*dlnr);
+        a[i] = v;
+        gs[i] = g[i];
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += nt) {
+        double s = 0.0;
+        int d = N - 1 - j;                   // index (N-1-j-l) mod N, decreasing with l
+        for (int l = 0; l < N; l++) {
+            s = fma(a[l], gs[d], s);
+            d = (d == 0) ? N - 1 : d - 1;
+        }
+        if (q != 0.0) s *= exp(-q*(((j + 1) - jc)*dlnr + lnkr));
+        out[(size_t)b*N + j] = s;
+    }
+}
+
+void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, double* d_out)
+{
+    if (batch <= 0) return;
+    const int N = p.N;
+    if (p.pow2) {
+        int logN = 0;
+        while ((1 << logN) < N) logN++;
+        const size_t smem = (size_t)N*sizeof(double2) + (size_t)(N/2)*sizeof(double2);
+        PRSD_REQUIRE(smem <= ctx.smem_optin, "FFTLog: N = %d needs %zu B of shared memory", N, smem);
+        PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_pow2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fftlog_pow2<<<(batch + 1)/2, 256, smem, ctx.stream>>>(N, logN, batch, p.q, p.dlnr, std::log(p.kr),
+                                                              p.ure.p, p.uim.p, d_in, d_out);
+    } else {
+        p.build_g(ctx);
+        PRSD_REQUIRE(d_in != d_out, "FFTLog: in-place transform needs a power-of-two length");
+        const size_t smem = (size_t)2*N*sizeof(double);
+        if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fftlog_direct<<<batch, 256, smem, ctx.stream>>>(N, p.q, p.dlnr, std::log(p.kr), p.g.p, d_in, d_out);
+    }
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
+} // namespace prsd

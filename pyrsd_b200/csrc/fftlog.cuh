@@ -1,0 +1,32 @@
+// fftlog.cuh -- batched discrete log-space Hankel transform (FFTLog) on the device.
+//
+// Replaces FortranFFTLog + fhti/fht/fhtq + FFTPACK (pyRSD/_gcl/cpp/FortranFFTLog.cpp,
+// pyRSD/_gcl/extern/fftlog/fftlog.f:233-784, drfftf/drfftb.f).  One CTA transforms TWO real
+// sequences at once (packed as one complex sequence: the operator is real-linear), entirely in
+// shared memory: power-law bias -> radix-2 FFT -> multiply by u_m -> inverse FFT -> reversal,
+// 1/N and output bias, i.e. the whole of fht() fused in one kernel.  Lengths that are not a
+// power of two use the equivalent real-space circular kernel g (an O(N^2) contraction).
+#pragma once
+#include "common.h"
+
+#include <memory>
+
+namespace prsd {
+
+struct FFTLogPlan {
+    int N = 0;
+    double mu = 0, q = 0, dlnr = 0, kr = 1;     // kr AFTER the optional low-ringing adjustment
+    bool pow2 = false;
+    DevBuf<double> ure, uim;     // multipliers, m = 0 .. N/2
+    DevBuf<double> g;            // real-space circular kernel g[d], d = 0 .. N-1 (built on demand)
+    void build_g(Context& ctx);
+};
+
+// cached per (device, N, mu, q, dlnr, kr, kropt)
+std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt);
+
+// forward transform (dir = +1) of `batch` sequences; d_in / d_out are device pointers [batch][N]
+// (may alias).
+void fftlog_apply(Context& ctx, FFTLogPlan& plan, int batch, const double* d_in, double* d_out);
+
+} // namespace prsd

@@ -1,0 +1,521 @@
+// galaxy.cu -- GalaxySpectrum P(k, mu) assembly (see galaxy.cuh).
+#include "galaxy.cuh"
+
+#include <cmath>
+
+namespace prsd {
+
+void galaxy_config_default(GalaxyConfig& c)
+{
+    c.max_mu = 4;
+    c.fog_model = 0;
+    c.use_P00_model = c.use_P01_model = c.use_P11_model = c.use_Pdv_model = c.use_Pvv_model = c.use_Phm_model = 1;
+    c.use_tidal_bias = 0;
+    c.use_so_correction = 0;
+    c.k0_low = 5e-3;
+    // rsd/hzpt/__init__.py:66-92
+    const double h00[10] = {707.8, 3.654, 31.76, 0.1257, 3.243, 0.3729, 3.768, -0.1043, 1.699, 0.4224};
+    // rsd/hzpt/P11.py:33-61
+    const double h11[9] = {658.9, 3.91, 1.917, 18.95, -0.3657, -0.2585, 0.8473, -0.1524, 0.7769};
+    // rsd/hzpt/Phm.py:24-68 : A0, R1, R1h, R2h, R  x (amp, alpha, beta, run)
+    const double hhm[20] = {751.9, 1.657, 3.752, 0., 5.192, -0.5739, 0.1616, 0., 8.253, -0.8421, -0.1345, 0.,
+                            3.053, -1.03, -0.3596, 0., 16.9, -0.1185, -1.067, 0.};
+    for (int i = 0; i < 10; i++) c.hz00[i] = h00[i];
+    for (int i = 0; i < 9; i++) c.hz11[i] = h11[i];
+    for (int i = 0; i < 20; i++) c.hzhm[i] = hhm[i];
+}
+
+// ---- row layout of the PT-table spline buffer: [cosmo][PT_NROWS][5 nk]
+enum { PT_I = 0, PT_J = 16, PT_K = 22, PT_ML = 35, PT_SIGK = 56, PT_NROWS = 57 };
+// ---- base arrays on the model grid: [walker][NB][nkm]
+enum {
+    B_PLIN = 0, B_P00, B_P01, B_P11MU4, B_PDV, B_PVV, B_PDD, B_P02NV2, B_P02NV4, B_P12NV4, B_P22NV4,
+    B_K00, B_K00S, B_K10, B_K10S, B_K11, B_K11S, B_K20A, B_K20B, B_K20SA, B_K20SB,
+    B_C11MU2, B_C11MU4, B_I03F3, B_SIGK2, B_Z00, B_MU6A, B_I30F3, NB
+};
+// ---- walker parameter slots
+enum {
+    W_S8Z = 0, W_F, W_APAR, W_APERP, W_ADRAG, W_B1 = 5 /* cA cB sA sB */, W_FS = 9, W_FCB, W_FSB, W_SIGC, W_SIGSA,
+    W_SIGSB, W_NCBS, W_NSBSB, W_FSO, W_SIGSO, W_SIGV, W_D, W_S80, W_B2 = 22 /* [6 kinds][4 biases] */, W_END = 46
+};
+
+// --------------------------------------------------------------- spline builds
+__global__ void k_nak_rows(int nk, const double* __restrict__ X, const double* __restrict__ src, int rows_per_cosmo,
+                           int row_offset, double* __restrict__ dst)
+{
+    extern __shared__ double sm_nak[];
+    double* x = sm_nak;
+    double* y = x + nk; double* b = y + nk; double* c = b + nk; double* d = c + nk; double* M = d + nk; double* w = M + nk;
+    const int r = blockIdx.x, cc = blockIdx.y, tid = threadIdx.x;
+    const double* s = src + ((size_t)cc*rows_per_cosmo + r)*nk;
+    for (int i = tid; i < nk; i += blockDim.x) { x[i] = X[i]; y[i] = s[i]; }
+    __syncthreads();
+    if (tid == 0) nak_spline_build(nk, x, y, b, c, d, M, w);
+    __syncthreads();
+    double* o = dst + ((size_t)cc*PT_NROWS + row_offset + r)*5*nk;
+    for (int i = tid; i < nk; i += blockDim.x) { o[i] = x[i]; o[nk + i] = y[i]; o[2*nk + i] = b[i]; o[3*nk + i] = c[i]; o[4*nk + i] = d[i]; }
+}
+
+// --------------------------------------------------------------- HZPT broadband
+__device__ __forceinline__ double pade_bb(double k, double A0, double R, double R1, double R1h, double R2h)
+{
+    const double k2 = k*k;
+    const double F = 1.0 - 1.0/(1.0 + k2*R*R);
+    const double r2 = k*R2h, r22 = r2*r2;
+    return F*A0*(1.0 + k2*R1*R1)/(1.0 + k2*R1h*R1h + r22*r22);
+}
+
+struct GalDev {
+    GalaxyConfig cfg;
+    int nkm, nk, nspl;
+    double lnkm0, inv_dlnkm;        // model grid (log-uniform)
+    double lnki0, inv_dlnki;        // k_interp grid
+    double lnk1l0, inv_dlnk1l;      // one-loop grid
+};
+
+__global__ void k_gal_base(GalDev G, const double* __restrict__ km, const int* __restrict__ cmap,
+                           const double* __restrict__ par, const double* __restrict__ ptspl,
+                           const double* __restrict__ plin_m, const double* __restrict__ olspl,
+                           const double* __restrict__ scal, const double* __restrict__ zel1, const double* __restrict__ zel2,
+                           double* __restrict__ base)
+{
+    const int w = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int nkm = G.nkm, nk = G.nk;
+    if (i >= nkm) return;
+    const int c = cmap[w];
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double k = km[i], k2 = k*k;
+    const double s8z = p[W_S8Z], f = p[W_F], D = p[W_D];
+    const double norm = (s8z/p[W_S80])*(s8z/p[W_S80]);
+    const double norm2 = norm*norm;
+    auto T = [&](int row) {
+        const double* s = ptspl + ((size_t)c*PT_NROWS + row)*5*nk;
+        return pw_cubic_eval_log(nk, s, s + nk, s + 2*nk, s + 3*nk, s + 4*nk, G.lnki0, G.inv_dlnki, k);
+    };
+    auto OL = [&](int which) {
+        const double* s = olspl + (size_t)(c*4 + which)*5*ONELOOP_N;
+        return (k < ONELOOP_KMIN || k > ONELOOP_KMAX) ? 0.0 : cubic_spline_eval_log(ONELOOP_N, s, G.lnk1l0, G.inv_dlnk1l, k);
+    };
+    auto I = [&](int m, int n) { return norm2*T(PT_I + 4*m + n); };
+    // J order: J00 J01 J02 J10 J11 J20
+    auto J = [&](int j) { return norm*T(PT_J + j); };
+    auto K = [&](int j) { return norm2*T(PT_K + j); };
+    auto ML = [&](int m) { return norm2*T(PT_ML + 3*m) + norm2*norm*T(PT_ML + 3*m + 1) + norm2*norm2*T(PT_ML + 3*m + 2); };
+
+    const double PL0 = plin_m[(size_t)c*nkm + i];
+    const double Plin = norm*PL0;
+    const double* z1 = zel1 + (size_t)w*3*nkm;
+    const double* z2 = zel2 + (size_t)w*3*nkm;
+    const double* h0 = G.cfg.hz00;
+    auto bb00 = [&](double s8) {
+        const double x = s8/0.8;
+        return pade_bb(k, h0[0]*pow(x, h0[1]), h0[2]*pow(x, h0[3]), h0[4]*pow(x, h0[5]), h0[6]*pow(x, h0[7]), h0[8]*pow(x, h0[9]));
+    };
+    // ---- P00 (dm/P00.py:9-26)
+    double P00;
+    if (G.cfg.use_P00_model) P00 = bb00(s8z) + z1[i];
+    else P00 = Plin + 2.0*I(0, 0) + 6.0*k2*J(0)*Plin;
+    // ---- P01 (dm/P01.py:9-31; broadband hzpt/P01.py:57-90)
+    double P01;
+    if (G.cfg.use_P01_model) {
+        const double x = s8z/0.8;
+        const double A0 = h0[0]*pow(x, h0[1]), R = h0[2]*pow(x, h0[3]), R1 = h0[4]*pow(x, h0[5]);
+        const double R1h = h0[6]*pow(x, h0[7]), R2h = h0[8]*pow(x, h0[9]);
+        const double dA0 = f*h0[1]*A0, dR = f*h0[3]*R, dR1 = f*h0[5]*R1, dR1h = f*h0[7]*R1h, dR2h = f*h0[9]*R2h;
+        const double k4 = k2*k2;
+        const double N = 1.0 + k2*R*R, F = 1.0 - 1.0/N;
+        const double num = 1.0 + k2*R1*R1, den = 1.0 + k2*R1h*R1h + k4*R2h*R2h*R2h*R2h;
+        const double bb = F*num/den*dA0 + 2.0*A0*k2*R*num/(N*N)/den*dR + 2.0*A0*k4*R*R*R1/N/den*dR1
+                        - 2.0*A0*k4*R*R*num*R1h/N/(den*den)*dR1h - 4.0*A0*k4*k2*R*R*num*R2h*R2h*R2h/N/(den*den)*dR2h;
+        P01 = bb + 2.0*f*z1[nkm + i];
+    } else P01 = 2.0*f*(Plin + 4.0*(I(0, 0) + 3.0*k2*J(0)*Plin));
+    // ---- P11[mu4] total (dm/P11.py:67-82)
+    double P11mu4;
+    if (G.cfg.use_P11_model) {
+        const double* h = G.cfg.hz11;
+        const double x = s8z/0.8, y = f/0.5;
+        const double A0 = h[0]*pow(x, h[1])*pow(y, h[2]), R = h[3]*pow(x, h[4])*pow(y, h[5]), R1h = h[6]*pow(x, h[7])*pow(y, h[8]);
+        const double F = 1.0 - 1.0/(1.0 + k2*R*R);
+        P11mu4 = F*A0/(1.0 + k2*R1h*R1h) + f*f*z1[2*nkm + i] - f*f*I(3, 1);
+    } else {
+        const double part2 = 2.0*I(1, 1) + 4.0*I(2, 2) + 6.0*k2*(J(4) + 2.0*J(3))*Plin;
+        P11mu4 = f*f*(Plin + part2 + I(1, 3));
+    }
+    // ---- Pdd, Pdv, Pvv (power_dm.py:676-718, 848-884)
+    const double Pdd = norm*(PL0 + norm*OL(0));
+    double Pdv, Pvv;
+    {
+        double P00_z0 = 0.0, zs2 = 1.0, P00_hz = 0.0;
+        if (G.cfg.use_Pdv_model || G.cfg.use_Pvv_model) {
+            P00_z0 = bb00(s8z/D) + z2[i];
+            P00_hz = bb00(s8z) + z1[i];          // self.hzpt.P00(k) regardless of use_P00_model
+            const double zs = 3.0/(D + D*D + D*D*D);
+            zs2 = zs*zs;
+        }
+        if (G.cfg.use_Pdv_model) {
+            const double g = (-12483.8*sqrt(P00_z0) + 2.554*P00_z0*P00_z0)/(1381.29 + 2.540*P00_z0);
+            Pdv = -f*((g - P00_z0)/zs2 + P00_hz);
+        } else Pdv = -f*norm*(PL0 + norm*OL(1));
+        if (G.cfg.use_Pvv_model) {
+            const double g = (-12480.5*sqrt(P00_z0) + 1.824*P00_z0*P00_z0)/(2165.87 + 1.796*P00_z0);
+            Pvv = f*f*((g - P00_z0)/zs2 + P00_hz);
+        } else Pvv = f*f*norm*(PL0 + norm*OL(2));
+    }
+    double* o = base + (size_t)w*NB*nkm + i;
+    const double f2 = f*f, f3 = f2*f, f4 = f2*f2;
+    o[B_PLIN*nkm] = Plin;
+    o[B_P00*nkm] = P00;
+    o[B_P01*nkm] = P01;
+    o[B_P11MU4*nkm] = P11mu4;
+    o[B_PDV*nkm] = Pdv;
+    o[B_PVV*nkm] = Pvv;
+    o[B_PDD*nkm] = Pdd;
+    o[B_P02NV2*nkm] = f2*(I(0, 2) + 2.0*k2*J(2)*Plin);          // dm/P02.py:8-21
+    o[B_P02NV4*nkm] = f2*(I(2, 0) + 2.0*k2*J(5)*Plin);          // dm/P02.py:49-56
+    o[B_P12NV4*nkm] = f3*(I(1, 2) - I(0, 3) + 2.0*k2*J(2)*Plin);// dm/P12.py:8-20
+    o[B_P22NV4*nkm] = (1.0/16.0)*f4*I(2, 3);                    // dm/P22.py:8-21
+    for (int j = 0; j < 10; j++) {
+        // K00 K00s K10 K10s K11 K11s K20_a K20_b K20s_a K20s_b from the K row order
+        const int rowmap[10] = {0, 2, 5, 7, 6, 8, 9, 10, 11, 12};
+        o[(B_K00 + j)*nkm] = K(rowmap[j]);
+    }
+    o[B_C11MU2*nkm] = f2*(ML(0) + ML(2));                        // biased/P11.py:8-17
+    o[B_C11MU4*nkm] = f2*(ML(1) + ML(3));                        // biased/P11.py:36-39
+    o[B_I03F3*nkm] = f3*I(0, 3);
+    { const double sk = norm*T(PT_SIGK); o[B_SIGK2*nkm] = sk*sk; }
+    o[B_Z00*nkm] = z1[i];
+    o[B_MU6A*nkm] = f3*(I(2, 1) + 2.0*k2*J(5)*Plin) + 0.125*f4*I(3, 2);   // biased/P12.py:33-45 + power_biased.py:525
+    o[B_I30F3*nkm] = f3*I(3, 0);
+    (void)scal;
+}
+
+// pair table: bias indices (0 cA, 1 cB, 2 sA, 3 sB)
+__constant__ int c_pair_a[GAL_NPAIR] = {0, 0, 1, 0, 0, 1, 1, 2, 2, 3};
+__constant__ int c_pair_b[GAL_NPAIR] = {0, 1, 1, 2, 3, 2, 3, 2, 3, 3};
+
+// ----------------------------------------------------------- halo moments + splines
+__global__ void __launch_bounds__(128)
+k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict__ kst, const int* __restrict__ cmap,
+              const double* __restrict__ par, const double* __restrict__ stoch, const double* __restrict__ scal,
+              const double* __restrict__ base, double* __restrict__ pairspl)
+{
+    extern __shared__ double sm_gm[];
+    const int nkm = G.nkm;
+    double* X = sm_gm;                       // [nkm]
+    double* Y = X + nkm;                     // [4][nkm]
+    double* W = Y + 4*nkm;                   // [4][5 nkm] work: b c d M w
+    double* S = W + 20*nkm;                  // stochasticity spline: x y b c d M w  [7][20]
+    const int pr = blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
+    const int c = cmap[w];
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double* B = base + (size_t)w*NB*nkm;
+    const int ia = c_pair_a[pr], ib = c_pair_b[pr];
+    const double b1 = p[W_B1 + ia], b1b = p[W_B1 + ib];
+    auto b2 = [&](int kind, int which) { return p[W_B2 + kind*4 + which]; };   // kind: 00_a 00_b 00_c 00_d 01_a 01_b
+    const double f = p[W_F], s8z = p[W_S8Z];
+    const double norm = (s8z/p[W_S80])*(s8z/p[W_S80]);
+    const double sig_lin = sqrt(norm*scal[(size_t)c*4 + 0]);
+    const double sigv = p[W_SIGV] > 0.0 ? p[W_SIGV] : sig_lin;   // sigma_v defaults to sigma_lin (power_dm.py:454-460)
+    const double sig2 = sigv*sigv, sig2b = sigv*sigv;            // sigmav_halo = sigmav_halo_bar = sigma_v
+    const double vkurt = norm*norm*scal[(size_t)c*4 + 1];
+    const double bs = G.cfg.use_tidal_bias ? -2.0/7.0*(b1 - 1.0) : 0.0;
+    const double bsb = G.cfg.use_tidal_bias ? -2.0/7.0*(b1b - 1.0) : 0.0;
+
+    for (int i = tid; i < nkm; i += blockDim.x) X[i] = km[i];
+    if (tid < GAL_NSTOCH) { S[tid] = kst[tid]; S[GAL_NSTOCH + tid] = stoch[((size_t)w*GAL_NPAIR + pr)*GAL_NSTOCH + tid]; }
+    __syncthreads();
+    if (tid == 0) nak_spline_build(GAL_NSTOCH, S, S + 20, S + 40, S + 60, S + 80, S + 100, S + 120);
+    __syncthreads();
+    const double lnks0 = log(S[0]), inv_dlnks = (GAL_NSTOCH - 1)/log(S[GAL_NSTOCH - 1]/S[0]);
+    const double* hm = G.cfg.hzhm;
+    auto phm = [&](double bb, int which, double k, double P00, double Z00, double K00, double K00s, double bsx) {
+        if (G.cfg.use_Phm_model) {
+            // HaloMatterBase._powerlaw (hzpt/Phm.py:231-236)
+            const double x = s8z/0.8, lb = log(bb);
+            auto pl = [&](int j) { return hm[4*j]*pow(bb, hm[4*j + 1] + hm[4*j + 3]*lb)*pow(x, hm[4*j + 2]); };
+            return pade_bb(k, pl(0), pl(4), pl(1), pl(2), pl(3)) + bb*Z00;
+        }
+        return bb*P00 + b2(0, which)*K00 + bsx*K00s;      // power_biased.py:325-340
+    };
+    for (int i = tid; i < nkm; i += blockDim.x) {
+        const double k = X[i], fk2 = f*f*k*k, fk4 = fk2*fk2;
+        const double P00 = B[B_P00*nkm + i], P01 = B[B_P01*nkm + i], Pdv = B[B_PDV*nkm + i], Pvv = B[B_PVV*nkm + i];
+        const double K00 = B[B_K00*nkm + i], K00s = B[B_K00S*nkm + i], K10 = B[B_K10*nkm + i], K10s = B[B_K10S*nkm + i];
+        const double K11 = B[B_K11*nkm + i], K11s = B[B_K11S*nkm + i];
+        const double P02nv2 = B[B_P02NV2*nkm + i], P02nv4 = B[B_P02NV4*nkm + i];
+        // P00_ss (biased/P00.py:19-43) with the stochasticity spline (power_biased.py:342-366)
+        const double st = pw_cubic_eval_log(GAL_NSTOCH, S, S + 20, S + 40, S + 60, S + 80, lnks0, inv_dlnks, k);
+        const double Phm1 = phm(b1, ia, k, P00, B[B_Z00*nkm + i], K00, K00s, bs);
+        const double Phm2 = (ia == ib) ? Phm1 : phm(b1b, ib, k, P00, B[B_Z00*nkm + i], K00, K00s, bsb);
+        const double mu0 = Phm1*Phm2/P00 + st;
+        // P01_mu2 with a given b2_01 kind (biased/P01.py:3-24)
+        auto P01mu2 = [&](int kind) {
+            const double c1 = b2(kind, ia), c2 = b2(kind, ib);
+            return b1*b1b*P01 - Pdv*(b1*(1.0 - b1b) + b1b*(1.0 - b1)) + f*((c1 + c2)*K10 + (bs + bsb)*K10s)
+                 + f*((b1b*c1 + b1*c2)*K11 + (b1b*bs + b1*bsb)*K11s);
+        };
+        // Phh_mu0 with a given b2_00 kind (biased/P00.py:3-17)
+        auto Phh = [&](int kind) {
+            const double c1 = b2(kind, ia), c2 = b2(kind, ib);
+            return b1*b1b*P00 + (b1*c2 + b1b*c1)*K00 + (bs*c2 + bsb*c1)*K00s;
+        };
+        const double P11ss_mu2 = b1*b1b*B[B_C11MU2*nkm + i];
+        // P[mu^2] (power_biased.py:494-505; biased/P02.py:5-33)
+        const double P02ss_mu2 = 0.5*(b1 + b1b)*P02nv2 - 0.5*fk2*(sig2 + sig2b)*Phh(2)
+                               + 0.5*f*f*((b2(2, ia) + b2(2, ib))*B[B_K20A*nkm + i] + (bs + bsb)*B[B_K20SA*nkm + i]);
+        const double mu2 = P01mu2(4) + P11ss_mu2 + P02ss_mu2;
+        // P[mu^4] (power_biased.py:507-520)
+        const double P11ss_mu4 = 0.5*(b1 + b1b)*B[B_P11MU4*nkm + i] - 0.5*((b1 - 1.0) + (b1b - 1.0))*Pvv
+                               + B[B_C11MU4*nkm + i]*(b1*b1b - 0.5*(b1 + b1b));                    // biased/P11.py:19-44
+        const double P02ss_mu4 = 0.5*(b1 + b1b)*P02nv4
+                               + 0.5*f*f*((b2(1, ia) + b2(1, ib))*B[B_K20B*nkm + i] + (bs + bsb)*B[B_K20SB*nkm + i]);  // P02.py:35-54
+        const double P01b = P01mu2(5);
+        const double P12ss_mu4 = B[B_P12NV4*nkm + i] - 0.5*fk2*0.5*(sig2 + sig2b)*P01
+                               - 0.5*((b1 - 1.0) + (b1b - 1.0))*B[B_I03F3*nkm + i]
+                               - 0.25*fk2*(sig2 + sig2b)*(P01b - P01);                                    // biased/P12.py:4-22
+        const double P03ss_mu4 = -0.25*fk2*(sig2 + sig2b)*P01b;                                            // biased/P03.py:4-16
+        const double PhhD = Phh(3);
+        const double P22ss_mu4 = B[B_P22NV4*nkm + i] + 0.5*fk4*(b1*b1b*B[B_PDD*nkm + i])*B[B_SIGK2*nkm + i]
+                               - 0.25*fk2*(sig2 + sig2b)*(0.5*(b1 + b1b)*P02nv2)
+                               + 0.125*fk4*(sig2*sig2 + sig2b*sig2b)*PhhD;                                  // biased/P22.py:4-34
+        const double P13ss_mu4 = -0.5*fk2*(sig2 + sig2b)*P11ss_mu2;                                        // biased/P13.py:3-19
+        const double P04ss_mu4 = -0.125*(b1 + b1b)*fk2*(sig2 + sig2b)*P02nv2
+                               + (1.0/12.0)*fk4*PhhD*(1.5*(sig2*sig2 + sig2b*sig2b) + vkurt);               // biased/P04.py:4-27
+        const double mu4 = P11ss_mu4 + P02ss_mu4 + P12ss_mu4 + P03ss_mu4 + P22ss_mu4 + P13ss_mu4 + P04ss_mu4;
+        // P[mu^6] (power_biased.py:522-528; biased/P12.py:24-45)
+        const double mu6 = B[B_MU6A*nkm + i] - 0.5*(b1 + b1b)*B[B_I30F3*nkm + i];
+        Y[i] = mu0; Y[nkm + i] = mu2; Y[2*nkm + i] = mu4; Y[3*nkm + i] = mu6;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        double* wk = W + (size_t)tid*5*nkm;
+        nak_spline_build(nkm, X, Y + tid*nkm, wk, wk + nkm, wk + 2*nkm, wk + 3*nkm, wk + 4*nkm);
+    }
+    __syncthreads();
+    // store [walker][pair][moment][Y | b | c | d]
+    double* o = pairspl + ((size_t)w*GAL_NPAIR + pr)*16*nkm;
+    for (int idx = tid; idx < 4*nkm; idx += blockDim.x) {
+        const int m = idx/nkm, i = idx - m*nkm;
+        const double* wk = W + (size_t)m*5*nkm;
+        o[(m*4 + 0)*nkm + i] = Y[m*nkm + i];
+        o[(m*4 + 1)*nkm + i] = wk[i];
+        o[(m*4 + 2)*nkm + i] = wk[nkm + i];
+        o[(m*4 + 3)*nkm + i] = wk[2*nkm + i];
+    }
+}
+
+// ------------------------------------------------------------------ P(k, mu)
+__device__ __forceinline__ double fog(int model, double x)
+{
+    const double h = 1.0 + 0.5*x*x;
+    if (model == 0) return 1.0/(h*h);            // fog_kernels.py:40-52
+    if (model == 1) return 1.0/h;                // :57-69
+    return exp(-0.5*x*x);                        // :72-84
+}
+
+__global__ void __launch_bounds__(128)
+k_gal_pkmu(GalDev G, const double* __restrict__ km, const double* __restrict__ par, const double* __restrict__ pairspl,
+           int npts, const double* __restrict__ kk, const double* __restrict__ mm, double* __restrict__ out)
+{
+    const int w = blockIdx.y, j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    const int nkm = G.nkm;
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double apar = p[W_APAR], aperp = p[W_APERP], adrag = p[W_ADRAG];
+    const double kobs = kk[j], muobs = mm[j];
+    // rsd/tools.py:54-75
+    const double F = apar/aperp;
+    double k = kobs/aperp, mu = muobs;
+    if (F != 1.0) {
+        const double fac = sqrt(1.0 + muobs*muobs*(1.0/(F*F) - 1.0));
+        k = kobs/aperp*fac;
+        mu = muobs/F/fac;
+    }
+    double res;
+    if (!(k >= km[0] && k <= km[nkm - 1])) {
+        res = nan("");           // the reference raises InterpolationDomainError here (_cache.py:327-339)
+    } else {
+        int i = (int)((log(k) - G.lnkm0)*G.inv_dlnkm);
+        if (i < 0) i = 0;
+        if (i > nkm - 2) i = nkm - 2;
+        while (i > 0 && k < km[i]) --i;
+        while (i < nkm - 2 && k > km[i + 1]) ++i;
+        const double t = k - km[i];
+        const double mu2 = mu*mu;
+        const int nmom = G.cfg.max_mu/2 + 1;
+        const double fs = p[W_FS], fcB = p[W_FCB], fsB = p[W_FSB];
+        const double sig[3] = {p[W_SIGC], p[W_SIGSA], p[W_SIGSB]};
+        const int fm = G.cfg.fog_model;
+        const double kmu = k*mu;
+        const bool so = G.cfg.use_so_correction != 0;
+        const double Gc = so ? 1.0 : fog(fm, kmu*sig[0]);       // SOCorrection sets sigma_c = 0 inside Pcc
+        const double GsA = fog(fm, kmu*sig[1]), GsB = fog(fm, kmu*sig[2]);
+        const double Gc_cs = fog(fm, kmu*sig[0]);
+        auto Phh = [&](int pr) {
+            const double* s = pairspl + ((size_t)w*GAL_NPAIR + pr)*16*nkm + i;
+            double tot = 0.0, mpow = 1.0;
+            for (int m = 0; m < nmom; m++) {
+                const double* q = s + (size_t)m*4*nkm;
+                tot += mpow*(q[0] + t*(q[nkm] + t*(q[2*nkm] + t*q[3*nkm])));
+                mpow *= mu2;
+            }
+            return tot;
+        };
+        // gal/Pcc, Pcs, Pss coefficient tables
+        double Pcc = (1.0 - fcB)*(1.0 - fcB)*Gc*Gc*Phh(0) + 2.0*fcB*(1.0 - fcB)*Gc*Gc*Phh(1) + fcB*fcB*Gc*Gc*Phh(2);
+        if (so) {
+            const double fso = p[W_FSO];
+            const double G1 = Gc_cs, G2 = fog(fm, kmu*p[W_SIGSO]);
+            Pcc = ((G1*(1.0 - fso))*(G1*(1.0 - fso)) + 2.0*fso*(1.0 - fso)*G1*G2 + (G2*fso)*(G2*fso))*Pcc
+                + 2.0*G1*G2*fso*fcB*p[W_NCBS];                    // gal/Pcc/__init__.py:39-60
+        }
+        const double Pcs = (1.0 - fcB)*(1.0 - fsB)*Gc_cs*GsA*Phh(3) + (1.0 - fcB)*fsB*Gc_cs*GsB*Phh(4)
+                         + fcB*(1.0 - fsB)*Gc_cs*GsA*(Phh(5) + p[W_NCBS]) + fcB*fsB*Gc_cs*GsB*(Phh(6) + p[W_NCBS]);
+        const double Pss = (1.0 - fsB)*(1.0 - fsB)*GsA*GsA*Phh(7) + 2.0*fsB*(1.0 - fsB)*GsA*GsB*Phh(8)
+                         + fsB*fsB*GsB*GsB*(Phh(9) + p[W_NSBSB]);
+        res = (1.0 - fs)*(1.0 - fs)*Pcc + 2.0*fs*(1.0 - fs)*Pcs + fs*fs*Pss;
+        res = res/(aperp*aperp*apar)*adrag*adrag*adrag;          // rsd/tools.py:211-214
+    }
+    out[(size_t)w*npts + j] = res;
+}
+
+__global__ void k_plin_model(int nspl, const PlinParams* __restrict__ params, const double* __restrict__ spl,
+                             int nq, const double* __restrict__ q, double* __restrict__ out)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
+}
+
+__global__ void k_scale_rows(int n, const double* __restrict__ in, const double* __restrict__ fac, const int* __restrict__ cmap,
+                             double* __restrict__ out)
+{
+    // out[w][i] = fac[w] * in[cmap[w]][i]
+    const int w = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[(size_t)w*n + i] = fac[w]*in[(size_t)cmap[w]*n + i];
+}
+
+// ------------------------------------------------------------------ host
+GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmodel, int nkm_, const double* k_interp, int nki)
+    : ctx(&c), cfg(cfg_), nkm(nkm_), nk_interp(nki)
+{
+    PRSD_REQUIRE(nkm >= 4 && nkm <= 1024, "GalaxyModel: model grid size %d outside [4, 1024]", nkm);
+    PRSD_REQUIRE(cfg.max_mu == 0 || cfg.max_mu == 2 || cfg.max_mu == 4 || cfg.max_mu == 6, "`max_mu` must be one of [0, 2, 4, 6]");
+    PRSD_REQUIRE(cfg.fog_model >= 0 && cfg.fog_model <= 2, "unknown FOG model %d", cfg.fog_model);
+    km.assign(kmodel, kmodel + nkm);
+    for (int i = 0; i < nkm; i++) PRSD_REQUIRE(km[i] > 0 && (i == 0 || km[i] > km[i - 1]), "model k grid must be positive and increasing");
+    d_km.upload(km, c.stream);
+    // GP_NK log-spaced points between the ends of the model grid (power_biased.py:357)
+    std::vector<double> ks(GAL_NSTOCH);
+    const double l0 = std::log10(km[0]), l1 = std::log10(km[nkm - 1]);
+    for (int i = 0; i < GAL_NSTOCH; i++) ks[i] = std::pow(10.0, l0 + (l1 - l0)*i/(GAL_NSTOCH - 1));
+    d_kstoch.upload(ks, c.stream);
+    d_kinterp.upload(k_interp, nki, c.stream);
+    zel.build(c, km.data(), nkm);
+    c.sync();
+}
+
+void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
+                        int npts, const double* d_k, const double* d_mu, double* d_out)
+{
+    Context& c = *ctx;
+    cudaStream_t s = c.stream;
+    PRSD_REQUIRE(nw > 0 && npts > 0, "GalaxyModel::power: empty request");
+    PRSD_REQUIRE(pt.nk == nk_interp, "GalaxyModel::power: PT tables are on %d k, model expects %d", pt.nk, nk_interp);
+    PRSD_REQUIRE(sp.have_oneloop, "GalaxyModel::power: the PT stage has not been run for this batch");
+    const int nc = sp.ncosmo;
+    std::vector<int> hmap(nw);
+    std::vector<double> r1(nw), r2(nw);
+    for (int w = 0; w < nw; w++) {
+        hmap[w] = cmap ? cmap[w] : w;
+        PRSD_REQUIRE(hmap[w] >= 0 && hmap[w] < nc, "walker %d maps to cosmology %d (batch has %d)", w, hmap[w], nc);
+        const double* p = par + (size_t)w*GAL_NPAR;
+        PRSD_REQUIRE(p[W_S8Z] > 0 && p[W_S80] > 0 && p[W_D] > 0, "walker %d: sigma8_z, sigma8 and D must be positive", w);
+        PRSD_REQUIRE(p[W_APAR] > 0 && p[W_APERP] > 0, "walker %d: AP parameters must be positive", w);
+        const double n1 = p[W_S8Z]/p[W_S80], n2 = n1/p[W_D];
+        r1[w] = n1*n1;
+        r2[w] = n2*n2;
+    }
+    d_cmap.upload(hmap, s);
+    d_par.upload(par, (size_t)nw*GAL_NPAR, s);
+    d_stoch.upload(stoch, (size_t)nw*GAL_NPAIR*GAL_NSTOCH, s);
+    ratio1.upload(r1, s);
+    ratio2.upload(r2, s);
+
+    // ---- per-cosmology: not-a-knot splines of every PT table on k_interp (rsd/_cache.py:344-389)
+    const int nk = nk_interp;
+    ptspl.ensure((size_t)nc*PT_NROWS*5*nk);
+    {
+        const size_t smem = (size_t)7*nk*sizeof(double);
+        if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_nak_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        struct Src { const double* p; int rows; int off; };
+        const Src srcs[5] = {{pt.I.p, 16, PT_I}, {pt.J.p, 6, PT_J}, {pt.K.p, 13, PT_K}, {pt.ML.p, 21, PT_ML}, {pt.sigmasq_k.p, 1, PT_SIGK}};
+        for (const Src& sr : srcs) {
+            k_nak_rows<<<dim3(sr.rows, nc), 64, smem, s>>>(nk, d_kinterp.p, sr.p, sr.rows, sr.off, ptspl.p);
+            c.launches++;
+        }
+        PRSD_CUDA(cudaGetLastError());
+    }
+    // ---- P_L on the model grid (z = 0 normalisation of the batch)
+    plin_m.ensure((size_t)nc*nkm);
+    k_plin_model<<<dim3((nkm + 127)/128, nc), 128, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, nkm, d_km.p, plin_m.p);
+    c.launches++;
+    // ---- Zel'dovich terms on the model grid at sigma8_z and at sigma8_z / D (Jennings fits)
+    DevBuf<double> plin_w((size_t)nw*nkm), plin_w2((size_t)nw*nkm);
+    k_scale_rows<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(nkm, plin_m.p, ratio1.p, d_cmap.p, plin_w.p);
+    k_scale_rows<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(nkm, plin_m.p, ratio2.p, d_cmap.p, plin_w2.p);
+    c.launches += 2;
+    zel1.ensure((size_t)nw*3*nkm);
+    zel2.ensure((size_t)nw*3*nkm);
+    zeldovich_eval_map(c, zel, nw, d_cmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio1.p, true, cfg.k0_low,
+                       plin_w.p, pt.scalars.p + 2, 4, zel1.p);
+    zeldovich_eval_map(c, zel, nw, d_cmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio2.p, true, cfg.k0_low,
+                       plin_w2.p, pt.scalars.p + 2, 4, zel2.p);
+
+    GalDev G;
+    G.cfg = cfg;
+    G.nkm = nkm; G.nk = nk; G.nspl = sp.nspl;
+    G.lnkm0 = std::log(km[0]); G.inv_dlnkm = (nkm - 1)/std::log(km[nkm - 1]/km[0]);
+    {
+        std::vector<double> ki(nk);
+        PRSD_CUDA(cudaMemcpyAsync(ki.data(), d_kinterp.p, nk*sizeof(double), cudaMemcpyDeviceToHost, s));
+        c.sync();
+        G.lnki0 = std::log(ki[0]); G.inv_dlnki = (nk - 1)/std::log(ki[nk - 1]/ki[0]);
+    }
+    G.lnk1l0 = std::log(ONELOOP_KMIN); G.inv_dlnk1l = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
+
+    base.ensure((size_t)nw*NB*nkm);
+    k_gal_base<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_cmap.p, d_par.p, ptspl.p, plin_m.p, sp.oneloop_spl.p,
+                                                         pt.scalars.p, zel1.p, zel2.p, base.p);
+    PRSD_CUDA(cudaGetLastError());
+    c.launches++;
+    pairspl.ensure((size_t)nw*GAL_NPAIR*16*nkm);
+    {
+        const size_t smem = (size_t)(25*nkm + 7*GAL_NSTOCH)*sizeof(double);
+        if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gal_moments<<<dim3(GAL_NPAIR, nw), 128, smem, s>>>(G, d_km.p, d_kstoch.p, d_cmap.p, d_par.p, d_stoch.p, pt.scalars.p,
+                                                             base.p, pairspl.p);
+        PRSD_CUDA(cudaGetLastError());
+        c.launches++;
+    }
+    k_gal_pkmu<<<dim3((npts + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_par.p, pairspl.p, npts, d_k, d_mu, d_out);
+    PRSD_CUDA(cudaGetLastError());
+    c.launches++;
+    c.sync();
+}
+
+void GalaxyModel::moments_to_host(int nw, double* out)
+{
+    std::vector<double> tmp((size_t)nw*GAL_NPAIR*16*nkm);
+    pairspl.download(tmp.data(), tmp.size(), ctx->stream);
+    ctx->sync();
+    for (int w = 0; w < nw; w++)
+        for (int p = 0; p < GAL_NPAIR; p++)
+            for (int m = 0; m < 4; m++)
+                for (int i = 0; i < nkm; i++)
+                    out[(((size_t)w*GAL_NPAIR + p)*4 + m)*nkm + i] = tmp[((size_t)w*GAL_NPAIR + p)*16*nkm + (size_t)(m*4)*nkm + i];
+}
+
+} // namespace prsd

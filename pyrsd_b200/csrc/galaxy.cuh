@@ -1,0 +1,60 @@
+// galaxy.cuh -- GalaxySpectrum P(k, mu) assembly on the device.
+//
+// Device restatement of the reference's Python model layer for the default galaxy model:
+//   dark-matter terms    pyRSD/rsd/power/dm/P00.py .. P22.py, power_dm.py:676-718, 848-884
+//   halo (biased) terms  pyRSD/rsd/power/biased/P00.py .. P22.py, power_biased.py:325-525
+//   HZPT broadband       pyRSD/rsd/hzpt/__init__.py:185-287, P01.py:57-104, P11.py:86-129, Phm.py:195-235
+//   galaxy sum, FOG, AP  pyRSD/rsd/power/gal/__init__.py:24-40, core.py:159-233, fog_kernels.py:40-84,
+//                        Pcc/__init__.py:39-60, rsd/tools.py:54-75, 166-222
+// Three kernels per batch of walkers:
+//   k_gal_base   : every cosmology-level quantity on the model k grid (one thread per k)
+//   k_gal_moments: P[mu^0], P[mu^2], P[mu^4] (, P[mu^6]) of the 10 (b1, b1_bar) pairs and their
+//                  not-a-knot splines (the reference's RSDSpline on self.k)
+//   k_gal_pkmu   : AP remap, spline evaluation, FOG damping, weighted sum of the 10 sub-spectra
+#pragma once
+#include "plan.cuh"
+#include "zeldovich.cuh"
+
+namespace prsd {
+
+static const int GAL_NPAR = 48;        // doubles per walker, see include/pyrsd_b200.h
+static const int GAL_NPAIR = 10;
+static const int GAL_NSTOCH = 20;      // GP_NK of power_biased.py:24
+
+struct GalaxyConfig {
+    int max_mu;                 // 0, 2, 4 or 6
+    int fog_model;              // 0 modified_lorentzian, 1 lorentzian, 2 gaussian
+    int use_P00_model, use_P01_model, use_P11_model, use_Pdv_model, use_Pvv_model, use_Phm_model;
+    int use_tidal_bias, use_so_correction;
+    double k0_low;              // low-k transition of the Zel'dovich drivers (5e-3)
+    double hz00[10];            // A0(amp, alpha) R R1 R1h R2h of HaloZeldovichBase.default_parameters
+    double hz11[9];             // A0(amp, alpha, beta) R R1h of HaloZeldovichP11.default_parameters
+    double hzhm[20];            // A0 R1 R1h R2h R (amp, alpha, beta, run) of HaloMatterBase.default_parameters
+};
+void galaxy_config_default(GalaxyConfig& c);
+
+struct GalaxyModel {
+    Context* ctx;
+    GalaxyConfig cfg;
+    int nkm = 0;
+    std::vector<double> km;             // model k grid (numpy.logspace(log10 kmin, log10 kmax, Nk))
+    DevBuf<double> d_km, d_kstoch;
+    ZelPlan zel;                        // Zel'dovich stencils for the model grid
+    int nk_interp = 0;
+    DevBuf<double> d_kinterp;
+    // scratch
+    DevBuf<double> ptspl, zel1, zel2, plin_m, ratio1, ratio2, base, pairspl, d_par, d_stoch, ol_m;
+    DevBuf<int> d_cmap;
+
+    GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmodel, int nkm_, const double* k_interp, int nk_interp_);
+
+    // P(k, mu) of `nw` walkers: walker w uses the tables of cosmology cmap[w] in (sp, pt).
+    //   par    host [nw][GAL_NPAR]      stoch  host [nw][10][20]
+    //   k, mu  host [npts] (paired)     out    DEVICE [nw][npts]
+    void power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
+               int npts, const double* d_k, const double* d_mu, double* d_out);
+    // diagnostic: the spline knots of P[mu^0,2,4,6] per (walker, pair): host [nw][10][4][nkm]
+    void moments_to_host(int nw, double* out);
+};
+
+} // namespace prsd

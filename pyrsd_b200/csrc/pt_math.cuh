@@ -272,6 +272,83 @@ PRSD_HD double cubic_spline_eval_log(int n, const double* spl, double lnx0, doub
     return spl[n + i] + t*(spl[2*n + i] + t*(spl[3*n + i] + t*spl[4*n + i]));
 }
 
+// Not-a-knot cubic spline (what SciPy's InterpolatedUnivariateSpline(k=3) / FITPACK build, used by
+// the reference's RSDSpline, pyRSD/rsd/tools.py:331-388).  Output in the same piecewise layout as
+// cubic_spline_build: y = Y[i] + b t + c t^2 + d t^3 on [X[i], X[i+1]].  `M` and `w` are work
+// arrays of length n (n >= 4).
+PRSD_HD void nak_spline_build(int n, const double* X, const double* Y, double* b, double* c, double* d,
+                              double* M, double* w)
+{
+    // interior equations for the second derivatives M_1 .. M_{n-2}; M_0 and M_{n-1} eliminated with
+    // the not-a-knot conditions (continuous third derivative at X[1] and X[n-2])
+    const int m = n - 2;                // unknowns M_1..M_{n-2} stored at M[1..n-2]
+    // diagonal in b[], super-diagonal in c[], sub-diagonal in d[], rhs in M[]
+    for (int i = 1; i <= m; i++) {
+        const double h0 = X[i] - X[i - 1], h1 = X[i + 1] - X[i];
+        b[i] = 2.0*(h0 + h1);
+        c[i] = h1;
+        d[i] = h0;
+        M[i] = 6.0*((Y[i + 1] - Y[i])/h1 - (Y[i] - Y[i - 1])/h0);
+    }
+    {
+        const double h0 = X[1] - X[0], h1 = X[2] - X[1];
+        b[1] += h0*(1.0 + h0/h1);
+        c[1] -= h0*h0/h1;
+        const double hn = X[n - 1] - X[n - 2], hm = X[n - 2] - X[n - 3];
+        b[m] += hn*(1.0 + hn/hm);
+        d[m] -= hn*hn/hm;
+    }
+    // Thomas algorithm
+    w[1] = c[1]/b[1];
+    M[1] = M[1]/b[1];
+    for (int i = 2; i <= m; i++) {
+        const double den = b[i] - d[i]*w[i - 1];
+        w[i] = c[i]/den;
+        M[i] = (M[i] - d[i]*M[i - 1])/den;
+    }
+    for (int i = m - 1; i >= 1; i--) M[i] -= w[i]*M[i + 1];
+    {
+        const double h0 = X[1] - X[0], h1 = X[2] - X[1];
+        M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
+        const double hn = X[n - 1] - X[n - 2], hm = X[n - 2] - X[n - 3];
+        M[n - 1] = M[n - 2] + (hn/hm)*(M[n - 2] - M[n - 3]);
+    }
+    for (int i = 0; i < n - 1; i++) {
+        const double h = X[i + 1] - X[i];
+        b[i] = (Y[i + 1] - Y[i])/h - h*(2.0*M[i] + M[i + 1])/6.0;
+        c[i] = 0.5*M[i];
+        d[i] = (M[i + 1] - M[i])/(6.0*h);
+    }
+    b[n - 1] = b[n - 2]; c[n - 1] = c[n - 2]; d[n - 1] = d[n - 2];
+}
+
+// piecewise-cubic evaluation on knots that are (near-)uniform in ln x; no range check
+PRSD_HD double pw_cubic_eval_log(int n, const double* X, const double* Y, const double* b, const double* c,
+                                 const double* d, double lnx0, double inv_dlnx, double x)
+{
+    int i = (int)((log(x) - lnx0)*inv_dlnx);
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    while (i > 0 && x < X[i]) --i;
+    while (i < n - 2 && x > X[i + 1]) ++i;
+    const double t = x - X[i];
+    return Y[i] + t*(b[i] + t*(c[i] + t*d[i]));
+}
+
+// Cubic spline on arbitrary increasing knots (binary search), 0 outside the domain like
+// Spline::Evaluate (Spline.cpp:362-367); spl = [X | Y | b | c | d].
+PRSD_HD double cubic_spline_eval_bsearch(int n, const double* spl, double x)
+{
+    if (!(x >= spl[0]) || x > spl[n - 1]) return 0.0;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (spl[mid] <= x) lo = mid; else hi = mid;
+    }
+    const double t = x - spl[lo];
+    return spl[n + lo] + t*(spl[2*n + lo] + t*(spl[3*n + lo] + t*spl[4*n + lo]));
+}
+
 // Fill the Eisenstein-Hu no-wiggle parameters used for the extrapolation of T(k)
 // (Cosmology.cpp:311-362) and the spline end-point ratios (Cosmology.cpp:288-300).
 PRSD_HD void plin_params_init(PlinParams& p, int n, const double* k, const double* T, double ns,

@@ -22,10 +22,10 @@ namespace prsd {
 
 struct QuadConfig {
     double qmin     = 1e-8;   // lower cut of the outer variable [h/Mpc]
-    int    n_outer  = 8;      // Gauss-Legendre points per outer panel
+    int    n_outer  = 12;     // Gauss-Legendre points per outer panel
     int    n_inner  = 8;      // Gauss-Legendre points per inner panel
     double ln_far   = 2.0;    // max panel width in ln q, featureless power-law regions
-    double ln_mid   = 0.8;    // max panel width in ln q for mid_lo <= q <= mid_hi
+    double ln_mid   = 0.5;    // max panel width in ln q for mid_lo <= q <= mid_hi
     double mid_lo   = 1e-3;
     double mid_hi   = 2.0;
     double bao_lo   = 0.01;   // panels at most bao_dq wide in q (not ln q) in the BAO range

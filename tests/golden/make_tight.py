@@ -1,0 +1,107 @@
+"""Generate ``tests/golden/oracle_tight.npz``: the reference C++ (oracle/_ref) run at TIGHT
+``epsrel`` on the golden Planck15 transfer function.
+
+Why: at its default epsrel (1e-4 / 1e-3) the reference's adaptive cubature is only accurate to
+3e-4 .. 5e-3, so 1e-5 parity is defined against the same code at tight
+tolerance (``epsrel`` is a public constructor argument of Imn/Jmn/Kmn/ImnOneLoop/OneLoopPS).
+Integrals whose tolerances are hard-coded literals in the reference (sigma_v, X_Zel, Y_Zel, Q3,
+velocity kurtosis) go through oracle/ref_shim.cpp's ``*_tol`` entry points: same integrands, same
+reference quadrature templates, caller-chosen tolerance.
+
+Run in the build container only:   python tests/golden/make_tight.py   (takes several minutes)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import gcl_ref as R  # noqa: E402
+
+EPS2D = 1e-9
+EPS1D = 1e-10
+
+
+def main():
+    g = np.load(os.path.join(HERE, 'golden_pt.npz'))
+    cosmo = R.golden_cosmology(g)
+    PL = R.RefLinearPS(cosmo)
+    out = {'delta_H': cosmo.delta_H(), 'Omega0_m': cosmo.args[5], 'Tcmb': cosmo.args[7]}
+
+    # 20 k values: a spread of k_interp points plus high-k points of the one-loop grid
+    kint = g['k_interp']
+    k = np.concatenate([kint[[0, 30, 60, 100, 130, 150, 170, 185, 195, 205, 215, 225, 235, 242, 249]],
+                        [1.7, 3.0, 6.0, 10.0]])
+    out['k'] = k
+    out['plin_k'] = PL(k)
+    t0 = time.time()
+    I = np.empty((16, len(k)))
+    for m in range(4):
+        for n in range(4):
+            I[4*m + n] = R.Imn(PL, k, m, n, epsrel=EPS2D)
+    out['I'] = I
+    print('I done %.0fs' % (time.time() - t0), flush=True)
+    J = np.empty((6, len(k)))
+    for j, (m, n) in enumerate([(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (2, 0)]):
+        J[j] = R.Jmn(PL, k, m, n, epsrel=EPS1D)
+    out['J'] = J
+    Kspec = [(0, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 1, 1, 0), (0, 2, 1, 0), (1, 0, 0, 0), (1, 1, 0, 0),
+             (1, 0, 1, 0), (1, 1, 1, 0), (2, 0, 0, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1)]
+    K = np.empty((13, len(k)))
+    for j, (m, n, tid, part) in enumerate(Kspec):
+        K[j] = R.Kmn(PL, k, m, n, bool(tid), part, epsrel=EPS2D)
+    out['K'] = K
+    print('K done %.0fs' % (time.time() - t0), flush=True)
+
+    # 1-D integrals with hard-coded tolerances in the reference
+    out['sigma_v2'] = PL.sigv_tol()
+    out['sigmasq_k'] = np.array([PL.sigv_tol(0.5*kk) for kk in k])
+    r = np.array([0.01, 0.03, 0.1, 0.3, 1., 3., 10., 20., 40., 60., 80., 100., 105., 110., 130., 150., 200., 300.,
+                  500., 1000., 3000., 1e4, 3e4, 1e5])
+    out['r'] = r
+    out['X_Zel'] = PL.X_Zel(r, 1e-10, 1e-14)
+    out['Y_Zel'] = PL.Y_Zel(r, 1e-10, 1e-14)
+    out['Q3_at_k1'] = PL.Q3_tol([1.0])[0]
+    out['Sigma_R'] = np.array([1., 4., 8., 16., 50.])
+    out['Sigma'] = PL.Sigma_tol(out['Sigma_R'])
+    print('1-D done %.0fs' % (time.time() - t0), flush=True)
+
+    # ImnOneLoop at tight eps, with the GOLDEN (default-eps) one-loop tables as common input
+    ol = {w: R.RefOneLoop(PL, w, 1e-4, g['oneloop_P%s_0' % w]) for w in ('dd', 'dv', 'vv', '22bar')}
+    out['kurtosis_golden_tables'] = ol['22bar'].VelocityKurtosis(1e-10)
+    kml = kint[[60, 130, 170, 195, 215, 235, 249]]
+    out['k_ml'] = kml
+    spec = [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
+            ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]
+    ML = np.empty((7, 3, len(kml)))
+    for j, (p1, p2, m, n) in enumerate(spec):
+        for w, which in enumerate(('linear', 'cross', 'oneloop')):
+            ML[j, w] = R.ImnOneLoop(ol[p1], None if p2 is None else ol[p2], kml, m, n, which, epsrel=1e-8)
+        print('ML %d done %.0fs' % (j, time.time() - t0), flush=True)
+    out['ML'] = ML
+
+    # tight one-loop tables on a sparse subset of the 1000-point grid
+    k1 = R.logspace(1e-5, 10, 1000)
+    idx = np.arange(0, 1000, 37)
+    idx = np.unique(np.concatenate([idx, [999]]))
+    out['oneloop_idx'] = idx
+    kk = k1[idx]
+    P = PL(kk)
+    OL = np.empty((4, len(idx)))
+    for j, (a, b) in enumerate([(0, 0), (0, 1), (1, 1)]):
+        OL[j] = 2*R.Imn(PL, kk, a, b, epsrel=EPS2D) + 6*kk**2*R.Jmn(PL, kk, a, b, epsrel=EPS1D)*P
+    OL[3] = R.Imn(PL, kk, 2, 3, epsrel=EPS2D) + (2./3)*R.Imn(PL, kk, 3, 2, epsrel=EPS2D) + 0.2*R.Imn(PL, kk, 3, 3, epsrel=EPS2D)
+    out['oneloop'] = OL
+    out['oneloop_plin'] = P
+    print('one-loop done %.0fs' % (time.time() - t0), flush=True)
+
+    path = os.path.join(HERE, 'oracle_tight.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, '%.1f kB' % (os.path.getsize(path)/1e3))
+
+
+if __name__ == '__main__':
+    main()

@@ -125,3 +125,38 @@ extern "C" void emul_linear(int type, int sub, int n, const double* param, const
         out[o] = acc;
     }
 }
+
+// same as emul_ik (Imn convention, symmetric kernels only) but with P_L evaluated exactly at the
+// nodes instead of read from the table: isolates the quadrature error from the table error.
+extern "C" void emul_ik_exactP(int kid, int nk, const double* k, double qmax, int n, const double* ki, const double* Ti,
+                               double ns, double amp, double h, double Om, double Ob, double Tcmb, double* out)
+{
+    PlinParams p;
+    plin_params_init(p, n, ki, Ti, ns, amp, h, Om, Ob, Tcmb);
+    std::vector<double> spl(5*n);
+    for (int i = 0; i < n; i++) { spl[i] = ki[i]; spl[n + i] = Ti[i]; }
+    cubic_spline_build(n, &spl[0], &spl[n], &spl[2*n], &spl[3*n], &spl[4*n]);
+    HalfNodes H;
+    build_half_nodes(k, nk, qmax, g_cfg, g_grid, H);
+    for (int ik = 0; ik < nk; ik++) {
+        const double kk = k[ik];
+        double pos = 0.0;
+        int32_t last_o = -1; double Pa = 0;
+        for (int64_t j = H.node_off[ik]; j < H.node_off[ik+1]; j++) {
+            const int32_t o = H.n_outer[j];
+            const double a = H.a[o], b = H.b[j];
+            if (o != last_o) { Pa = plin_eval(p, spl.data(), a); last_o = o; }
+            if (H.wgt[j] == 0.0) continue;
+            pos += H.wgt[j]*Pa*plin_eval(p, spl.data(), b)*pt_kernel(kid, (a + b)/kk, (b - a)/kk, 2*a/kk, 2*b/kk);
+        }
+        out[ik] = 2*kk/(8*M_PI*M_PI)*pos;
+    }
+}
+
+extern "C" void emul_nak_spline(int n, const double* x, const double* y, int nq, const double* xq, double* out)
+{
+    std::vector<double> b(n), c(n), d(n), M(n), w(n);
+    nak_spline_build(n, x, y, b.data(), c.data(), d.data(), M.data(), w.data());
+    const double lnx0 = std::log(x[0]), inv = (n - 1)/std::log(x[n-1]/x[0]);
+    for (int i = 0; i < nq; i++) out[i] = pw_cubic_eval_log(n, x, y, b.data(), c.data(), d.data(), lnx0, inv, xq[i]);
+}
