@@ -45,7 +45,7 @@ int prsd_ctx_stream(prsd_ctx* ctx, void** cuda_stream);
 int prsd_knot_grid(int* n, double* lnq /* may be NULL */);
 
 /* ---- quadrature configuration: cfg[9] = {qmin, n_outer, n_inner, ln_far, ln_mid,
- *      bao_lo, bao_hi, bao_dq, reserved}.  Replaces the reference's `epsrel` constructor
+ *      bao_lo, bao_hi, bao_dq, ln_inner}.  Replaces the reference's `epsrel` constructor
  *      argument (Imn.i:8, Jmn.i:8, Kmn.i:8): accuracy is set by the fixed rule. */
 int prsd_quad_config_default(double* cfg9);
 
@@ -64,6 +64,17 @@ int prsd_spectra_table(prsd_spectra* sp, int kind, double* out /*[ncosmo][n_knot
 int prsd_spectra_set_oneloop(prsd_spectra* sp, const double* tables /*[ncosmo][4][1000]*/);
 int prsd_spectra_oneloop_eval(prsd_spectra* sp, int which, int full, int nq, const double* q,
                               double* out /*[ncosmo][nq]*/);
+
+/* OneLoopPdd/Pdv/Pvv/P22Bar(P_L) constructors: compute the four 1000-point one-loop tables of every
+ * cosmology of the batch (OneLoopPS.cpp:56-185), install them in `sp`; out (may be NULL) [ncosmo][4][1000] */
+int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg9, double* out);
+/* OneLoopPS(P_L, epsrel, oneloop_power): install ONE table, host [ncosmo][1000] */
+int prsd_spectra_set_oneloop_one(prsd_spectra* sp, int which, const double* table);
+int prsd_spectra_get_oneloop(prsd_spectra* sp, double* out /*[ncosmo][4][1000]*/);
+/* CubicSpline(x, y)(xq) -- netlib cubic spline of the reference (Spline.cpp:211-273), 0 outside the
+ * domain (:362-367); y [batch][n] on shared x [n] */
+int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, const double* y, int nq,
+                           const double* xq, double* out /*[batch][nq]*/);
 
 /* ---- one-off evaluations with the call shapes of the pygcl drivers ------------------- */
 /* Imn(P_L)(k, m, n)  [Imn.i:8-14, Imn.cpp:142-189] */
@@ -160,6 +171,16 @@ int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
                              const double* d_mu, double* d_out);
 /* spline knots of P[mu^0], P[mu^2], P[mu^4], P[mu^6] of the last call: out [nw][10][4][nkm] */
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
+
+/* ---- measurement support (bench.py) -------------------------------------------------- */
+/* per-kernel-family CUDA-event timing on the context's stream; families: 0 bilinear (DMMA contraction),
+ * 1 linear operators, 2 Zel'dovich, 3 galaxy assembly, 4 spline builds, 5 FFTLog */
+int prsd_ctx_profile(prsd_ctx* ctx, int enable);      /* also resets the counters */
+int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms6, long long* count6);
+/* FP64 pipe microbenchmarks: mode 0 DFMA, mode 1 DMMA m8n8k4 (TFLOP/s, best of 4) */
+int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops);
+/* rebuild the linear spectra of a batch from DEVICE-resident k, T [ncosmo][nspl], pars [ncosmo][8] */
+int prsd_spectra_reload_device(prsd_spectra* sp, const double* d_k, const double* d_T, const double* d_pars);
 
 #ifdef __cplusplus
 }

@@ -236,6 +236,7 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
     PRSD_REQUIRE(smem <= ctx.smem_optin, "bilinear apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_bilinear_apply<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(g.nk, ntiles);
+    ProfScope prof(ctx, PROF_BILINEAR);
     k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, g.max_outer, g.outer_off.p, g.node_off.p,
         g.a_j0.p, g.a_coef.p, g.b_j0.p, g.n_outer_local.p, g.b_coef.p, op.W.p, tables, slot_tab, rowA, rowB, out);
     PRSD_CUDA(cudaGetLastError());

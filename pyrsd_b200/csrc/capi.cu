@@ -9,6 +9,7 @@
 #include <mutex>
 
 using namespace prsd;
+namespace prsd { double fp64_peak_tflops(Context& ctx, int mode); }
 
 struct prsd_ctx { Context c; explicit prsd_ctx(int d) : c(d) {} };
 struct prsd_spectra { SpectraBatch s; prsd_spectra(Context& c, int nc, int ns, const double* k, const double* T, const double* p) : s(c, nc, ns, k, T, p) {} };
@@ -47,6 +48,7 @@ static QuadConfig cfg_from(const double* c9)
     if (c9) {
         q.qmin = c9[0]; q.n_outer = (int)c9[1]; q.n_inner = (int)c9[2]; q.ln_far = c9[3]; q.ln_mid = c9[4];
         q.bao_lo = c9[5]; q.bao_hi = c9[6]; q.bao_dq = c9[7];
+        if (c9[8] > 0) q.ln_inner = c9[8];
         PRSD_REQUIRE(q.qmin >= 1e-8 && q.qmin < 1e-5, "quadrature config: qmin = %g outside [1e-8, 1e-5)", q.qmin);
         PRSD_REQUIRE(q.n_outer >= 2 && q.n_outer <= 64 && q.n_inner >= 2 && q.n_inner <= 64, "quadrature config: bad point counts");
         PRSD_REQUIRE(q.ln_far > 0 && q.ln_mid > 0 && q.bao_dq > 0, "quadrature config: widths must be positive");
@@ -202,7 +204,7 @@ int prsd_quad_config_default(double* c9)
         PRSD_REQUIRE(c9, "null argument");
         QuadConfig q;
         c9[0] = q.qmin; c9[1] = q.n_outer; c9[2] = q.n_inner; c9[3] = q.ln_far; c9[4] = q.ln_mid;
-        c9[5] = q.bao_lo; c9[6] = q.bao_hi; c9[7] = q.bao_dq; c9[8] = 0.0;
+        c9[5] = q.bao_lo; c9[6] = q.bao_hi; c9[7] = q.bao_dq; c9[8] = q.ln_inner;
     });
 }
 
@@ -615,6 +617,92 @@ int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
 {
     return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });
+}
+
+
+/* -------------------------------------------- one-loop tables for the pygcl-style classes */
+int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg9, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(sp, "null argument");
+        Context& c = *sp->s.ctx;
+        const QuadConfig cfg = cfg_from(cfg9);
+        static std::mutex mu;
+        static std::list<std::pair<std::pair<int, QuadConfig>, std::shared_ptr<PTPlan>>> cache;
+        std::shared_ptr<PTPlan> plan;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            for (auto& e : cache)
+                if (e.first.first == c.device && std::memcmp(&e.first.second, &cfg, sizeof(QuadConfig)) == 0) { plan = e.second; break; }
+            if (!plan) {
+                plan = std::make_shared<PTPlan>(c, nullptr, 0, cfg, false, false, true);
+                cache.emplace_front(std::make_pair(c.device, cfg), plan);
+                while (cache.size() > 2) cache.pop_back();
+            }
+        }
+        PTResult res;
+        plan->run_oneloop(sp->s, res);
+        if (out) sp->s.get_oneloop_tables(out);
+    });
+}
+
+int prsd_spectra_set_oneloop_one(prsd_spectra* sp, int which, const double* table)
+{
+    return guarded([&] { PRSD_REQUIRE(sp && table, "null argument"); sp->s.set_oneloop_table(which, table); });
+}
+
+int prsd_spectra_get_oneloop(prsd_spectra* sp, double* out)
+{
+    return guarded([&] { PRSD_REQUIRE(sp && out, "null argument"); sp->s.get_oneloop_tables(out); });
+}
+
+/* CubicSpline(x, y)(xq)  [Spline.i, Spline.cpp:211-273, 362-367]: netlib cubic spline, 0 outside the domain */
+int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, const double* y, int nq, const double* xq, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && x && y && xq && out, "null argument");
+        PRSD_REQUIRE(batch > 0 && nq > 0, "CubicSpline: empty request");
+        for (int i = 1; i < n; i++) PRSD_REQUIRE(x[i] > x[i - 1], "CubicSpline: abscissae must be increasing");
+        DevBuf<double> dy;
+        dy.upload(y, (size_t)batch*n, ctx->c.stream);
+        DevBuf<double> dout((size_t)batch*nq);
+        spline_eval_host_x(ctx->c, batch, n, x, dy.p, nq, xq, dout.p);
+        dout.download(out, (size_t)batch*nq, ctx->c.stream);
+        ctx->c.sync();
+    });
+}
+
+
+/* ----------------------------------------------------- measurement support */
+int prsd_ctx_profile(prsd_ctx* ctx, int enable)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx, "null argument");
+        ctx->c.prof_reset();
+        ctx->c.profiling = enable != 0;
+    });
+}
+
+int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms6, long long* count6)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && ms6 && count6, "null argument");
+        ctx->c.prof_collect();
+        for (int t = 0; t < PROF_NTAGS; t++) { ms6[t] = ctx->c.prof_ms[t]; count6[t] = ctx->c.prof_count[t]; }
+    });
+}
+
+int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && tflops && (mode == 0 || mode == 1), "bad argument");
+        *tflops = fp64_peak_tflops(ctx->c, mode);
+    });
+}
+
+int prsd_spectra_reload_device(prsd_spectra* sp, const double* d_k, const double* d_T, const double* d_pars)
+{
+    return guarded([&] { PRSD_REQUIRE(sp && d_k && d_T && d_pars, "null argument"); sp->s.reload_device(d_k, d_T, d_pars); });
 }
 
 } // extern "C"

@@ -94,15 +94,41 @@ struct DevBuf {
     void zero(cudaStream_t s) { if (n) PRSD_CUDA(cudaMemsetAsync(p, 0, n*sizeof(T), s)); }
 };
 
+enum ProfTag { PROF_BILINEAR = 0, PROF_LINEAR, PROF_ZELDOVICH, PROF_GALAXY, PROF_SPLINE, PROF_FFTLOG, PROF_NTAGS };
+
 struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     size_t smem_optin = 0;
     long long launches = 0;        // kernels launched through this context (bench bookkeeping)
+    // optional per-kernel-family timing with CUDA events on `stream` (bench.py roofline)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending[PROF_NTAGS];
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[PROF_NTAGS] = {0};
+    long long prof_count[PROF_NTAGS] = {0};
     explicit Context(int dev);
     ~Context();
     void sync() { PRSD_CUDA(cudaStreamSynchronize(stream)); }
+    cudaEvent_t prof_event();
+    void prof_collect();           // sync + fold pending event pairs into prof_ms / prof_count
+    void prof_reset();
+};
+
+// records a start event at construction and a stop event at destruction when profiling is on
+struct ProfScope {
+    Context& c;
+    int tag;
+    cudaEvent_t e0 = nullptr;
+    ProfScope(Context& ctx, int t) : c(ctx), tag(t)
+    {
+        if (c.profiling) { e0 = c.prof_event(); cudaEventRecord(e0, c.stream); }
+    }
+    ~ProfScope()
+    {
+        if (e0) { cudaEvent_t e1 = c.prof_event(); cudaEventRecord(e1, c.stream); c.prof_pending[tag].push_back({e0, e1}); }
+    }
 };
 
 } // namespace prsd

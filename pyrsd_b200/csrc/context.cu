@@ -24,7 +24,38 @@ Context::Context(int dev) : device(dev)
 
 Context::~Context()
 {
+    for (int t = 0; t < PROF_NTAGS; t++)
+        for (auto& pr : prof_pending[t]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+}
+
+cudaEvent_t Context::prof_event()
+{
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    PRSD_CUDA(cudaEventCreate(&e));
+    return e;
+}
+
+void Context::prof_collect()
+{
+    sync();
+    for (int t = 0; t < PROF_NTAGS; t++) {
+        for (auto& pr : prof_pending[t]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { prof_ms[t] += ms; prof_count[t]++; }
+            prof_pool.push_back(pr.first);
+            prof_pool.push_back(pr.second);
+        }
+        prof_pending[t].clear();
+    }
+}
+
+void Context::prof_reset()
+{
+    prof_collect();
+    for (int t = 0; t < PROF_NTAGS; t++) { prof_ms[t] = 0; prof_count[t] = 0; }
 }
 
 } // namespace prsd

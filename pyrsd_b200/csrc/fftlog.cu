@@ -178,6 +178,7 @@ void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, do
 {
     if (batch <= 0) return;
     const int N = p.N;
+    ProfScope prof(ctx, PROF_FFTLOG);
     if (p.pow2) {
         int logN = 0;
         while ((1 << logN) < N) logN++;

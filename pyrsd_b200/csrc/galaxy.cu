@@ -448,6 +448,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     const int nk = nk_interp;
     ptspl.ensure((size_t)nc*PT_NROWS*5*nk);
     {
+        ProfScope prof(c, PROF_SPLINE);
         const size_t smem = (size_t)7*nk*sizeof(double);
         if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_nak_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         struct Src { const double* p; int rows; int off; };
@@ -487,6 +488,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     G.lnk1l0 = std::log(ONELOOP_KMIN); G.inv_dlnk1l = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
 
     base.ensure((size_t)nw*NB*nkm);
+    ProfScope prof_gal(c, PROF_GALAXY);
     k_gal_base<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_cmap.p, d_par.p, ptspl.p, plin_m.p, sp.oneloop_spl.p,
                                                          pt.scalars.p, zel1.p, zel2.p, base.p);
     PRSD_CUDA(cudaGetLastError());

@@ -97,6 +97,7 @@ k_linear_apply(int nout, int nrow, const double* __restrict__ Omega, const doubl
 void LinearOp::apply(Context& ctx, const double* tables, const int* tab_index, int nrow, double* out) const
 {
     dim3 grid((nout + 4*LA_OUT - 1)/(4*LA_OUT), (nrow + LA_ROW - 1)/LA_ROW);
+    ProfScope prof(ctx, PROF_LINEAR);
     k_linear_apply<<<grid, 128, 0, ctx.stream>>>(nout, nrow, Omega.p, tables, tab_index, out);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;

@@ -51,12 +51,12 @@ static const int J_IDS[6] = {0, 1, 2, 3, 4, 6};                    // J00 J01 J0
 static const int NONSYM[8] = {KID_F03, KID_F10, KID_F13, KID_F22, KID_F30, KID_F31, KID_K11, KID_K11S};
 static const int ML_KID[N_ML] = {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33};
 
-PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel)
-    : ctx(&c), cfg(q), nk(nk_), with_ml(ml), with_zel(zel)
+PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l)
+    : ctx(&c), cfg(q), nk(nk_), with_ml(ml), with_zel(zel), only_oneloop(only1l)
 {
     auto t0 = std::chrono::steady_clock::now();
-    PRSD_REQUIRE(nk > 0, "PTPlan: empty k grid");
-    k_interp.assign(k, k + nk);
+    PRSD_REQUIRE(nk > 0 || only_oneloop, "PTPlan: empty k grid");
+    if (nk > 0) k_interp.assign(k, k + nk);
     k_1loop = oneloop_kgrid();
     r_zel = zeldovich_rgrid();
     const KnotGrid& grid = knot_grid();
@@ -69,7 +69,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         op_1loop.build(c, geo, cols);
     }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
-    {
+    if (!only_oneloop) {
         auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid);
         std::vector<ColSpec> cols;
         for (int id = 0; id < 16; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
@@ -78,7 +78,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         op_ik.build(c, geo, cols);
     }
     // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
-    if (with_ml) {
+    if (with_ml && !only_oneloop) {
         auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg, grid);
         std::vector<ColSpec> pos, neg;
         for (int id : ML_KID) { pos.push_back({id, +1, INV8PI2}); neg.push_back({id, -1, INV8PI2}); }
@@ -92,7 +92,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
             for (int i = 0; i < ONELOOP_N; i++) o.push_back({LK_JMN, id, k_1loop[i], 1e-5, 1e5, 1.0});
         lin_1loop.build(c, o);
     }
-    {
+    if (!only_oneloop) {
         std::vector<LinOutSpec> o;
         for (int j = 0; j < 6; j++)
             for (int i = 0; i < nk; i++) o.push_back({LK_JMN, J_IDS[j], k_interp[i], 1e-5, 1e5, 1.0});
@@ -110,10 +110,12 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         }
         lin_main.build(c, o);
     }
-    lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}});
-    lin_kurt.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}});
+    if (!only_oneloop) {
+        lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}});
+        lin_kurt.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}});
+        d_kinterp.upload(k_interp, c.stream);
+    }
     d_k1loop.upload(k_1loop, c.stream);
-    d_kinterp.upload(k_interp, c.stream);
     c.sync();
     build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -236,7 +238,7 @@ __global__ void k_plin_at(int nspl, const PlinParams* __restrict__ params, const
     out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
 }
 
-void PTPlan::run(SpectraBatch& sp, PTResult& res)
+void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res)
 {
     Context& c = *ctx;
     cudaStream_t s = c.stream;
@@ -277,6 +279,27 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
         c.launches += 2;
     }
     sp.set_oneloop_tables(res.oneloop.p);
+    c.sync();
+}
+
+void PTPlan::run(SpectraBatch& sp, PTResult& res)
+{
+    PRSD_REQUIRE(!only_oneloop, "this plan only holds the one-loop stage");
+    run_oneloop(sp, res);
+    Context& c = *ctx;
+    cudaStream_t s = c.stream;
+    const int nc = sp.ncosmo;
+    const int ntile = (nc + 7)/8;
+    std::vector<int> tabL(nc), tabSq(nc), tab22(nc);
+    for (int i = 0; i < nc; i++) {
+        tabL[i] = sp.table_index(i, SP_LIN);
+        tabSq[i] = sp.table_index(i, SP_LIN_SQ);
+        tab22[i] = sp.table_index(i, SP_P22BAR);
+    }
+    DevBuf<int> d_tabL, d_tabSq, d_tab22;
+    d_tabL.upload(tabL, s);
+    d_tabSq.upload(tabSq, s);
+    d_tab22.upload(tab22, s);
 
     // ---- stage B: I_mn, K_mn
     s_ik.ensure((size_t)ntile*8*nk*40);

@@ -42,7 +42,7 @@ struct PTPlan {
     QuadConfig cfg;
     std::vector<double> k_interp, k_1loop, r_zel;
     int nk = 0;
-    bool with_ml = true, with_zel = true;
+    bool with_ml = true, with_zel = true, only_oneloop = false;
     BilinearOp op_1loop, op_ik, op_ml_pos, op_ml_neg;
     LinearOp lin_1loop;        // J00, J01, J11 on k_1loop                      (P_L table)
     LinearOp lin_main;         // J x6 (nk each), sigmasq_k (nk), sigma_v^2, X (1024), Y (1024)   (P_L table)
@@ -54,7 +54,9 @@ struct PTPlan {
     DevBuf<int> s_slot, s_rowA, s_rowB, s_tabidx;
     double build_seconds = 0.0;
 
-    PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel);
+    PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l = false);
+    // stage A only: the four one-loop tables (left in sp and in res.oneloop)
+    void run_oneloop(SpectraBatch& sp, PTResult& res);
     void run(SpectraBatch& sp, PTResult& res);
     size_t device_bytes() const;
     long long nodes_total() const;

@@ -92,7 +92,7 @@ static double local_width(double q, const QuadConfig& c)
 }
 
 std::vector<double> panel_edges(double lo, double hi, const std::vector<double>& extra,
-                                const QuadConfig& c)
+                                const QuadConfig& c, double width_cap)
 {
     std::vector<double> brk;
     brk.push_back(lo);
@@ -115,7 +115,7 @@ std::vector<double> panel_edges(double lo, double hi, const std::vector<double>&
         xs.push_back(x0);
         while (xs.back() < x1 - 1e-12) {
             double q = std::min(std::exp(xs.back())*1.0000001, p1);
-            xs.push_back(xs.back() + local_width(q, c));
+            xs.push_back(xs.back() + std::min(local_width(q, c), width_cap));
         }
         const double scale = (x1 - x0)/(xs.back() - x0);
         for (size_t j = 1; j < xs.size(); j++) {
@@ -171,7 +171,7 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
                 H.a_j0.push_back(j0);
                 H.a_coef.insert(H.a_coef.end(), coef, coef + 4);
                 H.o_kid.push_back(ik);
-                std::vector<double> ie = panel_edges(blo, bhi, zone_breaks, cfg);
+                std::vector<double> ie = panel_edges(blo, bhi, zone_breaks, cfg, cfg.ln_inner);
                 for (size_t pb = 0; pb + 1 < ie.size(); pb++) {
                     const double b0 = ie[pb], b1 = ie[pb + 1];
                     const double hb = 0.5*(b1 - b0), mb = 0.5*(b1 + b0);

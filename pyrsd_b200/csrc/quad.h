@@ -31,7 +31,7 @@ struct QuadConfig {
     double bao_lo   = 0.01;   // panels at most bao_dq wide in q (not ln q) in the BAO range
     double bao_hi   = 0.7;
     double bao_dq   = 0.05;
-    int    n_1d     = 12;     // Gauss-Legendre points per panel for 1-D operators
+    double ln_inner = 0.5;    // max panel width in ln b of the inner integral (any region)
 };
 
 // Tabulation grid of every spectrum: piecewise-uniform in x = ln q, zone edges at the hard
@@ -53,7 +53,7 @@ void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w);
 
 // Panel edges between lo and hi (in q), honouring `extra` break points.
 std::vector<double> panel_edges(double lo, double hi, const std::vector<double>& extra,
-                                const QuadConfig& cfg);
+                                const QuadConfig& cfg, double width_cap = 1e30);
 
 // One half (b >= a) of the 2-D integration domain for a list of k.
 struct HalfNodes {

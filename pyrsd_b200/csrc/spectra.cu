@@ -111,6 +111,7 @@ void spline_build_batched(Context& ctx, int nspline, int n, const double* dX, in
     const size_t smem = (size_t)5*n*sizeof(double);
     if (smem > 48*1024)
         PRSD_CUDA(cudaFuncSetAttribute(k_spline_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(ctx, PROF_SPLINE);
     k_spline_build<<<nspline, 128, smem, ctx.stream>>>(n, dX, x_stride, dY, dspl);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
@@ -182,6 +183,29 @@ SpectraBatch::SpectraBatch(Context& c, int ncosmo_, int nspl_, const double* k, 
     PRSD_CUDA(cudaGetLastError());
     ctx->launches++;
     ctx->sync();
+}
+
+__global__ void k_params_init(int nspl, const double* __restrict__ k, const double* __restrict__ T,
+                              const double* __restrict__ pars, PlinParams* __restrict__ out)
+{
+    const int c = blockIdx.x;
+    const double* p = pars + (size_t)c*8;
+    PlinParams P;
+    plin_params_init(P, nspl, k + (size_t)c*nspl, T + (size_t)c*nspl, p[0], p[1], p[2], p[3], p[4], p[5]);
+    out[c] = P;
+}
+
+void SpectraBatch::reload_device(const double* d_k, const double* d_T, const double* d_pars)
+{
+    cudaStream_t s = ctx->stream;
+    k_params_init<<<ncosmo, 1, 0, s>>>(nspl, d_k, d_T, d_pars, params.p);
+    ctx->launches++;
+    spline_build_batched(*ctx, ncosmo, nspl, d_k, nspl, d_T, spl.p);
+    dim3 grid((TAB_MPAD + 255)/256, ncosmo);
+    k_plin_table<<<grid, 256, 0, s>>>(nspl, params.p, spl.p, knot_grid_dev(*ctx), tables.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx->launches++;
+    have_oneloop = false;
 }
 
 void SpectraBatch::rescale_linear(const double* fac_host)
@@ -260,7 +284,10 @@ void SpectraBatch::set_oneloop_tables(const double* d_tables)
         dk_dev = ctx->device;
     }
     oneloop_spl.ensure((size_t)ncosmo*4*5*ONELOOP_N);
-    spline_build_batched(*ctx, ncosmo*4, ONELOOP_N, dk.p, 0, d_tables, oneloop_spl.p);
+    oneloop_raw.ensure((size_t)ncosmo*4*ONELOOP_N);
+    if (d_tables != oneloop_raw.p)
+        PRSD_CUDA(cudaMemcpyAsync(oneloop_raw.p, d_tables, (size_t)ncosmo*4*ONELOOP_N*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    spline_build_batched(*ctx, ncosmo*4, ONELOOP_N, dk.p, 0, oneloop_raw.p, oneloop_spl.p);
     const double lnk0 = std::log(ONELOOP_KMIN);
     const double inv = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
     // zones 1..3 of the knot grid span [1e-5, 10] exactly (quad.cpp make_knot_grid)
@@ -271,6 +298,27 @@ void SpectraBatch::set_oneloop_tables(const double* d_tables)
     PRSD_CUDA(cudaGetLastError());
     ctx->launches++;
     have_oneloop = true;
+}
+
+void SpectraBatch::set_oneloop_table(int which, const double* h_table)
+{
+    PRSD_REQUIRE(which >= 0 && which < 4, "set_oneloop_table: invalid spectrum %d", which);
+    if (!oneloop_raw.n) {
+        oneloop_raw.alloc((size_t)ncosmo*4*ONELOOP_N);
+        oneloop_raw.zero(ctx->stream);
+    }
+    for (int c = 0; c < ncosmo; c++)
+        PRSD_CUDA(cudaMemcpyAsync(oneloop_raw.p + ((size_t)c*4 + which)*ONELOOP_N, h_table + (size_t)c*ONELOOP_N,
+                                  ONELOOP_N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    set_oneloop_tables(oneloop_raw.p);
+    ctx->sync();
+}
+
+void SpectraBatch::get_oneloop_tables(double* h_out)
+{
+    PRSD_REQUIRE(have_oneloop, "one-loop tables have not been computed for this batch");
+    oneloop_raw.download(h_out, (size_t)ncosmo*4*ONELOOP_N, ctx->stream);
+    ctx->sync();
 }
 
 void SpectraBatch::eval_oneloop(int which, bool full, int nq, const double* q_host, double* out_host)

@@ -30,9 +30,13 @@ struct SpectraBatch {
     DevBuf<double> spl;            // [ncosmo][5*nspl]   X | Y | b | c | d
     DevBuf<double> tables;         // [ncosmo*SP_NKIND][TAB_MPAD]
     DevBuf<double> oneloop_spl;    // [ncosmo][4][5*ONELOOP_N] splines of the one-loop tables
+    DevBuf<double> oneloop_raw;    // [ncosmo][4][ONELOOP_N] the tables themselves
     bool have_oneloop = false;
 
     SpectraBatch(Context& c, int ncosmo_, int nspl_, const double* k, const double* T, const double* pars);
+    // rebuild every linear-spectrum table from DEVICE-resident inputs: d_k, d_T [ncosmo][nspl],
+    // d_pars [ncosmo][8] (same meaning as the host constructor); asynchronous on the context's stream
+    void reload_device(const double* d_k, const double* d_T, const double* d_pars);
     int table_index(int cosmo, int kind) const { return cosmo*SP_NKIND + kind; }
     const double* table_ptr(int cosmo, int kind) const { return tables.p + (size_t)table_index(cosmo, kind)*TAB_MPAD; }
     // multiply P_L (spline amplitude and tables) of cosmology c by fac
@@ -41,6 +45,9 @@ struct SpectraBatch {
     // install the four one-loop tables (device, [ncosmo][4][ONELOOP_N]), build their splines
     // and tabulate them on the knot grid
     void set_oneloop_tables(const double* d_tables);
+    // replace ONE table (host, [ncosmo][ONELOOP_N]); the other three keep their values (0 if never set)
+    void set_oneloop_table(int which, const double* h_table);
+    void get_oneloop_tables(double* h_out);      // [ncosmo][4][ONELOOP_N]
     void eval_oneloop(int which, bool full, int nq, const double* q_host, double* out_host);
 };
 

@@ -49,6 +49,19 @@ __global__ void k_spline_eval_rows(int nspl, const double* __restrict__ spl, int
     out[(size_t)b*nq + i] = scale*cubic_spline_eval_bsearch(nspl, spl + (size_t)b*5*nspl, xq[i]);
 }
 
+void spline_eval_host_x(Context& ctx, int batch, int n, const double* h_x, const double* d_y, int nq, const double* h_xq, double* d_out)
+{
+    PRSD_REQUIRE(n >= 4, "CubicSpline: need at least 4 points");
+    DevBuf<double> dx, dq, spl((size_t)batch*5*n);
+    dx.upload(h_x, n, ctx.stream);
+    dq.upload(h_xq, nq, ctx.stream);
+    spline_build_batched(ctx, batch, n, dx.p, 0, d_y, spl.p);
+    k_spline_eval_rows<<<dim3((nq + 127)/128, batch), 128, 0, ctx.stream>>>(n, spl.p, nq, dq.p, 1.0, d_out);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+    ctx.sync();
+}
+
 void xilm_log_grid(int N, double xmin, double xmax, std::vector<double>& grid, double& dlogr, double& logrc)
 {
     // CorrelationFunction.cpp:65-73

@@ -15,4 +15,7 @@ void compute_xilm_fftlog_dev(Context& ctx, int batch, int l, int m, int N, const
 void compute_xilm_dev(Context& ctx, int batch, int l, int m, int nk, const double* h_k, const double* d_pk,
                       int nr, const double* h_r, double smoothing, double scale, double* d_out);
 
+// netlib cubic spline of `batch` rows y [batch][n] on shared abscissae h_x, evaluated at h_xq -> d_out [batch][nq]
+void spline_eval_host_x(Context& ctx, int batch, int n, const double* h_x, const double* d_y, int nq, const double* h_xq, double* d_out);
+
 } // namespace prsd

@@ -174,6 +174,7 @@ void zeldovich_eval_map(Context& ctx, const ZelPlan& plan, int nrow, const int* 
     if (nrow <= 0) return;
     PRSD_REQUIRE(!lowk || (plin && q3coef), "zeldovich_eval: low-k approximation needs P_lin(k) and Q3");
     dim3 grid(plan.nk, nrow);
+    ProfScope prof(ctx, PROF_ZELDOVICH);
     k_zeldovich<<<grid, 256, 0, ctx.stream>>>(plan.nk, plan.dk.p, plan.r.p, plan.g.p, plan.ja.p, plan.jb.p, plan.wa.p, plan.wb.p,
                                             cmap, X0, XX, YY, sigmasq, sigmasq_stride, ratio, lowk ? 1 : 0, k0_low, plin, q3coef, q3_stride, out);
     PRSD_CUDA(cudaGetLastError());

@@ -1,0 +1,392 @@
+"""Drop-in for the P(k, mu) evaluation path of ``pyRSD.rsd``.
+
+``GalaxySpectrum`` mirrors the reference class (``pyRSD/rsd/power/gal/power_gal.py:10-425``) for
+the call contract the fitting layer uses -- ``model.update(**params)`` followed by
+``model.power(k, mu)`` (``pyRSD/rsdfit/theory/base.py:612-699``) -- with the same attribute names and
+defaults.  ``PTEngine`` is the batched form: many cosmologies / MCMC walkers per call, which is what
+the GPU is for.
+
+Inputs that the reference obtains from Gaussian-process fits to simulations (needing ``george`` and
+pandas pickles) are HOST INPUTS here: ``b2_00``, ``b2_01`` (callables of the linear bias) and
+``stochasticity`` (callable ``(k, sigma8_z, b1, b1_bar)``); see DESIGN.md.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import pygcl
+
+INTERP_KMIN = 5e-6      # pyRSD/rsd/__init__.py:3-4
+INTERP_KMAX = 1.0
+NPAR = 48
+NPAIR = 10
+NSTOCH = 20
+
+_vp = C.c_void_p
+_dp = N._dp
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags='C_CONTIGUOUS')
+
+FOG_MODELS = {'modified_lorentzian': 0, 'lorentzian': 1, 'gaussian': 2}
+# (bias a, bias b) of the ten sub-spectra: cAcA cAcB cBcB cAsA cAsB cBsA cBsB sAsA sAsB sBsB
+PAIRS = [(0, 0), (0, 1), (1, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]
+
+
+def _L():
+    L = pygcl._L()
+    if not getattr(L, '_rsd_sigs', False):
+        i, d = C.c_int, C.c_double
+        L.prsd_galaxy_config_default.argtypes = [_dp]
+        L.prsd_galaxy_create.argtypes = [_vp, _vp, i, _dp, i, _dp, C.POINTER(_vp)]
+        L.prsd_galaxy_destroy.argtypes = [_vp]
+        L.prsd_galaxy_power.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, _dp, _dp]
+        L.prsd_galaxy_power_device.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _vp, _vp, _vp]
+        L.prsd_galaxy_moments.argtypes = [_vp, i, _dp]
+        for name in ('prsd_galaxy_config_default', 'prsd_galaxy_create', 'prsd_galaxy_destroy', 'prsd_galaxy_power',
+                     'prsd_galaxy_power_device', 'prsd_galaxy_moments'):
+            getattr(L, name).restype = i
+        L._rsd_sigs = True
+    return L
+
+
+def k_interp_default():
+    """the PT interpolation grid of the reference (power_dm.py:22)"""
+    return np.logspace(np.log10(INTERP_KMIN), np.log10(INTERP_KMAX), 250)
+
+
+class _Plan(N.Handle):
+    _destroy = 'prsd_plan_destroy'
+
+
+class _Result(N.Handle):
+    _destroy = 'prsd_result_destroy'
+
+
+class _Galaxy(N.Handle):
+    _destroy = 'prsd_galaxy_destroy'
+
+
+class PTEngine(object):
+    """Batched PT + galaxy-assembly engine: one quadrature plan (cosmology independent) reused for
+    any number of cosmologies / walkers."""
+
+    RESULT_SHAPES = {'I': (0, lambda c, nk: (c, 16, nk)), 'J': (1, lambda c, nk: (c, 6, nk)), 'K': (2, lambda c, nk: (c, 13, nk)),
+                     'ML': (3, lambda c, nk: (c, 7, 3, nk)), 'oneloop': (4, lambda c, nk: (c, 4, 1000)),
+                     'sigmasq_k': (5, lambda c, nk: (c, nk)), 'scalars': (6, lambda c, nk: (c, 4)),
+                     'X0': (7, lambda c, nk: (c, 1024)), 'YY': (8, lambda c, nk: (c, 1024))}
+
+    def __init__(self, k_interp=None, quad_config=None, context=None, with_ml=True, with_zel=True):
+        self.ctx = context if context is not None else N.default_context()
+        self.k_interp = N.as_f64(k_interp_default() if k_interp is None else k_interp)
+        keep, cfgp = N.cfg_ptr(quad_config)
+        p = _vp()
+        flags = (1 if with_ml else 0) | (2 if with_zel else 0)
+        N.check(_L().prsd_plan_create(self.ctx.ptr, len(self.k_interp), self.k_interp, cfgp, flags, C.byref(p)))
+        self.plan = _Plan(p)
+        self._galaxies = {}
+        self._result = None
+
+    def info(self):
+        out = np.empty(8)
+        N.check(_L().prsd_plan_info(self.plan.ptr, out))
+        return dict(nodes=int(out[0]), device_bytes=int(out[1]), build_seconds=out[2], nk=int(out[3]), n_knots=int(out[4]),
+                    nodes_oneloop=int(out[5]), nodes_ik=int(out[6]), nodes_ml_half=int(out[7]))
+
+    # ------------------------------------------------------------------ spectra
+    def spectra(self, k, T, n_s, amp, h, Omega0_m, Omega0_b, Tcmb=2.7255):
+        """upload a batch of linear spectra: k, T [ncosmo][nspl]; the rest scalars or [ncosmo]"""
+        k = np.atleast_2d(np.asarray(k, dtype=np.float64))
+        T = np.atleast_2d(np.asarray(T, dtype=np.float64))
+        nc = T.shape[0]
+        if k.shape[0] == 1 and nc > 1:
+            k = np.repeat(k, nc, axis=0)
+        pars = np.zeros((nc, 8))
+        for j, v in enumerate((n_s, amp, h, Omega0_m, Omega0_b, Tcmb)):
+            pars[:, j] = v
+        return pygcl._Spectra(self.ctx, k, T, pars)
+
+    def run(self, spectra, result=None):
+        """everything rsd/pt_integrals.py tabulates, for every cosmology of the batch"""
+        res = result if result is not None else self._result
+        if res is None:
+            res = _new_result()
+        cur = res.ptr.value if isinstance(res.ptr, _vp) else res.ptr
+        p = _vp(cur)
+        N.check(_L().prsd_plan_run(self.plan.ptr, spectra.ptr, C.byref(p)))
+        res.ptr = p
+        res.ncosmo = spectra.ncosmo
+        if result is None:
+            self._result = res
+        spectra.have_oneloop = True
+        return res
+
+    def get(self, result, name):
+        what, shape = self.RESULT_SHAPES[name]
+        out = np.empty(shape(result.ncosmo, len(self.k_interp)))
+        N.check(_L().prsd_result_get(result.ptr, what, out, out.size))
+        return out
+
+    # ------------------------------------------------------------------- galaxy
+    def galaxy(self, kmodel, config=None):
+        kmodel = N.as_f64(kmodel)
+        cfg = None if config is None else N.as_f64(config)
+        key = (kmodel.tobytes(), None if cfg is None else cfg.tobytes())
+        if key not in self._galaxies:
+            p = _vp()
+            N.check(_L().prsd_galaxy_create(self.ctx.ptr, None if cfg is None else cfg.ctypes.data_as(_vp), len(kmodel), kmodel,
+                                            len(self.k_interp), self.k_interp, C.byref(p)))
+            g = _Galaxy(p)
+            g.nkm = len(kmodel)
+            self._galaxies[key] = g
+        return self._galaxies[key]
+
+    def galaxy_power(self, gal, spectra, result, par, stoch, k, mu, cmap=None):
+        """P(k, mu) of nw walkers at paired (k, mu) points -> [nw][npts]"""
+        par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, NPAR)
+        nw = par.shape[0]
+        stoch = np.ascontiguousarray(stoch, dtype=np.float64).reshape(nw, NPAIR, NSTOCH)
+        k, mu = N.as_f64(k), N.as_f64(mu)
+        assert k.shape == mu.shape
+        out = np.empty((nw, len(k)))
+        cm = None
+        if cmap is not None:
+            cm = np.ascontiguousarray(cmap, dtype=np.int32)
+        N.check(_L().prsd_galaxy_power(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
+                                       par, stoch, len(k), k, mu, out))
+        return out
+
+    def galaxy_moments(self, gal, nw):
+        out = np.empty((nw, NPAIR, 4, gal.nkm))
+        N.check(_L().prsd_galaxy_moments(gal.ptr, nw, out))
+        return out
+
+
+def galaxy_config(max_mu=4, fog_model='modified_lorentzian', use_P00_model=True, use_P01_model=True, use_P11_model=True,
+                  use_Pdv_model=True, use_Pvv_model=True, use_Phm_model=True, use_tidal_bias=False,
+                  use_so_correction=False, k0_low=5e-3):
+    cfg = np.empty(64)
+    N.check(_L().prsd_galaxy_config_default(cfg))
+    if fog_model not in FOG_MODELS:
+        raise ValueError("`fog_model` must be one of %s" % sorted(FOG_MODELS))
+    if max_mu not in (0, 2, 4, 6):
+        raise ValueError("`max_mu` must be one of [0, 2, 4, 6]")
+    cfg[0], cfg[1] = max_mu, FOG_MODELS[fog_model]
+    cfg[2:10] = [use_P00_model, use_P01_model, use_P11_model, use_Pdv_model, use_Pvv_model, use_Phm_model,
+                 use_tidal_bias, use_so_correction]
+    cfg[10] = k0_low
+    return cfg
+
+
+def pack_walker(sigma8_z, f, alpha_par, alpha_perp, alpha_drag, b1, fs, fcB, fsB, sigma_c, sigma_sA, sigma_sB, NcBs, NsBsB,
+                f_so, sigma_so, sigma_v, D, sigma8, b2):
+    """one row of the walker-parameter matrix of the C-ABI (include/pyrsd_b200.h)"""
+    p = np.zeros(NPAR)
+    p[0:5] = sigma8_z, f, alpha_par, alpha_perp, alpha_drag
+    p[5:9] = b1
+    p[9:19] = fs, fcB, fsB, sigma_c, sigma_sA, sigma_sB, NcBs, NsBsB, f_so, sigma_so
+    p[19], p[20], p[21] = (sigma_v if sigma_v is not None else -1.0), D, sigma8
+    p[22:46] = np.asarray(b2, dtype=float).reshape(24)
+    return p
+
+
+def stochasticity_grid(kmodel):
+    """the 20 log-spaced k the stochasticity is tabulated on (power_biased.py:357)"""
+    return np.logspace(np.log10(kmodel.min()), np.log10(kmodel.max()), NSTOCH)
+
+
+# polynomial nonlinear-bias defaults shipped by the reference (data/simulation_fits/b2_0?_fits_runPB.npz,
+# exposed as `nonlinear_bias_defaults`, nonlinear_biasing.py:54-72): coefficients of b1^0, b1^2, b1^4 for
+# b2_00 and of b1^0, b1^1, b1^2 for b2_01 (the "_a" variants, used for all terms under `use_vlah_biasing`)
+_B2_00_A = (-0.9097586321233345, 0.42328044892648975, 0.008338610073394552)
+_B2_01_A = (0.4541869219609199, -1.4949433955934217, 0.7001525446354208)
+
+
+def default_b2_00(b1):
+    return _B2_00_A[0] + _B2_00_A[1]*b1**2 + _B2_00_A[2]*b1**4
+
+
+def default_b2_01(b1):
+    return _B2_01_A[0] + _B2_01_A[1]*b1 + _B2_01_A[2]*b1**2
+
+
+class GalaxySpectrum(object):
+    """The model for the galaxy redshift-space power spectrum (power_gal.py:10-425).
+
+    Same keyword arguments / attributes as the reference where they belong to the P(k, mu) path;
+    ``params`` must be a :class:`pyrsd_b200.pygcl.Cosmology`."""
+
+    _PARAMS = ('sigma8_z', 'f', 'alpha_par', 'alpha_perp', 'alpha_drag', 'b1_cA', 'b1_cB', 'b1_sA', 'b1_sB', 'fs', 'fcB',
+               'fsB', 'sigma_c', 'sigma_s', 'sigma_sA', 'sigma_sB', 'NcBs', 'NsBsB', 'N', 'f_so', 'sigma_so', 'sigma_v',
+               'sigma_v2', 'sigma_bv2', 'sigma_bv4')
+
+    def __init__(self, kmin=1e-3, kmax=0.5, Nk=200, z=0., params=None, include_2loop=False, transfer_fit="CLASS",
+                 max_mu=4, interpolate=False, k0_low=5e-3, Pdv_model_type='jennings', fog_model='modified_lorentzian',
+                 use_so_correction=False, use_tidal_bias=False, use_mean_bias=False, vel_disp_from_sims=False,
+                 correct_mu2=False, correct_mu4=False, use_vlah_biasing=True, b2_00=None, b2_01=None,
+                 stochasticity=None, engine=None, **kwargs):
+        if not isinstance(params, pygcl.Cosmology):
+            raise TypeError("`params` must be a pyrsd_b200.pygcl.Cosmology (the linear T(k) is a host input)")
+        if include_2loop:
+            raise ValueError("`include_2loop` is forced to False for biased tracers (power_biased.py:47)")
+        if interpolate:
+            raise NotImplementedError("interpolate=True (sigma8 x k Zel'dovich tables) is not needed: the Zel'dovich "
+                                      "terms are evaluated exactly at every call")
+        if Pdv_model_type != 'jennings':
+            raise NotImplementedError("only Pdv_model_type='jennings' is available (the 'sims' model needs george)")
+        if use_mean_bias or vel_disp_from_sims or correct_mu2 or correct_mu4:
+            raise NotImplementedError("use_mean_bias / vel_disp_from_sims / correct_mu2 / correct_mu4 need the "
+                                      "reference's Gaussian-process fits, which are host inputs not available here")
+        if kmin < INTERP_KMIN:
+            raise ValueError("kmin = %.2e h/Mpc below PT integrals interpolation lower bound" % kmin)
+        if kmax > INTERP_KMAX:
+            raise ValueError("kmax = %.2e h/Mpc above PT integrals interpolation upper bound" % kmax)
+        self.cosmo = params
+        self.z, self.kmin, self.kmax, self.Nk = z, kmin, kmax, Nk
+        self.max_mu, self.fog_model, self.use_so_correction, self.use_tidal_bias = max_mu, fog_model, use_so_correction, use_tidal_bias
+        self.k0_low = k0_low
+        self.include_2loop = False
+        self.interpolate = False
+        self.transfer_fit = transfer_fit
+        self.use_vlah_biasing = use_vlah_biasing
+        self._models = {}
+        for kw in ('use_P00_model', 'use_P01_model', 'use_P11_model', 'use_Pdv_model', 'use_Pvv_model', 'use_Phm_model'):
+            self._models[kw] = bool(kwargs.pop(kw, True))
+        if kwargs:
+            raise TypeError("unexpected keyword arguments %s" % sorted(kwargs))
+        self.b2_00 = b2_00 if b2_00 is not None else default_b2_00
+        self.b2_01 = b2_01 if b2_01 is not None else default_b2_01
+        self.stochasticity = stochasticity
+        # defaults of DarkMatterSpectrum / GalaxySpectrum (power_dm.py:119-126, power_gal.py:103-123)
+        self.sigma8_z = params.Sigma8_z(z)
+        self.f = params.f_z(z)
+        self.alpha_par = self.alpha_perp = self.alpha_drag = 1.
+        self.sigma_v = None
+        self.sigma_v2 = self.sigma_bv2 = self.sigma_bv4 = 0.
+        self.fs, self.fcB, self.fsB = 0.10, 0.08, 0.40
+        self.b1_cA, self.b1_cB, self.b1_sA, self.b1_sB = 1.85, 2.8, 2.6, 3.6
+        self.sigma_c, self.sigma_s, self.sigma_sA, self.sigma_sB = 1., 5., 4.2, 6.
+        self.NcBs, self.NsBsB, self.N = 3e4, 9e4, 0.
+        self.f_so = self.sigma_so = 0.
+        self._engine = engine
+        self._spectra = None
+        self._result = None
+
+    # -------------------------------------------------------------- derived
+    def __getattr__(self, name):
+        models = self.__dict__.get('_models', {})
+        if name in models:
+            return models[name]
+        raise AttributeError(name)
+
+    @property
+    def k(self):
+        """the spline domain of the model (power_dm.py:526-538)"""
+        return np.logspace(np.log10(max(self.kmin, INTERP_KMIN)), np.log10(min(self.kmax, INTERP_KMAX)), self.Nk)
+
+    @property
+    def D(self):
+        return self.cosmo.D_z(self.z)
+
+    @property
+    def _power_norm(self):
+        return (self.sigma8_z/self.cosmo.sigma8())**2
+
+    @property
+    def b1_c(self):
+        return self.fcB*self.b1_cB + (1. - self.fcB)*self.b1_cA
+
+    @property
+    def b1_s(self):
+        return self.fsB*self.b1_sB + (1. - self.fsB)*self.b1_sA
+
+    def update(self, **kwargs):
+        for k, v in kwargs.items():
+            if k in self._models:
+                self._models[k] = bool(v)
+            elif k in self._PARAMS or k in ('max_mu', 'fog_model', 'use_so_correction', 'use_tidal_bias', 'b2_00', 'b2_01',
+                                            'stochasticity'):
+                setattr(self, k, v)
+            else:
+                raise RuntimeError("failure to set parameter `%s` to value %s: unknown parameter" % (k, v))
+
+    # ---------------------------------------------------------------- tables
+    def _ensure_tables(self):
+        if self._engine is None:
+            self._engine = PTEngine(context=self.cosmo._ctx)
+        if self._result is None:
+            c = self.cosmo
+            self._spectra = self._engine.spectra(c.GetDiscreteK(), c.GetDiscreteTk(), c.n_s(), c.delta_H()**2, c.h(),
+                                                 c.Omega0_m(), c.Omega0_b(), c.Tcmb())
+            self._result = self._engine.run(self._spectra, result=_new_result())
+        return self._engine
+
+    def initialize(self):
+        """build every PT / Zel'dovich table (the reference's minutes-long step, power_dm.py:154-159)"""
+        return self.power(0.5*(self.kmin + self.kmax), 0.5)
+
+    def pt_table(self, name):
+        """unnormalised PT tables on k_interp: 'I', 'J', 'K', 'ML', 'oneloop', 'sigmasq_k', 'scalars', 'X0', 'YY'"""
+        eng = self._ensure_tables()
+        return eng.get(self._result, name)[0]
+
+    @property
+    def sigma_lin(self):
+        return np.sqrt(self._power_norm*self.pt_table('scalars')[0])
+
+    @property
+    def velocity_kurtosis(self):
+        return self._power_norm**2*self.pt_table('scalars')[1]
+
+    def _walker(self):
+        b1 = [self.b1_cA, self.b1_cB, self.b1_sA, self.b1_sB]
+        b00 = [self.b2_00(b) for b in b1]
+        b01 = [self.b2_01(b) for b in b1]
+        b2 = [b00, b00, b00, b00, b01, b01]
+        return pack_walker(self.sigma8_z, self.f, self.alpha_par, self.alpha_perp, self.alpha_drag, b1, self.fs, self.fcB,
+                           self.fsB, self.sigma_c, self.sigma_sA, self.sigma_sB, self.NcBs, self.NsBsB, self.f_so,
+                           self.sigma_so, self.sigma_v, self.D, self.cosmo.sigma8(), b2)
+
+    def _stoch(self, kmodel):
+        ks = stochasticity_grid(kmodel)
+        b1 = [self.b1_cA, self.b1_cB, self.b1_sA, self.b1_sB]
+        out = np.zeros((NPAIR, NSTOCH))
+        if self.stochasticity is not None:
+            for p, (a, b) in enumerate(PAIRS):
+                lo, hi = sorted([b1[a], b1[b]])
+                out[p] = self.stochasticity(ks, self.sigma8_z, lo, hi)
+        return out
+
+    def _config(self):
+        return galaxy_config(max_mu=self.max_mu, fog_model=self.fog_model, use_tidal_bias=self.use_tidal_bias,
+                             use_so_correction=self.use_so_correction, k0_low=5e-3, **self._models)
+
+    def power(self, k, mu, flatten=False):
+        """P(k, mu) with the broadcasting rules of ``tools.broadcast_kmu`` (rsd/tools.py:225-266)"""
+        eng = self._ensure_tables()
+        k = np.atleast_1d(np.asarray(k, dtype=np.float64))
+        mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+        if k.ndim == 1 and mu.ndim == 1:
+            if len(mu) != len(k):
+                k, mu = k[:, None], mu[None, :]
+        elif k.ndim > 1 and mu.ndim < 2:
+            mu = mu[None, :]
+        elif mu.ndim > 1 and k.ndim < 2:
+            k = k[:, None]
+        kb, mub = np.broadcast_arrays(k, mu)
+        if kb.ndim > 2:
+            raise ValueError("incompatible `k`, `mu` dimensions for broadcasted; arrays should have maximum dimension of 2")
+        kmodel = self.k
+        gal = eng.galaxy(kmodel, self._config())
+        P = eng.galaxy_power(gal, self._spectra, self._result, self._walker(), self._stoch(kmodel),
+                             np.ascontiguousarray(kb).ravel(), np.ascontiguousarray(mub).ravel())[0]
+        if np.isnan(P).any():
+            raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
+                             "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+        P = np.squeeze(P.reshape(kb.shape))
+        return np.ravel(P, order='F') if flatten else P
+
+
+def _new_result():
+    r = _Result(None)
+    r.ncosmo = 0
+    return r

@@ -1,0 +1,249 @@
+"""Generate ``tests/golden/galaxy_ref.npz``: GalaxySpectrum.power(k, mu) computed by the
+UNMODIFIED reference Python (``pyRSD.rsd`` imported from /root/reference) on top of the reference's
+own C++ (oracle/_ref/libgcl_ref.so, through tests/golden/fake_gcl.py).
+
+What is NOT the reference here (all stated in DESIGN.md):
+  * ``pyRSD.gcl`` (SWIG artefact)  -> fake_gcl.py, same C++ underneath except Cosmology (CLASS) and
+    FFTLog (Fortran) which are the oracle's stand-ins;
+  * astropy / xarray / george      -> absent: stubbed (only used for unit handling, the xarray return
+    wrapper and Gaussian-process fits);
+  * the Gaussian-process fits (stochasticity, nonlinear biases) -> replaced on BOTH sides by the
+    same smooth synthetic functions below ("parity unpinned at this sub-boundary");
+  * quadrature tolerances: the reference's defaults (1e-4 / 1e-3) are replaced by TIGHT values
+    (see TIGHT below) because 1e-5 parity is defined against the converged reference.
+
+Run in the build container only:  python tests/golden/make_galaxy_ref.py  (tens of minutes)
+"""
+import os
+import sys
+import time
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import fake_gcl  # noqa: E402
+from oracle import gcl_ref as R  # noqa: E402
+
+TIGHT = dict(imn=1e-8, jmn=1e-10, kmn=1e-8, oneloop=1e-8, ml=1e-8)
+CACHE = '/tmp/galaxy_ref_cache.npz'
+
+
+# ----------------------------------------------------------------- synthetic GP replacements
+def b2_00(b1):
+    return 0.77 - 2.43*b1 + b1**2
+
+
+def b2_01(b1):
+    return 0.9 - 1.4*b1 + 0.45*b1**2
+
+
+def stochasticity(k, sigma8_z, b1a, b1b):
+    """smooth stand-in for the GP stochasticity Lambda(k; sigma8, b1, b1_bar)"""
+    return (sigma8_z/0.8)*(120.*b1a*b1b - 400.)*(1.0 + 0.3*np.log(k/0.1) - 0.05*np.log(k/0.1)**2)
+
+
+# ------------------------------------------------------------------- tight-tolerance patches
+_cache = {}
+
+
+def _cached(key, fn):
+    key = repr(key)
+    if key not in _cache:
+        _cache[key] = fn()
+    return _cache[key]
+
+
+def install_tight():
+    """make the fake gcl classes use tight tolerances, with an on-disk cache of the slow integrals"""
+    if os.path.exists(CACHE):
+        _cache.update({k: v for k, v in np.load(CACHE, allow_pickle=True).items()})
+
+    def imn_call(self, k, m, n):
+        return _cached(('I', m, n, np.asarray(k).tobytes()), lambda: R.Imn(self._P._r, k, m, n, TIGHT['imn']))
+
+    def jmn_call(self, k, m, n):
+        return _cached(('J', m, n, np.asarray(k).tobytes()), lambda: R.Jmn(self._P._r, k, m, n, TIGHT['jmn']))
+
+    def kmn_call(self, k, m, n, tidal=False, part=0):
+        return _cached(('K', m, n, tidal, part, np.asarray(k).tobytes()),
+                       lambda: R.Kmn(self._P._r, k, m, n, tidal, part, TIGHT['kmn']))
+
+    fake_gcl.Imn.__call__ = imn_call
+    fake_gcl.Jmn.__call__ = jmn_call
+    fake_gcl.Kmn.__call__ = kmn_call
+
+    orig_ol_init = fake_gcl._OneLoop.__init__
+
+    def ol_init(self, P_L, epsrel=1e-4, oneloop_power=None):
+        if oneloop_power is None:
+            which = self.which
+            oneloop_power = _cached(('OL', which), lambda: R.RefOneLoop(P_L._r, which, TIGHT['oneloop']).table())
+        orig_ol_init(self, P_L, TIGHT['oneloop'], oneloop_power)
+
+    fake_gcl._OneLoop.__init__ = ol_init
+    fake_gcl.OneLoopP22Bar.VelocityKurtosis = lambda self: self._r.VelocityKurtosis(1e-10)
+
+    def ml_ev(self, which, k, m, n):
+        key = ('ML', self._P1.which, None if self._P2 is None else self._P2.which, which, m, n, np.asarray(k).tobytes())
+        return _cached(key, lambda: R.ImnOneLoop(self._P1._r, None if self._P2 is None else self._P2._r, k, m, n,
+                                                 which, TIGHT['ml']))
+
+    fake_gcl.ImnOneLoop._ev = ml_ev
+
+    def vd(self, *args):
+        if len(args) == 0:
+            return self._r.sigv_tol()
+        k = np.atleast_1d(np.asarray(args[0], dtype=float))
+        factor = args[1] if len(args) > 1 else 0.5
+        return np.array([self._r.sigv_tol(factor*kk) if factor*kk >= 1e-5 else -0.0 + self._r.VelocityDispersion(np.array([kk]), factor)[0]
+                         for kk in k])
+
+    fake_gcl._PS.VelocityDispersion = vd
+
+    # tight X(r), Y(r), sigma^2 for the Zel'dovich base state
+    def zel_init(self, *args):
+        if len(args) in (2, 3) and isinstance(args[0], fake_gcl.Cosmology):
+            cosmo = args[0]
+            lowk = args[2] if len(args) > 2 else False
+            P0 = R.RefLinearPS(cosmo._ref, cosmo.sigma8())
+            r = 10.**(1.5 + (np.arange(1, 1025) - 512.5)*(7./1024))
+
+            def state():
+                ssq = P0.sigv_tol()
+                return np.concatenate([[ssq], P0.X_Zel(r, 1e-10, 1e-14), P0.Y_Zel(r, 1e-10, 1e-14)])
+            st = _cached(('ZEL',), state)
+            s8z = cosmo.Sigma8_z(args[1])
+            norm = (s8z/cosmo.sigma8())**2
+            ssq, X0, YY = norm*st[0], norm*st[1:1025], norm*st[1025:]
+            fake_gcl.ZeldovichPS.__orig_init__(self, cosmo, lowk, s8z, 5e-3, ssq, X0, X0 + 2*ssq, YY)
+        else:
+            fake_gcl.ZeldovichPS.__orig_init__(self, *args)
+
+    fake_gcl.ZeldovichPS.__orig_init__ = fake_gcl.ZeldovichPS.__init__
+    fake_gcl.ZeldovichPS.__init__ = zel_init
+
+
+def save_cache():
+    np.savez(CACHE, **_cache)
+
+
+# ----------------------------------------------------------------------------- module stubs
+def install_stubs():
+    sys.path.insert(0, '/root/reference')
+    sys.modules['pyRSD.gcl'] = fake_gcl
+    # API renames in the SciPy / NumPy of this container (the reference targets 2017-era versions)
+    import scipy.integrate
+    if not hasattr(scipy.integrate, 'simps'):
+        scipy.integrate.simps = scipy.integrate.simpson
+    for name, val in (('float', float), ('int', int), ('bool', bool)):
+        if not hasattr(np, name):
+            setattr(np, name, val)
+
+    xr = types.ModuleType('xarray')
+    xr.DataArray = lambda data, coords=None, dims=None: np.asarray(data)
+    sys.modules['xarray'] = xr
+
+    george = types.ModuleType('george')
+    george.__version__ = '0.3.0'
+    george.kernels = types.ModuleType('george.kernels')
+    george.kernels.ExpSquaredKernel = object
+    george.BasicSolver = object
+    george.HODLRSolver = object
+    george.GP = object
+    sys.modules['george'] = george
+    sys.modules['george.kernels'] = george.kernels
+
+    # pyRSD.rsd.cosmology needs astropy: provide the two names the model layer uses
+    cosmo_mod = types.ModuleType('pyRSD.rsd.cosmology')
+
+    class Cosmology(object):
+        """carries a ready pygcl.Cosmology through DarkMatterSpectrum.cosmo (power_dm.py:509-524)"""
+        def __init__(self, gcl_cosmo):
+            self._c = gcl_cosmo
+
+        def to_class(self, **kws):
+            return self._c
+
+    cosmo_mod.Cosmology = Cosmology
+    cosmo_mod.Planck15 = None
+    sys.modules['pyRSD.rsd.cosmology'] = cosmo_mod
+    return cosmo_mod
+
+
+def build_model(cosmo_mod, gcl_cosmo, z, **kwargs):
+    from pyRSD.rsd import GalaxySpectrum
+    model = GalaxySpectrum(params=cosmo_mod.Cosmology(gcl_cosmo), z=z, **kwargs)
+
+    def fitter(b1, select=None):
+        return b2_00(b1) if select.startswith('b2_00') else b2_01(b1)
+
+    model._cache['nonlinear_bias_fitter'] = fitter
+    model._cache['auto_stochasticity_fits'] = lambda b1, sigma8_z, k: stochasticity(k, sigma8_z, b1, b1)
+    model._cache['cross_stochasticity_fits'] = lambda b1_1, b1_2, sigma8_z, k: stochasticity(k, sigma8_z, b1_1, b1_2)
+    return model
+
+
+def main():
+    t0 = time.time()
+    cosmo_mod = install_stubs()
+    install_tight()
+    from pyRSD import pygcl
+
+    g = np.load(os.path.join(HERE, 'golden_pt.npz'))
+    params = {k[len('cosmo_'):]: float(g[k]) for k in g.files
+              if k.startswith('cosmo_') and k not in ('cosmo_k', 'cosmo_T', 'cosmo_sigma8', 'cosmo_tf')}
+    # background quantities that CLASS would supply (Planck15-like values, documented inputs)
+    params['_growth'] = {0.0: 1.0, 0.55: 0.7486}
+    params['_f'] = {0.0: float(g['par_f']), 0.55: 0.7602}
+    params['_H'] = {0.0: 100.*params['h'], 0.55: 100.*params['h']*1.3386}
+    cosmo = pygcl.Cosmology(pygcl.ClassParams.from_dict(params), 0, float(g['cosmo_sigma8']), g['cosmo_k'], g['cosmo_T'])
+
+    out = {'f_055': 0.7602, 'D_055': 0.7486}
+    k = np.logspace(np.log10(0.012), np.log10(0.38), 24)
+    mu = np.linspace(0., 1., 9)
+    out['k'], out['mu'] = k, mu
+
+    cases = {
+        # name: (z, model kwargs, attribute updates)
+        'z0_default': (0.0, dict(interpolate=False), {}),
+        'z055_ap': (0.55, dict(interpolate=False),
+                    dict(alpha_par=1.03, alpha_perp=0.98, b1_cA=1.9, b1_cB=2.7, b1_sA=2.4, b1_sB=3.3, fs=0.12,
+                         fcB=0.09, fsB=0.35, sigma_c=1.1, sigma_sA=3.9, sigma_sB=5.5, NcBs=4.2e4, NsBsB=8.1e4,
+                         sigma8_z=0.61, f=0.78)),
+        'z055_spt': (0.55, dict(interpolate=False, use_P00_model=False, use_P01_model=False, use_P11_model=False,
+                                use_Pdv_model=False, use_Pvv_model=False, use_Phm_model=False),
+                     dict(sigma8_z=0.6)),
+        'z055_so_gauss': (0.55, dict(interpolate=False, use_so_correction=True, fog_model='gaussian', max_mu=6,
+                                     use_tidal_bias=True),
+                          dict(f_so=0.04, sigma_so=4.0, alpha_par=0.97, alpha_perp=1.02)),
+    }
+    names = ['sigma8_z', 'f', 'alpha_par', 'alpha_perp', 'alpha_drag', 'b1_cA', 'b1_cB', 'b1_sA', 'b1_sB', 'fs', 'fcB',
+             'fsB', 'sigma_c', 'sigma_sA', 'sigma_sB', 'NcBs', 'NsBsB', 'f_so', 'sigma_so', 'sigma_v', 'D']
+    for name, (z, kw, upd) in cases.items():
+        model = build_model(cosmo_mod, cosmo, z, **kw)
+        model.update(**upd)
+        P = np.asarray(model.power(k, mu))
+        out[name + '_P'] = P
+        out[name + '_pars'] = np.array([float(getattr(model, n)) for n in names])
+        out[name + '_modelk'] = np.asarray(model.k)
+        # the four moment splines of one bias pair, for a finer-grained check
+        model.b1, model.b1_bar = model.b1_cB, model.b1_sA
+        out[name + '_moments_cBsA'] = np.array([model.P_mu0(model.k), model.P_mu2(model.k), model.P_mu4(model.k),
+                                                model.P_mu6(model.k)])
+        out[name + '_sigma_lin'] = float(model.sigma_lin)
+        out[name + '_velocity_kurtosis'] = float(model.velocity_kurtosis)
+        print(name, 'done  %.0fs' % (time.time() - t0), flush=True)
+        save_cache()
+    out['par_names'] = np.array(names)
+    path = os.path.join(HERE, 'galaxy_ref.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, '%.1f kB' % (os.path.getsize(path)/1e3))
+
+
+if __name__ == '__main__':
+    main()

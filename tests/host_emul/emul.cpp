@@ -17,6 +17,7 @@ extern "C" {
 void emul_set_config(double qmin, int n_outer, int n_inner, double ln_far, double ln_mid,
                      double bao_lo, double bao_hi, double bao_dq)
 {
+    g_cfg = QuadConfig();
     g_cfg.qmin = qmin; g_cfg.n_outer = n_outer; g_cfg.n_inner = n_inner;
     g_cfg.ln_far = ln_far; g_cfg.ln_mid = ln_mid;
     g_cfg.bao_lo = bao_lo; g_cfg.bao_hi = bao_hi; g_cfg.bao_dq = bao_dq;

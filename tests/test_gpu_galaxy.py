@@ -1,0 +1,123 @@
+"""GPU parity of the GalaxySpectrum P(k, mu) assembly against the UNMODIFIED reference Python run on
+the reference C++ at tight tolerances (tests/golden/galaxy_ref.npz, tests/golden/make_galaxy_ref.py),
+plus size-independent properties at the BASELINE C2 grid (1000 k x 40 mu)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, 'golden', 'galaxy_ref.npz')
+TOL = 1e-5
+
+CASES = {
+    'z0_default': (0.0, dict(), dict()),
+    'z055_ap': (0.55, dict(), dict()),
+    'z055_spt': (0.55, dict(use_P00_model=False, use_P01_model=False, use_P11_model=False, use_Pdv_model=False,
+                            use_Pvv_model=False, use_Phm_model=False), dict()),
+    'z055_so_gauss': (0.55, dict(use_so_correction=True, fog_model='gaussian', max_mu=6, use_tidal_bias=True), dict()),
+}
+
+
+@pytest.fixture(scope='module')
+def cosmo(golden):
+    return golden_pygcl_cosmology(golden)
+
+
+@pytest.fixture(scope='module')
+def engine():
+    from pyrsd_b200 import rsd
+    return rsd.PTEngine()
+
+
+def make_model(cosmo, engine, z, **kw):
+    from pyrsd_b200 import rsd
+    return rsd.GalaxySpectrum(params=cosmo, z=z, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine, **kw)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/galaxy_ref.npz not generated")
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_power_vs_reference_python(cosmo, engine, case):
+    ref = np.load(REF)
+    z, kw, _ = CASES[case]
+    model = make_model(cosmo, engine, z, **kw)
+    names = [str(n) for n in ref['par_names']]
+    pars = dict(zip(names, ref[case + '_pars']))
+    pars.pop('D')
+    model.update(**pars)
+    assert np.allclose(model.k, ref[case + '_modelk'], rtol=1e-14)
+    assert abs(model.sigma_lin/float(ref[case + '_sigma_lin']) - 1) < TOL
+    P = model.power(ref['k'], ref['mu'])
+    assert P.shape == ref[case + '_P'].shape
+    err = np.abs(P/ref[case + '_P'] - 1)
+    assert err.max() < TOL, (case, err.max())
+
+
+def test_power_properties_at_baseline_grid(cosmo, engine):
+    """BASELINE config C2: 1000 k x 40 mu.  No oracle at this size: identities the model must obey."""
+    model = make_model(cosmo, engine, 0.55)
+    k = np.logspace(-2.9, np.log10(0.49), 1000)
+    mu = np.linspace(0., 1., 40)
+    P = model.power(k, mu)
+    assert P.shape == (1000, 40) and np.all(np.isfinite(P)) and np.all(P > 0)
+    # flatten = column-major ravel (power_dm.py:1011-1012)
+    assert np.array_equal(model.power(k, mu, flatten=True), np.ravel(P, order='F'))
+    # paired (k, mu) evaluation equals the grid
+    assert np.array_equal(model.power(k[::50], np.full(20, mu[7])), P[::50, 7])
+    # isotropic AP: P_obs(k, mu) = P(k/alpha, mu)/alpha^3 (rsd/tools.py:54-75, 211)
+    a = 1.02
+    model.update(alpha_par=a, alpha_perp=a)
+    Pa = model.power(k[100:900:40], mu)
+    model.update(alpha_par=1., alpha_perp=1.)
+    assert np.max(np.abs(Pa*a**3/model.power(k[100:900:40]/a, mu) - 1)) < 1e-12
+    # alpha_drag rescales by its cube (tools.py:214)
+    model.update(alpha_drag=1.01)
+    assert np.max(np.abs(model.power(k[::100], mu)/(1.01**3*P[::100]) - 1)) < 1e-13
+    model.update(alpha_drag=1.)
+    # no satellites: only the centrals' terms survive; mu = 0 is undamped
+    model.update(fs=0., fcB=0.)
+    P0 = model.power(k[::100], np.array([0.]))
+    model.update(sigma_c=7.)
+    assert np.max(np.abs(model.power(k[::100], np.array([0.]))/P0 - 1)) < 1e-14
+    # out-of-domain k raises like the reference's InterpolationDomainError
+    with pytest.raises(ValueError):
+        model.power(np.array([0.9]), np.array([0.5]))
+
+
+def test_moment_splines_reproduce_knots(cosmo, engine):
+    """the not-a-knot splines of P[mu^n] interpolate their knots (RSDSpline on self.k)"""
+    model = make_model(cosmo, engine, 0.)
+    kmodel = model.k
+    P = model.power(kmodel, np.array([0., 0.5, 1.0]))
+    gal = engine.galaxy(kmodel, model._config())
+    mom = engine.galaxy_moments(gal, 1)[0]           # [pair][moment][nkm]
+    assert mom.shape == (10, 4, len(kmodel)) and np.all(np.isfinite(mom))
+    # with fs = fcB = 0 and mu = 0 the model is the cAcA P[mu^0] knot values themselves
+    model.update(fs=0., fcB=0.)
+    P0 = model.power(kmodel, np.array([0.]))
+    assert np.max(np.abs(P0/engine.galaxy_moments(gal, 1)[0][0, 0] - 1)) < 1e-13
+
+
+def test_walker_batch_matches_single_evaluations(cosmo, engine):
+    """many walkers on one cosmology (the reference's fitting mode) == one at a time"""
+    from pyrsd_b200 import rsd
+    model = make_model(cosmo, engine, 0.55)
+    k = np.logspace(-2, np.log10(0.4), 30)
+    mu = np.linspace(0, 1, 5)
+    kk, mm = [a.ravel() for a in np.meshgrid(k, mu, indexing='ij')]
+    rng = np.random.default_rng(7)
+    pars, stochs, singles = [], [], []
+    for i in range(5):
+        model.update(sigma8_z=rng.uniform(0.5, 0.8), f=rng.uniform(0.6, 0.9), b1_cA=rng.uniform(1.5, 2.2),
+                     alpha_par=rng.uniform(0.97, 1.03), alpha_perp=rng.uniform(0.97, 1.03), fs=rng.uniform(0.05, 0.2))
+        pars.append(model._walker())
+        stochs.append(model._stoch(model.k))
+        singles.append(model.power(kk, mm))
+    model._ensure_tables()
+    gal = engine.galaxy(model.k, model._config())
+    out = engine.galaxy_power(gal, model._spectra, model._result, np.array(pars), np.array(stochs), kk, mm,
+                              cmap=np.zeros(5, dtype=np.int32))
+    assert np.array_equal(out, np.array(singles))

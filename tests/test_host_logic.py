@@ -1,0 +1,103 @@
+"""Host logic shared with the CUDA kernels (knot grid, panel generator, kernel formulae, table
+reads, product-integration weights) exercised on the CPU through tests/host_emul and checked
+against the reference C++ at tight tolerance (tests/golden/oracle_tight.npz).  CPU only."""
+import numpy as np
+import pytest
+
+KID = dict(I=lambda m, n: 4*m + n)
+K_IDS = [16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28]
+
+
+@pytest.fixture(scope='module')
+def table(emul, golden, tight):
+    h = float(golden['cosmo_h'])
+    args = (float(golden['cosmo_n_s']), float(tight['delta_H'])**2, h, float(tight['Omega0_m']),
+            float(golden['cosmo_Omega_b']), float(tight['Tcmb']))
+    return emul.plin_table(golden['cosmo_k'], golden['cosmo_T'], *args), args
+
+
+def test_knot_grid(emul):
+    x = emul.knots()
+    assert len(x) == 2342
+    d = np.diff(x)
+    assert np.all(d >= 0) and np.sum(d == 0) == 5          # zone edges are duplicated, nothing else
+    for edge in (1e-5, 10., 100.):
+        assert np.min(np.abs(x - np.log(edge))) < 1e-12
+
+
+def test_plin_matches_reference_formula(emul, ref_plin, golden, table):
+    _, args = table
+    q = np.exp(np.random.default_rng(0).uniform(np.log(1e-8), np.log(1e5), 3000))
+    out = emul.plin_eval(golden['cosmo_k'], golden['cosmo_T'], *args, q)
+    assert np.max(np.abs(out/ref_plin(q) - 1)) < 1e-13
+
+
+def test_table_read_accuracy(emul, ref_plin, table):
+    tab, _ = table
+    q = np.exp(np.random.default_rng(1).uniform(np.log(1e-7), np.log(15.), 4000))
+    err = np.abs(emul.table_read(tab, q)/ref_plin(q) - 1)
+    assert err.max() < 2e-6 and np.median(err) < 5e-8
+
+
+def test_netlib_spline_matches_reference(emul, oracle):
+    x = np.exp(np.linspace(np.log(1e-5), np.log(10.), 1000))
+    y = np.sin(3*np.log(x))*x**-0.7
+    xq = np.exp(np.random.default_rng(2).uniform(np.log(1e-5), np.log(10.), 2000))
+    assert np.max(np.abs(emul.spline(x, y, xq) - oracle.CubicSpline(x, y, xq))) < 1e-11*np.max(np.abs(y))
+    assert emul.spline(x, y, np.array([0.5e-5, 11.]))[0] == 0.0      # zero outside the domain (Spline.cpp:362-367)
+
+
+@pytest.mark.parametrize('idx', [0, 5, 7, 10, 12, 15])
+def test_imn_fixed_rule_vs_tight_reference(emul, tight, table, idx):
+    tab, _ = table
+    out, nodes = emul.ik(idx, tight['k'], tab, tab, 0)
+    err = np.abs(out - tight['I'][idx])/np.maximum(np.abs(tight['I'][idx]), tight['plin_k'])
+    assert err.max() < 1e-5, err
+    assert nodes/len(tight['k']) < 2e4
+
+
+@pytest.mark.parametrize('j', [0, 2, 6, 8, 10, 12])
+def test_kmn_fixed_rule_vs_tight_reference(emul, tight, table, j):
+    tab, _ = table
+    out, _ = emul.ik(K_IDS[j], tight['k'], tab, tab, 1)
+    err = np.abs(out - tight['K'][j])/np.maximum(np.abs(tight['K'][j]), tight['plin_k'])
+    assert err.max() < 1e-5, err
+
+
+def test_jmn_product_integration_vs_tight_reference(emul, tight, table):
+    tab, _ = table
+    sel = tight['k'] <= 1.0
+    for j, sub in enumerate([0, 1, 2, 3, 4, 6]):
+        out = emul.linear(0, sub, tight['k'][sel], 1e-5, 1e5, tab)
+        assert np.max(np.abs(out/tight['J'][j][sel] - 1)) < 1e-5
+
+
+def test_one_dimensional_integrals_vs_tight_reference(emul, tight, table):
+    tab, _ = table
+    assert abs(emul.linear(1, 0, [0.], 1e-5, 100., tab)[0]/float(tight['sigma_v2']) - 1) < 1e-7
+    r = tight['r'][::3]
+    X = emul.linear(2, 0, r, 1e-5, 100., tab)
+    Y = emul.linear(3, 0, r, 1e-5, 100., tab)
+    scale = 2*float(tight['sigma_v2'])
+    assert np.max(np.abs(X - tight['X_Zel'][::3])) < 1e-7*scale
+    assert np.max(np.abs(Y - tight['Y_Zel'][::3])) < 1e-7*scale
+    q3 = emul.linear(4, 0, [0.], 1e-5, 100., tab*tab, scale=1/(10*np.pi**2))[0]
+    assert abs(q3/float(tight['Q3_at_k1']) - 1) < 1e-7
+    sig = np.sqrt(emul.linear(5, 0, tight['Sigma_R'], 1e-5, 100., tab))
+    assert np.max(np.abs(sig/tight['Sigma'] - 1)) < 1e-7
+
+
+def test_not_a_knot_spline_matches_scipy():
+    import ctypes as C
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    from tests.host_emul import emul_lib
+    L = emul_lib.load().L
+    dp = emul_lib.dp
+    L.emul_nak_spline.argtypes = [C.c_int, dp, dp, C.c_int, dp, dp]
+    for n in (20, 200):
+        x = np.logspace(-3, np.log10(0.5), n)
+        y = np.cos(25*x)*x**-1.1 + 3
+        xq = np.exp(np.random.default_rng(3).uniform(np.log(x[0]), np.log(x[-1]), 1000))
+        out = np.empty_like(xq)
+        L.emul_nak_spline(n, x, y, len(xq), xq, out)
+        assert np.max(np.abs(out/InterpolatedUnivariateSpline(x, y)(xq) - 1)) < 1e-12
