@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- full PT P(k, mu) model evaluations per second (BASELINE.json metric).
+
+One "evaluation" = rebuild of EVERY perturbation-theory table for a new linear P(k) (16 I_mn, 6 J_mn,
+13 K_mn, the four one-loop spectra on 1000 k, the 7 x 3 ImnOneLoop integrals, sigma_v^2(k), X(r), Y(r),
+Zel'dovich P00/P01/P11) plus one GalaxySpectrum.power on the BASELINE C2 grid (1000 k x 40 mu).
+One "step" = a batch of `--batch` such evaluations per GPU (distinct synthetic cosmologies).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); cosmologies are sharded over ranks with no data-path
+collective, the per-walker result (mu-averaged P(k), 1000 doubles) is all-gathered over NCCL inside the
+timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "full PT P(k,mu) model evals/sec"
+UNIT = "evals/s"
+NK_OUT, NMU_OUT = 1000, 40
+SEED = 20261019
+
+
+# ----------------------------------------------------------------------------- workload
+def synthetic_batch(n, rank=0):
+    """n synthetic cosmologies + walker vectors: base = the reference's shipped Planck15 transfer
+    function; variant i: sigma8_z in U[0.45, 0.95], f in U[0.4, 1.0], b1_cA in U[1.2, 2.5] and a shape tilt
+    T_i(k) (k/0.05)^(delta/2), delta ~ N(0, 0.02), so that every table genuinely has to be rebuilt."""
+    from tests.gpu_common import b2_00, b2_01, stochasticity
+    from pyrsd_b200 import rsd
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_pt.npz'))
+    t = np.load(os.path.join(ROOT, 'tests', 'golden', 'oracle_tight.npz'))
+    rng = np.random.default_rng(SEED + 1000*rank)
+    k_i, T_i = g['cosmo_k'], g['cosmo_T']
+    delta = rng.normal(0, 0.02, n)
+    T = T_i[None, :]*(k_i[None, :]/0.05)**(delta[:, None]/2)
+    k = np.repeat(k_i[None, :], n, axis=0)
+    pars = np.zeros((n, 8))
+    pars[:, 0] = float(g['cosmo_n_s'])
+    pars[:, 1] = float(t['delta_H'])**2        # re-normalisation to sigma8 is per-cosmology algebra done at assembly
+    pars[:, 2] = float(g['cosmo_h'])
+    pars[:, 3] = float(t['Omega0_m'])
+    pars[:, 4] = float(g['cosmo_Omega_b'])
+    pars[:, 5] = float(t['Tcmb'])
+    s8z = rng.uniform(0.45, 0.95, n)
+    f = rng.uniform(0.4, 1.0, n)
+    b1cA = rng.uniform(1.2, 2.5, n)
+    kmodel = np.logspace(np.log10(1e-3), np.log10(0.5), 200)
+    ks = rsd.stochasticity_grid(kmodel)
+    wpar = np.zeros((n, rsd.NPAR))
+    stoch = np.zeros((n, rsd.NPAIR, rsd.NSTOCH))
+    for i in range(n):
+        b1 = [b1cA[i], 1.5*b1cA[i], 1.4*b1cA[i], 1.9*b1cA[i]]
+        b00, b01 = [b2_00(b) for b in b1], [b2_01(b) for b in b1]
+        wpar[i] = rsd.pack_walker(s8z[i], f[i], 1.0, 1.0, 1.0, b1, 0.10, 0.08, 0.40, 1.0, 4.2, 6.0, 3e4, 9e4, 0., 0., None,
+                                  0.7486, float(g['cosmo_sigma8']), [b00, b00, b00, b00, b01, b01])
+        for p, (a, b) in enumerate(rsd.PAIRS):
+            lo, hi = sorted([b1[a], b1[b]])
+            stoch[i, p] = stochasticity(ks, s8z[i], lo, hi)
+    kout = np.logspace(-2.95, np.log10(0.49), NK_OUT)
+    mu = np.linspace(0., 1., NMU_OUT)
+    kk, mm = [a.ravel() for a in np.meshgrid(kout, mu, indexing='ij')]
+    return dict(k=k, T=T, pars=pars, wpar=wpar, stoch=stoch, kmodel=kmodel, kk=np.ascontiguousarray(kk), mm=np.ascontiguousarray(mm))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for j, name in enumerate(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']):
+            if any(s[2 + j].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm)//2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from pyrsd_b200 import _native as N, pygcl, rsd
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    L = rsd._L()
+    vp, dp = C.c_void_p, N._dp
+    L.prsd_ctx_profile.argtypes = [vp, C.c_int]
+    L.prsd_ctx_profile_read.argtypes = [vp, dp, np.ctypeslib.ndpointer(dtype=np.int64, flags='C_CONTIGUOUS')]
+    L.prsd_fp64_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.prsd_spectra_reload_device.argtypes = [vp, vp, vp, vp]
+    L.prsd_ctx_stream.argtypes = [vp, C.POINTER(vp)]
+
+    ctx = N.default_context(local)
+    sptr = vp()
+    N.check(L.prsd_ctx_stream(ctx.ptr, C.byref(sptr)))
+    stream = torch.cuda.ExternalStream(sptr.value, device=torch.device('cuda', local))
+
+    B = args.batch
+    data = synthetic_batch(B, rank)
+    eng = rsd.PTEngine(context=ctx)
+    info = eng.info()
+    gal = eng.galaxy(data['kmodel'], rsd.galaxy_config())
+    npts = len(data['kk'])
+
+    # pinned host staging (e2e) and device-resident copies (value)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    h_k, h_T, h_pars = pinned(data['k']), pinned(data['T']), pinned(data['pars'])
+    h_wpar, h_stoch = pinned(data['wpar']), pinned(data['stoch'])
+    h_kk, h_mm = pinned(data['kk']), pinned(data['mm'])
+    h_out = torch.empty((B, npts), dtype=torch.float64, pin_memory=True)
+    dev = torch.device('cuda', local)
+    d_k, d_T, d_pars = h_k.to(dev), h_T.to(dev), h_pars.to(dev)
+    d_kk, d_mm = h_kk.to(dev), h_mm.to(dev)
+    d_out = torch.empty((B, npts), dtype=torch.float64, device=dev)
+    gather = torch.empty((world*B, NK_OUT), dtype=torch.float64, device=dev) if world > 1 else None
+    # L2 flush buffer (> 126 MB): written between timed iterations
+    flush = torch.empty(64*1024*1024, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    sp = eng.spectra(data['k'], data['T'], data['pars'][:, 0], data['pars'][:, 1], data['pars'][:, 2], data['pars'][:, 3],
+                     data['pars'][:, 4], data['pars'][:, 5])
+    res = rsd._new_result()
+
+    def step_device():
+        """inputs resident in HBM, outputs left in HBM"""
+        N.check(L.prsd_spectra_reload_device(sp.ptr, d_k.data_ptr(), d_T.data_ptr(), d_pars.data_ptr()))
+        eng.run(sp, result=res)
+        N.check(L.prsd_galaxy_power_device(gal.ptr, sp.ptr, res.ptr, B, None, h_wpar.numpy(), h_stoch.numpy(), npts,
+                                           d_kk.data_ptr(), d_mm.data_ptr(), d_out.data_ptr()))
+        if world > 1:
+            dist.all_gather_into_tensor(gather, d_out.view(B, NK_OUT, NMU_OUT).mean(-1))
+
+    def step_e2e():
+        """the public call path with HOST buffers: H2D of the step's inputs and D2H of P(k, mu) inside"""
+        sp2 = eng.spectra(h_k.numpy(), h_T.numpy(), h_pars.numpy()[:, 0], h_pars.numpy()[:, 1], h_pars.numpy()[:, 2],
+                          h_pars.numpy()[:, 3], h_pars.numpy()[:, 4], h_pars.numpy()[:, 5])
+        eng.run(sp2, result=res)
+        N.check(L.prsd_galaxy_power(gal.ptr, sp2.ptr, res.ptr, B, None, h_wpar.numpy(), h_stoch.numpy(), npts,
+                                    h_kk.numpy(), h_mm.numpy(), h_out.numpy()))
+        sp2.close()
+        return h_out
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+            flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if profile:
+            N.check(L.prsd_ctx_profile(ctx.ptr, 1))
+        l0 = ctx.launches()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in evs:
+            flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        launches = ctx.launches() - l0
+        prof = None
+        if profile:
+            pms, pc = np.zeros(6), np.zeros(6, dtype=np.int64)
+            N.check(L.prsd_ctx_profile_read(ctx.ptr, pms, pc))
+            N.check(L.prsd_ctx_profile(ctx.ptr, 0))
+            prof = (pms, pc)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof
+
+    # FP64 pipe peaks, measured once outside the timed region (MEASURED_PEAKS.json has no FP64 entry)
+    pk = C.c_double()
+    N.check(L.prsd_fp64_peak(ctx.ptr, 0, C.byref(pk)))
+    peak_dfma = pk.value
+    N.check(L.prsd_fp64_peak(ctx.ptr, 1, C.byref(pk)))
+    peak_dmma = pk.value
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, prof = timed(step_device, args.steps, args.warmup, profile=True)
+    ms_e2e, _, _ = timed(step_e2e, max(2, args.steps//2), 1)
+    sampler.stop_flag = True
+    e2e_steps = max(2, args.steps//2)
+
+    # quick in-run parity guard: the first cosmology of the batch equals an independent one-off evaluation
+    out0 = d_out[0].cpu().numpy()
+    assert np.all(np.isfinite(out0)) and np.all(out0 > 0)
+    assert np.allclose(step_e2e()[0].numpy(), out0, rtol=1e-12)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel family (DMMA contraction), see DESIGN.md section 5
+    pms, pc = prof
+    rows_1l = 8*((B + 7)//8)
+    flops_launch = {   # algorithmic FP64 flops per step: nodes x rows x (2 ncol + 9)
+        'oneloop': info['nodes_oneloop']*rows_1l*(2*6 + 9),
+        'ik': info['nodes_ik']*rows_1l*(2*37 + 9),
+        'ml': 2*info['nodes_ml_half']*B*8*(2*7 + 9),
+    }
+    flops_step = sum(flops_launch.values())
+    bil_ms_step = pms[0]/args.steps
+    achieved = flops_step/(bil_ms_step*1e-3)/1e12 if bil_ms_step > 0 else None
+    fam = ['bilinear_dmma', 'linear_ops', 'zeldovich', 'galaxy', 'spline_builds', 'fftlog']
+    shares = {fam[i]: round(pms[i]/ms_dev, 4) for i in range(6)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    value = world*B*args.steps/(ms_dev*1e-3)
+    e2e_value = world*B*e2e_steps/(ms_e2e*1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: GalaxySpectrum P(k,mu) full model (all one-loop + Zel'dovich terms) on 1000 k x 40 mu, "
+                               "every PT table rebuilt per cosmology; batch of %d distinct synthetic cosmologies per GPU per step" % B,
+                   "batch_per_gpu": B, "k_interp": 250, "oneloop_k": 1000, "model_k": 200, "out_grid": [NK_OUT, NMU_OUT],
+                   "quadrature_nodes_per_cosmology": info['nodes'], "l2": "flushed between timed iterations (256 MB write)",
+                   "parallelism": "walkers sharded over %d rank(s), NCCL all-gather of the mu-averaged P(k)" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(h_k.numel()*8 + h_T.numel()*8 + h_pars.numel()*8 + h_wpar.numel()*8 + h_stoch.numel()*8
+                                          + h_kk.numel()*8 + h_mm.numel()*8),
+                "d2h_bytes_per_step": int(h_out.numel()*8), "ms_per_step": ms_e2e/e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
+                     "frac": (achieved/peak_dmma) if (achieved and peak_dmma) else None, "traffic": None,
+                     "kernel": "k_bilinear_apply<NT> (FP64 DMMA m8n8k4 contraction, 3 operators x launches per step)",
+                     "peak_source": "FP64 DMMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                                    "DFMA pipe measured at %.1f TFLOP/s; hbm_gbs of measured = %s" % (peak_dfma, peaks.get('hbm_gbs')),
+                     "algorithmic_flops_per_step": flops_step, "kernel_ms_per_step": bil_ms_step,
+                     "launches_per_step": int(pc[0]//args.steps), "kernel_share_of_step": shares},
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ CPU reference (oracle)
+def _cpu_sample(seed):
+    """a BOUNDED sample of one full evaluation on the reference's own C++ (oracle/_ref) at the reference's default
+    tolerances; returns the estimated seconds of the full evaluation (sample time / fraction of the work)."""
+    from oracle import gcl_ref as R
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_pt.npz'))
+    cosmo = R.golden_cosmology(g)
+    P = R.RefLinearPS(cosmo)
+    rng = np.random.default_rng(seed)
+    kint = np.logspace(np.log10(5e-6), 0, 250)
+    sub = np.sort(rng.choice(250, 10, replace=False))            # 1/25 of k_interp
+    k1 = R.logspace(1e-5, 10, 1000)
+    sub1 = np.sort(rng.choice(1000, 20, replace=False))          # 1/50 of the one-loop grid
+    t_total = 0.0
+    t0 = time.perf_counter()
+    for m in range(4):
+        for n in range(4):
+            R.Imn(P, kint[sub], m, n, epsrel=1e-4)
+    for (m, n) in [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (2, 0)]:
+        R.Jmn(P, kint[sub], m, n, epsrel=1e-4)
+    for (m, n, t, p) in [(0, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 1, 1, 0), (0, 2, 1, 0), (1, 0, 0, 0), (1, 1, 0, 0),
+                         (1, 0, 1, 0), (1, 1, 1, 0), (2, 0, 0, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1)]:
+        R.Kmn(P, kint[sub], m, n, bool(t), p, epsrel=1e-3)
+    P.VelocityDispersion(kint[sub], 0.5)
+    t_total += (time.perf_counter() - t0)*25
+    t0 = time.perf_counter()
+    for (m, n) in [(0, 0), (0, 1), (1, 1), (2, 3), (3, 2), (3, 3)]:
+        R.Imn(P, k1[sub1], m, n, epsrel=1e-4)
+    for (m, n) in [(0, 0), (0, 1), (1, 1)]:
+        R.Jmn(P, k1[sub1], m, n, epsrel=1e-4)
+    t_total += (time.perf_counter() - t0)*50
+    # ImnOneLoop on the shipped one-loop tables
+    ol = {w: R.RefOneLoop(P, w, 1e-4, g['oneloop_P%s_0' % w]) for w in ('dd', 'dv', 'vv')}
+    sub2 = sub[:5]                                                 # 1/50
+    t0 = time.perf_counter()
+    for (p1, p2, m, n) in [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
+                           ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]:
+        for which in ('linear', 'cross', 'oneloop'):
+            R.ImnOneLoop(ol[p1], None if p2 is None else ol[p2], kint[sub2], m, n, which, 1e-4)
+    t_total += (time.perf_counter() - t0)*50
+    # Zel'dovich set-up X(r), Y(r) and P00/P01/P11 on the 200-point model grid
+    r = 10.**(1.5 + (np.arange(1, 1025) - 512.5)*(7./1024))
+    subr = np.sort(rng.choice(1024, 16, replace=False))           # 1/64
+    t0 = time.perf_counter()
+    P.X_Zel(r[subr])
+    P.Y_Zel(r[subr])
+    t_total += (time.perf_counter() - t0)*64
+    state = (float(g['zel_sigma8_z']), float(g['zel_k0_low']), float(g['zel_sigmasq']), g['zel_X0'], g['zel_XX'], g['zel_YY'])
+    z = R.RefZeldovich(cosmo, False, state)
+    km = np.logspace(-3, np.log10(0.5), 200)[::20]                # 1/20
+    t0 = time.perf_counter()
+    for name in ('P00', 'P01', 'P11'):
+        z(name, km)
+        z(name, km)                                               # second normalisation (Jennings fits at sigma8_z / D)
+    t_total += (time.perf_counter() - t0)*20
+    return t_total
+
+
+def cpu_baseline_sample():
+    """reference C++ (oracle/_ref), 1 core (its packaged build has no OpenMP, setup.py:188), bounded sample"""
+    from oracle import gcl_ref as R
+    if not R.available():
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/libgcl_ref.so missing"}
+    t0 = time.perf_counter()
+    est = _cpu_sample(SEED)
+    wall = time.perf_counter() - t0
+    return {"value": 1.0/est, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "reference C++ at its default epsrel on 1/25 of k_interp (all 16 I, 6 J, 13 K, sigma_v^2(k)), 1/50 of the one-loop "
+                      "grid (6 I + 3 J), 1/50 of the ImnOneLoop work, 1/64 of X(r)/Y(r), 1/20 of the Zel'dovich P00/P01/P11 "
+                      "evaluations; each part scaled by its fraction (%.1f s of CPU work -> %.1f s per full evaluation); the "
+                      "Python P(k,mu) assembly of the reference (<1 s) is NOT included" % (wall, est),
+            "seconds_per_eval_estimate": est}
+
+
+def _ref_worker(seed):
+    return _cpu_sample(seed)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on every host core (one process per core, one
+    cosmology each: how rsdfit's MPI pool uses it), bounded sample per step"""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import gcl_ref as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgcl_ref.so missing on this box"}))
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    cores = max(1, min(cores, 64))
+    pool = mp.get_context('fork').Pool(cores)
+    for w in range(args.warmup if args.warmup < 2 else 1):
+        pool.map(_ref_worker, [SEED + i for i in range(cores)])
+    t0 = time.perf_counter()
+    ests = []
+    for s in range(args.steps):
+        ests += pool.map(_ref_worker, [SEED + 100*s + i for i in range(cores)])
+    wall = time.perf_counter() - t0
+    pool.close()
+    # every worker processed a bounded sample standing for one full evaluation of `est` seconds
+    est = float(np.mean(ests))
+    value = cores/est
+    sample = ("%d processes x %d steps, each a bounded sample of one full evaluation (fractions as in cpu_baseline); "
+              "mean estimated %.1f s per evaluation per core; wall %.1f s" % (cores, args.steps, est, wall))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3*wall/max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: full PT table rebuild per cosmology (reference C++ at default epsrel, no Python assembly)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=128, help='cosmologies per GPU per step')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        if args.steps > 3:
+            args.steps = 3
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

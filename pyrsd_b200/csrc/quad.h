@@ -27,7 +27,7 @@ struct QuadConfig {
     double ln_far   = 2.0;    // max panel width in ln q, featureless power-law regions
     double ln_mid   = 0.5;    // max panel width in ln q for mid_lo <= q <= mid_hi
     double mid_lo   = 1e-3;
-    double mid_hi   = 2.0;
+    double mid_hi   = 10.0;
     double bao_lo   = 0.01;   // panels at most bao_dq wide in q (not ln q) in the BAO range
     double bao_hi   = 0.7;
     double bao_dq   = 0.05;

@@ -25,11 +25,47 @@ EPS2D = 1e-9
 EPS1D = 1e-10
 
 
+def ml_part(out, R, PL, kint, t0):
+    # ImnOneLoop at tight eps with COMMON one-loop tables as input to both sides.  The reference's shipped
+    # (default-eps) tables carry point-to-point quadrature noise of ~1e-4, which its own 1000-point spline then
+    # interpolates; parity of the ImnOneLoop stage is defined on smooth inputs, so the common tables are the
+    # reference's own OneLoopP* constructors run at epsrel = 1e-7 (stored in the fixture).
+    common = {}
+    for w in ('dd', 'dv', 'vv', '22bar'):
+        common[w] = R.RefOneLoop(PL, w, 1e-7).table()
+        print('one-loop table', w, 'done %.0fs' % (time.time() - t0), flush=True)
+    out['oneloop_common'] = np.array([common[w] for w in ('dd', 'dv', 'vv', '22bar')])
+    ol = {w: R.RefOneLoop(PL, w, 1e-7, common[w]) for w in ('dd', 'dv', 'vv', '22bar')}
+    out['kurtosis_common_tables'] = ol['22bar'].VelocityKurtosis(1e-10)
+    kml = kint[[60, 130, 170, 195, 215, 235, 249]]
+    out['k_ml'] = kml
+    spec = [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
+            ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]
+    ML = np.empty((7, 3, len(kml)))
+    for j, (p1, p2, m, n) in enumerate(spec):
+        for w, which in enumerate(('linear', 'cross', 'oneloop')):
+            ML[j, w] = R.ImnOneLoop(ol[p1], None if p2 is None else ol[p2], kml, m, n, which, epsrel=1e-8)
+        print('ML %d done %.0fs' % (j, time.time() - t0), flush=True)
+    out['ML'] = ML
+
+
+
+def finish_ml(out, R, PL, kint, t0, path):
+    ml_part(out, R, PL, kint, t0)
+    np.savez_compressed(path, **out)
+    print('wrote', path, '%.1f kB' % (os.path.getsize(path)/1e3))
+
+
 def main():
     g = np.load(os.path.join(HERE, 'golden_pt.npz'))
     cosmo = R.golden_cosmology(g)
     PL = R.RefLinearPS(cosmo)
     out = {'delta_H': cosmo.delta_H(), 'Omega0_m': cosmo.args[5], 'Tcmb': cosmo.args[7]}
+    path = os.path.join(HERE, 'oracle_tight.npz')
+    ml_only = '--ml-only' in sys.argv and os.path.exists(path)
+    if ml_only:
+        out = dict(np.load(path))
+        out.pop('kurtosis_golden_tables', None)
 
     # 20 k values: a spread of k_interp points plus high-k points of the one-loop grid
     kint = g['k_interp']
@@ -38,6 +74,8 @@ def main():
     out['k'] = k
     out['plin_k'] = PL(k)
     t0 = time.time()
+    if ml_only:
+        return finish_ml(out, R, PL, kint, t0, path)
     I = np.empty((16, len(k)))
     for m in range(4):
         for n in range(4):
@@ -69,19 +107,7 @@ def main():
     out['Sigma'] = PL.Sigma_tol(out['Sigma_R'])
     print('1-D done %.0fs' % (time.time() - t0), flush=True)
 
-    # ImnOneLoop at tight eps, with the GOLDEN (default-eps) one-loop tables as common input
-    ol = {w: R.RefOneLoop(PL, w, 1e-4, g['oneloop_P%s_0' % w]) for w in ('dd', 'dv', 'vv', '22bar')}
-    out['kurtosis_golden_tables'] = ol['22bar'].VelocityKurtosis(1e-10)
-    kml = kint[[60, 130, 170, 195, 215, 235, 249]]
-    out['k_ml'] = kml
-    spec = [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
-            ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]
-    ML = np.empty((7, 3, len(kml)))
-    for j, (p1, p2, m, n) in enumerate(spec):
-        for w, which in enumerate(('linear', 'cross', 'oneloop')):
-            ML[j, w] = R.ImnOneLoop(ol[p1], None if p2 is None else ol[p2], kml, m, n, which, epsrel=1e-8)
-        print('ML %d done %.0fs' % (j, time.time() - t0), flush=True)
-    out['ML'] = ML
+    ml_part(out, R, PL, kint, t0)
 
     # tight one-loop tables on a sparse subset of the 1000-point grid
     k1 = R.logspace(1e-5, 10, 1000)
