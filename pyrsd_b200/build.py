@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libpyrsd_b200.so')
 
-CU_SOURCES = ['context.cu', 'bilinear.cu', 'linear.cu', 'spectra.cu', 'plan.cu', 'zeldovich.cu',
+CU_SOURCES = ['context.cu', 'bilinear.cu', 'nodal.cu', 'linear.cu', 'spectra.cu', 'plan.cu', 'zeldovich.cu',
               'fftlog.cu', 'xilm.cu', 'galaxy.cu', 'microbench.cu', 'capi.cu']
 CXX_SOURCES = ['quad.cpp', 'fftlog_host.cpp']
 

@@ -74,7 +74,7 @@ __host__ __device__ inline int w_slot(int col, int nt) { return (col & 7)*nt + (
 
 struct ColSpecDev { int kid; int sign; double fac; };
 
-__global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, const ColSpecDev* __restrict__ cols,
+__global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, int soa, const ColSpecDev* __restrict__ cols,
                           const int64_t* __restrict__ outer_off, const int64_t* __restrict__ node_off, int nk,
                           const double* __restrict__ kk, const double* __restrict__ a_arr,
                           const int* __restrict__ n_outer_local, const double* __restrict__ b_arr,
@@ -100,17 +100,20 @@ __global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, const ColSpe
         double val = 0.0;
         if (c < ncol_used && w != 0.0) {
             const ColSpecDev cs = cols[c];
-            const double f = cs.sign > 0 ? pt_kernel(cs.kid, u, vp, ea, eb)
-                                         : pt_kernel(cs.kid, u, -vp, eb, ea);
+            double f = 0.0;
+            if (cs.sign >= 0) f += pt_kernel(cs.kid, u, vp, ea, eb);
+            if (cs.sign <= 0) f += pt_kernel(cs.kid, u, -vp, eb, ea);
             val = w*k*cs.fac*f;
         }
-        row[w_slot(c, nt)] = val;
+        if (soa) { if (c < ncol_used) W[(int64_t)c*n_nodes + node] = val; }
+        else row[w_slot(c, nt)] = val;
     }
 }
 
-void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols)
+void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols, bool soa_layout)
 {
     geo = g;
+    soa = soa_layout;
     ncol_used = (int)cols.size();
     ncol = (ncol_used + 7)/8*8;
     PRSD_REQUIRE(ncol_used > 0 && ncol <= 40, "BilinearOp: %d columns unsupported", ncol_used);
@@ -118,10 +121,10 @@ void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std:
     for (int i = 0; i < ncol_used; i++) hc[i] = {cols[i].kid, cols[i].sign, cols[i].fac};
     DevBuf<ColSpecDev> dc;
     dc.upload(hc, ctx.stream);
-    W.alloc((size_t)g->n_nodes*ncol);
+    W.alloc((size_t)g->n_nodes*(soa ? ncol_used : ncol));
     const int threads = 128;
     const int64_t blocks = (g->n_nodes + threads - 1)/threads;
-    k_build_w<<<(unsigned)blocks, threads, 0, ctx.stream>>>(g->n_nodes, ncol, ncol_used, dc.p, g->outer_off.p,
+    k_build_w<<<(unsigned)blocks, threads, 0, ctx.stream>>>(g->n_nodes, ncol, ncol_used, soa ? 1 : 0, dc.p, g->outer_off.p,
         g->node_off.p, g->nk, g->kdev.p, g->a.p, g->n_outer_local.p, g->b.p, g->wgt.p, W.p);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
@@ -246,6 +249,7 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
 void BilinearOp::apply(Context& ctx, const double* tables, const int* slot_tab, const int* rowA,
                        const int* rowB, int ntiles, double* out) const
 {
+    PRSD_REQUIRE(!soa, "BilinearOp::apply: operator was built for the nodal kernels");
     switch (ncol/8) {
         case 1: launch_apply<1>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
         case 2: launch_apply<2>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;

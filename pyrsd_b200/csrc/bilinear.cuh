@@ -16,12 +16,12 @@
 
 namespace prsd {
 
-static const int TAB_M    = 2342;   // knots of make_knot_grid() (checked at start-up)
-static const int TAB_MPAD = 2356;   // row stride of every spectra table: = 4 (mod 16) doubles
+static const int TAB_M    = 2457;   // knots of make_knot_grid() (checked at start-up)
+static const int TAB_MPAD = 2468;   // row stride of every spectra table: = 4 (mod 16) doubles
 
 struct ColSpec {
     int kid;        // KernelId
-    int sign;       // +1: f(u, +v') with P_1(a) P_2(b);  -1: f(u, -v') (the r <= q half)
+    int sign;       // +1: f(u, +v') with P_1(a) P_2(b);  -1: f(u, -v') (the r <= q half);  0: their sum
     double fac;     // coefficient c in the prefactor c * k  (k/(8 pi^2) etc.)
 };
 
@@ -48,8 +48,10 @@ struct BilinearOp {
     std::shared_ptr<NodeGeometry> geo;
     int ncol = 0;       // padded to a multiple of 8
     int ncol_used = 0;
-    DevBuf<double> W;   // [n_nodes][ncol] in fragment-major column order
-    void build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols);
+    bool soa = false;   // false: W [n_nodes][ncol] in fragment-major column order (DMMA kernel);
+                        // true : W [ncol_used][n_nodes] (one-lane-per-node kernels, nodal.cuh)
+    DevBuf<double> W;
+    void build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols, bool soa_layout = false);
 
     // out[row][k][ncol] (device) = sum_nodes W * TA_row(a) * TB_row(b)
     //   tables   : device pool [ntab][TAB_MPAD]

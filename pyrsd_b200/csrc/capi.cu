@@ -405,7 +405,7 @@ int prsd_plan_info(prsd_plan* plan, double* info)
         info[4] = TAB_M;
         info[5] = p.op_1loop.geo ? (double)p.op_1loop.geo->n_nodes : 0.0;
         info[6] = p.op_ik.geo ? (double)p.op_ik.geo->n_nodes : 0.0;
-        info[7] = p.op_ml_pos.geo ? (double)p.op_ml_pos.geo->n_nodes : 0.0;
+        info[7] = p.op_ml.geo ? (double)p.op_ml.geo->n_nodes : 0.0;
     });
 }
 int prsd_plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res)

@@ -1,0 +1,241 @@
+// nodal.cu -- one-lane-per-node evaluation of the ImnOneLoop and one-loop-table operators (see nodal.cuh).
+#include "nodal.cuh"
+#include "pt_math.cuh"
+#include "ptx.cuh"
+
+namespace prsd {
+
+static const int NL_THREADS = 256;
+static const int NL_WARPS = NL_THREADS/32;
+static const int NL_SLOTS = 4;
+static const double NL_INV8PI2 = 1.0/(8.0*M_PI*M_PI);
+
+struct NodalArgs {
+    int nk, max_outer, kchunk, nrow;
+    const int64_t* outer_off;
+    const int64_t* node_off;
+    const int* a_j0;
+    const double* a_coef;
+    const int* b_j0;
+    const int* ol;
+    const double* b_coef;
+    const double* W;        // [NW][n_nodes]
+    int64_t n_nodes;
+    const double* tables;
+    const int* slot_tab;    // [ntiles][4]
+    double* out;
+};
+
+// ------------------------------------------------------------------ ImnOneLoop
+// slots: 0 P_L, 1 P_dd, 2 P_dv, 3 P_vv.  W columns (ml_columns()):
+//   0..5   (f(+v) + f(-v)) of h01 h02 h03 h04 f23 f33          -> products symmetric in (a, b)
+//   6..12  f(+v)  of h01 h02 h03 h04 f23 f32 f33               -> P_1(a) P_2(b)
+//   13..19 f(-v)  of the same                                  -> P_1(b) P_2(a)
+// accumulators:
+//   0..5 (L,L): h01 h02 h03 h04 f23 f33 | 6,7 cross of ImnOneLoop(P_vv, P_dd): h01 h02 | 8,9 its one-loop part
+//   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
+struct SpecML {
+    static const int NACC = 19, NW = 20, NOUT = 21;
+    __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
+    {
+        const double La = pa[0], Da = pa[1], Va = pa[2], Wa = pa[3];
+        const double Lb = pb[0], Db = pb[1], Vb = pb[2], Wb = pb[3];
+        const double* ws = w;
+        const double* wp = w + 6;
+        const double* wn = w + 13;
+        const double ll = La*Lb;
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[i] = fma(ws[i], ll, acc[i]);
+        // ImnOneLoop(P_vv, P_dd): cross = (P_L, P_dd) + (P_vv, P_L) (ImnOneLoop.cpp:130-148)
+        const double cp = fma(La, Db, Wa*Lb), cn = fma(Lb, Da, Wb*La);
+        acc[6] = fma(wp[0], cp, fma(wn[0], cn, acc[6]));
+        acc[7] = fma(wp[1], cp, fma(wn[1], cn, acc[7]));
+        const double op = Wa*Db, on = Wb*Da;
+        acc[8] = fma(wp[0], op, fma(wn[0], on, acc[8]));
+        acc[9] = fma(wp[1], op, fma(wn[1], on, acc[9]));
+        // ImnOneLoop(P_dv): h03, h04
+        const double dp = La*Vb, dn = Lb*Va;
+        acc[10] = fma(wp[2], dp, fma(wn[2], dn, acc[10]));
+        acc[11] = fma(wp[3], dp, fma(wn[3], dn, acc[11]));
+        const double dd = Va*Vb;
+        acc[12] = fma(ws[2], dd, acc[12]);
+        acc[13] = fma(ws[3], dd, acc[13]);
+        // ImnOneLoop(P_vv): f23, f32, f33
+        const double vp = La*Wb, vn = Lb*Wa;
+        acc[14] = fma(wp[4], vp, fma(wn[4], vn, acc[14]));
+        acc[15] = fma(wp[5], vp, fma(wn[5], vn, acc[15]));
+        acc[16] = fma(wp[6], vp, fma(wn[6], vn, acc[16]));
+        const double vv = Wa*Wb;
+        acc[17] = fma(ws[4], vv, acc[17]);
+        acc[18] = fma(ws[5], vv, acc[18]);
+    }
+    // out [c][7][3][nk]; t = output index 0..20 = 3 m + part
+    __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, const double* f)
+    {
+        // The reference evaluates the LINEAR and ONE-LOOP parts of (m, n) = (3, 2) with the f23 kernel
+        // (ImnOneLoop.cpp:108-109, 199-200) and only the cross part with f32 (:160-165); reproduced as is.
+        double v;
+        switch (t) {
+            case 0: v = f[0]; break;  case 1: v = f[6]; break;       case 2: v = f[8]; break;
+            case 3: v = f[1]; break;  case 4: v = f[7]; break;       case 5: v = f[9]; break;
+            case 6: v = f[2]; break;  case 7: v = 2.0*f[10]; break;  case 8: v = f[12]; break;
+            case 9: v = f[3]; break;  case 10: v = 2.0*f[11]; break; case 11: v = f[13]; break;
+            case 12: v = f[4]; break; case 13: v = 2.0*f[14]; break; case 14: v = f[17]; break;
+            case 15: v = f[4]; break; case 16: v = 2.0*f[15]; break; case 17: v = f[17]; break;
+            case 18: v = f[5]; break; case 19: v = 2.0*f[16]; break; default: v = f[18]; break;
+        }
+        g.out[((size_t)tile*21 + t)*g.nk + ik] = v;
+    }
+};
+
+std::vector<ColSpec> ml_columns()
+{
+    std::vector<ColSpec> c;
+    for (int id : {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F33}) c.push_back({id, 0, NL_INV8PI2});
+    for (int sign : {+1, -1})
+        for (int id : {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33}) c.push_back({id, sign, NL_INV8PI2});
+    return c;
+}
+
+// ------------------------------------------------------------ one-loop tables
+// slots: P_L of 4 cosmologies; W columns: the operator's 6 kernels; accumulator 6 r + c
+struct SpecDiag {
+    static const int NACC = 24, NW = 6, NOUT = 24;
+    __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const double pp = pa[r]*pb[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[6*r + c] = fma(w[c], pp, acc[6*r + c]);
+        }
+    }
+    // out [cosmology][nk][8]
+    __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, const double* f)
+    {
+        const int r = t/6, c = t - 6*r;
+        const int cosmo = tile*4 + r;
+        if (cosmo < g.nrow) g.out[((size_t)cosmo*g.nk + ik)*8 + c] = f[t];
+    }
+};
+
+template <class Spec>
+__global__ void __launch_bounds__(NL_THREADS, 2)
+k_nodal_apply(const NodalArgs g)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tabs = reinterpret_cast<double*>(smem_raw);                 // [4][TAB_MPAD]
+    double* PaS = tabs + NL_SLOTS*TAB_MPAD;                             // [4][max_outer]
+    double* red = PaS + NL_SLOTS*g.max_outer;                           // [NL_WARPS][NACC]
+    double* fin = red + NL_WARPS*Spec::NACC;                            // [NACC]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fin + Spec::NACC + (Spec::NACC & 1));
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_lo = blockIdx.y*g.kchunk, k_hi = min(g.nk, k_lo + g.kchunk);
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = TAB_MPAD*sizeof(double);
+        mbar_expect_tx(mbar, NL_SLOTS*bytes);
+        for (int s = 0; s < NL_SLOTS; s++)
+            bulk_copy_g2s(tabs + s*TAB_MPAD, g.tables + (size_t)g.slot_tab[tile*NL_SLOTS + s]*TAB_MPAD, bytes, mbar);
+    }
+    mbar_wait(mbar, 0);
+
+    for (int ik = k_lo; ik < k_hi; ik++) {
+        // ---- P(a) of the four spectra for every outer node of this k
+        const int64_t o0 = g.outer_off[ik];
+        const int n_out = (int)(g.outer_off[ik + 1] - o0);
+        for (int o = tid; o < n_out; o += NL_THREADS) {
+            const int j0 = g.a_j0[o0 + o];
+            const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)));
+            const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)) + 1);
+#pragma unroll
+            for (int s = 0; s < NL_SLOTS; s++) {
+                const double* t = tabs + s*TAB_MPAD + j0;
+                PaS[s*g.max_outer + o] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
+            }
+        }
+        __syncthreads();
+
+        double acc[Spec::NACC];
+#pragma unroll
+        for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
+        const int64_t n0 = g.node_off[ik], n1 = g.node_off[ik + 1];
+        for (int64_t node = n0 + tid; node < n1; node += NL_THREADS) {
+            const int j0 = __ldg(g.b_j0 + node);
+            const int ol = __ldg(g.ol + node);
+            const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node));
+            const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node) + 1);
+            double w[Spec::NW];
+#pragma unroll
+            for (int c = 0; c < Spec::NW; c++) w[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
+            double pa[NL_SLOTS], pb[NL_SLOTS];
+#pragma unroll
+            for (int s = 0; s < NL_SLOTS; s++) {
+                const double* t = tabs + s*TAB_MPAD + j0;
+                pb[s] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
+                pa[s] = PaS[s*g.max_outer + ol];
+            }
+            Spec::accumulate(acc, pa, pb, w);
+        }
+        // ---- reduce over the CTA
+#pragma unroll
+        for (int i = 0; i < Spec::NACC; i++) {
+            double v = acc[i];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0) red[warp*Spec::NACC + i] = v;
+        }
+        __syncthreads();
+        if (tid < Spec::NACC) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NL_WARPS; w++) s += red[w*Spec::NACC + tid];
+            fin[tid] = s;
+        }
+        __syncthreads();
+        if (tid < Spec::NOUT) Spec::store(g, tile, ik, tid, fin);
+        // the next k's PaS writes are ordered after this k's reads by the two barriers above
+    }
+}
+
+template <class Spec>
+static void launch_nodal(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ntiles,
+                         int nrow, int kchunk, double* out)
+{
+    PRSD_REQUIRE(op.soa && op.ncol_used == Spec::NW, "nodal operator has the wrong layout");
+    const NodeGeometry& geo = *op.geo;
+    NodalArgs a;
+    a.nk = geo.nk; a.max_outer = geo.max_outer; a.kchunk = kchunk; a.nrow = nrow;
+    a.outer_off = geo.outer_off.p; a.node_off = geo.node_off.p;
+    a.a_j0 = geo.a_j0.p; a.a_coef = geo.a_coef.p;
+    a.b_j0 = geo.b_j0.p; a.ol = geo.n_outer_local.p; a.b_coef = geo.b_coef.p;
+    a.W = op.W.p; a.n_nodes = geo.n_nodes;
+    a.tables = tables; a.slot_tab = slot_tab; a.out = out;
+    const size_t smem = (size_t)(NL_SLOTS*TAB_MPAD + NL_SLOTS*geo.max_outer + (NL_WARPS + 1)*Spec::NACC + 2)*sizeof(double) + 16;
+    PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
+    PRSD_CUDA(cudaFuncSetAttribute(k_nodal_apply<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ntiles, (geo.nk + kchunk - 1)/kchunk);
+    ProfScope prof(ctx, PROF_BILINEAR);
+    k_nodal_apply<Spec><<<grid, NL_THREADS, smem, ctx.stream>>>(a);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
+void nodal_apply_ml(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
+{
+    launch_nodal<SpecML>(ctx, op, tables, slot_tab, ncosmo, ncosmo, 2, out);
+}
+
+void nodal_apply_diag(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
+{
+    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + 3)/4, ncosmo, 4, out);
+}
+
+} // namespace prsd

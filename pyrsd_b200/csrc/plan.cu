@@ -1,5 +1,6 @@
 // plan.cu -- PT plan construction and the batched PT stage (see plan.cuh).
 #include "plan.cuh"
+#include "nodal.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -66,7 +67,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         auto geo = make_geometry(c, k_1loop.data(), ONELOOP_N, 1e5, cfg, grid);
         std::vector<ColSpec> cols;
         for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
-        op_1loop.build(c, geo, cols);
+        op_1loop.build(c, geo, cols, true);
     }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
     if (!only_oneloop) {
@@ -80,10 +81,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
     if (with_ml && !only_oneloop) {
         auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg, grid);
-        std::vector<ColSpec> pos, neg;
-        for (int id : ML_KID) { pos.push_back({id, +1, INV8PI2}); neg.push_back({id, -1, INV8PI2}); }
-        op_ml_pos.build(c, geo, pos);
-        op_ml_neg.build(c, geo, neg);
+        op_ml.build(c, geo, ml_columns(), true);
     }
     // ---- 1-D operators
     {
@@ -123,13 +121,13 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
 size_t PTPlan::device_bytes() const
 {
     size_t b = 0;
-    for (const BilinearOp* op : {&op_1loop, &op_ik, &op_ml_pos, &op_ml_neg}) {
+    for (const BilinearOp* op : {&op_1loop, &op_ik, &op_ml}) {
         if (!op->geo) continue;
         b += op->W.n*sizeof(double);
     }
     if (op_1loop.geo) b += op_1loop.geo->bytes();
     if (op_ik.geo) b += op_ik.geo->bytes();
-    if (op_ml_pos.geo) b += op_ml_pos.geo->bytes();
+    if (op_ml.geo) b += op_ml.geo->bytes();
     for (const LinearOp* l : {&lin_1loop, &lin_main, &lin_invq2_100, &lin_kurt}) b += l->Omega.n*sizeof(double);
     return b;
 }
@@ -139,7 +137,7 @@ long long PTPlan::nodes_total() const
     long long n = 0;
     if (op_1loop.geo) n += op_1loop.geo->n_nodes;
     if (op_ik.geo) n += op_ik.geo->n_nodes;
-    if (op_ml_pos.geo) n += 2*op_ml_pos.geo->n_nodes;
+    if (op_ml.geo) n += 2*op_ml.geo->n_nodes;
     return n;
 }
 
@@ -175,37 +173,6 @@ __global__ void k_pack_ik(int nk, const double* __restrict__ s /*[c][nk][40]*/, 
     for (int j = 0; j < 16; j++) I[((size_t)c*16 + j)*nk + i] = v[j];
 #pragma unroll
     for (int j = 0; j < 13; j++) K[((size_t)c*13 + j)*nk + i] = v[16 + j];
-}
-
-// rows of the ImnOneLoop contraction: (P_1(q), P_2(r)) =
-//   0 (L,L)  1 (L,dv)  2 (dv,dv)  3 (L,dd)  4 (vv,L)  5 (vv,dd)  6 (L,vv)  7 (vv,vv)
-// columns: h01 h02 h03 h04 f23 f32 f33
-__global__ void k_pack_ml(int nk, const double* __restrict__ sp, const double* __restrict__ sn, double* __restrict__ ML)
-{
-    const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
-    if (i >= nk) return;
-    auto at = [&](int row, int col) {
-        const size_t idx = (((size_t)c*8 + row)*nk + i)*8 + col;
-        return sp[idx] + sn[idx];
-    };
-    double* o = ML + (size_t)c*N_ML*3*nk;
-    auto put = [&](int m, double lin, double cross, double one) {
-        o[((size_t)m*3 + 0)*nk + i] = lin;
-        o[((size_t)m*3 + 1)*nk + i] = cross;
-        o[((size_t)m*3 + 2)*nk + i] = one;
-    };
-    // ImnOneLoop(Pvv, Pdd): h01, h02  (cross = \int P_L P_2 + \int P_1 P_L, ImnOneLoop.cpp:130-148)
-    put(0, at(0, 0), at(3, 0) + at(4, 0), at(5, 0));
-    put(1, at(0, 1), at(3, 1) + at(4, 1), at(5, 1));
-    // ImnOneLoop(Pdv): h03, h04  (equal spectra: cross = 2 x part1)
-    put(2, at(0, 2), 2.0*at(1, 2), at(2, 2));
-    put(3, at(0, 3), 2.0*at(1, 3), at(2, 3));
-    // ImnOneLoop(Pvv): f23, f32, f33.  The reference evaluates the LINEAR and ONE-LOOP parts of
-    // (m,n) = (3,2) with the f23 kernel (ImnOneLoop.cpp:108-109, 199-200) and only the cross
-    // part with f32 (:160-165); reproduced as is.
-    put(4, at(0, 4), 2.0*at(6, 4), at(7, 4));
-    put(5, at(0, 4), 2.0*at(6, 5), at(7, 4));
-    put(6, at(0, 6), 2.0*at(6, 6), at(7, 6));
 }
 
 __global__ void k_pack_lin(int nk, int nout, int with_zel, const double* __restrict__ s /*[c][nout]*/,
@@ -247,27 +214,21 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res)
     const int ntile = (nc + 7)/8;
 
     // ---- tile maps
-    std::vector<int> slot(ntile*8), rowI(ntile*8), tabL(nc), tabSq(nc), tab22(nc);
+    std::vector<int> slot(ntile*8), rowI(ntile*8), tabL(nc);
     for (int t = 0; t < ntile; t++)
         for (int r = 0; r < 8; r++) {
             slot[t*8 + r] = sp.table_index(std::min(t*8 + r, nc - 1), SP_LIN);
             rowI[t*8 + r] = r;
         }
-    for (int i = 0; i < nc; i++) {
-        tabL[i] = sp.table_index(i, SP_LIN);
-        tabSq[i] = sp.table_index(i, SP_LIN_SQ);
-        tab22[i] = sp.table_index(i, SP_P22BAR);
-    }
+    for (int i = 0; i < nc; i++) tabL[i] = sp.table_index(i, SP_LIN);
     s_slot.upload(slot, s);
     s_rowA.upload(rowI, s);
-    DevBuf<int> d_tabL, d_tabSq, d_tab22;
+    DevBuf<int> d_tabL;
     d_tabL.upload(tabL, s);
-    d_tabSq.upload(tabSq, s);
-    d_tab22.upload(tab22, s);
 
-    // ---- stage A: one-loop tables
+    // ---- stage A: one-loop tables (tiles of 4 cosmologies; s_slot is laid out [.][8] = two such tiles)
     s_op1.ensure((size_t)ntile*8*ONELOOP_N*8);
-    op_1loop.apply(c, sp.tables.p, s_slot.p, s_rowA.p, s_rowA.p, ntile, s_op1.p);
+    nodal_apply_diag(c, op_1loop, sp.tables.p, s_slot.p, nc, s_op1.p);
     s_lin1.ensure((size_t)nc*3*ONELOOP_N);
     lin_1loop.apply(c, sp.tables.p, d_tabL.p, nc, s_lin1.p);
     s_plk.ensure((size_t)nc*ONELOOP_N);
@@ -312,31 +273,13 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
     }
     // ---- stage B: ImnOneLoop (one tile = one cosmology, rows = spectrum pairs)
     if (with_ml) {
-        std::vector<int> mslot(nc*8), mA(nc*8), mB(nc*8);
-        const int a_of[8] = {0, 0, 2, 0, 3, 3, 0, 3};   // slot of P_1: 0 L, 1 dd, 2 dv, 3 vv
-        const int b_of[8] = {0, 2, 2, 1, 0, 1, 3, 3};   // slot of P_2
+        std::vector<int> mslot(nc*4);
         for (int i = 0; i < nc; i++) {
-            const int kinds[8] = {SP_LIN, SP_DD1, SP_DV1, SP_VV1, SP_LIN, SP_LIN, SP_LIN, SP_LIN};
-            for (int r = 0; r < 8; r++) {
-                mslot[i*8 + r] = sp.table_index(i, kinds[r]);
-                mA[i*8 + r] = a_of[r];
-                mB[i*8 + r] = b_of[r];
-            }
+            const int kinds[4] = {SP_LIN, SP_DD1, SP_DV1, SP_VV1};
+            for (int r = 0; r < 4; r++) mslot[i*4 + r] = sp.table_index(i, kinds[r]);
         }
-        DevBuf<int> dslot, dA, dB;
-        dslot.upload(mslot, s);
-        dA.upload(mA, s);
-        dB.upload(mB, s);
-        s_mlp.ensure((size_t)nc*8*nk*8);
-        s_mln.ensure((size_t)nc*8*nk*8);
-        // v > 0 half: a = q, b = r -> (A, B) = (P_1, P_2); v < 0 half: a = r, b = q -> swapped
-        op_ml_pos.apply(c, sp.tables.p, dslot.p, dA.p, dB.p, nc, s_mlp.p);
-        op_ml_neg.apply(c, sp.tables.p, dslot.p, dB.p, dA.p, nc, s_mln.p);
-        dim3 g((nk + 127)/128, nc);
-        k_pack_ml<<<g, 128, 0, s>>>(nk, s_mlp.p, s_mln.p, res.ML.p);
-        PRSD_CUDA(cudaGetLastError());
-        c.launches++;
-        c.sync();    // the index buffers above are locals
+        s_tabidx.upload(mslot, s);
+        nodal_apply_ml(c, op_ml, sp.tables.p, s_tabidx.p, nc, res.ML.p);
     }
     // ---- 1-D functionals
     s_linmain.ensure((size_t)nc*lin_main.nout);

@@ -43,7 +43,7 @@ struct PTPlan {
     std::vector<double> k_interp, k_1loop, r_zel;
     int nk = 0;
     bool with_ml = true, with_zel = true, only_oneloop = false;
-    BilinearOp op_1loop, op_ik, op_ml_pos, op_ml_neg;
+    BilinearOp op_1loop, op_ik, op_ml;
     LinearOp lin_1loop;        // J00, J01, J11 on k_1loop                      (P_L table)
     LinearOp lin_main;         // J x6 (nk each), sigmasq_k (nk), sigma_v^2, X (1024), Y (1024)   (P_L table)
     LinearOp lin_invq2_100;    // \int S/q^2 dq over [1e-5, 100] x 1/(10 pi^2)  (P_L^2 table)  -> Q3 / k^4

@@ -15,7 +15,7 @@ KnotGrid make_knot_grid()
     struct Z { double lo, hi, h; };
     const Z zs[] = {
         {1e-8, 1e-5, 0.03}, {1e-5, 5e-3, 0.02}, {5e-3, 1.0, 0.004},
-        {1.0, 10.0, 0.02},  {10.0, 100.0, 0.02}, {100.0, 1.2e5, 0.03},
+        {1.0, 10.0, 0.01},  {10.0, 100.0, 0.02}, {100.0, 1.2e5, 0.03},
     };
     KnotGrid g;
     for (const Z& z : zs) {
@@ -149,6 +149,14 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
         extra.push_back(0.5*kk);
         extra.push_back(kk);
         extra.push_back(2.0*kk);
+        // the cut u <= umax makes the inner upper limit min(a + k, 2 qmax - a): kink at a = qmax - k/2
+        if (qmax - 0.5*kk > 0) extra.push_back(qmax - 0.5*kk);
+        // a hard edge of a spectrum at b = z (one-loop tables vanish outside [1e-5, 10]) is crossed by
+        // the inner limits k - a and a + k at a = k - z and a = z - k
+        for (double z : zone_breaks) {
+            if (z - kk > 0) extra.push_back(z - kk);
+            if (kk - z > 0) extra.push_back(kk - z);
+        }
         std::vector<double> oe = panel_edges(cfg.qmin, qmax, extra, cfg);
         for (size_t p = 0; p + 1 < oe.size(); p++) {
             const double l0 = std::log(oe[p]), l1 = std::log(oe[p + 1]);
@@ -160,9 +168,10 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
                 double blo, bhi;
                 if (a < 0.5*kk) { blo = kk - a; bhi = kk + a; }
                 else            { blo = a;      bhi = a + kk; }
-                // u = (a+b)/k <= umax  ->  b <= k umax - a
+                // u = (a+b)/k <= umax  ->  b <= k umax - a: the inner range ends there
                 const double bcap = kk*umax - a;
                 if (bcap <= blo) continue;
+                if (bcap < bhi) bhi = bcap;
                 const int32_t oid = (int32_t)H.a.size();
                 int j0; double s;
                 grid.locate(x, j0, s);
@@ -177,8 +186,7 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
                     const double hb = 0.5*(b1 - b0), mb = 0.5*(b1 + b0);
                     for (int ii = 0; ii < cfg.n_inner; ii++) {
                         const double b = mb + hb*xi[ii];
-                        double w = wx*(hb*wi[ii]/kk)*(2.0/kk)*a*a*b;
-                        if (b > bcap) w = 0.0;
+                        const double w = wx*(hb*wi[ii]/kk)*(2.0/kk)*a*a*b;
                         grid.locate(std::log(b), j0, s);
                         lagrange4(s, coef);
                         H.b.push_back(b);

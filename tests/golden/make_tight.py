@@ -28,12 +28,21 @@ EPS1D = 1e-10
 def ml_part(out, R, PL, kint, t0):
     # ImnOneLoop at tight eps with COMMON one-loop tables as input to both sides.  The reference's shipped
     # (default-eps) tables carry point-to-point quadrature noise of ~1e-4, which its own 1000-point spline then
-    # interpolates; parity of the ImnOneLoop stage is defined on smooth inputs, so the common tables are the
-    # reference's own OneLoopP* constructors run at epsrel = 1e-7 (stored in the fixture).
+    # interpolates; parity of the ImnOneLoop stage is defined on smooth inputs, so the common tables are computed
+    # at tight eps by the reference's own drivers (stored in the fixture).
+    # The tables follow OneLoopPS.cpp:56-185 (2 I_ab + 6 k^2 J_ab P_L; I23 + 2/3 I32 + 1/5 I33) from the reference's
+    # Imn at epsrel = 1e-8 and Jmn at 1e-10.  The OneLoopP* constructors pass ONE epsrel to both drivers, and the
+    # reference's adaptive Gauss-Kronrod Jmn is still off by 2e-6 at isolated k for epsrel >= 1e-8 (measured:
+    # J01(0.46416) at 1e-7), which the 6 k^2 J P_L - 2 I cancellation amplifies to 1.6e-5.
+    k1 = R.logspace(1e-5, 10, 1000)
+    P1 = PL(k1)
     common = {}
-    for w in ('dd', 'dv', 'vv', '22bar'):
-        common[w] = R.RefOneLoop(PL, w, 1e-7).table()
+    for w, (m, n), jj in (('dd', (0, 0), (0, 0)), ('dv', (0, 1), (0, 1)), ('vv', (1, 1), (1, 1))):
+        common[w] = 2*R.Imn(PL, k1, m, n, epsrel=1e-8) + 6*k1*k1*R.Jmn(PL, k1, jj[0], jj[1], epsrel=1e-10)*P1
         print('one-loop table', w, 'done %.0fs' % (time.time() - t0), flush=True)
+    common['22bar'] = (R.Imn(PL, k1, 2, 3, epsrel=1e-8) + (2./3.)*R.Imn(PL, k1, 3, 2, epsrel=1e-8)
+                       + (1./5.)*R.Imn(PL, k1, 3, 3, epsrel=1e-8))
+    print('one-loop table 22bar done %.0fs' % (time.time() - t0), flush=True)
     out['oneloop_common'] = np.array([common[w] for w in ('dd', 'dv', 'vv', '22bar')])
     ol = {w: R.RefOneLoop(PL, w, 1e-7, common[w]) for w in ('dd', 'dv', 'vv', '22bar')}
     out['kurtosis_common_tables'] = ol['22bar'].VelocityKurtosis(1e-10)

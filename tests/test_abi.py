@@ -65,6 +65,6 @@ def test_context_fails_loudly_without_gpu(lib):
 def test_static_queries_work_without_gpu(lib):
     from pyrsd_b200 import _native
     x = _native.knot_grid()
-    assert len(x) == 2342
+    assert len(x) == 2457
     cfg = _native.quad_config_default()
     assert cfg[1] == 12 and cfg[2] == 8

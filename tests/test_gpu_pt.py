@@ -191,9 +191,13 @@ def test_batch_consistency_and_scaling_property(cosmo, golden):
     res = eng.run(sp)
     I, J, ML = eng.get(res, 'I'), eng.get(res, 'J'), eng.get(res, 'ML')
     r = amp/amp[4]
-    assert np.max(np.abs(I/(r[:, None, None]**2*I[4][None]) - 1)) < 1e-12
+    # measured against max(|value|, P_L(k)) as everywhere for I: at the lowest k the kernels cancel by
+    # ~1e7 between the two halves of the domain, so the bare ratio only scales to ~1e-9
+    from pyrsd_b200 import pygcl
+    floor = pygcl.LinearPS(cosmo, 0.)(k_interp)[None, None, :]
+    assert relerr_floor(I, r[:, None, None]**2*I[4][None], floor).max() < 1e-12
     assert np.max(np.abs(J/(r[:, None, None]*J[4][None]) - 1)) < 1e-12
     # ImnOneLoop: linear ~ A^2, cross ~ A^3, one-loop ~ A^4
     for part, power in ((0, 2), (1, 3), (2, 4)):
-        ratio = ML[:, :, part, :]/(r[:, None, None]**power*ML[4][None, :, part, :])
-        assert np.max(np.abs(ratio - 1)) < 1e-9
+        err = relerr_floor(ML[:, :, part, :], r[:, None, None]**power*ML[4][None, :, part, :], floor)
+        assert err.max() < 1e-9

@@ -18,7 +18,7 @@ def table(emul, golden, tight):
 
 def test_knot_grid(emul):
     x = emul.knots()
-    assert len(x) == 2342
+    assert len(x) == 2457
     d = np.diff(x)
     assert np.all(d >= 0) and np.sum(d == 0) == 5          # zone edges are duplicated, nothing else
     for edge in (1e-5, 10., 100.):
