@@ -87,11 +87,12 @@ def as_f64(x):
 
 
 def cfg_ptr(cfg):
-    """cfg: None or array of 9 doubles -> (keepalive, void*)"""
+    """cfg: None or array of 40 doubles (include/pyrsd_b200.h) -> (keepalive, void*)"""
     if cfg is None:
         return None, None
     a = as_f64(cfg)
-    assert a.size == 9
+    if a.size != 40:
+        raise ValueError("quadrature configuration must hold 40 numbers (see prsd_quad_config_default)")
     return a, a.ctypes.data_as(C.c_void_p)
 
 
@@ -104,7 +105,7 @@ def knot_grid():
 
 
 def quad_config_default():
-    c = np.empty(9)
+    c = np.empty(40)
     check(lib().prsd_quad_config_default(c))
     return c
 

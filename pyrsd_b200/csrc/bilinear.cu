@@ -152,8 +152,10 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
     double* PaS = tabs + 8*TAB_MPAD;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(PaS + 8*max_outer);
 
-    const int ik = blockIdx.x;
-    const int tile = blockIdx.y;
+    // tiles of the same k are adjacent in launch order: the node stream of a k is read from DRAM once
+    // and from L2 by the other tiles
+    const int ik = blockIdx.y;
+    const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- stage the (up to) 8 spectra tables of this row tile with TMA bulk copies
@@ -238,7 +240,7 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
     const size_t smem = (size_t)(8*TAB_MPAD + 8*g.max_outer)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "bilinear apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_bilinear_apply<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(g.nk, ntiles);
+    dim3 grid(ntiles, g.nk);
     ProfScope prof(ctx, PROF_BILINEAR);
     k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, g.max_outer, g.outer_off.p, g.node_off.p,
         g.a_j0.p, g.a_coef.p, g.b_j0.p, g.n_outer_local.p, g.b_coef.p, op.W.p, tables, slot_tab, rowA, rowB, out);

@@ -42,16 +42,21 @@ static int guarded(F&& f)
     }
 }
 
-static QuadConfig cfg_from(const double* c9)
+static QuadConfig cfg_from(const double* c)
 {
     QuadConfig q;
-    if (c9) {
-        q.qmin = c9[0]; q.n_outer = (int)c9[1]; q.n_inner = (int)c9[2]; q.ln_far = c9[3]; q.ln_mid = c9[4];
-        q.bao_lo = c9[5]; q.bao_hi = c9[6]; q.bao_dq = c9[7];
-        if (c9[8] > 0) q.ln_inner = c9[8];
+    if (c) {
+        q.qmin = c[0]; q.ln_far = c[1]; q.ln_mid = c[2]; q.bao_lo = c[3]; q.bao_hi = c[4]; q.bao_dq = c[5];
+        q.ln_inner = c[6]; q.ln_thin = c[7];
+        for (int i = 0; i < 4; i++) {
+            q.tier[i] = {c[8 + 4*i], (int)c[9 + 4*i], (int)c[10 + 4*i], (int)c[11 + 4*i]};
+            q.ml_tier[i] = {c[24 + 4*i], (int)c[25 + 4*i], (int)c[26 + 4*i], (int)c[27 + 4*i]};
+        }
         PRSD_REQUIRE(q.qmin >= 1e-8 && q.qmin < 1e-5, "quadrature config: qmin = %g outside [1e-8, 1e-5)", q.qmin);
-        PRSD_REQUIRE(q.n_outer >= 2 && q.n_outer <= 64 && q.n_inner >= 2 && q.n_inner <= 64, "quadrature config: bad point counts");
-        PRSD_REQUIRE(q.ln_far > 0 && q.ln_mid > 0 && q.bao_dq > 0, "quadrature config: widths must be positive");
+        for (int i = 0; i < 4; i++)
+            for (int n : {q.tier[i].n_outer, q.tier[i].n_inner, q.tier[i].n_thin, q.ml_tier[i].n_outer, q.ml_tier[i].n_inner, q.ml_tier[i].n_thin})
+                PRSD_REQUIRE(n >= 2 && n <= 64, "quadrature config: bad point count %d", n);
+        PRSD_REQUIRE(q.ln_far > 0 && q.ln_mid > 0 && q.bao_dq > 0 && q.ln_inner > 0 && q.ln_thin >= 0, "quadrature config: widths must be positive");
     }
     return q;
 }
@@ -61,7 +66,7 @@ struct GeoKey {
     int device; double qmax; QuadConfig cfg; std::vector<double> k;
     bool operator==(const GeoKey& o) const
     {
-        return device == o.device && qmax == o.qmax && k == o.k && std::memcmp(&cfg, &o.cfg, sizeof(QuadConfig)) == 0;
+        return device == o.device && qmax == o.qmax && k == o.k && cfg == o.cfg;
     }
 };
 static std::mutex g_geo_mu;
@@ -120,7 +125,8 @@ static void eval_kernel_generic(SpectraBatch& sp, int kid, int convention, int k
     // convention 0: Imn, 1: Kmn, 2: ImnOneLoop (see Imn.cpp:120-140, Kmn.cpp:118-138, ImnOneLoop.cpp:82-93)
     Context& c = *sp.ctx;
     if (nk <= 0) return;
-    const QuadConfig cfg = cfg_from(cfg9);
+    const QuadConfig base = cfg_from(cfg9);
+    const QuadConfig cfg = convention == 2 ? base.ml_variant() : base;
     // the reference returns 0 for k <= 0 (Imn.cpp:122)
     std::vector<double> kpos;
     std::vector<int> where;
@@ -203,8 +209,13 @@ int prsd_quad_config_default(double* c9)
     return guarded([&] {
         PRSD_REQUIRE(c9, "null argument");
         QuadConfig q;
-        c9[0] = q.qmin; c9[1] = q.n_outer; c9[2] = q.n_inner; c9[3] = q.ln_far; c9[4] = q.ln_mid;
-        c9[5] = q.bao_lo; c9[6] = q.bao_hi; c9[7] = q.bao_dq; c9[8] = q.ln_inner;
+        double* c = c9;
+        c[0] = q.qmin; c[1] = q.ln_far; c[2] = q.ln_mid; c[3] = q.bao_lo; c[4] = q.bao_hi; c[5] = q.bao_dq;
+        c[6] = q.ln_inner; c[7] = q.ln_thin;
+        for (int i = 0; i < 4; i++) {
+            c[8 + 4*i] = q.tier[i].k_below; c[9 + 4*i] = q.tier[i].n_outer; c[10 + 4*i] = q.tier[i].n_inner; c[11 + 4*i] = q.tier[i].n_thin;
+            c[24 + 4*i] = q.ml_tier[i].k_below; c[25 + 4*i] = q.ml_tier[i].n_outer; c[26 + 4*i] = q.ml_tier[i].n_inner; c[27 + 4*i] = q.ml_tier[i].n_thin;
+        }
     });
 }
 
@@ -633,7 +644,7 @@ int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg9, double* out)
         {
             std::lock_guard<std::mutex> lock(mu);
             for (auto& e : cache)
-                if (e.first.first == c.device && std::memcmp(&e.first.second, &cfg, sizeof(QuadConfig)) == 0) { plan = e.second; break; }
+                if (e.first.first == c.device && e.first.second == cfg) { plan = e.second; break; }
             if (!plan) {
                 plan = std::make_shared<PTPlan>(c, nullptr, 0, cfg, false, false, true);
                 cache.emplace_front(std::make_pair(c.device, cfg), plan);

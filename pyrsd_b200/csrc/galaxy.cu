@@ -40,20 +40,81 @@ enum {
 };
 
 // --------------------------------------------------------------- spline builds
-__global__ void k_nak_rows(int nk, const double* __restrict__ X, const double* __restrict__ src, int rows_per_cosmo,
-                           int row_offset, double* __restrict__ dst)
+// Not-a-knot splines of every PT table of every cosmology on the SHARED abscissae k_interp in one launch.
+// The tridiagonal matrix depends only on the abscissae, so its Thomas factors (nak_factor) are computed once
+// per model; a row then costs a right-hand side, two substitution sweeps without divisions, and the
+// coefficient formulas of nak_spline_build (pt_math.cuh).
+struct NakSrc { const double* p[5]; int rows[5]; int off[5]; };
+
+static void nak_factor(int n, const double* X, std::vector<double>& fac /*[3][n]: w, 1/den, sub-diagonal*/)
+{
+    fac.assign((size_t)3*n, 0.0);
+    double* w = fac.data(); double* iden = w + n; double* sub = iden + n;
+    const int m = n - 2;
+    std::vector<double> b(n), c(n);
+    for (int i = 1; i <= m; i++) {
+        const double h0 = X[i] - X[i - 1], h1 = X[i + 1] - X[i];
+        b[i] = 2.0*(h0 + h1); c[i] = h1; sub[i] = h0;
+    }
+    {
+        const double h0 = X[1] - X[0], h1 = X[2] - X[1];
+        b[1] += h0*(1.0 + h0/h1);
+        c[1] -= h0*h0/h1;
+        const double hn = X[n - 1] - X[n - 2], hm = X[n - 2] - X[n - 3];
+        b[m] += hn*(1.0 + hn/hm);
+        sub[m] -= hn*hn/hm;
+    }
+    w[1] = c[1]/b[1];
+    iden[1] = 1.0/b[1];
+    for (int i = 2; i <= m; i++) {
+        const double den = b[i] - sub[i]*w[i - 1];
+        w[i] = c[i]/den;
+        iden[i] = 1.0/den;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+k_nak_rows(int nk, const double* __restrict__ X, const double* __restrict__ fac, NakSrc S, double* __restrict__ dst)
 {
     extern __shared__ double sm_nak[];
     double* x = sm_nak;
-    double* y = x + nk; double* b = y + nk; double* c = b + nk; double* d = c + nk; double* M = d + nk; double* w = M + nk;
-    const int r = blockIdx.x, cc = blockIdx.y, tid = threadIdx.x;
-    const double* s = src + ((size_t)cc*rows_per_cosmo + r)*nk;
+    double* y = x + nk;
+    double* M = y + nk;
+    const int row = blockIdx.x, cc = blockIdx.y, tid = threadIdx.x;
+    int g = 0;
+#pragma unroll
+    for (int j = 1; j < 5; j++) if (row >= S.off[j]) g = j;
+    const double* s = S.p[g] + ((size_t)cc*S.rows[g] + (row - S.off[g]))*nk;
     for (int i = tid; i < nk; i += blockDim.x) { x[i] = X[i]; y[i] = s[i]; }
     __syncthreads();
-    if (tid == 0) nak_spline_build(nk, x, y, b, c, d, M, w);
+    const int m = nk - 2;
+    for (int i = 1 + tid; i <= m; i += blockDim.x) {
+        const double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
+        M[i] = 6.0*((y[i + 1] - y[i])/h1 - (y[i] - y[i - 1])/h0);
+    }
     __syncthreads();
-    double* o = dst + ((size_t)cc*PT_NROWS + row_offset + r)*5*nk;
-    for (int i = tid; i < nk; i += blockDim.x) { o[i] = x[i]; o[nk + i] = y[i]; o[2*nk + i] = b[i]; o[3*nk + i] = c[i]; o[4*nk + i] = d[i]; }
+    if (tid == 0) {
+        const double* w = fac; const double* iden = fac + nk; const double* sub = fac + 2*nk;
+        double prev = M[1]*iden[1];
+        M[1] = prev;
+        for (int i = 2; i <= m; i++) { prev = (M[i] - sub[i]*prev)*iden[i]; M[i] = prev; }
+        for (int i = m - 1; i >= 1; i--) { prev = M[i] - w[i]*prev; M[i] = prev; }
+        const double h0 = x[1] - x[0], h1 = x[2] - x[1];
+        M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
+        const double hn = x[nk - 1] - x[nk - 2], hm = x[nk - 2] - x[nk - 3];
+        M[nk - 1] = M[nk - 2] + (hn/hm)*(M[nk - 2] - M[nk - 3]);
+    }
+    __syncthreads();
+    double* o = dst + ((size_t)cc*PT_NROWS + row)*5*nk;
+    for (int i = tid; i < nk; i += blockDim.x) {
+        const int j = min(i, nk - 2);          // the last knot repeats the last interval's coefficients
+        const double h = x[j + 1] - x[j];
+        o[i] = x[i];
+        o[nk + i] = y[i];
+        o[2*nk + i] = (y[j + 1] - y[j])/h - h*(2.0*M[j] + M[j + 1])/6.0;
+        o[3*nk + i] = 0.5*M[j];
+        o[4*nk + i] = (M[j + 1] - M[j])/(6.0*h);
+    }
 }
 
 // --------------------------------------------------------------- HZPT broadband
@@ -413,6 +474,10 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     for (int i = 0; i < GAL_NSTOCH; i++) ks[i] = std::pow(10.0, l0 + (l1 - l0)*i/(GAL_NSTOCH - 1));
     d_kstoch.upload(ks, c.stream);
     d_kinterp.upload(k_interp, nki, c.stream);
+    PRSD_REQUIRE(nki >= 4, "GalaxyModel: the PT interpolation grid needs at least 4 points");
+    std::vector<double> fac;
+    nak_factor(nki, k_interp, fac);
+    d_nakfac.upload(fac, c.stream);
     zel.build(c, km.data(), nkm);
     c.sync();
 }
@@ -449,14 +514,11 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     ptspl.ensure((size_t)nc*PT_NROWS*5*nk);
     {
         ProfScope prof(c, PROF_SPLINE);
-        const size_t smem = (size_t)7*nk*sizeof(double);
+        const size_t smem = (size_t)3*nk*sizeof(double);
         if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_nak_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        struct Src { const double* p; int rows; int off; };
-        const Src srcs[5] = {{pt.I.p, 16, PT_I}, {pt.J.p, 6, PT_J}, {pt.K.p, 13, PT_K}, {pt.ML.p, 21, PT_ML}, {pt.sigmasq_k.p, 1, PT_SIGK}};
-        for (const Src& sr : srcs) {
-            k_nak_rows<<<dim3(sr.rows, nc), 64, smem, s>>>(nk, d_kinterp.p, sr.p, sr.rows, sr.off, ptspl.p);
-            c.launches++;
-        }
+        NakSrc S = {{pt.I.p, pt.J.p, pt.K.p, pt.ML.p, pt.sigmasq_k.p}, {16, 6, 13, 21, 1}, {PT_I, PT_J, PT_K, PT_ML, PT_SIGK}};
+        k_nak_rows<<<dim3(PT_NROWS, nc), 64, smem, s>>>(nk, d_kinterp.p, d_nakfac.p, S, ptspl.p);
+        c.launches++;
         PRSD_CUDA(cudaGetLastError());
     }
     // ---- P_L on the model grid (z = 0 normalisation of the batch)

@@ -80,7 +80,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     }
     // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
     if (with_ml && !only_oneloop) {
-        auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg, grid);
+        auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg.ml_variant(), grid);
         op_ml.build(c, geo, ml_columns(), true);
     }
     // ---- 1-D operators

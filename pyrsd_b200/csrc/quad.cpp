@@ -130,9 +130,10 @@ std::vector<double> panel_edges(double lo, double hi, const std::vector<double>&
 void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cfg,
                       const KnotGrid& grid, HalfNodes& H)
 {
-    std::vector<double> xo, wo, xi, wi;
-    gauss_legendre(cfg.n_outer, xo, wo);
-    gauss_legendre(cfg.n_inner, xi, wi);
+    // Gauss-Legendre rules by order (a handful of distinct orders over the tiers)
+    std::vector<std::vector<double>> glx(65), glw(65);
+    auto rule = [&](int n) { if (glx[n].empty()) gauss_legendre(n, glx[n], glw[n]); };
+    for (int i = 0; i < 4; i++) { rule(cfg.tier[i].n_outer); rule(cfg.tier[i].n_inner); rule(cfg.tier[i].n_thin); }
     const std::vector<double> zone_breaks = {1e-5, 10.0, 100.0};
 
     H = HalfNodes();
@@ -144,6 +145,9 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
     for (int ik = 0; ik < nk; ik++) {
         const double kk = k[ik];
         const double umax = 2.0*qmax/kk;
+        const QuadTier& T = cfg.tier_of(kk);
+        const std::vector<double>& xo = glx[T.n_outer];
+        const std::vector<double>& wo = glw[T.n_outer];
         // a = min(q, r) <= (q + r)/2 <= qmax
         extra = zone_breaks;
         extra.push_back(0.5*kk);
@@ -161,7 +165,7 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
         for (size_t p = 0; p + 1 < oe.size(); p++) {
             const double l0 = std::log(oe[p]), l1 = std::log(oe[p + 1]);
             const double hw = 0.5*(l1 - l0), mid = 0.5*(l1 + l0);
-            for (int io = 0; io < cfg.n_outer; io++) {
+            for (size_t io = 0; io < xo.size(); io++) {
                 const double x = mid + hw*xo[io];
                 const double wx = hw*wo[io];
                 const double a = std::exp(x);
@@ -184,9 +188,12 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
                 for (size_t pb = 0; pb + 1 < ie.size(); pb++) {
                     const double b0 = ie[pb], b1 = ie[pb + 1];
                     const double hb = 0.5*(b1 - b0), mb = 0.5*(b1 + b0);
-                    for (int ii = 0; ii < cfg.n_inner; ii++) {
-                        const double b = mb + hb*xi[ii];
-                        const double w = wx*(hb*wi[ii]/kk)*(2.0/kk)*a*a*b;
+                    const bool thin = std::log(b1/b0) < cfg.ln_thin;
+                    const std::vector<double>& xq = glx[thin ? T.n_thin : T.n_inner];
+                    const std::vector<double>& wq = glw[thin ? T.n_thin : T.n_inner];
+                    for (size_t ii = 0; ii < xq.size(); ii++) {
+                        const double b = mb + hb*xq[ii];
+                        const double w = wx*(hb*wq[ii]/kk)*(2.0/kk)*a*a*b;
                         grid.locate(std::log(b), j0, s);
                         lagrange4(s, coef);
                         H.b.push_back(b);

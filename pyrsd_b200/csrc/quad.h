@@ -20,10 +20,14 @@
 
 namespace prsd {
 
+// Gauss-Legendre orders as a function of k.  Parity is measured relative to max(|value|, P_L(k)) (the reference
+// itself stops on epsabs = epsrel P_L(k)/V, Imn.cpp:129): below k ~ 0.02 every mode-coupling integral is < 1e-3 of
+// P_L(k), so a low-order rule already has an error < 1e-6 P_L(k); the orders grow with k up to the range where
+// 2 I + 6 k^2 J P_L cancels to a few per cent (k > 0.3).  A tier applies to k < k_below.
+struct QuadTier { double k_below; int n_outer, n_inner, n_thin; };
+
 struct QuadConfig {
     double qmin     = 1e-8;   // lower cut of the outer variable [h/Mpc]
-    int    n_outer  = 12;     // Gauss-Legendre points per outer panel
-    int    n_inner  = 8;      // Gauss-Legendre points per inner panel
     double ln_far   = 2.0;    // max panel width in ln q, featureless power-law regions
     double ln_mid   = 0.5;    // max panel width in ln q for mid_lo <= q <= mid_hi
     double mid_lo   = 1e-3;
@@ -32,6 +36,41 @@ struct QuadConfig {
     double bao_hi   = 0.7;
     double bao_dq   = 0.05;
     double ln_inner = 0.5;    // max panel width in ln b of the inner integral (any region)
+    double ln_thin  = 0.2;    // inner panels narrower than this in ln b use n_thin points: far from q ~ k the
+                              // strip |q - r| <= k is thin and the integrand nearly polynomial across it
+    // I_mn, K_mn and the one-loop tables (q_max = 1e5)
+    QuadTier tier[4]    = {{0.02, 6, 4, 3}, {0.08, 8, 5, 4}, {0.3, 10, 7, 5}, {1e30, 12, 7, 5}};
+    // ImnOneLoop (q_max = 10): the one-loop spectra are large at the hard cut and the h02-type kernels cancel to
+    // leading order across v, so above k = 0.06 that operator keeps full-order panels everywhere
+    QuadTier ml_tier[4] = {{0.02, 6, 4, 3}, {0.06, 8, 5, 4}, {1e30, 12, 8, 8}, {1e30, 12, 8, 8}};
+
+    const QuadTier& tier_of(double k) const
+    {
+        for (int i = 0; i < 3; i++) if (k < tier[i].k_below) return tier[i];
+        return tier[3];
+    }
+    QuadConfig ml_variant() const
+    {
+        QuadConfig q = *this;
+        for (int i = 0; i < 4; i++) q.tier[i] = ml_tier[i];
+        return q;
+    }
+    void set_uniform(int n_outer, int n_inner, int n_thin)
+    {
+        for (int i = 0; i < 4; i++) { tier[i].n_outer = ml_tier[i].n_outer = n_outer; tier[i].n_inner = ml_tier[i].n_inner = n_inner;
+                                      tier[i].n_thin = ml_tier[i].n_thin = n_thin; }
+    }
+    bool operator==(const QuadConfig& o) const
+    {
+        bool same = qmin == o.qmin && ln_far == o.ln_far && ln_mid == o.ln_mid && mid_lo == o.mid_lo && mid_hi == o.mid_hi &&
+                    bao_lo == o.bao_lo && bao_hi == o.bao_hi && bao_dq == o.bao_dq && ln_inner == o.ln_inner && ln_thin == o.ln_thin;
+        for (int i = 0; i < 4 && same; i++)
+            for (const QuadTier* p : {tier, ml_tier}) {
+                const QuadTier* q = (p == tier) ? o.tier : o.ml_tier;
+                same = same && p[i].k_below == q[i].k_below && p[i].n_outer == q[i].n_outer && p[i].n_inner == q[i].n_inner && p[i].n_thin == q[i].n_thin;
+            }
+        return same;
+    }
 };
 
 // Tabulation grid of every spectrum: piecewise-uniform in x = ln q, zone edges at the hard

@@ -27,36 +27,49 @@ const double* knot_grid_dev(Context& ctx)
 }
 
 // ------------------------------------------------------------ spline build
-// One CTA per spline.  The tridiagonal sweeps are inherently serial (thread 0, operands in
-// shared memory); set-up and the final polynomial coefficients are done by the whole CTA.
-// Same arithmetic as cubic_spline_build() in pt_math.cuh (netlib fmm/spline.f).
-__global__ void k_spline_build(int n, const double* __restrict__ X, int x_stride,
-                               const double* __restrict__ Y, double* __restrict__ out)
+// Same arithmetic as cubic_spline_build() in pt_math.cuh (netlib fmm/spline.f), split so that the serial
+// sweeps are as short as possible: the eliminated diagonal depends only on the abscissae (k_spline_factor:
+// one division per knot, once per distinct abscissa set), after which a spline costs two sweeps of fused
+// multiply-adds by one thread (operands in shared memory) between CTA-parallel set-up and coefficient passes.
+__global__ void k_spline_factor(int n, const double* __restrict__ X, int x_stride, double* __restrict__ invb)
+{
+    const double* x = X + (size_t)blockIdx.x*x_stride;
+    double* o = invb + (size_t)blockIdx.x*n;
+    if (threadIdx.x != 0) return;
+    double dm = x[1] - x[0];
+    double ib = 1.0/(-dm);                       // b[0] = -d[0]
+    o[0] = ib;
+    for (int i = 1; i < n; i++) {
+        const double di = (i < n - 1) ? x[i + 1] - x[i] : 0.0;
+        const double bi = (i < n - 1) ? 2.0*(dm + di) : -dm;     // b[n-1] = -d[n-2]
+        ib = 1.0/fma(-dm*dm, ib, bi);
+        o[i] = ib;
+        dm = di;
+    }
+}
+
+__global__ void k_spline_build(int n, const double* __restrict__ X, int x_stride, const double* __restrict__ invb_all,
+                               int invb_stride, const double* __restrict__ Y, double* __restrict__ out)
 {
     extern __shared__ double sm[];
     double* x = sm;
     double* y = sm + n;
-    double* b = sm + 2*n;
+    double* ib = sm + 2*n;
     double* c = sm + 3*n;
     double* d = sm + 4*n;
     const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const double* Xs = X + (size_t)s*x_stride;
     const double* Ys = Y + (size_t)s*n;
-    for (int i = tid; i < n; i += nt) { x[i] = Xs[i]; y[i] = Ys[i]; }
+    const double* IB = invb_all + (size_t)s*invb_stride;
+    for (int i = tid; i < n; i += nt) { x[i] = Xs[i]; y[i] = Ys[i]; ib[i] = IB[i]; }
     __syncthreads();
     for (int i = tid; i < n - 1; i += nt) d[i] = x[i + 1] - x[i];
     __syncthreads();
     // right-hand side: second differences of the slopes
-    for (int i = tid; i < n; i += nt) {
-        if (i >= 1 && i <= n - 2) {
-            b[i] = 2.0*(d[i - 1] + d[i]);
-            c[i] = (y[i + 1] - y[i])/d[i] - (y[i] - y[i - 1])/d[i - 1];
-        }
-    }
+    for (int i = tid; i < n; i += nt)
+        if (i >= 1 && i <= n - 2) c[i] = (y[i + 1] - y[i])/d[i] - (y[i] - y[i - 1])/d[i - 1];
     __syncthreads();
     if (tid == 0) {
-        b[0] = -d[0];
-        b[n - 1] = -d[n - 2];
         double c0 = 0.0, cn = 0.0;
         if (n > 3) {
             c0 = c[2]/(x[3] - x[1]) - c[1]/(x[2] - x[0]);
@@ -66,21 +79,17 @@ __global__ void k_spline_build(int n, const double* __restrict__ X, int x_stride
         }
         c[0] = c0;
         c[n - 1] = cn;
-        // forward elimination
-        double bp = b[0], cp = c[0];
+        // forward elimination of the right-hand side: c_i -= (d_{i-1}/b_{i-1}) c_{i-1}
+        double cp = c0;
         for (int i = 1; i < n; i++) {
-            const double dm = d[i - 1];
-            const double t = dm/bp;
-            bp = b[i] - t*dm;
-            cp = c[i] - t*cp;
-            b[i] = bp;
+            cp = fma(-(d[i - 1]*ib[i - 1]), cp, c[i]);
             c[i] = cp;
         }
         // back substitution
-        double cn1 = c[n - 1]/b[n - 1];
+        double cn1 = c[n - 1]*ib[n - 1];
         c[n - 1] = cn1;
         for (int i = n - 2; i >= 0; i--) {
-            cn1 = (c[i] - d[i]*cn1)/b[i];
+            cn1 = fma(-d[i], cn1, c[i])*ib[i];
             c[i] = cn1;
         }
     }
@@ -104,15 +113,29 @@ __global__ void k_spline_build(int n, const double* __restrict__ X, int x_stride
     }
 }
 
+void spline_factor(Context& ctx, int nfac, int n, const double* dX, int x_stride, double* d_invb)
+{
+    k_spline_factor<<<nfac, 32, 0, ctx.stream>>>(n, dX, x_stride, d_invb);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
 void spline_build_batched(Context& ctx, int nspline, int n, const double* dX, int x_stride,
-                          const double* dY, double* dspl)
+                          const double* dY, double* dspl, const double* d_invb)
 {
     PRSD_REQUIRE(n >= 4 && n <= 4096, "spline_build_batched: n = %d out of range [4, 4096]", n);
     const size_t smem = (size_t)5*n*sizeof(double);
     if (smem > 48*1024)
         PRSD_CUDA(cudaFuncSetAttribute(k_spline_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(ctx, PROF_SPLINE);
-    k_spline_build<<<nspline, 128, smem, ctx.stream>>>(n, dX, x_stride, dY, dspl);
+    static thread_local DevBuf<double> scratch;       // factors when the caller holds none
+    if (!d_invb) {
+        const int nfac = x_stride == 0 ? 1 : nspline;
+        scratch.ensure((size_t)nfac*n);
+        spline_factor(ctx, nfac, n, dX, x_stride, scratch.p);
+        d_invb = scratch.p;
+    }
+    k_spline_build<<<nspline, 128, smem, ctx.stream>>>(n, dX, x_stride, d_invb, x_stride == 0 ? 0 : n, dY, dspl);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
 }
@@ -277,17 +300,19 @@ std::vector<double> oneloop_kgrid();   // defined in plan.cu
 
 void SpectraBatch::set_oneloop_tables(const double* d_tables)
 {
-    static DevBuf<double> dk;    // shared abscissae
+    static DevBuf<double> dk, dk_invb;    // shared abscissae and their spline factors
     static int dk_dev = -1;
     if (dk_dev != ctx->device) {
         dk.upload(oneloop_kgrid(), ctx->stream);
+        dk_invb.alloc(ONELOOP_N);
+        spline_factor(*ctx, 1, ONELOOP_N, dk.p, 0, dk_invb.p);
         dk_dev = ctx->device;
     }
     oneloop_spl.ensure((size_t)ncosmo*4*5*ONELOOP_N);
     oneloop_raw.ensure((size_t)ncosmo*4*ONELOOP_N);
     if (d_tables != oneloop_raw.p)
         PRSD_CUDA(cudaMemcpyAsync(oneloop_raw.p, d_tables, (size_t)ncosmo*4*ONELOOP_N*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    spline_build_batched(*ctx, ncosmo*4, ONELOOP_N, dk.p, 0, oneloop_raw.p, oneloop_spl.p);
+    spline_build_batched(*ctx, ncosmo*4, ONELOOP_N, dk.p, 0, oneloop_raw.p, oneloop_spl.p, dk_invb.p);
     const double lnk0 = std::log(ONELOOP_KMIN);
     const double inv = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
     // zones 1..3 of the knot grid span [1e-5, 10] exactly (quad.cpp make_knot_grid)

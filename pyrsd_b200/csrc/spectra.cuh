@@ -56,7 +56,9 @@ const double* knot_grid_dev(Context&);   // ln q of every knot on the device [TA
 
 // batched netlib cubic-spline build: Y [nspline][n] -> spl [nspline][5n]; X is [n] if
 // x_stride == 0 (shared abscissae) else [nspline][n]
+// d_invb (optional): factors of the abscissae from spline_factor(), [1][n] if x_stride == 0 else [nspline][n]
 void spline_build_batched(Context& ctx, int nspline, int n, const double* dX, int x_stride,
-                          const double* dY, double* dspl);
+                          const double* dY, double* dspl, const double* d_invb = nullptr);
+void spline_factor(Context& ctx, int nfac, int n, const double* dX, int x_stride, double* d_invb);
 
 } // namespace prsd

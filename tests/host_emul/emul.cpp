@@ -18,9 +18,25 @@ void emul_set_config(double qmin, int n_outer, int n_inner, double ln_far, doubl
                      double bao_lo, double bao_hi, double bao_dq)
 {
     g_cfg = QuadConfig();
-    g_cfg.qmin = qmin; g_cfg.n_outer = n_outer; g_cfg.n_inner = n_inner;
-    g_cfg.ln_far = ln_far; g_cfg.ln_mid = ln_mid;
+    g_cfg.qmin = qmin; g_cfg.ln_far = ln_far; g_cfg.ln_mid = ln_mid;
     g_cfg.bao_lo = bao_lo; g_cfg.bao_hi = bao_hi; g_cfg.bao_dq = bao_dq;
+    g_cfg.ln_thin = 0.0;
+    g_cfg.set_uniform(n_outer, n_inner, n_inner);
+}
+
+void emul_set_config_default() { g_cfg = QuadConfig(); }
+void emul_use_ml_variant() { g_cfg = g_cfg.ml_variant(); }
+
+void emul_set_tier(int i, double k_below, int n_outer, int n_inner, int n_thin)
+{
+    g_cfg.tier[i] = {k_below, n_outer, n_inner, n_thin};
+}
+
+void emul_set_config_ext(int n_inner_thin, double ln_thin, double ln_inner, double mid_lo, double mid_hi)
+{
+    for (int i = 0; i < 4; i++) g_cfg.tier[i].n_thin = n_inner_thin;
+    g_cfg.ln_thin = ln_thin; g_cfg.ln_inner = ln_inner;
+    g_cfg.mid_lo = mid_lo; g_cfg.mid_hi = mid_hi;
 }
 
 int emul_knot_count() { return g_grid.size(); }
@@ -160,4 +176,14 @@ extern "C" void emul_nak_spline(int n, const double* x, const double* y, int nq,
     nak_spline_build(n, x, y, b.data(), c.data(), d.data(), M.data(), w.data());
     const double lnx0 = std::log(x[0]), inv = (n - 1)/std::log(x[n-1]/x[0]);
     for (int i = 0; i < nq; i++) out[i] = pw_cubic_eval_log(n, x, y, b.data(), c.data(), d.data(), lnx0, inv, xq[i]);
+}
+
+// node census for quadrature tuning: per node the global outer index and the stencil start
+extern "C" long long emul_nodes(int nk, const double* k, double qmax, long long cap, int* outer, int* j0, double* wgt)
+{
+    HalfNodes H;
+    build_half_nodes(k, nk, qmax, g_cfg, g_grid, H);
+    const long long n = (long long)H.n_nodes();
+    for (long long i = 0; i < n && i < cap; i++) { outer[i] = H.n_outer[i]; j0[i] = H.b_j0[i]; wgt[i] = H.wgt[i]; }
+    return n;
 }
