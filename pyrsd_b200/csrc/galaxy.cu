@@ -258,14 +258,14 @@ __constant__ int c_pair_b[GAL_NPAIR] = {0, 1, 1, 2, 3, 2, 3, 2, 3, 3};
 __global__ void __launch_bounds__(128)
 k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict__ kst, const int* __restrict__ cmap,
               const double* __restrict__ par, const double* __restrict__ stoch, const double* __restrict__ scal,
-              const double* __restrict__ base, double* __restrict__ pairspl)
+              const double* __restrict__ base, const double* __restrict__ nakfac, double* __restrict__ pairspl)
 {
     extern __shared__ double sm_gm[];
     const int nkm = G.nkm;
     double* X = sm_gm;                       // [nkm]
     double* Y = X + nkm;                     // [4][nkm]
-    double* W = Y + 4*nkm;                   // [4][5 nkm] work: b c d M w
-    double* S = W + 20*nkm;                  // stochasticity spline: x y b c d M w  [7][20]
+    double* W = Y + 4*nkm;                   // [4][nkm] second derivatives of the moment splines
+    double* S = W + 4*nkm;                   // stochasticity spline: x y b c d M w  [7][20]
     const int pr = blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
     const int c = cmap[w];
     const double* p = par + (size_t)w*GAL_NPAR;
@@ -348,20 +348,45 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
         Y[i] = mu0; Y[nkm + i] = mu2; Y[2*nkm + i] = mu4; Y[3*nkm + i] = mu6;
     }
     __syncthreads();
+    // not-a-knot splines of the four moments on the model grid (the reference's RSDSpline on self.k): right-hand
+    // sides by the whole CTA, the two substitution sweeps with the precomputed Thomas factors of the grid
+    // (nak_factor) by one thread per moment, coefficients by the whole CTA
+    double* Mm = W;                          // [4][nkm] second derivatives
+    const int m_in = nkm - 2;
+    for (int idx = tid; idx < 4*nkm; idx += blockDim.x) {
+        const int m = idx/nkm, i = idx - m*nkm;
+        if (i >= 1 && i <= m_in) {
+            const double h0 = X[i] - X[i - 1], h1 = X[i + 1] - X[i];
+            const double* y = Y + m*nkm;
+            Mm[idx] = 6.0*((y[i + 1] - y[i])/h1 - (y[i] - y[i - 1])/h0);
+        }
+    }
+    __syncthreads();
     if (tid < 4) {
-        double* wk = W + (size_t)tid*5*nkm;
-        nak_spline_build(nkm, X, Y + tid*nkm, wk, wk + nkm, wk + 2*nkm, wk + 3*nkm, wk + 4*nkm);
+        double* M = Mm + tid*nkm;
+        const double* w = nakfac; const double* iden = nakfac + nkm; const double* sub = nakfac + 2*nkm;
+        double prev = M[1]*iden[1];
+        M[1] = prev;
+        for (int i = 2; i <= m_in; i++) { prev = (M[i] - sub[i]*prev)*iden[i]; M[i] = prev; }
+        for (int i = m_in - 1; i >= 1; i--) { prev = M[i] - w[i]*prev; M[i] = prev; }
+        const double h0 = X[1] - X[0], h1 = X[2] - X[1];
+        M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
+        const double hn = X[nkm - 1] - X[nkm - 2], hm = X[nkm - 2] - X[nkm - 3];
+        M[nkm - 1] = M[nkm - 2] + (hn/hm)*(M[nkm - 2] - M[nkm - 3]);
     }
     __syncthreads();
     // store [walker][pair][moment][Y | b | c | d]
     double* o = pairspl + ((size_t)w*GAL_NPAIR + pr)*16*nkm;
     for (int idx = tid; idx < 4*nkm; idx += blockDim.x) {
         const int m = idx/nkm, i = idx - m*nkm;
-        const double* wk = W + (size_t)m*5*nkm;
-        o[(m*4 + 0)*nkm + i] = Y[m*nkm + i];
-        o[(m*4 + 1)*nkm + i] = wk[i];
-        o[(m*4 + 2)*nkm + i] = wk[nkm + i];
-        o[(m*4 + 3)*nkm + i] = wk[2*nkm + i];
+        const int j = min(i, nkm - 2);       // the last knot repeats the last interval's coefficients
+        const double* y = Y + m*nkm;
+        const double* M = Mm + m*nkm;
+        const double h = X[j + 1] - X[j];
+        o[(m*4 + 0)*nkm + i] = y[i];
+        o[(m*4 + 1)*nkm + i] = (y[j + 1] - y[j])/h - h*(2.0*M[j] + M[j + 1])/6.0;
+        o[(m*4 + 2)*nkm + i] = 0.5*M[j];
+        o[(m*4 + 3)*nkm + i] = (M[j + 1] - M[j])/(6.0*h);
     }
 }
 
@@ -478,6 +503,8 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     std::vector<double> fac;
     nak_factor(nki, k_interp, fac);
     d_nakfac.upload(fac, c.stream);
+    nak_factor(nkm, km.data(), fac);
+    d_nakfac_m.upload(fac, c.stream);
     zel.build(c, km.data(), nkm);
     c.sync();
 }
@@ -557,10 +584,10 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     c.launches++;
     pairspl.ensure((size_t)nw*GAL_NPAIR*16*nkm);
     {
-        const size_t smem = (size_t)(25*nkm + 7*GAL_NSTOCH)*sizeof(double);
+        const size_t smem = (size_t)(9*nkm + 7*GAL_NSTOCH)*sizeof(double);
         if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_gal_moments<<<dim3(GAL_NPAIR, nw), 128, smem, s>>>(G, d_km.p, d_kstoch.p, d_cmap.p, d_par.p, d_stoch.p, pt.scalars.p,
-                                                             base.p, pairspl.p);
+                                                             base.p, d_nakfac_m.p, pairspl.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches++;
     }

@@ -2,6 +2,7 @@
 #include "linear.cuh"
 #include "linear_math.cuh"
 #include "spectra.cuh"
+#include "ptx.cuh"
 
 namespace prsd {
 
@@ -50,55 +51,50 @@ void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs)
 }
 
 // ---------------------------------------------------------------- apply
-// One warp computes 4 outputs for 8 rows; lanes stride over the knots.
-static const int LA_OUT = 4, LA_ROW = 8;
+// out[row][o] = sum_j T[row][j] Omega[o][j] is a (rows x knots) . (knots x outputs) product: FP64 tensor-core MMAs
+// (DMMA m8n8k4).  One warp owns 8 outputs and 32 rows (4 row tiles), the 8 warps of a CTA share the same rows so
+// the table fragments come from L1; Omega, the large operand (nout x 2468 doubles), is read once per 32 rows.
+static const int LA_MT = 4;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_linear_apply(int nout, int nrow, const double* __restrict__ Omega, const double* __restrict__ tables,
                const int* __restrict__ tab_index, double* __restrict__ out)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int o0 = (blockIdx.x*4 + warp)*LA_OUT;
-    const int r0 = blockIdx.y*LA_ROW;
+    const int o0 = (blockIdx.x*8 + warp)*8;
+    const int r0 = blockIdx.y*(8*LA_MT);
     if (o0 >= nout) return;
-    const double* om[LA_OUT];
-    const double* tb[LA_ROW];
+    const int sub = lane & 3, grp = lane >> 2;
+    const double* bp = Omega + (size_t)min(o0 + grp, nout - 1)*TAB_MPAD + sub;
+    const double* ap[LA_MT];
 #pragma unroll
-    for (int i = 0; i < LA_OUT; i++) om[i] = Omega + (size_t)min(o0 + i, nout - 1)*TAB_MPAD;
+    for (int m = 0; m < LA_MT; m++) ap[m] = tables + (size_t)tab_index[min(r0 + 8*m + grp, nrow - 1)]*TAB_MPAD + sub;
+    double acc[LA_MT][2];
 #pragma unroll
-    for (int r = 0; r < LA_ROW; r++) tb[r] = tables + (size_t)tab_index[min(r0 + r, nrow - 1)]*TAB_MPAD;
-    double acc[LA_OUT][LA_ROW];
+    for (int m = 0; m < LA_MT; m++) acc[m][0] = acc[m][1] = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < TAB_MPAD; j += 4) {
+        const double b = __ldg(bp + j);
 #pragma unroll
-    for (int i = 0; i < LA_OUT; i++)
-#pragma unroll
-        for (int r = 0; r < LA_ROW; r++) acc[i][r] = 0.0;
-    for (int j = lane; j < TAB_M; j += 32) {
-        double w[LA_OUT], t[LA_ROW];
-#pragma unroll
-        for (int i = 0; i < LA_OUT; i++) w[i] = __ldg(om[i] + j);
-#pragma unroll
-        for (int r = 0; r < LA_ROW; r++) t[r] = __ldg(tb[r] + j);
-#pragma unroll
-        for (int i = 0; i < LA_OUT; i++)
-#pragma unroll
-            for (int r = 0; r < LA_ROW; r++) acc[i][r] = fma(w[i], t[r], acc[i][r]);
+        for (int m = 0; m < LA_MT; m++) dmma_m8n8k4(acc[m][0], acc[m][1], __ldg(ap[m] + j), b);
     }
 #pragma unroll
-    for (int i = 0; i < LA_OUT; i++)
+    for (int m = 0; m < LA_MT; m++) {
+        const int row = r0 + 8*m + grp;
 #pragma unroll
-        for (int r = 0; r < LA_ROW; r++) {
-            double v = acc[i][r];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            if (lane == 0 && o0 + i < nout && r0 + r < nrow) out[(size_t)(r0 + r)*nout + o0 + i] = v;
+        for (int e = 0; e < 2; e++) {
+            const int col = o0 + 2*sub + e;
+            if (row < nrow && col < nout) out[(size_t)row*nout + col] = acc[m][e];
         }
+    }
 }
 
 void LinearOp::apply(Context& ctx, const double* tables, const int* tab_index, int nrow, double* out) const
 {
-    dim3 grid((nout + 4*LA_OUT - 1)/(4*LA_OUT), (nrow + LA_ROW - 1)/LA_ROW);
+    static_assert(TAB_MPAD % 4 == 0, "table rows must be a whole number of DMMA k-steps");
+    dim3 grid((nout + 63)/64, (nrow + 8*LA_MT - 1)/(8*LA_MT));
     ProfScope prof(ctx, PROF_LINEAR);
-    k_linear_apply<<<grid, 128, 0, ctx.stream>>>(nout, nrow, Omega.p, tables, tab_index, out);
+    k_linear_apply<<<grid, 256, 0, ctx.stream>>>(nout, nrow, Omega.p, tables, tab_index, out);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
 }

@@ -132,7 +132,9 @@ k_nodal_apply(const NodalArgs g)
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k_lo = blockIdx.y*g.kchunk, k_hi = min(g.nk, k_lo + g.kchunk);
+    // k is dealt round-robin over blockIdx.y: the node count grows ~10x from the lowest to the highest k
+    // (quad.h tiers), contiguous chunks would leave a long tail
+    const int k_stride = gridDim.y;
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -147,7 +149,7 @@ k_nodal_apply(const NodalArgs g)
     }
     mbar_wait(mbar, 0);
 
-    for (int ik = k_lo; ik < k_hi; ik++) {
+    for (int ik = blockIdx.y; ik < g.nk; ik += k_stride) {
         // ---- P(a) of the four spectra for every outer node of this k
         const int64_t o0 = g.outer_off[ik];
         const int n_out = (int)(g.outer_off[ik + 1] - o0);
@@ -230,12 +232,12 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
 
 void nodal_apply_ml(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
 {
-    launch_nodal<SpecML>(ctx, op, tables, slot_tab, ncosmo, ncosmo, 2, out);
+    launch_nodal<SpecML>(ctx, op, tables, slot_tab, ncosmo, ncosmo, 8, out);
 }
 
 void nodal_apply_diag(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
 {
-    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + 3)/4, ncosmo, 4, out);
+    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + 3)/4, ncosmo, 8, out);
 }
 
 } // namespace prsd

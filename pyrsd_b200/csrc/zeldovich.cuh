@@ -26,6 +26,7 @@ struct ZelPlan {
     std::vector<double> k;
     DevBuf<double> dk;
     DevBuf<double> g;           // [16][1024]
+    DevBuf<double> G;           // [nk][16][1024] g folded with the per-k output stencil
     DevBuf<int> ja, jb;         // [nk][16]
     DevBuf<double> wa, wb;      // [nk][16]
     DevBuf<double> r;           // [1024]
