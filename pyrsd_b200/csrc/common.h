@@ -52,7 +52,14 @@ inline std::string strprintf(const char* fmt, ...)
         if (!(cond)) throw ::prsd::Error(::prsd::ERR_INVALID, ::prsd::strprintf(__VA_ARGS__)); \
     } while (0)
 
-// Device buffer (cudaMallocAsync-free: plain cudaMalloc, freed in dtor).
+// Device memory comes from a small caching allocator (context.cu): cudaMalloc / cudaFree cost 0.1-1 ms each and
+// cudaFree synchronises the device, which would serialise every call that owns temporaries.  A freed block
+// becomes reusable only after the next cudaDeviceSynchronize() issued by the allocator itself, so work still in
+// flight on any stream can never see its memory handed to someone else.
+void* pool_alloc(size_t bytes);
+void  pool_free(void* p) noexcept;
+void  pool_trim() noexcept;          // give every cached block back to the driver
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -70,7 +77,7 @@ struct DevBuf {
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
     }
@@ -78,7 +85,7 @@ struct DevBuf {
     {
         release();
         n = n_;
-        if (n) PRSD_CUDA(cudaMalloc((void**)&p, n*sizeof(T)));
+        if (n) p = static_cast<T*>(pool_alloc(n*sizeof(T)));
     }
     void ensure(size_t n_) { if (n_ > n) alloc(n_); }
     void upload(const T* h, size_t cnt, cudaStream_t s)

@@ -1,7 +1,92 @@
 // context.cu -- device context.
 #include "common.h"
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 namespace prsd {
+
+// ------------------------------------------------------------------ caching allocator
+namespace {
+struct Block { size_t bytes; int device; };
+struct Pool {
+    std::mutex mu;
+    std::unordered_map<void*, Block> live;                     // every block handed out
+    std::multimap<std::pair<int, size_t>, void*> ready;        // (device, bytes) -> reusable blocks
+    std::vector<std::pair<void*, Block>> pending;              // freed, but work using them may be in flight
+    bool closed = false;                                       // set at static destruction: leak instead of touching CUDA
+    ~Pool() { closed = true; }
+};
+Pool& pool() { static Pool* p = new Pool; return *p; }         // never destroyed: static DevBufs outlive main()
+
+size_t round_up(size_t b) { return (b + 511) & ~size_t(511); }
+}
+
+void* pool_alloc(size_t bytes)
+{
+    Pool& P = pool();
+    int dev = 0;
+    PRSD_CUDA(cudaGetDevice(&dev));
+    const size_t want = round_up(bytes);
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto take = [&]() -> void* {
+        auto it = P.ready.lower_bound({dev, want});
+        if (it != P.ready.end() && it->first.first == dev && it->first.second <= want + want/4) {
+            void* p = it->second;
+            P.live[p] = {it->first.second, dev};
+            P.ready.erase(it);
+            return p;
+        }
+        return nullptr;
+    };
+    if (void* p = take()) return p;
+    if (!P.pending.empty()) {
+        // blocks freed since the last synchronisation become reusable now
+        PRSD_CUDA(cudaDeviceSynchronize());           // the CURRENT device: only its blocks move
+        std::vector<std::pair<void*, Block>> keep;
+        for (auto& e : P.pending) {
+            if (e.second.device == dev) P.ready.insert({{dev, e.second.bytes}, e.first});
+            else keep.push_back(e);
+        }
+        P.pending.swap(keep);
+        if (void* p = take()) return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        // out of memory: return the cache to the driver and retry once
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        for (auto& r : P.ready) cudaFree(r.second);
+        P.ready.clear();
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess)
+        throw Error(ERR_CUDA, strprintf("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)));
+    P.live[p] = {want, dev};
+    return p;
+}
+
+void pool_free(void* p) noexcept
+{
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) return;
+    P.pending.push_back({p, it->second});
+    P.live.erase(it);
+}
+
+void pool_trim() noexcept
+{
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    for (auto& e : P.pending) cudaFree(e.first);     // cudaFree synchronises the owning device
+    for (auto& r : P.ready) cudaFree(r.second);
+    P.pending.clear();
+    P.ready.clear();
+}
 
 Context::Context(int dev) : device(dev)
 {
@@ -28,6 +113,7 @@ Context::~Context()
         for (auto& pr : prof_pending[t]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+    pool_trim();
 }
 
 cudaEvent_t Context::prof_event()
