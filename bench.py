@@ -74,34 +74,56 @@ def synthetic_batch(n, rank=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every few ms (the timed
+    region of a default run lasts tens of ms), `nvidia-smi` as a fallback"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.armed = index, [], False, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
+            if not self.armed:
+                time.sleep(0.001)
+                continue
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(',')])
+                if self.nvml is not None:
+                    n = self.nvml
+                    mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+                        else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                    self.samples.append([mhz, self.max_mhz] + flags)
+                    time.sleep(0.002)
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                    if out:
+                        f = [x.strip() for x in out.split(',')]
+                        self.samples.append([float(f[0]), float(f[1])] + [x.lower().startswith('active') for x in f[2:6]])
+                    time.sleep(0.05)
             except Exception:
-                pass
-            time.sleep(0.2)
+                time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = []
-        for j, name in enumerate(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']):
-            if any(s[2 + j].lower().startswith('active') for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm)//2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        sm = sorted(s[0] for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [names[j] for j in range(4) if any(s[2 + j] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm)//2], "sm_max_mhz": self.samples[0][1], "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -120,7 +142,7 @@ def run_gpu(args):
     L = rsd._L()
     vp, dp = C.c_void_p, N._dp
     L.prsd_ctx_profile.argtypes = [vp, C.c_int]
-    L.prsd_ctx_profile_read.argtypes = [vp, dp, np.ctypeslib.ndpointer(dtype=np.int64, flags='C_CONTIGUOUS')]
+    L.prsd_ctx_profile_read.argtypes = [vp, dp, np.ctypeslib.ndpointer(dtype=np.int64, flags='C_CONTIGUOUS')]   # 8 families
     L.prsd_fp64_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.prsd_spectra_reload_device.argtypes = [vp, vp, vp, vp]
     L.prsd_ctx_stream.argtypes = [vp, C.POINTER(vp)]
@@ -178,6 +200,8 @@ def run_gpu(args):
         sp2.close()
         return h_out
 
+    sampler = ClockSampler(local)
+
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
             fn()
@@ -187,6 +211,7 @@ def run_gpu(args):
             dist.barrier()
         if profile:
             N.check(L.prsd_ctx_profile(ctx.ptr, 1))
+        sampler.armed = True
         l0 = ctx.launches()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for e0, e1 in evs:
@@ -196,13 +221,14 @@ def run_gpu(args):
             fn()
             e1.record(stream)
         torch.cuda.synchronize()
+        sampler.armed = False
         if world > 1:
             dist.barrier()
         ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
         launches = ctx.launches() - l0
         prof = None
         if profile:
-            pms, pc = np.zeros(6), np.zeros(6, dtype=np.int64)
+            pms, pc = np.zeros(8), np.zeros(8, dtype=np.int64)
             N.check(L.prsd_ctx_profile_read(ctx.ptr, pms, pc))
             N.check(L.prsd_ctx_profile(ctx.ptr, 0))
             prof = (pms, pc)
@@ -219,7 +245,6 @@ def run_gpu(args):
     N.check(L.prsd_fp64_peak(ctx.ptr, 1, C.byref(pk)))
     peak_dmma = pk.value
 
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, launches, prof = timed(step_device, args.steps, args.warmup, profile=True)
@@ -236,19 +261,31 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel family (DMMA contraction), see DESIGN.md section 5
+    # ---- roofline of the mode-coupling operators: algorithmic FP64 flops = declared nodes x
+    #      cosmologies x flops per (node, cosmology) of the implemented rule, FMA = 2
     pms, pc = prof
-    rows_1l = 8*((B + 7)//8)
-    flops_launch = {   # algorithmic FP64 flops per step: nodes x rows x (2 ncol + 9)
-        'oneloop': info['nodes_oneloop']*rows_1l*(2*6 + 9),
-        'ik': info['nodes_ik']*rows_1l*(2*37 + 9),
-        'ml': 2*info['nodes_ml_half']*B*8*(2*7 + 9),
+    FLOP_ML, FLOP_DIAG, FLOP_IK = 105, 21, 83
+    kern = {
+        'k_nodal_apply<SpecML>': dict(fam=6, flops=info['nodes_ml_half']*B*FLOP_ML, pipe='fp64 DFMA'),
+        'k_nodal_apply<SpecDiag>': dict(fam=7, flops=info['nodes_oneloop']*B*FLOP_DIAG, pipe='fp64 DFMA'),
+        'k_bilinear_apply<5>': dict(fam=0, flops=info['nodes_ik']*8*((B + 7)//8)*FLOP_IK, pipe='fp64 DMMA m8n8k4'),
     }
-    flops_step = sum(flops_launch.values())
-    bil_ms_step = pms[0]/args.steps
-    achieved = flops_step/(bil_ms_step*1e-3)/1e12 if bil_ms_step > 0 else None
-    fam = ['bilinear_dmma', 'linear_ops', 'zeldovich', 'galaxy', 'spline_builds', 'fftlog']
-    shares = {fam[i]: round(pms[i]/ms_dev, 4) for i in range(6)}
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_summary.json'))).get('dram_bytes_per_launch', {})
+    except Exception:
+        pass
+    for name, kd in kern.items():
+        n = max(int(pc[kd['fam']]), 1)
+        kd['ms'] = pms[kd['fam']]/n
+        kd['launches_per_step'] = n//args.steps
+        kd['flops'] = float(kd['flops'])
+        kd['achieved'] = kd['flops']/(kd['ms']*1e-3)/1e12 if kd['ms'] > 0 else None
+        kd['share'] = pms[kd['fam']]/ms_dev
+    top = max(kern, key=lambda k: kern[k]['share'])
+    peak = peak_dmma if 'DMMA' in kern[top]['pipe'] else peak_dfma
+    fam = ['ik_dmma', 'linear_ops', 'zeldovich', 'galaxy', 'spline_builds', 'fftlog', 'imn_oneloop_nodal', 'oneloop_tables_nodal']
+    shares = {fam[i]: round(pms[i]/ms_dev, 4) for i in range(8)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -270,13 +307,22 @@ def run_gpu(args):
                                           + h_kk.numel()*8 + h_mm.numel()*8),
                 "d2h_bytes_per_step": int(h_out.numel()*8), "ms_per_step": ms_e2e/e2e_steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
-                     "frac": (achieved/peak_dmma) if (achieved and peak_dmma) else None, "traffic": None,
-                     "kernel": "k_bilinear_apply<NT> (FP64 DMMA m8n8k4 contraction, 3 operators x launches per step)",
-                     "peak_source": "FP64 DMMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                                    "DFMA pipe measured at %.1f TFLOP/s; hbm_gbs of measured = %s" % (peak_dfma, peaks.get('hbm_gbs')),
-                     "algorithmic_flops_per_step": flops_step, "kernel_ms_per_step": bil_ms_step,
-                     "launches_per_step": int(pc[0]//args.steps), "kernel_share_of_step": shares},
+        "roofline": {"bound": "tensor", "achieved": kern[top]['achieved'], "peak": peak, "unit": "TFLOP/s",
+                     "frac": (kern[top]['achieved']/peak) if (kern[top]['achieved'] and peak) else None,
+                     "traffic": traffic.get(top),
+                     "kernel": top, "pipe": kern[top]['pipe'] + " (B200 runs DFMA and FP64 DMMA on the same pipe: measured peaks "
+                                                                "%.1f / %.1f TFLOP/s)" % (peak_dfma, peak_dmma),
+                     "peak_source": "FP64 microbenchmark (csrc/microbench.cu) run in this process before the timed region; "
+                                    "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs there = %s)" % peaks.get('hbm_gbs'),
+                     "algorithmic_flops_per_launch": kern[top]['flops'], "kernel_ms_per_launch": kern[top]['ms'],
+                     "launches_per_step": kern[top]['launches_per_step'],
+                     "flops_per_node_per_cosmology": {"k_nodal_apply<SpecML>": FLOP_ML, "k_nodal_apply<SpecDiag>": FLOP_DIAG,
+                                                      "k_bilinear_apply<5>": FLOP_IK},
+                     "nodes": {"imn_oneloop": info['nodes_ml_half'], "oneloop_tables": info['nodes_oneloop'], "ik": info['nodes_ik']},
+                     "other_kernels": {k: {"achieved": v['achieved'], "frac": (v['achieved']/(peak_dmma if 'DMMA' in v['pipe'] else peak_dfma))
+                                           if v['achieved'] else None, "ms_per_launch": v['ms'], "traffic": traffic.get(k)}
+                                       for k, v in kern.items() if k != top},
+                     "kernel_share_of_step": shares},
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
@@ -287,86 +333,77 @@ def run_gpu(args):
 
 
 # ------------------------------------------------------------------ CPU reference (oracle)
-def _cpu_sample(seed):
-    """a BOUNDED sample of one full evaluation on the reference's own C++ (oracle/_ref) at the reference's default
-    tolerances; returns the estimated seconds of the full evaluation (sample time / fraction of the work)."""
+def _cpu_eval(seed, thin=1):
+    """ONE evaluation of the hot path on the reference's own C++ (oracle/_ref) at the reference's default tolerances:
+    every PT table of rsd/pt_integrals.py (16 I, 6 J, 13 K, sigma_v^2(k) on the 250-point k_interp; the four
+    one-loop spectra on 1000 k; the 7 x 3 ImnOneLoop integrals), X(r), Y(r) on 1024 r, and the Zel'dovich P00/P01/P11
+    on the 200-point model grid at both normalisations.  `thin` > 1 evaluates every thin-th point of each grid and
+    scales the time (a bounded sample); returns the seconds of the full evaluation."""
     from oracle import gcl_ref as R
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_pt.npz'))
     cosmo = R.golden_cosmology(g)
     P = R.RefLinearPS(cosmo)
-    rng = np.random.default_rng(seed)
-    kint = np.logspace(np.log10(5e-6), 0, 250)
-    sub = np.sort(rng.choice(250, 10, replace=False))            # 1/25 of k_interp
-    k1 = R.logspace(1e-5, 10, 1000)
-    sub1 = np.sort(rng.choice(1000, 20, replace=False))          # 1/50 of the one-loop grid
-    t_total = 0.0
+    off = seed % thin
+    kint = np.ascontiguousarray(np.logspace(np.log10(5e-6), 0, 250)[off::thin])
+    k1 = np.ascontiguousarray(R.logspace(1e-5, 10, 1000)[off::thin])
     t0 = time.perf_counter()
     for m in range(4):
         for n in range(4):
-            R.Imn(P, kint[sub], m, n, epsrel=1e-4)
+            R.Imn(P, kint, m, n, epsrel=1e-4)
     for (m, n) in [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (2, 0)]:
-        R.Jmn(P, kint[sub], m, n, epsrel=1e-4)
+        R.Jmn(P, kint, m, n, epsrel=1e-4)
     for (m, n, t, p) in [(0, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 1, 1, 0), (0, 2, 1, 0), (1, 0, 0, 0), (1, 1, 0, 0),
                          (1, 0, 1, 0), (1, 1, 1, 0), (2, 0, 0, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1)]:
-        R.Kmn(P, kint[sub], m, n, bool(t), p, epsrel=1e-3)
-    P.VelocityDispersion(kint[sub], 0.5)
-    t_total += (time.perf_counter() - t0)*25
-    t0 = time.perf_counter()
+        R.Kmn(P, kint, m, n, bool(t), p, epsrel=1e-3)
+    P.VelocityDispersion(kint, 0.5)
     for (m, n) in [(0, 0), (0, 1), (1, 1), (2, 3), (3, 2), (3, 3)]:
-        R.Imn(P, k1[sub1], m, n, epsrel=1e-4)
+        R.Imn(P, k1, m, n, epsrel=1e-4)
     for (m, n) in [(0, 0), (0, 1), (1, 1)]:
-        R.Jmn(P, k1[sub1], m, n, epsrel=1e-4)
-    t_total += (time.perf_counter() - t0)*50
+        R.Jmn(P, k1, m, n, epsrel=1e-4)
     # ImnOneLoop on the shipped one-loop tables
     ol = {w: R.RefOneLoop(P, w, 1e-4, g['oneloop_P%s_0' % w]) for w in ('dd', 'dv', 'vv')}
-    sub2 = sub[:5]                                                 # 1/50
-    t0 = time.perf_counter()
     for (p1, p2, m, n) in [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
                            ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]:
         for which in ('linear', 'cross', 'oneloop'):
-            R.ImnOneLoop(ol[p1], None if p2 is None else ol[p2], kint[sub2], m, n, which, 1e-4)
-    t_total += (time.perf_counter() - t0)*50
+            R.ImnOneLoop(ol[p1], None if p2 is None else ol[p2], kint, m, n, which, 1e-4)
     # Zel'dovich set-up X(r), Y(r) and P00/P01/P11 on the 200-point model grid
-    r = 10.**(1.5 + (np.arange(1, 1025) - 512.5)*(7./1024))
-    subr = np.sort(rng.choice(1024, 16, replace=False))           # 1/64
-    t0 = time.perf_counter()
-    P.X_Zel(r[subr])
-    P.Y_Zel(r[subr])
-    t_total += (time.perf_counter() - t0)*64
+    r = np.ascontiguousarray((10.**(1.5 + (np.arange(1, 1025) - 512.5)*(7./1024)))[off::thin])
+    P.X_Zel(r)
+    P.Y_Zel(r)
     state = (float(g['zel_sigma8_z']), float(g['zel_k0_low']), float(g['zel_sigmasq']), g['zel_X0'], g['zel_XX'], g['zel_YY'])
     z = R.RefZeldovich(cosmo, False, state)
-    km = np.logspace(-3, np.log10(0.5), 200)[::20]                # 1/20
-    t0 = time.perf_counter()
+    km = np.ascontiguousarray(np.logspace(-3, np.log10(0.5), 200)[off::thin])
     for name in ('P00', 'P01', 'P11'):
         z(name, km)
         z(name, km)                                               # second normalisation (Jennings fits at sigma8_z / D)
-    t_total += (time.perf_counter() - t0)*20
-    return t_total
+    return (time.perf_counter() - t0)*thin
 
 
 def cpu_baseline_sample():
-    """reference C++ (oracle/_ref), 1 core (its packaged build has no OpenMP, setup.py:188), bounded sample"""
+    """reference C++ (oracle/_ref), 1 core (its packaged build has no OpenMP, setup.py:188): bounded sample = every
+    4th point of every grid of one evaluation (~10-15 s of CPU work), scaled by 4"""
     from oracle import gcl_ref as R
     if not R.available():
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/libgcl_ref.so missing"}
     t0 = time.perf_counter()
-    est = _cpu_sample(SEED)
+    est = _cpu_eval(SEED, thin=4)
     wall = time.perf_counter() - t0
     return {"value": 1.0/est, "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": "reference C++ at its default epsrel on 1/25 of k_interp (all 16 I, 6 J, 13 K, sigma_v^2(k)), 1/50 of the one-loop "
-                      "grid (6 I + 3 J), 1/50 of the ImnOneLoop work, 1/64 of X(r)/Y(r), 1/20 of the Zel'dovich P00/P01/P11 "
-                      "evaluations; each part scaled by its fraction (%.1f s of CPU work -> %.1f s per full evaluation); the "
-                      "Python P(k,mu) assembly of the reference (<1 s) is NOT included" % (wall, est),
-            "seconds_per_eval_estimate": est}
+            "sample": "every 4th point of every grid of ONE evaluation on the reference C++ at its default epsrel (all 16 I, 6 J, 13 K "
+                      "and sigma_v^2(k) on 250 k, the four one-loop spectra on 1000 k, 7 x 3 ImnOneLoop integrals, X(r)/Y(r) on 1024 r, "
+                      "Zel'dovich P00/P01/P11 on the 200-point model grid at two normalisations): %.1f s of CPU work, x 4 = %.1f s per "
+                      "evaluation; the Python P(k,mu) assembly of the reference (<1 s, docs/source/gal-power-overview.rst:68-69) is "
+                      "NOT included" % (wall, est),
+            "seconds_per_eval": est}
 
 
 def _ref_worker(seed):
-    return _cpu_sample(seed)
+    return _cpu_eval(seed, thin=4)
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation on every host core (one process per core, one
-    cosmology each: how rsdfit's MPI pool uses it), bounded sample per step"""
+    cosmology each: how rsdfit's MPI pool uses it); each step is a bounded sample (every 4th point of each grid)"""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -376,9 +413,9 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    cores = max(1, min(cores, 64))
+    cores = max(1, min(cores, 256))
     pool = mp.get_context('fork').Pool(cores)
-    for w in range(args.warmup if args.warmup < 2 else 1):
+    for w in range(min(args.warmup, 1)):
         pool.map(_ref_worker, [SEED + i for i in range(cores)])
     t0 = time.perf_counter()
     ests = []
@@ -389,8 +426,9 @@ def run_reference(args):
     # every worker processed a bounded sample standing for one full evaluation of `est` seconds
     est = float(np.mean(ests))
     value = cores/est
-    sample = ("%d processes x %d steps, each a bounded sample of one full evaluation (fractions as in cpu_baseline); "
-              "mean estimated %.1f s per evaluation per core; wall %.1f s" % (cores, args.steps, est, wall))
+    sample = ("%d processes x %d steps; each step of a process = every 4th point of every grid of one full evaluation "
+              "(as in cpu_baseline), time scaled by 4; mean %.1f s per evaluation per core; wall %.1f s"
+              % (cores, args.steps, est, wall))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3*wall/max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -176,10 +176,11 @@ int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
 
 /* ---- measurement support (bench.py) -------------------------------------------------- */
-/* per-kernel-family CUDA-event timing on the context's stream; families: 0 bilinear (DMMA contraction),
- * 1 linear operators, 2 Zel'dovich, 3 galaxy assembly, 4 spline builds, 5 FFTLog */
+/* per-kernel-family CUDA-event timing on the context's stream; families: 0 I/K operator (DMMA contraction),
+ * 1 linear operators, 2 Zel'dovich, 3 galaxy assembly, 4 spline builds, 5 FFTLog, 6 ImnOneLoop operator
+ * (k_nodal_apply<SpecML>), 7 one-loop-table operator (k_nodal_apply<SpecDiag>) */
 int prsd_ctx_profile(prsd_ctx* ctx, int enable);      /* also resets the counters */
-int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms6, long long* count6);
+int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms8, long long* count8);
 /* FP64 pipe microbenchmarks: mode 0 DFMA, mode 1 DMMA m8n8k4 (TFLOP/s, best of 4) */
 int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops);
 /* rebuild the linear spectra of a batch from DEVICE-resident k, T [ncosmo][nspl], pars [ncosmo][8] */

@@ -20,7 +20,10 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     HalfNodes H;
     build_half_nodes(k, nk, qmax, cfg, grid, H);
 
-    // pad every k's node list to a multiple of 4 (one DMMA k-step) with weightless nodes
+    // Per k: pad the node list to a multiple of 4 (one DMMA k-step) with weightless nodes, then order it for the
+    // shared-memory reads of the nodal kernels: a half-warp (16 consecutive nodes) reads t[j0 + m] with 8-byte
+    // accesses, which is one wavefront only if the 16 stencil starts are equal or distinct modulo 16.  Nodes
+    // sharing a stencil start are kept together (broadcast) and every half-warp is filled from distinct residues.
     auto g = std::make_shared<NodeGeometry>();
     g->nk = nk;
     g->k.assign(k, k + nk);
@@ -28,23 +31,58 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     std::vector<double> b, wgt, b_coef;
     g->h_node_off.assign(1, 0);
     g->h_outer_off = H.outer_off;
+    std::vector<int64_t> src;                     // source node of every slot of this k (-1: padding)
+    std::vector<std::vector<int64_t>> queue(16);  // per residue: nodes sorted by stencil start
     for (int ik = 0; ik < nk; ik++) {
         const int64_t n0 = H.node_off[ik], n1 = H.node_off[ik + 1];
         const int64_t o0 = H.outer_off[ik];
         g->max_outer = std::max<int>(g->max_outer, (int)(H.outer_off[ik + 1] - o0));
-        for (int64_t j = n0; j < n1; j++) {
-            b.push_back(H.b[j]);
-            wgt.push_back(H.wgt[j]);
-            b_j0.push_back(H.b_j0[j]);
-            n_ol.push_back((int)(H.n_outer[j] - o0));
-            b_coef.insert(b_coef.end(), &H.b_coef[4*j], &H.b_coef[4*j] + 4);
+        const int64_t cnt = n1 - n0, padded = (cnt + 3) & ~int64_t(3);
+        for (auto& q : queue) q.clear();
+        for (int64_t j = n0; j < n1; j++) queue[H.b_j0[j] & 15].push_back(j);
+        for (int64_t j = cnt; j < padded; j++) queue[0].push_back(-1);     // padding reads stencil 0
+        size_t head[16] = {0};
+        for (auto& q : queue)
+            std::stable_sort(q.begin(), q.end(), [&](int64_t x, int64_t y) {
+                return (x < 0 ? 0 : H.b_j0[x]) < (y < 0 ? 0 : H.b_j0[y]); });
+        src.clear();
+        int64_t left = padded;
+        while (left > 0) {
+            int room = (int)std::min<int64_t>(16, left);
+            int order[16];
+            for (int r = 0; r < 16; r++) order[r] = r;
+            std::sort(order, order + 16, [&](int x, int y) { return queue[x].size() - head[x] > queue[y].size() - head[y]; });
+            auto take_item = [&](int r) {
+                // one item = the run of nodes with the same stencil start at the head of residue r
+                auto& q = queue[r];
+                const int j0 = q[head[r]] < 0 ? 0 : H.b_j0[q[head[r]]];
+                while (room > 0 && head[r] < q.size() && (q[head[r]] < 0 ? 0 : H.b_j0[q[head[r]]]) == j0) {
+                    src.push_back(q[head[r]++]);
+                    room--; left--;
+                }
+            };
+            for (int i = 0; i < 16 && room > 0; i++) if (head[order[i]] < queue[order[i]].size()) take_item(order[i]);
+            // residues exhausted: complete the half-warp from the fullest queue (conflicting reads)
+            while (room > 0 && left > 0) {
+                int best = 0;
+                for (int r = 1; r < 16; r++) if (queue[r].size() - head[r] > queue[best].size() - head[best]) best = r;
+                take_item(best);
+            }
         }
-        while ((b.size() & 3) != 0) {
-            b.push_back(k[ik]);
-            wgt.push_back(0.0);
-            b_j0.push_back(0);
-            n_ol.push_back(0);
-            b_coef.insert(b_coef.end(), 4, 0.0);
+        for (int64_t j : src) {
+            if (j >= 0) {
+                b.push_back(H.b[j]);
+                wgt.push_back(H.wgt[j]);
+                b_j0.push_back(H.b_j0[j]);
+                n_ol.push_back((int)(H.n_outer[j] - o0));
+                b_coef.insert(b_coef.end(), &H.b_coef[4*j], &H.b_coef[4*j] + 4);
+            } else {
+                b.push_back(k[ik]);
+                wgt.push_back(0.0);
+                b_j0.push_back(0);
+                n_ol.push_back(0);
+                b_coef.insert(b_coef.end(), 4, 0.0);
+            }
         }
         g->h_node_off.push_back((int64_t)b.size());
     }

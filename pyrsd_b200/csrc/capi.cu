@@ -694,12 +694,13 @@ int prsd_ctx_profile(prsd_ctx* ctx, int enable)
     });
 }
 
-int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms6, long long* count6)
+int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms8, long long* count8)
 {
     return guarded([&] {
-        PRSD_REQUIRE(ctx && ms6 && count6, "null argument");
+        PRSD_REQUIRE(ctx && ms8 && count8, "null argument");
         ctx->c.prof_collect();
-        for (int t = 0; t < PROF_NTAGS; t++) { ms6[t] = ctx->c.prof_ms[t]; count6[t] = ctx->c.prof_count[t]; }
+        static_assert(PROF_NTAGS == 8, "header documents 8 families");
+        for (int t = 0; t < PROF_NTAGS; t++) { ms8[t] = ctx->c.prof_ms[t]; count8[t] = ctx->c.prof_count[t]; }
     });
 }
 

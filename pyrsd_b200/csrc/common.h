@@ -101,7 +101,7 @@ struct DevBuf {
     void zero(cudaStream_t s) { if (n) PRSD_CUDA(cudaMemsetAsync(p, 0, n*sizeof(T), s)); }
 };
 
-enum ProfTag { PROF_BILINEAR = 0, PROF_LINEAR, PROF_ZELDOVICH, PROF_GALAXY, PROF_SPLINE, PROF_FFTLOG, PROF_NTAGS };
+enum ProfTag { PROF_BILINEAR = 0, PROF_LINEAR, PROF_ZELDOVICH, PROF_GALAXY, PROF_SPLINE, PROF_FFTLOG, PROF_NODAL_ML, PROF_NODAL_DIAG, PROF_NTAGS };
 
 struct Context {
     int device = 0;

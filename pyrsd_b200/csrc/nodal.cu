@@ -28,21 +28,22 @@ struct NodalArgs {
 
 // ------------------------------------------------------------------ ImnOneLoop
 // slots: 0 P_L, 1 P_dd, 2 P_dv, 3 P_vv.  W columns (ml_columns()):
-//   0..5   (f(+v) + f(-v)) of h01 h02 h03 h04 f23 f33          -> products symmetric in (a, b)
-//   6..12  f(+v)  of h01 h02 h03 h04 f23 f32 f33               -> P_1(a) P_2(b)
-//   13..19 f(-v)  of the same                                  -> P_1(b) P_2(a)
+//   0..6   f(+v)  of h01 h02 h03 h04 f23 f32 f33               -> P_1(a) P_2(b)
+//   7..13  f(-v)  of the same                                  -> P_1(b) P_2(a)
+// products symmetric in (a, b) use the sum of the two (formed in registers: the FP64 pipe has room, the
+// load pipe does not)
 // accumulators:
 //   0..5 (L,L): h01 h02 h03 h04 f23 f33 | 6,7 cross of ImnOneLoop(P_vv, P_dd): h01 h02 | 8,9 its one-loop part
 //   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
 struct SpecML {
-    static const int NACC = 19, NW = 20, NOUT = 21;
+    static const int NACC = 19, NW = 14, NOUT = 21;
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
         const double La = pa[0], Da = pa[1], Va = pa[2], Wa = pa[3];
         const double Lb = pb[0], Db = pb[1], Vb = pb[2], Wb = pb[3];
-        const double* ws = w;
-        const double* wp = w + 6;
-        const double* wn = w + 13;
+        const double* wp = w;
+        const double* wn = w + 7;
+        const double ws[6] = {wp[0] + wn[0], wp[1] + wn[1], wp[2] + wn[2], wp[3] + wn[3], wp[4] + wn[4], wp[6] + wn[6]};
         const double ll = La*Lb;
 #pragma unroll
         for (int i = 0; i < 6; i++) acc[i] = fma(ws[i], ll, acc[i]);
@@ -91,7 +92,6 @@ struct SpecML {
 std::vector<ColSpec> ml_columns()
 {
     std::vector<ColSpec> c;
-    for (int id : {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F33}) c.push_back({id, 0, NL_INV8PI2});
     for (int sign : {+1, -1})
         for (int id : {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33}) c.push_back({id, sign, NL_INV8PI2});
     return c;
@@ -209,7 +209,7 @@ k_nodal_apply(const NodalArgs g)
 
 template <class Spec>
 static void launch_nodal(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ntiles,
-                         int nrow, int kchunk, double* out)
+                         int nrow, int kchunk, double* out, int prof_tag)
 {
     PRSD_REQUIRE(op.soa && op.ncol_used == Spec::NW, "nodal operator has the wrong layout");
     const NodeGeometry& geo = *op.geo;
@@ -224,7 +224,7 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_nodal_apply<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ntiles, (geo.nk + kchunk - 1)/kchunk);
-    ProfScope prof(ctx, PROF_BILINEAR);
+    ProfScope prof(ctx, prof_tag);
     k_nodal_apply<Spec><<<grid, NL_THREADS, smem, ctx.stream>>>(a);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
@@ -232,12 +232,12 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
 
 void nodal_apply_ml(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
 {
-    launch_nodal<SpecML>(ctx, op, tables, slot_tab, ncosmo, ncosmo, 8, out);
+    launch_nodal<SpecML>(ctx, op, tables, slot_tab, ncosmo, ncosmo, 8, out, PROF_NODAL_ML);
 }
 
 void nodal_apply_diag(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
 {
-    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + 3)/4, ncosmo, 8, out);
+    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + 3)/4, ncosmo, 8, out, PROF_NODAL_DIAG);
 }
 
 } // namespace prsd

@@ -42,7 +42,7 @@ struct QuadConfig {
     QuadTier tier[4]    = {{0.02, 6, 4, 3}, {0.08, 8, 5, 4}, {0.3, 10, 7, 5}, {1e30, 12, 7, 5}};
     // ImnOneLoop (q_max = 10): the one-loop spectra are large at the hard cut and the h02-type kernels cancel to
     // leading order across v, so above k = 0.06 that operator keeps full-order panels everywhere
-    QuadTier ml_tier[4] = {{0.02, 6, 4, 3}, {0.06, 8, 5, 4}, {1e30, 12, 8, 8}, {1e30, 12, 8, 8}};
+    QuadTier ml_tier[4] = {{0.02, 6, 4, 3}, {0.06, 8, 5, 4}, {0.3, 10, 7, 7}, {1e30, 10, 8, 8}};
 
     const QuadTier& tier_of(double k) const
     {
