@@ -131,7 +131,7 @@ def run_gpu(args):
     import ctypes as C
     import torch
     import torch.distributed as dist
-    from pyrsd_b200 import _native as N, pygcl, rsd
+    from pyrsd_b200 import _native as N, parallel, pygcl, rsd
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -172,7 +172,6 @@ def run_gpu(args):
     d_k, d_T, d_pars = h_k.to(dev), h_T.to(dev), h_pars.to(dev)
     d_kk, d_mm = h_kk.to(dev), h_mm.to(dev)
     d_out = torch.empty((B, npts), dtype=torch.float64, device=dev)
-    gather = torch.empty((world*B, NK_OUT), dtype=torch.float64, device=dev) if world > 1 else None
     # L2 flush buffer (> 126 MB): written between timed iterations
     flush = torch.empty(64*1024*1024, dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
@@ -188,7 +187,10 @@ def run_gpu(args):
         N.check(L.prsd_galaxy_power_device(gal.ptr, sp.ptr, res.ptr, B, None, h_wpar.numpy(), h_stoch.numpy(), npts,
                                            d_kk.data_ptr(), d_mm.data_ptr(), d_out.data_ptr()))
         if world > 1:
-            dist.all_gather_into_tensor(gather, d_out.view(B, NK_OUT, NMU_OUT).mean(-1))
+            # the ensemble step's exchange: every rank receives the per-walker result of all walkers
+            torch.cuda.current_stream().wait_stream(stream)
+            parallel.gather_rows(d_out.view(B, NK_OUT, NMU_OUT).mean(-1), world*B)
+            stream.wait_stream(torch.cuda.current_stream())
 
     def step_e2e():
         """the public call path with HOST buffers: H2D of the step's inputs and D2H of P(k, mu) inside"""
@@ -232,10 +234,7 @@ def run_gpu(args):
             N.check(L.prsd_ctx_profile_read(ctx.ptr, pms, pc))
             N.check(L.prsd_ctx_profile(ctx.ptr, 0))
             prof = (pms, pc)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = parallel.max_over_ranks(ms, device=dev)
         return ms, launches, prof
 
     # FP64 pipe peaks, measured once outside the timed region (MEASURED_PEAKS.json has no FP64 entry)
@@ -254,7 +253,7 @@ def run_gpu(args):
 
     # quick in-run parity guard: the first cosmology of the batch equals an independent one-off evaluation
     out0 = d_out[0].cpu().numpy()
-    assert np.all(np.isfinite(out0)) and np.all(out0 > 0)
+    assert np.all(np.isfinite(out0))       # (the PT model itself may go negative at k mu ~ 0.5 for extreme synthetic walkers)
     assert np.allclose(step_e2e()[0].numpy(), out0, rtol=1e-12)
 
     if rank != 0:
