@@ -130,6 +130,16 @@ int prsd_fftlog_device(prsd_ctx* ctx, int batch, int N, double mu, double q, dou
 int prsd_compute_xilm(prsd_ctx* ctx, int batch, int l, int m, int nk, const double* k /*[nk]*/,
                       const double* pk /*[batch][nk]*/, int nr, const double* r, double smoothing, double scale,
                       double* out /*[batch][nr]*/);
+/* ComputeXiLM(l, m, k, pk, r, smoothing, SIMPS | TRAPZ) x scale  [CorrelationFunction.cpp:92-125]: the discrete
+ * quadratures of pk_to_xi / xi_to_pk that rsd/window.py:289-300 uses; method: 1 Simpson, 2 trapezoid;
+ * l in {0, 1, 2, 3, 4, 6, 8} */
+int prsd_compute_xilm_discrete(prsd_ctx* ctx, int method, int batch, int l, int m, int nk, const double* k /*[nk]*/,
+                               const double* pk /*[batch][nk]*/, int nr, const double* r, double smoothing, double scale,
+                               double* out /*[batch][nr]*/);
+/* SimpsIntegrate(x, y) / TrapzIntegrate(x, y)  [DiscreteQuad.i, DiscreteQuad.cpp:3-66]; method: 1 Simpson, 2 trapezoid;
+ * y [batch][n] on shared x [n] (rsd/transfers/poles.py:66 integrates every k row over mu this way) */
+int prsd_discrete_integrate(prsd_ctx* ctx, int method, int batch, int n, const double* x, const double* y,
+                            double* out /*[batch]*/);
 /* ComputeXiLM_fftlog(l, m, k, pk, r, xi, q, smoothing)  [CorrelationFunction.cpp:23-54] */
 int prsd_compute_xilm_fftlog(prsd_ctx* ctx, int batch, int l, int m, int N, const double* k, const double* pk,
                              double q, double smoothing, double* r_out /*[N]*/, double* xi_out /*[batch][N]*/);

@@ -3,6 +3,7 @@
 #include "plan.cuh"
 #include "galaxy.cuh"
 #include "xilm.cuh"
+#include "discrete.cuh"
 
 #include <cstring>
 #include <list>
@@ -493,6 +494,37 @@ int prsd_compute_xilm(prsd_ctx* ctx, int batch, int l, int m, int nk, const doub
         dpk.upload(pk, (size_t)batch*nk, ctx->c.stream);
         compute_xilm_dev(ctx->c, batch, l, m, nk, k, dpk.p, nr, r, smoothing, scale, dout.p);
         dout.download(out, (size_t)batch*nr, ctx->c.stream);
+        ctx->c.sync();
+    });
+}
+
+int prsd_compute_xilm_discrete(prsd_ctx* ctx, int method, int batch, int l, int m, int nk, const double* k, const double* pk,
+                               int nr, const double* r, double smoothing, double scale, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && k && pk && r && out, "null argument");
+        PRSD_REQUIRE(batch > 0 && nr > 0, "ComputeXiLM: empty request");
+        for (int i = 1; i < nk; i++) PRSD_REQUIRE(k[i] > k[i - 1], "ComputeXiLM: abscissae must increase");
+        DevBuf<double> dk, dpk, dr, dout((size_t)batch*nr);
+        dk.upload(k, nk, ctx->c.stream);
+        dr.upload(r, nr, ctx->c.stream);
+        dpk.upload(pk, (size_t)batch*nk, ctx->c.stream);
+        xilm_discrete_dev(ctx->c, method, batch, l, m, nk, dk.p, dpk.p, nr, dr.p, smoothing, scale, dout.p);
+        dout.download(out, (size_t)batch*nr, ctx->c.stream);
+        ctx->c.sync();
+    });
+}
+
+int prsd_discrete_integrate(prsd_ctx* ctx, int method, int batch, int n, const double* x, const double* y, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && x && y && out, "null argument");
+        PRSD_REQUIRE(batch > 0, "discrete integration: empty request");
+        DevBuf<double> dx, dy, dout((size_t)batch);
+        dx.upload(x, n, ctx->c.stream);
+        dy.upload(y, (size_t)batch*n, ctx->c.stream);
+        discrete_integrate_dev(ctx->c, method, batch, n, dx.p, dy.p, dout.p);
+        dout.download(out, (size_t)batch, ctx->c.stream);
         ctx->c.sync();
     });
 }

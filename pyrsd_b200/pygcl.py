@@ -40,6 +40,10 @@ def _L():
         L.prsd_zeldovich.restype = i
         L.prsd_compute_xilm.argtypes = [_vp, i, i, i, i, _dp, _dp, i, _dp, d, d, _dp]
         L.prsd_compute_xilm.restype = i
+        L.prsd_compute_xilm_discrete.argtypes = [_vp, i, i, i, i, i, _dp, _dp, i, _dp, d, d, _dp]
+        L.prsd_compute_xilm_discrete.restype = i
+        L.prsd_discrete_integrate.argtypes = [_vp, i, i, i, _dp, _dp, _dp]
+        L.prsd_discrete_integrate.restype = i
         L.prsd_compute_xilm_fftlog.argtypes = [_vp, i, i, i, i, _dp, _dp, d, d, _dp, _dp]
         L.prsd_compute_xilm_fftlog.restype = i
         L.prsd_oneloop_tables.argtypes = [_vp, _vp, _vp]
@@ -638,14 +642,38 @@ class ZeldovichCF(PickalableSWIG):
 
 # ------------------------------------------------------------------- correlation functions
 def ComputeXiLM(l, m, k, pk, r, smoothing=0., method=IntegrationMethods.FFTLOG):
-    """xi_l^m(r) = int dk/(2 pi^2) k^m j_l(kr) P(k) (CorrelationFunction.i:16-37, .cpp:56-125)"""
-    if method != IntegrationMethods.FFTLOG:
-        raise NotImplementedError("only the FFTLOG method runs on the device (SIMPS / TRAPZ are next-tier)")
-    k, pk, r = N.as_f64(k), N.as_f64(pk), N.as_f64(r)
-    out = np.empty((1, len(r)))
-    N.check(_L().prsd_compute_xilm(N.default_context().ptr, 1, int(l), int(m), len(k), k, pk.reshape(1, -1), len(r), r,
-                                   float(smoothing), 1.0, out))
-    return out[0]
+    """xi_l^m(r) = int dk/(2 pi^2) k^m j_l(kr) P(k) (CorrelationFunction.i:16-37, .cpp:56-125); ``pk`` may hold a
+    batch of spectra [nbatch][nk] on the shared ``k`` (the SWIG call takes one)"""
+    k, pk, r = N.as_f64(k), np.ascontiguousarray(pk, dtype=np.float64), N.as_f64(r)
+    batch = pk.reshape(-1, len(k))
+    out = np.empty((batch.shape[0], len(r)))
+    if method == IntegrationMethods.FFTLOG:
+        N.check(_L().prsd_compute_xilm(N.default_context().ptr, batch.shape[0], int(l), int(m), len(k), k, batch, len(r), r,
+                                       float(smoothing), 1.0, out))
+    elif method in (IntegrationMethods.SIMPS, IntegrationMethods.TRAPZ):
+        N.check(_L().prsd_compute_xilm_discrete(N.default_context().ptr, int(method), batch.shape[0], int(l), int(m), len(k), k,
+                                                batch, len(r), r, float(smoothing), 1.0, out))
+    else:
+        raise ValueError("the integration method in `ComputeXiLM` must be one of [`fftlog=0`, `simps=1`, `trapz=2`]")
+    return out[0] if pk.ndim == 1 else out
+
+
+def _discrete(method, x, y):
+    x, y = N.as_f64(x), np.ascontiguousarray(y, dtype=np.float64)
+    batch = y.reshape(-1, len(x))
+    out = np.empty(batch.shape[0])
+    N.check(_L().prsd_discrete_integrate(N.default_context().ptr, method, batch.shape[0], len(x), x, batch, out))
+    return float(out[0]) if y.ndim == 1 else out
+
+
+def SimpsIntegrate(x, y):
+    """Simpson's rule on arbitrary abscissae (DiscreteQuad.i; DiscreteQuad.cpp:3-28, 41-66); ``y`` may be [nbatch][n]"""
+    return _discrete(1, x, y)
+
+
+def TrapzIntegrate(x, y):
+    """trapezoid rule (DiscreteQuad.i; DiscreteQuad.cpp:30-39); ``y`` may be [nbatch][n]"""
+    return _discrete(2, x, y)
 
 
 def pk_to_xi(ell, k, pk, r, smoothing=0.5, method=IntegrationMethods.FFTLOG):

@@ -103,8 +103,6 @@ def test_pk_to_xi_and_back(oracle, cosmo):
     ref = oracle.xi_to_pk(0, rr, xi2, np.logspace(-2, 0, 20), 0.005)
     out = pygcl.xi_to_pk(0, rr, xi2, np.logspace(-2, 0, 20), 0.005)
     assert np.max(np.abs(out - ref)) < 1e-9*np.max(np.abs(ref))
-    with pytest.raises(NotImplementedError):
-        pygcl.ComputeXiLM(0, 2, k, P(k), r, 0., pygcl.IntegrationMethods.SIMPS)
 
 
 def test_zeldovich_cf_vs_oracle(oracle, ref_cosmo, cosmo, golden):
@@ -127,3 +125,40 @@ def test_cubic_spline_zero_outside(oracle):
     out = pygcl.CubicSpline(x, y)(xq)
     assert out[0] == 0.0 and out[-1] == 0.0
     assert np.max(np.abs(out - oracle.CubicSpline(x, y, xq))) < 1e-12
+
+
+def test_discrete_quadratures_vs_oracle(oracle):
+    """SimpsIntegrate / TrapzIntegrate and the SIMPS / TRAPZ methods of ComputeXiLM / pk_to_xi / xi_to_pk"""
+    from pyrsd_b200 import pygcl
+    rng = np.random.default_rng(9)
+    for n in (3, 4, 41, 200, 1001):                       # even and odd sample counts (DiscreteQuad.cpp:47-63)
+        x = np.cumsum(rng.uniform(0.5, 1.5, n))
+        y = np.sin(0.3*x) + rng.normal(size=n)
+        assert abs(pygcl.SimpsIntegrate(x, y) - oracle.SimpsIntegrate(x, y)) < 1e-12*np.abs(y).sum()
+        assert abs(pygcl.TrapzIntegrate(x, y) - oracle.TrapzIntegrate(x, y)) < 1e-12*np.abs(y).sum()
+    # batched rows (MultipoleTransfer: every k row over mu, transfers/poles.py:66)
+    mu = np.linspace(0., 1., 41)
+    rows = rng.normal(size=(200, 41))
+    got = pygcl.SimpsIntegrate(mu, rows)
+    assert np.allclose(got, [oracle.SimpsIntegrate(mu, r) for r in rows], rtol=0, atol=1e-13)
+    # xi_l^m by discrete quadrature, every supported l
+    k = np.logspace(-4, 1, 700)
+    pk = 2e4*(k/0.02)/(1 + (k/0.02)**2.6)
+    r = np.logspace(-0.5, 2.2, 40)
+    for method in (pygcl.IntegrationMethods.SIMPS, pygcl.IntegrationMethods.TRAPZ):
+        for l in (0, 1, 2, 3, 4):
+            mine = pygcl.ComputeXiLM(l, 2, k, pk, r, 0.5, method)
+            ref = oracle.ComputeXiLM(l, 2, k, pk, r, 0.5, method)
+            assert np.max(np.abs(mine - ref)) < 1e-11*np.max(np.abs(ref)), (method, l)
+        # the reference's closed forms of j_6, j_8 (SpecialFunctions.cpp:50-66) cancel catastrophically for
+        # 1e-4 < x < ~3 (terms ~1e4..1e6 against a result ~x^l/(2l+1)!!): there BOTH sides return rounding noise,
+        # so parity is only defined where k r >= 3
+        kh, rh = k[k >= 0.1], r[r >= 30.]
+        for l in (6, 8):
+            mine = pygcl.ComputeXiLM(l, 2, kh, pk[k >= 0.1], rh, 0.5, method)
+            ref = oracle.ComputeXiLM(l, 2, kh, pk[k >= 0.1], rh, 0.5, method)
+            assert np.max(np.abs(mine - ref)) < 1e-9*np.max(np.abs(ref)), (method, l)
+        mine = pygcl.pk_to_xi(2, k, pk, r, 0.25, method)
+        assert np.max(np.abs(mine - oracle.pk_to_xi(2, k, pk, r, 0.25, method))) < 1e-11*np.max(np.abs(mine))
+    with pytest.raises(Exception):
+        pygcl.ComputeXiLM(5, 2, k, pk, r, 0.5, pygcl.IntegrationMethods.SIMPS)     # l = 5 unsupported (:104-107)
