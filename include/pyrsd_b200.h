@@ -182,6 +182,17 @@ int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
 int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
                              const double* par, const double* stoch, int npts, const double* d_k,
                              const double* d_mu, double* d_out);
+/* GalaxySpectrum.poles(k, ells, Nmu)  [rsd/power/dm/power_dm.py:1016-1050 -> MultipoleTransfer,
+ * rsd/transfers/poles.py:8-69]: P_ell(k) = (2 ell + 1) int_0^1 dmu L_ell(mu) P(k, mu) by Simpson's rule
+ * (pygcl.SimpsIntegrate) on nmu equally spaced mu in [0, 1] (nmu odd; the reference turns 40 into 41), fused
+ * behind the assembly so that only [nw][nell][nk] numbers leave the device.  k [nk], ells [nell <= 8]. */
+int prsd_galaxy_poles(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
+                      const double* par, const double* stoch, int nk, const double* k, int nell, const int* ells,
+                      int nmu, double* out /*[nw][nell][nk]*/);
+/* d_k and d_out are DEVICE pointers */
+int prsd_galaxy_poles_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
+                             const double* par, const double* stoch, int nk, const double* d_k, int nell,
+                             const int* ells, int nmu, double* d_out);
 /* spline knots of P[mu^0], P[mu^2], P[mu^4], P[mu^6] of the last call: out [nw][10][4][nkm] */
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
 

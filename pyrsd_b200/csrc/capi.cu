@@ -657,6 +657,30 @@ int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
     });
 }
 
+int prsd_galaxy_poles(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
+                      const double* stoch, int nk, const double* k, int nell, const int* ells, int nmu, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && sp && res && par && stoch && k && ells && out, "null argument");
+        PRSD_REQUIRE(nk > 0 && nell > 0, "prsd_galaxy_poles: empty request");
+        Context& c = *g->g.ctx;
+        g->dk.upload(k, nk, c.stream);
+        g->dout.ensure((size_t)nw*nell*nk);
+        g->g.poles(sp->s, res->r, nw, cmap, par, stoch, nk, g->dk.p, nell, ells, nmu, g->dout.p);
+        g->dout.download(out, (size_t)nw*nell*nk, c.stream);
+        c.sync();
+    });
+}
+
+int prsd_galaxy_poles_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
+                             const double* stoch, int nk, const double* d_k, int nell, const int* ells, int nmu, double* d_out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && sp && res && par && stoch && d_k && ells && d_out, "null argument");
+        g->g.poles(sp->s, res->r, nw, cmap, par, stoch, nk, d_k, nell, ells, nmu, d_out);
+    });
+}
+
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
 {
     return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });

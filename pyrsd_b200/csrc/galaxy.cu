@@ -126,13 +126,6 @@ __device__ __forceinline__ double pade_bb(double k, double A0, double R, double 
     return F*A0*(1.0 + k2*R1*R1)/(1.0 + k2*R1h*R1h + r22*r22);
 }
 
-struct GalDev {
-    GalaxyConfig cfg;
-    int nkm, nk, nspl;
-    double lnkm0, inv_dlnkm;        // model grid (log-uniform)
-    double lnki0, inv_dlnki;        // k_interp grid
-    double lnk1l0, inv_dlnk1l;      // one-loop grid
-};
 
 __global__ void k_gal_base(GalDev G, const double* __restrict__ km, const int* __restrict__ cmap,
                            const double* __restrict__ par, const double* __restrict__ ptspl,
@@ -399,16 +392,50 @@ __device__ __forceinline__ double fog(int model, double x)
     return exp(-0.5*x*x);                        // :72-84
 }
 
-__global__ void __launch_bounds__(128)
-k_gal_pkmu(GalDev G, const double* __restrict__ km, const double* __restrict__ par, const double* __restrict__ pairspl,
-           int npts, const double* __restrict__ kk, const double* __restrict__ mm, double* __restrict__ out)
+// The ten sub-spectra enter P_gal only through six distinct FOG products (gal/Pcc, Pcs, Pss coefficient tables,
+// SURVEY Appendix A):  G_c^2 {cAcA, cAcB, cBcB},  G_c G_sA {cAsA, cBsA},  G_c G_sB {cAsB, cBsB},  G_sA^2 {sAsA},
+// G_sA G_sB {sAsB},  G_sB^2 {sBsB}.  Splines are linear in their ordinates, so the weighted sums of the moment
+// splines inside a group are formed once per walker; a (k, mu) point then reads 6 x 3 cubics instead of 10 x 3.
+// Group g keeps [moment][Y | b | c | d][nkm] like pairspl, plus its 1-halo constant in grpconst[w][6].
+static const int GAL_NGRP = 6;
+
+__global__ void k_gal_groups(int nkm, const double* __restrict__ par, const double* __restrict__ pairspl,
+                             double* __restrict__ grpspl, double* __restrict__ grpconst)
 {
-    const int w = blockIdx.y, j = blockIdx.x*blockDim.x + threadIdx.x;
-    if (j >= npts) return;
-    const int nkm = G.nkm;
+    const int w = blockIdx.y;
     const double* p = par + (size_t)w*GAL_NPAR;
+    const double fcB = p[W_FCB], fsB = p[W_FSB];
+    // weight of pair pr inside its group
+    const double wt[GAL_NPAIR] = {(1.0 - fcB)*(1.0 - fcB), 2.0*fcB*(1.0 - fcB), fcB*fcB,
+                                  (1.0 - fcB)*(1.0 - fsB), (1.0 - fcB)*fsB, fcB*(1.0 - fsB), fcB*fsB,
+                                  (1.0 - fsB)*(1.0 - fsB), 2.0*fsB*(1.0 - fsB), fsB*fsB};
+    const int grp[GAL_NPAIR] = {0, 0, 0, 1, 2, 1, 2, 3, 4, 5};
+    const int n = 16*nkm;
+    for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
+        double acc[GAL_NGRP] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int pr = 0; pr < GAL_NPAIR; pr++) acc[grp[pr]] += wt[pr]*pairspl[((size_t)w*GAL_NPAIR + pr)*n + idx];
+#pragma unroll
+        for (int g = 0; g < GAL_NGRP; g++) grpspl[((size_t)w*GAL_NGRP + g)*n + idx] = acc[g];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double* c = grpconst + (size_t)w*GAL_NGRP;
+        c[0] = 0.0;
+        c[1] = wt[5]*p[W_NCBS];          // cBsA
+        c[2] = wt[6]*p[W_NCBS];          // cBsB
+        c[3] = 0.0;
+        c[4] = 0.0;
+        c[5] = wt[9]*p[W_NSBSB];         // sBsB
+    }
+}
+
+// P_gal(k_obs, mu_obs) of walker parameters p from its group splines
+__device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* __restrict__ km, const double* __restrict__ p,
+                                                 const double* __restrict__ gs /*[6][16][nkm]*/, const double* __restrict__ gc,
+                                                 double kobs, double muobs)
+{
+    const int nkm = G.nkm;
     const double apar = p[W_APAR], aperp = p[W_APERP], adrag = p[W_ADRAG];
-    const double kobs = kk[j], muobs = mm[j];
     // rsd/tools.py:54-75
     const double F = apar/aperp;
     double k = kobs/aperp, mu = muobs;
@@ -417,52 +444,98 @@ k_gal_pkmu(GalDev G, const double* __restrict__ km, const double* __restrict__ p
         k = kobs/aperp*fac;
         mu = muobs/F/fac;
     }
-    double res;
-    if (!(k >= km[0] && k <= km[nkm - 1])) {
-        res = nan("");           // the reference raises InterpolationDomainError here (_cache.py:327-339)
-    } else {
-        int i = (int)((log(k) - G.lnkm0)*G.inv_dlnkm);
-        if (i < 0) i = 0;
-        if (i > nkm - 2) i = nkm - 2;
-        while (i > 0 && k < km[i]) --i;
-        while (i < nkm - 2 && k > km[i + 1]) ++i;
-        const double t = k - km[i];
-        const double mu2 = mu*mu;
-        const int nmom = G.cfg.max_mu/2 + 1;
-        const double fs = p[W_FS], fcB = p[W_FCB], fsB = p[W_FSB];
-        const double sig[3] = {p[W_SIGC], p[W_SIGSA], p[W_SIGSB]};
-        const int fm = G.cfg.fog_model;
-        const double kmu = k*mu;
-        const bool so = G.cfg.use_so_correction != 0;
-        const double Gc = so ? 1.0 : fog(fm, kmu*sig[0]);       // SOCorrection sets sigma_c = 0 inside Pcc
-        const double GsA = fog(fm, kmu*sig[1]), GsB = fog(fm, kmu*sig[2]);
-        const double Gc_cs = fog(fm, kmu*sig[0]);
-        auto Phh = [&](int pr) {
-            const double* s = pairspl + ((size_t)w*GAL_NPAIR + pr)*16*nkm + i;
-            double tot = 0.0, mpow = 1.0;
-            for (int m = 0; m < nmom; m++) {
-                const double* q = s + (size_t)m*4*nkm;
-                tot += mpow*(q[0] + t*(q[nkm] + t*(q[2*nkm] + t*q[3*nkm])));
-                mpow *= mu2;
-            }
-            return tot;
-        };
-        // gal/Pcc, Pcs, Pss coefficient tables
-        double Pcc = (1.0 - fcB)*(1.0 - fcB)*Gc*Gc*Phh(0) + 2.0*fcB*(1.0 - fcB)*Gc*Gc*Phh(1) + fcB*fcB*Gc*Gc*Phh(2);
-        if (so) {
-            const double fso = p[W_FSO];
-            const double G1 = Gc_cs, G2 = fog(fm, kmu*p[W_SIGSO]);
-            Pcc = ((G1*(1.0 - fso))*(G1*(1.0 - fso)) + 2.0*fso*(1.0 - fso)*G1*G2 + (G2*fso)*(G2*fso))*Pcc
-                + 2.0*G1*G2*fso*fcB*p[W_NCBS];                    // gal/Pcc/__init__.py:39-60
+    if (!(k >= km[0] && k <= km[nkm - 1])) return nan("");   // the reference raises InterpolationDomainError (_cache.py:327-339)
+    int i = (int)((log(k) - G.lnkm0)*G.inv_dlnkm);
+    if (i < 0) i = 0;
+    if (i > nkm - 2) i = nkm - 2;
+    while (i > 0 && k < km[i]) --i;
+    while (i < nkm - 2 && k > km[i + 1]) ++i;
+    const double t = k - km[i];
+    const double mu2 = mu*mu;
+    const int nmom = G.cfg.max_mu/2 + 1;
+    const double fs = p[W_FS];
+    const int fm = G.cfg.fog_model;
+    const double kmu = k*mu;
+    const bool so = G.cfg.use_so_correction != 0;
+    const double Gc = fog(fm, kmu*p[W_SIGC]), GsA = fog(fm, kmu*p[W_SIGSA]), GsB = fog(fm, kmu*p[W_SIGSB]);
+    auto grp = [&](int g) {
+        const double* s = gs + (size_t)g*16*nkm + i;
+        double tot = gc[g], mpow = 1.0;
+        for (int m = 0; m < nmom; m++) {
+            const double* q = s + (size_t)m*4*nkm;
+            tot += mpow*(q[0] + t*(q[nkm] + t*(q[2*nkm] + t*q[3*nkm])));
+            mpow *= mu2;
         }
-        const double Pcs = (1.0 - fcB)*(1.0 - fsB)*Gc_cs*GsA*Phh(3) + (1.0 - fcB)*fsB*Gc_cs*GsB*Phh(4)
-                         + fcB*(1.0 - fsB)*Gc_cs*GsA*(Phh(5) + p[W_NCBS]) + fcB*fsB*Gc_cs*GsB*(Phh(6) + p[W_NCBS]);
-        const double Pss = (1.0 - fsB)*(1.0 - fsB)*GsA*GsA*Phh(7) + 2.0*fsB*(1.0 - fsB)*GsA*GsB*Phh(8)
-                         + fsB*fsB*GsB*GsB*(Phh(9) + p[W_NSBSB]);
-        res = (1.0 - fs)*(1.0 - fs)*Pcc + 2.0*fs*(1.0 - fs)*Pcs + fs*fs*Pss;
-        res = res/(aperp*aperp*apar)*adrag*adrag*adrag;          // rsd/tools.py:211-214
+        return tot;
+    };
+    double Pcc;
+    if (so) {
+        // SOCorrection sets sigma_c = 0 inside Pcc and re-damps the group (gal/Pcc/__init__.py:39-60)
+        const double fso = p[W_FSO], fcB = p[W_FCB];
+        const double G1 = Gc, G2 = fog(fm, kmu*p[W_SIGSO]);
+        Pcc = ((G1*(1.0 - fso))*(G1*(1.0 - fso)) + 2.0*fso*(1.0 - fso)*G1*G2 + (G2*fso)*(G2*fso))*grp(0)
+            + 2.0*G1*G2*fso*fcB*p[W_NCBS];
+    } else {
+        Pcc = Gc*Gc*grp(0);
     }
-    out[(size_t)w*npts + j] = res;
+    const double Pcs = Gc*GsA*grp(1) + Gc*GsB*grp(2);
+    const double Pss = GsA*GsA*grp(3) + GsA*GsB*grp(4) + GsB*GsB*grp(5);
+    const double res = (1.0 - fs)*(1.0 - fs)*Pcc + 2.0*fs*(1.0 - fs)*Pcs + fs*fs*Pss;
+    return res/(aperp*aperp*apar)*adrag*adrag*adrag;          // rsd/tools.py:211-214
+}
+
+__global__ void __launch_bounds__(128)
+k_gal_pkmu(GalDev G, const double* __restrict__ km, const double* __restrict__ par, const double* __restrict__ grpspl,
+           const double* __restrict__ grpconst, int npts, const double* __restrict__ kk, const double* __restrict__ mm,
+           double* __restrict__ out)
+{
+    const int w = blockIdx.y, j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    out[(size_t)w*npts + j] = gal_pkmu_point(G, km, par + (size_t)w*GAL_NPAR, grpspl + (size_t)w*GAL_NGRP*16*G.nkm,
+                                             grpconst + (size_t)w*GAL_NGRP, kk[j], mm[j]);
+}
+
+// P_ell(k) = (2 ell + 1) \int_0^1 dmu L_ell(mu) P(k, mu) with Simpson's rule on nmu (odd) equally spaced mu:
+// MultipoleTransfer (rsd/transfers/poles.py:8-69; SimpsIntegrate of DiscreteQuad.cpp:41-66 on a uniform grid).
+// One thread per (walker, k); out [walker][ell index][k].
+__device__ __forceinline__ double legendre_even(int ell, double x)
+{
+    const double x2 = x*x;
+    switch (ell) {
+        case 0: return 1.0;
+        case 2: return 0.5*(3.0*x2 - 1.0);
+        case 4: return 0.125*((35.0*x2 - 30.0)*x2 + 3.0);
+        case 6: return 0.0625*(((231.0*x2 - 315.0)*x2 + 105.0)*x2 - 5.0);
+        default: {      // generic recurrence (odd ell or ell > 6)
+            double p0 = 1.0, p1 = x;
+            if (ell == 1) return x;
+            for (int n = 2; n <= ell; n++) { const double pn = ((2.0*n - 1.0)*x*p1 - (n - 1.0)*p0)/n; p0 = p1; p1 = pn; }
+            return p1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_gal_poles(GalDev G, const double* __restrict__ km, const double* __restrict__ par, const double* __restrict__ grpspl,
+            const double* __restrict__ grpconst, int nk, const double* __restrict__ kk, int nell, const int* __restrict__ ells,
+            int nmu, double* __restrict__ out)
+{
+    const int w = blockIdx.y, j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= nk) return;
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double* gs = grpspl + (size_t)w*GAL_NGRP*16*G.nkm;
+    const double* gc = grpconst + (size_t)w*GAL_NGRP;
+    const double k = kk[j];
+    const double h = 1.0/(nmu - 1);
+    double acc[8];
+    for (int e = 0; e < nell; e++) acc[e] = 0.0;
+    for (int m = 0; m < nmu; m++) {
+        const double mu = (m == nmu - 1) ? 1.0 : m*h;
+        const double sw = (m == 0 || m == nmu - 1) ? 1.0 : ((m & 1) ? 4.0 : 2.0);       // Simpson weights x 3/h
+        const double P = gal_pkmu_point(G, km, p, gs, gc, k, mu);
+        for (int e = 0; e < nell; e++) acc[e] += sw*legendre_even(ells[e], mu)*P;
+    }
+    for (int e = 0; e < nell; e++) out[((size_t)w*nell + e)*nk + j] = (2.0*ells[e] + 1.0)*acc[e]*h*(1.0/3.0);
 }
 
 __global__ void k_plin_model(int nspl, const PlinParams* __restrict__ params, const double* __restrict__ spl,
@@ -514,7 +587,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
 {
     Context& c = *ctx;
     cudaStream_t s = c.stream;
-    PRSD_REQUIRE(nw > 0 && npts > 0, "GalaxyModel::power: empty request");
+    PRSD_REQUIRE(nw > 0 && npts >= 0, "GalaxyModel::power: empty request");
     PRSD_REQUIRE(pt.nk == nk_interp, "GalaxyModel::power: PT tables are on %d k, model expects %d", pt.nk, nk_interp);
     PRSD_REQUIRE(sp.have_oneloop, "GalaxyModel::power: the PT stage has not been run for this batch");
     const int nc = sp.ncosmo;
@@ -591,7 +664,35 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         PRSD_CUDA(cudaGetLastError());
         c.launches++;
     }
-    k_gal_pkmu<<<dim3((npts + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_par.p, pairspl.p, npts, d_k, d_mu, d_out);
+    grpspl.ensure((size_t)nw*GAL_NGRP*16*nkm);
+    grpconst.ensure((size_t)nw*GAL_NGRP);
+    k_gal_groups<<<dim3((16*nkm + 255)/256, nw), 256, 0, s>>>(nkm, d_par.p, pairspl.p, grpspl.p, grpconst.p);
+    PRSD_CUDA(cudaGetLastError());
+    c.launches++;
+    last_G = G;
+    last_nw = nw;
+    if (npts > 0) {
+        k_gal_pkmu<<<dim3((npts + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_par.p, grpspl.p, grpconst.p, npts, d_k, d_mu, d_out);
+        PRSD_CUDA(cudaGetLastError());
+        c.launches++;
+    }
+    c.sync();
+}
+
+void GalaxyModel::poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
+                        int nk, const double* d_k, int nell, const int* ells, int nmu, double* d_out)
+{
+    PRSD_REQUIRE(nk > 0 && nell > 0 && nell <= 8, "GalaxyModel::poles: need 1..8 multipoles and a non-empty k list");
+    PRSD_REQUIRE(nmu >= 3 && (nmu & 1), "GalaxyModel::poles: Simpson's rule needs an odd number (>= 3) of mu samples");
+    for (int e = 0; e < nell; e++) PRSD_REQUIRE(ells[e] >= 0 && ells[e] <= 16, "multipole %d unsupported", ells[e]);
+    // every table, moment spline and group spline of the walkers (no (k, mu) evaluation)
+    power(sp, pt, nw, cmap, par, stoch, 0, nullptr, nullptr, nullptr);
+    Context& c = *ctx;
+    DevBuf<int> d_ells;
+    d_ells.upload(ells, nell, c.stream);
+    ProfScope prof_gal(c, PROF_GALAXY);
+    k_gal_poles<<<dim3((nk + 127)/128, nw), 128, 0, c.stream>>>(last_G, d_km.p, d_par.p, grpspl.p, grpconst.p, nk, d_k, nell,
+                                                                d_ells.p, nmu, d_out);
     PRSD_CUDA(cudaGetLastError());
     c.launches++;
     c.sync();

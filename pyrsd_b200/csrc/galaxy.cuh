@@ -33,6 +33,15 @@ struct GalaxyConfig {
 };
 void galaxy_config_default(GalaxyConfig& c);
 
+// launch-time constants of the assembly kernels
+struct GalDev {
+    GalaxyConfig cfg;
+    int nkm, nk, nspl;
+    double lnkm0, inv_dlnkm;        // model grid (log-uniform)
+    double lnki0, inv_dlnki;        // k_interp grid
+    double lnk1l0, inv_dlnk1l;      // one-loop grid
+};
+
 struct GalaxyModel {
     Context* ctx;
     GalaxyConfig cfg;
@@ -44,8 +53,10 @@ struct GalaxyModel {
     DevBuf<double> d_kinterp, d_nakfac;   // k_interp and the Thomas factors of its not-a-knot spline matrix
     DevBuf<double> d_nakfac_m;            // the same factors for the model grid
     // scratch
-    DevBuf<double> ptspl, zel1, zel2, plin_m, ratio1, ratio2, base, pairspl, d_par, d_stoch, ol_m;
+    DevBuf<double> ptspl, zel1, zel2, plin_m, ratio1, ratio2, base, pairspl, grpspl, grpconst, d_par, d_stoch, ol_m;
     DevBuf<int> d_cmap;
+    GalDev last_G;                      // constants of the last power() call (reused by poles())
+    int last_nw = 0;
 
     GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmodel, int nkm_, const double* k_interp, int nk_interp_);
 
@@ -54,6 +65,10 @@ struct GalaxyModel {
     //   k, mu  host [npts] (paired)     out    DEVICE [nw][npts]
     void power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
                int npts, const double* d_k, const double* d_mu, double* d_out);
+    // multipoles P_ell(k) of `nw` walkers by Simpson's rule over nmu (odd) mu in [0, 1] -- MultipoleTransfer of
+    // rsd/transfers/poles.py:8-69 fused behind the assembly: d_k DEVICE [nk], ells host [nell], d_out DEVICE [nw][nell][nk]
+    void poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
+               int nk, const double* d_k, int nell, const int* ells, int nmu, double* d_out);
     // diagnostic: the spline knots of P[mu^0,2,4,6] per (walker, pair): host [nw][10][4][nkm]
     void moments_to_host(int nw, double* out);
 };

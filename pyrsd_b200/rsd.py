@@ -42,8 +42,10 @@ def _L():
         L.prsd_galaxy_power.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, _dp, _dp]
         L.prsd_galaxy_power_device.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _vp, _vp, _vp]
         L.prsd_galaxy_moments.argtypes = [_vp, i, _dp]
+        L.prsd_galaxy_poles.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, i, _ip, i, _dp]
+        L.prsd_galaxy_poles_device.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _vp, i, _ip, i, _vp]
         for name in ('prsd_galaxy_config_default', 'prsd_galaxy_create', 'prsd_galaxy_destroy', 'prsd_galaxy_power',
-                     'prsd_galaxy_power_device', 'prsd_galaxy_moments'):
+                     'prsd_galaxy_power_device', 'prsd_galaxy_moments', 'prsd_galaxy_poles', 'prsd_galaxy_poles_device'):
             getattr(L, name).restype = i
         L._rsd_sigs = True
     return L
@@ -153,6 +155,21 @@ class PTEngine(object):
             cm = np.ascontiguousarray(cmap, dtype=np.int32)
         N.check(_L().prsd_galaxy_power(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
                                        par, stoch, len(k), k, mu, out))
+        return out
+
+    def galaxy_poles(self, gal, spectra, result, par, stoch, k, ells, Nmu=40, cmap=None):
+        """P_ell(k) of nw walkers -> [nw][nell][nk]; Simpson over Nmu (made odd as MultipoleTransfer does) mu in [0, 1]"""
+        par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, NPAR)
+        nw = par.shape[0]
+        stoch = np.ascontiguousarray(stoch, dtype=np.float64).reshape(nw, NPAIR, NSTOCH)
+        k = N.as_f64(k)
+        ells = np.ascontiguousarray(np.atleast_1d(ells), dtype=np.int32)
+        if Nmu % 2 == 0:
+            Nmu += 1                      # poles.py:29
+        out = np.empty((nw, len(ells), len(k)))
+        cm = None if cmap is None else np.ascontiguousarray(cmap, dtype=np.int32)
+        N.check(_L().prsd_galaxy_poles(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
+                                       par, stoch, len(k), k, len(ells), ells, int(Nmu), out))
         return out
 
     def galaxy_moments(self, gal, nw):
@@ -384,6 +401,22 @@ class GalaxySpectrum(object):
                              "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
         P = np.squeeze(P.reshape(kb.shape))
         return np.ravel(P, order='F') if flatten else P
+
+
+def _poles(self, k, ells, Nmu=40):
+    """``GalaxySpectrum.poles(k, ells, Nmu=40)`` (power_dm.py:1016-1050): list of P_ell(k), one array per ell"""
+    eng = self._ensure_tables()
+    scalar = np.isscalar(ells)
+    kmodel = self.k
+    gal = eng.galaxy(kmodel, self._config())
+    P = eng.galaxy_poles(gal, self._spectra, self._result, self._walker(), self._stoch(kmodel), k, ells, Nmu)[0]
+    if np.isnan(P).any():
+        raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
+                         "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+    return P[0] if scalar else [P[i] for i in range(P.shape[0])]
+
+
+GalaxySpectrum.poles = _poles
 
 
 def _new_result():

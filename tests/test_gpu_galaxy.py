@@ -121,3 +121,26 @@ def test_walker_batch_matches_single_evaluations(cosmo, engine):
     out = engine.galaxy_power(gal, model._spectra, model._result, np.array(pars), np.array(stochs), kk, mm,
                               cmap=np.zeros(5, dtype=np.int32))
     assert np.array_equal(out, np.array(singles))
+
+
+def test_poles_match_simpson_of_the_power_grid(cosmo, engine, oracle):
+    """GalaxySpectrum.poles == MultipoleTransfer(k, ells, Nmu)(power(k, mu)) (rsd/transfers/poles.py:8-69): the fused
+    device kernel against the reference's SimpsIntegrate applied to this library's own P(k, mu) grid"""
+    from pyrsd_b200 import rsd
+    from scipy.special import legendre
+    model = rsd.GalaxySpectrum(params=cosmo, z=0.55, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine)
+    model.update(alpha_par=1.02, alpha_perp=0.985, f=0.78)
+    k = np.logspace(-2, np.log10(0.4), 30)
+    for Nmu in (40, 41, 11):
+        n = Nmu + 1 if Nmu % 2 == 0 else Nmu
+        mu = np.linspace(0., 1., n)
+        P = model.power(k, mu)
+        poles = model.poles(k, [0, 2, 4], Nmu=Nmu)
+        assert len(poles) == 3
+        for ell, got in zip((0, 2, 4), poles):
+            kern = (2*ell + 1.)*legendre(ell)(mu)
+            ref = np.array([oracle.SimpsIntegrate(mu, kern*row) for row in P])
+            assert np.max(np.abs(got - ref)) < 1e-12*np.max(np.abs(P)), (Nmu, ell)
+    assert np.array_equal(model.poles(k, 2, Nmu=11), poles[1])           # scalar ell -> one array
+    with pytest.raises(Exception):
+        model.poles(np.array([5.0]), [0])           # AP-distorted k outside the model's spline domain
