@@ -1,5 +1,6 @@
 // galaxy.cu -- GalaxySpectrum P(k, mu) assembly (see galaxy.cuh).
 #include "galaxy.cuh"
+#include "pcr.cuh"
 
 #include <cmath>
 
@@ -41,45 +42,32 @@ enum {
 
 // --------------------------------------------------------------- spline builds
 // Not-a-knot splines of every PT table of every cosmology on the SHARED abscissae k_interp in one launch.
-// The tridiagonal matrix depends only on the abscissae, so its Thomas factors (nak_factor) are computed once
-// per model; a row then costs a right-hand side, two substitution sweeps without divisions, and the
-// coefficient formulas of nak_spline_build (pt_math.cuh).
+// The tridiagonal systems are solved by parallel cyclic reduction (pcr.cuh); the coefficient formulas are those of
+// nak_spline_build (pt_math.cuh).
 struct NakSrc { const double* p[5]; int rows[5]; int off[5]; };
 
-static void nak_factor(int n, const double* X, std::vector<double>& fac /*[3][n]: w, 1/den, sub-diagonal*/)
+// not-a-knot system of nak_spline_build (pt_math.cuh) for the interior second derivatives M_1 .. M_{n-2}, written
+// into the PCR arrays at offset `off` (unknown j = i - 1); x, y in shared memory
+__device__ __forceinline__ void nak_system_row(int n, const double* x, const double* y, int i,
+                                               double* a, double* b, double* c, double* r, int off)
 {
-    fac.assign((size_t)3*n, 0.0);
-    double* w = fac.data(); double* iden = w + n; double* sub = iden + n;
     const int m = n - 2;
-    std::vector<double> b(n), c(n);
-    for (int i = 1; i <= m; i++) {
-        const double h0 = X[i] - X[i - 1], h1 = X[i + 1] - X[i];
-        b[i] = 2.0*(h0 + h1); c[i] = h1; sub[i] = h0;
-    }
-    {
-        const double h0 = X[1] - X[0], h1 = X[2] - X[1];
-        b[1] += h0*(1.0 + h0/h1);
-        c[1] -= h0*h0/h1;
-        const double hn = X[n - 1] - X[n - 2], hm = X[n - 2] - X[n - 3];
-        b[m] += hn*(1.0 + hn/hm);
-        sub[m] -= hn*hn/hm;
-    }
-    w[1] = c[1]/b[1];
-    iden[1] = 1.0/b[1];
-    for (int i = 2; i <= m; i++) {
-        const double den = b[i] - sub[i]*w[i - 1];
-        w[i] = c[i]/den;
-        iden[i] = 1.0/den;
-    }
+    const double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
+    double bb = 2.0*(h0 + h1), cc = h1, aa = h0;
+    if (i == 1) { bb += h0*(1.0 + h0/h1); cc -= h0*h0/h1; }
+    if (i == m) { bb += h1*(1.0 + h1/h0); aa -= h1*h1/h0; }
+    a[off + i - 1] = aa; b[off + i - 1] = bb; c[off + i - 1] = cc;
+    r[off + i - 1] = 6.0*((y[i + 1] - y[i])/h1 - (y[i] - y[i - 1])/h0);
 }
 
-__global__ void __launch_bounds__(64)
-k_nak_rows(int nk, const double* __restrict__ X, const double* __restrict__ fac, NakSrc S, double* __restrict__ dst)
+__global__ void __launch_bounds__(128)
+k_nak_rows(int nk, const double* __restrict__ X, NakSrc S, double* __restrict__ dst)
 {
     extern __shared__ double sm_nak[];
     double* x = sm_nak;
     double* y = x + nk;
-    double* M = y + nk;
+    double* M = y + nk;                  // [nk] second derivatives
+    double* w = M + nk;                  // 8 (nk - 2) reduction arrays
     const int row = blockIdx.x, cc = blockIdx.y, tid = threadIdx.x;
     int g = 0;
 #pragma unroll
@@ -88,17 +76,10 @@ k_nak_rows(int nk, const double* __restrict__ X, const double* __restrict__ fac,
     for (int i = tid; i < nk; i += blockDim.x) { x[i] = X[i]; y[i] = s[i]; }
     __syncthreads();
     const int m = nk - 2;
-    for (int i = 1 + tid; i <= m; i += blockDim.x) {
-        const double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
-        M[i] = 6.0*((y[i + 1] - y[i])/h1 - (y[i] - y[i - 1])/h0);
-    }
+    for (int i = 1 + tid; i <= m; i += blockDim.x) nak_system_row(nk, x, y, i, w, w + m, w + 2*m, w + 3*m, 0);
     __syncthreads();
+    pcr_solve(1, m, w, w + m, w + 2*m, w + 3*m, w + 4*m, w + 5*m, w + 6*m, w + 7*m, M + 1);
     if (tid == 0) {
-        const double* w = fac; const double* iden = fac + nk; const double* sub = fac + 2*nk;
-        double prev = M[1]*iden[1];
-        M[1] = prev;
-        for (int i = 2; i <= m; i++) { prev = (M[i] - sub[i]*prev)*iden[i]; M[i] = prev; }
-        for (int i = m - 1; i >= 1; i--) { prev = M[i] - w[i]*prev; M[i] = prev; }
         const double h0 = x[1] - x[0], h1 = x[2] - x[1];
         M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
         const double hn = x[nk - 1] - x[nk - 2], hm = x[nk - 2] - x[nk - 3];
@@ -251,14 +232,14 @@ __constant__ int c_pair_b[GAL_NPAIR] = {0, 1, 1, 2, 3, 2, 3, 2, 3, 3};
 __global__ void __launch_bounds__(128)
 k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict__ kst, const int* __restrict__ cmap,
               const double* __restrict__ par, const double* __restrict__ stoch, const double* __restrict__ scal,
-              const double* __restrict__ base, const double* __restrict__ nakfac, double* __restrict__ pairspl)
+              const double* __restrict__ base, double* __restrict__ pairspl)
 {
     extern __shared__ double sm_gm[];
     const int nkm = G.nkm;
     double* X = sm_gm;                       // [nkm]
     double* Y = X + nkm;                     // [4][nkm]
-    double* W = Y + 4*nkm;                   // [4][nkm] second derivatives of the moment splines
-    double* S = W + 4*nkm;                   // stochasticity spline: x y b c d M w  [7][20]
+    double* W = Y + 4*nkm;                   // [4][nkm] second derivatives + 36 x 4 (nkm - 2) PCR work
+    double* S = W + 40*nkm;                  // stochasticity spline: x y b c d M w  [7][20]
     const int pr = blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
     const int c = cmap[w];
     const double* p = par + (size_t)w*GAL_NPAR;
@@ -341,27 +322,25 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
         Y[i] = mu0; Y[nkm + i] = mu2; Y[2*nkm + i] = mu4; Y[3*nkm + i] = mu6;
     }
     __syncthreads();
-    // not-a-knot splines of the four moments on the model grid (the reference's RSDSpline on self.k): right-hand
-    // sides by the whole CTA, the two substitution sweeps with the precomputed Thomas factors of the grid
-    // (nak_factor) by one thread per moment, coefficients by the whole CTA
+    // not-a-knot splines of the four moments on the model grid (the reference's RSDSpline on self.k): the four
+    // tridiagonal systems are solved together by parallel cyclic reduction (pcr.cuh)
     double* Mm = W;                          // [4][nkm] second derivatives
+    double* pw = W + 4*nkm;                  // 8 x 4 (nkm - 2) reduction arrays + 4 (nkm - 2) solutions
     const int m_in = nkm - 2;
-    for (int idx = tid; idx < 4*nkm; idx += blockDim.x) {
-        const int m = idx/nkm, i = idx - m*nkm;
-        if (i >= 1 && i <= m_in) {
-            const double h0 = X[i] - X[i - 1], h1 = X[i + 1] - X[i];
-            const double* y = Y + m*nkm;
-            Mm[idx] = 6.0*((y[i + 1] - y[i])/h1 - (y[i] - y[i - 1])/h0);
-        }
+    for (int idx = tid; idx < 4*m_in; idx += blockDim.x) {
+        const int m = idx/m_in, i = 1 + idx - m*m_in;
+        nak_system_row(nkm, X, Y + m*nkm, i, pw, pw + 4*m_in, pw + 8*m_in, pw + 12*m_in, m*m_in);
+    }
+    __syncthreads();
+    double* sol = pw + 32*m_in;
+    pcr_solve(4, m_in, pw, pw + 4*m_in, pw + 8*m_in, pw + 12*m_in, pw + 16*m_in, pw + 20*m_in, pw + 24*m_in, pw + 28*m_in, sol);
+    for (int idx = tid; idx < 4*m_in; idx += blockDim.x) {
+        const int m = idx/m_in, i = 1 + idx - m*m_in;
+        Mm[m*nkm + i] = sol[idx];
     }
     __syncthreads();
     if (tid < 4) {
         double* M = Mm + tid*nkm;
-        const double* w = nakfac; const double* iden = nakfac + nkm; const double* sub = nakfac + 2*nkm;
-        double prev = M[1]*iden[1];
-        M[1] = prev;
-        for (int i = 2; i <= m_in; i++) { prev = (M[i] - sub[i]*prev)*iden[i]; M[i] = prev; }
-        for (int i = m_in - 1; i >= 1; i--) { prev = M[i] - w[i]*prev; M[i] = prev; }
         const double h0 = X[1] - X[0], h1 = X[2] - X[1];
         M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
         const double hn = X[nkm - 1] - X[nkm - 2], hm = X[nkm - 2] - X[nkm - 3];
@@ -560,7 +539,7 @@ __global__ void k_scale_rows(int n, const double* __restrict__ in, const double*
 GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmodel, int nkm_, const double* k_interp, int nki)
     : ctx(&c), cfg(cfg_), nkm(nkm_), nk_interp(nki)
 {
-    PRSD_REQUIRE(nkm >= 4 && nkm <= 1024, "GalaxyModel: model grid size %d outside [4, 1024]", nkm);
+    PRSD_REQUIRE(nkm >= 4 && nkm <= 512, "GalaxyModel: model grid size %d outside [4, 512]", nkm);
     PRSD_REQUIRE(cfg.max_mu == 0 || cfg.max_mu == 2 || cfg.max_mu == 4 || cfg.max_mu == 6, "`max_mu` must be one of [0, 2, 4, 6]");
     PRSD_REQUIRE(cfg.fog_model >= 0 && cfg.fog_model <= 2, "unknown FOG model %d", cfg.fog_model);
     km.assign(kmodel, kmodel + nkm);
@@ -573,11 +552,6 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     d_kstoch.upload(ks, c.stream);
     d_kinterp.upload(k_interp, nki, c.stream);
     PRSD_REQUIRE(nki >= 4, "GalaxyModel: the PT interpolation grid needs at least 4 points");
-    std::vector<double> fac;
-    nak_factor(nki, k_interp, fac);
-    d_nakfac.upload(fac, c.stream);
-    nak_factor(nkm, km.data(), fac);
-    d_nakfac_m.upload(fac, c.stream);
     zel.build(c, km.data(), nkm);
     c.sync();
 }
@@ -614,10 +588,10 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     ptspl.ensure((size_t)nc*PT_NROWS*5*nk);
     {
         ProfScope prof(c, PROF_SPLINE);
-        const size_t smem = (size_t)3*nk*sizeof(double);
+        const size_t smem = (size_t)11*nk*sizeof(double);
         if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_nak_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NakSrc S = {{pt.I.p, pt.J.p, pt.K.p, pt.ML.p, pt.sigmasq_k.p}, {16, 6, 13, 21, 1}, {PT_I, PT_J, PT_K, PT_ML, PT_SIGK}};
-        k_nak_rows<<<dim3(PT_NROWS, nc), 64, smem, s>>>(nk, d_kinterp.p, d_nakfac.p, S, ptspl.p);
+        k_nak_rows<<<dim3(PT_NROWS, nc), 128, smem, s>>>(nk, d_kinterp.p, S, ptspl.p);
         c.launches++;
         PRSD_CUDA(cudaGetLastError());
     }
@@ -657,10 +631,10 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     c.launches++;
     pairspl.ensure((size_t)nw*GAL_NPAIR*16*nkm);
     {
-        const size_t smem = (size_t)(9*nkm + 7*GAL_NSTOCH)*sizeof(double);
+        const size_t smem = (size_t)(45*nkm + 7*GAL_NSTOCH)*sizeof(double);
         if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_gal_moments<<<dim3(GAL_NPAIR, nw), 128, smem, s>>>(G, d_km.p, d_kstoch.p, d_cmap.p, d_par.p, d_stoch.p, pt.scalars.p,
-                                                             base.p, d_nakfac_m.p, pairspl.p);
+                                                             base.p, pairspl.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches++;
     }

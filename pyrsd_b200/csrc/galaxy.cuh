@@ -50,8 +50,7 @@ struct GalaxyModel {
     DevBuf<double> d_km, d_kstoch;
     ZelPlan zel;                        // Zel'dovich stencils for the model grid
     int nk_interp = 0;
-    DevBuf<double> d_kinterp, d_nakfac;   // k_interp and the Thomas factors of its not-a-knot spline matrix
-    DevBuf<double> d_nakfac_m;            // the same factors for the model grid
+    DevBuf<double> d_kinterp;
     // scratch
     DevBuf<double> ptspl, zel1, zel2, plin_m, ratio1, ratio2, base, pairspl, grpspl, grpconst, d_par, d_stoch, ol_m;
     DevBuf<int> d_cmap;

@@ -3,6 +3,8 @@
 #include "pt_math.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace prsd {
 
 static const int NL_THREADS = 256;
@@ -223,7 +225,10 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     const size_t smem = (size_t)(NL_SLOTS*TAB_MPAD + NL_SLOTS*geo.max_outer + (NL_WARPS + 1)*Spec::NACC + 2)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_nodal_apply<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ntiles, (geo.nk + kchunk - 1)/kchunk);
+    // k chunks: few enough to amortise the table staging, enough CTAs to fill 148 SMs x 2 when the batch is small
+    int nchunks = (geo.nk + kchunk - 1)/kchunk;
+    nchunks = std::min(geo.nk, std::max(nchunks, (2400 + ntiles - 1)/ntiles));
+    dim3 grid(ntiles, nchunks);
     ProfScope prof(ctx, prof_tag);
     k_nodal_apply<Spec><<<grid, NL_THREADS, smem, ctx.stream>>>(a);
     PRSD_CUDA(cudaGetLastError());

@@ -1,5 +1,6 @@
 // spectra.cu -- device-resident spectra tables (see spectra.cuh).
 #include "spectra.cuh"
+#include "pcr.cuh"
 
 #include <cmath>
 #include <mutex>
@@ -113,6 +114,67 @@ __global__ void k_spline_build(int n, const double* __restrict__ X, int x_stride
     }
 }
 
+// The same spline with the tridiagonal system solved by parallel cyclic reduction (pcr.cuh): no serial sweep at all.
+// Shared memory: x, y, h, sigma and the eight reduction arrays, 12 n doubles (n <= 2048).
+__global__ void __launch_bounds__(256)
+k_spline_build_pcr(int n, const double* __restrict__ X, int x_stride, const double* __restrict__ Y, double* __restrict__ out)
+{
+    extern __shared__ double sm[];
+    double* x = sm;
+    double* y = sm + n;
+    double* h = sm + 2*n;
+    double* sig = sm + 3*n;
+    double* w = sm + 4*n;                 // a b c r | a2 b2 c2 r2
+    const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const double* Xs = X + (size_t)s*x_stride;
+    const double* Ys = Y + (size_t)s*n;
+    for (int i = tid; i < n; i += nt) { x[i] = Xs[i]; y[i] = Ys[i]; }
+    __syncthreads();
+    for (int i = tid; i < n - 1; i += nt) h[i] = x[i + 1] - x[i];
+    __syncthreads();
+    double* a = w; double* b = w + n; double* c = w + 2*n; double* r = w + 3*n;
+    for (int i = tid; i < n; i += nt) {
+        if (i >= 1 && i <= n - 2) {
+            a[i] = h[i - 1];
+            b[i] = 2.0*(h[i - 1] + h[i]);
+            c[i] = h[i];
+            r[i] = (y[i + 1] - y[i])/h[i] - (y[i] - y[i - 1])/h[i - 1];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // end conditions of netlib spline.f (Spline.cpp:229-242): third derivatives from the cubics through
+        // the first / last four points
+        double r0 = 0.0, rn = 0.0;
+        if (n > 3) {
+            r0 = r[2]/(x[3] - x[1]) - r[1]/(x[2] - x[0]);
+            rn = r[n - 2]/(x[n - 1] - x[n - 3]) - r[n - 3]/(x[n - 2] - x[n - 4]);
+            r0 = r0*h[0]*h[0]/(x[3] - x[0]);
+            rn = -rn*h[n - 2]*h[n - 2]/(x[n - 1] - x[n - 4]);
+        }
+        a[0] = 0.0;       b[0] = -h[0];           c[0] = h[0];      r[0] = r0;
+        a[n - 1] = h[n - 2]; b[n - 1] = -h[n - 2]; c[n - 1] = 0.0;  r[n - 1] = rn;
+    }
+    __syncthreads();
+    pcr_solve(1, n, a, b, c, r, w + 4*n, w + 5*n, w + 6*n, w + 7*n, sig);
+    double* o = out + (size_t)s*5*n;
+    for (int i = tid; i < n; i += nt) {
+        double bi, di;
+        if (i < n - 1) {
+            bi = (y[i + 1] - y[i])/h[i] - h[i]*(sig[i + 1] + 2.0*sig[i]);
+            di = (sig[i + 1] - sig[i])/h[i];
+        } else {
+            bi = (y[n - 1] - y[n - 2])/h[n - 2] + h[n - 2]*(sig[n - 2] + 2.0*sig[n - 1]);
+            di = (sig[n - 1] - sig[n - 2])/h[n - 2];
+        }
+        o[i] = x[i];
+        o[n + i] = y[i];
+        o[2*n + i] = bi;
+        o[3*n + i] = 3.0*sig[i];
+        o[4*n + i] = di;
+    }
+}
+
 void spline_factor(Context& ctx, int nfac, int n, const double* dX, int x_stride, double* d_invb)
 {
     k_spline_factor<<<nfac, 32, 0, ctx.stream>>>(n, dX, x_stride, d_invb);
@@ -124,6 +186,17 @@ void spline_build_batched(Context& ctx, int nspline, int n, const double* dX, in
                           const double* dY, double* dspl, const double* d_invb)
 {
     PRSD_REQUIRE(n >= 4 && n <= 4096, "spline_build_batched: n = %d out of range [4, 4096]", n);
+    if (n <= 2048) {
+        const size_t smem_pcr = (size_t)12*n*sizeof(double);
+        if (smem_pcr > 48*1024)
+            PRSD_CUDA(cudaFuncSetAttribute(k_spline_build_pcr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcr));
+        ProfScope prof(ctx, PROF_SPLINE);
+        k_spline_build_pcr<<<nspline, 256, smem_pcr, ctx.stream>>>(n, dX, x_stride, dY, dspl);
+        PRSD_CUDA(cudaGetLastError());
+        ctx.launches++;
+        return;
+    }
+    // longer splines: serial sweeps with factored abscissae
     const size_t smem = (size_t)5*n*sizeof(double);
     if (smem > 48*1024)
         PRSD_CUDA(cudaFuncSetAttribute(k_spline_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
