@@ -9,12 +9,14 @@ namespace prsd {
 
 size_t NodeGeometry::bytes() const
 {
-    return n_nodes*(sizeof(int)*2 + sizeof(double)*6) + n_outer*(sizeof(int)*2 + sizeof(double)*5);
+    return n_nodes*(sizeof(int)*3 + sizeof(double)*6) + n_outer*(sizeof(int)*2 + sizeof(double)*5);
 }
 
 std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
-                                            const QuadConfig& cfg, const KnotGrid& grid)
+                                            const QuadConfig& cfg, const KnotGrid& grid, int bank_mod)
 {
+    PRSD_REQUIRE(bank_mod == 16 || bank_mod == 32, "make_geometry: bank_mod must be 16 or 32");
+    const int BM = bank_mod;
     PRSD_REQUIRE(nk > 0, "make_geometry: empty k list");
     for (int i = 0; i < nk; i++) PRSD_REQUIRE(k[i] > 0 && std::isfinite(k[i]), "make_geometry: k[%d] = %g must be > 0", i, k[i]);
     HalfNodes H;
@@ -32,26 +34,26 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     g->h_node_off.assign(1, 0);
     g->h_outer_off = H.outer_off;
     std::vector<int64_t> src;                     // source node of every slot of this k (-1: padding)
-    std::vector<std::vector<int64_t>> queue(16);  // per residue: nodes sorted by stencil start
+    std::vector<std::vector<int64_t>> queue(BM);  // per residue: nodes sorted by stencil start
     for (int ik = 0; ik < nk; ik++) {
         const int64_t n0 = H.node_off[ik], n1 = H.node_off[ik + 1];
         const int64_t o0 = H.outer_off[ik];
         g->max_outer = std::max<int>(g->max_outer, (int)(H.outer_off[ik + 1] - o0));
         const int64_t cnt = n1 - n0, padded = (cnt + 3) & ~int64_t(3);
         for (auto& q : queue) q.clear();
-        for (int64_t j = n0; j < n1; j++) queue[H.b_j0[j] & 15].push_back(j);
+        for (int64_t j = n0; j < n1; j++) queue[H.b_j0[j] & (BM - 1)].push_back(j);
         for (int64_t j = cnt; j < padded; j++) queue[0].push_back(-1);     // padding reads stencil 0
-        size_t head[16] = {0};
+        size_t head[32] = {0};
         for (auto& q : queue)
             std::stable_sort(q.begin(), q.end(), [&](int64_t x, int64_t y) {
                 return (x < 0 ? 0 : H.b_j0[x]) < (y < 0 ? 0 : H.b_j0[y]); });
         src.clear();
         int64_t left = padded;
         while (left > 0) {
-            int room = (int)std::min<int64_t>(16, left);
-            int order[16];
-            for (int r = 0; r < 16; r++) order[r] = r;
-            std::sort(order, order + 16, [&](int x, int y) { return queue[x].size() - head[x] > queue[y].size() - head[y]; });
+            int room = (int)std::min<int64_t>(BM, left);
+            int order[32];
+            for (int r = 0; r < BM; r++) order[r] = r;
+            std::sort(order, order + BM, [&](int x, int y) { return queue[x].size() - head[x] > queue[y].size() - head[y]; });
             auto take_item = [&](int r) {
                 // one item = the run of nodes with the same stencil start at the head of residue r
                 auto& q = queue[r];
@@ -61,11 +63,11 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
                     room--; left--;
                 }
             };
-            for (int i = 0; i < 16 && room > 0; i++) if (head[order[i]] < queue[order[i]].size()) take_item(order[i]);
+            for (int i = 0; i < BM && room > 0; i++) if (head[order[i]] < queue[order[i]].size()) take_item(order[i]);
             // residues exhausted: complete the half-warp from the fullest queue (conflicting reads)
             while (room > 0 && left > 0) {
                 int best = 0;
-                for (int r = 1; r < 16; r++) if (queue[r].size() - head[r] > queue[best].size() - head[best]) best = r;
+                for (int r = 1; r < BM; r++) if (queue[r].size() - head[r] > queue[best].size() - head[best]) best = r;
                 take_item(best);
             }
         }
@@ -100,6 +102,14 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     g->b.upload(b, s);
     g->wgt.upload(wgt, s);
     g->b_coef.upload(b_coef, s);
+    {
+        std::vector<int> pack(b_j0.size());
+        for (size_t i = 0; i < b_j0.size(); i++) {
+            PRSD_REQUIRE(b_j0[i] >= 0 && b_j0[i] < 4096 && n_ol[i] >= 0 && n_ol[i] < (1 << 19), "node index does not fit the packed stream");
+            pack[i] = (n_ol[i] << 12) | b_j0[i];
+        }
+        g->b_pack.upload(pack, s);
+    }
     g->kdev.upload(g->k, s);
     ctx.sync();   // the host vectors go out of scope
     return g;

@@ -37,12 +37,16 @@ struct NodeGeometry {
     DevBuf<double> a, a_coef;
     DevBuf<int> b_j0, n_outer_local;
     DevBuf<double> b, wgt, b_coef;
+    // compact index stream of the one-lane-per-node kernels: (outer index << 12) | stencil start
+    DevBuf<int> b_pack;
     DevBuf<double> kdev;
     size_t bytes() const;
 };
 
+// bank_mod: the node order makes the stencil starts of `bank_mod` consecutive nodes equal or distinct modulo
+// bank_mod -- 16 for 8-byte table reads (half-warp wavefronts), 32 for the 4-byte reads of the nodal kernels
 std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
-                                            const QuadConfig& cfg, const KnotGrid& grid);
+                                            const QuadConfig& cfg, const KnotGrid& grid, int bank_mod = 16);
 
 struct BilinearOp {
     std::shared_ptr<NodeGeometry> geo;

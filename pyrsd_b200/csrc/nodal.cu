@@ -18,9 +18,8 @@ struct NodalArgs {
     const int64_t* node_off;
     const int* a_j0;
     const double* a_coef;
-    const int* b_j0;
-    const int* ol;
-    const double* b_coef;
+    const int* b_pack;      // (outer index << 12) | stencil start
+    const double* b_coef;   // Lagrange coefficients, 4 per node
     const double* W;        // [NW][n_nodes]
     int64_t n_nodes;
     const double* tables;
@@ -121,6 +120,10 @@ struct SpecDiag {
     }
 };
 
+// (Tried and rejected this round: staging the tables in binary32.  Rounding the TABLE is harmless -- the error of
+// a knot is common to every node that reads it and cancels wherever the kernels cancel -- and halves the table
+// wavefronts, but the kernel then runs into the P(a) reads and the global stream and gains only ~10 %; with the
+// interpolation ARITHMETIC in binary32 the h01-type cancellations amplify the independent 6e-8 errors to 1e-4.)
 template <class Spec>
 __global__ void __launch_bounds__(NL_THREADS, 2)
 k_nodal_apply(const NodalArgs g)
@@ -171,11 +174,26 @@ k_nodal_apply(const NodalArgs g)
 #pragma unroll
         for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
         const int64_t n0 = g.node_off[ik], n1 = g.node_off[ik + 1];
-        for (int64_t node = n0 + tid; node < n1; node += NL_THREADS) {
-            const int j0 = __ldg(g.b_j0 + node);
-            const int ol = __ldg(g.ol + node);
-            const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node));
-            const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node) + 1);
+        // the index word and the coefficients of the NEXT node of this lane are loaded one iteration ahead: the
+        // shared-memory reads depend on them, and an exposed L2 round trip per node was the largest stall
+        int64_t node = n0 + tid;
+        int pk_next = 0;
+        double2 c01_next = make_double2(0.0, 0.0), c23_next = c01_next;
+        if (node < n1) {
+            pk_next = __ldg(g.b_pack + node);
+            c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node));
+            c23_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node) + 1);
+        }
+        for (; node < n1; node += NL_THREADS) {
+            const int pk = pk_next;
+            const double2 c01 = c01_next, c23 = c23_next;
+            const int64_t nx = node + NL_THREADS;
+            if (nx < n1) {
+                pk_next = __ldg(g.b_pack + nx);
+                c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx));
+                c23_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx) + 1);
+            }
+            const int j0 = pk & 4095, ol = pk >> 12;
             double w[Spec::NW];
 #pragma unroll
             for (int c = 0; c < Spec::NW; c++) w[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
@@ -219,7 +237,7 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     a.nk = geo.nk; a.max_outer = geo.max_outer; a.kchunk = kchunk; a.nrow = nrow;
     a.outer_off = geo.outer_off.p; a.node_off = geo.node_off.p;
     a.a_j0 = geo.a_j0.p; a.a_coef = geo.a_coef.p;
-    a.b_j0 = geo.b_j0.p; a.ol = geo.n_outer_local.p; a.b_coef = geo.b_coef.p;
+    a.b_pack = geo.b_pack.p; a.b_coef = geo.b_coef.p;
     a.W = op.W.p; a.n_nodes = geo.n_nodes;
     a.tables = tables; a.slot_tab = slot_tab; a.out = out;
     const size_t smem = (size_t)(NL_SLOTS*TAB_MPAD + NL_SLOTS*geo.max_outer + (NL_WARPS + 1)*Spec::NACC + 2)*sizeof(double) + 16;

@@ -224,6 +224,7 @@ class _Spectra(N.Handle):
 
     def rescale(self, fac):
         N.check(_L().prsd_spectra_rescale(self.ptr, N.as_f64(fac)))
+        self._computed_oneloop = None        # a one-loop object built from now on sees the new normalisation
 
     def ps_integral(self, what, x, factor=0.5):
         x = N.as_f64(x)
@@ -232,9 +233,14 @@ class _Spectra(N.Handle):
         return out
 
     def ensure_oneloop(self):
-        if not self.have_oneloop:
-            N.check(_L().prsd_oneloop_tables(self.ptr, None, None))
+        """the four one-loop tables COMPUTED from this batch's linear spectra (cached: objects built on explicit
+        ``oneloop_power`` arrays overwrite the device copy, never this cache)"""
+        if getattr(self, '_computed_oneloop', None) is None:
+            out = np.empty((self.ncosmo, 4, 1000))
+            N.check(_L().prsd_oneloop_tables(self.ptr, None, out.ctypes.data_as(_vp)))
+            self._computed_oneloop = out
             self.have_oneloop = True
+        return self._computed_oneloop
 
     def oneloop_tables(self):
         out = np.empty((self.ncosmo, 4, 1000))
@@ -371,13 +377,13 @@ class OneLoopPS(PowerSpectrum, PickalableSWIG):
         self._P, self._eps = P_L, epsrel
         self._sp = P_L._sp
         if oneloop_power is None:
-            self._sp.ensure_oneloop()
+            self._table = self._sp.ensure_oneloop()[0, self._which].copy()
         else:
             t = np.ascontiguousarray(np.asarray(oneloop_power, dtype=np.float64).reshape(1, -1))
             if t.shape[1] != 1000:
                 raise ValueError("oneloop_power must have 1000 entries (OneLoopPS.cpp:11-13)")
-            N.check(_L().prsd_spectra_set_oneloop_one(self._sp.ptr, self._which, t))
-        self._table = self._sp.oneloop_tables()[0, self._which].copy()
+            self._table = t[0].copy()
+        self._install()
 
     def __getstate__(self):
         return {'args': self.args + (self.GetEpsrel(), self.GetOneLoopPower())}
@@ -387,6 +393,7 @@ class OneLoopPS(PowerSpectrum, PickalableSWIG):
         cur = self._sp.oneloop_tables()[0, self._which] if self._sp.have_oneloop else None
         if cur is None or not np.array_equal(cur, self._table):
             N.check(_L().prsd_spectra_set_oneloop_one(self._sp.ptr, self._which, self._table.reshape(1, -1)))
+            self._sp.have_oneloop = True
 
     def _ev(self, k, full):
         self._install()

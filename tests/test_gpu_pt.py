@@ -164,6 +164,18 @@ def test_plan_matches_one_off_calls_and_golden(plin, cosmo, golden, tight):
     assert np.max(np.abs(I[10][sel] - pygcl.Imn(plin)(k[sel], 2, 2))) <= 1e-12*np.max(np.abs(I[10]))
     assert np.max(np.abs(K[6][sel] - pygcl.Kmn(plin)(k[sel], 1, 1))) <= 1e-12*np.max(np.abs(K[6]))
     Pk = plin(k)
+    # ImnOneLoop comes from the one-lane-per-node kernel in the plan and from the DMMA operator in the one-off pygcl
+    # calls: same nodes, different kernels and summation orders
+    ML = eng.get(res, 'ML')[0]
+    ol = {w: cls(plin) for w, cls in (('dd', pygcl.OneLoopPdd), ('dv', pygcl.OneLoopPdv), ('vv', pygcl.OneLoopPvv))}
+    spec = [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
+            ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]
+    sel_ml = np.array([60, 130, 170, 195, 215, 235, 249])
+    for j, (p1, p2, m, n) in enumerate(spec):
+        Iml = pygcl.ImnOneLoop(ol[p1]) if p2 is None else pygcl.ImnOneLoop(ol[p1], ol[p2], 1e-4)
+        for w, fn in enumerate((Iml.EvaluateLinear, Iml.EvaluateCross, Iml.EvaluateOneLoop)):
+            err = relerr_floor(ML[j, w][sel_ml], fn(k[sel_ml], m, n), Pk[sel_ml])
+            assert err.max() < 1e-10, (j, w, err.max())
     # shipped tables were computed at the reference's default epsrel: medians agree to ~1e-9, the
     # worst points differ by what epsrel = 1e-4 / 1e-3 allows
     for name, arr in [('I02', I[2]), ('I22', I[10]), ('I31', I[13]), ('K00', K[0]), ('K11', K[6]), ('K20s_b', K[12]),
