@@ -34,41 +34,75 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     g->h_node_off.assign(1, 0);
     g->h_outer_off = H.outer_off;
     std::vector<int64_t> src;                     // source node of every slot of this k (-1: padding)
-    std::vector<std::vector<int64_t>> queue(BM);  // per residue: nodes sorted by stencil start
+    // an item = the nodes of one k that share the stencil start AND the outer node: every read of theirs is a
+    // broadcast.  A group of BM lanes takes items whose stencil starts are distinct modulo BM (table reads) and,
+    // where possible, whose outer indices are too (the P(a) reads of the nodal kernels).
+    struct Item { int j0, ol; int64_t begin, end; };
+    std::vector<int64_t> sorted;
+    std::vector<Item> items;
+    std::vector<std::vector<int>> queue(BM);      // per stencil residue: item indices, ascending
     for (int ik = 0; ik < nk; ik++) {
         const int64_t n0 = H.node_off[ik], n1 = H.node_off[ik + 1];
         const int64_t o0 = H.outer_off[ik];
         g->max_outer = std::max<int>(g->max_outer, (int)(H.outer_off[ik + 1] - o0));
         const int64_t cnt = n1 - n0, padded = (cnt + 3) & ~int64_t(3);
+        auto j0_of = [&](int64_t j) { return j < 0 ? 0 : H.b_j0[j]; };
+        auto ol_of = [&](int64_t j) { return j < 0 ? 0 : (int)(H.n_outer[j] - o0); };
+        sorted.clear();
+        for (int64_t j = n0; j < n1; j++) sorted.push_back(j);
+        for (int64_t j = cnt; j < padded; j++) sorted.push_back(-1);       // padding reads stencil 0, outer node 0
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int64_t x, int64_t y) {
+            return j0_of(x) != j0_of(y) ? j0_of(x) < j0_of(y) : ol_of(x) < ol_of(y); });
+        items.clear();
         for (auto& q : queue) q.clear();
-        for (int64_t j = n0; j < n1; j++) queue[H.b_j0[j] & (BM - 1)].push_back(j);
-        for (int64_t j = cnt; j < padded; j++) queue[0].push_back(-1);     // padding reads stencil 0
+        for (int64_t i = 0; i < padded; ) {
+            int64_t e = i + 1;
+            while (e < padded && j0_of(sorted[e]) == j0_of(sorted[i]) && ol_of(sorted[e]) == ol_of(sorted[i])) e++;
+            queue[j0_of(sorted[i]) & (BM - 1)].push_back((int)items.size());
+            items.push_back({j0_of(sorted[i]), ol_of(sorted[i]), i, e});
+            i = e;
+        }
         size_t head[32] = {0};
-        for (auto& q : queue)
-            std::stable_sort(q.begin(), q.end(), [&](int64_t x, int64_t y) {
-                return (x < 0 ? 0 : H.b_j0[x]) < (y < 0 ? 0 : H.b_j0[y]); });
+        int64_t remaining[32];
+        for (int r = 0; r < BM; r++) {
+            remaining[r] = 0;
+            for (int it : queue[r]) remaining[r] += items[it].end - items[it].begin;
+        }
         src.clear();
         int64_t left = padded;
         while (left > 0) {
             int room = (int)std::min<int64_t>(BM, left);
+            int used_j0[32], used_ol[32];
+            for (int r = 0; r < BM; r++) used_j0[r] = used_ol[r] = -1;
             int order[32];
             for (int r = 0; r < BM; r++) order[r] = r;
-            std::sort(order, order + BM, [&](int x, int y) { return queue[x].size() - head[x] > queue[y].size() - head[y]; });
-            auto take_item = [&](int r) {
-                // one item = the run of nodes with the same stencil start at the head of residue r
-                auto& q = queue[r];
-                const int j0 = q[head[r]] < 0 ? 0 : H.b_j0[q[head[r]]];
-                while (room > 0 && head[r] < q.size() && (q[head[r]] < 0 ? 0 : H.b_j0[q[head[r]]]) == j0) {
-                    src.push_back(q[head[r]++]);
-                    room--; left--;
+            std::sort(order, order + BM, [&](int x, int y) { return remaining[x] > remaining[y]; });
+            // strict: 0 = both reads conflict-free, 1 = table reads conflict-free, 2 = anything
+            for (int pass = 0; room > 0 && left > 0; pass++) {
+                const int strict = std::min(pass, 2);
+                for (int i = 0; i < BM && room > 0; i++) {
+                    const int r = order[i];
+                    auto& q = queue[r];
+                    while (head[r] < q.size() && items[q[head[r]]].begin == items[q[head[r]]].end) head[r]++;
+                    int pick = -1;
+                    for (size_t c = head[r], seen = 0; c < q.size() && seen < 8; c++) {
+                        const Item& it = items[q[c]];
+                        if (it.begin == it.end) continue;
+                        seen++;
+                        const bool ok_j0 = used_j0[r] < 0 || used_j0[r] == it.j0;
+                        const int ro = it.ol & (BM - 1);
+                        const bool ok_ol = used_ol[ro] < 0 || used_ol[ro] == it.ol;
+                        if ((strict == 0 && ok_j0 && ok_ol) || (strict == 1 && ok_j0) || strict == 2) { pick = q[c]; break; }
+                    }
+                    if (pick < 0) continue;
+                    Item& it = items[pick];
+                    used_j0[r] = it.j0;
+                    used_ol[it.ol & (BM - 1)] = it.ol;
+                    while (room > 0 && it.begin < it.end) {
+                        src.push_back(sorted[it.begin++]);
+                        room--; left--; remaining[r]--;
+                    }
                 }
-            };
-            for (int i = 0; i < BM && room > 0; i++) if (head[order[i]] < queue[order[i]].size()) take_item(order[i]);
-            // residues exhausted: complete the half-warp from the fullest queue (conflicting reads)
-            while (room > 0 && left > 0) {
-                int best = 0;
-                for (int r = 1; r < BM; r++) if (queue[r].size() - head[r] > queue[best].size() - head[best]) best = r;
-                take_item(best);
             }
         }
         for (int64_t j : src) {

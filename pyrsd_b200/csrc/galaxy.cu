@@ -609,7 +609,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     zeldovich_eval_map(c, zel, nw, d_cmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio1.p, true, cfg.k0_low,
                        plin_w.p, pt.scalars.p + 2, 4, zel1.p);
     zeldovich_eval_map(c, zel, nw, d_cmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio2.p, true, cfg.k0_low,
-                       plin_w2.p, pt.scalars.p + 2, 4, zel2.p);
+                       plin_w2.p, pt.scalars.p + 2, 4, zel2.p, true);       // only P00 is read at sigma8_z / D
 
     GalDev G;
     G.cfg = cfg;

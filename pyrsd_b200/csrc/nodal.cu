@@ -38,6 +38,7 @@ struct NodalArgs {
 //   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
 struct SpecML {
     static const int NACC = 19, NW = 14, NOUT = 21;
+    static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
         const double La = pa[0], Da = pa[1], Va = pa[2], Wa = pa[3];
@@ -102,6 +103,7 @@ std::vector<ColSpec> ml_columns()
 // slots: P_L of 4 cosmologies; W columns: the operator's 6 kernels; accumulator 6 r + c
 struct SpecDiag {
     static const int NACC = 24, NW = 6, NOUT = 24;
+    static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
 #pragma unroll
@@ -179,24 +181,39 @@ k_nodal_apply(const NodalArgs g)
         int64_t node = n0 + tid;
         int pk_next = 0;
         double2 c01_next = make_double2(0.0, 0.0), c23_next = c01_next;
+        double w_next[Spec::PREFETCH_W ? Spec::NW : 1];
         if (node < n1) {
             pk_next = __ldg(g.b_pack + node);
             c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node));
             c23_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node) + 1);
+            if (Spec::PREFETCH_W) {
+#pragma unroll
+                for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
+            }
         }
         for (; node < n1; node += NL_THREADS) {
             const int pk = pk_next;
             const double2 c01 = c01_next, c23 = c23_next;
+            double w[Spec::NW];
+            if (Spec::PREFETCH_W) {
+#pragma unroll
+                for (int c = 0; c < Spec::NW; c++) w[c] = w_next[c];
+            }
             const int64_t nx = node + NL_THREADS;
             if (nx < n1) {
                 pk_next = __ldg(g.b_pack + nx);
                 c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx));
                 c23_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx) + 1);
+                if (Spec::PREFETCH_W) {
+#pragma unroll
+                    for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + nx);
+                }
             }
             const int j0 = pk & 4095, ol = pk >> 12;
-            double w[Spec::NW];
+            if (!Spec::PREFETCH_W) {
 #pragma unroll
-            for (int c = 0; c < Spec::NW; c++) w[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
+                for (int c = 0; c < Spec::NW; c++) w[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
+            }
             double pa[NL_SLOTS], pb[NL_SLOTS];
 #pragma unroll
             for (int s = 0; s < NL_SLOTS; s++) {

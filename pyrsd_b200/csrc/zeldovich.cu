@@ -83,6 +83,9 @@ __global__ void k_zel_fold(int nk, const double* __restrict__ g, const int* __re
 // (Fsec of ZeldovichPS.cpp:198-203, 241-246, 285-296 expanded in powers of n), evaluated by Horner.
 static const int ZW = 8;
 
+// ONLY00: P00 alone (the Jennings fits need P00 at a second normalisation, power_dm.py:676-718); P01, P11 are
+// written as 0
+template <bool ONLY00>
 __global__ void __launch_bounds__(256)
 k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __restrict__ rr, const double* __restrict__ G,
             const int* __restrict__ cmap,
@@ -144,16 +147,24 @@ k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __res
             const double E0 = s_E0[j];
             const double E = exp(-0.5*k2*(xx + yy));
             const double kxx = k2*xx, kyy = k2*yy;
+            const double rho = kr*yy;
+            const double g0 = r15*gl[0];
+            const double pre = r15*E*rho;
+            if (ONLY00) {
+                double S0 = 0.0;
+#pragma unroll
+                for (int n = ZEL_NMAX; n >= 1; n--) S0 = fma(S0, rho, gl[n]);
+                acc[3*j] += g0*(E - E0) + pre*S0;
+                continue;
+            }
             const double common = k4*xx*xx - 2.0*k2*x0;      // k^4 XX^2 - 2 k^2 X0
             const double c11 = common + 2.0*(kxx - 1.0)*kyy + k4*yy*yy;
             // n = 0 (Fprim of the three spectra, ZeldovichPS.cpp:190-196, 234-239, 273-283)
-            const double g0 = r15*gl[0];
             double a00 = g0*(E - E0);
             double a01 = g0*k2*((xx + yy)*E - 2.0*s2*E0);
             double a11 = g0*(c11*E - 4.0*k4*s2*s2*E0);
             // n >= 1: v_n = r^1.5 E rho^n G_n;  P00 += v_n, P01 += v_n (kxx + kyy - 2n),
             //         P11 += v_n (c11 - 4 n (kxx - 1) - 4 n kyy + 4 n (n - 1))
-            const double rho = kr*yy;
             double S0 = 0.0, S1 = 0.0, S2 = 0.0;
 #pragma unroll
             for (int n = ZEL_NMAX; n >= 1; n--) {
@@ -161,7 +172,6 @@ k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __res
                 S1 = fma(S1, rho, (double)n*gl[n]);
                 S2 = fma(S2, rho, (double)(n*n)*gl[n]);
             }
-            const double pre = r15*E*rho;
             S0 *= pre; S1 *= pre; S2 *= pre;
             a00 += S0;
             a01 += (kxx + kyy)*S0 - 2.0*S1;
@@ -207,13 +217,16 @@ void zeldovich_eval_xx(Context& ctx, const ZelPlan& plan, int ncosmo, const doub
 
 void zeldovich_eval_map(Context& ctx, const ZelPlan& plan, int nrow, const int* cmap, const double* X0, const double* XX,
                         const double* YY, const double* sigmasq, int sigmasq_stride, const double* ratio, bool lowk,
-                        double k0_low, const double* plin, const double* q3coef, int q3_stride, double* out)
+                        double k0_low, const double* plin, const double* q3coef, int q3_stride, double* out, bool only_p00)
 {
     if (nrow <= 0) return;
     PRSD_REQUIRE(!lowk || (plin && q3coef), "zeldovich_eval: low-k approximation needs P_lin(k) and Q3");
     dim3 grid((nrow + ZW - 1)/ZW, plan.nk);
     ProfScope prof(ctx, PROF_ZELDOVICH);
-    k_zeldovich<<<grid, 256, 0, ctx.stream>>>(plan.nk, nrow, plan.dk.p, plan.r.p, plan.G.p, cmap, X0, XX, YY, sigmasq, sigmasq_stride, ratio, lowk ? 1 : 0, k0_low, plin, q3coef, q3_stride, out);
+    if (only_p00)
+        k_zeldovich<true><<<grid, 256, 0, ctx.stream>>>(plan.nk, nrow, plan.dk.p, plan.r.p, plan.G.p, cmap, X0, XX, YY, sigmasq, sigmasq_stride, ratio, lowk ? 1 : 0, k0_low, plin, q3coef, q3_stride, out);
+    else
+        k_zeldovich<false><<<grid, 256, 0, ctx.stream>>>(plan.nk, nrow, plan.dk.p, plan.r.p, plan.G.p, cmap, X0, XX, YY, sigmasq, sigmasq_stride, ratio, lowk ? 1 : 0, k0_low, plin, q3coef, q3_stride, out);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
 }

@@ -54,6 +54,6 @@ void zeldovich_eval_xx(Context& ctx, const ZelPlan& plan, int ncosmo, const doub
 // and out are indexed by w
 void zeldovich_eval_map(Context& ctx, const ZelPlan& plan, int nrow, const int* cmap, const double* X0, const double* XX,
                         const double* YY, const double* sigmasq, int sigmasq_stride, const double* ratio, bool lowk,
-                        double k0_low, const double* plin, const double* q3coef, int q3_stride, double* out);
+                        double k0_low, const double* plin, const double* q3coef, int q3_stride, double* out, bool only_p00 = false);
 
 } // namespace prsd
