@@ -15,7 +15,7 @@ size_t NodeGeometry::bytes() const
 std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
                                             const QuadConfig& cfg, const KnotGrid& grid, int bank_mod)
 {
-    PRSD_REQUIRE(bank_mod == 16 || bank_mod == 32, "make_geometry: bank_mod must be 16 or 32");
+    PRSD_REQUIRE(bank_mod == 4 || bank_mod == 16 || bank_mod == 32, "make_geometry: bank_mod must be 4, 16 or 32");
     const int BM = bank_mod;
     PRSD_REQUIRE(nk > 0, "make_geometry: empty k list");
     for (int i = 0; i < nk; i++) PRSD_REQUIRE(k[i] > 0 && std::isfinite(k[i]), "make_geometry: k[%d] = %g must be > 0", i, k[i]);
@@ -232,7 +232,7 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tabs = reinterpret_cast<double*>(smem_raw);
     double* PaS = tabs + 8*TAB_MPAD;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(PaS + 8*max_outer);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(PaS + 8*max_outer);      // max_outer = padded row stride (= 4 mod 16)
 
     // tiles of the same k are adjacent in launch order: the node stream of a k is read from DRAM once
     // and from L2 by the other tiles
@@ -319,12 +319,15 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
                          const int* rowA, const int* rowB, int ntiles, double* out)
 {
     const NodeGeometry& g = *op.geo;
-    const size_t smem = (size_t)(8*TAB_MPAD + 8*g.max_outer)*sizeof(double) + 16;
+    // row stride of the P(a) buffer = 4 (mod 16) doubles like the tables: rows r and r + 4 share banks, the node
+    // order (make_geometry, bank_mod = 4) keeps the four nodes of a k-step on distinct residues modulo 4
+    const int pas_stride = ((g.max_outer + 15)/16)*16 + 4;
+    const size_t smem = (size_t)(8*TAB_MPAD + 8*pas_stride)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "bilinear apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_bilinear_apply<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ntiles, g.nk);
     ProfScope prof(ctx, PROF_BILINEAR);
-    k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, g.max_outer, g.outer_off.p, g.node_off.p,
+    k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, pas_stride, g.outer_off.p, g.node_off.p,
         g.a_j0.p, g.a_coef.p, g.b_j0.p, g.n_outer_local.p, g.b_coef.p, op.W.p, tables, slot_tab, rowA, rowB, out);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;

@@ -82,7 +82,7 @@ static std::shared_ptr<NodeGeometry> cached_geometry(Context& c, const double* k
             g_geo_cache.splice(g_geo_cache.begin(), g_geo_cache, it);
             return g_geo_cache.front().second;
         }
-    auto g = make_geometry(c, k, nk, qmax, cfg, knot_grid());
+    auto g = make_geometry(c, k, nk, qmax, cfg, knot_grid(), 4);      // consumed by the DMMA kernel
     g_geo_cache.emplace_front(std::move(key), g);
     while (g_geo_cache.size() > 6) g_geo_cache.pop_back();
     return g;

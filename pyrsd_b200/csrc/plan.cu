@@ -71,7 +71,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
     if (!only_oneloop) {
-        auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid);
+        auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid, 4);     // DMMA lane layout: 4 nodes per k-step
         std::vector<ColSpec> cols;
         for (int id = 0; id < 16; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
         for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
