@@ -377,6 +377,7 @@ __device__ __forceinline__ double fog(int model, double x)
 // splines inside a group are formed once per walker; a (k, mu) point then reads 6 x 3 cubics instead of 10 x 3.
 // Group g keeps [moment][Y | b | c | d][nkm] like pairspl, plus its 1-halo constant in grpconst[w][6].
 static const int GAL_NGRP = 6;
+static const int GAL_NCONST = 12;    // per walker: 6 one-halo constants + {1/alpha_perp, 1/F, 1/F^2 - 1, alpha_drag^3/(alpha_perp^2 alpha_par)}
 
 __global__ void k_gal_groups(int nkm, const double* __restrict__ par, const double* __restrict__ pairspl,
                              double* __restrict__ grpspl, double* __restrict__ grpconst)
@@ -398,7 +399,13 @@ __global__ void k_gal_groups(int nkm, const double* __restrict__ par, const doub
         for (int g = 0; g < GAL_NGRP; g++) grpspl[((size_t)w*GAL_NGRP + g)*n + idx] = acc[g];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double* c = grpconst + (size_t)w*GAL_NGRP;
+        double* c = grpconst + (size_t)w*GAL_NCONST;
+        const double apar = p[W_APAR], aperp = p[W_APERP], adrag = p[W_ADRAG], F = apar/aperp;
+        c[6] = 1.0/aperp;
+        c[7] = 1.0/F;
+        c[8] = 1.0/(F*F) - 1.0;
+        c[9] = adrag*adrag*adrag/(aperp*aperp*apar);          // rsd/tools.py:211-214
+        c[10] = c[11] = 0.0;
         c[0] = 0.0;
         c[1] = wt[5]*p[W_NCBS];          // cBsA
         c[2] = wt[6]*p[W_NCBS];          // cBsB
@@ -414,14 +421,13 @@ __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* 
                                                  double kobs, double muobs)
 {
     const int nkm = G.nkm;
-    const double apar = p[W_APAR], aperp = p[W_APERP], adrag = p[W_ADRAG];
-    // rsd/tools.py:54-75
-    const double F = apar/aperp;
-    double k = kobs/aperp, mu = muobs;
-    if (F != 1.0) {
-        const double fac = sqrt(1.0 + muobs*muobs*(1.0/(F*F) - 1.0));
-        k = kobs/aperp*fac;
-        mu = muobs/F/fac;
+    // rsd/tools.py:54-75: F = alpha_par/alpha_perp, k' = (k/alpha_perp) sqrt(1 + mu^2 (F^-2 - 1)), mu' = (mu/F)/sqrt(...)
+    double k = kobs*gc[6], mu = muobs;
+    if (gc[8] != 0.0) {
+        const double y = 1.0 + muobs*muobs*gc[8];
+        const double inv = rsqrt(y);
+        k = kobs*gc[6]*(y*inv);
+        mu = muobs*gc[7]*inv;
     }
     if (!(k >= km[0] && k <= km[nkm - 1])) return nan("");   // the reference raises InterpolationDomainError (_cache.py:327-339)
     int i = (int)((log(k) - G.lnkm0)*G.inv_dlnkm);
@@ -436,7 +442,17 @@ __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* 
     const int fm = G.cfg.fog_model;
     const double kmu = k*mu;
     const bool so = G.cfg.use_so_correction != 0;
-    const double Gc = fog(fm, kmu*p[W_SIGC]), GsA = fog(fm, kmu*p[W_SIGSA]), GsB = fog(fm, kmu*p[W_SIGSB]);
+    double Gc, GsA, GsB;
+    if (fm == 0) {
+        // modified Lorentzian 1/(1 + x^2/2)^2 for the three dispersions with ONE division
+        const double xc = kmu*p[W_SIGC], xa = kmu*p[W_SIGSA], xb = kmu*p[W_SIGSB];
+        const double hc = 1.0 + 0.5*xc*xc, ha = 1.0 + 0.5*xa*xa, hb = 1.0 + 0.5*xb*xb;
+        const double inv = 1.0/(hc*ha*hb);
+        const double ic = inv*ha*hb, ia = inv*hc*hb, ib = inv*hc*ha;
+        Gc = ic*ic; GsA = ia*ia; GsB = ib*ib;
+    } else {
+        Gc = fog(fm, kmu*p[W_SIGC]); GsA = fog(fm, kmu*p[W_SIGSA]); GsB = fog(fm, kmu*p[W_SIGSB]);
+    }
     auto grp = [&](int g) {
         const double* s = gs + (size_t)g*16*nkm + i;
         double tot = gc[g], mpow = 1.0;
@@ -460,7 +476,7 @@ __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* 
     const double Pcs = Gc*GsA*grp(1) + Gc*GsB*grp(2);
     const double Pss = GsA*GsA*grp(3) + GsA*GsB*grp(4) + GsB*GsB*grp(5);
     const double res = (1.0 - fs)*(1.0 - fs)*Pcc + 2.0*fs*(1.0 - fs)*Pcs + fs*fs*Pss;
-    return res/(aperp*aperp*apar)*adrag*adrag*adrag;          // rsd/tools.py:211-214
+    return res*gc[9];
 }
 
 __global__ void __launch_bounds__(128)
@@ -471,7 +487,7 @@ k_gal_pkmu(GalDev G, const double* __restrict__ km, const double* __restrict__ p
     const int w = blockIdx.y, j = blockIdx.x*blockDim.x + threadIdx.x;
     if (j >= npts) return;
     out[(size_t)w*npts + j] = gal_pkmu_point(G, km, par + (size_t)w*GAL_NPAR, grpspl + (size_t)w*GAL_NGRP*16*G.nkm,
-                                             grpconst + (size_t)w*GAL_NGRP, kk[j], mm[j]);
+                                             grpconst + (size_t)w*GAL_NCONST, kk[j], mm[j]);
 }
 
 // P_ell(k) = (2 ell + 1) \int_0^1 dmu L_ell(mu) P(k, mu) with Simpson's rule on nmu (odd) equally spaced mu:
@@ -503,7 +519,7 @@ k_gal_poles(GalDev G, const double* __restrict__ km, const double* __restrict__ 
     if (j >= nk) return;
     const double* p = par + (size_t)w*GAL_NPAR;
     const double* gs = grpspl + (size_t)w*GAL_NGRP*16*G.nkm;
-    const double* gc = grpconst + (size_t)w*GAL_NGRP;
+    const double* gc = grpconst + (size_t)w*GAL_NCONST;
     const double k = kk[j];
     const double h = 1.0/(nmu - 1);
     double acc[8];
@@ -639,7 +655,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         c.launches++;
     }
     grpspl.ensure((size_t)nw*GAL_NGRP*16*nkm);
-    grpconst.ensure((size_t)nw*GAL_NGRP);
+    grpconst.ensure((size_t)nw*GAL_NCONST);
     k_gal_groups<<<dim3((16*nkm + 255)/256, nw), 256, 0, s>>>(nkm, d_par.p, pairspl.p, grpspl.p, grpconst.p);
     PRSD_CUDA(cudaGetLastError());
     c.launches++;
