@@ -37,7 +37,7 @@ struct NodalArgs {
 //   0..5 (L,L): h01 h02 h03 h04 f23 f33 | 6,7 cross of ImnOneLoop(P_vv, P_dd): h01 h02 | 8,9 its one-loop part
 //   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
 struct SpecML {
-    static const int NACC = 19, NW = 14, NOUT = 21;
+    static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 14, NOUT = 21;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
@@ -100,14 +100,15 @@ std::vector<ColSpec> ml_columns()
 }
 
 // ------------------------------------------------------------ one-loop tables
-// slots: P_L of 4 cosmologies; W columns: the operator's 6 kernels; accumulator 6 r + c
+// slots: P_L of DIAG_R cosmologies; W columns: the operator's 6 kernels; accumulator 6 r + c
+static const int DIAG_R = 4;      // measured: 2 cosmologies per CTA at 3 CTAs per SM is slower (1.50 vs 1.22 ms): the node stream is re-read twice as often
 struct SpecDiag {
-    static const int NACC = 24, NW = 6, NOUT = 24;
+    static const int NSLOT = DIAG_R, MINB = DIAG_R == 2 ? 3 : 2, NACC = 6*DIAG_R, NW = 6, NOUT = 6*DIAG_R;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < DIAG_R; r++) {
             const double pp = pa[r]*pb[r];
 #pragma unroll
             for (int c = 0; c < 6; c++) acc[6*r + c] = fma(w[c], pp, acc[6*r + c]);
@@ -117,7 +118,7 @@ struct SpecDiag {
     __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, const double* f)
     {
         const int r = t/6, c = t - 6*r;
-        const int cosmo = tile*4 + r;
+        const int cosmo = tile*DIAG_R + r;
         if (cosmo < g.nrow) g.out[((size_t)cosmo*g.nk + ik)*8 + c] = f[t];
     }
 };
@@ -127,13 +128,13 @@ struct SpecDiag {
 // wavefronts, but the kernel then runs into the P(a) reads and the global stream and gains only ~10 %; with the
 // interpolation ARITHMETIC in binary32 the h01-type cancellations amplify the independent 6e-8 errors to 1e-4.)
 template <class Spec>
-__global__ void __launch_bounds__(NL_THREADS, 2)
+__global__ void __launch_bounds__(NL_THREADS, Spec::MINB)
 k_nodal_apply(const NodalArgs g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tabs = reinterpret_cast<double*>(smem_raw);                 // [4][TAB_MPAD]
-    double* PaS = tabs + NL_SLOTS*TAB_MPAD;                             // [4][max_outer]
-    double* red = PaS + NL_SLOTS*g.max_outer;                           // [NL_WARPS][NACC]
+    double* PaS = tabs + Spec::NSLOT*TAB_MPAD;                             // [4][max_outer]
+    double* red = PaS + Spec::NSLOT*g.max_outer;                           // [NL_WARPS][NACC]
     double* fin = red + NL_WARPS*Spec::NACC;                            // [NACC]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(fin + Spec::NACC + (Spec::NACC & 1));
 
@@ -150,9 +151,9 @@ k_nodal_apply(const NodalArgs g)
     __syncthreads();
     if (tid == 0) {
         const uint32_t bytes = TAB_MPAD*sizeof(double);
-        mbar_expect_tx(mbar, NL_SLOTS*bytes);
-        for (int s = 0; s < NL_SLOTS; s++)
-            bulk_copy_g2s(tabs + s*TAB_MPAD, g.tables + (size_t)g.slot_tab[tile*NL_SLOTS + s]*TAB_MPAD, bytes, mbar);
+        mbar_expect_tx(mbar, Spec::NSLOT*bytes);
+        for (int s = 0; s < Spec::NSLOT; s++)
+            bulk_copy_g2s(tabs + s*TAB_MPAD, g.tables + (size_t)g.slot_tab[tile*Spec::NSLOT + s]*TAB_MPAD, bytes, mbar);
     }
     mbar_wait(mbar, 0);
 
@@ -165,7 +166,7 @@ k_nodal_apply(const NodalArgs g)
             const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)));
             const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)) + 1);
 #pragma unroll
-            for (int s = 0; s < NL_SLOTS; s++) {
+            for (int s = 0; s < Spec::NSLOT; s++) {
                 const double* t = tabs + s*TAB_MPAD + j0;
                 PaS[s*g.max_outer + o] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
             }
@@ -214,9 +215,9 @@ k_nodal_apply(const NodalArgs g)
 #pragma unroll
                 for (int c = 0; c < Spec::NW; c++) w[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
             }
-            double pa[NL_SLOTS], pb[NL_SLOTS];
+            double pa[Spec::NSLOT], pb[Spec::NSLOT];
 #pragma unroll
-            for (int s = 0; s < NL_SLOTS; s++) {
+            for (int s = 0; s < Spec::NSLOT; s++) {
                 const double* t = tabs + s*TAB_MPAD + j0;
                 pb[s] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
                 pa[s] = PaS[s*g.max_outer + ol];
@@ -257,7 +258,7 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     a.b_pack = geo.b_pack.p; a.b_coef = geo.b_coef.p;
     a.W = op.W.p; a.n_nodes = geo.n_nodes;
     a.tables = tables; a.slot_tab = slot_tab; a.out = out;
-    const size_t smem = (size_t)(NL_SLOTS*TAB_MPAD + NL_SLOTS*geo.max_outer + (NL_WARPS + 1)*Spec::NACC + 2)*sizeof(double) + 16;
+    const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + Spec::NSLOT*geo.max_outer + (NL_WARPS + 1)*Spec::NACC + 2)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_nodal_apply<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // k chunks: few enough to amortise the table staging, enough CTAs to fill 148 SMs x 2 when the batch is small
@@ -277,7 +278,7 @@ void nodal_apply_ml(Context& ctx, const BilinearOp& op, const double* tables, co
 
 void nodal_apply_diag(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
 {
-    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + 3)/4, ncosmo, 8, out, PROF_NODAL_DIAG);
+    launch_nodal<SpecDiag>(ctx, op, tables, slot_tab, (ncosmo + DIAG_R - 1)/DIAG_R, ncosmo, 8, out, PROF_NODAL_DIAG);
 }
 
 } // namespace prsd
