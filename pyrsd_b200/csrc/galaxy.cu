@@ -263,13 +263,19 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
     __syncthreads();
     const double lnks0 = log(S[0]), inv_dlnks = (GAL_NSTOCH - 1)/log(S[GAL_NSTOCH - 1]/S[0]);
     const double* hm = G.cfg.hzhm;
-    auto phm = [&](double bb, int which, double k, double P00, double Z00, double K00, double K00s, double bsx) {
-        if (G.cfg.use_Phm_model) {
-            // HaloMatterBase._powerlaw (hzpt/Phm.py:231-236)
-            const double x = s8z/0.8, lb = log(bb);
-            auto pl = [&](int j) { return hm[4*j]*pow(bb, hm[4*j + 1] + hm[4*j + 3]*lb)*pow(x, hm[4*j + 2]); };
-            return pade_bb(k, pl(0), pl(4), pl(1), pl(2), pl(3)) + bb*Z00;
+    // HaloMatterBase._powerlaw (hzpt/Phm.py:231-236): the five Pade parameters depend on (sigma8_z, b1) only --
+    // evaluated once per (walker, bias), not per k
+    double hp1[5] = {0, 0, 0, 0, 0}, hp2[5] = {0, 0, 0, 0, 0};
+    if (G.cfg.use_Phm_model) {
+        const double x = s8z/0.8;
+        for (int side = 0; side < 2; side++) {
+            const double bb = side ? b1b : b1, lb = log(bb);
+            double* hp = side ? hp2 : hp1;
+            for (int j = 0; j < 5; j++) hp[j] = hm[4*j]*pow(bb, hm[4*j + 1] + hm[4*j + 3]*lb)*pow(x, hm[4*j + 2]);
         }
+    }
+    auto phm = [&](double bb, const double* hp, int which, double k, double P00, double Z00, double K00, double K00s, double bsx) {
+        if (G.cfg.use_Phm_model) return pade_bb(k, hp[0], hp[4], hp[1], hp[2], hp[3]) + bb*Z00;
         return bb*P00 + b2(0, which)*K00 + bsx*K00s;      // power_biased.py:325-340
     };
     for (int i = tid; i < nkm; i += blockDim.x) {
@@ -280,8 +286,8 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
         const double P02nv2 = B[B_P02NV2*nkm + i], P02nv4 = B[B_P02NV4*nkm + i];
         // P00_ss (biased/P00.py:19-43) with the stochasticity spline (power_biased.py:342-366)
         const double st = pw_cubic_eval_log(GAL_NSTOCH, S, S + 20, S + 40, S + 60, S + 80, lnks0, inv_dlnks, k);
-        const double Phm1 = phm(b1, ia, k, P00, B[B_Z00*nkm + i], K00, K00s, bs);
-        const double Phm2 = (ia == ib) ? Phm1 : phm(b1b, ib, k, P00, B[B_Z00*nkm + i], K00, K00s, bsb);
+        const double Phm1 = phm(b1, hp1, ia, k, P00, B[B_Z00*nkm + i], K00, K00s, bs);
+        const double Phm2 = (ia == ib) ? Phm1 : phm(b1b, hp2, ib, k, P00, B[B_Z00*nkm + i], K00, K00s, bsb);
         const double mu0 = Phm1*Phm2/P00 + st;
         // P01_mu2 with a given b2_01 kind (biased/P01.py:3-24)
         auto P01mu2 = [&](int kind) {
