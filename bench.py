@@ -380,17 +380,17 @@ def _cpu_eval(seed, thin=1):
 
 def cpu_baseline_sample():
     """reference C++ (oracle/_ref), 1 core (its packaged build has no OpenMP, setup.py:188): bounded sample = every
-    4th point of every grid of one evaluation (~10-15 s of CPU work), scaled by 4"""
+    second point of every grid of one evaluation (~10-25 s of CPU work), scaled by 2"""
     from oracle import gcl_ref as R
     if not R.available():
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/libgcl_ref.so missing"}
     t0 = time.perf_counter()
-    est = _cpu_eval(SEED, thin=4)
+    est = _cpu_eval(SEED, thin=2)
     wall = time.perf_counter() - t0
     return {"value": 1.0/est, "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": "every 4th point of every grid of ONE evaluation on the reference C++ at its default epsrel (all 16 I, 6 J, 13 K "
+            "sample": "every second point of every grid of ONE evaluation on the reference C++ at its default epsrel (all 16 I, 6 J, 13 K "
                       "and sigma_v^2(k) on 250 k, the four one-loop spectra on 1000 k, 7 x 3 ImnOneLoop integrals, X(r)/Y(r) on 1024 r, "
-                      "Zel'dovich P00/P01/P11 on the 200-point model grid at two normalisations): %.1f s of CPU work, x 4 = %.1f s per "
+                      "Zel'dovich P00/P01/P11 on the 200-point model grid at two normalisations): %.1f s of CPU work, x 2 = %.1f s per "
                       "evaluation; the Python P(k,mu) assembly of the reference (<1 s, docs/source/gal-power-overview.rst:68-69) is "
                       "NOT included" % (wall, est),
             "seconds_per_eval": est}
@@ -442,7 +442,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=128, help='cosmologies per GPU per step')
+    ap.add_argument('--batch', type=int, default=256, help='cosmologies per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
