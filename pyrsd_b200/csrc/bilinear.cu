@@ -150,9 +150,13 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
 }
 
 // ------------------------------------------------------------------ W build
-// fragment-major column order: stored index of column c is (c % 8) * NT + c / 8, so that the
-// NT B-fragment values one lane needs (columns 8 j + lane/4) are contiguous.
-__host__ __device__ inline int w_slot(int col, int nt) { return (col & 7)*nt + (col >> 3); }
+// Fragment order: the B fragment of n-tile j for the k-step of nodes 4g .. 4g+3 is stored as 32 consecutive
+// doubles in LANE order (lane = 4 (col % 8) + node % 4), so that one warp-wide load of a fragment is a single
+// 256-byte coalesced access:  index(node, col) = ((node / 4) NT + col / 8) 32 + 4 (col % 8) + node % 4.
+__host__ __device__ inline int64_t w_index(int64_t node, int col, int nt)
+{
+    return ((node >> 2)*nt + (col >> 3))*32 + ((col & 7) << 2) + (node & 3);
+}
 
 struct ColSpecDev { int kid; int sign; double fac; };
 
@@ -177,7 +181,6 @@ __global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, int soa, con
     const double u = (a + b)/k, vp = (b - a)/k;
     const double ea = 2.0*a/k, eb = 2.0*b/k;
     const int nt = ncol >> 3;
-    double* row = W + node*ncol;
     for (int c = 0; c < ncol; c++) {
         double val = 0.0;
         if (c < ncol_used && w != 0.0) {
@@ -188,7 +191,7 @@ __global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, int soa, con
             val = w*k*cs.fac*f;
         }
         if (soa) { if (c < ncol_used) W[(int64_t)c*n_nodes + node] = val; }
-        else row[w_slot(c, nt)] = val;
+        else W[w_index(node, c, nt)] = val;
     }
 }
 
@@ -282,9 +285,9 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
         const double2 c01 = __ldg(reinterpret_cast<const double2*>(b_coef + 4*node));
         const double2 c23 = __ldg(reinterpret_cast<const double2*>(b_coef + 4*node) + 1);
         double wf[NT];
-        const double* wrow = W + node*(8*NT) + row*NT;
+        const double* wrow = W + (base >> 2)*(32*NT) + lane;      // base is a multiple of 4 (node lists are padded)
 #pragma unroll
-        for (int j = 0; j < NT; j++) wf[j] = __ldg(wrow + j);
+        for (int j = 0; j < NT; j++) wf[j] = __ldg(wrow + 32*j);
         const double* t = tb + j0;
         double pb = c01.x*t[0];
         pb = fma(c01.y, t[1], pb);
