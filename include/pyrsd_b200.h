@@ -193,6 +193,12 @@ int prsd_galaxy_poles(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
 int prsd_galaxy_poles_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
                              const double* par, const double* stoch, int nk, const double* d_k, int nell,
                              const int* ells, int nmu, double* d_out);
+/* FittingDriver.chi2  [rsdfit/driver.py:780-802]: chi^2 = (M - D)^T C^-1 (M - D) of every walker, M = the walker's
+ * multipoles in the order [ell][k] (prsd_galaxy_poles), data [nell nk], cinv [nell nk][nell nk] the precision
+ * matrix; chi2 [nw]; poles (may be NULL) [nw][nell][nk] receives the model vectors */
+int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
+                     const double* par, const double* stoch, int nk, const double* k, int nell, const int* ells,
+                     int nmu, const double* data, const double* cinv, double* chi2, double* poles);
 /* spline knots of P[mu^0], P[mu^2], P[mu^4], P[mu^6] of the last call: out [nw][10][4][nkm] */
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
 

@@ -681,6 +681,27 @@ int prsd_galaxy_poles_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
     });
 }
 
+int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
+                     const double* stoch, int nk, const double* k, int nell, const int* ells, int nmu,
+                     const double* data, const double* cinv, double* chi2, double* poles)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && sp && res && par && stoch && k && ells && data && cinv && chi2, "null argument");
+        PRSD_REQUIRE(nk > 0 && nell > 0 && nw > 0, "prsd_galaxy_chi2: empty request");
+        Context& c = *g->g.ctx;
+        const size_t n = (size_t)nell*nk;
+        g->dk.upload(k, nk, c.stream);
+        g->dout.ensure((size_t)nw*n);
+        DevBuf<double> ddata, dcinv, dchi((size_t)nw);
+        ddata.upload(data, n, c.stream);
+        dcinv.upload(cinv, n*n, c.stream);
+        g->g.chi2(sp->s, res->r, nw, cmap, par, stoch, nk, g->dk.p, nell, ells, nmu, ddata.p, dcinv.p, g->dout.p, dchi.p);
+        dchi.download(chi2, (size_t)nw, c.stream);
+        if (poles) g->dout.download(poles, (size_t)nw*n, c.stream);
+        c.sync();
+    });
+}
+
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
 {
     return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });

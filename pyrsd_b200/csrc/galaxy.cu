@@ -557,6 +557,36 @@ __global__ void k_scale_rows(int n, const double* __restrict__ in, const double*
     out[(size_t)w*n + i] = fac[w]*in[(size_t)cmap[w]*n + i];
 }
 
+// chi^2 = (M - D)^T C^-1 (M - D) per walker (rsdfit/driver.py:780-802): M = the walker's multipoles in the order
+// [ell][k] (the reference's `combined_model`), D the data vector, C^-1 the precision matrix [n][n].
+__global__ void __launch_bounds__(256)
+k_gal_chi2(int n, const double* __restrict__ model /*[nw][n]*/, const double* __restrict__ data, const double* __restrict__ cinv,
+           double* __restrict__ out)
+{
+    extern __shared__ double sm_chi[];
+    double* diff = sm_chi;                 // [n]
+    __shared__ double red[8];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < n; i += blockDim.x) diff[i] = model[(size_t)w*n + i] - data[i];
+    __syncthreads();
+    double acc = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double* row = cinv + (size_t)i*n;
+        double y = 0.0;
+        for (int j = 0; j < n; j++) y = fma(row[j], diff[j], y);
+        acc = fma(diff[i], y, acc);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        out[w] = t;
+    }
+}
+
 // ------------------------------------------------------------------ host
 GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmodel, int nkm_, const double* k_interp, int nki)
     : ctx(&c), cfg(cfg_), nkm(nkm_), nk_interp(nki)
@@ -689,6 +719,23 @@ void GalaxyModel::poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     ProfScope prof_gal(c, PROF_GALAXY);
     k_gal_poles<<<dim3((nk + 127)/128, nw), 128, 0, c.stream>>>(last_G, d_km.p, d_par.p, grpspl.p, grpconst.p, nk, d_k, nell,
                                                                 d_ells.p, nmu, d_out);
+    PRSD_CUDA(cudaGetLastError());
+    c.launches++;
+    c.sync();
+}
+
+void GalaxyModel::chi2(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
+                       int nk, const double* d_k, int nell, const int* ells, int nmu, const double* d_data,
+                       const double* d_cinv, double* d_poles, double* d_out)
+{
+    poles(sp, pt, nw, cmap, par, stoch, nk, d_k, nell, ells, nmu, d_poles);
+    Context& c = *ctx;
+    const int n = nell*nk;
+    const size_t smem = (size_t)n*sizeof(double);
+    PRSD_REQUIRE(smem <= 200*1024, "chi2: data vector of %d entries too long", n);
+    if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof_gal(c, PROF_GALAXY);
+    k_gal_chi2<<<nw, 256, smem, c.stream>>>(n, d_poles, d_data, d_cinv, d_out);
     PRSD_CUDA(cudaGetLastError());
     c.launches++;
     c.sync();

@@ -68,6 +68,11 @@ struct GalaxyModel {
     // rsd/transfers/poles.py:8-69 fused behind the assembly: d_k DEVICE [nk], ells host [nell], d_out DEVICE [nw][nell][nk]
     void poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
                int nk, const double* d_k, int nell, const int* ells, int nmu, double* d_out);
+    // chi^2 of every walker against a data vector [nell][nk] with precision matrix [n][n], n = nell nk
+    // (rsdfit/driver.py:780-802); d_poles [nw][nell][nk] receives the model vectors, d_out [nw] the chi^2
+    void chi2(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
+              int nk, const double* d_k, int nell, const int* ells, int nmu, const double* d_data, const double* d_cinv,
+              double* d_poles, double* d_out);
     // diagnostic: the spline knots of P[mu^0,2,4,6] per (walker, pair): host [nw][10][4][nkm]
     void moments_to_host(int nw, double* out);
 };

@@ -44,8 +44,10 @@ def _L():
         L.prsd_galaxy_moments.argtypes = [_vp, i, _dp]
         L.prsd_galaxy_poles.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, i, _ip, i, _dp]
         L.prsd_galaxy_poles_device.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _vp, i, _ip, i, _vp]
+        L.prsd_galaxy_chi2.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, i, _ip, i, _dp, _dp, _dp, _vp]
         for name in ('prsd_galaxy_config_default', 'prsd_galaxy_create', 'prsd_galaxy_destroy', 'prsd_galaxy_power',
-                     'prsd_galaxy_power_device', 'prsd_galaxy_moments', 'prsd_galaxy_poles', 'prsd_galaxy_poles_device'):
+                     'prsd_galaxy_power_device', 'prsd_galaxy_moments', 'prsd_galaxy_poles', 'prsd_galaxy_poles_device',
+                     'prsd_galaxy_chi2'):
             getattr(L, name).restype = i
         L._rsd_sigs = True
     return L
@@ -171,6 +173,26 @@ class PTEngine(object):
         N.check(_L().prsd_galaxy_poles(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
                                        par, stoch, len(k), k, len(ells), ells, int(Nmu), out))
         return out
+
+    def galaxy_chi2(self, gal, spectra, result, par, stoch, k, ells, data, cinv, Nmu=40, cmap=None, return_poles=False):
+        """chi^2 of nw walkers against ``data`` [nell][nk] with precision matrix ``cinv`` (rsdfit/driver.py:780-802)"""
+        par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, NPAR)
+        nw = par.shape[0]
+        stoch = np.ascontiguousarray(stoch, dtype=np.float64).reshape(nw, NPAIR, NSTOCH)
+        k = N.as_f64(k)
+        ells = np.ascontiguousarray(np.atleast_1d(ells), dtype=np.int32)
+        n = len(ells)*len(k)
+        data = np.ascontiguousarray(data, dtype=np.float64).reshape(n)
+        cinv = np.ascontiguousarray(cinv, dtype=np.float64).reshape(n, n)
+        if Nmu % 2 == 0:
+            Nmu += 1
+        chi2 = np.empty(nw)
+        poles = np.empty((nw, len(ells), len(k))) if return_poles else None
+        cm = None if cmap is None else np.ascontiguousarray(cmap, dtype=np.int32)
+        N.check(_L().prsd_galaxy_chi2(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
+                                      par, stoch, len(k), k, len(ells), ells, int(Nmu), data, cinv, chi2,
+                                      None if poles is None else poles.ctypes.data_as(_vp)))
+        return (chi2, poles) if return_poles else chi2
 
     def galaxy_moments(self, gal, nw):
         out = np.empty((nw, NPAIR, 4, gal.nkm))

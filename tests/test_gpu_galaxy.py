@@ -144,3 +144,40 @@ def test_poles_match_simpson_of_the_power_grid(cosmo, engine, oracle):
     assert np.array_equal(model.poles(k, 2, Nmu=11), poles[1])           # scalar ell -> one array
     with pytest.raises(Exception):
         model.poles(np.array([5.0]), [0])           # AP-distorted k outside the model's spline domain
+
+
+def test_chi2_of_an_ensemble(cosmo, engine):
+    """chi^2 = (M - D)^T C^-1 (M - D) per walker (rsdfit/driver.py:780-802), fused behind the multipole kernel"""
+    from pyrsd_b200 import rsd
+    rng = np.random.default_rng(21)
+    sp = engine.spectra(cosmo.GetDiscreteK(), cosmo.GetDiscreteTk(), cosmo.n_s(), cosmo.delta_H()**2, cosmo.h(),
+                        cosmo.Omega0_m(), cosmo.Omega0_b(), cosmo.Tcmb())
+    res = engine.run(sp, result=rsd._new_result())
+    kmodel = np.logspace(-3, np.log10(0.5), 200)
+    gal = engine.galaxy(kmodel, rsd.galaxy_config())
+    ks = rsd.stochasticity_grid(kmodel)
+    nw = 37
+    wpar = np.zeros((nw, rsd.NPAR)); stoch = np.zeros((nw, rsd.NPAIR, rsd.NSTOCH))
+    for i in range(nw):
+        b1 = [1.8 + 0.01*i, 2.7, 2.5, 3.4]
+        b00, b01 = [b2_00(b) for b in b1], [b2_01(b) for b in b1]
+        wpar[i] = rsd.pack_walker(0.6 + 0.002*i, 0.75, 1.0, 1.0, 1.0, b1, 0.10, 0.08, 0.40, 1.0, 4.2, 6.0, 3e4, 9e4, 0., 0., None,
+                                  0.7486, cosmo.sigma8(), [b00, b00, b00, b00, b01, b01])
+        for p, (a, b) in enumerate(rsd.PAIRS):
+            lo, hi = sorted([b1[a], b1[b]])
+            stoch[i, p] = stochasticity(ks, wpar[i, 0], lo, hi)
+    kd = np.linspace(0.02, 0.38, 19)
+    ells = [0, 2, 4]
+    cmap = np.zeros(nw, dtype=np.int32)
+    poles = engine.galaxy_poles(gal, sp, res, wpar, stoch, kd, ells, 40, cmap=cmap)
+    n = 3*len(kd)
+    data = poles[5].ravel()*(1 + 0.01*rng.normal(size=n))
+    A = rng.normal(size=(n, n))
+    cinv = A @ A.T/n + np.eye(n)
+    cinv /= np.outer(np.abs(data), np.abs(data))*1e-4
+    chi2, M = engine.galaxy_chi2(gal, sp, res, wpar, stoch, kd, ells, data, cinv, 40, cmap=cmap, return_poles=True)
+    assert np.array_equal(M, poles)
+    d = poles.reshape(nw, n) - data[None, :]
+    ref = np.einsum('wi,ij,wj->w', d, cinv, d)
+    assert np.allclose(chi2, ref, rtol=1e-12)
+    assert np.argmin(chi2) == 5
