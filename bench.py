@@ -263,7 +263,7 @@ def run_gpu(args):
     # ---- roofline of the mode-coupling operators: algorithmic FP64 flops = declared nodes x
     #      cosmologies x flops per (node, cosmology) of the implemented rule, FMA = 2
     pms, pc = prof
-    FLOP_ML, FLOP_DIAG, FLOP_IK = 105, 21, 83
+    FLOP_ML, FLOP_DIAG, FLOP_IK = 105, 17, 83
     kern = {
         'k_nodal_apply<SpecML>': dict(fam=6, flops=info['nodes_ml_half']*B*FLOP_ML, pipe='fp64 DFMA'),
         'k_nodal_apply<SpecDiag>': dict(fam=7, flops=info['nodes_oneloop']*B*FLOP_DIAG, pipe='fp64 DFMA'),

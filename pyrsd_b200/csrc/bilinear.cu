@@ -216,6 +216,27 @@ void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std:
     ctx.sync();
 }
 
+__global__ void k_fold_column(int64_t n, double* __restrict__ dst, const double* __restrict__ src, double coef)
+{
+    const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = fma(coef, src[i], dst[i]);
+}
+
+void BilinearOp::fold_columns(Context& ctx, int dst, const std::vector<std::pair<int, double>>& terms, int ncol_keep)
+{
+    PRSD_REQUIRE(soa && dst >= 0 && dst < ncol_keep && ncol_keep <= ncol_used, "fold_columns: bad arguments");
+    const int64_t n = geo->n_nodes;
+    for (const auto& t : terms) {
+        PRSD_REQUIRE(t.first >= 0 && t.first < ncol_used && t.first != dst, "fold_columns: bad source column");
+        k_fold_column<<<(unsigned)((n + 255)/256), 256, 0, ctx.stream>>>(n, W.p + (int64_t)dst*n, W.p + (int64_t)t.first*n, t.second);
+        PRSD_CUDA(cudaGetLastError());
+        ctx.launches++;
+    }
+    ncol_used = ncol_keep;
+    ncol = (ncol_used + 7)/8*8;
+    ctx.sync();
+}
+
 // -------------------------------------------------------------------- apply
 // One CTA per (k, tile of 8 rows).  Shared memory:
 //   [ nslots tables (TAB_MPAD doubles each) | PaS[8][max_outer] | mbarrier ]

@@ -56,6 +56,8 @@ struct BilinearOp {
                         // true : W [ncol_used][n_nodes] (one-lane-per-node kernels, nodal.cuh)
     DevBuf<double> W;
     void build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols, bool soa_layout = false);
+    // SoA operators only: column `dst` += sum_i coef_i * column src_i, then keep the first `ncol_keep` columns
+    void fold_columns(Context& ctx, int dst, const std::vector<std::pair<int, double>>& terms, int ncol_keep);
 
     // out[row][k][ncol] (device) = sum_nodes W * TA_row(a) * TB_row(b)
     //   tables   : device pool [ntab][TAB_MPAD]

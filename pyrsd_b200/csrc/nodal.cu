@@ -100,10 +100,11 @@ std::vector<ColSpec> ml_columns()
 }
 
 // ------------------------------------------------------------ one-loop tables
-// slots: P_L of DIAG_R cosmologies; W columns: the operator's 6 kernels; accumulator 6 r + c
+// slots: P_L of DIAG_R cosmologies; W columns: the operator's 4 kernels; accumulator 4 r + c
 static const int DIAG_R = 4;      // measured: 2 cosmologies per CTA at 3 CTAs per SM is slower (1.50 vs 1.22 ms): the node stream is re-read twice as often
 struct SpecDiag {
-    static const int NSLOT = DIAG_R, MINB = DIAG_R == 2 ? 3 : 2, NACC = 6*DIAG_R, NW = 6, NOUT = 6*DIAG_R;
+    static const int NC = 4;      // I00, I01, I11 and P22bar = I23 + 2/3 I32 + 1/5 I33 (combined in W at build time)
+    static const int NSLOT = DIAG_R, MINB = DIAG_R == 2 ? 3 : 2, NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
@@ -111,13 +112,13 @@ struct SpecDiag {
         for (int r = 0; r < DIAG_R; r++) {
             const double pp = pa[r]*pb[r];
 #pragma unroll
-            for (int c = 0; c < 6; c++) acc[6*r + c] = fma(w[c], pp, acc[6*r + c]);
+            for (int c = 0; c < NC; c++) acc[NC*r + c] = fma(w[c], pp, acc[NC*r + c]);
         }
     }
     // out [cosmology][nk][8]
     __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, const double* f)
     {
-        const int r = t/6, c = t - 6*r;
+        const int r = t/NC, c = t - NC*r;
         const int cosmo = tile*DIAG_R + r;
         if (cosmo < g.nrow) g.out[((size_t)cosmo*g.nk + ik)*8 + c] = f[t];
     }

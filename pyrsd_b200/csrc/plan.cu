@@ -68,6 +68,8 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         std::vector<ColSpec> cols;
         for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
         op_1loop.build(c, geo, cols, true);
+        // OneLoopP22Bar only ever needs I23 + 2/3 I32 + 1/5 I33 (OneLoopPS.cpp:164-185): fold the three columns
+        op_1loop.fold_columns(c, 3, {{4, 2.0/3.0}, {5, 1.0/5.0}}, 4);
     }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
     if (!only_oneloop) {
@@ -156,7 +158,7 @@ __global__ void k_oneloop_combine(int ncosmo, const double* __restrict__ op1 /*[
     o[i]               = 2.0*a[0] + 6.0*k*k*j[i]*P;
     o[ONELOOP_N + i]   = 2.0*a[1] + 6.0*k*k*j[ONELOOP_N + i]*P;
     o[2*ONELOOP_N + i] = 2.0*a[2] + 6.0*k*k*j[2*ONELOOP_N + i]*P;
-    o[3*ONELOOP_N + i] = a[3] + (2.0/3.0)*a[4] + (1.0/5.0)*a[5];
+    o[3*ONELOOP_N + i] = a[3];         // I23 + 2/3 I32 + 1/5 I33, combined in the operator (PTPlan ctor)
 }
 
 __global__ void k_pack_ik(int nk, const double* __restrict__ s /*[c][nk][40]*/, double* __restrict__ I, double* __restrict__ K)
