@@ -263,11 +263,11 @@ def run_gpu(args):
     # ---- roofline of the mode-coupling operators: algorithmic FP64 flops = declared nodes x
     #      cosmologies x flops per (node, cosmology) of the implemented rule, FMA = 2
     pms, pc = prof
-    FLOP_ML, FLOP_DIAG, FLOP_IK = 105, 17, 83
+    FLOP_ML, FLOP_DIAG, FLOP_IK = 105, 17, 67
     kern = {
         'k_nodal_apply<SpecML>': dict(fam=6, flops=info['nodes_ml_half']*B*FLOP_ML, pipe='fp64 DFMA'),
         'k_nodal_apply<SpecDiag>': dict(fam=7, flops=info['nodes_oneloop']*B*FLOP_DIAG, pipe='fp64 DFMA'),
-        'k_bilinear_apply<5>': dict(fam=0, flops=info['nodes_ik']*8*((B + 7)//8)*FLOP_IK, pipe='fp64 DMMA m8n8k4'),
+        'k_bilinear_apply<4>': dict(fam=0, flops=info['nodes_ik']*8*((B + 7)//8)*FLOP_IK, pipe='fp64 DMMA m8n8k4'),
     }
     traffic = {}
     try:
@@ -316,7 +316,7 @@ def run_gpu(args):
                      "algorithmic_flops_per_launch": kern[top]['flops'], "kernel_ms_per_launch": kern[top]['ms'],
                      "launches_per_step": kern[top]['launches_per_step'],
                      "flops_per_node_per_cosmology": {"k_nodal_apply<SpecML>": FLOP_ML, "k_nodal_apply<SpecDiag>": FLOP_DIAG,
-                                                      "k_bilinear_apply<5>": FLOP_IK},
+                                                      "k_bilinear_apply<4>": FLOP_IK},
                      "nodes": {"imn_oneloop": info['nodes_ml_half'], "oneloop_tables": info['nodes_oneloop'], "ik": info['nodes_ik']},
                      "other_kernels": {k: {"achieved": v['achieved'], "frac": (v['achieved']/(peak_dmma if 'DMMA' in v['pipe'] else peak_dfma))
                                            if v['achieved'] else None, "ms_per_launch": v['ms'], "traffic": traffic.get(k)}

@@ -49,7 +49,6 @@ void PTResult::ensure(int ncosmo_, int nk_)
 static const double INV8PI2 = 1.0/(8.0*M_PI*M_PI);
 static const double INV4PI2 = 1.0/(4.0*M_PI*M_PI);
 static const int J_IDS[6] = {0, 1, 2, 3, 4, 6};                    // J00 J01 J02 J10 J11 J20 -> 3m+n
-static const int NONSYM[8] = {KID_F03, KID_F10, KID_F13, KID_F22, KID_F30, KID_F31, KID_K11, KID_K11S};
 static const int ML_KID[N_ML] = {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33};
 
 PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l)
@@ -75,9 +74,10 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     if (!only_oneloop) {
         auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid, 4);     // DMMA lane layout: 4 nodes per k-step
         std::vector<ColSpec> cols;
-        for (int id = 0; id < 16; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
-        for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, +1, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
-        for (int id : NONSYM) cols.push_back({id, -1, id < 16 ? INV8PI2 : 0.5*INV4PI2});
+        // both spectra are P_L here, so P(a) P(b) is the same on the two halves of the v domain and the
+        // non-symmetric kernels simply use f(u, v) + f(u, -v) (ColSpec sign 0): 29 columns, 4 n-tiles
+        for (int id = 0; id < 16; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
+        for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
         op_ik.build(c, geo, cols);
     }
     // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
@@ -161,16 +161,14 @@ __global__ void k_oneloop_combine(int ncosmo, const double* __restrict__ op1 /*[
     o[3*ONELOOP_N + i] = a[3];         // I23 + 2/3 I32 + 1/5 I33, combined in the operator (PTPlan ctor)
 }
 
-__global__ void k_pack_ik(int nk, const double* __restrict__ s /*[c][nk][40]*/, double* __restrict__ I, double* __restrict__ K)
+__global__ void k_pack_ik(int nk, const double* __restrict__ s /*[c][nk][32]*/, double* __restrict__ I, double* __restrict__ K)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
     if (i >= nk) return;
-    const double* r = s + ((size_t)c*nk + i)*40;
+    const double* r = s + ((size_t)c*nk + i)*32;
     double v[29];
 #pragma unroll
     for (int j = 0; j < 29; j++) v[j] = r[j];
-    v[KID_F03] += r[29]; v[KID_F10] += r[30]; v[KID_F13] += r[31]; v[KID_F22] += r[32];
-    v[KID_F30] += r[33]; v[KID_F31] += r[34]; v[KID_K11] += r[35]; v[KID_K11S] += r[36];
 #pragma unroll
     for (int j = 0; j < 16; j++) I[((size_t)c*16 + j)*nk + i] = v[j];
 #pragma unroll
@@ -265,7 +263,7 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
     d_tab22.upload(tab22, s);
 
     // ---- stage B: I_mn, K_mn
-    s_ik.ensure((size_t)ntile*8*nk*40);
+    s_ik.ensure((size_t)ntile*8*nk*32);
     op_ik.apply(c, sp.tables.p, s_slot.p, s_rowA.p, s_rowA.p, ntile, s_ik.p);
     {
         dim3 g((nk + 127)/128, nc);
