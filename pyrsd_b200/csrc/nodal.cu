@@ -225,12 +225,16 @@ k_nodal_apply(const NodalArgs g)
             }
             Spec::accumulate(acc, pa, pb, w);
         }
-        // ---- reduce over the CTA
+        // ---- reduce over the CTA.  Across the warp: one FP64 tensor MMA with A = 1 adds the four lanes of every
+        // quad (B[k][n] = value of lane 4 n + k, D[m][n] = sum_k B[k][n]: lane l receives the sums of quads
+        // 2 (l % 4) and 2 (l % 4) + 1), two shuffles add the four pairs -- 4 shuffles instead of 10 per accumulator.
 #pragma unroll
         for (int i = 0; i < Spec::NACC; i++) {
-            double v = acc[i];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            double c0 = 0.0, c1 = 0.0;
+            dmma_m8n8k4(c0, c1, 1.0, acc[i]);
+            double v = c0 + c1;
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
             if (lane == 0) red[warp*Spec::NACC + i] = v;
         }
         __syncthreads();
