@@ -72,21 +72,17 @@ struct SpecML {
         acc[17] = fma(ws[4], vv, acc[17]);
         acc[18] = fma(ws[5], vv, acc[18]);
     }
-    // out [c][7][3][nk]; t = output index 0..20 = 3 m + part
-    __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, const double* f)
+    // out [c][7][3][nk]; t = output index 0..20 = 3 m + part; every output is one accumulator (x 2 for the cross
+    // parts of the equal-spectra drivers).  The reference evaluates the LINEAR and ONE-LOOP parts of (m, n) = (3, 2)
+    // with the f23 kernel (ImnOneLoop.cpp:108-109, 199-200) and only the cross part with f32 (:160-165); as is.
+    __device__ __forceinline__ static int source(int t, double& fac)
     {
-        // The reference evaluates the LINEAR and ONE-LOOP parts of (m, n) = (3, 2) with the f23 kernel
-        // (ImnOneLoop.cpp:108-109, 199-200) and only the cross part with f32 (:160-165); reproduced as is.
-        double v;
-        switch (t) {
-            case 0: v = f[0]; break;  case 1: v = f[6]; break;       case 2: v = f[8]; break;
-            case 3: v = f[1]; break;  case 4: v = f[7]; break;       case 5: v = f[9]; break;
-            case 6: v = f[2]; break;  case 7: v = 2.0*f[10]; break;  case 8: v = f[12]; break;
-            case 9: v = f[3]; break;  case 10: v = 2.0*f[11]; break; case 11: v = f[13]; break;
-            case 12: v = f[4]; break; case 13: v = 2.0*f[14]; break; case 14: v = f[17]; break;
-            case 15: v = f[4]; break; case 16: v = 2.0*f[15]; break; case 17: v = f[17]; break;
-            case 18: v = f[5]; break; case 19: v = 2.0*f[16]; break; default: v = f[18]; break;
-        }
+        const int src[21] = {0, 6, 8,  1, 7, 9,  2, 10, 12,  3, 11, 13,  4, 14, 17,  4, 15, 17,  5, 16, 18};
+        fac = (t >= 6 && t % 3 == 1) ? 2.0 : 1.0;
+        return src[t];
+    }
+    __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, double v)
+    {
         g.out[((size_t)tile*21 + t)*g.nk + ik] = v;
     }
 };
@@ -115,12 +111,13 @@ struct SpecDiag {
             for (int c = 0; c < NC; c++) acc[NC*r + c] = fma(w[c], pp, acc[NC*r + c]);
         }
     }
+    __device__ __forceinline__ static int source(int t, double& fac) { fac = 1.0; return t; }
     // out [cosmology][nk][8]
-    __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, const double* f)
+    __device__ __forceinline__ static void store(const NodalArgs& g, int tile, int ik, int t, double v)
     {
         const int r = t/NC, c = t - NC*r;
         const int cosmo = tile*DIAG_R + r;
-        if (cosmo < g.nrow) g.out[((size_t)cosmo*g.nk + ik)*8 + c] = f[t];
+        if (cosmo < g.nrow) g.out[((size_t)cosmo*g.nk + ik)*8 + c] = v;
     }
 };
 
@@ -238,15 +235,15 @@ k_nodal_apply(const NodalArgs g)
             if (lane == 0) red[warp*Spec::NACC + i] = v;
         }
         __syncthreads();
-        if (tid < Spec::NACC) {
+        if (tid < Spec::NOUT) {
+            double fac;
+            const int src = Spec::source(tid, fac);
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NL_WARPS; w++) s += red[w*Spec::NACC + tid];
-            fin[tid] = s;
+            for (int w = 0; w < NL_WARPS; w++) s += red[w*Spec::NACC + src];
+            Spec::store(g, tile, ik, tid, fac*s);
         }
-        __syncthreads();
-        if (tid < Spec::NOUT) Spec::store(g, tile, ik, tid, fin);
-        // the next k's PaS writes are ordered after this k's reads by the two barriers above
+        // the next k's writes of PaS and red are ordered after this k's reads by the barrier after the next P(a) pass
     }
 }
 
