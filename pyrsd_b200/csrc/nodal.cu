@@ -155,26 +155,21 @@ k_nodal_apply(const NodalArgs g)
     }
     mbar_wait(mbar, 0);
 
-    for (int ik = blockIdx.y; ik < g.nk; ik += k_stride) {
-        // ---- P(a) of the four spectra for every outer node of this k
-        const int64_t o0 = g.outer_off[ik];
-        const int n_out = (int)(g.outer_off[ik + 1] - o0);
-        for (int o = tid; o < n_out; o += NL_THREADS) {
-            const int j0 = g.a_j0[o0 + o];
-            const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)));
-            const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)) + 1);
-#pragma unroll
-            for (int s = 0; s < Spec::NSLOT; s++) {
-                const double* t = tabs + s*TAB_MPAD + j0;
-                PaS[s*g.max_outer + o] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
-            }
+    // the offsets of the NEXT k of this CTA are fetched during the current one, and the first node of a k is
+    // requested before the P(a) pass: the k loop starts without a chain of exposed L2 round trips
+    int ik = blockIdx.y;
+    int64_t o0_next = 0, o1_next = 0, n0_next = 0, n1_next = 0;
+    if (ik < g.nk) {
+        o0_next = g.outer_off[ik]; o1_next = g.outer_off[ik + 1];
+        n0_next = g.node_off[ik];  n1_next = g.node_off[ik + 1];
+    }
+    for (; ik < g.nk; ik += k_stride) {
+        const int64_t o0 = o0_next, n0 = n0_next, n1 = n1_next;
+        const int n_out = (int)(o1_next - o0);
+        if (ik + k_stride < g.nk) {
+            o0_next = g.outer_off[ik + k_stride]; o1_next = g.outer_off[ik + k_stride + 1];
+            n0_next = g.node_off[ik + k_stride];  n1_next = g.node_off[ik + k_stride + 1];
         }
-        __syncthreads();
-
-        double acc[Spec::NACC];
-#pragma unroll
-        for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
-        const int64_t n0 = g.node_off[ik], n1 = g.node_off[ik + 1];
         // the index word and the coefficients of the NEXT node of this lane are loaded one iteration ahead: the
         // shared-memory reads depend on them, and an exposed L2 round trip per node was the largest stall
         int64_t node = n0 + tid;
@@ -190,6 +185,22 @@ k_nodal_apply(const NodalArgs g)
                 for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
             }
         }
+        // ---- P(a) of the four spectra for every outer node of this k
+        for (int o = tid; o < n_out; o += NL_THREADS) {
+            const int j0 = g.a_j0[o0 + o];
+            const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)));
+            const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)) + 1);
+#pragma unroll
+            for (int s = 0; s < Spec::NSLOT; s++) {
+                const double* t = tabs + s*TAB_MPAD + j0;
+                PaS[s*g.max_outer + o] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
+            }
+        }
+        __syncthreads();
+
+        double acc[Spec::NACC];
+#pragma unroll
+        for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
         for (; node < n1; node += NL_THREADS) {
             const int pk = pk_next;
             const double2 c01 = c01_next, c23 = c23_next;
