@@ -52,63 +52,76 @@ void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs)
 
 // ---------------------------------------------------------------- apply
 // out[row][o] = sum_j T[row][j] Omega[o][j] is a (rows x knots) . (knots x outputs) product: FP64 tensor-core MMAs
-// (DMMA m8n8k4).  One CTA owns 8 outputs x 32 rows; its 8 warps split the knots, so every warp streams a
+// (DMMA m8n8k4).  One CTA owns 16 outputs x 32 rows; its 8 warps split the knots, so every warp streams a
 // contiguous 1/8 of 8 Omega rows and of 32 table rows with 16-byte loads (each lane's two values feed two
 // consecutive k-steps: the order of the knots inside a sum is free as long as both operands agree), and a
 // shared-memory pass adds the eight partial tiles.  Omega, the large operand, is read once per 32 rows.
-static const int LA_MT = 4;
+static const int LA_MT = 4;                            // row tiles (of 8) per CTA
+static const int LA_NT = 2;                            // output tiles (of 8) per CTA
 static const int LA_JS = ((TAB_MPAD + 63)/64)*8;      // knots per warp, a multiple of 8
 
 __global__ void __launch_bounds__(256)
 k_linear_apply(int nout, int nrow, const double* __restrict__ Omega, const double* __restrict__ tables,
                const int* __restrict__ tab_index, double* __restrict__ out)
 {
-    __shared__ double red[8][LA_MT][64];
+    __shared__ double red[8][LA_NT*LA_MT][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int o0 = blockIdx.x*8;
+    const int o0 = blockIdx.x*(8*LA_NT);
     const int r0 = blockIdx.y*(8*LA_MT);
     const int sub = lane & 3, grp = lane >> 2;
-    const double* bp = Omega + (size_t)min(o0 + grp, nout - 1)*TAB_MPAD;
+    const double* bp[LA_NT];
+#pragma unroll
+    for (int n = 0; n < LA_NT; n++) bp[n] = Omega + (size_t)min(o0 + 8*n + grp, nout - 1)*TAB_MPAD;
     const double* ap[LA_MT];
 #pragma unroll
     for (int m = 0; m < LA_MT; m++) ap[m] = tables + (size_t)tab_index[min(r0 + 8*m + grp, nrow - 1)]*TAB_MPAD;
-    double acc[LA_MT][2];
+    double acc[LA_NT][LA_MT][2];
 #pragma unroll
-    for (int m = 0; m < LA_MT; m++) acc[m][0] = acc[m][1] = 0.0;
+    for (int n = 0; n < LA_NT; n++)
+#pragma unroll
+        for (int m = 0; m < LA_MT; m++) acc[n][m][0] = acc[n][m][1] = 0.0;
     const int j_lo = warp*LA_JS, j_hi = min(j_lo + LA_JS, TAB_MPAD);
-#pragma unroll 4
+#pragma unroll 2
     for (int j = j_lo; j < j_hi; j += 8) {
         const int idx = j + 2*sub;
-        double2 b = make_double2(0.0, 0.0), a[LA_MT];
         const bool ok = idx < TAB_MPAD;
-        if (ok) b = __ldg(reinterpret_cast<const double2*>(bp + idx));
+        double2 b[LA_NT], a[LA_MT];
+#pragma unroll
+        for (int n = 0; n < LA_NT; n++) b[n] = ok ? __ldg(reinterpret_cast<const double2*>(bp[n] + idx)) : make_double2(0.0, 0.0);
 #pragma unroll
         for (int m = 0; m < LA_MT; m++) a[m] = ok ? __ldg(reinterpret_cast<const double2*>(ap[m] + idx)) : make_double2(0.0, 0.0);
 #pragma unroll
+        for (int n = 0; n < LA_NT; n++)
+#pragma unroll
+            for (int m = 0; m < LA_MT; m++) {
+                dmma_m8n8k4(acc[n][m][0], acc[n][m][1], a[m].x, b[n].x);
+                dmma_m8n8k4(acc[n][m][0], acc[n][m][1], a[m].y, b[n].y);
+            }
+    }
+#pragma unroll
+    for (int n = 0; n < LA_NT; n++)
+#pragma unroll
         for (int m = 0; m < LA_MT; m++) {
-            dmma_m8n8k4(acc[m][0], acc[m][1], a[m].x, b.x);
-            dmma_m8n8k4(acc[m][0], acc[m][1], a[m].y, b.y);
+            red[warp][n*LA_MT + m][grp*8 + 2*sub] = acc[n][m][0];
+            red[warp][n*LA_MT + m][grp*8 + 2*sub + 1] = acc[n][m][1];
         }
-    }
-#pragma unroll
-    for (int m = 0; m < LA_MT; m++) {
-        red[warp][m][grp*8 + 2*sub] = acc[m][0];
-        red[warp][m][grp*8 + 2*sub + 1] = acc[m][1];
-    }
     __syncthreads();
-    // 256 threads = 4 row tiles x 64 tile elements
-    const int m = threadIdx.x >> 6, e = threadIdx.x & 63;
-    double v = 0.0;
+    // 64 elements per tile, LA_NT x LA_MT tiles
+    for (int idx = threadIdx.x; idx < LA_NT*LA_MT*64; idx += 256) {
+        const int t = idx >> 6, e = idx & 63;
+        const int n = t/LA_MT, m = t - n*LA_MT;
+        double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) v += red[w][m][e];
-    const int row = r0 + 8*m + (e >> 3), col = o0 + (e & 7);
-    if (row < nrow && col < nout) out[(size_t)row*nout + col] = v;
+        for (int w = 0; w < 8; w++) v += red[w][t][e];
+        const int row = r0 + 8*m + (e >> 3), col = o0 + 8*n + (e & 7);
+        if (row < nrow && col < nout) out[(size_t)row*nout + col] = v;
+    }
 }
 
 void LinearOp::apply(Context& ctx, const double* tables, const int* tab_index, int nrow, double* out) const
 {
     static_assert(TAB_MPAD % 2 == 0, "table rows must be 16-byte multiples");
-    dim3 grid((nout + 7)/8, (nrow + 8*LA_MT - 1)/(8*LA_MT));
+    dim3 grid((nout + 8*LA_NT - 1)/(8*LA_NT), (nrow + 8*LA_MT - 1)/(8*LA_MT));
     ProfScope prof(ctx, PROF_LINEAR);
     k_linear_apply<<<grid, 256, 0, ctx.stream>>>(nout, nrow, Omega.p, tables, tab_index, out);
     PRSD_CUDA(cudaGetLastError());
