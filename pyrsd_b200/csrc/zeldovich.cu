@@ -137,6 +137,12 @@ k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __res
         const double r = rr[l];
         const double r15 = r*sqrt(r);
         const double kr = k/r;
+        // n G_n and n^2 G_n are walker independent: formed once per r
+        double g1[16], g2[16];
+        if (!ONLY00) {
+#pragma unroll
+            for (int n = 1; n < 16; n++) { g1[n] = (double)n*gl[n]; g2[n] = (double)(n*n)*gl[n]; }
+        }
 #pragma unroll
         for (int j = 0; j < ZW; j++) {
             const int c = s_c[j];
@@ -169,8 +175,8 @@ k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __res
 #pragma unroll
             for (int n = ZEL_NMAX; n >= 1; n--) {
                 S0 = fma(S0, rho, gl[n]);
-                S1 = fma(S1, rho, (double)n*gl[n]);
-                S2 = fma(S2, rho, (double)(n*n)*gl[n]);
+                S1 = fma(S1, rho, g1[n]);
+                S2 = fma(S2, rho, g2[n]);
             }
             S0 *= pre; S1 *= pre; S2 *= pre;
             a00 += S0;
