@@ -396,13 +396,16 @@ __global__ void k_gal_groups(int nkm, const double* __restrict__ par, const doub
                                   (1.0 - fcB)*(1.0 - fsB), (1.0 - fcB)*fsB, fcB*(1.0 - fsB), fcB*fsB,
                                   (1.0 - fsB)*(1.0 - fsB), 2.0*fsB*(1.0 - fsB), fsB*fsB};
     const int grp[GAL_NPAIR] = {0, 0, 0, 1, 2, 1, 2, 3, 4, 5};
+    // pairspl [w][pair][moment][Y | b | c | d][nkm]  ->  grpspl [w][knot][group][moment][Y b c d]: the 96 numbers a
+    // (k, mu) point needs are contiguous, addressed from one base pointer with constant offsets
     const int n = 16*nkm;
     for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
+        const int mc = idx/nkm, i = idx - mc*nkm;          // mc = 4 moment + coefficient
         double acc[GAL_NGRP] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int pr = 0; pr < GAL_NPAIR; pr++) acc[grp[pr]] += wt[pr]*pairspl[((size_t)w*GAL_NPAIR + pr)*n + idx];
 #pragma unroll
-        for (int g = 0; g < GAL_NGRP; g++) grpspl[((size_t)w*GAL_NGRP + g)*n + idx] = acc[g];
+        for (int g = 0; g < GAL_NGRP; g++) grpspl[(((size_t)w*nkm + i)*GAL_NGRP + g)*16 + mc] = acc[g];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double* c = grpconst + (size_t)w*GAL_NCONST;
@@ -423,7 +426,7 @@ __global__ void k_gal_groups(int nkm, const double* __restrict__ par, const doub
 
 // P_gal(k_obs, mu_obs) of walker parameters p from its group splines
 __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* __restrict__ km, const double* __restrict__ p,
-                                                 const double* __restrict__ gs /*[6][16][nkm]*/, const double* __restrict__ gc,
+                                                 const double* __restrict__ gs /*[nkm][6][4][4]*/, const double* __restrict__ gc,
                                                  double kobs, double muobs)
 {
     const int nkm = G.nkm;
@@ -459,12 +462,14 @@ __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* 
     } else {
         Gc = fog(fm, kmu*p[W_SIGC]); GsA = fog(fm, kmu*p[W_SIGSA]); GsB = fog(fm, kmu*p[W_SIGSB]);
     }
+    const double* knot = gs + (size_t)i*(GAL_NGRP*16);
     auto grp = [&](int g) {
-        const double* s = gs + (size_t)g*16*nkm + i;
+        const double2* q = reinterpret_cast<const double2*>(knot + g*16);
         double tot = gc[g], mpow = 1.0;
+#pragma unroll 4
         for (int m = 0; m < nmom; m++) {
-            const double* q = s + (size_t)m*4*nkm;
-            tot += mpow*(q[0] + t*(q[nkm] + t*(q[2*nkm] + t*q[3*nkm])));
+            const double2 yb = __ldg(q + 2*m), cd = __ldg(q + 2*m + 1);
+            tot += mpow*(yb.x + t*(yb.y + t*(cd.x + t*cd.y)));
             mpow *= mu2;
         }
         return tot;
