@@ -18,30 +18,31 @@ namespace prsd {
 __device__ __forceinline__ void pcr_solve(int nsys, int n, double* a, double* b, double* c, double* d,
                                           double* a2, double* b2, double* c2, double* d2, double* x)
 {
-    const int tid = threadIdx.x, nt = blockDim.x, tot = nsys*n;
-    for (int g = tid; g < tot; g += nt) {
-        const int i = g % n;
-        if (i == 0) a[g] = 0.0;
-        if (i == n - 1) c[g] = 0.0;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int sy = 0; sy < nsys; sy++) {
+        if (tid == 0) { a[sy*n] = 0.0; c[sy*n + n - 1] = 0.0; }
     }
     __syncthreads();
     for (int s = 1; s < n; s <<= 1) {
-        for (int g = tid; g < tot; g += nt) {
-            const int i = g % n;
-            double aa = 0.0, cc = 0.0, bb = b[g], dd = d[g];
-            if (i - s >= 0) {
-                const double al = -a[g]/b[g - s];
-                aa = al*a[g - s];
-                bb = fma(al, c[g - s], bb);
-                dd = fma(al, d[g - s], dd);
+        for (int sy = 0; sy < nsys; sy++) {
+            const int off = sy*n;
+            for (int i = tid; i < n; i += nt) {
+                const int g = off + i;
+                double aa = 0.0, cc = 0.0, bb = b[g], dd = d[g];
+                if (i - s >= 0) {
+                    const double al = -a[g]/b[g - s];
+                    aa = al*a[g - s];
+                    bb = fma(al, c[g - s], bb);
+                    dd = fma(al, d[g - s], dd);
+                }
+                if (i + s < n) {
+                    const double ga = -c[g]/b[g + s];
+                    cc = ga*c[g + s];
+                    bb = fma(ga, a[g + s], bb);
+                    dd = fma(ga, d[g + s], dd);
+                }
+                a2[g] = aa; b2[g] = bb; c2[g] = cc; d2[g] = dd;
             }
-            if (i + s < n) {
-                const double ga = -c[g]/b[g + s];
-                cc = ga*c[g + s];
-                bb = fma(ga, a[g + s], bb);
-                dd = fma(ga, d[g + s], dd);
-            }
-            a2[g] = aa; b2[g] = bb; c2[g] = cc; d2[g] = dd;
         }
         __syncthreads();
         double* t;
@@ -50,7 +51,7 @@ __device__ __forceinline__ void pcr_solve(int nsys, int n, double* a, double* b,
         t = c; c = c2; c2 = t;
         t = d; d = d2; d2 = t;
     }
-    for (int g = tid; g < tot; g += nt) x[g] = d[g]/b[g];
+    for (int g = tid; g < nsys*n; g += nt) x[g] = d[g]/b[g];
     __syncthreads();
 }
 
