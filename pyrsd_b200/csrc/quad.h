@@ -39,10 +39,10 @@ struct QuadConfig {
     double ln_thin  = 0.2;    // inner panels narrower than this in ln b use n_thin points: far from q ~ k the
                               // strip |q - r| <= k is thin and the integrand nearly polynomial across it
     // I_mn, K_mn and the one-loop tables (q_max = 1e5)
-    QuadTier tier[4]    = {{0.02, 6, 4, 3}, {0.08, 8, 5, 4}, {0.3, 10, 7, 5}, {1e30, 12, 7, 5}};
+    QuadTier tier[4]    = {{0.02, 5, 4, 3}, {0.08, 6, 5, 4}, {0.3, 8, 6, 5}, {1e30, 12, 7, 5}};
     // ImnOneLoop (q_max = 10): the one-loop spectra are large at the hard cut and the h02-type kernels cancel to
     // leading order across v, so above k = 0.06 that operator keeps full-order panels everywhere
-    QuadTier ml_tier[4] = {{0.02, 6, 4, 3}, {0.06, 8, 5, 4}, {0.3, 10, 7, 7}, {1e30, 10, 8, 8}};
+    QuadTier ml_tier[4] = {{0.02, 4, 4, 3}, {0.06, 6, 5, 4}, {0.3, 10, 7, 7}, {1e30, 10, 8, 8}};
 
     const QuadTier& tier_of(double k) const
     {
