@@ -15,6 +15,7 @@ struct Pool {
     std::unordered_map<void*, Block> live;                     // every block handed out
     std::multimap<std::pair<int, size_t>, void*> ready;        // (device, bytes) -> reusable blocks
     std::vector<std::pair<void*, Block>> pending;              // freed, but work using them may be in flight
+    size_t cached_bytes = 0;                                   // bytes held in `ready` + `pending`
     bool closed = false;                                       // set at static destruction: leak instead of touching CUDA
     ~Pool() { closed = true; }
 };
@@ -35,6 +36,7 @@ void* pool_alloc(size_t bytes)
         if (it != P.ready.end() && it->first.first == dev && it->first.second <= want + want/4) {
             void* p = it->second;
             P.live[p] = {it->first.second, dev};
+            P.cached_bytes -= it->first.second;
             P.ready.erase(it);
             return p;
         }
@@ -58,7 +60,7 @@ void* pool_alloc(size_t bytes)
         // out of memory: return the cache to the driver and retry once
         cudaGetLastError();
         cudaDeviceSynchronize();
-        for (auto& r : P.ready) cudaFree(r.second);
+        for (auto& r : P.ready) { cudaFree(r.second); P.cached_bytes -= r.first.second; }
         P.ready.clear();
         e = cudaMalloc(&p, want);
     }
@@ -75,7 +77,14 @@ void pool_free(void* p) noexcept
     auto it = P.live.find(p);
     if (it == P.live.end()) return;
     P.pending.push_back({p, it->second});
+    P.cached_bytes += it->second.bytes;
     P.live.erase(it);
+    // bound the cache (varying batch sizes would otherwise accumulate blocks of every size ever used)
+    static const size_t CACHE_LIMIT = size_t(24) << 30;
+    if (P.cached_bytes > CACHE_LIMIT) {
+        for (auto& r : P.ready) { cudaFree(r.second); P.cached_bytes -= r.first.second; }
+        P.ready.clear();
+    }
 }
 
 void pool_trim() noexcept
@@ -86,6 +95,7 @@ void pool_trim() noexcept
     for (auto& r : P.ready) cudaFree(r.second);
     P.pending.clear();
     P.ready.clear();
+    P.cached_bytes = 0;
 }
 
 Context::Context(int dev) : device(dev)
