@@ -97,10 +97,10 @@ std::vector<ColSpec> ml_columns()
 
 // ------------------------------------------------------------ one-loop tables
 // slots: P_L of DIAG_R cosmologies; W columns: the operator's 4 kernels; accumulator 4 r + c
-static const int DIAG_R = 4;      // measured: 2 cosmologies per CTA at 3 CTAs per SM is slower (1.50 vs 1.22 ms): the node stream is re-read twice as often
+static const int DIAG_R = 4;      // measured at batch 256: R = 4 (2 CTAs per SM) 1.71 ms, R = 3 (3 CTAs) 1.86 ms, R = 2 (3 CTAs) +23 %
 struct SpecDiag {
     static const int NC = 4;      // I00, I01, I11 and P22bar = I23 + 2/3 I32 + 1/5 I33 (combined in W at build time)
-    static const int NSLOT = DIAG_R, MINB = DIAG_R == 2 ? 3 : 2, NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
+    static const int NSLOT = DIAG_R, MINB = DIAG_R <= 3 ? 3 : 2, NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
@@ -288,6 +288,8 @@ void nodal_apply_ml(Context& ctx, const BilinearOp& op, const double* tables, co
 {
     launch_nodal<SpecML>(ctx, op, tables, slot_tab, ncosmo, ncosmo, 8, out, PROF_NODAL_ML);
 }
+
+int nodal_diag_rows() { return DIAG_R; }
 
 void nodal_apply_diag(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo, double* out)
 {

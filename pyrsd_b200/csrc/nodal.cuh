@@ -27,7 +27,9 @@ std::vector<ColSpec> ml_columns();
 void nodal_apply_ml(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo,
                     double* out);
 
-// out[c][nk][8] (columns = the operator's 6 kernels), slot_tab [ntiles][4] = P_L table of 4 cosmologies
+// out[c][nk][8] (columns = the operator's kernels); slot_tab [ntiles][R] = P_L table of the R = nodal_diag_rows()
+// cosmologies of every tile, ntiles = ceil(ncosmo / R) (pad the last tile with any valid table)
+int nodal_diag_rows();
 void nodal_apply_diag(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ncosmo,
                       double* out);
 

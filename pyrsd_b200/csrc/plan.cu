@@ -226,9 +226,15 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res)
     DevBuf<int> d_tabL;
     d_tabL.upload(tabL, s);
 
-    // ---- stage A: one-loop tables (tiles of 4 cosmologies; s_slot is laid out [.][8] = two such tiles)
+    // ---- stage A: one-loop tables (tiles of nodal_diag_rows() cosmologies)
+    {
+        const int R = nodal_diag_rows(), nt = (nc + R - 1)/R;
+        std::vector<int> dslot((size_t)nt*R);
+        for (int i = 0; i < nt*R; i++) dslot[i] = sp.table_index(std::min(i, nc - 1), SP_LIN);
+        s_rowB.upload(dslot, s);
+    }
     s_op1.ensure((size_t)ntile*8*ONELOOP_N*8);
-    nodal_apply_diag(c, op_1loop, sp.tables.p, s_slot.p, nc, s_op1.p);
+    nodal_apply_diag(c, op_1loop, sp.tables.p, s_rowB.p, nc, s_op1.p);
     s_lin1.ensure((size_t)nc*3*ONELOOP_N);
     lin_1loop.apply(c, sp.tables.p, d_tabL.p, nc, s_lin1.p);
     s_plk.ensure((size_t)nc*ONELOOP_N);
