@@ -144,6 +144,165 @@ k_fftlog_pow2(int N, int logN, int batch, double q, double dlnr, double lnkr,
     }
 }
 
+// ------------------------------------------------- register-tiled kernel (N = 1024 .. 8192)
+// Stockham autosort FFT with 16 complex values per thread: every pass is a radix-16 (8, 4, 2 for the remainder)
+// butterfly in registers, so N = 4096 needs 3 + 3 shared-memory exchanges instead of the 12 + 12 passes of the
+// radix-2 kernel above.  One CTA of N/16 threads transforms two real sequences packed as one complex one;
+// twiddles exp(-2 pi i j / N), j < N/2, come from a table built once per plan.
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x); }
+
+// (tr + i ti) * exp(SIGN 2 pi i e / 16), e = 0 .. 7 known at compile time after unrolling
+template <int SIGN>
+__device__ __forceinline__ double2 mul_w16(double tr, double ti, int e)
+{
+    const double C[8] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
+                         0.0, -0.38268343236508977, -0.70710678118654752, -0.92387953251128674};
+    const double S[8] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674,
+                         1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977};
+    if (e == 0) return make_double2(tr, ti);
+    if (e == 4) return SIGN < 0 ? make_double2(ti, -tr) : make_double2(-ti, tr);
+    const double c = C[e], sn = SIGN*S[e];
+    return make_double2(tr*c - ti*sn, tr*sn + ti*c);
+}
+
+// in-register DFT of R = 2, 4, 8, 16 values, natural order in and out; SIGN = -1 forward, +1 inverse
+template <int R, int SIGN>
+__device__ __forceinline__ void dft_regs(double2* v)
+{
+#pragma unroll
+    for (int len = R; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int b = 0; b < R; b += len) {
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                const double2 u = v[b + j], w = v[b + j + half];
+                v[b + j] = make_double2(u.x + w.x, u.y + w.y);
+                v[b + j + half] = mul_w16<SIGN>(u.x - w.x, u.y - w.y, j*(16/len));
+            }
+        }
+    }
+    // decimation in frequency leaves bit-reversed order
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        int rev = 0;
+#pragma unroll
+        for (int bit = 1, t = i; bit < R; bit <<= 1, t >>= 1) rev = (rev << 1) | (t & 1);
+        if (i < rev) { const double2 tmp = v[i]; v[i] = v[rev]; v[rev] = tmp; }
+    }
+}
+
+// shared-memory index with one pad element per 16: the radix-16 scatter of the first pass (positions 16 t + r)
+// and the stride-N/16 gathers then fall on distinct banks
+__device__ __forceinline__ int zpad(int i) { return i + (i >> 4); }
+
+// one Stockham pass of radix R over z[N] (in place through registers); Ns = product of the previous radices
+template <int R, int SIGN>
+__device__ __forceinline__ void fft_pass(double2* __restrict__ z, const double2* __restrict__ tw, int N, int Ns)
+{
+    constexpr int ITEMS = 16/R;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int stride = N/R;
+    const int tunit = N/(Ns*R);
+    double2 v[16];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const int j = tid + it*nthr;
+        const int k = j & (Ns - 1);
+#pragma unroll
+        for (int r = 0; r < R; r++) v[it*R + r] = z[zpad(j + r*stride)];
+        if (Ns > 1) {
+            // twiddles exp(SIGN 2 pi i r k / (Ns R)), r = 1 .. R-1: one table read, the powers by multiplication
+            // (depth <= 4 products: a few ulp)
+            double2 w[R];
+            const int idx = k*tunit;                 // < N/R <= N/2
+            w[1] = tw[idx];
+            if (SIGN > 0) w[1].y = -w[1].y;
+#pragma unroll
+            for (int r = 2; r < R; r++) {
+                // r = 2^p: square of r/2; otherwise (highest power of two below r) x (remainder)
+                int hp = 1;
+                while (hp*2 <= r) hp *= 2;
+                w[r] = (hp == r) ? cmul(w[r/2], w[r/2]) : cmul(w[hp], w[r - hp]);
+            }
+#pragma unroll
+            for (int r = 1; r < R; r++) v[it*R + r] = cmul(v[it*R + r], w[r]);
+        }
+        dft_regs<R, SIGN>(v + it*R);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const int j = tid + it*nthr;
+        const int k = j & (Ns - 1);
+        const int j0 = (j - k)*R + k;
+#pragma unroll
+        for (int r = 0; r < R; r++) z[zpad(j0 + r*Ns)] = v[it*R + r];
+    }
+    __syncthreads();
+}
+
+template <int SIGN>
+__device__ __forceinline__ void fft_all(double2* z, const double2* tw, int N, int r0, int r1, int r2, int r3)
+{
+    int Ns = 1;
+    const int rad[4] = {r0, r1, r2, r3};
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const int R = rad[s];
+        if (R == 16) fft_pass<16, SIGN>(z, tw, N, Ns);
+        else if (R == 8) fft_pass<8, SIGN>(z, tw, N, Ns);
+        else if (R == 4) fft_pass<4, SIGN>(z, tw, N, Ns);
+        else if (R == 2) fft_pass<2, SIGN>(z, tw, N, Ns);
+        Ns *= (R > 0 ? R : 1);
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int batch, double q, double dlnr, double lnkr,
+             const double* __restrict__ ure, const double* __restrict__ uim, const double2* __restrict__ twg,
+             const double* __restrict__ in, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw3[];
+    double2* z = reinterpret_cast<double2*>(smem_raw3);
+    double2* tw = z + N + N/16;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b0 = 2*blockIdx.x, b1 = b0 + 1;
+    const bool two = b1 < batch;
+    const double jc = 0.5*(N + 1);
+    for (int j = tid; j < N/2; j += nt) tw[j] = __ldg(twg + j);
+    for (int i = tid; i < N; i += nt) {
+        double a0 = in[(size_t)b0*N + i];
+        double a1 = two ? in[(size_t)b1*N + i] : 0.0;
+        if (q != 0.0) {
+            const double f = exp(-q*((i + 1) - jc)*dlnr);      // fht: a(r) = A(r) (r/rc)^(-q)
+            a0 *= f; a1 *= f;
+        }
+        z[zpad(i)] = make_double2(a0, a1);
+    }
+    __syncthreads();
+    fft_all<-1>(z, tw, N, r0, r1, r2, r3);
+    // multiply by U_m (natural order)
+    for (int m = tid; m < N; m += nt) {
+        double ur, ui;
+        if (m <= N/2) { ur = ure[m]; ui = uim[m]; }
+        else { ur = ure[N - m]; ui = -uim[N - m]; }
+        const double2 v = z[zpad(m)];
+        z[zpad(m)] = make_double2(v.x*ur - v.y*ui, v.x*ui + v.y*ur);
+    }
+    __syncthreads();
+    fft_all<+1>(z, tw, N, r0, r1, r2, r3);
+    // reversal, 1/N, output bias (fhtq :772-782, fht :632-638)
+    const double invN = 1.0/N;
+    for (int i = tid; i < N; i += nt) {
+        const double2 v = z[zpad(N - 1 - i)];
+        double f = invN;
+        if (q != 0.0) f *= exp(-q*(((i + 1) - jc)*dlnr + lnkr));
+        out[(size_t)b0*N + i] = v.x*f;
+        if (two) out[(size_t)b1*N + i] = v.y*f;
+    }
+}
+
 // ------------------------------------------------------------ generic kernel
 // out[j] = sum_l a_l g[(N-1-j-l) mod N]   (one CTA per sequence, a and g in shared memory)
 __global__ void __launch_bounds__(256)
@@ -179,7 +338,23 @@ void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, do
     if (batch <= 0) return;
     const int N = p.N;
     ProfScope prof(ctx, PROF_FFTLOG);
-    if (p.pow2) {
+    if (p.pow2 && N >= 1024) {
+        // radices: as many 16s as possible, then one of 8 / 4 / 2
+        int rad[4] = {0, 0, 0, 0}, ns = 0, rest = N;
+        while (rest >= 16) { rad[ns++] = 16; rest /= 16; }
+        if (rest > 1) rad[ns++] = rest;
+        if (!p.tw.n) {
+            std::vector<double> t((size_t)N);
+            for (int j = 0; j < N/2; j++) { t[2*j] = std::cos(-2.0*M_PI*j/N); t[2*j + 1] = std::sin(-2.0*M_PI*j/N); }
+            p.tw.upload(t, ctx.stream);
+            ctx.sync();
+        }
+        const size_t smem = (size_t)(N + N/16)*sizeof(double2) + (size_t)(N/2)*sizeof(double2);
+        PRSD_REQUIRE(smem <= ctx.smem_optin, "FFTLog: N = %d needs %zu B of shared memory", N, smem);
+        PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_r16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fftlog_r16<<<(batch + 1)/2, N/16, smem, ctx.stream>>>(N, rad[0], rad[1], rad[2], rad[3], batch, p.q, p.dlnr, std::log(p.kr),
+                                                                p.ure.p, p.uim.p, reinterpret_cast<const double2*>(p.tw.p), d_in, d_out);
+    } else if (p.pow2) {
         int logN = 0;
         while ((1 << logN) < N) logN++;
         const size_t smem = (size_t)N*sizeof(double2) + (size_t)(N/2)*sizeof(double2);

@@ -4,7 +4,8 @@
 // pyRSD/_gcl/extern/fftlog/fftlog.f:233-784, drfftf/drfftb.f).  One CTA transforms TWO real
 // sequences at once (packed as one complex sequence: the operator is real-linear), entirely in
 // shared memory: power-law bias -> radix-2 FFT -> multiply by u_m -> inverse FFT -> reversal,
-// 1/N and output bias, i.e. the whole of fht() fused in one kernel.  Lengths that are not a
+// 1/N and output bias, i.e. the whole of fht() fused in one kernel (N >= 1024: register-tiled Stockham passes of
+// radix 16, k_fftlog_r16; smaller powers of two: radix-2 passes).  Lengths that are not a
 // power of two use the equivalent real-space circular kernel g (an O(N^2) contraction).
 #pragma once
 #include "common.h"
@@ -19,6 +20,7 @@ struct FFTLogPlan {
     bool pow2 = false;
     DevBuf<double> ure, uim;     // multipliers, m = 0 .. N/2
     DevBuf<double> g;            // real-space circular kernel g[d], d = 0 .. N-1 (built on demand)
+    DevBuf<double> tw;           // exp(-2 pi i j / N), j < N/2, interleaved (re, im): register-tiled kernel
     void build_g(Context& ctx);
 };
 
