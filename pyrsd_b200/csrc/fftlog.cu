@@ -259,7 +259,7 @@ __device__ __forceinline__ void fft_all(double2* z, const double2* tw, int N, in
 }
 
 __global__ void __launch_bounds__(512)
-k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int batch, double q, double dlnr, double lnkr,
+k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int ntw, int batch, double q, double dlnr, double lnkr,
              const double* __restrict__ ure, const double* __restrict__ uim, const double2* __restrict__ twg,
              const double* __restrict__ in, double* __restrict__ out)
 {
@@ -270,7 +270,7 @@ k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int batch, double q, double 
     const int b0 = 2*blockIdx.x, b1 = b0 + 1;
     const bool two = b1 < batch;
     const double jc = 0.5*(N + 1);
-    for (int j = tid; j < N/2; j += nt) tw[j] = __ldg(twg + j);
+    for (int j = tid; j < ntw; j += nt) tw[j] = __ldg(twg + j);      // a pass of radix R reads entries < N/R only
     for (int i = tid; i < N; i += nt) {
         double a0 = in[(size_t)b0*N + i];
         double a1 = two ? in[(size_t)b1*N + i] : 0.0;
@@ -349,10 +349,11 @@ void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, do
             p.tw.upload(t, ctx.stream);
             ctx.sync();
         }
-        const size_t smem = (size_t)(N + N/16)*sizeof(double2) + (size_t)(N/2)*sizeof(double2);
+        const int ntw = N/rad[ns - 1];                 // the smallest radix comes last
+        const size_t smem = (size_t)(N + N/16)*sizeof(double2) + (size_t)ntw*sizeof(double2);
         PRSD_REQUIRE(smem <= ctx.smem_optin, "FFTLog: N = %d needs %zu B of shared memory", N, smem);
         PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_r16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fftlog_r16<<<(batch + 1)/2, N/16, smem, ctx.stream>>>(N, rad[0], rad[1], rad[2], rad[3], batch, p.q, p.dlnr, std::log(p.kr),
+        k_fftlog_r16<<<(batch + 1)/2, N/16, smem, ctx.stream>>>(N, rad[0], rad[1], rad[2], rad[3], ntw, batch, p.q, p.dlnr, std::log(p.kr),
                                                                 p.ure.p, p.uim.p, reinterpret_cast<const double2*>(p.tw.p), d_in, d_out);
     } else if (p.pow2) {
         int logN = 0;
