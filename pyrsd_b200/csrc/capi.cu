@@ -161,11 +161,42 @@ static void eval_kernel_generic(SpectraBatch& sp, int kid, int convention, int k
         }
 }
 
+// The 1-D operators are cosmology independent and some are expensive to build (X_Zel / Y_Zel integrate j0, j1(q r)
+// against every table basis function: ~1.3 s for the 1024-point Zel'dovich r grid), so the one-off entry points keep
+// the most recent ones per device.
+static std::shared_ptr<LinearOp> cached_linear_op(Context& c, const std::vector<LinOutSpec>& outs)
+{
+    struct Entry { int dev; std::vector<LinOutSpec> outs; std::shared_ptr<LinearOp> op; };
+    static std::mutex mu;
+    static std::list<Entry> cache;
+    auto same = [](const std::vector<LinOutSpec>& a, const std::vector<LinOutSpec>& b) {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); i++)
+            if (a[i].type != b[i].type || a[i].sub != b[i].sub || a[i].param != b[i].param || a[i].lo != b[i].lo ||
+                a[i].hi != b[i].hi || a[i].scale != b[i].scale) return false;
+        return true;
+    };
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto it = cache.begin(); it != cache.end(); ++it)
+            if (it->dev == c.device && same(it->outs, outs)) {
+                cache.splice(cache.begin(), cache, it);
+                return cache.front().op;
+            }
+    }
+    auto op = std::make_shared<LinearOp>();
+    op->build(c, outs);
+    std::lock_guard<std::mutex> lock(mu);
+    cache.push_front({c.device, outs, op});
+    while (cache.size() > 12) cache.pop_back();
+    return op;
+}
+
 static void eval_linear_generic(SpectraBatch& sp, const std::vector<LinOutSpec>& outs, int kind, double* out)
 {
     Context& c = *sp.ctx;
-    LinearOp op;
-    op.build(c, outs);
+    std::shared_ptr<LinearOp> opp = cached_linear_op(c, outs);
+    LinearOp& op = *opp;
     std::vector<int> idx(sp.ncosmo);
     for (int i = 0; i < sp.ncosmo; i++) idx[i] = sp.table_index(i, kind);
     DevBuf<int> di;
