@@ -269,9 +269,16 @@ def run_gpu(args):
         'k_nodal_apply<SpecDiag>': dict(fam=7, flops=info['nodes_oneloop']*B*FLOP_DIAG, pipe='fp64 DFMA'),
         'k_bilinear_apply<4>': dict(fam=0, flops=info['nodes_ik']*8*((B + 7)//8)*FLOP_IK, pipe='fp64 DMMA m8n8k4'),
     }
-    traffic = {}
+    traffic, limiter = {}, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_summary.json'))).get('dram_bytes_per_launch', {})
+        prof_json = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_summary.json')))
+        traffic = prof_json.get('dram_bytes_per_launch', {})
+        for kname, kd in prof_json.get('kernels', {}).items():
+            limiter[kname] = {m.split('.')[0]: float(kd[m]['value']) for m in (
+                'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+                'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+                'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+                'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed') if m in kd}
     except Exception:
         pass
     for name, kd in kern.items():
@@ -309,6 +316,7 @@ def run_gpu(args):
         "roofline": {"bound": "tensor", "achieved": kern[top]['achieved'], "peak": peak, "unit": "TFLOP/s",
                      "frac": (kern[top]['achieved']/peak) if (kern[top]['achieved'] and peak) else None,
                      "traffic": traffic.get(top),
+                     "ncu_pct_of_peak": limiter.get(top),     # from profiles/r01_ncu_summary.json: the binding unit is the LSU data pipe
                      "kernel": top, "pipe": kern[top]['pipe'] + " (B200 runs DFMA and FP64 DMMA on the same pipe: measured peaks "
                                                                 "%.1f / %.1f TFLOP/s)" % (peak_dfma, peak_dmma),
                      "peak_source": "FP64 microbenchmark (csrc/microbench.cu) run in this process before the timed region; "
