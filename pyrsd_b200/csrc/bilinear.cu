@@ -255,12 +255,13 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tabs = reinterpret_cast<double*>(smem_raw);
-    double* PaS = tabs + 8*TAB_MPAD;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(PaS + 8*max_outer);      // max_outer = padded row stride (= 4 mod 16)
+    double* PaS = tabs + 8*TAB_MPAD;                                      // [8][max_outer], max_outer = padded stride (= 4 mod 16)
+    double* red = PaS + 8*max_outer;                                      // [8 warps][NT][64]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + (BL_WARPS/2)*NT*64);
 
     // tiles of the same k are adjacent in launch order: the node stream of a k is read from DRAM once
-    // and from L2 by the other tiles
-    const int ik = blockIdx.y;
+    // and from L2 by the other tiles.  A CTA keeps its eight tables for several k (dealt round-robin over
+    // blockIdx.y: the node count grows ~10x from the lowest to the highest k).
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -278,6 +279,10 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
     }
     mbar_wait(mbar, 0);
 
+    const int row = lane >> 2, sub = lane & 3;
+    const double* tb = tabs + rowB[tile*8 + row]*TAB_MPAD;
+    const double* pa = PaS + row*max_outer;
+    for (int ik = blockIdx.y; ik < nk; ik += gridDim.y) {
     // ---- P_A(a) for every outer node of this k and every row
     const int64_t o0 = outer_off[ik];
     const int n_out = (int)(outer_off[ik + 1] - o0);
@@ -290,9 +295,6 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
     __syncthreads();
 
     // ---- node loop: each warp consumes 4 nodes per step; lane = (row = lane/4, node = lane%4)
-    const int row = lane >> 2, sub = lane & 3;
-    const double* tb = tabs + rowB[tile*8 + row]*TAB_MPAD;
-    const double* pa = PaS + row*max_outer;
     double acc[NT][2];
 #pragma unroll
     for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = 0.0;
@@ -319,22 +321,34 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
         for (int j = 0; j < NT; j++) dmma_m8n8k4(acc[j][0], acc[j][1], pp, wf[j]);
     }
 
-    // ---- reduce the C fragments of the 16 warps and write out[row][k][col]
-    __syncthreads();                       // everyone is done reading the tables
-    double* red = tabs;                    // [warp][NT][64]
+    // ---- reduce the C fragments of the 16 warps (upper half into the buffer, lower half on top) and write
+    //      out[row][k][col]
+    if (warp >= BL_WARPS/2) {
 #pragma unroll
-    for (int j = 0; j < NT; j++) {
-        red[(warp*NT + j)*64 + row*8 + sub*2 + 0] = acc[j][0];
-        red[(warp*NT + j)*64 + row*8 + sub*2 + 1] = acc[j][1];
+        for (int j = 0; j < NT; j++) {
+            red[((warp - BL_WARPS/2)*NT + j)*64 + row*8 + sub*2 + 0] = acc[j][0];
+            red[((warp - BL_WARPS/2)*NT + j)*64 + row*8 + sub*2 + 1] = acc[j][1];
+        }
+    }
+    __syncthreads();
+    if (warp < BL_WARPS/2) {
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            red[(warp*NT + j)*64 + row*8 + sub*2 + 0] += acc[j][0];
+            red[(warp*NT + j)*64 + row*8 + sub*2 + 1] += acc[j][1];
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < NT*64; idx += BL_THREADS) {
         const int j = idx >> 6, e = idx & 63;
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < BL_WARPS; w++) s += red[(w*NT + j)*64 + e];
+        for (int w = 0; w < BL_WARPS/2; w++) s += red[(w*NT + j)*64 + e];
         const int r = e >> 3, c = 8*j + (e & 7);
         out[((size_t)(tile*8 + r)*nk + ik)*(8*NT) + c] = s;
+    }
+    // the next k rewrites PaS at once (its readers passed the barriers above) and `red` only after its own
+    // P(a) barrier, which the threads of the loop above reach after their reads
     }
 }
 
@@ -346,10 +360,12 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
     // row stride of the P(a) buffer = 4 (mod 16) doubles like the tables: rows r and r + 4 share banks, the node
     // order (make_geometry, bank_mod = 4) keeps the four nodes of a k-step on distinct residues modulo 4
     const int pas_stride = ((g.max_outer + 15)/16)*16 + 4;
-    const size_t smem = (size_t)(8*TAB_MPAD + 8*pas_stride)*sizeof(double) + 16;
+    const size_t smem = (size_t)(8*TAB_MPAD + 8*pas_stride + (BL_WARPS/2)*NT*64)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "bilinear apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_bilinear_apply<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ntiles, g.nk);
+    // k chunks: few enough to amortise the 158 kB table staging, enough CTAs to fill 148 SMs when the batch is small
+    const int nchunks = std::min(g.nk, std::max(1, (1200 + ntiles - 1)/ntiles));
+    dim3 grid(ntiles, nchunks);
     ProfScope prof(ctx, PROF_BILINEAR);
     k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, pas_stride, g.outer_off.p, g.node_off.p,
         g.a_j0.p, g.a_coef.p, g.b_j0.p, g.n_outer_local.p, g.b_coef.p, op.W.p, tables, slot_tab, rowA, rowB, out);
