@@ -300,7 +300,7 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
     for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = 0.0;
 
     const int64_t n0 = node_off[ik], n1 = node_off[ik + 1];
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t base = n0 + 4*warp; base < n1; base += 4*BL_WARPS) {
         const int64_t node = base + sub;
         const int j0 = __ldg(b_j0 + node);
