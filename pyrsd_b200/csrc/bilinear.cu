@@ -22,6 +22,39 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     HalfNodes H;
     build_half_nodes(k, nk, qmax, cfg, grid, H);
 
+    // Outer nodes of one k are tabulated P(a) = sum_m coef_m t[j0 + m] by consecutive lanes: order them so that every
+    // run of 16 has stencil starts distinct modulo 16 where the list allows (same wavefront argument as below).
+    for (int ik = 0; ik < nk; ik++) {
+        const int64_t o0 = H.outer_off[ik], no = H.outer_off[ik + 1] - o0;
+        std::vector<std::vector<int>> q(16);
+        for (int64_t o = no - 1; o >= 0; o--) q[H.a_j0[o0 + o] & 15].push_back((int)o);     // pop_back = ascending
+        std::vector<int> perm, inv(no);
+        perm.reserve(no);
+        while ((int64_t)perm.size() < no) {
+            int order[16];
+            for (int r = 0; r < 16; r++) order[r] = r;
+            std::sort(order, order + 16, [&](int x, int y) { return q[x].size() > q[y].size(); });
+            int room = (int)std::min<int64_t>(16, no - (int64_t)perm.size());
+            for (int i = 0; i < 16 && room > 0; i++)
+                if (!q[order[i]].empty()) { perm.push_back(q[order[i]].back()); q[order[i]].pop_back(); room--; }
+            for (int i = 0; room > 0; i = (i + 1) & 15)
+                if (!q[order[i]].empty()) { perm.push_back(q[order[i]].back()); q[order[i]].pop_back(); room--; }
+        }
+        std::vector<double> a2(no), c2(4*no);
+        std::vector<int> j2(no);
+        for (int64_t n = 0; n < no; n++) {
+            const int64_t o = perm[n];
+            inv[o] = (int)n;
+            a2[n] = H.a[o0 + o];
+            j2[n] = H.a_j0[o0 + o];
+            for (int m = 0; m < 4; m++) c2[4*n + m] = H.a_coef[4*(o0 + o) + m];
+        }
+        std::copy(a2.begin(), a2.end(), H.a.begin() + o0);
+        std::copy(j2.begin(), j2.end(), H.a_j0.begin() + o0);
+        std::copy(c2.begin(), c2.end(), H.a_coef.begin() + 4*o0);
+        for (int64_t j = H.node_off[ik]; j < H.node_off[ik + 1]; j++) H.n_outer[j] = o0 + inv[H.n_outer[j] - o0];
+    }
+
     // Per k: pad the node list to a multiple of 4 (one DMMA k-step) with weightless nodes, then order it for the
     // shared-memory reads of the nodal kernels: a half-warp (16 consecutive nodes) reads t[j0 + m] with 8-byte
     // accesses, which is one wavefront only if the 16 stencil starts are equal or distinct modulo 16.  Nodes
@@ -45,7 +78,10 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
         const int64_t n0 = H.node_off[ik], n1 = H.node_off[ik + 1];
         const int64_t o0 = H.outer_off[ik];
         g->max_outer = std::max<int>(g->max_outer, (int)(H.outer_off[ik + 1] - o0));
-        const int64_t cnt = n1 - n0, padded = (cnt + 3) & ~int64_t(3);
+        // nodal kernels (BM = 16) read the node stream 32 nodes per warp: segments that start on a 128-byte
+        // boundary cost two cache lines per load instead of three
+        const int64_t pad_to = BM >= 16 ? 16 : 4;
+        const int64_t cnt = n1 - n0, padded = (cnt + pad_to - 1) / pad_to * pad_to;
         auto j0_of = [&](int64_t j) { return j < 0 ? 0 : H.b_j0[j]; };
         auto ol_of = [&](int64_t j) { return j < 0 ? 0 : (int)(H.n_outer[j] - o0); };
         sorted.clear();
