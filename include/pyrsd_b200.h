@@ -202,6 +202,42 @@ int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw,
 /* spline knots of P[mu^0], P[mu^2], P[mu^4], P[mu^6] of the last call: out [nw][10][4][nkm] */
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
 
+/* ---- transfer functions: theory -> what a survey measures --------------------------- */
+typedef struct prsd_gridop prsd_gridop;
+typedef struct prsd_window prsd_window;
+/* GriddedWedgeTransfer.average / GriddedMultipoleTransfer.__call__  [rsd/transfers/grid.py:165-187, 300-319]:
+ * out[w][b][k] = sum_mu weights[b][k][mu] * power[w][k][mu].  The caller folds the mode counts N(k, mu), the
+ * mu-bin membership (np.digitize on mu_edges) and, for multipoles, (2 ell + 1) L_ell(mu) into `weights`
+ * (host, [nbin][nk][nmu], 0 at null grid points): weights = N * leg * [mu in bin] / sum_mu(N * [mu in bin]). */
+int prsd_gridop_create(prsd_ctx* ctx, int nbin, int nk, int nmu, const double* weights, prsd_gridop** out);
+int prsd_gridop_destroy(prsd_gridop* op);
+/* power [nw][nk][nmu] -> out [nw][nbin][nk]; device_ptrs != 0: both are DEVICE pointers and the call does not
+ * synchronise */
+int prsd_gridop_apply(prsd_gridop* op, int nw, const double* power, double* out, int device_ptrs);
+/* WindowFunctionTransfer  [rsd/transfers/window.py:9-132] on the vendored mcfit transforms
+ * [extern/mcfit/mcfit.py:86-176, cosmology.py:15-35, kernels.py:14-17].  k [nk]: the log-spaced grid of the
+ * multipoles INCLUDING the zero-padded extension (window.py:84-93); ells [nell] even; q the mcfit tilt (1.5);
+ * N the FFT length (0 = mcfit's default 2^(ceil(log2 nk) + 1)); must be a power of two in [1024, 8192]. */
+int prsd_window_create(prsd_ctx* ctx, int nk, const double* k, int nell, const int* ells, double q, int N,
+                       prsd_window** out);
+int prsd_window_destroy(prsd_window* w);
+/* info [4] = {N, left padding of the input, first output slot, nk}; rr [nk]: the separation grid on which the
+ * reference evaluates the window kernels (mcfit's y of the LAST multipole, window.py:98-110) */
+int prsd_window_info(prsd_window* w, int* info, double* rr);
+/* kern [nell][nell][nk]: kern[i][j][n] multiplies xi_{ells[j]}(rr[n]) into the convolved xi_{ells[i]}
+ * (WindowConvolution._get_kernel, rsd/window.py:147-163) */
+int prsd_window_set_kernel(prsd_window* w, const double* kern);
+/* poles [nw][nell][nk] -> out [nw][nell][nk] (on the same k grid, as the reference assumes); mode 0 convolves,
+ * mode 1 is the reference's dry_run (P -> xi -> P); xi / xi_conv (may be NULL, host, [nw][nell][nk]) receive the
+ * configuration-space multipoles when device_ptrs == 0 */
+int prsd_window_apply(prsd_window* w, int nw, const double* poles, double* out, int mode, int device_ptrs,
+                      double* xi, double* xi_conv);
+/* cubic spline through (x, y[row]) evaluated at xq: the k_out resampling of window.py:112-124 and
+ * RSDSpline; natural end conditions (Spline.cpp:211-273) -- identical to FITPACK's interpolating spline to
+ * rounding a few knots away from the ends.  x [n], xq [nq] host; y [nrows][n] -> out [nrows][nq] DEVICE */
+int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x, const double* d_y, int nq,
+                                const double* xq, double* d_out);
+
 /* ---- measurement support (bench.py) -------------------------------------------------- */
 /* per-kernel-family CUDA-event timing on the context's stream; families: 0 I/K operator (DMMA contraction),
  * 1 linear operators, 2 Zel'dovich, 3 galaxy assembly, 4 spline builds, 5 FFTLog, 6 ImnOneLoop operator

@@ -4,6 +4,7 @@
 #include "galaxy.cuh"
 #include "xilm.cuh"
 #include "discrete.cuh"
+#include "transfer.cuh"
 
 #include <cstring>
 #include <list>
@@ -20,6 +21,12 @@ struct prsd_galaxy {
     GalaxyModel g;
     DevBuf<double> dk, dmu, dout;
     prsd_galaxy(Context& c, const GalaxyConfig& cfg, const double* km, int nkm, const double* ki, int nki) : g(c, cfg, km, nkm, ki, nki) {}
+};
+struct prsd_gridop { GridOp op; DevBuf<double> din, dout; prsd_gridop(Context& c, int nb, int nk, int nmu, const double* w) : op(c, nb, nk, nmu, w) {} };
+struct prsd_window {
+    WindowOp op;
+    DevBuf<double> din, dout;
+    prsd_window(Context& c, int nk, const double* k, int nell, const int* ells, double q, int N) : op(c, nk, k, nell, ells, q, N) {}
 };
 struct prsd_zelplan { ZelPlan z; Context* ctx = nullptr; };
 
@@ -730,6 +737,99 @@ int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw,
         dchi.download(chi2, (size_t)nw, c.stream);
         if (poles) g->dout.download(poles, (size_t)nw*n, c.stream);
         c.sync();
+    });
+}
+
+int prsd_gridop_create(prsd_ctx* ctx, int nbin, int nk, int nmu, const double* weights, prsd_gridop** out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && weights && out, "null argument");
+        *out = new prsd_gridop(ctx->c, nbin, nk, nmu, weights);
+    });
+}
+
+int prsd_gridop_destroy(prsd_gridop* op)
+{
+    return guarded([&] { delete op; });
+}
+
+int prsd_gridop_apply(prsd_gridop* g, int nw, const double* power, double* out, int device_ptrs)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && power && out, "null argument");
+        PRSD_REQUIRE(nw > 0, "prsd_gridop_apply: empty request");
+        GridOp& op = g->op;
+        Context& c = *op.ctx;
+        if (device_ptrs) { op.apply(nw, power, out); return; }
+        const size_t nin = (size_t)nw*op.nk*op.nmu, nout = (size_t)nw*op.nbin*op.nk;
+        g->din.ensure(nin);
+        g->dout.ensure(nout);
+        g->din.upload(power, nin, c.stream);
+        op.apply(nw, g->din.p, g->dout.p);
+        g->dout.download(out, nout, c.stream);
+        c.sync();
+    });
+}
+
+int prsd_window_create(prsd_ctx* ctx, int nk, const double* k, int nell, const int* ells, double q, int N, prsd_window** out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && k && ells && out, "null argument");
+        *out = new prsd_window(ctx->c, nk, k, nell, ells, q, N);
+    });
+}
+
+int prsd_window_destroy(prsd_window* w)
+{
+    return guarded([&] { delete w; });
+}
+
+int prsd_window_info(prsd_window* w, int* info, double* rr)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(w, "null argument");
+        if (info) { info[0] = w->op.N; info[1] = w->op.off_in; info[2] = w->op.off_out; info[3] = w->op.nk; }
+        if (rr) std::memcpy(rr, w->op.rr.data(), sizeof(double)*w->op.nk);
+    });
+}
+
+int prsd_window_set_kernel(prsd_window* w, const double* kern)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(w && kern, "null argument");
+        w->op.set_kernel(kern);
+    });
+}
+
+int prsd_window_apply(prsd_window* w, int nw, const double* poles, double* out, int mode, int device_ptrs, double* xi,
+                      double* xi_conv)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(w && poles && out, "null argument");
+        PRSD_REQUIRE(nw > 0, "prsd_window_apply: empty request");
+        WindowOp& op = w->op;
+        Context& c = *op.ctx;
+        if (device_ptrs) { op.apply(nw, poles, out, mode); return; }
+        const size_t n = (size_t)nw*op.nell*op.nk;
+        w->din.ensure(n);
+        w->dout.ensure(n);
+        w->din.upload(poles, n, c.stream);
+        op.apply(nw, w->din.p, w->dout.p, mode);
+        w->dout.download(out, n, c.stream);
+        if (xi) op.xi.download(xi, n, c.stream);
+        if (xi_conv) (mode == 0 ? op.xic : op.xi).download(xi_conv, n, c.stream);
+        c.sync();
+    });
+}
+
+int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x, const double* d_y, int nq, const double* xq,
+                                double* d_out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && x && d_y && xq && d_out, "null argument");
+        PRSD_REQUIRE(nrows > 0 && nq > 0, "prsd_spline_resample_device: empty request");
+        for (int i = 1; i < n; i++) PRSD_REQUIRE(x[i] > x[i - 1], "prsd_spline_resample_device: x must be increasing");
+        spline_eval_host_x(ctx->c, nrows, n, x, d_y, nq, xq, d_out);
     });
 }
 

@@ -39,6 +39,20 @@ std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q
     return p;
 }
 
+std::shared_ptr<FFTLogPlan> fftlog_plan_custom(Context& ctx, int N, double dlnr, const std::vector<double>& re,
+                                               const std::vector<double>& im)
+{
+    PRSD_REQUIRE(N >= 2 && N <= 8192, "FFTLog: N = %d outside [2, 8192]", N);
+    PRSD_REQUIRE((int)re.size() == N/2 + 1 && (int)im.size() == N/2 + 1, "FFTLog: multiplier table must have N/2 + 1 entries");
+    auto p = std::make_shared<FFTLogPlan>();
+    p->N = N; p->mu = 0; p->q = 0; p->dlnr = dlnr; p->kr = 1;
+    p->pow2 = (N & (N - 1)) == 0 && N >= 8;
+    p->ure.upload(re, ctx.stream);
+    p->uim.upload(im, ctx.stream);
+    ctx.sync();
+    return p;
+}
+
 // ------------------------------------------------------------ real-space g
 // g[d] = (1/N) sum_{m=0}^{N-1} U_m exp(2 pi i d m / N), U_{N-m} = conj(U_m)
 __global__ void k_fftlog_g(int N, const double* __restrict__ ure, const double* __restrict__ uim, double* __restrict__ g)
@@ -258,10 +272,21 @@ __device__ __forceinline__ void fft_all(double2* z, const double2* tw, int N, in
     }
 }
 
+// WIN: the sequence is a window of a longer zero-padded one (mcfit-style transforms, transfer.cu): element i of the
+// n_io inputs of row b sits at in[b*in_stride + i], is multiplied by pre[i] and placed at slot off_in + i; outputs
+// are slots off_out .. off_out + n_io - 1, multiplied by post[i]; no power-law bias.
+struct FFTWindow {
+    const double* pre;
+    const double* post;
+    int n_io, off_in, off_out;
+    long long in_stride, out_stride;
+};
+
+template <bool WIN>
 __global__ void __launch_bounds__(512)
 k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int ntw, int batch, double q, double dlnr, double lnkr,
              const double* __restrict__ ure, const double* __restrict__ uim, const double2* __restrict__ twg,
-             const double* __restrict__ in, double* __restrict__ out)
+             const double* __restrict__ in, double* __restrict__ out, FFTWindow win)
 {
     extern __shared__ __align__(16) unsigned char smem_raw3[];
     double2* z = reinterpret_cast<double2*>(smem_raw3);
@@ -272,11 +297,20 @@ k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int ntw, int batch, double q
     const double jc = 0.5*(N + 1);
     for (int j = tid; j < ntw; j += nt) tw[j] = __ldg(twg + j);      // a pass of radix R reads entries < N/R only
     for (int i = tid; i < N; i += nt) {
-        double a0 = in[(size_t)b0*N + i];
-        double a1 = two ? in[(size_t)b1*N + i] : 0.0;
-        if (q != 0.0) {
-            const double f = exp(-q*((i + 1) - jc)*dlnr);      // fht: a(r) = A(r) (r/rc)^(-q)
-            a0 *= f; a1 *= f;
+        double a0, a1;
+        if (WIN) {
+            const int j = i - win.off_in;
+            const bool inside = j >= 0 && j < win.n_io;
+            const double f = inside ? win.pre[j] : 0.0;
+            a0 = inside ? f*in[(size_t)b0*win.in_stride + j] : 0.0;
+            a1 = (inside && two) ? f*in[(size_t)b1*win.in_stride + j] : 0.0;
+        } else {
+            a0 = in[(size_t)b0*N + i];
+            a1 = two ? in[(size_t)b1*N + i] : 0.0;
+            if (q != 0.0) {
+                const double f = exp(-q*((i + 1) - jc)*dlnr);      // fht: a(r) = A(r) (r/rc)^(-q)
+                a0 *= f; a1 *= f;
+            }
         }
         z[zpad(i)] = make_double2(a0, a1);
     }
@@ -294,6 +328,15 @@ k_fftlog_r16(int N, int r0, int r1, int r2, int r3, int ntw, int batch, double q
     fft_all<+1>(z, tw, N, r0, r1, r2, r3);
     // reversal, 1/N, output bias (fhtq :772-782, fht :632-638)
     const double invN = 1.0/N;
+    if (WIN) {
+        for (int j = tid; j < win.n_io; j += nt) {
+            const double2 v = z[zpad(N - 1 - (win.off_out + j))];
+            const double f = invN*win.post[j];
+            out[(size_t)b0*win.out_stride + j] = v.x*f;
+            if (two) out[(size_t)b1*win.out_stride + j] = v.y*f;
+        }
+        return;
+    }
     for (int i = tid; i < N; i += nt) {
         const double2 v = z[zpad(N - 1 - i)];
         double f = invN;
@@ -333,7 +376,7 @@ k_fftlog_direct(int N, double q, double dlnr, double lnkr, const double* __restr
     }
 }
 
-void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, double* d_out)
+void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, double* d_out, const FFTLogWindow* win)
 {
     if (batch <= 0) return;
     const int N = p.N;
@@ -352,10 +395,18 @@ void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, do
         const int ntw = N/rad[ns - 1];                 // the smallest radix comes last
         const size_t smem = (size_t)(N + N/16)*sizeof(double2) + (size_t)ntw*sizeof(double2);
         PRSD_REQUIRE(smem <= ctx.smem_optin, "FFTLog: N = %d needs %zu B of shared memory", N, smem);
-        PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_r16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fftlog_r16<<<(batch + 1)/2, N/16, smem, ctx.stream>>>(N, rad[0], rad[1], rad[2], rad[3], ntw, batch, p.q, p.dlnr, std::log(p.kr),
-                                                                p.ure.p, p.uim.p, reinterpret_cast<const double2*>(p.tw.p), d_in, d_out);
+        if (win) {
+            FFTWindow fw{win->pre, win->post, win->n_io, win->off_in, win->off_out, win->in_stride, win->out_stride};
+            PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_r16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fftlog_r16<true><<<(batch + 1)/2, N/16, smem, ctx.stream>>>(N, rad[0], rad[1], rad[2], rad[3], ntw, batch, 0.0, p.dlnr, 0.0,
+                p.ure.p, p.uim.p, reinterpret_cast<const double2*>(p.tw.p), d_in, d_out, fw);
+        } else {
+            PRSD_CUDA(cudaFuncSetAttribute(k_fftlog_r16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fftlog_r16<false><<<(batch + 1)/2, N/16, smem, ctx.stream>>>(N, rad[0], rad[1], rad[2], rad[3], ntw, batch, p.q, p.dlnr,
+                std::log(p.kr), p.ure.p, p.uim.p, reinterpret_cast<const double2*>(p.tw.p), d_in, d_out, FFTWindow{});
+        }
     } else if (p.pow2) {
+        PRSD_REQUIRE(!win, "FFTLog: windowed transforms need a power-of-two N in [1024, 8192]");
         int logN = 0;
         while ((1 << logN) < N) logN++;
         const size_t smem = (size_t)N*sizeof(double2) + (size_t)(N/2)*sizeof(double2);
@@ -364,6 +415,7 @@ void fftlog_apply(Context& ctx, FFTLogPlan& p, int batch, const double* d_in, do
         k_fftlog_pow2<<<(batch + 1)/2, 256, smem, ctx.stream>>>(N, logN, batch, p.q, p.dlnr, std::log(p.kr),
                                                               p.ure.p, p.uim.p, d_in, d_out);
     } else {
+        PRSD_REQUIRE(!win, "FFTLog: windowed transforms need a power-of-two N in [1024, 8192]");
         p.build_g(ctx);
         PRSD_REQUIRE(d_in != d_out, "FFTLog: in-place transform needs a power-of-two length");
         const size_t smem = (size_t)2*N*sizeof(double);

@@ -11,6 +11,7 @@
 #include "common.h"
 
 #include <memory>
+#include <vector>
 
 namespace prsd {
 
@@ -27,8 +28,23 @@ struct FFTLogPlan {
 // cached per (device, N, mu, q, dlnr, kr, kropt)
 std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt);
 
+// plan with caller-supplied multipliers U_m, m = 0 .. N/2 (U_{N/2} real), no bias: out[i] = (1/N) sum_m F_m U_m
+// exp(-2 pi i m (i + 1) / N) with F = DFT of the input -- the mcfit-style transforms of transfer.cu; not cached
+std::shared_ptr<FFTLogPlan> fftlog_plan_custom(Context& ctx, int N, double dlnr, const std::vector<double>& re,
+                                               const std::vector<double>& im);
+
+// optional windowing of a zero-padded sequence (N in [1024, 8192] only): input element i of row b is
+// pre[i] * in[b*in_stride + i] placed at slot off_in + i, i < n_io; output i = post[i] * slot (off_out + i)
+struct FFTLogWindow {
+    const double* pre = nullptr;     // device [n_io]
+    const double* post = nullptr;    // device [n_io]
+    int n_io = 0, off_in = 0, off_out = 0;
+    long long in_stride = 0, out_stride = 0;
+};
+
 // forward transform (dir = +1) of `batch` sequences; d_in / d_out are device pointers [batch][N]
 // (may alias).
-void fftlog_apply(Context& ctx, FFTLogPlan& plan, int batch, const double* d_in, double* d_out);
+void fftlog_apply(Context& ctx, FFTLogPlan& plan, int batch, const double* d_in, double* d_out,
+                  const FFTLogWindow* win = nullptr);
 
 } // namespace prsd

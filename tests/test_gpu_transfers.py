@@ -1,0 +1,117 @@
+"""GPU parity of the transfer functions (gridded wedges / multipoles, window-function convolution) against the
+golden vectors of the reference's own Python (tests/golden/window_ref.npz) and the NumPy oracle, through the
+C-ABI (prsd_gridop_*, prsd_window_*, prsd_spline_resample_device)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+from window_inputs import synthetic_power, synthetic_window  # noqa: E402
+
+REF = np.load(os.path.join(HERE, 'golden', 'window_ref.npz'))
+# deterministic transforms: the budget is rounding (1 ulp of the input moves xi by ~3e-13 of its maximum, see
+# tests/golden/make_window_ref.py), far inside the 1e-5 of the north star
+TOL = 1e-10
+
+
+def relmax(a, b):
+    return np.nanmax(np.abs(a - b))/np.nanmax(np.abs(b))
+
+
+def grid_of(tag):
+    kmin, kmax, Nk, Nmu = REF[tag + '_grid']
+    return float(kmin), float(kmax), int(Nk), int(Nmu)
+
+
+def test_gridded_wedges_and_poles_vs_reference():
+    from pyrsd_b200 import transfers as TR
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        grid = TR.PkmuGrid([REF['g_k_cen'], REF['g_mu_cen']], REF['g_k'], REF['g_mu'], REF['g_modes'])
+    bounds = [tuple(b) for b in REF['g_bounds']]
+    power = np.where(grid.notnull, REF['g_power'], np.nan)          # null cells hold NaN: they must not leak
+    in_range = (REF['g_k_cen'] >= 0.01) & (REF['g_k_cen'] <= 0.3)
+    # the low-k rows of this grid have empty mu bins: the reference raises there, so start above them
+    kmin = REF['g_k_cen'][6] - 1e-9
+    wt = TR.GriddedWedgeTransfer(grid, list(bounds), kmin=kmin, kmax=0.3)
+    got = wt(power)
+    sel = (REF['g_k_cen'] >= kmin) & (REF['g_k_cen'] <= 0.3)
+    assert np.isnan(got[~sel]).all() and np.isfinite(got[sel]).all()
+    assert relmax(got[sel], REF['g_wedges'][sel]) < 1e-13
+    mt = TR.GriddedMultipoleTransfer(grid, [0, 2, 4], kmin=0.01, kmax=0.3)
+    got = mt(power)
+    assert np.isnan(got[~in_range]).all()
+    assert relmax(got[in_range], REF['g_poles'][in_range]) < 1e-13
+    # batch of walkers, and device tensors in / out
+    import torch
+    batch = np.stack([power, 2.*power, power + 1.])
+    gb = mt(batch)
+    assert relmax(gb[0][in_range], got[in_range]) == 0.
+    dev = mt(torch.from_numpy(np.nan_to_num(batch)).cuda())
+    assert dev.is_cuda and tuple(dev.shape) == (3, 3, grid.Nk)
+    assert relmax(dev.cpu().numpy()[1].T[in_range], gb[1][in_range]) < 1e-15
+    with pytest.raises(ValueError):
+        TR.GriddedWedgeTransfer(grid, list(bounds), kmin=0.01, kmax=0.3)(power)     # empty bins inside the range
+    with pytest.raises(ValueError):
+        mt(power[:, :10])
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_window_transfer_vs_reference(tag):
+    from pyrsd_b200 import transfers as TR
+    kmin, kmax, Nk, Nmu = grid_of(tag)
+    tr = TR.WindowFunctionTransfer(synthetic_window(), [0, 2, 4], kmin=kmin, kmax=kmax, Nk=Nk, Nmu=Nmu, max_ellprime=4)
+    k, mu = tr.grid.k_cen, tr.grid.mu_cen
+    power = synthetic_power(k[:, None], mu[None, :])
+    full, xi, xic = tr(power, return_xi=True)
+    assert tr.N_fft == int(REF[tag + '_N'])
+    assert np.array_equal(tr.k_pad, REF[tag + '_newk'])
+    assert relmax(tr.rr, REF[tag + '_rr']) < 1e-14
+    assert relmax(xi[0].T, REF[tag + '_xi']) < TOL
+    assert relmax(xic[0].T, REF[tag + '_xi_conv']) < TOL
+    assert relmax(full, REF[tag + '_Pconv']) < TOL
+    out = tr(power, k_out=REF[tag + '_k_out'])
+    assert relmax(out, REF[tag + '_Pout']) < TOL
+    dry = tr(power, dry_run=True)
+    assert relmax(dry, REF[tag + '_Pdry']) < TOL
+    noconv = tr(power, no_convolution=True)
+    assert relmax(noconv[:Nk], REF[tag + '_Pell0']) < 1e-14 and np.all(noconv[Nk:] == 0.)
+    with pytest.raises(NotImplementedError):
+        tr(power, extrap=True)
+
+
+def test_window_transfer_batch_linearity_and_device_tensors():
+    """at the reference's default size (Nk = 1024, N = 4096): a batch of walkers, odd batch size (the FFT kernel
+    packs two sequences per CTA), linearity of the whole chain, and device-resident input / output"""
+    import torch
+    from pyrsd_b200 import transfers as TR
+    tr = TR.WindowFunctionTransfer(synthetic_window(), [0, 2, 4])
+    k, mu = tr.grid.k_cen, tr.grid.mu_cen
+    p1 = synthetic_power(k[:, None], mu[None, :])
+    p2 = synthetic_power(k[:, None], mu[None, :], b=1.3, f=0.5, sigma=5.0)
+    batch = np.stack([p1, p2, 0.3*p1 - 1.7*p2, p1, p2])
+    k_out = np.linspace(0.01, 0.4, 40)
+    out = tr(batch, k_out=k_out)
+    assert out.shape == (5, 40, 3)
+    assert relmax(out[0], REF['a_Pout']) < TOL
+    assert np.array_equal(out[0], out[3]) and np.array_equal(out[1], out[4])
+    assert relmax(out[2], 0.3*out[0] - 1.7*out[1]) < 1e-11
+    dev = tr(torch.from_numpy(batch).cuda(), k_out=k_out)
+    assert dev.is_cuda and tuple(dev.shape) == (5, 3, 40)
+    assert relmax(np.swapaxes(dev.cpu().numpy(), 1, 2), out) < 1e-15
+
+
+def test_window_errors():
+    from pyrsd_b200 import transfers as TR
+    with pytest.raises(ValueError):
+        TR.WindowFunctionTransfer(synthetic_window(), [0, 2])               # needs the first 3 even multipoles
+    with pytest.raises(ValueError):
+        TR.WindowFunctionTransfer(synthetic_window()[:, :4], [0, 2, 4])     # window multipoles up to ell = 8
+    from pyrsd_b200._native import NativeError
+    with pytest.raises(NativeError):
+        TR.WindowFunctionTransfer(synthetic_window(), [0, 2, 4], Nk=100)._window()     # FFT length below 1024
