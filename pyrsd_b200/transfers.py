@@ -204,11 +204,11 @@ class GriddedWedgeTransfer(object):
     def _operator(self):
         if self._op is None:
             w = self._weights()
+            if (self._empty & self.in_k_range.T).any():
+                raise ValueError("NaN values in %s result within valid k range!" % self.__class__.__name__)
             p = _vp()
             N.check(_L().prsd_gridop_create(self._ctx.ptr, w.shape[0], w.shape[1], w.shape[2], w, C.byref(p)))
             self._op = _GridOp(p)
-            if (self._empty & self.in_k_range.T).any():
-                raise ValueError("NaN values in %s result within valid k range!" % self.__class__.__name__)
         return self._op
 
     def __call__(self, power):

@@ -55,8 +55,15 @@ def test_gridded_wedges_and_poles_vs_reference():
     dev = mt(torch.from_numpy(np.nan_to_num(batch)).cuda())
     assert dev.is_cuda and tuple(dev.shape) == (3, 3, grid.Nk)
     assert relmax(dev.cpu().numpy()[1].T[in_range], gb[1][in_range]) < 1e-15
+    modes = REF['g_modes'].copy()
+    modes[10, REF['g_mu'][10] < 0.2] = 0.                            # an empty mu bin inside the k range
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        holed = TR.PkmuGrid([REF['g_k_cen'], REF['g_mu_cen']], REF['g_k'], REF['g_mu'], modes)
     with pytest.raises(ValueError):
-        TR.GriddedWedgeTransfer(grid, list(bounds), kmin=0.01, kmax=0.3)(power)     # empty bins inside the range
+        TR.GriddedWedgeTransfer(holed, list(bounds), kmin=0.01, kmax=0.3)(power)
+    got = TR.GriddedWedgeTransfer(holed, list(bounds), kmin=0.06, kmax=0.3)(power)   # row 10 (k = 0.0575) excluded
+    assert np.isfinite(got[(REF['g_k_cen'] >= 0.06) & (REF['g_k_cen'] <= 0.3)]).all()
     with pytest.raises(ValueError):
         mt(power[:, :10])
 
@@ -69,7 +76,7 @@ def test_window_transfer_vs_reference(tag):
     k, mu = tr.grid.k_cen, tr.grid.mu_cen
     power = synthetic_power(k[:, None], mu[None, :])
     full, xi, xic = tr(power, return_xi=True)
-    assert tr.N_fft == int(REF[tag + '_N'])
+    assert tr.N_fft == int(REF[tag + '_N'].ravel()[0])
     assert np.array_equal(tr.k_pad, REF[tag + '_newk'])
     assert relmax(tr.rr, REF[tag + '_rr']) < 1e-14
     assert relmax(xi[0].T, REF[tag + '_xi']) < TOL
@@ -99,7 +106,8 @@ def test_window_transfer_batch_linearity_and_device_tensors():
     out = tr(batch, k_out=k_out)
     assert out.shape == (5, 40, 3)
     assert relmax(out[0], REF['a_Pout']) < TOL
-    assert np.array_equal(out[0], out[3]) and np.array_equal(out[1], out[4])
+    # two sequences share one complex FFT: the same walker in another slot agrees to rounding, not bit for bit
+    assert relmax(out[3], out[0]) < 1e-12 and relmax(out[4], out[1]) < 1e-12
     assert relmax(out[2], 0.3*out[0] - 1.7*out[1]) < 1e-11
     dev = tr(torch.from_numpy(batch).cuda(), k_out=k_out)
     assert dev.is_cuda and tuple(dev.shape) == (5, 3, 40)
