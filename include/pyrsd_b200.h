@@ -238,6 +238,11 @@ int prsd_window_apply(prsd_window* w, int nw, const double* poles, double* out, 
 int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x, const double* d_y, int nq,
                                 const double* xq, double* d_out);
 
+/* FittingDriver.chi2  [rsdfit/driver.py:780-802] of nw model vectors model [nw][n] (host, or DEVICE when
+ * model_on_device != 0) against data [n] with precision matrix cinv [n][n] (host); chi2 [nw] host */
+int prsd_chi2(prsd_ctx* ctx, int nw, int n, const double* model, const double* data, const double* cinv,
+              double* chi2, int model_on_device);
+
 /* ---- measurement support (bench.py) -------------------------------------------------- */
 /* per-kernel-family CUDA-event timing on the context's stream; families: 0 I/K operator (DMMA contraction),
  * 1 linear operators, 2 Zel'dovich, 3 galaxy assembly, 4 spline builds, 5 FFTLog, 6 ImnOneLoop operator

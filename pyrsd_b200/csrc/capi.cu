@@ -833,6 +833,23 @@ int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x
     });
 }
 
+int prsd_chi2(prsd_ctx* ctx, int nw, int n, const double* model, const double* data, const double* cinv, double* chi2,
+              int model_on_device)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(ctx && model && data && cinv && chi2, "null argument");
+        PRSD_REQUIRE(nw > 0 && n > 0, "prsd_chi2: empty request");
+        Context& c = ctx->c;
+        DevBuf<double> dmodel, ddata, dcinv, dchi((size_t)nw);
+        ddata.upload(data, (size_t)n, c.stream);
+        dcinv.upload(cinv, (size_t)n*n, c.stream);
+        if (!model_on_device) dmodel.upload(model, (size_t)nw*n, c.stream);
+        chi2_rows(c, nw, n, model_on_device ? model : dmodel.p, ddata.p, dcinv.p, dchi.p);
+        dchi.download(chi2, (size_t)nw, c.stream);
+        c.sync();
+    });
+}
+
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
 {
     return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });

@@ -734,16 +734,19 @@ void GalaxyModel::chi2(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, 
                        const double* d_cinv, double* d_poles, double* d_out)
 {
     poles(sp, pt, nw, cmap, par, stoch, nk, d_k, nell, ells, nmu, d_poles);
-    Context& c = *ctx;
-    const int n = nell*nk;
+    chi2_rows(*ctx, nw, nell*nk, d_poles, d_data, d_cinv, d_out);
+    ctx->sync();
+}
+
+void chi2_rows(Context& c, int nw, int n, const double* d_model, const double* d_data, const double* d_cinv, double* d_out)
+{
     const size_t smem = (size_t)n*sizeof(double);
     PRSD_REQUIRE(smem <= 200*1024, "chi2: data vector of %d entries too long", n);
     if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof_gal(c, PROF_GALAXY);
-    k_gal_chi2<<<nw, 256, smem, c.stream>>>(n, d_poles, d_data, d_cinv, d_out);
+    k_gal_chi2<<<nw, 256, smem, c.stream>>>(n, d_model, d_data, d_cinv, d_out);
     PRSD_CUDA(cudaGetLastError());
     c.launches++;
-    c.sync();
 }
 
 void GalaxyModel::moments_to_host(int nw, double* out)

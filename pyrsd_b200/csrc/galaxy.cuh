@@ -77,4 +77,8 @@ struct GalaxyModel {
     void moments_to_host(int nw, double* out);
 };
 
+// chi^2 = (M - D)^T C^-1 (M - D) of nw model vectors d_model [nw][n] (FittingDriver.chi2, rsdfit/driver.py:780-802);
+// all pointers on the device, no synchronisation
+void chi2_rows(Context& c, int nw, int n, const double* d_model, const double* d_data, const double* d_cinv, double* d_out);
+
 } // namespace prsd

@@ -45,6 +45,8 @@ def _L():
         L.prsd_galaxy_poles.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, i, _ip, i, _dp]
         L.prsd_galaxy_poles_device.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _vp, i, _ip, i, _vp]
         L.prsd_galaxy_chi2.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, i, _ip, i, _dp, _dp, _dp, _vp]
+        L.prsd_chi2.argtypes = [_vp, i, i, _vp, _dp, _dp, _dp, i]
+        L.prsd_chi2.restype = i
         for name in ('prsd_galaxy_config_default', 'prsd_galaxy_create', 'prsd_galaxy_destroy', 'prsd_galaxy_power',
                      'prsd_galaxy_power_device', 'prsd_galaxy_moments', 'prsd_galaxy_poles', 'prsd_galaxy_poles_device',
                      'prsd_galaxy_chi2'):
@@ -192,6 +194,59 @@ class PTEngine(object):
         N.check(_L().prsd_galaxy_chi2(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
                                       par, stoch, len(k), k, len(ells), ells, int(Nmu), data, cinv, chi2,
                                       None if poles is None else poles.ctypes.data_as(_vp)))
+        return (chi2, poles) if return_poles else chi2
+
+    def galaxy_power_device(self, gal, spectra, result, par, stoch, d_k, d_mu, cmap=None):
+        """P(k, mu) of nw walkers at paired device-resident (k, mu) points -> CUDA tensor [nw][npts]; nothing
+        but the walker parameters crosses the host boundary (input of the device-side transfer functions)"""
+        import torch
+        par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, NPAR)
+        nw = par.shape[0]
+        stoch = np.ascontiguousarray(stoch, dtype=np.float64).reshape(nw, NPAIR, NSTOCH)
+        assert d_k.is_cuda and d_mu.is_cuda and d_k.dtype == torch.float64 and d_k.shape == d_mu.shape
+        out = torch.empty((nw, d_k.numel()), dtype=torch.float64, device=d_k.device)
+        cm = None if cmap is None else np.ascontiguousarray(cmap, dtype=np.int32)
+        N.check(_L().prsd_galaxy_power_device(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
+                                              par, stoch, d_k.numel(), _vp(d_k.data_ptr()), _vp(d_mu.data_ptr()),
+                                              _vp(out.data_ptr())))
+        return out
+
+    def chi2(self, model, data, cinv):
+        """chi^2 of nw model vectors [nw][n] (NumPy array or CUDA tensor) against ``data`` [n] with precision
+        matrix ``cinv`` [n][n] (rsdfit/driver.py:780-802) -> [nw]"""
+        on_dev = type(model).__module__.split('.')[0] == 'torch'
+        if on_dev:
+            m = model.contiguous().reshape(model.shape[0], -1)
+            nw, n = m.shape
+            ptr = _vp(m.data_ptr())
+        else:
+            m = np.ascontiguousarray(model, dtype=np.float64)
+            m = m.reshape(m.shape[0], -1)
+            nw, n = m.shape
+            ptr = m.ctypes.data_as(_vp)
+        data = np.ascontiguousarray(data, dtype=np.float64).reshape(n)
+        cinv = np.ascontiguousarray(cinv, dtype=np.float64).reshape(n, n)
+        out = np.empty(nw)
+        N.check(_L().prsd_chi2(self.ctx.ptr, nw, n, ptr, data, cinv, out, int(on_dev)))
+        return out
+
+    def galaxy_window_chi2(self, gal, spectra, result, par, stoch, transfer, k_out, data, cinv, cmap=None,
+                           return_poles=False):
+        """One likelihood evaluation of a survey fit for nw walkers, entirely on the device: P(k, mu) on the grid
+        of ``transfer`` (a transfers.WindowFunctionTransfer / GriddedMultipoleTransfer) -> multipoles -> window
+        convolution -> spline onto ``k_out`` -> chi^2 against ``data`` in the order [ell][k]
+        (rsdfit/theory/base.py:612-699 + rsdfit/driver.py:780-802)"""
+        import torch
+        dev = 'cuda:%d' % self.ctx.device
+        grid = transfer.grid
+        if getattr(transfer, '_dgrid', None) is None:
+            transfer._dgrid = (torch.from_numpy(np.ascontiguousarray(grid.k).ravel()).to(dev),
+                               torch.from_numpy(np.ascontiguousarray(grid.mu).ravel()).to(dev))
+        dk, dmu = transfer._dgrid
+        P = self.galaxy_power_device(gal, spectra, result, par, stoch, dk, dmu, cmap=cmap)
+        P = P.reshape(P.shape[0], grid.Nk, grid.Nmu)
+        poles = transfer(P, k_out=k_out) if k_out is not None else transfer(P)          # [nw][nell][nk]
+        chi2 = self.chi2(poles, data, cinv)
         return (chi2, poles) if return_poles else chi2
 
     def galaxy_moments(self, gal, nw):

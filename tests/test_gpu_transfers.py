@@ -123,3 +123,55 @@ def test_window_errors():
     from pyrsd_b200._native import NativeError
     with pytest.raises(NativeError):
         TR.WindowFunctionTransfer(synthetic_window(), [0, 2, 4], Nk=100)._window()     # FFT length below 1024
+
+
+def test_survey_likelihood_chain_on_device(golden):
+    """PT tables -> galaxy P(k, mu) on the window grid -> multipoles -> window convolution -> spline -> chi^2, all
+    on the device (PTEngine.galaxy_window_chi2), against the same chain assembled on the host from this
+    library's P(k, mu) with the NumPy oracle of the reference's transfer functions"""
+    from pyrsd_b200 import rsd, transfers as TR
+    from oracle import transfer_restate as T
+    from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity
+    cosmo = golden_pygcl_cosmology(golden)
+    engine = rsd.PTEngine()
+    sp = engine.spectra(cosmo.GetDiscreteK(), cosmo.GetDiscreteTk(), cosmo.n_s(), cosmo.delta_H()**2, cosmo.h(),
+                        cosmo.Omega0_m(), cosmo.Omega0_b(), cosmo.Tcmb())
+    res = engine.run(sp, result=rsd._new_result())
+    kmin, kmax = 1e-4, 0.7
+    kmodel = np.logspace(np.log10(kmin), np.log10(kmax), 200)
+    gal = engine.galaxy(kmodel, rsd.galaxy_config())
+    ks = rsd.stochasticity_grid(kmodel)
+    nw = 5
+    wpar = np.zeros((nw, rsd.NPAR)); stoch = np.zeros((nw, rsd.NPAIR, rsd.NSTOCH))
+    for i in range(nw):
+        b1 = [1.8 + 0.05*i, 2.7, 2.5, 3.4]
+        b00, b01 = [b2_00(b) for b in b1], [b2_01(b) for b in b1]
+        wpar[i] = rsd.pack_walker(0.6 + 0.01*i, 0.75, 1.0, 1.0, 1.0, b1, 0.10, 0.08, 0.40, 1.0, 4.2, 6.0, 3e4, 9e4, 0., 0., None,
+                                  0.7486, cosmo.sigma8(), [b00, b00, b00, b00, b01, b01])
+        for p, (a, b) in enumerate(rsd.PAIRS):
+            lo, hi = sorted([b1[a], b1[b]])
+            stoch[i, p] = stochasticity(ks, wpar[i, 0], lo, hi)
+    cmap = np.zeros(nw, dtype=np.int32)
+    window = synthetic_window()
+    tr = TR.WindowFunctionTransfer(window, [0, 2, 4], kmin=kmin, kmax=kmax, Nk=1024, Nmu=40)
+    k_out = np.linspace(0.02, 0.38, 19)
+    # host chain: this library's P(k, mu), the reference's transfer arithmetic (NumPy restatement)
+    P = engine.galaxy_power(gal, sp, res, wpar, stoch, tr.grid.k.ravel(), tr.grid.mu.ravel(), cmap=cmap)
+    P = P.reshape(nw, 1024, 40)
+    ref = np.array([T.window_transfer(P[i], tr.grid.k_cen, tr.grid.mu_cen, window, [0, 2, 4], 4, k_out)['Pout'].T
+                    for i in range(nw)])                                              # [nw][ell][k]
+    rng = np.random.default_rng(5)
+    n = 3*len(k_out)
+    data = ref[2].ravel()*(1 + 0.01*rng.normal(size=n))
+    A = rng.normal(size=(n, n))
+    cinv = (A @ A.T/n + np.eye(n))/(np.outer(np.abs(data), np.abs(data))*1e-4)
+    d = ref.reshape(nw, n) - data[None, :]
+    chi2_ref = np.einsum('wi,ij,wj->w', d, cinv, d)
+    chi2, poles = engine.galaxy_window_chi2(gal, sp, res, wpar, stoch, tr, k_out, data, cinv, cmap=cmap, return_poles=True)
+    assert poles.is_cuda and tuple(poles.shape) == (nw, 3, len(k_out))
+    got = poles.cpu().numpy()
+    assert np.max(np.abs(got - ref))/np.max(np.abs(ref)) < TOL
+    # chi^2 amplifies the 1e-10 of the multipoles by |d|/sigma ~ 1e2
+    assert np.allclose(chi2, chi2_ref, rtol=1e-6)
+    assert np.argmin(chi2) == 2
+    assert np.allclose(engine.chi2(ref, data, cinv), chi2_ref, rtol=1e-12)
