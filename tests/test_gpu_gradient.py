@@ -1,0 +1,94 @@
+"""GPU parity of GalaxySpectrum.gradient (batched central differences on the device) against the reference's
+ANALYTIC derivatives (pyRSD/rsd/power/gal/derivatives/*.py, run unmodified on the tight-tolerance reference model,
+tests/golden/make_gradient_ref.py) and against the reference's own finite differences for the rest."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, 'golden', 'gradient_ref.npz')
+# the model itself matches the reference to 1e-5 of P; a derivative inherits that, relative to its own scale
+TOL = 2e-5
+
+CASES = {
+    'ap': (dict(),
+           dict(alpha_par=1.03, alpha_perp=0.98, b1_cA=1.9, b1_cB=2.7, b1_sA=2.4, b1_sB=3.3, fs=0.12, fcB=0.09, fsB=0.35,
+                sigma_c=1.1, sigma_sA=3.9, sigma_sB=5.5, NcBs=4.2e4, NsBsB=8.1e4, sigma8_z=0.61, f=0.78)),
+    'so': (dict(use_so_correction=True, fog_model='gaussian', max_mu=6, use_tidal_bias=True),
+           dict(f_so=0.04, sigma_so=4.0, alpha_par=0.97, alpha_perp=1.02)),
+}
+
+
+@pytest.fixture(scope='module')
+def ref():
+    if not os.path.exists(REF):
+        pytest.skip("tests/golden/gradient_ref.npz not generated")
+    return np.load(REF)
+
+
+@pytest.fixture(scope='module')
+def models(golden):
+    from pyrsd_b200 import rsd
+    cosmo = golden_pygcl_cosmology(golden)
+    engine = rsd.PTEngine()
+    out = {}
+    for tag, (kw, upd) in CASES.items():
+        m = rsd.GalaxySpectrum(params=cosmo, z=0.55, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine, **kw)
+        m.update(**upd)
+        out[tag] = m
+    return out
+
+
+@pytest.mark.parametrize('tag', ['ap', 'so'])
+def test_gradient_vs_reference_analytic(ref, models, tag):
+    m = models[tag]
+    k, mu = ref['k'], ref['mu']
+    P = m.power(k, mu)
+    assert np.max(np.abs(P/ref[tag + '_P'] - 1.)) < 1e-5
+    names = [n[len(tag) + 3:] for n in ref.files if n.startswith(tag + '_d_')]
+    assert len(names) >= 8
+    # P is linear in the one-halo amplitudes: any step is exact, a unit step avoids cancellation
+    eps = [1.0 if n in ('NcBs', 'NsBsB') else 1e-4 for n in names]
+    g = m.gradient(k, mu, names, epsilon=eps)
+    assert g.shape == (len(names), len(k))
+    for n, row in zip(names, g):
+        want = ref['%s_d_%s' % (tag, n)]
+        err = np.max(np.abs(row - want))/np.max(np.abs(want))
+        assert err < TOL, (tag, n, err)
+    # the model is left untouched
+    assert np.array_equal(m.power(k, mu), P)
+
+
+def test_gradient_vs_reference_finite_differences(ref, models):
+    m = models['ap']
+    k, mu = ref['k'], ref['mu']
+    names = [n[len('ap_n_'):] for n in ref.files if n.startswith('ap_n_')]
+    g = m.gradient(k, mu, names)                  # epsilon = 1e-4, the reference's default
+    for n, row in zip(names, g):
+        want = ref['ap_n_' + n]
+        err = np.max(np.abs(row - want))/np.max(np.abs(want))
+        # both sides difference P at +-1e-4: the 1e-5-level mismatch of P is smooth in the parameter and cancels, what
+        # is left is the rounding of the reference's own difference quotient
+        assert err < 5e-5, (n, err)
+
+
+def test_gradient_properties(models):
+    m = models['ap']
+    k = np.logspace(-2, np.log10(0.3), 12)
+    mu = np.linspace(0., 1., 5)
+    g = m.gradient(k, mu, 'fs')                   # broadcast grid, scalar name
+    assert g.shape == (1, 60)
+    # step-size independence where the model is smooth: O(eps^2) truncation
+    g2 = m.gradient(k, mu, ['fs', 'sigma8_z', 'f'], epsilon=[2e-4, 2e-4, 2e-4])
+    g1 = m.gradient(k, mu, ['fs', 'sigma8_z', 'f'])
+    assert np.max(np.abs(g1 - g2))/np.max(np.abs(g1)) < 1e-6
+    # f_so does nothing without the SO correction
+    assert np.all(m.gradient(k, mu, 'f_so') == 0.)
+    with pytest.raises(ValueError):
+        m.gradient(k, mu, ['not_a_parameter'])
+    with pytest.raises(ValueError):
+        m.gradient(k, mu, ['fs'], epsilon=0.)
