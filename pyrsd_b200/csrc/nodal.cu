@@ -37,7 +37,7 @@ struct NodalArgs {
 //   0..5 (L,L): h01 h02 h03 h04 f23 f33 | 6,7 cross of ImnOneLoop(P_vv, P_dd): h01 h02 | 8,9 its one-loop part
 //   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
 struct SpecML {
-    static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 14, NOUT = 21;
+    static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 14, NOUT = 21, THREADS = NL_THREADS;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
@@ -97,10 +97,12 @@ std::vector<ColSpec> ml_columns()
 
 // ------------------------------------------------------------ one-loop tables
 // slots: P_L of DIAG_R cosmologies; W columns: the operator's 4 kernels; accumulator 4 r + c
-static const int DIAG_R = 4;      // measured at batch 256: R = 4 (2 CTAs per SM) 1.71 ms, R = 3 (3 CTAs) 1.86 ms, R = 2 (3 CTAs) +23 %
+static const int DIAG_R = 4;      // measured at batch 256: R = 4 (2 CTAs per SM) 1.65 ms, R = 3 (3 CTAs) +9 %, R = 2 (3 CTAs) +23 %,
+                                  // R = 8 (one CTA of 512 threads per SM, 128 registers) +23 %
 struct SpecDiag {
     static const int NC = 4;      // I00, I01, I11 and P22bar = I23 + 2/3 I32 + 1/5 I33 (combined in W at build time)
-    static const int NSLOT = DIAG_R, MINB = DIAG_R <= 3 ? 3 : 2, NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
+    static const int NSLOT = DIAG_R, MINB = DIAG_R <= 3 ? 3 : (DIAG_R <= 4 ? 2 : 1), NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
+    static const int THREADS = DIAG_R <= 4 ? NL_THREADS : 2*NL_THREADS;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
@@ -126,14 +128,14 @@ struct SpecDiag {
 // wavefronts, but the kernel then runs into the P(a) reads and the global stream and gains only ~10 %; with the
 // interpolation ARITHMETIC in binary32 the h01-type cancellations amplify the independent 6e-8 errors to 1e-4.)
 template <class Spec>
-__global__ void __launch_bounds__(NL_THREADS, Spec::MINB)
+__global__ void __launch_bounds__(Spec::THREADS, Spec::MINB)
 k_nodal_apply(const NodalArgs g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tabs = reinterpret_cast<double*>(smem_raw);                 // [4][TAB_MPAD]
     double* PaS = tabs + Spec::NSLOT*TAB_MPAD;                             // [4][max_outer]
-    double* red = PaS + Spec::NSLOT*g.max_outer;                           // [NL_WARPS][NACC]
-    double* fin = red + NL_WARPS*Spec::NACC;                            // [NACC]
+    double* red = PaS + Spec::NSLOT*g.max_outer;                           // [(Spec::THREADS/32)][NACC]
+    double* fin = red + (Spec::THREADS/32)*Spec::NACC;                            // [NACC]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(fin + Spec::NACC + (Spec::NACC & 1));
 
     const int tile = blockIdx.x;
@@ -186,7 +188,7 @@ k_nodal_apply(const NodalArgs g)
             }
         }
         // ---- P(a) of the four spectra for every outer node of this k
-        for (int o = tid; o < n_out; o += NL_THREADS) {
+        for (int o = tid; o < n_out; o += Spec::THREADS) {
             const int j0 = g.a_j0[o0 + o];
             const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)));
             const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)) + 1);
@@ -201,7 +203,7 @@ k_nodal_apply(const NodalArgs g)
         double acc[Spec::NACC];
 #pragma unroll
         for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
-        for (; node < n1; node += NL_THREADS) {
+        for (; node < n1; node += Spec::THREADS) {
             const int pk = pk_next;
             const double2 c01 = c01_next, c23 = c23_next;
             double w[Spec::NW];
@@ -209,7 +211,7 @@ k_nodal_apply(const NodalArgs g)
 #pragma unroll
                 for (int c = 0; c < Spec::NW; c++) w[c] = w_next[c];
             }
-            const int64_t nx = node + NL_THREADS;
+            const int64_t nx = node + Spec::THREADS;
             if (nx < n1) {
                 pk_next = __ldg(g.b_pack + nx);
                 c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx));
@@ -251,7 +253,7 @@ k_nodal_apply(const NodalArgs g)
             const int src = Spec::source(tid, fac);
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NL_WARPS; w++) s += red[w*Spec::NACC + src];
+            for (int w = 0; w < (Spec::THREADS/32); w++) s += red[w*Spec::NACC + src];
             Spec::store(g, tile, ik, tid, fac*s);
         }
         // the next k's writes of PaS and red are ordered after this k's reads by the barrier after the next P(a) pass
@@ -271,7 +273,7 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     a.b_pack = geo.b_pack.p; a.b_coef = geo.b_coef.p;
     a.W = op.W.p; a.n_nodes = geo.n_nodes;
     a.tables = tables; a.slot_tab = slot_tab; a.out = out;
-    const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + Spec::NSLOT*geo.max_outer + (NL_WARPS + 1)*Spec::NACC + 2)*sizeof(double) + 16;
+    const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + Spec::NSLOT*geo.max_outer + ((Spec::THREADS/32) + 1)*Spec::NACC + 2)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_nodal_apply<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // k chunks: few enough to amortise the table staging, enough CTAs to fill 148 SMs x 2 when the batch is small
@@ -279,7 +281,7 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     nchunks = std::min(geo.nk, std::max(nchunks, (2400 + ntiles - 1)/ntiles));
     dim3 grid(ntiles, nchunks);
     ProfScope prof(ctx, prof_tag);
-    k_nodal_apply<Spec><<<grid, NL_THREADS, smem, ctx.stream>>>(a);
+    k_nodal_apply<Spec><<<grid, Spec::THREADS, smem, ctx.stream>>>(a);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
 }

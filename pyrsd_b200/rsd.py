@@ -205,6 +205,7 @@ class PTEngine(object):
         stoch = np.ascontiguousarray(stoch, dtype=np.float64).reshape(nw, NPAIR, NSTOCH)
         assert d_k.is_cuda and d_mu.is_cuda and d_k.dtype == torch.float64 and d_k.shape == d_mu.shape
         out = torch.empty((nw, d_k.numel()), dtype=torch.float64, device=d_k.device)
+        torch.cuda.current_stream(d_k.device).synchronize()      # the library runs on its own non-blocking stream
         cm = None if cmap is None else np.ascontiguousarray(cmap, dtype=np.int32)
         N.check(_L().prsd_galaxy_power_device(gal.ptr, spectra.ptr, result.ptr, nw, None if cm is None else cm.ctypes.data_as(_vp),
                                               par, stoch, d_k.numel(), _vp(d_k.data_ptr()), _vp(d_mu.data_ptr()),
@@ -216,7 +217,9 @@ class PTEngine(object):
         matrix ``cinv`` [n][n] (rsdfit/driver.py:780-802) -> [nw]"""
         on_dev = type(model).__module__.split('.')[0] == 'torch'
         if on_dev:
+            import torch
             m = model.contiguous().reshape(model.shape[0], -1)
+            torch.cuda.current_stream(m.device).synchronize()    # the library runs on its own non-blocking stream
             nw, n = m.shape
             ptr = _vp(m.data_ptr())
         else:

@@ -98,6 +98,38 @@ def _empty_like(p, shape, on_device):
     return np.empty(shape)
 
 
+class _CtxStream(object):
+    """Run the enclosed torch operations on the library's (non-blocking) stream: they are then ordered with the
+    library's kernels; the caller's current stream is joined on entry and on exit."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch = torch
+        sp = _vp()
+        N.check(N.lib().prsd_ctx_stream(ctx.ptr, C.byref(sp)))
+        self.dev = torch.device('cuda', ctx.device)
+        self.ext = torch.cuda.ExternalStream(sp.value, device=self.dev)
+
+    def __enter__(self):
+        self.ext.wait_stream(self.torch.cuda.current_stream(self.dev))
+        self.cm = self.torch.cuda.stream(self.ext)
+        self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.cm.__exit__(*exc)
+        self.torch.cuda.current_stream(self.dev).wait_stream(self.ext)
+        return False
+
+
+class _NoStream(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class PkmuGrid(object):
     """A 2D grid of (k, mu): bin centres, mean k and mu of every cell and its number of modes
     (``rsd/transfers/__init__.py:5-82``)."""
@@ -217,8 +249,9 @@ class GriddedWedgeTransfer(object):
         op = self._operator()
         p, multi, dev = _prepare(power, self.grid.shape)
         nw = p.shape[0]
-        out = _empty_like(p, (nw, self.N2, self.grid.Nk), dev)
-        N.check(_L().prsd_gridop_apply(op.ptr, nw, _ptr(p), _ptr(out), int(dev)))
+        with (_CtxStream(self._ctx) if dev else _NoStream()):
+            out = _empty_like(p, (nw, self.N2, self.grid.Nk), dev)
+            N.check(_L().prsd_gridop_apply(op.ptr, nw, _ptr(p), _ptr(out), int(dev)))
         if dev:
             return out if multi else out[0]
         out = np.ascontiguousarray(np.swapaxes(out, 1, 2))
@@ -378,37 +411,38 @@ class WindowFunctionTransfer(GriddedMultipoleTransfer):
         op = self._operator()
         p, multi, dev = _prepare(power, self.grid.shape)
         nw, nell, Nk, Npad = p.shape[0], len(self.ells), self.grid.Nk, len(self.k_pad)
-        poles = _empty_like(p, (nw, nell, Nk), dev)
-        N.check(_L().prsd_gridop_apply(op.ptr, nw, _ptr(p), _ptr(poles), int(dev)))
-        # copy over with zeros
-        padded = _empty_like(p, (nw, nell, Npad), dev)
-        padded[..., :Nk] = poles
-        padded[..., Nk:] = 0.
-        xi = xic = None
-        if no_convolution:
-            conv = padded
-        else:
-            win = self._window()
-            conv = _empty_like(p, (nw, nell, Npad), dev)
-            if return_xi and not dev:
-                xi, xic = np.empty((nw, nell, Npad)), np.empty((nw, nell, Npad))
-            N.check(_L().prsd_window_apply(win.ptr, nw, _ptr(padded), _ptr(conv), 1 if dry_run else 0, int(dev),
-                                           None if xi is None else _ptr(xi), None if xic is None else _ptr(xic)))
-        if k_out is not None:
-            k_out = N.as_f64(k_out)
-            if dev:
-                res = _empty_like(p, (nw, nell, len(k_out)), True)
-                N.check(_L().prsd_spline_resample_device(self._ctx.ptr, nw*nell, Npad, self.k_pad, _ptr(conv), len(k_out),
-                                                         k_out, _ptr(res)))
+        with (_CtxStream(self._ctx) if (dev or k_out is not None) else _NoStream()):
+            poles = _empty_like(p, (nw, nell, Nk), dev)
+            N.check(_L().prsd_gridop_apply(op.ptr, nw, _ptr(p), _ptr(poles), int(dev)))
+            # copy over with zeros
+            padded = _empty_like(p, (nw, nell, Npad), dev)
+            padded[..., :Nk] = poles
+            padded[..., Nk:] = 0.
+            xi = xic = None
+            if no_convolution:
+                conv = padded
             else:
-                import torch
-                d_in = torch.from_numpy(conv).to('cuda:%d' % self._ctx.device)
-                d_res = torch.empty((nw, nell, len(k_out)), dtype=torch.float64, device=d_in.device)
-                N.check(_L().prsd_spline_resample_device(self._ctx.ptr, nw*nell, Npad, self.k_pad, _ptr(d_in), len(k_out),
-                                                         k_out, _ptr(d_res)))
-                res = d_res.cpu().numpy()
-        else:
-            res = conv
+                win = self._window()
+                conv = _empty_like(p, (nw, nell, Npad), dev)
+                if return_xi and not dev:
+                    xi, xic = np.empty((nw, nell, Npad)), np.empty((nw, nell, Npad))
+                N.check(_L().prsd_window_apply(win.ptr, nw, _ptr(padded), _ptr(conv), 1 if dry_run else 0, int(dev),
+                                               None if xi is None else _ptr(xi), None if xic is None else _ptr(xic)))
+            if k_out is not None:
+                k_out = N.as_f64(k_out)
+                if dev:
+                    res = _empty_like(p, (nw, nell, len(k_out)), True)
+                    N.check(_L().prsd_spline_resample_device(self._ctx.ptr, nw*nell, Npad, self.k_pad, _ptr(conv), len(k_out),
+                                                             k_out, _ptr(res)))
+                else:
+                    import torch
+                    d_in = torch.from_numpy(conv).to('cuda:%d' % self._ctx.device)
+                    d_res = torch.empty((nw, nell, len(k_out)), dtype=torch.float64, device=d_in.device)
+                    N.check(_L().prsd_spline_resample_device(self._ctx.ptr, nw*nell, Npad, self.k_pad, _ptr(d_in), len(k_out),
+                                                             k_out, _ptr(d_res)))
+                    res = d_res.cpu().numpy()
+            else:
+                res = conv
         if dev:
             return res if multi else res[0]
         res = np.ascontiguousarray(np.swapaxes(res, 1, 2))

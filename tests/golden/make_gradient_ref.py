@@ -20,7 +20,9 @@ import make_galaxy_ref as G  # noqa: E402
 
 ANALYTIC = ['fs', 'fcB', 'fsB', 'sigma_c', 'NcBs', 'NsBsB', 'alpha_par', 'alpha_perp']
 ANALYTIC_SO = ANALYTIC + ['f_so', 'sigma_so']
-NUMERICAL = ['sigma8_z', 'f', 'b1_cA', 'b1_sB', 'sigma_sA', 'sigma_sB']
+# fsB: the reference's analytic form (derivatives/fsB.py:14-15) has the satellite-satellite part only and omits the
+# dependence of the central-satellite term on fsB (compare fcB.py:16-17) -- its finite difference is the pin
+NUMERICAL = ['sigma8_z', 'f', 'b1_cA', 'b1_sB', 'sigma_sA', 'sigma_sB', 'fsB']
 
 
 def main():
