@@ -8,25 +8,49 @@
 namespace prsd {
 
 // ------------------------------------------------------------------------------------------------ GridOp
-// one warp per (walker, k): lanes stride over mu, so that the rows of P and of the weights are read coalesced
+// One CTA per (tile of KT k rows, group of GRID_WPC walkers): the tiles of the weights are staged in shared memory once
+// and reused for every walker of the group, whose tile of P follows (coalesced loads; row stride nmu + 1 doubles, so
+// that threads walk different rows without bank conflicts); every (k, bin) pair is one thread's dot product over mu.
+static const int GRID_WPC = 8;
+
 __global__ void __launch_bounds__(128)
-k_grid_reduce(int nk, int nmu, int nbin, const double* __restrict__ w, const double* __restrict__ power,
+k_grid_reduce(int nw, int nk, int nmu, int nbin, int KT, const double* __restrict__ w, const double* __restrict__ power,
               double* __restrict__ out)
 {
-    const int wlk = blockIdx.y, lane = threadIdx.x & 31;
-    const int k = blockIdx.x*4 + (threadIdx.x >> 5);
-    if (k >= nk) return;
-    const double* P = power + ((size_t)wlk*nk + k)*nmu;
+    extern __shared__ double sm_grid[];
+    const int ld = nmu + 1;
+    double* Pt = sm_grid;                         // [KT][ld]
+    double* Wt = sm_grid + (size_t)KT*ld;         // [nbin][KT][ld]
+    const int k0 = blockIdx.x*KT, tid = threadIdx.x;
+    const int rows = min(KT, nk - k0);
+    const int cells = rows*nmu;
     for (int b = 0; b < nbin; b++) {
-        const double* wb = w + ((size_t)b*nk + k)*nmu;
-        double s = 0.0;
-        for (int m = lane; m < nmu; m += 32) {
-            const double ww = wb[m];
-            if (ww != 0.0) s = fma(ww, P[m], s);         // weight 0 = null grid point: P may be anything there
+        const double* wb = w + ((size_t)b*nk + k0)*nmu;
+        for (int i = tid; i < cells; i += blockDim.x) {
+            const int r = i/nmu, m = i - r*nmu;
+            Wt[((size_t)b*KT + r)*ld + m] = wb[i];
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) out[((size_t)wlk*nbin + b)*nk + k] = s;
+    }
+    const int w_end = min(nw, (int)(blockIdx.y + 1)*GRID_WPC);
+    for (int wlk = blockIdx.y*GRID_WPC; wlk < w_end; wlk++) {
+        const double* P = power + ((size_t)wlk*nk + k0)*nmu;
+        __syncthreads();                          // previous walker's dot products are done with Pt
+        for (int i = tid; i < cells; i += blockDim.x) {
+            const int r = i/nmu, m = i - r*nmu;
+            Pt[r*ld + m] = P[i];
+        }
+        __syncthreads();
+        for (int item = tid; item < rows*nbin; item += blockDim.x) {
+            const int b = item/rows, r = item - b*rows;
+            const double* pr = Pt + r*ld;
+            const double* wr = Wt + ((size_t)b*KT + r)*ld;
+            double s = 0.0;
+            for (int m = 0; m < nmu; m++) {
+                const double ww = wr[m];
+                if (ww != 0.0) s = fma(ww, pr[m], s);    // weight 0 = null grid point: P may be anything there
+            }
+            out[((size_t)wlk*nbin + b)*nk + k0 + r] = s;
+        }
     }
 }
 
@@ -43,7 +67,13 @@ void GridOp::apply(int nw, const double* d_power, double* d_out)
 {
     if (nw <= 0) return;
     ProfScope prof(*ctx, PROF_GALAXY);
-    k_grid_reduce<<<dim3((nk + 3)/4, nw), 128, 0, ctx->stream>>>(nk, nmu, nbin, w.p, d_power, d_out);
+    int KT = 32;
+    auto need = [&](int kt) { return (size_t)(1 + nbin)*kt*(nmu + 1)*sizeof(double); };
+    while (KT > 1 && need(KT) > 96*1024) KT /= 2;
+    const size_t smem = need(KT);
+    PRSD_REQUIRE(smem <= ctx->smem_optin, "GridOp: %d bins x %d mu need %zu B of shared memory per k row", nbin, nmu, smem);
+    if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_grid_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_reduce<<<dim3((nk + KT - 1)/KT, (nw + GRID_WPC - 1)/GRID_WPC), 128, smem, ctx->stream>>>(nw, nk, nmu, nbin, KT, w.p, d_power, d_out);
     PRSD_CUDA(cudaGetLastError());
     ctx->launches++;
 }

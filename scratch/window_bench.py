@@ -40,3 +40,15 @@ for name, fn in (('grid multipoles + window + spline', lambda: tr(P, k_out=k_out
     fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(5): fn()
     torch.cuda.synchronize(); print('%s: %.2f ms per step' % (name, 1e3*(time.perf_counter() - t0)/5))
+
+# kernel-family breakdown of one likelihood step (CUDA events inside the library)
+import ctypes as C
+from pyrsd_b200 import _native as N
+L = N.lib()
+N.check(L.prsd_ctx_profile(eng.ctx.ptr, 1))
+chi2 = eng.galaxy_window_chi2(gal, sp, res, wpar, data['stoch'], tr, k_out, d, cinv, cmap=cmap)
+ms, cnt = np.zeros(8), np.zeros(8, dtype=np.int64)
+L.prsd_ctx_profile_read.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.float64), np.ctypeslib.ndpointer(dtype=np.int64)]
+N.check(L.prsd_ctx_profile_read(eng.ctx.ptr, ms, cnt))
+N.check(L.prsd_ctx_profile(eng.ctx.ptr, 0))
+print('families [IK, linear, zel, galaxy(+transfers), splines, fftlog, ML, diag] ms:', np.round(ms, 3), cnt)
