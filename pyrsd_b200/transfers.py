@@ -449,3 +449,55 @@ class WindowFunctionTransfer(GriddedMultipoleTransfer):
         if return_xi:
             return (res if multi else res[0]), xi, xic
         return res if multi else res[0]
+
+
+# ------------------------------------------------------------------------- continuous-model transfers
+def simpson_weights(x):
+    """weights w with ``SimpsIntegrate(x, y) == w @ y`` for an ODD number of samples (DiscreteQuad.cpp:3-21, 40-66):
+    per pair of intervals (h0, h1): (h0 + h1)/6 * [2 - h1/h0, (h0 + h1)^2/(h0 h1), 2 - h0/h1]"""
+    x = np.asarray(x, dtype=float)
+    if len(x) % 2 == 0 or len(x) < 3:
+        raise ValueError("Simpson weights need an odd number (>= 3) of samples")
+    h = np.diff(x)
+    h0, h1 = h[0::2], h[1::2]
+    hsum = h0 + h1
+    w = np.zeros(len(x))
+    w[0:-2:2] += hsum/6.*(2. - h1/h0)
+    w[1:-1:2] += hsum/6.*hsum*hsum/(h0*h1)
+    w[2::2] += hsum/6.*(2. - h0/h1)
+    return w
+
+
+class MultipoleTransfer(GriddedMultipoleTransfer):
+    """P(k, mu) sampled on ``k`` x ``linspace(0, 1, Nmu)`` -> P_ell(k) = (2 ell + 1) int_0^1 L_ell P dmu by Simpson's
+    rule (``rsd/transfers/poles.py:8-69``: ``pygcl.SimpsIntegrate`` row by row); Nmu is made odd as the reference
+    does.  ``GalaxySpectrum.poles`` fuses the same rule behind the assembly kernel; this class serves P(k, mu) arrays
+    that already exist."""
+
+    def __init__(self, k, ells, Nmu=40, context=None):
+        if Nmu % 2 == 0:
+            Nmu += 1
+        k = np.asarray(k, dtype=float)
+        mu = np.linspace(0., 1., Nmu, endpoint=True)
+        grid_k, grid_mu = np.meshgrid(k, mu, indexing='ij')
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            grid = PkmuGrid([k, mu], grid_k, grid_mu, np.ones_like(grid_k))
+        GriddedMultipoleTransfer.__init__(self, grid, ells, context=context)
+
+    def _weights(self):
+        w = simpson_weights(self.grid.mu_cen)
+        self._empty = np.zeros((len(self.ells), self.grid.Nk), dtype=bool)
+        return np.ascontiguousarray(self.legendre_weights*w[None, None, :])
+
+
+class WedgeTransfer(GriddedWedgeTransfer):
+    """P(k, mu) sampled on ``k`` x ``linspace(0, 1, Nmu + 1)`` -> the plain mean over the samples of every wide mu
+    bin (``rsd/transfers/wedges.py:7-108``)."""
+
+    def __init__(self, k, mu_bounds, Nmu=40, context=None):
+        k = np.asarray(k, dtype=float)
+        mu = np.linspace(0., 1., Nmu + 1, endpoint=True)
+        grid_k, grid_mu = np.meshgrid(k, mu, indexing='ij')
+        grid = PkmuGrid([k, mu], grid_k, grid_mu, np.ones_like(grid_k))
+        GriddedWedgeTransfer.__init__(self, grid, mu_bounds, context=context)

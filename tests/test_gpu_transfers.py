@@ -175,3 +175,29 @@ def test_survey_likelihood_chain_on_device(golden):
     assert np.allclose(chi2, chi2_ref, rtol=1e-6)
     assert np.argmin(chi2) == 2
     assert np.allclose(engine.chi2(ref, data, cinv), chi2_ref, rtol=1e-12)
+
+
+def test_continuous_multipole_and_wedge_transfers(oracle):
+    """MultipoleTransfer (Simpson over mu, rsd/transfers/poles.py) and WedgeTransfer (rsd/transfers/wedges.py) on the
+    device against the reference C++ SimpsIntegrate / a plain NumPy mean"""
+    from pyrsd_b200 import transfers as TR
+    from scipy.special import legendre
+    k = np.logspace(-2, np.log10(0.4), 37)
+    mt = TR.MultipoleTransfer(k, [0, 2, 4], Nmu=40)
+    mu = mt.grid.mu_cen
+    assert len(mu) == 41
+    P = synthetic_power(k[:, None], mu[None, :])
+    got = mt(P)
+    assert got.shape == (37, 3)
+    for i, ell in enumerate([0, 2, 4]):
+        kern = (2*ell + 1.)*legendre(ell)(mu)
+        ref = np.array([oracle.SimpsIntegrate(mu, kern*row) for row in P])
+        assert np.max(np.abs(got[:, i] - ref)) < 1e-12*np.max(np.abs(P))
+    bounds = [(0., 0.2), (0.2, 0.4), (0.4, 0.6), (0.6, 0.8), (0.8, 1.0)]
+    wt = TR.WedgeTransfer(k, list(bounds), Nmu=40)
+    mug = wt.grid.mu_cen
+    Pw = synthetic_power(k[:, None], mug[None, :])
+    got = wt(Pw)
+    for b, (lo, hi) in enumerate(bounds):
+        sel = (mug >= lo) & (mug < (1.0005 if hi == 1.0 else hi))
+        assert np.max(np.abs(got[:, b] - Pw[:, sel].mean(axis=1))) < 1e-12*np.max(np.abs(Pw))

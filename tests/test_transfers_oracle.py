@@ -103,3 +103,44 @@ def test_window_kernel_matrix_matches_restatement():
     assert relmax(conv([0, 2, 4], r, xi), REF['a_xi_conv']) < 1e-14
     with pytest.raises(ValueError):
         conv([0, 2, 4], r, xi[:, :2])
+
+
+def test_simpson_weights_match_reference_SimpsIntegrate(oracle):
+    """the folded Simpson weights of MultipoleTransfer against the reference C++ SimpsIntegrate (DiscreteQuad.cpp:40-66)"""
+    from pyrsd_b200.transfers import simpson_weights
+    rng = np.random.default_rng(3)
+    for n in (3, 11, 41):
+        x = np.linspace(0., 1., n)
+        y = rng.normal(size=n)
+        assert abs(simpson_weights(x) @ y - oracle.SimpsIntegrate(x, y)) < 1e-14
+        xs = np.sort(rng.random(n))              # uneven spacing
+        assert abs(simpson_weights(xs) @ y - oracle.SimpsIntegrate(xs, y)) < 1e-12
+    with pytest.raises(ValueError):
+        simpson_weights(np.linspace(0., 1., 40))
+
+
+def test_continuous_transfer_weights():
+    from pyrsd_b200 import transfers as TR
+    from scipy.special import legendre
+    k = np.logspace(-2, -0.4, 12)
+    mt = TR.MultipoleTransfer.__new__(TR.MultipoleTransfer)
+    TR.MultipoleTransfer.__init__(mt, k, [0, 2, 4], Nmu=40, context=object())
+    assert mt.grid.Nmu == 41
+    w = mt._weights()
+    mu = mt.grid.mu_cen
+    P = (1. + 0.5*mu[None, :]**2)**2*(1. + k[:, None])
+    got = np.einsum('bkm,km->kb', w, P)
+    # Kaiser-like input: P_0 = (1 + b/3 + b^2/20 ...) known in closed form: int (1 + mu^2/2)^2 = 1 + 1/3 + 1/20
+    assert np.allclose(got[:, 0], (1. + 1./3 + 1./20)*(1. + k), rtol=1e-6)
+    ref2 = np.array([np.dot(TR.simpson_weights(mu), 5.*legendre(2)(mu)*row) for row in P])
+    assert np.allclose(got[:, 1], ref2, rtol=1e-13)
+    wt = TR.WedgeTransfer.__new__(TR.WedgeTransfer)
+    bounds = [(0., 0.2), (0.2, 0.4), (0.4, 0.6), (0.6, 0.8), (0.8, 1.0)]
+    TR.WedgeTransfer.__init__(wt, k, list(bounds), Nmu=40, context=object())
+    ww = wt._weights()
+    assert ww.shape == (5, 12, 41) and np.allclose(ww.sum(axis=-1), 1.)
+    # wedges.py:84-95: plain mean of the samples with lo <= mu < hi (the last bin includes mu = 1)
+    mug = wt.grid.mu_cen
+    for b, (lo, hi) in enumerate(bounds):
+        sel = (mug >= lo) & (mug < (1.0005 if hi == 1.0 else hi))
+        assert np.allclose(ww[b, 0], sel/sel.sum())
