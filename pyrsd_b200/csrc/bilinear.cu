@@ -173,6 +173,14 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     g->wgt.upload(wgt, s);
     g->b_coef.upload(b_coef, s);
     {
+        // s = sum_m m c_m exactly reproduces the abscissa of a Lagrange rule of degree >= 1
+        std::vector<double> bs(b_j0.size()), as(H.a_j0.size());
+        for (size_t i = 0; i < bs.size(); i++) bs[i] = b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3];
+        for (size_t i = 0; i < as.size(); i++) as[i] = H.a_coef[4*i + 1] + 2.0*H.a_coef[4*i + 2] + 3.0*H.a_coef[4*i + 3];
+        g->b_s.upload(bs, s);
+        g->a_s.upload(as, s);
+    }
+    {
         std::vector<int> pack(b_j0.size());
         for (size_t i = 0; i < b_j0.size(); i++) {
             PRSD_REQUIRE(b_j0[i] >= 0 && b_j0[i] < 4096 && n_ol[i] >= 0 && n_ol[i] < (1 << 19), "node index does not fit the packed stream");

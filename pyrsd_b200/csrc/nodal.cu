@@ -17,9 +17,9 @@ struct NodalArgs {
     const int64_t* outer_off;
     const int64_t* node_off;
     const int* a_j0;
-    const double* a_coef;
+    const double* a_s;      // stencil coordinate of every outer node
     const int* b_pack;      // (outer index << 12) | stencil start
-    const double* b_coef;   // Lagrange coefficients, 4 per node
+    const double* b_s;      // stencil coordinate of every node: the Lagrange coefficients are lagrange4(s)
     const double* W;        // [NW][n_nodes]
     int64_t n_nodes;
     const double* tables;
@@ -176,12 +176,11 @@ k_nodal_apply(const NodalArgs g)
         // shared-memory reads depend on them, and an exposed L2 round trip per node was the largest stall
         int64_t node = n0 + tid;
         int pk_next = 0;
-        double2 c01_next = make_double2(0.0, 0.0), c23_next = c01_next;
+        double s_next = 0.0;
         double w_next[Spec::PREFETCH_W ? Spec::NW : 1];
         if (node < n1) {
             pk_next = __ldg(g.b_pack + node);
-            c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node));
-            c23_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*node) + 1);
+            s_next = __ldg(g.b_s + node);
             if (Spec::PREFETCH_W) {
 #pragma unroll
                 for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
@@ -190,12 +189,12 @@ k_nodal_apply(const NodalArgs g)
         // ---- P(a) of the four spectra for every outer node of this k
         for (int o = tid; o < n_out; o += Spec::THREADS) {
             const int j0 = g.a_j0[o0 + o];
-            const double2 c01 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)));
-            const double2 c23 = __ldg(reinterpret_cast<const double2*>(g.a_coef + 4*(o0 + o)) + 1);
+            double c[4];
+            lagrange4(__ldg(g.a_s + o0 + o), c);
 #pragma unroll
             for (int s = 0; s < Spec::NSLOT; s++) {
                 const double* t = tabs + s*TAB_MPAD + j0;
-                PaS[s*g.max_outer + o] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
+                PaS[s*g.max_outer + o] = fma(c[3], t[3], fma(c[2], t[2], fma(c[1], t[1], c[0]*t[0])));
             }
         }
         __syncthreads();
@@ -205,7 +204,8 @@ k_nodal_apply(const NodalArgs g)
         for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
         for (; node < n1; node += Spec::THREADS) {
             const int pk = pk_next;
-            const double2 c01 = c01_next, c23 = c23_next;
+            double c[4];
+            lagrange4(s_next, c);
             double w[Spec::NW];
             if (Spec::PREFETCH_W) {
 #pragma unroll
@@ -214,8 +214,7 @@ k_nodal_apply(const NodalArgs g)
             const int64_t nx = node + Spec::THREADS;
             if (nx < n1) {
                 pk_next = __ldg(g.b_pack + nx);
-                c01_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx));
-                c23_next = __ldg(reinterpret_cast<const double2*>(g.b_coef + 4*nx) + 1);
+                s_next = __ldg(g.b_s + nx);
                 if (Spec::PREFETCH_W) {
 #pragma unroll
                     for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + nx);
@@ -230,7 +229,7 @@ k_nodal_apply(const NodalArgs g)
 #pragma unroll
             for (int s = 0; s < Spec::NSLOT; s++) {
                 const double* t = tabs + s*TAB_MPAD + j0;
-                pb[s] = fma(c23.y, t[3], fma(c23.x, t[2], fma(c01.y, t[1], c01.x*t[0])));
+                pb[s] = fma(c[3], t[3], fma(c[2], t[2], fma(c[1], t[1], c[0]*t[0])));
                 pa[s] = PaS[s*g.max_outer + ol];
             }
             Spec::accumulate(acc, pa, pb, w);
@@ -269,8 +268,8 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     NodalArgs a;
     a.nk = geo.nk; a.max_outer = geo.max_outer; a.kchunk = kchunk; a.nrow = nrow;
     a.outer_off = geo.outer_off.p; a.node_off = geo.node_off.p;
-    a.a_j0 = geo.a_j0.p; a.a_coef = geo.a_coef.p;
-    a.b_pack = geo.b_pack.p; a.b_coef = geo.b_coef.p;
+    a.a_j0 = geo.a_j0.p; a.a_s = geo.a_s.p;
+    a.b_pack = geo.b_pack.p; a.b_s = geo.b_s.p;
     a.W = op.W.p; a.n_nodes = geo.n_nodes;
     a.tables = tables; a.slot_tab = slot_tab; a.out = out;
     const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + Spec::NSLOT*geo.max_outer + ((Spec::THREADS/32) + 1)*Spec::NACC + 2)*sizeof(double) + 16;
