@@ -263,7 +263,9 @@ def run_gpu(args):
     # ---- roofline of the mode-coupling operators: algorithmic FP64 flops = declared nodes x
     #      cosmologies x flops per (node, cosmology) of the implemented rule, FMA = 2
     pms, pc = prof
-    FLOP_ML, FLOP_DIAG, FLOP_IK = 105, 17, 67
+    # per (node, cosmology): 4-point table read of every spectrum (7 flop each) + products/accumulation + the Lagrange
+    # coefficients formed from the stencil coordinate (13 flop per node, shared by the 4 cosmologies of a one-loop CTA)
+    FLOP_ML, FLOP_DIAG, FLOP_IK = 109, 20.25, 67
     kern = {
         'k_nodal_apply<SpecML>': dict(fam=6, flops=info['nodes_ml_half']*B*FLOP_ML, pipe='fp64 DFMA'),
         'k_nodal_apply<SpecDiag>': dict(fam=7, flops=info['nodes_oneloop']*B*FLOP_DIAG, pipe='fp64 DFMA'),

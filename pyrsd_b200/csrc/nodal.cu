@@ -30,47 +30,50 @@ struct NodalArgs {
 // ------------------------------------------------------------------ ImnOneLoop
 // slots: 0 P_L, 1 P_dd, 2 P_dv, 3 P_vv.  W columns (ml_columns()):
 //   0..6   f(+v)  of h01 h02 h03 h04 f23 f32 f33               -> P_1(a) P_2(b)
-//   7..13  f(-v)  of the same                                  -> P_1(b) P_2(a)
-// products symmetric in (a, b) use the sum of the two (formed in registers: the FP64 pipe has room, the
-// load pipe does not)
+//   7, 8   f(-v)  of h01 h02                                   -> P_1(b) P_2(a)
+// h03, h04, f23, f32, f33 depend on u^2, v^2 and (u^2 - v^2) only: their f(-v) column IS the f(+v) one, so the
+// two halves share it (9 columns streamed instead of 14).
 // accumulators:
 //   0..5 (L,L): h01 h02 h03 h04 f23 f33 | 6,7 cross of ImnOneLoop(P_vv, P_dd): h01 h02 | 8,9 its one-loop part
 //   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
 struct SpecML {
-    static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 14, NOUT = 21, THREADS = NL_THREADS;
+    static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 9, NOUT = 21, THREADS = NL_THREADS;
     static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
         const double La = pa[0], Da = pa[1], Va = pa[2], Wa = pa[3];
         const double Lb = pb[0], Db = pb[1], Vb = pb[2], Wb = pb[3];
-        const double* wp = w;
-        const double* wn = w + 7;
-        const double ws[6] = {wp[0] + wn[0], wp[1] + wn[1], wp[2] + wn[2], wp[3] + wn[3], wp[4] + wn[4], wp[6] + wn[6]};
-        const double ll = La*Lb;
-#pragma unroll
-        for (int i = 0; i < 6; i++) acc[i] = fma(ws[i], ll, acc[i]);
+        const double h01p = w[0], h02p = w[1], h01n = w[7], h02n = w[8];
+        // (L, L): both halves of every kernel
+        const double ll = La*Lb, ll2 = ll + ll;
+        acc[0] = fma(h01p + h01n, ll, acc[0]);
+        acc[1] = fma(h02p + h02n, ll, acc[1]);
+        acc[2] = fma(w[2], ll2, acc[2]);
+        acc[3] = fma(w[3], ll2, acc[3]);
+        acc[4] = fma(w[4], ll2, acc[4]);
+        acc[5] = fma(w[6], ll2, acc[5]);
         // ImnOneLoop(P_vv, P_dd): cross = (P_L, P_dd) + (P_vv, P_L) (ImnOneLoop.cpp:130-148)
         const double cp = fma(La, Db, Wa*Lb), cn = fma(Lb, Da, Wb*La);
-        acc[6] = fma(wp[0], cp, fma(wn[0], cn, acc[6]));
-        acc[7] = fma(wp[1], cp, fma(wn[1], cn, acc[7]));
+        acc[6] = fma(h01p, cp, fma(h01n, cn, acc[6]));
+        acc[7] = fma(h02p, cp, fma(h02n, cn, acc[7]));
         const double op = Wa*Db, on = Wb*Da;
-        acc[8] = fma(wp[0], op, fma(wn[0], on, acc[8]));
-        acc[9] = fma(wp[1], op, fma(wn[1], on, acc[9]));
+        acc[8] = fma(h01p, op, fma(h01n, on, acc[8]));
+        acc[9] = fma(h02p, op, fma(h02n, on, acc[9]));
         // ImnOneLoop(P_dv): h03, h04
-        const double dp = La*Vb, dn = Lb*Va;
-        acc[10] = fma(wp[2], dp, fma(wn[2], dn, acc[10]));
-        acc[11] = fma(wp[3], dp, fma(wn[3], dn, acc[11]));
-        const double dd = Va*Vb;
-        acc[12] = fma(ws[2], dd, acc[12]);
-        acc[13] = fma(ws[3], dd, acc[13]);
+        const double dpn = fma(La, Vb, Lb*Va);
+        acc[10] = fma(w[2], dpn, acc[10]);
+        acc[11] = fma(w[3], dpn, acc[11]);
+        const double dd2 = 2.0*(Va*Vb);
+        acc[12] = fma(w[2], dd2, acc[12]);
+        acc[13] = fma(w[3], dd2, acc[13]);
         // ImnOneLoop(P_vv): f23, f32, f33
-        const double vp = La*Wb, vn = Lb*Wa;
-        acc[14] = fma(wp[4], vp, fma(wn[4], vn, acc[14]));
-        acc[15] = fma(wp[5], vp, fma(wn[5], vn, acc[15]));
-        acc[16] = fma(wp[6], vp, fma(wn[6], vn, acc[16]));
-        const double vv = Wa*Wb;
-        acc[17] = fma(ws[4], vv, acc[17]);
-        acc[18] = fma(ws[5], vv, acc[18]);
+        const double vpn = fma(La, Wb, Lb*Wa);
+        acc[14] = fma(w[4], vpn, acc[14]);
+        acc[15] = fma(w[5], vpn, acc[15]);
+        acc[16] = fma(w[6], vpn, acc[16]);
+        const double vv2 = 2.0*(Wa*Wb);
+        acc[17] = fma(w[4], vv2, acc[17]);
+        acc[18] = fma(w[6], vv2, acc[18]);
     }
     // out [c][7][3][nk]; t = output index 0..20 = 3 m + part; every output is one accumulator (x 2 for the cross
     // parts of the equal-spectra drivers).  The reference evaluates the LINEAR and ONE-LOOP parts of (m, n) = (3, 2)
@@ -90,8 +93,8 @@ struct SpecML {
 std::vector<ColSpec> ml_columns()
 {
     std::vector<ColSpec> c;
-    for (int sign : {+1, -1})
-        for (int id : {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33}) c.push_back({id, sign, NL_INV8PI2});
+    for (int id : {KID_H01, KID_H02, KID_K20A, KID_K20B, KID_F23, KID_F32, KID_F33}) c.push_back({id, +1, NL_INV8PI2});
+    for (int id : {KID_H01, KID_H02}) c.push_back({id, -1, NL_INV8PI2});
     return c;
 }
 
