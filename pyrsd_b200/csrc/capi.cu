@@ -680,9 +680,7 @@ int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
         g->dk.upload(k, npts, c.stream);
         g->dmu.upload(mu, npts, c.stream);
         g->dout.ensure((size_t)nw*npts);
-        g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p);
-        g->dout.download(out, (size_t)nw*npts, c.stream);
-        c.sync();
+        g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p, out);
     });
 }
 

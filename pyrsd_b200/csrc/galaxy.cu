@@ -608,13 +608,14 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     for (int i = 0; i < GAL_NSTOCH; i++) ks[i] = std::pow(10.0, l0 + (l1 - l0)*i/(GAL_NSTOCH - 1));
     d_kstoch.upload(ks, c.stream);
     d_kinterp.upload(k_interp, nki, c.stream);
+    h_kinterp.assign(k_interp, k_interp + nki);
     PRSD_REQUIRE(nki >= 4, "GalaxyModel: the PT interpolation grid needs at least 4 points");
     zel.build(c, km.data(), nkm);
     c.sync();
 }
 
 void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
-                        int npts, const double* d_k, const double* d_mu, double* d_out)
+                        int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out)
 {
     Context& c = *ctx;
     cudaStream_t s = c.stream;
@@ -656,58 +657,78 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     plin_m.ensure((size_t)nc*nkm);
     k_plin_model<<<dim3((nkm + 127)/128, nc), 128, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, nkm, d_km.p, plin_m.p);
     c.launches++;
-    // ---- Zel'dovich terms on the model grid at sigma8_z and at sigma8_z / D (Jennings fits)
-    DevBuf<double> plin_w((size_t)nw*nkm), plin_w2((size_t)nw*nkm);
-    k_scale_rows<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(nkm, plin_m.p, ratio1.p, d_cmap.p, plin_w.p);
-    k_scale_rows<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(nkm, plin_m.p, ratio2.p, d_cmap.p, plin_w2.p);
-    c.launches += 2;
-    zel1.ensure((size_t)nw*3*nkm);
-    zel2.ensure((size_t)nw*3*nkm);
-    zeldovich_eval_map(c, zel, nw, d_cmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio1.p, true, cfg.k0_low,
-                       plin_w.p, pt.scalars.p + 2, 4, zel1.p);
-    zeldovich_eval_map(c, zel, nw, d_cmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio2.p, true, cfg.k0_low,
-                       plin_w2.p, pt.scalars.p + 2, 4, zel2.p, true);       // only P00 is read at sigma8_z / D
-
     GalDev G;
     G.cfg = cfg;
     G.nkm = nkm; G.nk = nk; G.nspl = sp.nspl;
     G.lnkm0 = std::log(km[0]); G.inv_dlnkm = (nkm - 1)/std::log(km[nkm - 1]/km[0]);
-    {
-        std::vector<double> ki(nk);
-        PRSD_CUDA(cudaMemcpyAsync(ki.data(), d_kinterp.p, nk*sizeof(double), cudaMemcpyDeviceToHost, s));
-        c.sync();
-        G.lnki0 = std::log(ki[0]); G.inv_dlnki = (nk - 1)/std::log(ki[nk - 1]/ki[0]);
-    }
+    G.lnki0 = std::log(h_kinterp[0]); G.inv_dlnki = (nk - 1)/std::log(h_kinterp[nk - 1]/h_kinterp[0]);
     G.lnk1l0 = std::log(ONELOOP_KMIN); G.inv_dlnk1l = (ONELOOP_N - 1)/std::log(ONELOOP_KMAX/ONELOOP_KMIN);
-
-    base.ensure((size_t)nw*NB*nkm);
-    ProfScope prof_gal(c, PROF_GALAXY);
-    k_gal_base<<<dim3((nkm + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_cmap.p, d_par.p, ptspl.p, plin_m.p, sp.oneloop_spl.p,
-                                                         pt.scalars.p, zel1.p, zel2.p, base.p);
-    PRSD_CUDA(cudaGetLastError());
-    c.launches++;
-    pairspl.ensure((size_t)nw*GAL_NPAIR*16*nkm);
-    {
-        const size_t smem = (size_t)(45*nkm + 7*GAL_NSTOCH)*sizeof(double);
-        if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gal_moments<<<dim3(GAL_NPAIR, nw), 128, smem, s>>>(G, d_km.p, d_kstoch.p, d_cmap.p, d_par.p, d_stoch.p, pt.scalars.p,
-                                                             base.p, pairspl.p);
-        PRSD_CUDA(cudaGetLastError());
-        c.launches++;
-    }
-    grpspl.ensure((size_t)nw*GAL_NGRP*16*nkm);
-    grpconst.ensure((size_t)nw*GAL_NCONST);
-    k_gal_groups<<<dim3((16*nkm + 255)/256, nw), 256, 0, s>>>(nkm, d_par.p, pairspl.p, grpspl.p, grpconst.p);
-    PRSD_CUDA(cudaGetLastError());
-    c.launches++;
     last_G = G;
     last_nw = nw;
-    if (npts > 0) {
-        k_gal_pkmu<<<dim3((npts + 127)/128, nw), 128, 0, s>>>(G, d_km.p, d_par.p, grpspl.p, grpconst.p, npts, d_k, d_mu, d_out);
+
+    DevBuf<double> plin_w((size_t)nw*nkm), plin_w2((size_t)nw*nkm);
+    zel1.ensure((size_t)nw*3*nkm);
+    zel2.ensure((size_t)nw*3*nkm);
+    base.ensure((size_t)nw*NB*nkm);
+    pairspl.ensure((size_t)nw*GAL_NPAIR*16*nkm);
+    grpspl.ensure((size_t)nw*GAL_NGRP*16*nkm);
+    grpconst.ensure((size_t)nw*GAL_NCONST);
+    const size_t smem_mom = (size_t)(45*nkm + 7*GAL_NSTOCH)*sizeof(double);
+    if (smem_mom > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mom));
+
+    // ---- everything below is per walker: walkers [w0, w0 + n) of the batch
+    auto run_walkers = [&](int w0, int n) {
+        const int* cm = d_cmap.p + w0;
+        const double* pr = d_par.p + (size_t)w0*GAL_NPAR;
+        const double* st = d_stoch.p + (size_t)w0*GAL_NPAIR*GAL_NSTOCH;
+        double* pw1 = plin_w.p + (size_t)w0*nkm;
+        double* pw2 = plin_w2.p + (size_t)w0*nkm;
+        double* z1 = zel1.p + (size_t)w0*3*nkm;
+        double* z2 = zel2.p + (size_t)w0*3*nkm;
+        double* bs = base.p + (size_t)w0*NB*nkm;
+        double* ps = pairspl.p + (size_t)w0*GAL_NPAIR*16*nkm;
+        double* gs = grpspl.p + (size_t)w0*GAL_NGRP*16*nkm;
+        double* gc = grpconst.p + (size_t)w0*GAL_NCONST;
+        // Zel'dovich terms on the model grid at sigma8_z and at sigma8_z / D (Jennings fits)
+        k_scale_rows<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(nkm, plin_m.p, ratio1.p + w0, cm, pw1);
+        k_scale_rows<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(nkm, plin_m.p, ratio2.p + w0, cm, pw2);
+        c.launches += 2;
+        zeldovich_eval_map(c, zel, n, cm, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio1.p + w0, true, cfg.k0_low,
+                           pw1, pt.scalars.p + 2, 4, z1);
+        zeldovich_eval_map(c, zel, n, cm, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio2.p + w0, true, cfg.k0_low,
+                           pw2, pt.scalars.p + 2, 4, z2, true);             // only P00 is read at sigma8_z / D
+        ProfScope prof_gal(c, PROF_GALAXY);
+        k_gal_base<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(G, d_km.p, cm, pr, ptspl.p, plin_m.p, sp.oneloop_spl.p,
+                                                            pt.scalars.p, z1, z2, bs);
+        k_gal_moments<<<dim3(GAL_NPAIR, n), 128, smem_mom, s>>>(G, d_km.p, d_kstoch.p, cm, pr, st, pt.scalars.p, bs, ps);
+        k_gal_groups<<<dim3((16*nkm + 255)/256, n), 256, 0, s>>>(nkm, pr, ps, gs, gc);
+        c.launches += 3;
+        if (npts > 0) {
+            k_gal_pkmu<<<dim3((npts + 127)/128, n), 128, 0, s>>>(G, d_km.p, pr, gs, gc, npts, d_k, d_mu, d_out + (size_t)w0*npts);
+            c.launches++;
+        }
         PRSD_CUDA(cudaGetLastError());
-        c.launches++;
+    };
+
+    // With a host destination the walkers go in chunks: the device-to-host copy of a chunk (PCIe, the slow leg when
+    // full P(k, mu) grids leave the device) runs on the copy stream under the kernels of the next chunk.
+    const int chunk = (h_out && npts > 0 && nw >= 2*GAL_PIPE_CHUNK) ? GAL_PIPE_CHUNK : nw;
+    for (int w0 = 0; w0 < nw; w0 += chunk) {
+        const int n = std::min(chunk, nw - w0);
+        run_walkers(w0, n);
+        if (h_out && npts > 0) {
+            if (!copy_stream) {
+                PRSD_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+                PRSD_CUDA(cudaEventCreateWithFlags(&copy_event, cudaEventDisableTiming));
+            }
+            PRSD_CUDA(cudaEventRecord(copy_event, s));
+            PRSD_CUDA(cudaStreamWaitEvent(copy_stream, copy_event, 0));
+            PRSD_CUDA(cudaMemcpyAsync(h_out + (size_t)w0*npts, d_out + (size_t)w0*npts, sizeof(double)*(size_t)n*npts,
+                                      cudaMemcpyDeviceToHost, copy_stream));
+        }
     }
     c.sync();
+    if (h_out && npts > 0) PRSD_CUDA(cudaStreamSynchronize(copy_stream));
 }
 
 void GalaxyModel::poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
