@@ -614,6 +614,12 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     c.sync();
 }
 
+GalaxyModel::~GalaxyModel()
+{
+    if (copy_event) cudaEventDestroy(copy_event);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+}
+
 void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
                         int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out)
 {

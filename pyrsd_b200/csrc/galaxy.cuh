@@ -64,6 +64,9 @@ struct GalaxyModel {
     int last_nw = 0;
 
     GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmodel, int nkm_, const double* k_interp, int nk_interp_);
+    ~GalaxyModel();
+    GalaxyModel(const GalaxyModel&) = delete;
+    GalaxyModel& operator=(const GalaxyModel&) = delete;
 
     // P(k, mu) of `nw` walkers: walker w uses the tables of cosmology cmap[w] in (sp, pt).
     //   par    host [nw][GAL_NPAR]      stoch  host [nw][10][20]
