@@ -205,7 +205,7 @@ __global__ void k_plin_at(int nspl, const PlinParams* __restrict__ params, const
     out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
 }
 
-void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res)
+void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
 {
     Context& c = *ctx;
     cudaStream_t s = c.stream;
@@ -246,13 +246,13 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res)
         c.launches += 2;
     }
     sp.set_oneloop_tables(res.oneloop.p);
-    c.sync();
+    if (sync) c.sync();
 }
 
 void PTPlan::run(SpectraBatch& sp, PTResult& res)
 {
     PRSD_REQUIRE(!only_oneloop, "this plan only holds the one-loop stage");
-    run_oneloop(sp, res);
+    run_oneloop(sp, res, false);          // stage B is enqueued behind stage A without a host round trip
     Context& c = *ctx;
     cudaStream_t s = c.stream;
     const int nc = sp.ncosmo;
