@@ -213,3 +213,47 @@ def test_batch_consistency_and_scaling_property(cosmo, golden):
     for part, power in ((0, 2), (1, 3), (2, 4)):
         err = relerr_floor(ML[:, :, part, :], r[:, None, None]**power*ML[4][None, :, part, :], floor)
         assert err.max() < 1e-9
+
+
+def test_variant_cosmology_vs_tight_reference(golden):
+    """the fixed rule was tuned on the golden Planck15 spectrum: the same parity on a tilted one (delta = +0.05,
+    n_s = 0.93; tests/golden/make_tight_variant.py)"""
+    import os
+    from pyrsd_b200 import pygcl
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'oracle_tight_variant.npz')
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/oracle_tight_variant.npz not generated")
+    v = np.load(path)
+    params = {k[len('cosmo_'):]: float(golden[k]) for k in golden.files
+              if k.startswith('cosmo_') and k not in ('cosmo_k', 'cosmo_T', 'cosmo_sigma8', 'cosmo_tf')}
+    params['T_cmb'] = 2.7255
+    params['n_s'] = float(v['n_s'])
+    k_i = golden['cosmo_k']
+    T_i = golden['cosmo_T']*(k_i/0.05)**(0.5*float(v['delta']))
+    cosmo = pygcl.Cosmology(params, 0, float(golden['cosmo_sigma8']), k_i, T_i)
+    assert abs(cosmo.delta_H()/float(v['delta_H']) - 1) < 1e-6
+    plin = pygcl.LinearPS(cosmo, 0.)
+    k, floor = v['k'], v['plin_k']
+    assert np.max(np.abs(plin(k)/floor - 1)) < 1e-6
+    I, K, J = pygcl.Imn(plin), pygcl.Kmn(plin), pygcl.Jmn(plin)
+    for m in range(4):
+        for n in range(4):
+            err = relerr_floor(I(k, m, n), v['I'][4*m + n], floor)
+            assert err.max() < TOL, ('I', m, n, err.max())
+    spec = [(0, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 1, 1, 0), (0, 2, 1, 0), (1, 0, 0, 0), (1, 1, 0, 0),
+            (1, 0, 1, 0), (1, 1, 1, 0), (2, 0, 0, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1)]
+    for j, (m, n, t, p) in enumerate(spec):
+        err = relerr_floor(K(k, m, n, bool(t), p), v['K'][j], floor)
+        assert err.max() < TOL, ('K', m, n, t, p, err.max())
+    sel = k <= 1.0
+    for j, (m, n) in enumerate([(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (2, 0)]):
+        kk = k if (m, n) in ((0, 0), (0, 1), (1, 1)) else k[sel]
+        ref = v['J'][j] if len(kk) == len(k) else v['J'][j][sel]
+        assert np.max(np.abs(J(kk, m, n)/ref - 1)) < TOL, ('J', m, n)
+    idx = v['oneloop_idx']
+    for j, o in enumerate([pygcl.OneLoopPdd(plin), pygcl.OneLoopPdv(plin), pygcl.OneLoopPvv(plin), pygcl.OneLoopP22Bar(plin)]):
+        err = relerr_floor(o.GetOneLoopPower()[idx], v['oneloop'][j], v['oneloop_plin'])
+        lowk = idx < 780
+        assert err[lowk].max() < TOL, ('one-loop', j, err[lowk].max())
+        assert err.max() < 2e-4, ('one-loop', j, err.max())
+    assert abs(plin.VelocityDispersion()/float(v['sigma_v2']) - 1) < TOL       # sigma_v^2 (PowerSpectrum.cpp:56-58)
