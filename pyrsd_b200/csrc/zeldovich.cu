@@ -81,7 +81,7 @@ __global__ void k_zel_fold(int nk, const double* __restrict__ g, const int* __re
 // values of that l in registers and reuses them for the ZW rows.  For n >= 1 the three spectra need
 //   S_p = sum_n n^p rho^n G_n,  p = 0, 1, 2,   rho = k Y / r
 // (Fsec of ZeldovichPS.cpp:198-203, 241-246, 285-296 expanded in powers of n), evaluated by Horner.
-static const int ZW = 8;
+static const int ZW = 8;      // 4 rows per CTA at two CTAs per SM (128 registers) measured the same: not occupancy-bound
 
 // ONLY00: P00 alone (the Jennings fits need P00 at a second normalisation, power_dm.py:676-718); P01, P11 are
 // written as 0
@@ -137,12 +137,6 @@ k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __res
         const double r = rr[l];
         const double r15 = r*sqrt(r);
         const double kr = k/r;
-        // n G_n and n^2 G_n are walker independent: formed once per r
-        double g1[16], g2[16];
-        if (!ONLY00) {
-#pragma unroll
-            for (int n = 1; n < 16; n++) { g1[n] = (double)n*gl[n]; g2[n] = (double)(n*n)*gl[n]; }
-        }
 #pragma unroll
         for (int j = 0; j < ZW; j++) {
             const int c = s_c[j];
@@ -171,13 +165,19 @@ k_zeldovich(int nk, int nrow, const double* __restrict__ kk, const double* __res
             double a11 = g0*(c11*E - 4.0*k4*s2*s2*E0);
             // n >= 1: v_n = r^1.5 E rho^n G_n;  P00 += v_n, P01 += v_n (kxx + kyy - 2n),
             //         P11 += v_n (c11 - 4 n (kxx - 1) - 4 n kyy + 4 n (n - 1))
-            double S0 = 0.0, S1 = 0.0, S2 = 0.0;
+            // S0 = sum_n G_n rho^(n-1), S1 = sum_n n G_n rho^(n-1), S2 = sum_n n^2 G_n rho^(n-1) from ONE Horner
+            // recurrence carrying the polynomial P = S0 and its derivatives (P1 = P', P2 = P''/2):
+            // S1 = (rho P)' = P + rho P',  S2 = S1 + rho (rho P)'' = P + 3 rho P' + rho^2 P''
+            double S0 = 0.0, P1 = 0.0, P2 = 0.0;
 #pragma unroll
             for (int n = ZEL_NMAX; n >= 1; n--) {
+                P2 = fma(P2, rho, P1);
+                P1 = fma(P1, rho, S0);
                 S0 = fma(S0, rho, gl[n]);
-                S1 = fma(S1, rho, g1[n]);
-                S2 = fma(S2, rho, g2[n]);
             }
+            const double rP1 = rho*P1;
+            double S1 = S0 + rP1;
+            double S2 = fma(2.0*rho, fma(rho, P2, P1), S1);
             S0 *= pre; S1 *= pre; S2 *= pre;
             a00 += S0;
             a01 += (kxx + kyy)*S0 - 2.0*S1;

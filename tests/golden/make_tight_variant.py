@@ -65,6 +65,10 @@ def main():
     out['oneloop_idx'], out['oneloop'], out['oneloop_plin'] = idx, ol, P1
     print('one-loop done %.0fs' % (time.time() - t0), flush=True)
     out['sigma_v2'] = PL.sigv_tol()
+    # ImnOneLoop on common tight one-loop tables (same recipe as make_tight.py)
+    sys.path.insert(0, HERE)
+    from make_tight import ml_part
+    ml_part(out, R, PL, kint, t0)
     path = os.path.join(HERE, 'oracle_tight_variant.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, '%.1f kB' % (os.path.getsize(path)/1e3))

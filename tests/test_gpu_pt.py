@@ -257,3 +257,24 @@ def test_variant_cosmology_vs_tight_reference(golden):
         assert err[lowk].max() < TOL, ('one-loop', j, err[lowk].max())
         assert err.max() < 2e-4, ('one-loop', j, err.max())
     assert abs(plin.VelocityDispersion()/float(v['sigma_v2']) - 1) < TOL       # sigma_v^2 (PowerSpectrum.cpp:56-58)
+    if 'ML' in v.files:
+        common = v['oneloop_common']
+        ol = {w: cls(plin, 1e-7, common[j]) for j, (w, cls) in
+              enumerate((('dd', pygcl.OneLoopPdd), ('dv', pygcl.OneLoopPdv), ('vv', pygcl.OneLoopPvv)))}
+        P22 = pygcl.OneLoopP22Bar(plin, 1e-7, common[3])
+        assert abs(P22.VelocityKurtosis()/float(v['kurtosis_common_tables']) - 1) < TOL
+        mspec = [('vv', 'dd', 0, 1), ('vv', 'dd', 0, 2), ('dv', None, 0, 3), ('dv', None, 0, 4),
+                 ('vv', None, 2, 3), ('vv', None, 3, 2), ('vv', None, 3, 3)]
+        kml = v['k_ml']
+        fl = plin(kml)
+        for j, (p1, p2, m, n) in enumerate(mspec):
+            Iml = pygcl.ImnOneLoop(ol[p1]) if p2 is None else pygcl.ImnOneLoop(ol[p1], ol[p2], 1e-4)
+            for w, fn in enumerate((Iml.EvaluateLinear, Iml.EvaluateCross, Iml.EvaluateOneLoop)):
+                err = relerr_floor(fn(kml, m, n), v['ML'][j, w], fl)
+                assert err.max() < TOL, ('ML', p1, p2, m, n, w, err.max())
+        # the computed one-loop tables against the tight common ones, whole grid
+        k1 = np.exp(np.log(1e-5) + np.arange(1000)*np.log(1e6)/999)
+        P1 = plin(k1)
+        for j, o in enumerate([pygcl.OneLoopPdd(plin), pygcl.OneLoopPdv(plin), pygcl.OneLoopPvv(plin), pygcl.OneLoopP22Bar(plin)]):
+            err = relerr_floor(o.GetOneLoopPower(), common[j], P1)
+            assert err[k1 < 0.5].max() < TOL, ('one-loop table', j, err[k1 < 0.5].max())
