@@ -234,7 +234,9 @@ int prsd_window_apply(prsd_window* w, int nw, const double* poles, double* out, 
                       double* xi, double* xi_conv);
 /* cubic spline through (x, y[row]) evaluated at xq: the k_out resampling of window.py:112-124 and
  * RSDSpline; natural end conditions (Spline.cpp:211-273) -- identical to FITPACK's interpolating spline to
- * rounding a few knots away from the ends.  x [n], xq [nq] host; y [nrows][n] -> out [nrows][nq] DEVICE */
+ * rounding a few knots away from the ends.  Only the window of knots within 64 of the queried range is solved (a
+ * far knot enters the second derivatives through 0.268^distance).  x [n], xq [nq] host; y [nrows][n] -> out
+ * [nrows][nq] DEVICE */
 int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x, const double* d_y, int nq,
                                 const double* xq, double* d_out);
 
