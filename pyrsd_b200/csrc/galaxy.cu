@@ -2,6 +2,8 @@
 #include "galaxy.cuh"
 #include "pcr.cuh"
 
+#include <algorithm>
+
 #include <cmath>
 
 namespace prsd {
@@ -40,11 +42,48 @@ enum {
     W_SIGSB, W_NCBS, W_NSBSB, W_FSO, W_SIGSO, W_SIGV, W_D, W_S80, W_B2 = 22 /* [6 kinds][4 biases] */, W_END = 46
 };
 
-// --------------------------------------------------------------- spline builds
-// Not-a-knot splines of every PT table of every cosmology on the SHARED abscissae k_interp in one launch.
-// The tridiagonal systems are solved by parallel cyclic reduction (pcr.cuh); the coefficient formulas are those of
-// nak_spline_build (pt_math.cuh).
+// ------------------------------------------------- PT tables on the model grid
+// The reference splines every PT table on k_interp (not-a-knot, rsd/_cache.py:344-389) and evaluates the spline on
+// the model grid.  Both grids are fixed for a GalaxyModel and a spline is linear in its ordinates, so
+// build-and-evaluate is ONE fixed matrix E [nkm][nk_interp] (column j = the not-a-knot spline through the unit
+// vector e_j, evaluated on the model grid; built on the host by the constructor with nak_spline_build /
+// pw_cubic_eval_log themselves).  A far knot enters a spline value through 0.268^distance: a band of RS_W = 64
+// columns around the interval of k_i reproduces the full product to < 1e-17, and the 14 592 tridiagonal solves
+// per batch of 256 cosmologies (185 us of parallel cyclic reduction, 146 MB of coefficients) become a banded
+// matrix product.
 struct NakSrc { const double* p[5]; int rows[5]; int off[5]; };
+static const int RS_W = 64;          // band width
+static const int RS_ROWS = 8;        // table rows per CTA
+
+__global__ void __launch_bounds__(256)
+k_pt_resample(int nk, int nkm, int band, const double* __restrict__ Eb /*[band][nkm]*/, const int* __restrict__ jlo,
+              NakSrc S, double* __restrict__ V /*[nc][PT_NROWS][nkm]*/)
+{
+    extern __shared__ double sm_rs[];            // [RS_ROWS][nk]
+    const int r0 = blockIdx.x*RS_ROWS, cc = blockIdx.y, tid = threadIdx.x;
+    const int nr = min(RS_ROWS, PT_NROWS - r0);
+    for (int r = 0; r < nr; r++) {
+        const int row = r0 + r;
+        int g = 0;
+#pragma unroll
+        for (int j = 1; j < 5; j++) if (row >= S.off[j]) g = j;
+        const double* src = S.p[g] + ((size_t)cc*S.rows[g] + (row - S.off[g]))*nk;
+        for (int i = tid; i < nk; i += blockDim.x) sm_rs[r*nk + i] = src[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < nkm; i += blockDim.x) {
+        const int j0 = jlo[i];
+        double acc[RS_ROWS];
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; r++) acc[r] = 0.0;
+        for (int jj = 0; jj < band; jj++) {
+            const double e = __ldg(Eb + (size_t)jj*nkm + i);
+#pragma unroll
+            for (int r = 0; r < RS_ROWS; r++) if (r < nr) acc[r] = fma(e, sm_rs[r*nk + j0 + jj], acc[r]);
+        }
+        for (int r = 0; r < nr; r++) V[((size_t)cc*PT_NROWS + r0 + r)*nkm + i] = acc[r];
+    }
+}
 
 // not-a-knot system of nak_spline_build (pt_math.cuh) for the interior second derivatives M_1 .. M_{n-2}, written
 // into the PCR arrays at offset `off` (unknown j = i - 1); x, y in shared memory
@@ -58,44 +97,6 @@ __device__ __forceinline__ void nak_system_row(int n, const double* x, const dou
     if (i == m) { bb += h1*(1.0 + h1/h0); aa -= h1*h1/h0; }
     a[off + i - 1] = aa; b[off + i - 1] = bb; c[off + i - 1] = cc;
     r[off + i - 1] = 6.0*((y[i + 1] - y[i])/h1 - (y[i] - y[i - 1])/h0);
-}
-
-__global__ void __launch_bounds__(128)
-k_nak_rows(int nk, const double* __restrict__ X, NakSrc S, double* __restrict__ dst)
-{
-    extern __shared__ double sm_nak[];
-    double* x = sm_nak;
-    double* y = x + nk;
-    double* M = y + nk;                  // [nk] second derivatives
-    double* w = M + nk;                  // 8 (nk - 2) reduction arrays
-    const int row = blockIdx.x, cc = blockIdx.y, tid = threadIdx.x;
-    int g = 0;
-#pragma unroll
-    for (int j = 1; j < 5; j++) if (row >= S.off[j]) g = j;
-    const double* s = S.p[g] + ((size_t)cc*S.rows[g] + (row - S.off[g]))*nk;
-    for (int i = tid; i < nk; i += blockDim.x) { x[i] = X[i]; y[i] = s[i]; }
-    __syncthreads();
-    const int m = nk - 2;
-    for (int i = 1 + tid; i <= m; i += blockDim.x) nak_system_row(nk, x, y, i, w, w + m, w + 2*m, w + 3*m, 0);
-    __syncthreads();
-    pcr_solve(1, m, w, w + m, w + 2*m, w + 3*m, w + 4*m, w + 5*m, w + 6*m, w + 7*m, M + 1);
-    if (tid == 0) {
-        const double h0 = x[1] - x[0], h1 = x[2] - x[1];
-        M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
-        const double hn = x[nk - 1] - x[nk - 2], hm = x[nk - 2] - x[nk - 3];
-        M[nk - 1] = M[nk - 2] + (hn/hm)*(M[nk - 2] - M[nk - 3]);
-    }
-    __syncthreads();
-    double* o = dst + ((size_t)cc*PT_NROWS + row)*5*nk;
-    for (int i = tid; i < nk; i += blockDim.x) {
-        const int j = min(i, nk - 2);          // the last knot repeats the last interval's coefficients
-        const double h = x[j + 1] - x[j];
-        o[i] = x[i];
-        o[nk + i] = y[i];
-        o[2*nk + i] = (y[j + 1] - y[j])/h - h*(2.0*M[j] + M[j + 1])/6.0;
-        o[3*nk + i] = 0.5*M[j];
-        o[4*nk + i] = (M[j + 1] - M[j])/(6.0*h);
-    }
 }
 
 // --------------------------------------------------------------- HZPT broadband
@@ -115,7 +116,7 @@ __global__ void k_gal_base(GalDev G, const double* __restrict__ km, const int* _
                            double* __restrict__ base)
 {
     const int w = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
-    const int nkm = G.nkm, nk = G.nk;
+    const int nkm = G.nkm;
     if (i >= nkm) return;
     const int c = cmap[w];
     const double* p = par + (size_t)w*GAL_NPAR;
@@ -123,10 +124,8 @@ __global__ void k_gal_base(GalDev G, const double* __restrict__ km, const int* _
     const double s8z = p[W_S8Z], f = p[W_F], D = p[W_D];
     const double norm = (s8z/p[W_S80])*(s8z/p[W_S80]);
     const double norm2 = norm*norm;
-    auto T = [&](int row) {
-        const double* s = ptspl + ((size_t)c*PT_NROWS + row)*5*nk;
-        return pw_cubic_eval_log(nk, s, s + nk, s + 2*nk, s + 3*nk, s + 4*nk, G.lnki0, G.inv_dlnki, k);
-    };
+    // PT table `row` of cosmology c at k_i: resampled from k_interp by k_pt_resample
+    auto T = [&](int row) { return ptspl[((size_t)c*PT_NROWS + row)*nkm + i]; };
     auto OL = [&](int which) {
         const double* s = olspl + (size_t)(c*4 + which)*5*ONELOOP_N;
         return (k < ONELOOP_KMIN || k > ONELOOP_KMAX) ? 0.0 : cubic_spline_eval_log(ONELOOP_N, s, G.lnk1l0, G.inv_dlnk1l, k);
@@ -611,6 +610,30 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     h_kinterp.assign(k_interp, k_interp + nki);
     PRSD_REQUIRE(nki >= 4, "GalaxyModel: the PT interpolation grid needs at least 4 points");
     zel.build(c, km.data(), nkm);
+    {
+        // E[i][j] = (not-a-knot spline through e_j on k_interp)(km[i]); band of rs_band columns around the interval of km[i]
+        const int n = nki;
+        const double lnx0 = std::log(k_interp[0]), inv = (n - 1)/std::log(k_interp[n - 1]/k_interp[0]);
+        std::vector<double> E((size_t)nkm*n), y(n), b(n), cc(n), d(n), M(n), w(n);
+        for (int j = 0; j < n; j++) {
+            std::fill(y.begin(), y.end(), 0.0);
+            y[j] = 1.0;
+            nak_spline_build(n, k_interp, y.data(), b.data(), cc.data(), d.data(), M.data(), w.data());
+            for (int i = 0; i < nkm; i++)
+                E[(size_t)i*n + j] = pw_cubic_eval_log(n, k_interp, y.data(), b.data(), cc.data(), d.data(), lnx0, inv, km[i]);
+        }
+        rs_band = std::min(RS_W, n);
+        std::vector<double> Eb((size_t)rs_band*nkm);
+        std::vector<int> jl(nkm);
+        for (int i = 0; i < nkm; i++) {
+            int ji = (int)(std::upper_bound(k_interp, k_interp + n, km[i]) - k_interp) - 1;
+            int lo = std::min(std::max(ji - rs_band/2 + 1, 0), n - rs_band);
+            jl[i] = lo;
+            for (int jj = 0; jj < rs_band; jj++) Eb[(size_t)jj*nkm + i] = E[(size_t)i*n + lo + jj];
+        }
+        d_rsE.upload(Eb, c.stream);
+        d_rsJ.upload(jl, c.stream);
+    }
     c.sync();
 }
 
@@ -647,15 +670,15 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     ratio1.upload(r1, s);
     ratio2.upload(r2, s);
 
-    // ---- per-cosmology: not-a-knot splines of every PT table on k_interp (rsd/_cache.py:344-389)
+    // ---- per-cosmology: every PT table splined on k_interp and read on the model grid (rsd/_cache.py:344-389)
     const int nk = nk_interp;
-    ptspl.ensure((size_t)nc*PT_NROWS*5*nk);
+    ptspl.ensure((size_t)nc*PT_NROWS*nkm);
     {
         ProfScope prof(c, PROF_SPLINE);
-        const size_t smem = (size_t)11*nk*sizeof(double);
-        if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_nak_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (size_t)RS_ROWS*nk*sizeof(double);
+        if (smem > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_pt_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NakSrc S = {{pt.I.p, pt.J.p, pt.K.p, pt.ML.p, pt.sigmasq_k.p}, {16, 6, 13, 21, 1}, {PT_I, PT_J, PT_K, PT_ML, PT_SIGK}};
-        k_nak_rows<<<dim3(PT_NROWS, nc), 128, smem, s>>>(nk, d_kinterp.p, S, ptspl.p);
+        k_pt_resample<<<dim3((PT_NROWS + RS_ROWS - 1)/RS_ROWS, nc), 256, smem, s>>>(nk, nkm, rs_band, d_rsE.p, d_rsJ.p, S, ptspl.p);
         c.launches++;
         PRSD_CUDA(cudaGetLastError());
     }

@@ -58,6 +58,10 @@ struct GalaxyModel {
     DevBuf<double> ptspl, zel1, zel2, plin_m, ratio1, ratio2, base, pairspl, grpspl, grpconst, d_par, d_stoch, ol_m;
     DevBuf<int> d_cmap;
     std::vector<double> h_kinterp;
+    // banded resampling operator k_interp -> model grid (see k_pt_resample)
+    int rs_band = 0;
+    DevBuf<double> d_rsE;
+    DevBuf<int> d_rsJ;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_event = nullptr;
     GalDev last_G;                      // constants of the last power() call (reused by poles())
