@@ -229,7 +229,9 @@ __constant__ int c_pair_b[GAL_NPAIR] = {0, 1, 1, 2, 3, 2, 3, 2, 3, 3};
 
 // ----------------------------------------------------------- halo moments + splines
 __global__ void __launch_bounds__(128)
-k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict__ kst, const int* __restrict__ cmap,
+k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict__ Es /*[GAL_NSTOCH][nkm]*/,
+              int mband, const double* __restrict__ Mb /*[mband][nkm]*/, const int* __restrict__ mlo,
+              const int* __restrict__ cmap,
               const double* __restrict__ par, const double* __restrict__ stoch, const double* __restrict__ scal,
               const double* __restrict__ base, double* __restrict__ pairspl)
 {
@@ -237,8 +239,8 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
     const int nkm = G.nkm;
     double* X = sm_gm;                       // [nkm]
     double* Y = X + nkm;                     // [4][nkm]
-    double* W = Y + 4*nkm;                   // [4][nkm] second derivatives + 36 x 4 (nkm - 2) PCR work
-    double* S = W + 40*nkm;                  // stochasticity spline: x y b c d M w  [7][20]
+    double* W = Y + 4*nkm;                   // [4][nkm] second derivatives
+    double* S = W + 4*nkm;                   // stochasticity ordinates [20]
     const int pr = blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
     const int c = cmap[w];
     const double* p = par + (size_t)w*GAL_NPAR;
@@ -256,11 +258,8 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
     const double bsb = G.cfg.use_tidal_bias ? -2.0/7.0*(b1b - 1.0) : 0.0;
 
     for (int i = tid; i < nkm; i += blockDim.x) X[i] = km[i];
-    if (tid < GAL_NSTOCH) { S[tid] = kst[tid]; S[GAL_NSTOCH + tid] = stoch[((size_t)w*GAL_NPAIR + pr)*GAL_NSTOCH + tid]; }
+    if (tid < GAL_NSTOCH) S[tid] = stoch[((size_t)w*GAL_NPAIR + pr)*GAL_NSTOCH + tid];
     __syncthreads();
-    if (tid == 0) nak_spline_build(GAL_NSTOCH, S, S + 20, S + 40, S + 60, S + 80, S + 100, S + 120);
-    __syncthreads();
-    const double lnks0 = log(S[0]), inv_dlnks = (GAL_NSTOCH - 1)/log(S[GAL_NSTOCH - 1]/S[0]);
     const double* hm = G.cfg.hzhm;
     // HaloMatterBase._powerlaw (hzpt/Phm.py:231-236): the five Pade parameters depend on (sigma8_z, b1) only --
     // evaluated once per (walker, bias), not per k
@@ -284,7 +283,10 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
         const double K11 = B[B_K11*nkm + i], K11s = B[B_K11S*nkm + i];
         const double P02nv2 = B[B_P02NV2*nkm + i], P02nv4 = B[B_P02NV4*nkm + i];
         // P00_ss (biased/P00.py:19-43) with the stochasticity spline (power_biased.py:342-366)
-        const double st = pw_cubic_eval_log(GAL_NSTOCH, S, S + 20, S + 40, S + 60, S + 80, lnks0, inv_dlnks, k);
+        // the 20-point not-a-knot spline evaluated at k_i is a fixed linear map of its ordinates (Es, built on the host)
+        double st = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < GAL_NSTOCH; j++) st = fma(__ldg(Es + (size_t)j*nkm + i), S[j], st);
         const double Phm1 = phm(b1, hp1, ia, k, P00, B[B_Z00*nkm + i], K00, K00s, bs);
         const double Phm2 = (ia == ib) ? Phm1 : phm(b1b, hp2, ib, k, P00, B[B_Z00*nkm + i], K00, K00s, bsb);
         const double mu0 = Phm1*Phm2/P00 + st;
@@ -327,29 +329,17 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
         Y[i] = mu0; Y[nkm + i] = mu2; Y[2*nkm + i] = mu4; Y[3*nkm + i] = mu6;
     }
     __syncthreads();
-    // not-a-knot splines of the four moments on the model grid (the reference's RSDSpline on self.k): the four
-    // tridiagonal systems are solved together by parallel cyclic reduction (pcr.cuh)
+    // not-a-knot splines of the four moments on the model grid (the reference's RSDSpline on self.k).  The second
+    // derivatives are a fixed linear map of the ordinates (the inverse of the tridiagonal not-a-knot system, built on
+    // the host); a far knot enters through 0.268^distance, so a band of `mband` columns reproduces it to < 1e-17 --
+    // no tridiagonal solve, no barrier-separated reduction sweeps
     double* Mm = W;                          // [4][nkm] second derivatives
-    double* pw = W + 4*nkm;                  // 8 x 4 (nkm - 2) reduction arrays + 4 (nkm - 2) solutions
-    const int m_in = nkm - 2;
-    for (int idx = tid; idx < 4*m_in; idx += blockDim.x) {
-        const int m = idx/m_in, i = 1 + idx - m*m_in;
-        nak_system_row(nkm, X, Y + m*nkm, i, pw, pw + 4*m_in, pw + 8*m_in, pw + 12*m_in, m*m_in);
-    }
-    __syncthreads();
-    double* sol = pw + 32*m_in;
-    pcr_solve(4, m_in, pw, pw + 4*m_in, pw + 8*m_in, pw + 12*m_in, pw + 16*m_in, pw + 20*m_in, pw + 24*m_in, pw + 28*m_in, sol);
-    for (int idx = tid; idx < 4*m_in; idx += blockDim.x) {
-        const int m = idx/m_in, i = 1 + idx - m*m_in;
-        Mm[m*nkm + i] = sol[idx];
-    }
-    __syncthreads();
-    if (tid < 4) {
-        double* M = Mm + tid*nkm;
-        const double h0 = X[1] - X[0], h1 = X[2] - X[1];
-        M[0] = M[1] - (h0/h1)*(M[2] - M[1]);
-        const double hn = X[nkm - 1] - X[nkm - 2], hm = X[nkm - 2] - X[nkm - 3];
-        M[nkm - 1] = M[nkm - 2] + (hn/hm)*(M[nkm - 2] - M[nkm - 3]);
+    for (int idx = tid; idx < 4*nkm; idx += blockDim.x) {
+        const int m = idx/nkm, i = idx - m*nkm;
+        const double* y = Y + m*nkm + mlo[i];
+        double acc = 0.0;
+        for (int jj = 0; jj < mband; jj++) acc = fma(__ldg(Mb + (size_t)jj*nkm + i), y[jj], acc);
+        Mm[idx] = acc;
     }
     __syncthreads();
     // store [walker][pair][moment][Y | b | c | d]
@@ -634,6 +624,40 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
         d_rsE.upload(Eb, c.stream);
         d_rsJ.upload(jl, c.stream);
     }
+    {
+        // stochasticity: (not-a-knot spline through e_j on the 20 GP points)(km[i])  (power_biased.py:342-366)
+        const int n = GAL_NSTOCH;
+        const double lnx0 = std::log(ks[0]), inv = (n - 1)/std::log(ks[n - 1]/ks[0]);
+        std::vector<double> Es((size_t)n*nkm), y(n), b(n), cc(n), d(n), M(n), w(n);
+        for (int j = 0; j < n; j++) {
+            std::fill(y.begin(), y.end(), 0.0);
+            y[j] = 1.0;
+            nak_spline_build(n, ks.data(), y.data(), b.data(), cc.data(), d.data(), M.data(), w.data());
+            for (int i = 0; i < nkm; i++)
+                Es[(size_t)j*nkm + i] = pw_cubic_eval_log(n, ks.data(), y.data(), b.data(), cc.data(), d.data(), lnx0, inv, km[i]);
+        }
+        d_stE.upload(Es, c.stream);
+    }
+    {
+        // moments: second derivatives of the not-a-knot spline on the model grid as a banded map of the ordinates
+        const int n = nkm;
+        std::vector<double> Mop((size_t)n*n), y(n), b(n), cc(n), d(n), M(n), w(n);
+        for (int j = 0; j < n; j++) {
+            std::fill(y.begin(), y.end(), 0.0);
+            y[j] = 1.0;
+            nak_spline_build(n, km.data(), y.data(), b.data(), cc.data(), d.data(), M.data(), w.data());
+            for (int i = 0; i < n; i++) Mop[(size_t)i*n + j] = M[i];
+        }
+        mom_band = std::min(RS_W, n);
+        std::vector<double> Mb((size_t)mom_band*n);
+        std::vector<int> lo(n);
+        for (int i = 0; i < n; i++) {
+            lo[i] = std::min(std::max(i - mom_band/2, 0), n - mom_band);
+            for (int jj = 0; jj < mom_band; jj++) Mb[(size_t)jj*n + i] = Mop[(size_t)i*n + lo[i] + jj];
+        }
+        d_momE.upload(Mb, c.stream);
+        d_momJ.upload(lo, c.stream);
+    }
     c.sync();
 }
 
@@ -702,7 +726,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     pairspl.ensure((size_t)nw*GAL_NPAIR*16*nkm);
     grpspl.ensure((size_t)nw*GAL_NGRP*16*nkm);
     grpconst.ensure((size_t)nw*GAL_NCONST);
-    const size_t smem_mom = (size_t)(45*nkm + 7*GAL_NSTOCH)*sizeof(double);
+    const size_t smem_mom = (size_t)(9*nkm + GAL_NSTOCH)*sizeof(double);
     if (smem_mom > 48*1024) PRSD_CUDA(cudaFuncSetAttribute(k_gal_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mom));
 
     // ---- everything below is per walker: walkers [w0, w0 + n) of the batch
@@ -729,7 +753,8 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         ProfScope prof_gal(c, PROF_GALAXY);
         k_gal_base<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(G, d_km.p, cm, pr, ptspl.p, plin_m.p, sp.oneloop_spl.p,
                                                             pt.scalars.p, z1, z2, bs);
-        k_gal_moments<<<dim3(GAL_NPAIR, n), 128, smem_mom, s>>>(G, d_km.p, d_kstoch.p, cm, pr, st, pt.scalars.p, bs, ps);
+        k_gal_moments<<<dim3(GAL_NPAIR, n), 128, smem_mom, s>>>(G, d_km.p, d_stE.p, mom_band, d_momE.p, d_momJ.p, cm, pr, st,
+                                                                pt.scalars.p, bs, ps);
         k_gal_groups<<<dim3((16*nkm + 255)/256, n), 256, 0, s>>>(nkm, pr, ps, gs, gc);
         c.launches += 3;
         if (npts > 0) {

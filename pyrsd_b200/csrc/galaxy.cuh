@@ -62,6 +62,11 @@ struct GalaxyModel {
     int rs_band = 0;
     DevBuf<double> d_rsE;
     DevBuf<int> d_rsJ;
+    // stochasticity spline evaluated on the model grid, and the second derivatives of the moment splines, as fixed
+    // (banded) linear maps of the ordinates (see k_gal_moments)
+    DevBuf<double> d_stE, d_momE;
+    DevBuf<int> d_momJ;
+    int mom_band = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_event = nullptr;
     GalDev last_G;                      // constants of the last power() call (reused by poles())
