@@ -101,3 +101,29 @@ def test_not_a_knot_spline_matches_scipy():
         out = np.empty_like(xq)
         L.emul_nak_spline(n, x, y, len(xq), xq, out)
         assert np.max(np.abs(out/InterpolatedUnivariateSpline(x, y)(xq) - 1)) < 1e-12
+
+
+def test_banded_spline_operator_claim():
+    """on FIXED abscissae the second derivatives of an interpolating cubic spline are a linear map
+    of the ordinates whose entries decay like 0.268^|i - j|, so a band of 64 columns is exact to rounding.  Checked
+    here with SciPy's not-a-knot spline on the model grid and on the 250-point PT grid (k_pt_resample, k_gal_moments,
+    k_spline_build_band use the same construction with the library's own spline builders)."""
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(11)
+    for x in (np.logspace(-3, np.log10(0.5), 200), np.logspace(np.log10(5e-6), 0., 250)):
+        n = len(x)
+        op = np.empty((n, n))
+        for j in range(n):
+            e = np.zeros(n)
+            e[j] = 1.
+            op[:, j] = CubicSpline(x, e, bc_type='not-a-knot')(x, 2)
+        band = 64
+        lo = np.clip(np.arange(n) - band//2, 0, n - band)
+        y = rng.normal(size=n)*np.exp(rng.normal(size=n))
+        full = CubicSpline(x, y, bc_type='not-a-knot')(x, 2)
+        banded = np.array([op[i, lo[i]:lo[i] + band] @ y[lo[i]:lo[i] + band] for i in range(n)])
+        scale = np.max(np.abs(op), axis=1)*np.max(np.abs(y))
+        assert np.max(np.abs(banded - full)/scale) < 1e-13
+        # the decay itself: 40 knots away the influence is below 1e-17 of the diagonal
+        i = n//2
+        assert abs(op[i, i + 40]) < 1e-17*abs(op[i, i])
