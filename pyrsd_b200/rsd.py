@@ -368,6 +368,26 @@ class GalaxySpectrum(object):
         self._spectra = None
         self._result = None
 
+    # -------------------------------------------------------------- pickling
+    def __getstate__(self):
+        """everything but the device handles: the PT tables are rebuilt on first use (a millisecond here, minutes in
+        the reference, which therefore pickles them: power_dm.py ``to_npy`` / ``from_npy``)"""
+        d = dict(self.__dict__)
+        for k in ('_engine', '_spectra', '_result'):
+            d[k] = None
+        return d
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    def to_npy(self, filename):
+        """``np.save`` of the pickled model, as the reference's ``DarkMatterSpectrum.to_npy``"""
+        np.save(filename, np.array(self, dtype=object), allow_pickle=True)
+
+    @classmethod
+    def from_npy(cls, filename):
+        return np.load(filename, allow_pickle=True).tolist()
+
     # -------------------------------------------------------------- derived
     def __getattr__(self, name):
         models = self.__dict__.get('_models', {})

@@ -58,3 +58,24 @@ def test_pickle_roundtrip_of_the_pt_objects(golden):
     zcf = pygcl.ZeldovichCF(cosmo, 0.55)
     r = np.array([20., 80., 105.])
     assert np.array_equal(roundtrip(zcf)(r), zcf(r))
+
+
+def test_galaxy_spectrum_pickle_and_npy(golden, tmp_path):
+    import pickle as pk
+    from pyrsd_b200 import rsd
+    from tests.gpu_common import b2_00, b2_01, stochasticity
+    cosmo = golden_pygcl_cosmology(golden)
+    m = rsd.GalaxySpectrum(params=cosmo, z=0.55, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity,
+                           use_so_correction=True, fog_model='gaussian', max_mu=6)
+    m.update(f=0.78, sigma8_z=0.61, f_so=0.04, sigma_so=4.0, alpha_par=0.97, fs=0.12)
+    k = np.logspace(-2, np.log10(0.35), 11)
+    mu = np.linspace(0., 1., 5)
+    P = m.power(k, mu)
+    m2 = pk.loads(pk.dumps(m))
+    assert m2._result is None and m2.f == 0.78 and m2.use_so_correction and m2.fog_model == 'gaussian'
+    assert np.array_equal(m2.power(k, mu), P)
+    path = str(tmp_path / 'model.npy')
+    m.to_npy(path)
+    m3 = rsd.GalaxySpectrum.from_npy(path)
+    assert np.array_equal(m3.power(k, mu), P)
+    assert np.array_equal(np.array(m3.poles(k, [0, 2])), np.array(m.poles(k, [0, 2])))
