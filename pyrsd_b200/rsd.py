@@ -371,7 +371,7 @@ class GalaxySpectrum(object):
     # -------------------------------------------------------------- pickling
     def __getstate__(self):
         """everything but the device handles: the PT tables are rebuilt on first use (a millisecond here, minutes in
-        the reference, which therefore pickles them: power_dm.py ``to_npy`` / ``from_npy``)"""
+        the reference, which therefore pickles them: power_dm.py:720-735 ``to_npy`` / ``from_npy``)"""
         d = dict(self.__dict__)
         for k in ('_engine', '_spectra', '_result'):
             d[k] = None
