@@ -577,6 +577,49 @@ def _gradient(self, k, mu, names, epsilon=1e-4):
 GalaxySpectrum.gradient = _gradient
 
 
+def _components(self, k, mu):
+    """(Pgal_cc, Pgal_cs, Pgal_ss)(k, mu): the central-central, central-satellite and satellite-satellite spectra of
+    ``power = (1 - fs)^2 Pcc + 2 fs (1 - fs) Pcs + fs^2 Pss`` (power_gal.py:316-399, gal/__init__.py:24-40), each
+    with the same AP treatment as ``power``.  Evaluated as ONE batch of three walkers of the assembly kernel at
+    fs = 0, 1/2, 1 (fs enters nowhere else): Pcc = P(0), Pss = P(1), Pcs = 2 P(1/2) - (Pcc + Pss)/2."""
+    eng = self._ensure_tables()
+    k = np.atleast_1d(np.asarray(k, dtype=np.float64))
+    mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+    if k.ndim == 1 and mu.ndim == 1 and len(mu) != len(k):
+        k, mu = k[:, None], mu[None, :]
+    kb, mub = np.broadcast_arrays(k, mu)
+    kmodel = self.k
+    gal = eng.galaxy(kmodel, self._config())
+    fs0 = self.fs
+    wpar = []
+    try:
+        for v in (0.0, 0.5, 1.0):
+            self.fs = v
+            wpar.append(self._walker())
+    finally:
+        self.fs = fs0
+    stoch = np.array([self._stoch(kmodel)]*3)
+    P = eng.galaxy_power(gal, self._spectra, self._result, np.array(wpar), stoch, np.ascontiguousarray(kb).ravel(),
+                         np.ascontiguousarray(mub).ravel(), cmap=np.zeros(3, dtype=np.int32))
+    if np.isnan(P).any():
+        raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
+                         "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+    shape = kb.shape
+    Pcc, Pss = P[0], P[2]
+    Pcs = 2.0*P[1] - 0.5*(Pcc + Pss)
+    return tuple(np.squeeze(x.reshape(shape)) for x in (Pcc, Pcs, Pss))
+
+
+GalaxySpectrum.components = _components
+GalaxySpectrum.Pgal_cc = lambda self, k, mu, flatten=False: _flat(_components(self, k, mu)[0], flatten)
+GalaxySpectrum.Pgal_cs = lambda self, k, mu, flatten=False: _flat(_components(self, k, mu)[1], flatten)
+GalaxySpectrum.Pgal_ss = lambda self, k, mu, flatten=False: _flat(_components(self, k, mu)[2], flatten)
+
+
+def _flat(P, flatten):
+    return np.ravel(P, order='F') if flatten else P
+
+
 def _new_result():
     r = _Result(None)
     r.ncosmo = 0

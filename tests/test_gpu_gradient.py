@@ -94,3 +94,24 @@ def test_gradient_properties(models):
         m.gradient(k, mu, ['not_a_parameter'])
     with pytest.raises(ValueError):
         m.gradient(k, mu, ['fs'], epsilon=0.)
+
+
+def test_component_spectra(ref, models):
+    """Pgal_cc / Pgal_cs / Pgal_ss (power_gal.py:316-399): they recompose power(), and the reference's analytic
+    dP/dfs = -2 (1 - fs) Pcc + 2 (1 - 2 fs) Pcs + 2 fs Pss (derivatives/fs.py:11-15) evaluated with them matches the
+    reference's value"""
+    for tag in ('ap', 'so'):
+        m = models[tag]
+        k, mu = ref['k'], ref['mu']
+        Pcc, Pcs, Pss = m.components(k, mu)
+        fs = m.fs
+        P = m.power(k, mu)
+        assert np.max(np.abs((1 - fs)**2*Pcc + 2*fs*(1 - fs)*Pcs + fs**2*Pss - P))/np.max(np.abs(P)) < 1e-13
+        dfs = -2*(1 - fs)*Pcc + 2*(1 - 2*fs)*Pcs + 2*fs*Pss
+        want = ref[tag + '_d_fs']
+        assert np.max(np.abs(dfs - want))/np.max(np.abs(want)) < TOL
+        assert np.array_equal(m.Pgal_cc(k, mu), Pcc) and np.array_equal(m.Pgal_ss(k, mu), Pss)
+        assert m.fs == fs
+    grid = models['ap'].Pgal_cs(np.logspace(-2, -1, 4), np.linspace(0, 1, 3))
+    assert grid.shape == (4, 3)
+    assert models['ap'].Pgal_cs(np.logspace(-2, -1, 4), np.linspace(0, 1, 3), flatten=True).shape == (12,)
