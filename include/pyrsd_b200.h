@@ -199,6 +199,12 @@ int prsd_galaxy_poles_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
 int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
                      const double* par, const double* stoch, int nk, const double* k, int nell, const int* ells,
                      int nmu, const double* data, const double* cinv, double* chi2, double* poles);
+/* dark-matter and bias building blocks of the last call on the model grid (rsd/power/dm/power_dm.py:797-884,
+ * dm/P00.py ... P22.py): out [nw][*nrows][nkm] (out may be NULL to query *nrows), rows in the order
+ * 0 P_lin, 1 P00, 2 P01, 3 P11[mu4], 4 Pdv, 5 Pvv, 6 Pdd, 7 P02[mu2] no-velocity, 8 P02[mu4] no-velocity,
+ * 9 P12[mu4] no-velocity, 10 P22[mu4] no-velocity, 11-20 K00 K00s K10 K10s K11 K11s K20_a K20_b K20s_a K20s_b,
+ * 21 f^2 (h01 + h03 ImnOneLoop), 22 f^2 (h02 + h04), 23 f^3 I03, 24 sigma^2(k)^2, 25 P00 Zel'dovich, 26, 27 mu^6 terms */
+int prsd_galaxy_base(prsd_galaxy* g, int nw, int* nrows, double* out);
 /* spline knots of P[mu^0], P[mu^2], P[mu^4], P[mu^6] of the last call: out [nw][10][4][nkm] */
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out);
 

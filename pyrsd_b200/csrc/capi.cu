@@ -867,6 +867,15 @@ int prsd_chi2(prsd_ctx* ctx, int nw, int n, const double* model, const double* d
     });
 }
 
+int prsd_galaxy_base(prsd_galaxy* g, int nw, int* nrows, double* out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(g && nrows, "null argument");
+        *nrows = GalaxyModel::n_base();
+        if (out) g->g.base_to_host(nw, out);
+    });
+}
+
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
 {
     return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });

@@ -824,6 +824,15 @@ void chi2_rows(Context& c, int nw, int n, const double* d_model, const double* d
     c.launches++;
 }
 
+void GalaxyModel::base_to_host(int nw, double* out)
+{
+    PRSD_REQUIRE(nw > 0 && nw <= last_nw, "GalaxyModel::base_to_host: %d walkers requested, the last call had %d", nw, last_nw);
+    base.download(out, (size_t)nw*NB*nkm, ctx->stream);
+    ctx->sync();
+}
+
+int GalaxyModel::n_base() { return NB; }
+
 void GalaxyModel::moments_to_host(int nw, double* out)
 {
     std::vector<double> tmp((size_t)nw*GAL_NPAIR*16*nkm);

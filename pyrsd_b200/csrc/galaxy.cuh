@@ -95,6 +95,9 @@ struct GalaxyModel {
               double* d_poles, double* d_out);
     // diagnostic: the spline knots of P[mu^0,2,4,6] per (walker, pair): host [nw][10][4][nkm]
     void moments_to_host(int nw, double* out);
+    // the dark-matter / bias building blocks on the model grid of the last call: out [nw][n_base()][nkm]
+    void base_to_host(int nw, double* out);
+    static int n_base();
 };
 
 // chi^2 = (M - D)^T C^-1 (M - D) of nw model vectors d_model [nw][n] (FittingDriver.chi2, rsdfit/driver.py:780-802);

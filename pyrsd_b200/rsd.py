@@ -252,6 +252,17 @@ class PTEngine(object):
         chi2 = self.chi2(poles, data, cinv)
         return (chi2, poles) if return_poles else chi2
 
+    def galaxy_base(self, gal, nw):
+        """dark-matter / bias building blocks of the last galaxy call on the model grid -> [nw][nrows][nkm]"""
+        n = C.c_int()
+        L = _L()
+        L.prsd_galaxy_base.argtypes = [_vp, C.c_int, C.POINTER(C.c_int), _vp]
+        L.prsd_galaxy_base.restype = C.c_int
+        N.check(L.prsd_galaxy_base(gal.ptr, nw, C.byref(n), None))
+        out = np.empty((nw, n.value, gal.nkm))
+        N.check(L.prsd_galaxy_base(gal.ptr, nw, C.byref(n), out.ctypes.data_as(_vp)))
+        return out
+
     def galaxy_moments(self, gal, nw):
         out = np.empty((nw, NPAIR, 4, gal.nkm))
         N.check(_L().prsd_galaxy_moments(gal.ptr, nw, out))
@@ -611,6 +622,23 @@ def _components(self, k, mu):
 
 
 GalaxySpectrum.components = _components
+
+_DM_ROWS = {'P_lin': 0, 'P00': 1, 'P01': 2, 'P11_mu4': 3, 'Pdv': 4, 'Pvv': 5, 'Pdd': 6}
+
+
+def _dm_spectra(self):
+    """the dark-matter building blocks on the model grid ``self.k`` at the current parameters: dict with
+    P_lin (normed_power_lin), P00, P01, P11_mu4 (dm/P00.py, P01.py, P11.py totals), Pdd, Pdv, Pvv
+    (power_dm.py:797-884 incl. the Jennings et al. fits of :676-718)"""
+    eng = self._ensure_tables()
+    kmodel = self.k
+    gal = eng.galaxy(kmodel, self._config())
+    eng.galaxy_power(gal, self._spectra, self._result, self._walker(), self._stoch(kmodel), kmodel[:1], np.zeros(1))
+    base = eng.galaxy_base(gal, 1)[0]
+    return {name: base[row].copy() for name, row in _DM_ROWS.items()}
+
+
+GalaxySpectrum.dm_spectra = _dm_spectra
 GalaxySpectrum.Pgal_cc = lambda self, k, mu, flatten=False: _flat(_components(self, k, mu)[0], flatten)
 GalaxySpectrum.Pgal_cs = lambda self, k, mu, flatten=False: _flat(_components(self, k, mu)[1], flatten)
 GalaxySpectrum.Pgal_ss = lambda self, k, mu, flatten=False: _flat(_components(self, k, mu)[2], flatten)

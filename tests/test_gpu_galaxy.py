@@ -181,3 +181,25 @@ def test_chi2_of_an_ensemble(cosmo, engine):
     ref = np.einsum('wi,ij,wj->w', d, cinv, d)
     assert np.allclose(chi2, ref, rtol=1e-12)
     assert np.argmin(chi2) == 5
+
+
+def test_dm_spectra_vs_shipped_model(cosmo, engine, golden):
+    """Pdd, Pdv, Pvv on the model grid against the arrays cached in the reference's shipped model
+    (docs/data/galaxy_power.npy: z = 0, default tolerances, Zel'dovich terms read from its interpolation tables):
+    the shipped numbers are only as good as epsrel = 1e-4 and a 100 x 300 table allow"""
+    from pyrsd_b200 import rsd
+    mk = golden['model_k']
+    m = rsd.GalaxySpectrum(params=cosmo, z=0., kmin=mk[0], kmax=mk[-1], Nk=len(mk), b2_00=b2_00, b2_01=b2_01,
+                           stochasticity=stochasticity, engine=engine)
+    m.update(f=float(golden['par_f']))
+    assert np.max(np.abs(m.k/mk - 1)) < 1e-12
+    dm = m.dm_spectra()
+    assert set(dm) == {'P_lin', 'P00', 'P01', 'P11_mu4', 'Pdd', 'Pdv', 'Pvv'}
+    for name in ('Pdd', 'Pdv', 'Pvv'):
+        err = np.abs(dm[name]/golden['model_' + name] - 1)
+        # Pdv / Pvv go through the shipped 100 x 300 Zel'dovich interpolation table: 1.6e-3 at worst, 1e-4 typically
+        assert err.max() < 3e-3 and np.median(err) < 3e-4, (name, err.max(), np.median(err))
+    # internal consistency: linear theory at low k
+    low = mk < 3e-3
+    assert np.max(np.abs(dm['P00'][low]/dm['P_lin'][low] - 1)) < 2e-2
+    assert np.max(np.abs(dm['P01'][low]/(2*m.f*dm['P_lin'][low]) - 1)) < 5e-2
