@@ -305,11 +305,9 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: GalaxySpectrum P(k,mu) full model (all one-loop + Zel'dovich terms) on 1000 k x 40 mu, "
-                               "every PT table rebuilt per cosmology; batch of %d distinct synthetic cosmologies per GPU per step" % B,
-                   "batch_per_gpu": B, "k_interp": 250, "oneloop_k": 1000, "model_k": 200, "out_grid": [NK_OUT, NMU_OUT],
-                   "quadrature_nodes_per_cosmology": info['nodes'], "l2": "flushed between timed iterations (256 MB write)",
-                   "parallelism": "walkers sharded over %d rank(s), NCCL all-gather of the mu-averaged P(k)" % world},
+        "config": dict(workload_config(B), quadrature_nodes_per_cosmology=info['nodes'],
+                       l2="flushed between timed iterations (256 MB write)",
+                       parallelism="walkers sharded over %d rank(s), NCCL all-gather of the mu-averaged P(k)" % world),
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(h_k.numel()*8 + h_T.numel()*8 + h_pars.numel()*8 + h_wpar.numel()*8 + h_stoch.numel()*8
                                           + h_kk.numel()*8 + h_mm.numel()*8),
@@ -410,6 +408,13 @@ def _ref_worker(seed):
     return _cpu_eval(seed, thin=4)
 
 
+def workload_config(B):
+    """the workload both arms are measured on (BASELINE.json configs[1])"""
+    return {"workload": "configs[1]: GalaxySpectrum P(k,mu) full model (all one-loop + Zel'dovich terms) on 1000 k x 40 mu, "
+                        "every PT table rebuilt per cosmology; batch of %d distinct synthetic cosmologies per GPU per step" % B,
+            "batch_per_gpu": B, "k_interp": 250, "oneloop_k": 1000, "model_k": 200, "out_grid": [NK_OUT, NMU_OUT]}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation on every host core (one process per core, one
     cosmology each: how rsdfit's MPI pool uses it); each step is a bounded sample (every 4th point of each grid)"""
@@ -441,7 +446,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3*wall/max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: full PT table rebuild per cosmology (reference C++ at default epsrel, no Python assembly)"},
+            "config": dict(workload_config(args.batch),
+                           reference_arm="full PT table rebuild per cosmology by the reference C++ at its default epsrel, one "
+                                         "cosmology per host core; the reference's Python P(k,mu) assembly (< 1 s) is not included"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
