@@ -767,8 +767,10 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     // With a host destination the walkers go in chunks: the device-to-host copy of a chunk (PCIe, the slow leg when
     // full P(k, mu) grids leave the device) runs on the copy stream under the kernels of the next chunk.
     const int chunk = (h_out && npts > 0 && nw >= 2*GAL_PIPE_CHUNK) ? GAL_PIPE_CHUNK : nw;
-    for (int w0 = 0; w0 < nw; w0 += chunk) {
-        const int n = std::min(chunk, nw - w0);
+    for (int w0 = 0, n = 0; w0 < nw; w0 += n) {
+        // the last chunk is halved: its copy is the only one nothing hides
+        const int left = nw - w0;
+        n = left > chunk ? chunk : ((chunk < nw && left > chunk/2) ? chunk/2 : left);
         run_walkers(w0, n);
         if (h_out && npts > 0) {
             if (!copy_stream) {
