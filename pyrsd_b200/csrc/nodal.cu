@@ -175,7 +175,7 @@ k_nodal_apply(const NodalArgs g)
             o0_next = g.outer_off[ik + k_stride]; o1_next = g.outer_off[ik + k_stride + 1];
             n0_next = g.node_off[ik + k_stride];  n1_next = g.node_off[ik + k_stride + 1];
         }
-        // the index word and the coefficients of the NEXT node of this lane are loaded one iteration ahead: the
+        // the index word and the stencil coordinate of the NEXT node of this lane are loaded one iteration ahead: the
         // shared-memory reads depend on them, and an exposed L2 round trip per node was the largest stall
         int64_t node = n0 + tid;
         int pk_next = 0;

@@ -12,7 +12,8 @@
 //
 // One CTA = (tile of spectra, chunk of k); the tile's tables are staged once with TMA bulk copies; per k the
 // outer values P(a) are tabulated in shared memory, then every thread walks nodes with coalesced loads of
-// the node stream {b_j0, outer index, Lagrange coefficients, W columns} (structure-of-arrays), reads the
+// the node stream {packed outer index and stencil start, stencil coordinate, W columns} (structure-of-arrays; the four
+// Lagrange coefficients are formed from the coordinate in registers), reads the
 // four table values per spectrum from shared memory and accumulates in registers; a shuffle reduction and
 // a cross-warp pass finish each k.  CTAs of the same k chunk are adjacent in launch order so that the node
 // stream is read from DRAM once and from L2 afterwards.
