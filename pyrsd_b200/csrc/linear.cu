@@ -118,8 +118,41 @@ k_linear_apply(int nout, int nrow, const double* __restrict__ Omega, const doubl
     }
 }
 
+// Operators with a handful of outputs (sigma_v^2-type scalars: one output per cosmology) leave the MMA kernel with
+// 8 CTAs on 148 SMs (55 us each, latency-bound: ncu, profiles/r01_ncu_others.json): one warp per (row, output) dot
+// product instead.
+__global__ void __launch_bounds__(256)
+k_linear_dot(int nout, int nrow, const double* __restrict__ Omega, const double* __restrict__ tables,
+             const int* __restrict__ tab_index, double* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= nrow*nout) return;
+    const int row = item/nout, o = item - row*nout;
+    const double2* a = reinterpret_cast<const double2*>(tables + (size_t)tab_index[row]*TAB_MPAD);
+    const double2* b = reinterpret_cast<const double2*>(Omega + (size_t)o*TAB_MPAD);
+    double s0 = 0.0, s1 = 0.0;
+    for (int j = lane; j < TAB_MPAD/2; j += 32) {
+        const double2 x = __ldg(a + j), y = __ldg(b + j);
+        s0 = fma(x.x, y.x, s0);
+        s1 = fma(x.y, y.y, s1);
+    }
+    double s = s0 + s1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) out[(size_t)row*nout + o] = s;
+}
+
 void LinearOp::apply(Context& ctx, const double* tables, const int* tab_index, int nrow, double* out) const
 {
+    if (nout <= 4) {
+        ProfScope prof(ctx, PROF_LINEAR);
+        const int items = nrow*nout;
+        k_linear_dot<<<(items + 7)/8, 256, 0, ctx.stream>>>(nout, nrow, Omega.p, tables, tab_index, out);
+        PRSD_CUDA(cudaGetLastError());
+        ctx.launches++;
+        return;
+    }
     static_assert(TAB_MPAD % 2 == 0, "table rows must be 16-byte multiples");
     dim3 grid((nout + 8*LA_NT - 1)/(8*LA_NT), (nrow + 8*LA_MT - 1)/(8*LA_MT));
     ProfScope prof(ctx, PROF_LINEAR);

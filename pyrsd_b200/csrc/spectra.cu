@@ -193,9 +193,20 @@ k_spline_build_band(int n, int band, const double* __restrict__ X, const double*
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
         const double* yy = y + lo[i];
-        double acc = 0.0;
-        for (int jj = 0; jj < band; jj++) acc = fma(__ldg(Sb + (size_t)jj*n + i), yy[jj], acc);
-        sig[i] = acc;
+        // four independent partial sums, loads of a group in flight together: the loop waits on L2 latency (ncu:
+        // long-scoreboard stalls 30 per issue with one chain)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int jj = 0;
+        for (; jj + 3 < band; jj += 4) {
+            const double e0 = __ldg(Sb + (size_t)jj*n + i), e1 = __ldg(Sb + (size_t)(jj + 1)*n + i);
+            const double e2 = __ldg(Sb + (size_t)(jj + 2)*n + i), e3 = __ldg(Sb + (size_t)(jj + 3)*n + i);
+            a0 = fma(e0, yy[jj], a0);
+            a1 = fma(e1, yy[jj + 1], a1);
+            a2 = fma(e2, yy[jj + 2], a2);
+            a3 = fma(e3, yy[jj + 3], a3);
+        }
+        for (; jj < band; jj++) a0 = fma(__ldg(Sb + (size_t)jj*n + i), yy[jj], a0);
+        sig[i] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     double* o = out + (size_t)s*5*n;
