@@ -414,26 +414,34 @@ __global__ void k_gal_groups(int nkm, const double* __restrict__ par, const doub
 }
 
 // P_gal(k_obs, mu_obs) of walker parameters p from its group splines
-__device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* __restrict__ km, const double* __restrict__ p,
-                                                 const double* __restrict__ gs /*[nkm][6][4][4]*/, const double* __restrict__ gc,
-                                                 double kobs, double muobs)
+// AP remapping and interval search: (k_obs, mu_obs) -> (k', mu', interval i of the model grid); false outside the grid
+__device__ __forceinline__ bool gal_locate(const GalDev& G, const double* __restrict__ km, const double* __restrict__ gc,
+                                           double kobs, double muobs, double& k, double& mu, int& i)
 {
     const int nkm = G.nkm;
     // rsd/tools.py:54-75: F = alpha_par/alpha_perp, k' = (k/alpha_perp) sqrt(1 + mu^2 (F^-2 - 1)), mu' = (mu/F)/sqrt(...)
-    double k = kobs*gc[6], mu = muobs;
+    k = kobs*gc[6]; mu = muobs;
     if (gc[8] != 0.0) {
         const double y = 1.0 + muobs*muobs*gc[8];
         const double inv = rsqrt(y);
         k = kobs*gc[6]*(y*inv);
         mu = muobs*gc[7]*inv;
     }
-    if (!(k >= km[0] && k <= km[nkm - 1])) return nan("");   // the reference raises InterpolationDomainError (_cache.py:327-339)
-    int i = (int)((log(k) - G.lnkm0)*G.inv_dlnkm);
+    i = 0;
+    if (!(k >= km[0] && k <= km[nkm - 1])) return false;     // the reference raises InterpolationDomainError (_cache.py:327-339)
+    i = (int)((log(k) - G.lnkm0)*G.inv_dlnkm);
     if (i < 0) i = 0;
     if (i > nkm - 2) i = nkm - 2;
     while (i > 0 && k < km[i]) --i;
     while (i < nkm - 2 && k > km[i + 1]) ++i;
-    const double t = k - km[i];
+    return true;
+}
+
+// P(k', mu') from the coefficient block `knot` [6][4][4] of interval i (global memory, or staged in shared memory)
+template <bool STAGED>
+__device__ __forceinline__ double gal_eval(const GalDev& G, const double* __restrict__ p, const double* knot,
+                                           const double* __restrict__ gc, double k, double mu, double t)
+{
     const double mu2 = mu*mu;
     const int nmom = G.cfg.max_mu/2 + 1;
     const double fs = p[W_FS];
@@ -451,13 +459,12 @@ __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* 
     } else {
         Gc = fog(fm, kmu*p[W_SIGC]); GsA = fog(fm, kmu*p[W_SIGSA]); GsB = fog(fm, kmu*p[W_SIGSB]);
     }
-    const double* knot = gs + (size_t)i*(GAL_NGRP*16);
     auto grp = [&](int g) {
         const double2* q = reinterpret_cast<const double2*>(knot + g*16);
         double tot = gc[g], mpow = 1.0;
 #pragma unroll 4
         for (int m = 0; m < nmom; m++) {
-            const double2 yb = __ldg(q + 2*m), cd = __ldg(q + 2*m + 1);
+            const double2 yb = STAGED ? q[2*m] : __ldg(q + 2*m), cd = STAGED ? q[2*m + 1] : __ldg(q + 2*m + 1);
             tot += mpow*(yb.x + t*(yb.y + t*(cd.x + t*cd.y)));
             mpow *= mu2;
         }
@@ -479,17 +486,58 @@ __device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* 
     return res*gc[9];
 }
 
+
+__device__ __forceinline__ double gal_pkmu_point(const GalDev& G, const double* __restrict__ km, const double* __restrict__ p,
+                                                 const double* __restrict__ gs /*[nkm][6][4][4]*/, const double* __restrict__ gc,
+                                                 double kobs, double muobs)
+{
+    double k, mu;
+    int i;
+    if (!gal_locate(G, km, gc, kobs, muobs, k, mu, i)) return nan("");
+    return gal_eval<false>(G, p, gs + (size_t)i*(GAL_NGRP*16), gc, k, mu, k - km[i]);
+}
+
+// One thread per (k, mu) point.  The 128 points of a CTA are neighbours in the caller's list, so their intervals of
+// the model grid usually span a few knots: those coefficient blocks (768 B each) are staged in shared memory once,
+// and the 36 16-byte reads of every point hit shared memory instead of waiting on L2 (ncu before: long-scoreboard
+// stalls 16 per issue, L1 hit rate 64 %).  CTAs whose points span more than PK_SPAN knots read global memory.
+static const int PK_SPAN = 8;
+
 __global__ void __launch_bounds__(128)
 k_gal_pkmu(GalDev G, const double* __restrict__ km, const double* __restrict__ par, const double* __restrict__ grpspl,
            const double* __restrict__ grpconst, int npts, const double* __restrict__ kk, const double* __restrict__ mm,
            double* __restrict__ out)
 {
+    __shared__ __align__(16) double s_knots[PK_SPAN*GAL_NGRP*16];
+    __shared__ int s_lo, s_hi;
     const int w = blockIdx.y, j = blockIdx.x*blockDim.x + threadIdx.x;
-    if (j >= npts) return;
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double* gs = grpspl + (size_t)w*GAL_NGRP*16*G.nkm;
+    const double* gc = grpconst + (size_t)w*GAL_NCONST;
+    if (threadIdx.x == 0) { s_lo = G.nkm; s_hi = -1; }
+    __syncthreads();
+    double k = 0.0, mu = 0.0;
+    int i = 0;
+    const bool live = j < npts;
+    const bool ok = live && gal_locate(G, km, gc, kk[j], mm[j], k, mu, i);
+    if (ok) { atomicMin(&s_lo, i); atomicMax(&s_hi, i); }
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi;
+    const bool staged = hi >= lo && hi - lo < PK_SPAN;
+    if (staged) {
+        const int n2 = (hi - lo + 1)*(GAL_NGRP*16/2);
+        const double2* src = reinterpret_cast<const double2*>(gs + (size_t)lo*(GAL_NGRP*16));
+        double2* dst = reinterpret_cast<double2*>(s_knots);
+        for (int t = threadIdx.x; t < n2; t += blockDim.x) dst[t] = __ldg(src + t);
+    }
+    __syncthreads();
+    if (!live) return;
+    double v;
+    if (!ok) v = nan("");
+    else if (staged) v = gal_eval<true>(G, p, s_knots + (size_t)(i - lo)*(GAL_NGRP*16), gc, k, mu, k - km[i]);
+    else v = gal_eval<false>(G, p, gs + (size_t)i*(GAL_NGRP*16), gc, k, mu, k - km[i]);
     // streaming store: the 82 MB of results per batch would otherwise evict the walkers' coefficient tables from L2
-    // (ncu: L2 hit rate 52 % with plain stores)
-    __stcs(out + (size_t)w*npts + j, gal_pkmu_point(G, km, par + (size_t)w*GAL_NPAR, grpspl + (size_t)w*GAL_NGRP*16*G.nkm,
-                                                    grpconst + (size_t)w*GAL_NCONST, kk[j], mm[j]));
+    __stcs(out + (size_t)w*npts + j, v);
 }
 
 // P_ell(k) = (2 ell + 1) \int_0^1 dmu L_ell(mu) P(k, mu) with Simpson's rule on nmu (odd) equally spaced mu:
