@@ -337,9 +337,19 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
     for (int idx = tid; idx < 4*nkm; idx += blockDim.x) {
         const int m = idx/nkm, i = idx - m*nkm;
         const double* y = Y + m*nkm + mlo[i];
-        double acc = 0.0;
-        for (int jj = 0; jj < mband; jj++) acc = fma(__ldg(Mb + (size_t)jj*nkm + i), y[jj], acc);
-        Mm[idx] = acc;
+        // four independent partial sums with their loads in flight together (the single chain waited on L2 latency)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int jj = 0;
+        for (; jj + 3 < mband; jj += 4) {
+            const double e0 = __ldg(Mb + (size_t)jj*nkm + i), e1 = __ldg(Mb + (size_t)(jj + 1)*nkm + i);
+            const double e2 = __ldg(Mb + (size_t)(jj + 2)*nkm + i), e3 = __ldg(Mb + (size_t)(jj + 3)*nkm + i);
+            a0 = fma(e0, y[jj], a0);
+            a1 = fma(e1, y[jj + 1], a1);
+            a2 = fma(e2, y[jj + 2], a2);
+            a3 = fma(e3, y[jj + 3], a3);
+        }
+        for (; jj < mband; jj++) a0 = fma(__ldg(Mb + (size_t)jj*nkm + i), y[jj], a0);
+        Mm[idx] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     // store [walker][pair][moment][Y | b | c | d]
