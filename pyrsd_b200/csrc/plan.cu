@@ -213,26 +213,28 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
     res.ensure(nc, nk);
     const int ntile = (nc + 7)/8;
 
-    // ---- tile maps
-    std::vector<int> slot(ntile*8), rowI(ntile*8), tabL(nc);
-    for (int t = 0; t < ntile; t++)
-        for (int r = 0; r < 8; r++) {
-            slot[t*8 + r] = sp.table_index(std::min(t*8 + r, nc - 1), SP_LIN);
-            rowI[t*8 + r] = r;
-        }
-    for (int i = 0; i < nc; i++) tabL[i] = sp.table_index(i, SP_LIN);
-    s_slot.upload(slot, s);
-    s_rowA.upload(rowI, s);
-    DevBuf<int> d_tabL;
-    d_tabL.upload(tabL, s);
-
-    // ---- stage A: one-loop tables (tiles of nodal_diag_rows() cosmologies)
-    {
+    // ---- tile maps: the table layout of a batch depends on its size only (SpectraBatch::table_index), so the index
+    // arrays are built and uploaded when the batch size changes, not on every run
+    if (idx_nc_a != nc) {
+        std::vector<int> slot(ntile*8), rowI(ntile*8), tabL(nc);
+        for (int t = 0; t < ntile; t++)
+            for (int r = 0; r < 8; r++) {
+                slot[t*8 + r] = sp.table_index(std::min(t*8 + r, nc - 1), SP_LIN);
+                rowI[t*8 + r] = r;
+            }
+        for (int i = 0; i < nc; i++) tabL[i] = sp.table_index(i, SP_LIN);
+        s_slot.upload(slot, s);
+        s_rowA.upload(rowI, s);
+        d_tabL.upload(tabL, s);
+        // stage A: tiles of nodal_diag_rows() cosmologies
         const int R = nodal_diag_rows(), nt = (nc + R - 1)/R;
         std::vector<int> dslot((size_t)nt*R);
         for (int i = 0; i < nt*R; i++) dslot[i] = sp.table_index(std::min(i, nc - 1), SP_LIN);
         s_rowB.upload(dslot, s);
+        idx_nc_a = nc;
     }
+
+    // ---- stage A: one-loop tables
     s_op1.ensure((size_t)ntile*8*ONELOOP_N*8);
     nodal_apply_diag(c, op_1loop, sp.tables.p, s_rowB.p, nc, s_op1.p);
     s_lin1.ensure((size_t)nc*3*ONELOOP_N);
@@ -257,16 +259,19 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
     cudaStream_t s = c.stream;
     const int nc = sp.ncosmo;
     const int ntile = (nc + 7)/8;
-    std::vector<int> tabL(nc), tabSq(nc), tab22(nc);
-    for (int i = 0; i < nc; i++) {
-        tabL[i] = sp.table_index(i, SP_LIN);
-        tabSq[i] = sp.table_index(i, SP_LIN_SQ);
-        tab22[i] = sp.table_index(i, SP_P22BAR);
+    if (idx_nc_b != nc) {
+        std::vector<int> tabSq(nc), tab22(nc), mslot(nc*4);
+        for (int i = 0; i < nc; i++) {
+            tabSq[i] = sp.table_index(i, SP_LIN_SQ);
+            tab22[i] = sp.table_index(i, SP_P22BAR);
+            const int kinds[4] = {SP_LIN, SP_DD1, SP_DV1, SP_VV1};
+            for (int r = 0; r < 4; r++) mslot[i*4 + r] = sp.table_index(i, kinds[r]);
+        }
+        d_tabSq.upload(tabSq, s);
+        d_tab22.upload(tab22, s);
+        s_tabidx.upload(mslot, s);
+        idx_nc_b = nc;
     }
-    DevBuf<int> d_tabL, d_tabSq, d_tab22;
-    d_tabL.upload(tabL, s);
-    d_tabSq.upload(tabSq, s);
-    d_tab22.upload(tab22, s);
 
     // ---- stage B: I_mn, K_mn
     s_ik.ensure((size_t)ntile*8*nk*32);
@@ -278,15 +283,7 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
         c.launches++;
     }
     // ---- stage B: ImnOneLoop (one tile = one cosmology, rows = spectrum pairs)
-    if (with_ml) {
-        std::vector<int> mslot(nc*4);
-        for (int i = 0; i < nc; i++) {
-            const int kinds[4] = {SP_LIN, SP_DD1, SP_DV1, SP_VV1};
-            for (int r = 0; r < 4; r++) mslot[i*4 + r] = sp.table_index(i, kinds[r]);
-        }
-        s_tabidx.upload(mslot, s);
-        nodal_apply_ml(c, op_ml, sp.tables.p, s_tabidx.p, nc, res.ML.p);
-    }
+    if (with_ml) nodal_apply_ml(c, op_ml, sp.tables.p, s_tabidx.p, nc, res.ML.p);
     // ---- 1-D functionals
     s_linmain.ensure((size_t)nc*lin_main.nout);
     lin_main.apply(c, sp.tables.p, d_tabL.p, nc, s_linmain.p);

@@ -52,6 +52,9 @@ struct PTPlan {
     // scratch
     DevBuf<double> s_op1, s_lin1, s_ik, s_mlp, s_mln, s_linmain, s_small, s_ol, s_plk;
     DevBuf<int> s_slot, s_rowA, s_rowB, s_tabidx;
+    // index arrays of the current batch size (rebuilt when it changes)
+    DevBuf<int> d_tabL, d_tabSq, d_tab22;
+    int idx_nc_a = -1, idx_nc_b = -1;
     double build_seconds = 0.0;
 
     PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l = false);
