@@ -48,6 +48,8 @@ int prsd_knot_grid(int* n, double* lnq /* may be NULL */);
  *      {qmin, ln_far, ln_mid, bao_lo, bao_hi, bao_dq, ln_inner, ln_thin,
  *       4 x {k_below, n_outer, n_inner, n_thin}   Gauss-Legendre orders by k for I_mn, K_mn, one-loop tables,
  *       4 x {k_below, n_outer, n_inner, n_thin}   the same for ImnOneLoop}.
+ *      A band applies to k < k_below (first match); at or above the fourth band's k_below the THIRD band applies
+ *      again (default 0.5: the top orders are only needed where the model reads the one-loop spectra; 1e30 = never).
  *      Replaces the reference's `epsrel` constructor argument (Imn.i:8, Jmn.i:8, Kmn.i:8): accuracy is set
  *      by the fixed rule.  Every `cfg40` argument below may be NULL (defaults). */
 int prsd_quad_config_default(double* cfg40);
