@@ -50,6 +50,34 @@ static int guarded(F&& f)
     }
 }
 
+// Every entry point that takes a context-owning handle runs with that context's device current (the current device
+// is per-thread state: another Context, torch, or a call from a different host thread may have changed it) and
+// restores the caller's device on exit.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(int dev) : want(dev)
+    {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) PRSD_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { if (want >= 0 && prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+
+template <typename F>
+static int guarded(int device, F&& f)
+{
+    return guarded([&] { DeviceGuard dg(device); f(); });
+}
+
+static int dev_of(const prsd_ctx* h) { return h ? h->c.device : -1; }
+static int dev_of(const prsd_spectra* h) { return (h && h->s.ctx) ? h->s.ctx->device : -1; }
+static int dev_of(const prsd_plan* h) { return (h && h->p.ctx) ? h->p.ctx->device : -1; }
+static int dev_of(const prsd_result* h) { return (h && h->ctx) ? h->ctx->device : -1; }
+static int dev_of(const prsd_galaxy* h) { return (h && h->g.ctx) ? h->g.ctx->device : -1; }
+static int dev_of(const prsd_gridop* h) { return (h && h->op.ctx) ? h->op.ctx->device : -1; }
+static int dev_of(const prsd_window* h) { return (h && h->op.ctx) ? h->op.ctx->device : -1; }
+
 static QuadConfig cfg_from(const double* c)
 {
     QuadConfig q;
@@ -223,15 +251,15 @@ int prsd_ctx_create(int device, prsd_ctx** out)
 {
     return guarded([&] { PRSD_REQUIRE(out, "null output"); *out = new prsd_ctx(device); });
 }
-int prsd_ctx_destroy(prsd_ctx* ctx) { return guarded([&] { delete ctx; }); }
-int prsd_ctx_sync(prsd_ctx* ctx) { return guarded([&] { PRSD_REQUIRE(ctx, "null context"); ctx->c.sync(); }); }
+int prsd_ctx_destroy(prsd_ctx* ctx) { return guarded(dev_of(ctx), [&] { delete ctx; }); }
+int prsd_ctx_sync(prsd_ctx* ctx) { return guarded(dev_of(ctx), [&] { PRSD_REQUIRE(ctx, "null context"); ctx->c.sync(); }); }
 int prsd_ctx_launches(prsd_ctx* ctx, long long* n)
 {
-    return guarded([&] { PRSD_REQUIRE(ctx && n, "null argument"); *n = ctx->c.launches; });
+    return guarded(dev_of(ctx), [&] { PRSD_REQUIRE(ctx && n, "null argument"); *n = ctx->c.launches; });
 }
 int prsd_ctx_stream(prsd_ctx* ctx, void** s)
 {
-    return guarded([&] { PRSD_REQUIRE(ctx && s, "null argument"); *s = (void*)ctx->c.stream; });
+    return guarded(dev_of(ctx), [&] { PRSD_REQUIRE(ctx && s, "null argument"); *s = (void*)ctx->c.stream; });
 }
 
 int prsd_knot_grid(int* n, double* lnq)
@@ -261,23 +289,23 @@ int prsd_quad_config_default(double* c9)
 int prsd_spectra_create(prsd_ctx* ctx, int ncosmo, int nspl, const double* k, const double* T,
                         const double* pars, prsd_spectra** out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && k && T && pars && out, "null argument");
         *out = new prsd_spectra(ctx->c, ncosmo, nspl, k, T, pars);
     });
 }
-int prsd_spectra_destroy(prsd_spectra* sp) { return guarded([&] { delete sp; }); }
+int prsd_spectra_destroy(prsd_spectra* sp) { return guarded(dev_of(sp), [&] { delete sp; }); }
 int prsd_spectra_rescale(prsd_spectra* sp, const double* fac)
 {
-    return guarded([&] { PRSD_REQUIRE(sp && fac, "null argument"); sp->s.rescale_linear(fac); });
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && fac, "null argument"); sp->s.rescale_linear(fac); });
 }
 int prsd_spectra_plin(prsd_spectra* sp, int nq, const double* q, double* out)
 {
-    return guarded([&] { PRSD_REQUIRE(sp && (nq == 0 || (q && out)), "null argument"); sp->s.eval_linear(nq, q, out); });
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && (nq == 0 || (q && out)), "null argument"); sp->s.eval_linear(nq, q, out); });
 }
 int prsd_spectra_table(prsd_spectra* sp, int kind, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && out, "null argument");
         PRSD_REQUIRE(kind >= 0 && kind < SP_NKIND, "invalid table kind %d", kind);
         SpectraBatch& s = sp->s;
@@ -288,7 +316,7 @@ int prsd_spectra_table(prsd_spectra* sp, int kind, double* out)
 }
 int prsd_spectra_set_oneloop(prsd_spectra* sp, const double* tables)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && tables, "null argument");
         SpectraBatch& s = sp->s;
         DevBuf<double> d;
@@ -299,12 +327,12 @@ int prsd_spectra_set_oneloop(prsd_spectra* sp, const double* tables)
 }
 int prsd_spectra_oneloop_eval(prsd_spectra* sp, int which, int full, int nq, const double* q, double* out)
 {
-    return guarded([&] { PRSD_REQUIRE(sp && (nq == 0 || (q && out)), "null argument"); sp->s.eval_oneloop(which, full != 0, nq, q, out); });
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && (nq == 0 || (q && out)), "null argument"); sp->s.eval_oneloop(which, full != 0, nq, q, out); });
 }
 
 int prsd_eval_imn(prsd_spectra* sp, int m, int n, int nk, const double* k, const double* cfg9, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
         // the reference aborts on invalid indices (Imn.cpp:186); here: error code
         PRSD_REQUIRE(m >= 0 && m <= 3 && n >= 0 && n <= 3, "Imn: invalid indices, m = %d, n = %d", m, n);
@@ -314,7 +342,7 @@ int prsd_eval_imn(prsd_spectra* sp, int m, int n, int nk, const double* k, const
 
 int prsd_eval_kmn(prsd_spectra* sp, int m, int n, int tidal, int part, int nk, const double* k, const double* cfg9, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
         int kid = -1;
         // Kmn::Evaluate dispatch on 2 (3 m + tidal) + n (Kmn.cpp:151-183)
@@ -335,7 +363,7 @@ int prsd_eval_kmn(prsd_spectra* sp, int m, int n, int tidal, int part, int nk, c
 
 int prsd_eval_jmn(prsd_spectra* sp, int m, int n, int nk, const double* k, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
         const int id = 3*m + n;
         PRSD_REQUIRE(m >= 0 && n >= 0 && (id == 0 || id == 1 || id == 2 || id == 3 || id == 4 || id == 6) && n <= 2,
@@ -356,7 +384,7 @@ int prsd_eval_jmn(prsd_spectra* sp, int m, int n, int nk, const double* k, doubl
 int prsd_eval_imn_oneloop(prsd_spectra* sp, int p1, int p2, int which, int m, int n, int nk, const double* k,
                           const double* cfg9, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && (nk == 0 || (k && out)), "null argument");
         PRSD_REQUIRE(sp->s.have_oneloop, "ImnOneLoop: one-loop spectra have not been set for this batch");
         PRSD_REQUIRE(p1 >= 0 && p1 <= 2 && p2 <= 2, "ImnOneLoop: invalid spectra (%d, %d)", p1, p2);
@@ -394,7 +422,7 @@ int prsd_eval_imn_oneloop(prsd_spectra* sp, int p1, int p2, int which, int m, in
 
 int prsd_eval_ps_integral(prsd_spectra* sp, int what, int n, const double* x, double factor, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && out, "null argument");
         std::vector<LinOutSpec> o;
         int kind = SP_LIN;
@@ -428,7 +456,7 @@ int prsd_eval_ps_integral(prsd_spectra* sp, int what, int n, const double* x, do
 
 int prsd_eval_kurtosis(prsd_spectra* sp, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp && out, "null argument");
         PRSD_REQUIRE(sp->s.have_oneloop, "VelocityKurtosis: one-loop spectra have not been set for this batch");
         eval_linear_generic(sp->s, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}}, SP_P22BAR, out);
@@ -437,15 +465,15 @@ int prsd_eval_kurtosis(prsd_spectra* sp, double* out)
 
 int prsd_plan_create(prsd_ctx* ctx, int nk, const double* k, const double* cfg9, int flags, prsd_plan** out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && k && out, "null argument");
         *out = new prsd_plan(ctx->c, k, nk, cfg_from(cfg9), (flags & 1) != 0, (flags & 2) != 0);
     });
 }
-int prsd_plan_destroy(prsd_plan* plan) { return guarded([&] { delete plan; }); }
+int prsd_plan_destroy(prsd_plan* plan) { return guarded(dev_of(plan), [&] { delete plan; }); }
 int prsd_plan_info(prsd_plan* plan, double* info)
 {
-    return guarded([&] {
+    return guarded(dev_of(plan), [&] {
         PRSD_REQUIRE(plan && info, "null argument");
         const PTPlan& p = plan->p;
         info[0] = (double)p.nodes_total();
@@ -460,16 +488,18 @@ int prsd_plan_info(prsd_plan* plan, double* info)
 }
 int prsd_plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res)
 {
-    return guarded([&] {
+    return guarded(dev_of(plan), [&] {
         PRSD_REQUIRE(plan && sp && res, "null argument");
+        PRSD_REQUIRE(plan->p.ctx == sp->s.ctx, "prsd_plan_run: the plan and the spectra batch belong to different contexts");
         if (!*res) { *res = new prsd_result(); (*res)->ctx = plan->p.ctx; }
+        PRSD_REQUIRE((*res)->ctx == plan->p.ctx, "prsd_plan_run: the result belongs to another context");
         plan->p.run(sp->s, (*res)->r);
     });
 }
-int prsd_result_destroy(prsd_result* res) { return guarded([&] { delete res; }); }
+int prsd_result_destroy(prsd_result* res) { return guarded(dev_of(res), [&] { delete res; }); }
 int prsd_result_get(prsd_result* res, int what, double* out, long long n_expected)
 {
-    return guarded([&] {
+    return guarded(dev_of(res), [&] {
         PRSD_REQUIRE(res && out, "null argument");
         PTResult& r = res->r;
         const size_t c = r.ncosmo, nk = r.nk;
@@ -498,7 +528,7 @@ int prsd_result_get(prsd_result* res, int what, double* out, long long n_expecte
 int prsd_fftlog(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
                 const double* a, double* out, double* kr_out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && a && out, "null argument");
         PRSD_REQUIRE(batch > 0, "FFTLog: empty batch");
         auto plan = fftlog_plan(ctx->c, N, mu, q, dlnr, kr, kropt);
@@ -514,7 +544,7 @@ int prsd_fftlog(prsd_ctx* ctx, int batch, int N, double mu, double q, double dln
 int prsd_fftlog_device(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
                        const double* d_in, double* d_out, double* kr_out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && d_in && d_out, "null argument");
         auto plan = fftlog_plan(ctx->c, N, mu, q, dlnr, kr, kropt);
         fftlog_apply(ctx->c, *plan, batch, d_in, d_out);
@@ -525,7 +555,7 @@ int prsd_fftlog_device(prsd_ctx* ctx, int batch, int N, double mu, double q, dou
 int prsd_compute_xilm(prsd_ctx* ctx, int batch, int l, int m, int nk, const double* k, const double* pk,
                       int nr, const double* r, double smoothing, double scale, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && k && pk && r && out, "null argument");
         PRSD_REQUIRE(batch > 0 && nr > 0, "ComputeXiLM: empty request");
         DevBuf<double> dpk, dout((size_t)batch*nr);
@@ -539,7 +569,7 @@ int prsd_compute_xilm(prsd_ctx* ctx, int batch, int l, int m, int nk, const doub
 int prsd_compute_xilm_discrete(prsd_ctx* ctx, int method, int batch, int l, int m, int nk, const double* k, const double* pk,
                                int nr, const double* r, double smoothing, double scale, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && k && pk && r && out, "null argument");
         PRSD_REQUIRE(batch > 0 && nr > 0, "ComputeXiLM: empty request");
         for (int i = 1; i < nk; i++) PRSD_REQUIRE(k[i] > k[i - 1], "ComputeXiLM: abscissae must increase");
@@ -555,7 +585,7 @@ int prsd_compute_xilm_discrete(prsd_ctx* ctx, int method, int batch, int l, int 
 
 int prsd_discrete_integrate(prsd_ctx* ctx, int method, int batch, int n, const double* x, const double* y, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && x && y && out, "null argument");
         PRSD_REQUIRE(batch > 0, "discrete integration: empty request");
         DevBuf<double> dx, dy, dout((size_t)batch);
@@ -570,7 +600,7 @@ int prsd_discrete_integrate(prsd_ctx* ctx, int method, int batch, int n, const d
 int prsd_compute_xilm_fftlog(prsd_ctx* ctx, int batch, int l, int m, int N, const double* k, const double* pk,
                              double q, double smoothing, double* r_out, double* xi_out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && k && pk && r_out && xi_out, "null argument");
         PRSD_REQUIRE(batch > 0 && N >= 2, "ComputeXiLM_fftlog: empty request");
         DevBuf<double> dk, dpk, dxi((size_t)batch*N);
@@ -589,7 +619,7 @@ int prsd_zeldovich(prsd_ctx* ctx, int nrow, const double* X0, const double* XX, 
                    const double* ratio, int lowk, double k0_low, const double* plin, const double* q3,
                    int nk, const double* k, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && X0 && YY && sigmasq && k && out, "null argument");
         PRSD_REQUIRE(nrow > 0 && nk > 0, "Zeldovich: empty request");
         Context& c = ctx->c;
@@ -664,17 +694,17 @@ int prsd_galaxy_config_default(double* cfg64)
 int prsd_galaxy_create(prsd_ctx* ctx, const double* cfg64, int nkm, const double* kmodel, int nk_interp,
                        const double* k_interp, prsd_galaxy** out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && kmodel && k_interp && out, "null argument");
         *out = new prsd_galaxy(ctx->c, gal_cfg_from(cfg64), kmodel, nkm, k_interp, nk_interp);
     });
 }
-int prsd_galaxy_destroy(prsd_galaxy* g) { return guarded([&] { delete g; }); }
+int prsd_galaxy_destroy(prsd_galaxy* g) { return guarded(dev_of(g), [&] { delete g; }); }
 
 int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
                       const double* stoch, int npts, const double* k, const double* mu, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && sp && res && par && stoch && k && mu && out, "null argument");
         Context& c = *g->g.ctx;
         g->dk.upload(k, npts, c.stream);
@@ -687,7 +717,7 @@ int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
 int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
                              const double* stoch, int npts, const double* d_k, const double* d_mu, double* d_out)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && sp && res && par && stoch && d_k && d_mu && d_out, "null argument");
         g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, d_k, d_mu, d_out);
     });
@@ -696,7 +726,7 @@ int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res,
 int prsd_galaxy_poles(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
                       const double* stoch, int nk, const double* k, int nell, const int* ells, int nmu, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && sp && res && par && stoch && k && ells && out, "null argument");
         PRSD_REQUIRE(nk > 0 && nell > 0, "prsd_galaxy_poles: empty request");
         Context& c = *g->g.ctx;
@@ -711,7 +741,7 @@ int prsd_galaxy_poles(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
 int prsd_galaxy_poles_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
                              const double* stoch, int nk, const double* d_k, int nell, const int* ells, int nmu, double* d_out)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && sp && res && par && stoch && d_k && ells && d_out, "null argument");
         g->g.poles(sp->s, res->r, nw, cmap, par, stoch, nk, d_k, nell, ells, nmu, d_out);
     });
@@ -721,7 +751,7 @@ int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw,
                      const double* stoch, int nk, const double* k, int nell, const int* ells, int nmu,
                      const double* data, const double* cinv, double* chi2, double* poles)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && sp && res && par && stoch && k && ells && data && cinv && chi2, "null argument");
         PRSD_REQUIRE(nk > 0 && nell > 0 && nw > 0, "prsd_galaxy_chi2: empty request");
         Context& c = *g->g.ctx;
@@ -740,7 +770,7 @@ int prsd_galaxy_chi2(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw,
 
 int prsd_gridop_create(prsd_ctx* ctx, int nbin, int nk, int nmu, const double* weights, prsd_gridop** out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && weights && out, "null argument");
         *out = new prsd_gridop(ctx->c, nbin, nk, nmu, weights);
     });
@@ -748,12 +778,12 @@ int prsd_gridop_create(prsd_ctx* ctx, int nbin, int nk, int nmu, const double* w
 
 int prsd_gridop_destroy(prsd_gridop* op)
 {
-    return guarded([&] { delete op; });
+    return guarded(dev_of(op), [&] { delete op; });
 }
 
 int prsd_gridop_apply(prsd_gridop* g, int nw, const double* power, double* out, int device_ptrs)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && power && out, "null argument");
         PRSD_REQUIRE(nw > 0, "prsd_gridop_apply: empty request");
         GridOp& op = g->op;
@@ -771,7 +801,7 @@ int prsd_gridop_apply(prsd_gridop* g, int nw, const double* power, double* out, 
 
 int prsd_window_create(prsd_ctx* ctx, int nk, const double* k, int nell, const int* ells, double q, int N, prsd_window** out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && k && ells && out, "null argument");
         *out = new prsd_window(ctx->c, nk, k, nell, ells, q, N);
     });
@@ -779,12 +809,12 @@ int prsd_window_create(prsd_ctx* ctx, int nk, const double* k, int nell, const i
 
 int prsd_window_destroy(prsd_window* w)
 {
-    return guarded([&] { delete w; });
+    return guarded(dev_of(w), [&] { delete w; });
 }
 
 int prsd_window_info(prsd_window* w, int* info, double* rr)
 {
-    return guarded([&] {
+    return guarded(dev_of(w), [&] {
         PRSD_REQUIRE(w, "null argument");
         if (info) { info[0] = w->op.N; info[1] = w->op.off_in; info[2] = w->op.off_out; info[3] = w->op.nk; }
         if (rr) std::memcpy(rr, w->op.rr.data(), sizeof(double)*w->op.nk);
@@ -793,7 +823,7 @@ int prsd_window_info(prsd_window* w, int* info, double* rr)
 
 int prsd_window_set_kernel(prsd_window* w, const double* kern)
 {
-    return guarded([&] {
+    return guarded(dev_of(w), [&] {
         PRSD_REQUIRE(w && kern, "null argument");
         w->op.set_kernel(kern);
     });
@@ -802,7 +832,7 @@ int prsd_window_set_kernel(prsd_window* w, const double* kern)
 int prsd_window_apply(prsd_window* w, int nw, const double* poles, double* out, int mode, int device_ptrs, double* xi,
                       double* xi_conv)
 {
-    return guarded([&] {
+    return guarded(dev_of(w), [&] {
         PRSD_REQUIRE(w && poles && out, "null argument");
         PRSD_REQUIRE(nw > 0, "prsd_window_apply: empty request");
         WindowOp& op = w->op;
@@ -823,7 +853,7 @@ int prsd_window_apply(prsd_window* w, int nw, const double* poles, double* out, 
 int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x, const double* d_y, int nq, const double* xq,
                                 double* d_out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && x && d_y && xq && d_out, "null argument");
         PRSD_REQUIRE(nrows > 0 && nq > 0, "prsd_spline_resample_device: empty request");
         for (int i = 1; i < n; i++) PRSD_REQUIRE(x[i] > x[i - 1], "prsd_spline_resample_device: x must be increasing");
@@ -853,7 +883,7 @@ int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x
 int prsd_chi2(prsd_ctx* ctx, int nw, int n, const double* model, const double* data, const double* cinv, double* chi2,
               int model_on_device)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && model && data && cinv && chi2, "null argument");
         PRSD_REQUIRE(nw > 0 && n > 0, "prsd_chi2: empty request");
         Context& c = ctx->c;
@@ -869,7 +899,7 @@ int prsd_chi2(prsd_ctx* ctx, int nw, int n, const double* model, const double* d
 
 int prsd_galaxy_base(prsd_galaxy* g, int nw, int* nrows, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(g), [&] {
         PRSD_REQUIRE(g && nrows, "null argument");
         *nrows = GalaxyModel::n_base();
         if (out) g->g.base_to_host(nw, out);
@@ -878,14 +908,14 @@ int prsd_galaxy_base(prsd_galaxy* g, int nw, int* nrows, double* out)
 
 int prsd_galaxy_moments(prsd_galaxy* g, int nw, double* out)
 {
-    return guarded([&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });
+    return guarded(dev_of(g), [&] { PRSD_REQUIRE(g && out, "null argument"); g->g.moments_to_host(nw, out); });
 }
 
 
 /* -------------------------------------------- one-loop tables for the pygcl-style classes */
 int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg9, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(sp), [&] {
         PRSD_REQUIRE(sp, "null argument");
         Context& c = *sp->s.ctx;
         const QuadConfig cfg = cfg_from(cfg9);
@@ -910,18 +940,18 @@ int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg9, double* out)
 
 int prsd_spectra_set_oneloop_one(prsd_spectra* sp, int which, const double* table)
 {
-    return guarded([&] { PRSD_REQUIRE(sp && table, "null argument"); sp->s.set_oneloop_table(which, table); });
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && table, "null argument"); sp->s.set_oneloop_table(which, table); });
 }
 
 int prsd_spectra_get_oneloop(prsd_spectra* sp, double* out)
 {
-    return guarded([&] { PRSD_REQUIRE(sp && out, "null argument"); sp->s.get_oneloop_tables(out); });
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && out, "null argument"); sp->s.get_oneloop_tables(out); });
 }
 
 /* CubicSpline(x, y)(xq)  [Spline.i, Spline.cpp:211-273, 362-367]: netlib cubic spline, 0 outside the domain */
 int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, const double* y, int nq, const double* xq, double* out)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && x && y && xq && out, "null argument");
         PRSD_REQUIRE(batch > 0 && nq > 0, "CubicSpline: empty request");
         for (int i = 1; i < n; i++) PRSD_REQUIRE(x[i] > x[i - 1], "CubicSpline: abscissae must be increasing");
@@ -938,7 +968,7 @@ int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, con
 /* ----------------------------------------------------- measurement support */
 int prsd_ctx_profile(prsd_ctx* ctx, int enable)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx, "null argument");
         ctx->c.prof_reset();
         ctx->c.profiling = enable != 0;
@@ -947,7 +977,7 @@ int prsd_ctx_profile(prsd_ctx* ctx, int enable)
 
 int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms8, long long* count8)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && ms8 && count8, "null argument");
         ctx->c.prof_collect();
         static_assert(PROF_NTAGS == 8, "header documents 8 families");
@@ -957,7 +987,7 @@ int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms8, long long* count8)
 
 int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops)
 {
-    return guarded([&] {
+    return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && tflops && (mode == 0 || mode == 1), "bad argument");
         *tflops = fp64_peak_tflops(ctx->c, mode);
     });
@@ -965,7 +995,7 @@ int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops)
 
 int prsd_spectra_reload_device(prsd_spectra* sp, const double* d_k, const double* d_T, const double* d_pars)
 {
-    return guarded([&] { PRSD_REQUIRE(sp && d_k && d_T && d_pars, "null argument"); sp->s.reload_device(d_k, d_T, d_pars); });
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && d_k && d_T && d_pars, "null argument"); sp->s.reload_device(d_k, d_T, d_pars); });
 }
 
 } // extern "C"

@@ -58,7 +58,7 @@ inline std::string strprintf(const char* fmt, ...)
 // flight on any stream can never see its memory handed to someone else.
 void* pool_alloc(size_t bytes);
 void  pool_free(void* p) noexcept;
-void  pool_trim() noexcept;          // give every cached block back to the driver
+void  pool_trim(int device = -1) noexcept;   // give the cached blocks of one device (or all) back to the driver
 
 template <typename T>
 struct DevBuf {

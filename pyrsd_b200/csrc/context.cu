@@ -57,11 +57,20 @@ void* pool_alloc(size_t bytes)
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
-        // out of memory: return the cache to the driver and retry once
+        // out of memory: return THIS device's cache (ready and, after a synchronisation, pending blocks) to the
+        // driver and retry once
         cudaGetLastError();
         cudaDeviceSynchronize();
-        for (auto& r : P.ready) { cudaFree(r.second); P.cached_bytes -= r.first.second; }
-        P.ready.clear();
+        for (auto it = P.ready.begin(); it != P.ready.end();) {
+            if (it->first.first == dev) { cudaFree(it->second); P.cached_bytes -= it->first.second; it = P.ready.erase(it); }
+            else ++it;
+        }
+        std::vector<std::pair<void*, Block>> keep;
+        for (auto& pe : P.pending) {
+            if (pe.second.device == dev) { cudaFree(pe.first); P.cached_bytes -= pe.second.bytes; }
+            else keep.push_back(pe);
+        }
+        P.pending.swap(keep);
         e = cudaMalloc(&p, want);
     }
     if (e != cudaSuccess)
@@ -82,20 +91,40 @@ void pool_free(void* p) noexcept
     // bound the cache (varying batch sizes would otherwise accumulate blocks of every size ever used)
     static const size_t CACHE_LIMIT = size_t(24) << 30;
     if (P.cached_bytes > CACHE_LIMIT) {
-        for (auto& r : P.ready) { cudaFree(r.second); P.cached_bytes -= r.first.second; }
+        int prev = -1;
+        cudaGetDevice(&prev);
+        for (auto& r : P.ready) { cudaSetDevice(r.first.first); cudaFree(r.second); P.cached_bytes -= r.first.second; }
         P.ready.clear();
+        if (prev >= 0) cudaSetDevice(prev);
     }
 }
 
-void pool_trim() noexcept
+void pool_trim(int device) noexcept
 {
+    // gives the cached blocks of ONE device back to the driver (device < 0: all of them); blocks of other devices
+    // may belong to live contexts whose streams are still running
     Pool& P = pool();
     std::lock_guard<std::mutex> lk(P.mu);
-    for (auto& e : P.pending) cudaFree(e.first);     // cudaFree synchronises the owning device
-    for (auto& r : P.ready) cudaFree(r.second);
-    P.pending.clear();
-    P.ready.clear();
-    P.cached_bytes = 0;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    std::vector<std::pair<void*, Block>> keep;
+    for (auto& e : P.pending) {
+        if (device < 0 || e.second.device == device) {
+            cudaSetDevice(e.second.device);
+            cudaFree(e.first);                       // cudaFree synchronises the owning device
+            P.cached_bytes -= e.second.bytes;
+        } else keep.push_back(e);
+    }
+    P.pending.swap(keep);
+    for (auto it = P.ready.begin(); it != P.ready.end();) {
+        if (device < 0 || it->first.first == device) {
+            cudaSetDevice(it->first.first);
+            cudaFree(it->second);
+            P.cached_bytes -= it->first.second;
+            it = P.ready.erase(it);
+        } else ++it;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 Context::Context(int dev) : device(dev)
@@ -123,7 +152,7 @@ Context::~Context()
         for (auto& pr : prof_pending[t]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
-    pool_trim();
+    pool_trim(device);
 }
 
 cudaEvent_t Context::prof_event()

@@ -735,6 +735,12 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     PRSD_REQUIRE(nw > 0 && npts >= 0, "GalaxyModel::power: empty request");
     PRSD_REQUIRE(pt.nk == nk_interp, "GalaxyModel::power: PT tables are on %d k, model expects %d", pt.nk, nk_interp);
     PRSD_REQUIRE(sp.have_oneloop, "GalaxyModel::power: the PT stage has not been run for this batch");
+    PRSD_REQUIRE(sp.ctx == ctx, "GalaxyModel::power: the model and the spectra batch belong to different contexts");
+    PRSD_REQUIRE(pt.ncosmo == sp.ncosmo && pt.src_uid == sp.uid && pt.src_gen == sp.lin_gen,
+                 "GalaxyModel::power: the PT result was not computed from this spectra batch in its current state "
+                 "(result: %d cosmologies of batch %llu.%llu, spectra: %d of batch %llu.%llu); run the plan on these spectra first",
+                 pt.ncosmo, (unsigned long long)pt.src_uid, (unsigned long long)pt.src_gen, sp.ncosmo,
+                 (unsigned long long)sp.uid, (unsigned long long)sp.lin_gen);
     const int nc = sp.ncosmo;
     std::vector<int> hmap(nw);
     std::vector<double> r1(nw), r2(nw);

@@ -254,6 +254,8 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
 void PTPlan::run(SpectraBatch& sp, PTResult& res)
 {
     PRSD_REQUIRE(!only_oneloop, "this plan only holds the one-loop stage");
+    PRSD_REQUIRE(sp.ctx == ctx, "PTPlan::run: the plan and the spectra batch belong to different contexts");
+    res.src_uid = 0;                      // invalid until this run has been enqueued completely
     run_oneloop(sp, res, false);          // stage B is enqueued behind stage A without a host round trip
     Context& c = *ctx;
     cudaStream_t s = c.stream;
@@ -298,6 +300,8 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
         PRSD_CUDA(cudaGetLastError());
         c.launches++;
     }
+    res.src_uid = sp.uid;
+    res.src_gen = sp.lin_gen;
     c.sync();
 }
 

@@ -24,6 +24,7 @@ std::vector<double> zeldovich_rgrid();
 
 struct PTResult {
     int ncosmo = 0, nk = 0;
+    uint64_t src_uid = 0, src_gen = 0;     // SpectraBatch::uid / lin_gen the tables were computed from (0: none yet)
     // all device buffers, layouts [cosmo][...]
     DevBuf<double> I;          // [c][16][nk]   I_mn, index 4 m + n
     DevBuf<double> J;          // [c][6][nk]    order J00 J01 J02 J10 J11 J20

@@ -39,11 +39,12 @@ struct QuadConfig {
     double ln_thin  = 0.2;    // inner panels narrower than this in ln b use n_thin points: far from q ~ k the
                               // strip |q - r| <= k is thin and the integrand nearly polynomial across it
     // I_mn, K_mn and the one-loop tables (q_max = 1e5)
-    // The last band ends at its k_below: above it the rule of band 2 applies again.  The top orders exist because
-    // 2 I + 6 k^2 J P_L cancels to a few per cent where the model READS the one-loop spectra (k < 0.5); beyond, the
-    // tables only feed the ImnOneLoop integrands and the spline's upper end, (8, 6, 5) is converged to 1e-6 of
-    // max(|I|, P_L) there (scratch/tier_hi.py) and 45 % of the one-loop nodes sit above k = 0.5.
-    QuadTier tier[4]    = {{0.02, 5, 4, 3}, {0.08, 6, 5, 4}, {0.3, 8, 6, 5}, {0.5, 12, 7, 5}};
+    // The top orders exist because 2 I + 6 k^2 J P_L cancels to a few per cent above k ~ 0.3; they are kept up to the
+    // end of the one-loop grid (k = 10): k_interp runs to 1.0 and with use_P00_model / use_Pdv_model off the galaxy
+    // assembly reads P_dd / P_dv / P_vv there, so the 1e-5 parity bound holds on the whole grid (round 1 dropped to
+    // (8, 6, 5) above k = 0.5 for 5 % of the step and was 2e-4 there).  Above the last finite k_below of a
+    // user-supplied configuration the LAST tier applies.
+    QuadTier tier[4]    = {{0.02, 5, 4, 3}, {0.08, 6, 5, 4}, {0.3, 8, 6, 5}, {1e30, 12, 7, 5}};
     // ImnOneLoop (q_max = 10): the one-loop spectra are large at the hard cut and the h02-type kernels cancel to
     // leading order across v, so above k = 0.06 that operator keeps full-order panels everywhere
     QuadTier ml_tier[4] = {{0.02, 4, 4, 3}, {0.06, 6, 5, 4}, {0.3, 10, 7, 7}, {1e30, 10, 8, 8}};
@@ -51,7 +52,7 @@ struct QuadConfig {
     const QuadTier& tier_of(double k) const
     {
         for (int i = 0; i < 4; i++) if (k < tier[i].k_below) return tier[i];
-        return tier[2];
+        return tier[3];
     }
     QuadConfig ml_variant() const
     {

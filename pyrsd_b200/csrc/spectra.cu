@@ -1,5 +1,6 @@
 // spectra.cu -- device-resident spectra tables (see spectra.cuh).
 #include "spectra.cuh"
+#include <atomic>
 #include "pcr.cuh"
 
 #include <cmath>
@@ -324,6 +325,8 @@ SpectraBatch::SpectraBatch(Context& c, int ncosmo_, int nspl_, const double* k, 
     : ctx(&c), ncosmo(ncosmo_), nspl(nspl_)
 {
     PRSD_REQUIRE(ncosmo > 0, "SpectraBatch: ncosmo must be positive");
+    static std::atomic<uint64_t> next_uid{1};
+    uid = next_uid++;
     PRSD_REQUIRE(nspl >= 4 && nspl <= 4096, "SpectraBatch: %d transfer-function samples unsupported", nspl);
     h_params.resize(ncosmo);
     for (int i = 0; i < ncosmo; i++) {
@@ -374,6 +377,7 @@ void SpectraBatch::reload_device(const double* d_k, const double* d_T, const dou
     PRSD_CUDA(cudaGetLastError());
     ctx->launches++;
     have_oneloop = false;
+    lin_gen++;
 }
 
 void SpectraBatch::rescale_linear(const double* fac_host)
@@ -385,6 +389,7 @@ void SpectraBatch::rescale_linear(const double* fac_host)
     PRSD_CUDA(cudaGetLastError());
     ctx->launches++;
     for (int i = 0; i < ncosmo; i++) h_params[i].amp *= fac_host[i];
+    lin_gen++;
     ctx->sync();
 }
 

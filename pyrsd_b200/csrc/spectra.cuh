@@ -32,6 +32,9 @@ struct SpectraBatch {
     DevBuf<double> oneloop_spl;    // [ncosmo][4][5*ONELOOP_N] splines of the one-loop tables
     DevBuf<double> oneloop_raw;    // [ncosmo][4][ONELOOP_N] the tables themselves
     bool have_oneloop = false;
+    // identity of the batch and of its current linear spectra: PTPlan::run stamps its result with both, and the
+    // galaxy stage refuses a result computed from another batch or from spectra that have since been replaced
+    uint64_t uid = 0, lin_gen = 0;
 
     SpectraBatch(Context& c, int ncosmo_, int nspl_, const double* k, const double* T, const double* pars);
     // rebuild every linear-spectrum table from DEVICE-resident inputs: d_k, d_T [ncosmo][nspl],

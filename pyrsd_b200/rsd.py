@@ -90,7 +90,6 @@ class PTEngine(object):
         N.check(_L().prsd_plan_create(self.ctx.ptr, len(self.k_interp), self.k_interp, cfgp, flags, C.byref(p)))
         self.plan = _Plan(p)
         self._galaxies = {}
-        self._result = None
 
     def info(self):
         out = np.empty(8)
@@ -113,16 +112,14 @@ class PTEngine(object):
 
     def run(self, spectra, result=None):
         """everything rsd/pt_integrals.py tabulates, for every cosmology of the batch"""
-        res = result if result is not None else self._result
-        if res is None:
-            res = _new_result()
+        # a fresh result unless the caller passes one to be overwritten: a result handed out earlier must not
+        # change under its holder when the engine runs another batch
+        res = result if result is not None else _new_result()
         cur = res.ptr.value if isinstance(res.ptr, _vp) else res.ptr
         p = _vp(cur)
         N.check(_L().prsd_plan_run(self.plan.ptr, spectra.ptr, C.byref(p)))
         res.ptr = p
         res.ncosmo = spectra.ncosmo
-        if result is None:
-            self._result = res
         spectra.have_oneloop = True
         return res
 
@@ -486,7 +483,7 @@ class GalaxySpectrum(object):
 
     def _config(self):
         return galaxy_config(max_mu=self.max_mu, fog_model=self.fog_model, use_tidal_bias=self.use_tidal_bias,
-                             use_so_correction=self.use_so_correction, k0_low=5e-3, **self._models)
+                             use_so_correction=self.use_so_correction, k0_low=self.k0_low, **self._models)
 
     def power(self, k, mu, flatten=False):
         """P(k, mu) with the broadcasting rules of ``tools.broadcast_kmu`` (rsd/tools.py:225-266)"""
