@@ -27,50 +27,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "full PT P(k,mu) model evals/sec"
 UNIT = "evals/s"
-NK_OUT, NMU_OUT = 1000, 40
-SEED = 20261019
-
-
-# ----------------------------------------------------------------------------- workload
-def synthetic_batch(n, rank=0):
-    """n synthetic cosmologies + walker vectors: base = the reference's shipped Planck15 transfer
-    function; variant i: sigma8_z in U[0.45, 0.95], f in U[0.4, 1.0], b1_cA in U[1.2, 2.5] and a shape tilt
-    T_i(k) (k/0.05)^(delta/2), delta ~ N(0, 0.02), so that every table genuinely has to be rebuilt."""
-    from tests.gpu_common import b2_00, b2_01, stochasticity
-    from pyrsd_b200 import rsd
-    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden_pt.npz'))
-    t = np.load(os.path.join(ROOT, 'tests', 'golden', 'oracle_tight.npz'))
-    rng = np.random.default_rng(SEED + 1000*rank)
-    k_i, T_i = g['cosmo_k'], g['cosmo_T']
-    delta = rng.normal(0, 0.02, n)
-    T = T_i[None, :]*(k_i[None, :]/0.05)**(delta[:, None]/2)
-    k = np.repeat(k_i[None, :], n, axis=0)
-    pars = np.zeros((n, 8))
-    pars[:, 0] = float(g['cosmo_n_s'])
-    pars[:, 1] = float(t['delta_H'])**2        # re-normalisation to sigma8 is per-cosmology algebra done at assembly
-    pars[:, 2] = float(g['cosmo_h'])
-    pars[:, 3] = float(t['Omega0_m'])
-    pars[:, 4] = float(g['cosmo_Omega_b'])
-    pars[:, 5] = float(t['Tcmb'])
-    s8z = rng.uniform(0.45, 0.95, n)
-    f = rng.uniform(0.4, 1.0, n)
-    b1cA = rng.uniform(1.2, 2.5, n)
-    kmodel = np.logspace(np.log10(1e-3), np.log10(0.5), 200)
-    ks = rsd.stochasticity_grid(kmodel)
-    wpar = np.zeros((n, rsd.NPAR))
-    stoch = np.zeros((n, rsd.NPAIR, rsd.NSTOCH))
-    for i in range(n):
-        b1 = [b1cA[i], 1.5*b1cA[i], 1.4*b1cA[i], 1.9*b1cA[i]]
-        b00, b01 = [b2_00(b) for b in b1], [b2_01(b) for b in b1]
-        wpar[i] = rsd.pack_walker(s8z[i], f[i], 1.0, 1.0, 1.0, b1, 0.10, 0.08, 0.40, 1.0, 4.2, 6.0, 3e4, 9e4, 0., 0., None,
-                                  0.7486, float(g['cosmo_sigma8']), [b00, b00, b00, b00, b01, b01])
-        for p, (a, b) in enumerate(rsd.PAIRS):
-            lo, hi = sorted([b1[a], b1[b]])
-            stoch[i, p] = stochasticity(ks, s8z[i], lo, hi)
-    kout = np.logspace(-2.95, np.log10(0.49), NK_OUT)
-    mu = np.linspace(0., 1., NMU_OUT)
-    kk, mm = [a.ravel() for a in np.meshgrid(kout, mu, indexing='ij')]
-    return dict(k=k, T=T, pars=pars, wpar=wpar, stoch=stoch, kmodel=kmodel, kk=np.ascontiguousarray(kk), mm=np.ascontiguousarray(mm))
+from pyrsd_b200.synthetic import NK_OUT, NMU_OUT, SEED, synthetic_batch  # noqa: E402  (workload generator, no GPU needed)
 
 
 class ClockSampler(threading.Thread):

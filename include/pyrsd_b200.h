@@ -15,6 +15,7 @@
 #ifndef PYRSD_B200_H
 #define PYRSD_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -44,15 +45,15 @@ int prsd_ctx_stream(prsd_ctx* ctx, void** cuda_stream);
 /* ---- tabulation grid shared by every operator (ln q of the knots) */
 int prsd_knot_grid(int* n, double* lnq /* may be NULL */);
 
-/* ---- quadrature configuration: cfg[40] (csrc/quad.h QuadConfig) =
+/* ---- quadrature configuration: cfg[56] (csrc/quad.h QuadConfig) =
  *      {qmin, ln_far, ln_mid, bao_lo, bao_hi, bao_dq, ln_inner, ln_thin,
- *       4 x {k_below, n_outer, n_inner, n_thin}   Gauss-Legendre orders by k for I_mn, K_mn, one-loop tables,
- *       4 x {k_below, n_outer, n_inner, n_thin}   the same for ImnOneLoop}.
- *      A band applies to k < k_below (first match); at or above the fourth band's k_below the THIRD band applies
- *      again (default 0.5: the top orders are only needed where the model reads the one-loop spectra; 1e30 = never).
+ *       6 x {k_below, n_outer, n_inner, n_thin}   Gauss-Legendre orders by k for I_mn, K_mn, one-loop tables,
+ *       6 x {k_below, n_outer, n_inner, n_thin}   the same for ImnOneLoop}.
+ *      A band applies to k < k_below (first match); at or above the last finite k_below the LAST band applies
+ *      (unused bands repeat the last one with k_below = 1e30).
  *      Replaces the reference's `epsrel` constructor argument (Imn.i:8, Jmn.i:8, Kmn.i:8): accuracy is set
- *      by the fixed rule.  Every `cfg40` argument below may be NULL (defaults). */
-int prsd_quad_config_default(double* cfg40);
+ *      by the fixed rule.  Every `cfg56` argument below may be NULL (defaults). */
+int prsd_quad_config_default(double* cfg56);
 
 /* ---- linear spectra: replaces Cosmology + LinearPS (LinearPS.i:5-14, LinearPS.cpp:11-15).
  *   k, T   [ncosmo][nspl]  discrete transfer function (Cosmology.GetDiscreteK/Tk)
@@ -72,7 +73,7 @@ int prsd_spectra_oneloop_eval(prsd_spectra* sp, int which, int full, int nq, con
 
 /* OneLoopPdd/Pdv/Pvv/P22Bar(P_L) constructors: compute the four 1000-point one-loop tables of every
  * cosmology of the batch (OneLoopPS.cpp:56-185), install them in `sp`; out (may be NULL) [ncosmo][4][1000] */
-int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg40, double* out);
+int prsd_oneloop_tables(prsd_spectra* sp, const double* cfg56, double* out);
 /* OneLoopPS(P_L, epsrel, oneloop_power): install ONE table, host [ncosmo][1000] */
 int prsd_spectra_set_oneloop_one(prsd_spectra* sp, int which, const double* table);
 int prsd_spectra_get_oneloop(prsd_spectra* sp, double* out /*[ncosmo][4][1000]*/);
@@ -83,18 +84,18 @@ int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, con
 
 /* ---- one-off evaluations with the call shapes of the pygcl drivers ------------------- */
 /* Imn(P_L)(k, m, n)  [Imn.i:8-14, Imn.cpp:142-189] */
-int prsd_eval_imn(prsd_spectra* sp, int m, int n, int nk, const double* k, const double* cfg40,
+int prsd_eval_imn(prsd_spectra* sp, int m, int n, int nk, const double* k, const double* cfg56,
                   double* out /*[ncosmo][nk]*/);
 /* Kmn(P_L)(k, m, n, tidal, part)  [Kmn.i:8-14, Kmn.cpp:109-184] */
 int prsd_eval_kmn(prsd_spectra* sp, int m, int n, int tidal, int part, int nk, const double* k,
-                  const double* cfg40, double* out);
+                  const double* cfg56, double* out);
 /* Jmn(P_L)(k, m, n)  [Jmn.i:8-14, Jmn.cpp:96-139] */
 int prsd_eval_jmn(prsd_spectra* sp, int m, int n, int nk, const double* k, double* out);
 /* ImnOneLoop(P1[,P2]).EvaluateLinear/Cross/OneLoop(k, m, n)  [ImnOneLoop.i:8-23,
  * ImnOneLoop.cpp:96-216]; p1, p2: 0 Pdd, 1 Pdv, 2 Pvv (p2 < 0: single-spectrum ctor);
  * which: 0 linear, 1 cross, 2 one-loop */
 int prsd_eval_imn_oneloop(prsd_spectra* sp, int p1, int p2, int which, int m, int n, int nk,
-                          const double* k, const double* cfg40, double* out);
+                          const double* k, const double* cfg56, double* out);
 /* PowerSpectrum::VelocityDispersion(), VelocityDispersion(k, factor), X_Zel, Y_Zel, Q3_Zel,
  * Sigma(R), sigma3_squared  [PowerSpectrum.i:5-45, PowerSpectrum.cpp:28-161]
  * what: 0 sigma_v^2 (n = 1, x ignored), 1 sigma_v^2(k; factor), 2 X_Zel(r), 3 Y_Zel(r), 4 Q3_Zel(k),
@@ -106,7 +107,7 @@ int prsd_eval_kurtosis(prsd_spectra* sp, double* out /*[ncosmo]*/);
 
 /* ---- the batched PT stage: everything rsd/pt_integrals.py:42-450 tabulates ------------ */
 /* flags: bit 0 = ImnOneLoop integrals, bit 1 = Zel'dovich X(r), Y(r) */
-int prsd_plan_create(prsd_ctx* ctx, int nk, const double* k_interp, const double* cfg40, int flags,
+int prsd_plan_create(prsd_ctx* ctx, int nk, const double* k_interp, const double* cfg56, int flags,
                      prsd_plan** out);
 int prsd_plan_destroy(prsd_plan* plan);
 /* info[8] = {total 2-D nodes, device bytes, build seconds, nk, n_knots, nodes(one-loop op),
@@ -263,6 +264,27 @@ int prsd_ctx_profile_read(prsd_ctx* ctx, double* ms8, long long* count8);
 int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops);
 /* rebuild the linear spectra of a batch from DEVICE-resident k, T [ncosmo][nspl], pars [ncosmo][8] */
 int prsd_spectra_reload_device(prsd_spectra* sp, const double* d_k, const double* d_T, const double* d_pars);
+
+/* ---- streaming (asynchronous) path -----------------------------------------------------
+ * The reference evaluates one model per process and blocks; a batch pipeline wants step i + 1 enqueued while the
+ * device still runs step i and while P(k, mu) of step i crosses PCIe.  These entry points enqueue on the context's
+ * stream and return without waiting.  Contract: every host buffer they are given (k, T, pars, par, stoch, cmap, k,
+ * mu, out) is PAGE-LOCKED (prsd_host_alloc, cudaHostAlloc, torch pin_memory) and stays untouched until
+ * prsd_galaxy_wait / prsd_galaxy_wait_copy / prsd_ctx_sync says the stream has passed it -- a pageable buffer is
+ * still correct but makes the call wait for the stream.  One step of the pipeline is
+ *     prsd_spectra_reload(sp, k, T, pars);  prsd_plan_run_async(plan, sp, &res);
+ *     prsd_galaxy_power_async(g, sp, res, ..., out_i, &ticket_i);
+ * and out_i is complete after prsd_galaxy_wait_copy(g, ticket_i); its copy to the host runs on a second stream
+ * under the PT kernels of step i + 1.  Same results as the blocking calls, bit for bit. */
+int prsd_spectra_reload(prsd_spectra* sp, const double* k, const double* T, const double* pars);   /* shapes of prsd_spectra_create */
+int prsd_plan_run_async(prsd_plan* plan, prsd_spectra* sp, prsd_result** res);
+int prsd_galaxy_power_async(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
+                            const double* par, const double* stoch, int npts, const double* k, const double* mu,
+                            double* out, long long* ticket /* may be NULL */);
+int prsd_galaxy_wait(prsd_galaxy* g);                        /* everything enqueued so far is done and on the host */
+int prsd_galaxy_wait_copy(prsd_galaxy* g, long long ticket); /* the P(k, mu) of that call is on the host */
+int prsd_host_alloc(size_t bytes, void** out);               /* page-locked host memory */
+int prsd_host_free(void* p);
 
 #ifdef __cplusplus
 }

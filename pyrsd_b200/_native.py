@@ -63,6 +63,13 @@ def lib():
         'prsd_plan_run': (i, [vp, vp, pvp]),
         'prsd_result_destroy': (i, [vp]),
         'prsd_result_get': (i, [vp, i, _dp, ll]),
+        'prsd_plan_run_async': (i, [vp, vp, pvp]),
+        'prsd_spectra_reload': (i, [vp, vp, vp, vp]),
+        'prsd_galaxy_power_async': (i, [vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, C.POINTER(ll)]),
+        'prsd_galaxy_wait': (i, [vp]),
+        'prsd_galaxy_wait_copy': (i, [vp, ll]),
+        'prsd_host_alloc': (i, [C.c_size_t, pvp]),
+        'prsd_host_free': (i, [vp]),
     }
     L.prsd_last_error.restype = C.c_char_p
     L.prsd_last_error.argtypes = []
@@ -87,13 +94,39 @@ def as_f64(x):
 
 
 def cfg_ptr(cfg):
-    """cfg: None or array of 40 doubles (include/pyrsd_b200.h) -> (keepalive, void*)"""
+    """cfg: None or array of 56 doubles (include/pyrsd_b200.h) -> (keepalive, void*)"""
     if cfg is None:
         return None, None
     a = as_f64(cfg)
-    if a.size != 40:
-        raise ValueError("quadrature configuration must hold 40 numbers (see prsd_quad_config_default)")
+    if a.size != 56:
+        raise ValueError("quadrature configuration must hold 56 numbers (see prsd_quad_config_default)")
     return a, a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray(object):
+    """page-locked host memory (prsd_host_alloc) viewed as a NumPy float64 / int32 array; freed with the object"""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        dt = np.dtype(dtype)
+        nbytes = max(int(np.prod(self.shape))*dt.itemsize, 8)
+        p = C.c_void_p()
+        check(lib().prsd_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p
+        buf = (C.c_char*nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if self.ptr is not None and _lib is not None:
+            self.array = None
+            _lib.prsd_host_free(self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def knot_grid():
@@ -105,7 +138,7 @@ def knot_grid():
 
 
 def quad_config_default():
-    c = np.empty(40)
+    c = np.empty(56)
     check(lib().prsd_quad_config_default(c))
     return c
 

@@ -55,28 +55,36 @@ static int guarded(F&& f)
 // restores the caller's device on exit.
 struct DeviceGuard {
     int prev = -1, want = -1;
-    explicit DeviceGuard(int dev) : want(dev)
+    cudaStream_t prev_stream = nullptr;
+    explicit DeviceGuard(const Context* c)
     {
-        if (dev < 0) return;
+        if (!c) return;
+        want = c->device;
         if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
-        if (prev != dev) PRSD_CUDA(cudaSetDevice(dev));
+        if (prev != want) PRSD_CUDA(cudaSetDevice(want));
+        prev_stream = pool_set_stream(c->stream);       // temporaries of this call are stream-ordered on the context's stream
     }
-    ~DeviceGuard() { if (want >= 0 && prev >= 0 && prev != want) cudaSetDevice(prev); }
+    ~DeviceGuard()
+    {
+        if (want < 0) return;
+        pool_set_stream(prev_stream);
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
 };
 
 template <typename F>
-static int guarded(int device, F&& f)
+static int guarded(const Context* c, F&& f)
 {
-    return guarded([&] { DeviceGuard dg(device); f(); });
+    return guarded([&] { DeviceGuard dg(c); f(); });
 }
 
-static int dev_of(const prsd_ctx* h) { return h ? h->c.device : -1; }
-static int dev_of(const prsd_spectra* h) { return (h && h->s.ctx) ? h->s.ctx->device : -1; }
-static int dev_of(const prsd_plan* h) { return (h && h->p.ctx) ? h->p.ctx->device : -1; }
-static int dev_of(const prsd_result* h) { return (h && h->ctx) ? h->ctx->device : -1; }
-static int dev_of(const prsd_galaxy* h) { return (h && h->g.ctx) ? h->g.ctx->device : -1; }
-static int dev_of(const prsd_gridop* h) { return (h && h->op.ctx) ? h->op.ctx->device : -1; }
-static int dev_of(const prsd_window* h) { return (h && h->op.ctx) ? h->op.ctx->device : -1; }
+static const Context* dev_of(const prsd_ctx* h) { return h ? &h->c : nullptr; }
+static const Context* dev_of(const prsd_spectra* h) { return h ? h->s.ctx : nullptr; }
+static const Context* dev_of(const prsd_plan* h) { return h ? h->p.ctx : nullptr; }
+static const Context* dev_of(const prsd_result* h) { return h ? h->ctx : nullptr; }
+static const Context* dev_of(const prsd_galaxy* h) { return h ? h->g.ctx : nullptr; }
+static const Context* dev_of(const prsd_gridop* h) { return h ? h->op.ctx : nullptr; }
+static const Context* dev_of(const prsd_window* h) { return h ? h->op.ctx : nullptr; }
 
 static QuadConfig cfg_from(const double* c)
 {
@@ -84,12 +92,13 @@ static QuadConfig cfg_from(const double* c)
     if (c) {
         q.qmin = c[0]; q.ln_far = c[1]; q.ln_mid = c[2]; q.bao_lo = c[3]; q.bao_hi = c[4]; q.bao_dq = c[5];
         q.ln_inner = c[6]; q.ln_thin = c[7];
-        for (int i = 0; i < 4; i++) {
+        const int NT = QuadConfig::NTIER;
+        for (int i = 0; i < NT; i++) {
             q.tier[i] = {c[8 + 4*i], (int)c[9 + 4*i], (int)c[10 + 4*i], (int)c[11 + 4*i]};
-            q.ml_tier[i] = {c[24 + 4*i], (int)c[25 + 4*i], (int)c[26 + 4*i], (int)c[27 + 4*i]};
+            q.ml_tier[i] = {c[8 + 4*NT + 4*i], (int)c[9 + 4*NT + 4*i], (int)c[10 + 4*NT + 4*i], (int)c[11 + 4*NT + 4*i]};
         }
         PRSD_REQUIRE(q.qmin >= 1e-8 && q.qmin < 1e-5, "quadrature config: qmin = %g outside [1e-8, 1e-5)", q.qmin);
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < QuadConfig::NTIER; i++)
             for (int n : {q.tier[i].n_outer, q.tier[i].n_inner, q.tier[i].n_thin, q.ml_tier[i].n_outer, q.ml_tier[i].n_inner, q.ml_tier[i].n_thin})
                 PRSD_REQUIRE(n >= 2 && n <= 64, "quadrature config: bad point count %d", n);
         PRSD_REQUIRE(q.ln_far > 0 && q.ln_mid > 0 && q.bao_dq > 0 && q.ln_inner > 0 && q.ln_thin >= 0, "quadrature config: widths must be positive");
@@ -279,9 +288,11 @@ int prsd_quad_config_default(double* c9)
         double* c = c9;
         c[0] = q.qmin; c[1] = q.ln_far; c[2] = q.ln_mid; c[3] = q.bao_lo; c[4] = q.bao_hi; c[5] = q.bao_dq;
         c[6] = q.ln_inner; c[7] = q.ln_thin;
-        for (int i = 0; i < 4; i++) {
+        const int NT = QuadConfig::NTIER;
+        for (int i = 0; i < NT; i++) {
             c[8 + 4*i] = q.tier[i].k_below; c[9 + 4*i] = q.tier[i].n_outer; c[10 + 4*i] = q.tier[i].n_inner; c[11 + 4*i] = q.tier[i].n_thin;
-            c[24 + 4*i] = q.ml_tier[i].k_below; c[25 + 4*i] = q.ml_tier[i].n_outer; c[26 + 4*i] = q.ml_tier[i].n_inner; c[27 + 4*i] = q.ml_tier[i].n_thin;
+            const int o = 8 + 4*NT + 4*i;
+            c[o] = q.ml_tier[i].k_below; c[o + 1] = q.ml_tier[i].n_outer; c[o + 2] = q.ml_tier[i].n_inner; c[o + 3] = q.ml_tier[i].n_thin;
         }
     });
 }
@@ -486,15 +497,27 @@ int prsd_plan_info(prsd_plan* plan, double* info)
         info[7] = p.op_ml.geo ? (double)p.op_ml.geo->n_nodes : 0.0;
     });
 }
+static void plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res, bool sync);
+
+int prsd_plan_run_async(prsd_plan* plan, prsd_spectra* sp, prsd_result** res)
+{
+    return guarded(dev_of(plan), [&] { plan_run(plan, sp, res, false); });
+}
+
 int prsd_plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res)
 {
-    return guarded(dev_of(plan), [&] {
+    return guarded(dev_of(plan), [&] { plan_run(plan, sp, res, true); });
+}
+
+static void plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res, bool sync)
+{
+    {
         PRSD_REQUIRE(plan && sp && res, "null argument");
         PRSD_REQUIRE(plan->p.ctx == sp->s.ctx, "prsd_plan_run: the plan and the spectra batch belong to different contexts");
         if (!*res) { *res = new prsd_result(); (*res)->ctx = plan->p.ctx; }
         PRSD_REQUIRE((*res)->ctx == plan->p.ctx, "prsd_plan_run: the result belongs to another context");
-        plan->p.run(sp->s, (*res)->r);
-    });
+        plan->p.run(sp->s, (*res)->r, sync);
+    }
 }
 int prsd_result_destroy(prsd_result* res) { return guarded(dev_of(res), [&] { delete res; }); }
 int prsd_result_get(prsd_result* res, int what, double* out, long long n_expected)
@@ -712,6 +735,31 @@ int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
         g->dout.ensure((size_t)nw*npts);
         g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p, out);
     });
+}
+
+/* asynchronous variants: see include/pyrsd_b200.h ("streaming") */
+int prsd_galaxy_power_async(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
+                            const double* stoch, int npts, const double* k, const double* mu, double* out, long long* ticket)
+{
+    return guarded(dev_of(g), [&] {
+        PRSD_REQUIRE(g && sp && res && par && stoch && k && mu && out, "null argument");
+        Context& c = *g->g.ctx;
+        g->dk.upload(k, npts, c.stream);
+        g->dmu.upload(mu, npts, c.stream);
+        if (g->dout.n < (size_t)nw*npts) { g->g.wait(); g->dout.ensure((size_t)nw*npts); }   // a copy may still read the old block
+        g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p, out, false);
+        if (ticket) *ticket = g->g.last_ticket();
+    });
+}
+
+int prsd_galaxy_wait(prsd_galaxy* g)
+{
+    return guarded(dev_of(g), [&] { PRSD_REQUIRE(g, "null argument"); g->g.wait(); });
+}
+
+int prsd_galaxy_wait_copy(prsd_galaxy* g, long long ticket)
+{
+    return guarded(dev_of(g), [&] { PRSD_REQUIRE(g, "null argument"); g->g.wait_copy(ticket); });
 }
 
 int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap, const double* par,
@@ -991,6 +1039,25 @@ int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops)
         PRSD_REQUIRE(ctx && tflops && (mode == 0 || mode == 1), "bad argument");
         *tflops = fp64_peak_tflops(ctx->c, mode);
     });
+}
+
+int prsd_spectra_reload(prsd_spectra* sp, const double* k, const double* T, const double* pars)
+{
+    return guarded(dev_of(sp), [&] { PRSD_REQUIRE(sp && k && T && pars, "null argument"); sp->s.reload_host(k, T, pars); });
+}
+
+/* page-locked host memory for the streaming entry points (callers without their own pinned allocator) */
+int prsd_host_alloc(size_t bytes, void** out)
+{
+    return guarded([&] {
+        PRSD_REQUIRE(out && bytes > 0, "bad argument");
+        PRSD_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    });
+}
+
+int prsd_host_free(void* p)
+{
+    return guarded([&] { if (p) PRSD_CUDA(cudaFreeHost(p)); });
 }
 
 int prsd_spectra_reload_device(prsd_spectra* sp, const double* d_k, const double* d_T, const double* d_pars)

@@ -53,9 +53,10 @@ inline std::string strprintf(const char* fmt, ...)
     } while (0)
 
 // Device memory comes from a small caching allocator (context.cu): cudaMalloc / cudaFree cost 0.1-1 ms each and
-// cudaFree synchronises the device, which would serialise every call that owns temporaries.  A freed block
-// becomes reusable only after the next cudaDeviceSynchronize() issued by the allocator itself, so work still in
-// flight on any stream can never see its memory handed to someone else.
+// cudaFree synchronises the device, which would serialise every call that owns temporaries.  The allocator is
+// stream-ordered: a block freed under a context is reusable at once for work on the same context's stream (safe
+// by stream order), and only after an allocator-issued device synchronisation by anyone else.
+cudaStream_t pool_set_stream(cudaStream_t s) noexcept;     // allocation stream of the calling thread; returns the previous one
 void* pool_alloc(size_t bytes);
 void  pool_free(void* p) noexcept;
 void  pool_trim(int device = -1) noexcept;   // give the cached blocks of one device (or all) back to the driver

@@ -8,20 +8,42 @@
 namespace prsd {
 
 // ------------------------------------------------------------------ caching allocator
+// Stream-ordered: a block remembers the stream of the context it was allocated under (the C-ABI entry points set
+// it for the calling thread, StreamScope).  Everything a context does runs on that one stream, so a block freed
+// by the host while kernels that use it are still queued can be handed out again at once for work on the SAME
+// stream -- stream order makes the reuse safe, and no host-side synchronisation is needed (the per-step path
+// of an asynchronous pipeline never blocks in the allocator).  Blocks allocated outside any context, or wanted
+// on a different stream than they were used on, go through the conservative path: reusable only after a
+// cudaDeviceSynchronize() issued by the allocator itself.
 namespace {
-struct Block { size_t bytes; int device; };
+struct Block { size_t bytes; int device; cudaStream_t stream; };
+struct Key {
+    int device; cudaStream_t stream; size_t bytes;
+    bool operator<(const Key& o) const
+    {
+        if (device != o.device) return device < o.device;
+        if (stream != o.stream) return stream < o.stream;
+        return bytes < o.bytes;
+    }
+};
 struct Pool {
     std::mutex mu;
     std::unordered_map<void*, Block> live;                     // every block handed out
-    std::multimap<std::pair<int, size_t>, void*> ready;        // (device, bytes) -> reusable blocks
-    std::vector<std::pair<void*, Block>> pending;              // freed, but work using them may be in flight
+    std::multimap<Key, void*> ready;                           // reusable blocks (stream == nullptr: by anyone)
+    std::vector<std::pair<void*, Block>> pending;              // freed, untagged: work using them may be in flight
     size_t cached_bytes = 0;                                   // bytes held in `ready` + `pending`
-    bool closed = false;                                       // set at static destruction: leak instead of touching CUDA
-    ~Pool() { closed = true; }
 };
 Pool& pool() { static Pool* p = new Pool; return *p; }         // never destroyed: static DevBufs outlive main()
 
 size_t round_up(size_t b) { return (b + 511) & ~size_t(511); }
+thread_local cudaStream_t tl_stream = nullptr;
+}
+
+cudaStream_t pool_set_stream(cudaStream_t s) noexcept
+{
+    cudaStream_t prev = tl_stream;
+    tl_stream = s;
+    return prev;
 }
 
 void* pool_alloc(size_t bytes)
@@ -30,39 +52,44 @@ void* pool_alloc(size_t bytes)
     int dev = 0;
     PRSD_CUDA(cudaGetDevice(&dev));
     const size_t want = round_up(bytes);
+    const cudaStream_t st = tl_stream;
     std::lock_guard<std::mutex> lk(P.mu);
-    auto take = [&]() -> void* {
-        auto it = P.ready.lower_bound({dev, want});
-        if (it != P.ready.end() && it->first.first == dev && it->first.second <= want + want/4) {
+    auto take = [&](cudaStream_t from) -> void* {
+        auto it = P.ready.lower_bound({dev, from, want});
+        if (it != P.ready.end() && it->first.device == dev && it->first.stream == from && it->first.bytes <= want + want/4) {
             void* p = it->second;
-            P.live[p] = {it->first.second, dev};
-            P.cached_bytes -= it->first.second;
+            P.live[p] = {it->first.bytes, dev, st};
+            P.cached_bytes -= it->first.bytes;
             P.ready.erase(it);
             return p;
         }
         return nullptr;
     };
-    if (void* p = take()) return p;
+    if (st) if (void* p = take(st)) return p;          // same stream: safe by stream order
+    if (void* p = take(nullptr)) return p;             // synchronised blocks: safe for anyone
     if (!P.pending.empty()) {
-        // blocks freed since the last synchronisation become reusable now
-        PRSD_CUDA(cudaDeviceSynchronize());           // the CURRENT device: only its blocks move
-        std::vector<std::pair<void*, Block>> keep;
-        for (auto& e : P.pending) {
-            if (e.second.device == dev) P.ready.insert({{dev, e.second.bytes}, e.first});
-            else keep.push_back(e);
+        // untagged blocks freed since the last synchronisation become reusable by anyone now
+        bool mine = false;
+        for (auto& e : P.pending) mine = mine || e.second.device == dev;
+        if (mine) {
+            PRSD_CUDA(cudaDeviceSynchronize());           // the CURRENT device: only its blocks move
+            std::vector<std::pair<void*, Block>> keep;
+            for (auto& e : P.pending) {
+                if (e.second.device == dev) P.ready.insert({{dev, nullptr, e.second.bytes}, e.first});
+                else keep.push_back(e);
+            }
+            P.pending.swap(keep);
+            if (void* p = take(nullptr)) return p;
         }
-        P.pending.swap(keep);
-        if (void* p = take()) return p;
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
-        // out of memory: return THIS device's cache (ready and, after a synchronisation, pending blocks) to the
-        // driver and retry once
+        // out of memory: synchronise, return THIS device's cache to the driver and retry once
         cudaGetLastError();
         cudaDeviceSynchronize();
         for (auto it = P.ready.begin(); it != P.ready.end();) {
-            if (it->first.first == dev) { cudaFree(it->second); P.cached_bytes -= it->first.second; it = P.ready.erase(it); }
+            if (it->first.device == dev) { cudaFree(it->second); P.cached_bytes -= it->first.bytes; it = P.ready.erase(it); }
             else ++it;
         }
         std::vector<std::pair<void*, Block>> keep;
@@ -75,7 +102,7 @@ void* pool_alloc(size_t bytes)
     }
     if (e != cudaSuccess)
         throw Error(ERR_CUDA, strprintf("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)));
-    P.live[p] = {want, dev};
+    P.live[p] = {want, dev, st};
     return p;
 }
 
@@ -85,15 +112,17 @@ void pool_free(void* p) noexcept
     std::lock_guard<std::mutex> lk(P.mu);
     auto it = P.live.find(p);
     if (it == P.live.end()) return;
-    P.pending.push_back({p, it->second});
-    P.cached_bytes += it->second.bytes;
+    const Block b = it->second;
     P.live.erase(it);
+    P.cached_bytes += b.bytes;
+    if (b.stream) P.ready.insert({{b.device, b.stream, b.bytes}, p});
+    else P.pending.push_back({p, b});
     // bound the cache (varying batch sizes would otherwise accumulate blocks of every size ever used)
     static const size_t CACHE_LIMIT = size_t(24) << 30;
     if (P.cached_bytes > CACHE_LIMIT) {
         int prev = -1;
         cudaGetDevice(&prev);
-        for (auto& r : P.ready) { cudaSetDevice(r.first.first); cudaFree(r.second); P.cached_bytes -= r.first.second; }
+        for (auto& r : P.ready) { cudaSetDevice(r.first.device); cudaFree(r.second); P.cached_bytes -= r.first.bytes; }   // cudaFree synchronises
         P.ready.clear();
         if (prev >= 0) cudaSetDevice(prev);
     }
@@ -117,10 +146,10 @@ void pool_trim(int device) noexcept
     }
     P.pending.swap(keep);
     for (auto it = P.ready.begin(); it != P.ready.end();) {
-        if (device < 0 || it->first.first == device) {
-            cudaSetDevice(it->first.first);
+        if (device < 0 || it->first.device == device) {
+            cudaSetDevice(it->first.device);
             cudaFree(it->second);
-            P.cached_bytes -= it->first.second;
+            P.cached_bytes -= it->first.bytes;
             it = P.ready.erase(it);
         } else ++it;
     }

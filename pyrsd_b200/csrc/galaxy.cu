@@ -602,6 +602,17 @@ __global__ void k_plin_model(int nspl, const PlinParams* __restrict__ params, co
     out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
 }
 
+// normalisation ratios of every walker: (sigma8_z / sigma8)^2 and the same at sigma8_z / D (Jennings fits)
+__global__ void k_gal_ratios(int nw, const double* __restrict__ par, double* __restrict__ r1, double* __restrict__ r2)
+{
+    const int w = blockIdx.x*blockDim.x + threadIdx.x;
+    if (w >= nw) return;
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double n1 = p[W_S8Z]/p[W_S80], n2 = n1/p[W_D];
+    r1[w] = n1*n1;
+    r2[w] = n2*n2;
+}
+
 __global__ void k_scale_rows(int n, const double* __restrict__ in, const double* __restrict__ fac, const int* __restrict__ cmap,
                              double* __restrict__ out)
 {
@@ -723,12 +734,14 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
 
 GalaxyModel::~GalaxyModel()
 {
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    for (cudaEvent_t e : copy_done) if (e) cudaEventDestroy(e);
     if (copy_event) cudaEventDestroy(copy_event);
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }
 
 void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
-                        int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out)
+                        int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out, bool sync)
 {
     Context& c = *ctx;
     cudaStream_t s = c.stream;
@@ -742,23 +755,34 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
                  pt.ncosmo, (unsigned long long)pt.src_uid, (unsigned long long)pt.src_gen, sp.ncosmo,
                  (unsigned long long)sp.uid, (unsigned long long)sp.lin_gen);
     const int nc = sp.ncosmo;
-    std::vector<int> hmap(nw);
-    std::vector<double> r1(nw), r2(nw);
     for (int w = 0; w < nw; w++) {
-        hmap[w] = cmap ? cmap[w] : w;
-        PRSD_REQUIRE(hmap[w] >= 0 && hmap[w] < nc, "walker %d maps to cosmology %d (batch has %d)", w, hmap[w], nc);
+        const int cm = cmap ? cmap[w] : w;
+        PRSD_REQUIRE(cm >= 0 && cm < nc, "walker %d maps to cosmology %d (batch has %d)", w, cm, nc);
         const double* p = par + (size_t)w*GAL_NPAR;
         PRSD_REQUIRE(p[W_S8Z] > 0 && p[W_S80] > 0 && p[W_D] > 0, "walker %d: sigma8_z, sigma8 and D must be positive", w);
         PRSD_REQUIRE(p[W_APAR] > 0 && p[W_APERP] > 0, "walker %d: AP parameters must be positive", w);
-        const double n1 = p[W_S8Z]/p[W_S80], n2 = n1/p[W_D];
-        r1[w] = n1*n1;
-        r2[w] = n2*n2;
     }
-    d_cmap.upload(hmap, s);
+    // No pageable staging on the per-call path (a copy from pageable memory waits for the stream first): the identity
+    // map is uploaded once, a caller's map / parameters go up straight from the caller's (ideally pinned) memory, and
+    // the two normalisation ratios are formed on the device.
+    if (cmap) d_cmap.upload(cmap, nw, s);
+    else if (ident_n < nw) {
+        std::vector<int> id(std::max(nw, 1024));
+        for (size_t i = 0; i < id.size(); i++) id[i] = (int)i;
+        d_ident.upload(id, s);
+        PRSD_CUDA(cudaStreamSynchronize(s));      // the host vector goes out of scope (once per size)
+        ident_n = (int)id.size();
+    }
+    const int* d_map = cmap ? d_cmap.p : d_ident.p;
     d_par.upload(par, (size_t)nw*GAL_NPAR, s);
     d_stoch.upload(stoch, (size_t)nw*GAL_NPAIR*GAL_NSTOCH, s);
-    ratio1.upload(r1, s);
-    ratio2.upload(r2, s);
+    ratio1.ensure(nw);
+    ratio2.ensure(nw);
+    k_gal_ratios<<<(nw + 127)/128, 128, 0, s>>>(nw, d_par.p, ratio1.p, ratio2.p);
+    c.launches++;
+    // a previous call's copy to the host may still be reading d_out: its end is ordered before this call's writes
+    // (in stream order this wait sits AFTER the PT stage of the current batch, which therefore overlaps that copy)
+    if (copy_ticket > 0 && copy_done[(copy_ticket - 1) & 1]) PRSD_CUDA(cudaStreamWaitEvent(s, copy_done[(copy_ticket - 1) & 1], 0));
 
     // ---- per-cosmology: every PT table splined on k_interp and read on the model grid (rsd/_cache.py:344-389)
     const int nk = nk_interp;
@@ -797,7 +821,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
 
     // ---- everything below is per walker: walkers [w0, w0 + n) of the batch
     auto run_walkers = [&](int w0, int n) {
-        const int* cm = d_cmap.p + w0;
+        const int* cm = d_map + w0;
         const double* pr = d_par.p + (size_t)w0*GAL_NPAR;
         const double* st = d_stoch.p + (size_t)w0*GAL_NPAIR*GAL_NSTOCH;
         double* pw1 = plin_w.p + (size_t)w0*nkm;
@@ -849,8 +873,26 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
                                       cudaMemcpyDeviceToHost, copy_stream));
         }
     }
-    c.sync();
-    if (h_out && npts > 0) PRSD_CUDA(cudaStreamSynchronize(copy_stream));
+    if (h_out && npts > 0) {
+        cudaEvent_t& done = copy_done[copy_ticket & 1];
+        if (!done) PRSD_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        PRSD_CUDA(cudaEventRecord(done, copy_stream));
+        copy_ticket++;
+    }
+    if (sync) wait();
+}
+
+void GalaxyModel::wait()
+{
+    ctx->sync();
+    if (copy_stream) PRSD_CUDA(cudaStreamSynchronize(copy_stream));
+}
+
+void GalaxyModel::wait_copy(long long ticket)
+{
+    PRSD_REQUIRE(ticket >= 1 && ticket <= copy_ticket, "GalaxyModel::wait_copy: unknown ticket %lld (last %lld)", ticket, copy_ticket);
+    if (ticket + 2 <= copy_ticket) return;          // two later copies have been issued on the same stream since: long done
+    PRSD_CUDA(cudaEventSynchronize(copy_done[(ticket - 1) & 1]));
 }
 
 void GalaxyModel::poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,

@@ -69,6 +69,10 @@ struct GalaxyModel {
     int mom_band = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_event = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};      // end of the device-to-host copies of the last two power() calls
+    long long copy_ticket = 0;                          // number of power() calls with a host destination so far
+    DevBuf<int> d_ident;                                // identity walker -> cosmology map (cmap == NULL)
+    int ident_n = 0;
     GalDev last_G;                      // constants of the last power() call (reused by poles())
     int last_nw = 0;
 
@@ -83,7 +87,13 @@ struct GalaxyModel {
     // h_out (optional, host, ideally pinned): the result is also copied there, chunk by chunk under the kernels of
     // the following walkers
     void power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
-               int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out = nullptr);
+               int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out = nullptr, bool sync = true);
+    // sync = false: the call returns once everything is enqueued -- no host-side wait, par / stoch / cmap and h_out must
+    // be page-locked and stay valid until wait() (or wait_copy of the returned ticket).  The copy to h_out of call
+    // i runs on the copy stream under whatever the context's stream executes next (the PT stage of batch i + 1).
+    void wait();                        // everything enqueued so far has finished, results are in host memory
+    void wait_copy(long long ticket);   // the host copy of the power() call that returned `ticket` has landed
+    long long last_ticket() const { return copy_ticket; }
     // multipoles P_ell(k) of `nw` walkers by Simpson's rule over nmu (odd) mu in [0, 1] -- MultipoleTransfer of
     // rsd/transfers/poles.py:8-69 fused behind the assembly: d_k DEVICE [nk], ells host [nell], d_out DEVICE [nw][nell][nk]
     void poles(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,

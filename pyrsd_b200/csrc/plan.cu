@@ -251,7 +251,7 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
     if (sync) c.sync();
 }
 
-void PTPlan::run(SpectraBatch& sp, PTResult& res)
+void PTPlan::run(SpectraBatch& sp, PTResult& res, bool sync)
 {
     PRSD_REQUIRE(!only_oneloop, "this plan only holds the one-loop stage");
     PRSD_REQUIRE(sp.ctx == ctx, "PTPlan::run: the plan and the spectra batch belong to different contexts");
@@ -302,7 +302,7 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res)
     }
     res.src_uid = sp.uid;
     res.src_gen = sp.lin_gen;
-    c.sync();
+    if (sync) c.sync();
 }
 
 } // namespace prsd

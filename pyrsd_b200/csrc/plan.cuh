@@ -61,7 +61,8 @@ struct PTPlan {
     PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l = false);
     // stage A only: the four one-loop tables (left in sp and in res.oneloop)
     void run_oneloop(SpectraBatch& sp, PTResult& res, bool sync = true);
-    void run(SpectraBatch& sp, PTResult& res);
+    // sync = false: everything is enqueued on the context's stream and the call returns (asynchronous pipeline)
+    void run(SpectraBatch& sp, PTResult& res, bool sync = true);
     size_t device_bytes() const;
     long long nodes_total() const;
 };

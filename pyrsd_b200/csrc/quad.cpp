@@ -133,7 +133,7 @@ void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cf
     // Gauss-Legendre rules by order (a handful of distinct orders over the tiers)
     std::vector<std::vector<double>> glx(65), glw(65);
     auto rule = [&](int n) { if (glx[n].empty()) gauss_legendre(n, glx[n], glw[n]); };
-    for (int i = 0; i < 4; i++) { rule(cfg.tier[i].n_outer); rule(cfg.tier[i].n_inner); rule(cfg.tier[i].n_thin); }
+    for (int i = 0; i < QuadConfig::NTIER; i++) { rule(cfg.tier[i].n_outer); rule(cfg.tier[i].n_inner); rule(cfg.tier[i].n_thin); }
     const std::vector<double> zone_breaks = {1e-5, 10.0, 100.0};
 
     H = HalfNodes();

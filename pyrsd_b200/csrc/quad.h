@@ -44,32 +44,36 @@ struct QuadConfig {
     // assembly reads P_dd / P_dv / P_vv there, so the 1e-5 parity bound holds on the whole grid (round 1 dropped to
     // (8, 6, 5) above k = 0.5 for 5 % of the step and was 2e-4 there).  Above the last finite k_below of a
     // user-supplied configuration the LAST tier applies.
-    QuadTier tier[4]    = {{0.02, 5, 4, 3}, {0.08, 6, 5, 4}, {0.3, 8, 6, 5}, {1e30, 12, 7, 5}};
+    // 0.5 <= k < 1: (16, 7, 5).  The one-loop tables in that band are the integrands that dominate the f32 / f33
+    // cross parts of ImnOneLoop, which change sign near k = 0.5 and 0.86: with (12, 7, 5) the tables are good to
+    // 5e-6 but those integrals are off by 1.4e-4 of |value| at the crossing (dense fixtures, profiles/r02_parity.md).
+    static const int NTIER = 6;
+    QuadTier tier[NTIER]    = {{0.02, 5, 4, 3}, {0.08, 6, 5, 4}, {0.3, 8, 6, 5}, {0.5, 12, 7, 5}, {1.0, 16, 7, 5}, {1e30, 12, 7, 5}};
     // ImnOneLoop (q_max = 10): the one-loop spectra are large at the hard cut and the h02-type kernels cancel to
     // leading order across v, so above k = 0.06 that operator keeps full-order panels everywhere
-    QuadTier ml_tier[4] = {{0.02, 4, 4, 3}, {0.06, 6, 5, 4}, {0.3, 10, 7, 7}, {1e30, 10, 8, 8}};
+    QuadTier ml_tier[NTIER] = {{0.02, 4, 4, 3}, {0.06, 6, 5, 4}, {0.2, 10, 7, 7}, {1e30, 10, 8, 8}, {1e30, 10, 8, 8}, {1e30, 10, 8, 8}};
 
     const QuadTier& tier_of(double k) const
     {
-        for (int i = 0; i < 4; i++) if (k < tier[i].k_below) return tier[i];
-        return tier[3];
+        for (int i = 0; i < NTIER; i++) if (k < tier[i].k_below) return tier[i];
+        return tier[NTIER - 1];
     }
     QuadConfig ml_variant() const
     {
         QuadConfig q = *this;
-        for (int i = 0; i < 4; i++) q.tier[i] = ml_tier[i];
+        for (int i = 0; i < NTIER; i++) q.tier[i] = ml_tier[i];
         return q;
     }
     void set_uniform(int n_outer, int n_inner, int n_thin)
     {
-        for (int i = 0; i < 4; i++) { tier[i].n_outer = ml_tier[i].n_outer = n_outer; tier[i].n_inner = ml_tier[i].n_inner = n_inner;
+        for (int i = 0; i < NTIER; i++) { tier[i].n_outer = ml_tier[i].n_outer = n_outer; tier[i].n_inner = ml_tier[i].n_inner = n_inner;
                                       tier[i].n_thin = ml_tier[i].n_thin = n_thin; }
     }
     bool operator==(const QuadConfig& o) const
     {
         bool same = qmin == o.qmin && ln_far == o.ln_far && ln_mid == o.ln_mid && mid_lo == o.mid_lo && mid_hi == o.mid_hi &&
                     bao_lo == o.bao_lo && bao_hi == o.bao_hi && bao_dq == o.bao_dq && ln_inner == o.ln_inner && ln_thin == o.ln_thin;
-        for (int i = 0; i < 4 && same; i++)
+        for (int i = 0; i < NTIER && same; i++)
             for (const QuadTier* p : {tier, ml_tier}) {
                 const QuadTier* q = (p == tier) ? o.tier : o.ml_tier;
                 same = same && p[i].k_below == q[i].k_below && p[i].n_outer == q[i].n_outer && p[i].n_inner == q[i].n_inner && p[i].n_thin == q[i].n_thin;

@@ -380,6 +380,15 @@ void SpectraBatch::reload_device(const double* d_k, const double* d_T, const dou
     lin_gen++;
 }
 
+void SpectraBatch::reload_host(const double* k, const double* T, const double* pars)
+{
+    cudaStream_t s = ctx->stream;
+    in_k.upload(k, (size_t)ncosmo*nspl, s);
+    in_T.upload(T, (size_t)ncosmo*nspl, s);
+    in_pars.upload(pars, (size_t)ncosmo*8, s);
+    reload_device(in_k.p, in_T.p, in_pars.p);
+}
+
 void SpectraBatch::rescale_linear(const double* fac_host)
 {
     DevBuf<double> f;

@@ -40,6 +40,11 @@ struct SpectraBatch {
     // rebuild every linear-spectrum table from DEVICE-resident inputs: d_k, d_T [ncosmo][nspl],
     // d_pars [ncosmo][8] (same meaning as the host constructor); asynchronous on the context's stream
     void reload_device(const double* d_k, const double* d_T, const double* d_pars);
+    // the same from HOST inputs (same shapes as the constructor's), asynchronous: the inputs are copied into
+    // persistent device staging and nothing waits for the stream.  For the call to return before the copies have
+    // run the host buffers must be page-locked, and they must stay unchanged until the stream has passed them.
+    void reload_host(const double* k, const double* T, const double* pars);
+    DevBuf<double> in_k, in_T, in_pars;
     int table_index(int cosmo, int kind) const { return cosmo*SP_NKIND + kind; }
     const double* table_ptr(int cosmo, int kind) const { return tables.p + (size_t)table_index(cosmo, kind)*TAB_MPAD; }
     // multiply P_L (spline amplitude and tables) of cosmology c by fac

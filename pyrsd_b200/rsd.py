@@ -110,14 +110,14 @@ class PTEngine(object):
             pars[:, j] = v
         return pygcl._Spectra(self.ctx, k, T, pars)
 
-    def run(self, spectra, result=None):
-        """everything rsd/pt_integrals.py tabulates, for every cosmology of the batch"""
+    def run(self, spectra, result=None, sync=True):
+        """everything rsd/pt_integrals.py tabulates, for every cosmology of the batch (``sync=False``: enqueue only)"""
         # a fresh result unless the caller passes one to be overwritten: a result handed out earlier must not
         # change under its holder when the engine runs another batch
         res = result if result is not None else _new_result()
         cur = res.ptr.value if isinstance(res.ptr, _vp) else res.ptr
         p = _vp(cur)
-        N.check(_L().prsd_plan_run(self.plan.ptr, spectra.ptr, C.byref(p)))
+        N.check((_L().prsd_plan_run if sync else _L().prsd_plan_run_async)(self.plan.ptr, spectra.ptr, C.byref(p)))
         res.ptr = p
         res.ncosmo = spectra.ncosmo
         spectra.have_oneloop = True
@@ -264,6 +264,73 @@ class PTEngine(object):
         out = np.empty((nw, NPAIR, 4, gal.nkm))
         N.check(_L().prsd_galaxy_moments(gal.ptr, nw, out))
         return out
+
+
+class PTStream(object):
+    """Pipelined evaluation of a stream of batches: every PT table rebuilt + P(k, mu) per cosmology, batch after
+    batch, with nothing on the host waiting for the device between ``submit`` calls.
+
+    ``submit`` copies a batch's inputs into page-locked slots and enqueues upload -> PT stage -> galaxy assembly ->
+    copy of P(k, mu) to a page-locked output slot; the copy runs on a second CUDA stream under the PT kernels of the
+    NEXT batch.  ``result(ticket)`` waits for that batch only and returns a view of its output slot, valid until
+    ``depth`` further batches have been submitted.  Results are bit-identical to the blocking
+    ``spectra -> run -> galaxy_power`` sequence (tests/test_gpu_stream.py)."""
+
+    def __init__(self, engine, kmodel, config, ncosmo, k_T_shape, k, mu, depth=2):
+        self.eng, self.depth = engine, int(depth)
+        self.gal = engine.galaxy(kmodel, config)
+        self.nc = int(ncosmo)
+        self.nspl = int(k_T_shape)
+        k, mu = N.as_f64(k), N.as_f64(mu)
+        assert k.shape == mu.shape
+        self.npts = len(k)
+        P = N.PinnedArray
+        self.h_kk, self.h_mm = P(self.npts), P(self.npts)
+        self.h_kk.array[:], self.h_mm.array[:] = k, mu
+        self.slots = [dict(k=P((self.nc, self.nspl)), T=P((self.nc, self.nspl)), pars=P((self.nc, 8)),
+                           wpar=P((self.nc, NPAR)), stoch=P((self.nc, NPAIR, NSTOCH)), out=P((self.nc, self.npts)),
+                           ticket=0) for _ in range(self.depth)]
+        self.sp = None
+        self.res = _new_result()
+        self.n = 0
+
+    def submit(self, k, T, pars, wpar, stoch):
+        """enqueue one batch: k, T [ncosmo][nspl], pars [ncosmo][8] (prsd_spectra_create), wpar [ncosmo][NPAR],
+        stoch [ncosmo][NPAIR][NSTOCH]; returns the batch's ticket"""
+        L = _L()
+        s = self.slots[self.n % self.depth]
+        if s['ticket']:
+            # the slot's previous batch: once its output has landed, its inputs were consumed long ago
+            N.check(L.prsd_galaxy_wait_copy(self.gal.ptr, s['ticket']))
+        for name, a in (('k', k), ('T', T), ('pars', pars), ('wpar', wpar), ('stoch', stoch)):
+            s[name].array[...] = np.asarray(a).reshape(s[name].shape)
+        if self.sp is None:
+            self.sp = pygcl._Spectra(self.eng.ctx, s['k'].array, s['T'].array, s['pars'].array)
+        else:
+            N.check(L.prsd_spectra_reload(self.sp.ptr, s['k'].ptr, s['T'].ptr, s['pars'].ptr))
+        self.eng.run(self.sp, result=self.res, sync=False)
+        t = C.c_longlong()
+        N.check(L.prsd_galaxy_power_async(self.gal.ptr, self.sp.ptr, self.res.ptr, self.nc, None, s['wpar'].ptr, s['stoch'].ptr,
+                                          self.npts, self.h_kk.ptr, self.h_mm.ptr, s['out'].ptr, C.byref(t)))
+        s['ticket'] = t.value
+        self.n += 1
+        return t.value
+
+    def result(self, ticket):
+        """P(k, mu) [ncosmo][npts] of the batch that returned ``ticket`` (a view of page-locked memory)"""
+        for s in self.slots:
+            if s['ticket'] == ticket:
+                N.check(_L().prsd_galaxy_wait_copy(self.gal.ptr, ticket))
+                return s['out'].array
+        raise ValueError("ticket %d is no longer held (depth = %d)" % (ticket, self.depth))
+
+    def drain(self):
+        N.check(_L().prsd_galaxy_wait(self.gal.ptr))
+
+    def bytes_per_step(self):
+        s = self.slots[0]
+        h2d = sum(s[n].array.nbytes for n in ('k', 'T', 'pars', 'wpar', 'stoch')) + self.h_kk.array.nbytes + self.h_mm.array.nbytes
+        return h2d, s['out'].array.nbytes
 
 
 def galaxy_config(max_mu=4, fog_model='modified_lorentzian', use_P00_model=True, use_P01_model=True, use_P11_model=True,

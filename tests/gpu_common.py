@@ -19,15 +19,18 @@ def relerr_floor(mine, ref, floor):
     return np.abs(mine - ref)/np.maximum(np.abs(ref), floor)
 
 
-# synthetic stand-ins for the reference's Gaussian-process fits -- identical to
-# tests/golden/make_galaxy_ref.py (both sides of the galaxy parity test use them)
-def b2_00(b1):
-    return 0.77 - 2.43*b1 + b1**2
+def ml_scale_floor(ref_parts, plin):
+    """scale of one ImnOneLoop integral as the model reads it.  ``ref_parts`` [3][nk] = its linear / cross / one-loop
+    parts on the tabulation grid.  The reference only ever uses norm^2 lin + norm^3 cross + norm^4 oneloop, splined in
+    k (rsd/pt_integrals.py:31-40, ``interpolated_function``), and the f32 / f33 parts change sign between tabulated
+    points (k ~ 0.5, 0.86-0.9) where |value| drops to 1/15 - 1/500 of its neighbours and of the other parts: the
+    floor of the parity metric is therefore max(P_L(k), |part| over the three parts at k_{i-2} .. k_{i+2})."""
+    a = np.max(np.abs(np.asarray(ref_parts)), axis=0)
+    n = len(a)
+    loc = np.array([a[max(i - 2, 0):i + 3].max() for i in range(n)])
+    return np.maximum(loc, plin)
 
 
-def b2_01(b1):
-    return 0.9 - 1.4*b1 + 0.45*b1**2
-
-
-def stochasticity(k, sigma8_z, b1a, b1b):
-    return (sigma8_z/0.8)*(120.*b1a*b1b - 400.)*(1.0 + 0.3*np.log(k/0.1) - 0.05*np.log(k/0.1)**2)
+# synthetic stand-ins for the reference's Gaussian-process fits -- identical to tests/golden/make_galaxy_ref.py
+# (both sides of the galaxy parity test use them); they live with the benchmark's workload generator
+from pyrsd_b200.synthetic import b2_00, b2_01, stochasticity  # noqa: E402,F401

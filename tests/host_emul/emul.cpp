@@ -34,7 +34,7 @@ void emul_set_tier(int i, double k_below, int n_outer, int n_inner, int n_thin)
 
 void emul_set_config_ext(int n_inner_thin, double ln_thin, double ln_inner, double mid_lo, double mid_hi)
 {
-    for (int i = 0; i < 4; i++) g_cfg.tier[i].n_thin = n_inner_thin;
+    for (int i = 0; i < QuadConfig::NTIER; i++) g_cfg.tier[i].n_thin = n_inner_thin;
     g_cfg.ln_thin = ln_thin; g_cfg.ln_inner = ln_inner;
     g_cfg.mid_lo = mid_lo; g_cfg.mid_hi = mid_hi;
 }

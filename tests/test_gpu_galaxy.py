@@ -38,22 +38,55 @@ def make_model(cosmo, engine, z, **kw):
     return rsd.GalaxySpectrum(params=cosmo, z=z, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine, **kw)
 
 
+# k0_low <= k' < 0.0075: the Zel'dovich transform amplifies errors of 1e-9 sigma_v^2 in Y(r > 1e4 Mpc/h) to 1e-4 in
+# P00.  The reference's own adaptive X_Zel / Y_Zel do not converge there even at epsrel = 1e-10 (Y off by 1.5e-4 at
+# r = 3.7e4 against brute-force quadrature, which the library's product integration matches to 1e-13 sigma_v^2;
+# tests/golden/make_galaxy_ref.py ZEL_SOURCE, profiles/r02_parity.md).  So: against the reference fed with ITS OWN
+# state the bound in that band is the reference's noise (2.5e-4), 1e-5 elsewhere; against the reference fed with the
+# converged state ("_pi" cases) it is 1e-5 everywhere.
+ZEL_BAND = (4.5e-3, 8e-3)       # in OBSERVED k: the AP cases map k to k' = k / alpha (3 %), and the model's spline rings one knot below k0_low
+VARIANTS = [(c, '') for c in sorted(CASES)] + [(c, '_pi') for c in sorted(CASES) if c != 'z055_spt']
+
+
+def _record(tag, value):
+    try:
+        import json
+        path = os.path.join(os.path.dirname(HERE), 'gpurun_out', 'r02_parity.json')
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur.setdefault('galaxy', {})[tag] = value
+        json.dump(cur, open(path, 'w'), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/galaxy_ref.npz not generated")
-@pytest.mark.parametrize('case', sorted(CASES))
-def test_power_vs_reference_python(cosmo, engine, case):
+@pytest.mark.parametrize('case,variant', VARIANTS)
+def test_power_vs_reference_python(cosmo, engine, case, variant):
     ref = np.load(REF)
     z, kw, _ = CASES[case]
     model = make_model(cosmo, engine, z, **kw)
     names = [str(n) for n in ref['par_names']]
-    pars = dict(zip(names, ref[case + '_pars']))
+    key = case + variant
+    pars = dict(zip(names, ref[key + '_pars']))
     pars.pop('D')
     model.update(**pars)
-    assert np.allclose(model.k, ref[case + '_modelk'], rtol=1e-14)
-    assert abs(model.sigma_lin/float(ref[case + '_sigma_lin']) - 1) < TOL
-    P = model.power(ref['k'], ref['mu'])
-    assert P.shape == ref[case + '_P'].shape
-    err = np.abs(P/ref[case + '_P'] - 1)
-    assert err.max() < TOL, (case, err.max())
+    assert np.allclose(model.k, ref[key + '_modelk'], rtol=1e-14)
+    assert abs(model.sigma_lin/float(ref[key + '_sigma_lin']) - 1) < TOL
+    # the benchmark's own output grid: every second k of bench.py's 1000 in [1.12e-3, 0.49] x 40 mu
+    k, mu = ref[key + '_k'], ref['mu']
+    assert len(mu) == 40 and k.min() < 1.2e-3 and k.max() > 0.475
+    P = model.power(k, mu)
+    assert P.shape == ref[key + '_P'].shape
+    err = np.abs(P/ref[key + '_P'] - 1)
+    band = (k >= ZEL_BAND[0]) & (k < ZEL_BAND[1]) if (variant == '' and case != 'z055_spt') else np.zeros(len(k), dtype=bool)
+    e_out = err[~band]
+    i, j = np.unravel_index(np.argmax(np.where(band[:, None], 0, err)), err.shape)
+    _record('power/' + key, dict(max_err=float(e_out.max()), at_k=float(k[i]), at_mu=float(mu[j]), grid=list(P.shape),
+                                 max_err_in_reference_noise_band=float(err[band].max()) if band.any() else None))
+    assert e_out.max() < TOL, (key, e_out.max(), k[i], mu[j])
+    if band.any():
+        assert err[band].max() < 2.5e-4, (key, err[band].max())
 
 
 def test_power_properties_at_baseline_grid(cosmo, engine):
@@ -203,3 +236,33 @@ def test_dm_spectra_vs_shipped_model(cosmo, engine, golden):
     low = mk < 3e-3
     assert np.max(np.abs(dm['P00'][low]/dm['P_lin'][low] - 1)) < 2e-2
     assert np.max(np.abs(dm['P01'][low]/(2*m.f*dm['P_lin'][low]) - 1)) < 5e-2
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/galaxy_ref.npz not generated")
+@pytest.mark.parametrize('case,variant', [('z0_default', ''), ('z055_ap', ''), ('z055_spt', ''), ('z0_default', '_pi'), ('z055_ap', '_pi')])
+def test_dm_blocks_vs_reference_python(cosmo, engine, case, variant):
+    """the dark-matter building blocks on the model grid (P_lin, P00, P01, P11[mu4], Pdv, Pvv, Pdd) against the
+    reference's own model objects (power_dm.py:797-884, dm/P00.py .. P11.py), all 200 model k"""
+    ref = np.load(REF)
+    key = case + variant
+    if key + '_dm' not in ref.files:
+        pytest.skip("fixture has no dm blocks")
+    z, kw, _ = CASES[case]
+    model = make_model(cosmo, engine, z, **kw)
+    names = [str(n) for n in ref['par_names']]
+    pars = dict(zip(names, ref[key + '_pars']))
+    pars.pop('D')
+    model.update(**pars)
+    dm = model.dm_spectra()
+    k = model.k
+    band = (k >= ZEL_BAND[0]) & (k < ZEL_BAND[1]) if (variant == '' and case != 'z055_spt') else np.zeros(len(k), dtype=bool)
+    worst = {}
+    for row, name in enumerate(('P_lin', 'P00', 'P01', 'P11_mu4', 'Pdv', 'Pvv', 'Pdd')):
+        r = ref[key + '_dm'][row]
+        err = np.abs(dm[name] - r)/np.maximum(np.abs(r), 1e-3*ref[key + '_dm'][0])
+        i = int(np.argmax(np.where(band, 0, err)))
+        worst[name] = [float(err[i]), float(k[i])]
+        _record('dm/' + key, worst)
+        assert err[i] < TOL, (key, name, err[i], k[i])
+        if band.any():
+            assert err[band].max() < 2.5e-4, (key, name, err[band].max())
