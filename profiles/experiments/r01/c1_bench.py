@@ -1,6 +1,6 @@
 """BASELINE configs[0]: pygcl OneLoopP00 + ZeldovichP00 at z = 0.55 on 200 k, single cosmology, through the pygcl drop-in"""
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
 import numpy as np
 from pyrsd_b200 import pygcl
 from tests.gpu_common import golden_pygcl_cosmology

@@ -1,6 +1,6 @@
 """timings of BASELINE configs[2] (PT tables of 1024 variants) and configs[4] (2048-walker ensemble step, chi^2 out)"""
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
 import numpy as np, ctypes as C
 import bench
 from pyrsd_b200 import _native as N, rsd

@@ -1,6 +1,6 @@
 """BASELINE configs[3]: 16384 FFTLog Hankel transforms on a 4096-point log grid (device-resident), CUDA-event timing"""
 import sys, ctypes as C
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
 import numpy as np, torch
 from pyrsd_b200 import _native as N, pygcl
 L = pygcl._L()

@@ -1,6 +1,6 @@
 """latency of one full evaluation as a function of the batch size (device-resident inputs, host-visible sync)"""
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
 import numpy as np, ctypes as C
 import bench
 from pyrsd_b200 import _native as N, rsd

@@ -1,7 +1,7 @@
 """reference-mode ensemble step: ONE tabulated cosmology, 2048 walkers varying sigma8_z, f, biases, FOG, AP (what
 rsdfit does during a fit): time of galaxy_power / galaxy_poles per step"""
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
 import numpy as np
 import bench
 from pyrsd_b200 import rsd

@@ -2,7 +2,7 @@
 -> multipoles -> window convolution (6 FFTLogs of N = 4096 per walker) -> spline onto the data k -> chi^2, all on
 the device (PTEngine.galaxy_window_chi2)"""
 import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/golden')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))); sys.path.insert(0, '/root/repo/tests/golden')
 import numpy as np
 import torch
 import bench

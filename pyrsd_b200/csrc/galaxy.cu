@@ -856,7 +856,9 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
 
     // With a host destination the walkers go in chunks: the device-to-host copy of a chunk (PCIe, the slow leg when
     // full P(k, mu) grids leave the device) runs on the copy stream under the kernels of the next chunk.
-    const int chunk = (h_out && npts > 0 && nw >= 2*GAL_PIPE_CHUNK) ? GAL_PIPE_CHUNK : nw;
+    // (only the blocking call chunks: in the streaming mode the whole copy hides under the PT stage of the NEXT batch, and
+    // one launch per kernel for all walkers avoids five kernel tails per step -- measured 6.30 -> see profiles/r02_summary.md)
+    const int chunk = (sync && h_out && npts > 0 && nw >= 2*GAL_PIPE_CHUNK) ? GAL_PIPE_CHUNK : nw;
     for (int w0 = 0, n = 0; w0 < nw; w0 += n) {
         // the last chunk is halved: its copy is the only one nothing hides
         const int left = nw - w0;

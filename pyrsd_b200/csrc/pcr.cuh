@@ -5,7 +5,7 @@
 // The Thomas algorithm is a chain of n dependent divisions on one thread (0.1-0.2 ms for n = 1000, the longest
 // serial stretch of a single-cosmology evaluation); cyclic reduction needs ceil(log2 n) fully parallel sweeps.
 // The systems here are (weakly) diagonally dominant, for which the reduction is as accurate as the elimination
-// (measured: <= 3e-13 pointwise, 4e-16 of the largest unknown, scratch/pcr_test.py).
+// (measured: <= 3e-13 pointwise, 4e-16 of the largest unknown, profiles/experiments/r01/pcr_test.py).
 #pragma once
 
 namespace prsd {
