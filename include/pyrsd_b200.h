@@ -113,6 +113,9 @@ int prsd_plan_destroy(prsd_plan* plan);
 /* info[8] = {total 2-D nodes, device bytes, build seconds, nk, n_knots, nodes(one-loop op),
  *            nodes(I/K op), nodes(ImnOneLoop op, one half)} */
 int prsd_plan_info(prsd_plan* plan, double* info8);
+/* wall-clock milliseconds of the build stages: 0 node geometry on the host + upload, 1 W operators (k_build_w),
+ * 2 J_mn operator on the one-loop grid, 3 main 1-D operators (J, sigma^2, X, Y), 4 rest, 5-7 unused */
+int prsd_plan_build_profile(prsd_plan* plan, double* ms8);
 /* *res may be NULL on first use (allocated) and is reused afterwards */
 int prsd_plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res);
 int prsd_result_destroy(prsd_result* res);

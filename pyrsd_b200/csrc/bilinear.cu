@@ -4,6 +4,10 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
 
 namespace prsd {
 
@@ -12,14 +16,20 @@ size_t NodeGeometry::bytes() const
     return n_nodes*(sizeof(int)*3 + sizeof(double)*6) + n_outer*(sizeof(int)*2 + sizeof(double)*5);
 }
 
-std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
-                                            const QuadConfig& cfg, const KnotGrid& grid, int bank_mod)
+// Host part of the geometry for a contiguous range of k: nodes, padding and lane ordering.  Every k is independent,
+// so make_geometry runs this on several threads over chunks of the k list and concatenates the pieces.
+namespace {
+struct GeoChunk {
+    HalfNodes H;                                  // outer-node arrays in their final (reordered) order
+    std::vector<int> b_j0, n_ol;
+    std::vector<double> b, wgt, b_coef;
+    std::vector<int64_t> node_off;                // padded node offsets, local, size nk + 1
+    int max_outer = 0;
+};
+
+void geometry_chunk(const double* k, int nk, double qmax, const QuadConfig& cfg, const KnotGrid& grid, int BM, GeoChunk& out)
 {
-    PRSD_REQUIRE(bank_mod == 4 || bank_mod == 16 || bank_mod == 32, "make_geometry: bank_mod must be 4, 16 or 32");
-    const int BM = bank_mod;
-    PRSD_REQUIRE(nk > 0, "make_geometry: empty k list");
-    for (int i = 0; i < nk; i++) PRSD_REQUIRE(k[i] > 0 && std::isfinite(k[i]), "make_geometry: k[%d] = %g must be > 0", i, k[i]);
-    HalfNodes H;
+    HalfNodes& H = out.H;
     build_half_nodes(k, nk, qmax, cfg, grid, H);
 
     // Outer nodes of one k are tabulated P(a) = sum_m coef_m t[j0 + m] by consecutive lanes: order them so that every
@@ -59,13 +69,12 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     // shared-memory reads of the nodal kernels: a half-warp (16 consecutive nodes) reads t[j0 + m] with 8-byte
     // accesses, which is one wavefront only if the 16 stencil starts are equal or distinct modulo 16.  Nodes
     // sharing a stencil start are kept together (broadcast) and every half-warp is filled from distinct residues.
-    auto g = std::make_shared<NodeGeometry>();
-    g->nk = nk;
-    g->k.assign(k, k + nk);
-    std::vector<int> b_j0, n_ol;
-    std::vector<double> b, wgt, b_coef;
-    g->h_node_off.assign(1, 0);
-    g->h_outer_off = H.outer_off;
+    std::vector<int>& b_j0 = out.b_j0;
+    std::vector<int>& n_ol = out.n_ol;
+    std::vector<double>& b = out.b;
+    std::vector<double>& wgt = out.wgt;
+    std::vector<double>& b_coef = out.b_coef;
+    out.node_off.assign(1, 0);
     std::vector<int64_t> src;                     // source node of every slot of this k (-1: padding)
     // an item = the nodes of one k that share the stencil start AND the outer node: every read of theirs is a
     // broadcast.  A group of BM lanes takes items whose stencil starts are distinct modulo BM (table reads) and,
@@ -77,7 +86,7 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     for (int ik = 0; ik < nk; ik++) {
         const int64_t n0 = H.node_off[ik], n1 = H.node_off[ik + 1];
         const int64_t o0 = H.outer_off[ik];
-        g->max_outer = std::max<int>(g->max_outer, (int)(H.outer_off[ik + 1] - o0));
+        out.max_outer = std::max<int>(out.max_outer, (int)(H.outer_off[ik + 1] - o0));
         // nodal kernels (BM = 16) read the node stream 32 nodes per warp: segments that start on a 128-byte
         // boundary cost two cache lines per load instead of three
         const int64_t pad_to = BM >= 16 ? 16 : 4;
@@ -156,7 +165,75 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
                 b_coef.insert(b_coef.end(), 4, 0.0);
             }
         }
-        g->h_node_off.push_back((int64_t)b.size());
+        out.node_off.push_back((int64_t)b.size());
+    }
+}
+} // namespace
+
+std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
+                                            const QuadConfig& cfg, const KnotGrid& grid, int bank_mod)
+{
+    PRSD_REQUIRE(bank_mod == 4 || bank_mod == 16 || bank_mod == 32, "make_geometry: bank_mod must be 4, 16 or 32");
+    const int BM = bank_mod;
+    PRSD_REQUIRE(nk > 0, "make_geometry: empty k list");
+    for (int i = 0; i < nk; i++) PRSD_REQUIRE(k[i] > 0 && std::isfinite(k[i]), "make_geometry: k[%d] = %g must be > 0", i, k[i]);
+    // chunks of k dealt round-robin in blocks to the threads (the node count grows ~10x from the lowest to the highest
+    // k): 4 chunks per thread keep the threads busy to the end
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int nthreads = std::max(1, std::min({hw > 0 ? hw : 4, 16, nk/4}));
+    const int nchunk = nthreads == 1 ? 1 : std::min(nk, 4*nthreads);
+    std::vector<GeoChunk> chunks(nchunk);
+    std::vector<int> lo(nchunk + 1);
+    for (int c = 0; c <= nchunk; c++) lo[c] = (int)((int64_t)nk*c/nchunk);
+    std::atomic<int> next{0};
+    std::string failure;
+    std::mutex fmu;
+    auto worker = [&]() {
+        for (int c = next++; c < nchunk; c = next++) {
+            try {
+                geometry_chunk(k + lo[c], lo[c + 1] - lo[c], qmax, cfg, grid, BM, chunks[c]);
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lk(fmu);
+                failure = e.what();
+            }
+        }
+    };
+    if (nthreads == 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+        for (auto& t : pool) t.join();
+    }
+    PRSD_REQUIRE(failure.empty(), "make_geometry: %s", failure.c_str());
+
+    auto g = std::make_shared<NodeGeometry>();
+    g->nk = nk;
+    g->k.assign(k, k + nk);
+    HalfNodes H;                                   // merged outer-node arrays
+    std::vector<int> b_j0, n_ol;
+    std::vector<double> b, wgt, b_coef;
+    g->h_node_off.assign(1, 0);
+    g->h_outer_off.assign(1, 0);
+    size_t tot_nodes = 0, tot_outer = 0;
+    for (const GeoChunk& c : chunks) { tot_nodes += c.b.size(); tot_outer += c.H.a.size(); }
+    b_j0.reserve(tot_nodes); n_ol.reserve(tot_nodes); b.reserve(tot_nodes); wgt.reserve(tot_nodes); b_coef.reserve(4*tot_nodes);
+    H.a.reserve(tot_outer); H.a_j0.reserve(tot_outer); H.a_coef.reserve(4*tot_outer); H.o_kid.reserve(tot_outer);
+    for (int ci = 0; ci < nchunk; ci++) {
+        GeoChunk& c = chunks[ci];
+        const int64_t node_base = (int64_t)b.size(), outer_base = (int64_t)H.a.size();
+        for (size_t i = 1; i < c.node_off.size(); i++) g->h_node_off.push_back(node_base + c.node_off[i]);
+        for (size_t i = 1; i < c.H.outer_off.size(); i++) g->h_outer_off.push_back(outer_base + c.H.outer_off[i]);
+        b_j0.insert(b_j0.end(), c.b_j0.begin(), c.b_j0.end());
+        n_ol.insert(n_ol.end(), c.n_ol.begin(), c.n_ol.end());
+        b.insert(b.end(), c.b.begin(), c.b.end());
+        wgt.insert(wgt.end(), c.wgt.begin(), c.wgt.end());
+        b_coef.insert(b_coef.end(), c.b_coef.begin(), c.b_coef.end());
+        H.a.insert(H.a.end(), c.H.a.begin(), c.H.a.end());
+        H.a_j0.insert(H.a_j0.end(), c.H.a_j0.begin(), c.H.a_j0.end());
+        H.a_coef.insert(H.a_coef.end(), c.H.a_coef.begin(), c.H.a_coef.end());
+        for (int32_t kid : c.H.o_kid) H.o_kid.push_back(kid + lo[ci]);
+        g->max_outer = std::max(g->max_outer, c.max_outer);
+        c = GeoChunk();                            // release the chunk's memory
     }
     g->n_nodes = (int64_t)b.size();
     g->n_outer = (int64_t)H.a.size();

@@ -499,6 +499,14 @@ int prsd_plan_info(prsd_plan* plan, double* info)
 }
 static void plan_run(prsd_plan* plan, prsd_spectra* sp, prsd_result** res, bool sync);
 
+int prsd_plan_build_profile(prsd_plan* plan, double* ms8)
+{
+    return guarded(dev_of(plan), [&] {
+        PRSD_REQUIRE(plan && ms8, "null argument");
+        for (int i = 0; i < 8; i++) ms8[i] = plan->p.build_stage_ms[i];
+    });
+}
+
 int prsd_plan_run_async(prsd_plan* plan, prsd_spectra* sp, prsd_result** res)
 {
     return guarded(dev_of(plan), [&] { plan_run(plan, sp, res, false); });

@@ -9,14 +9,77 @@ namespace prsd {
 __constant__ double c_glx[GLN];
 __constant__ double c_glw[GLN];
 
-__global__ void k_linear_build(int nout, const LinOutDev* __restrict__ outs, ZonesDev Z, double* __restrict__ Omega)
+// One WARP per (output, knot): the lanes share the (sub-panel, Gauss point) pairs of every cell piece.  The outputs
+// with an oscillatory kernel (X(r), Y(r) at r up to 1e5 Mpc/h: omega dq / 10 = 2e4 sub-panels per cell near q = 100)
+// cost 1e6 kernel evaluations per weight; with one thread per weight (round 1) a handful of threads ran for 1.6 s
+// while the rest of the device idled.  Same arithmetic as linear_weight() (linear_math.cuh, the CPU emulation's
+// copy); only the order of the partial sums differs.
+__device__ double linear_weight_warp(const LinOutDev& S, const ZonesDev& Z, int j, int lane)
+{
+    double total = 0.0;
+    int z = 0;
+    while (z < Z.nz - 1 && j >= Z.start[z + 1]) ++z;
+    const int jl = j - Z.start[z];
+    const int n = Z.n[z];
+    const double x0 = Z.x0[z], h = Z.h[z];
+    const double xlo = log(S.lo), xhi = log(S.hi);
+    const bool has_break = (S.type == LK_JMN || S.type == LK_SIGMA3);
+    const double omega = lin_omega(S.type, S.param);
+    const int c_lo = jl - 3 > 0 ? jl - 3 : 0;
+    const int c_hi = jl + 3 < n - 1 ? jl + 3 : n - 1;
+    for (int c = c_lo; c <= c_hi; c++) {
+        int s0 = c - 1;
+        if (s0 < 0) s0 = 0;
+        if (s0 > n - 3) s0 = n - 3;
+        const int l = jl - s0;
+        if (l < 0 || l > 3) continue;
+        double xa = x0 + h*c, xb = x0 + h*(c + 1);
+        if (xa < xlo) xa = xlo;
+        if (xb > xhi) xb = xhi;
+        if (!(xb > xa)) continue;
+        const double qa = exp(xa), qb = exp(xb);
+        double pe[3];
+        int np = 1;
+        pe[0] = qa;
+        if (has_break && S.param > qa && S.param < qb) { pe[1] = S.param; np = 2; }
+        pe[np] = qb;
+        for (int ip = 0; ip < np; ip++) {
+            const double p0 = pe[ip], p1 = pe[ip + 1];
+            long long nsub = 1;
+            if (omega > 0.0) {
+                const double ph = omega*(p1 - p0);
+                if (ph > 10.0) nsub = (long long)ceil(ph/10.0);
+            }
+            const double dq = (p1 - p0)/(double)nsub, hw = 0.5*dq;
+            double acc = 0.0;
+            const long long npts = nsub*GLN;
+            for (long long idx = lane; idx < npts; idx += 32) {
+                const long long is = idx/GLN;
+                const int g = (int)(idx - is*GLN);
+                const double q = p0 + dq*((double)is + 0.5) + hw*c_glx[g];
+                const double s = (log(q) - x0)/h - (double)s0;
+                double Lg[4];
+                lagrange4(s, Lg);
+                acc += c_glw[g]*Lg[l]*lin_kernel(S.type, S.sub, S.param, q);
+            }
+            total += acc*hw;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    return total*S.scale;
+}
+
+__global__ void __launch_bounds__(256)
+k_linear_build(int nout, const LinOutDev* __restrict__ outs, ZonesDev Z, double* __restrict__ Omega)
 {
     const int o = blockIdx.y;
-    const int j = blockIdx.x*blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= TAB_MPAD) return;
     double total = 0.0;
-    if (j < TAB_M) total = linear_weight(outs[o], Z, j, c_glx, c_glw);
-    Omega[(size_t)o*TAB_MPAD + j] = total;
+    if (j < TAB_M) total = linear_weight_warp(outs[o], Z, j, lane);
+    if (lane == 0) Omega[(size_t)o*TAB_MPAD + j] = total;
 }
 
 void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs)
@@ -43,8 +106,8 @@ void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs)
     DevBuf<LinOutDev> dout;
     dout.upload(ho, ctx.stream);
     Omega.alloc((size_t)nout*TAB_MPAD);
-    dim3 grid((TAB_MPAD + 63)/64, nout);
-    k_linear_build<<<grid, 64, 0, ctx.stream>>>(nout, dout.p, Z, Omega.p);
+    dim3 grid((TAB_MPAD + 7)/8, nout);
+    k_linear_build<<<grid, 256, 0, ctx.stream>>>(nout, dout.p, Z, Omega.p);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
     ctx.sync();

@@ -55,35 +55,48 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     : ctx(&c), cfg(q), nk(nk_), with_ml(ml), with_zel(zel), only_oneloop(only1l)
 {
     auto t0 = std::chrono::steady_clock::now();
+    auto t_lap = t0;
     PRSD_REQUIRE(nk > 0 || only_oneloop, "PTPlan: empty k grid");
     if (nk > 0) k_interp.assign(k, k + nk);
     k_1loop = oneloop_kgrid();
     r_zel = zeldovich_rgrid();
     const KnotGrid& grid = knot_grid();
 
+    auto lap = [&](int slot) {
+        c.sync();
+        const auto now = std::chrono::steady_clock::now();
+        build_stage_ms[slot] += std::chrono::duration<double, std::milli>(now - t_lap).count();
+        t_lap = now;
+    };
     // ---- one-loop tables: I00 I01 I11 I23 I32 I33 (all symmetric: 2 x the v > 0 half)
     {
         auto geo = make_geometry(c, k_1loop.data(), ONELOOP_N, 1e5, cfg, grid);
+        lap(0);
         std::vector<ColSpec> cols;
         for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
         op_1loop.build(c, geo, cols, true);
         // OneLoopP22Bar only ever needs I23 + 2/3 I32 + 1/5 I33 (OneLoopPS.cpp:164-185): fold the three columns
         op_1loop.fold_columns(c, 3, {{4, 2.0/3.0}, {5, 1.0/5.0}}, 4);
+        lap(1);
     }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
     if (!only_oneloop) {
         auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid, 4);     // DMMA lane layout: 4 nodes per k-step
+        lap(0);
         std::vector<ColSpec> cols;
         // both spectra are P_L here, so P(a) P(b) is the same on the two halves of the v domain and the
         // non-symmetric kernels simply use f(u, v) + f(u, -v) (ColSpec sign 0): 29 columns, 4 n-tiles
         for (int id = 0; id < 16; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
         for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
         op_ik.build(c, geo, cols);
+        lap(1);
     }
     // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
     if (with_ml && !only_oneloop) {
         auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg.ml_variant(), grid);
+        lap(0);
         op_ml.build(c, geo, ml_columns(), true);
+        lap(1);
     }
     // ---- 1-D operators
     {
@@ -91,6 +104,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         for (int id : {0, 1, 4})
             for (int i = 0; i < ONELOOP_N; i++) o.push_back({LK_JMN, id, k_1loop[i], 1e-5, 1e5, 1.0});
         lin_1loop.build(c, o);
+        lap(2);
     }
     if (!only_oneloop) {
         std::vector<LinOutSpec> o;
@@ -109,6 +123,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
             for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_YZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
         }
         lin_main.build(c, o);
+        lap(3);
     }
     if (!only_oneloop) {
         lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}});
@@ -116,7 +131,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         d_kinterp.upload(k_interp, c.stream);
     }
     d_k1loop.upload(k_1loop, c.stream);
-    c.sync();
+    lap(4);
     build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 

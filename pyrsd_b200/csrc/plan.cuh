@@ -57,6 +57,7 @@ struct PTPlan {
     DevBuf<int> d_tabL, d_tabSq, d_tab22;
     int idx_nc_a = -1, idx_nc_b = -1;
     double build_seconds = 0.0;
+    double build_stage_ms[8] = {0};    // 0 node geometry (host) + upload, 1 W operators, 2 J on the one-loop grid, 3 main 1-D operators, 4 rest
 
     PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l = false);
     // stage A only: the four one-loop tables (left in sp and in res.oneloop)

@@ -51,7 +51,9 @@ struct QuadConfig {
     QuadTier tier[NTIER]    = {{0.02, 5, 4, 3}, {0.08, 6, 5, 4}, {0.3, 8, 6, 5}, {0.5, 12, 7, 5}, {1.0, 16, 7, 5}, {1e30, 12, 7, 5}};
     // ImnOneLoop (q_max = 10): the one-loop spectra are large at the hard cut and the h02-type kernels cancel to
     // leading order across v, so above k = 0.06 that operator keeps full-order panels everywhere
-    QuadTier ml_tier[NTIER] = {{0.02, 4, 4, 3}, {0.06, 6, 5, 4}, {0.2, 10, 7, 7}, {1e30, 10, 8, 8}, {1e30, 10, 8, 8}, {1e30, 10, 8, 8}};
+    // 0.2 <= k < 0.45 uses 9 inner points: the f32 cross part (P_L x P_vv) is the worst-conditioned integral of the
+    // set there (8.7e-6 ... 1.2e-5 of its scale with (10, 8, 8) on the five dense-fixture cosmologies, 7e-6 with 9)
+    QuadTier ml_tier[NTIER] = {{0.02, 4, 4, 3}, {0.06, 6, 5, 4}, {0.2, 10, 7, 7}, {0.45, 10, 9, 9}, {1e30, 10, 8, 8}, {1e30, 10, 8, 8}};
 
     const QuadTier& tier_of(double k) const
     {

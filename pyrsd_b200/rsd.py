@@ -97,6 +97,15 @@ class PTEngine(object):
         return dict(nodes=int(out[0]), device_bytes=int(out[1]), build_seconds=out[2], nk=int(out[3]), n_knots=int(out[4]),
                     nodes_oneloop=int(out[5]), nodes_ik=int(out[6]), nodes_ml_half=int(out[7]))
 
+    def build_profile(self):
+        """milliseconds of the plan's build stages (prsd_plan_build_profile)"""
+        out = np.zeros(8)
+        L = _L()
+        L.prsd_plan_build_profile.argtypes = [_vp, _dp]
+        L.prsd_plan_build_profile.restype = C.c_int
+        N.check(L.prsd_plan_build_profile(self.plan.ptr, out))
+        return dict(geometry_host_ms=out[0], w_operators_ms=out[1], j_oneloop_grid_ms=out[2], linear_main_ms=out[3], rest_ms=out[4])
+
     # ------------------------------------------------------------------ spectra
     def spectra(self, k, T, n_s, amp, h, Omega0_m, Omega0_b, Tcmb=2.7255):
         """upload a batch of linear spectra: k, T [ncosmo][nspl]; the rest scalars or [ncosmo]"""

@@ -67,4 +67,4 @@ def test_static_queries_work_without_gpu(lib):
     x = _native.knot_grid()
     assert len(x) == 2457
     cfg = _native.quad_config_default()
-    assert len(cfg) == 56 and cfg[0] == 1e-8 and cfg[21] == 12 and cfg[25] == 16 and cfg[29] == 12 and cfg[41] == 10 and cfg[42] == 7 and cfg[45] == 10 and cfg[46] == 8
+    assert len(cfg) == 56 and cfg[0] == 1e-8 and cfg[21] == 12 and cfg[25] == 16 and cfg[29] == 12 and cfg[41] == 10 and cfg[42] == 7 and cfg[45] == 10 and cfg[46] == 9 and cfg[49] == 10 and cfg[50] == 8
