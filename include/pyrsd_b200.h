@@ -164,6 +164,9 @@ int prsd_zeldovich(prsd_ctx* ctx, int nrow, const double* X0, const double* XX, 
  * cfg64 (NULL = defaults, see prsd_galaxy_config_default):
  *   [0] max_mu  [1] fog_model (0 modified_lorentzian, 1 lorentzian, 2 gaussian)
  *   [2..7] use_P00/P01/P11/Pdv/Pvv/Phm_model  [8] use_tidal_bias  [9] use_so_correction  [10] k0_low
+ *   [11] interpolate: the Zel'dovich terms of P00 / P01 / P11 / Phm come from 100 sigma8_z x 300 k tables read
+ *        bilinearly (InterpolatedHZPTModels, rsd/hzpt/interpolated.py:8-72, 208-263 -- the reference's default);
+ *        0 (the library default): evaluated exactly at every call
  *   [16..25] HZPT P00/P01 parameters, [26..34] HZPT P11, [35..54] HZPT Phm
  * kmodel: the model's spline grid self.k (numpy.logspace(log10 kmin, log10 kmax, Nk));
  * k_interp: the PT interpolation grid of the plan.
@@ -256,6 +259,26 @@ int prsd_spline_resample_device(prsd_ctx* ctx, int nrows, int n, const double* x
  * model_on_device != 0) against data [n] with precision matrix cinv [n][n] (host); chi2 [nw] host */
 int prsd_chi2(prsd_ctx* ctx, int nw, int n, const double* model, const double* data, const double* cinv,
               double* chi2, int model_on_device);
+
+/* ---- Gaussian-process simulation fits  [rsd/simulation.py:16-256: GeorgeSimulationData on george.GP, ExpSquaredKernel]:
+ * mean prediction  y(x*) = y_mean + y_scale sum_i alpha_i amp exp(-1/2 sum_d ((x*_d - x_id) / x_scale_d)^2 / metric_d)
+ * x [n][ndim] raw training inputs, x_mean / x_scale [ndim] their StandardScaler, metric [ndim] the kernel metric in scaled
+ * units, alpha [n] = (K + diag(yerr^2))^-1 y_scaled (solved once per training set, pyrsd_b200/data/make_simulation_fits.py).
+ * prsd_gp_predict: x [npred][ndim] -> out [npred]; device_ptrs != 0: both on the device, no synchronisation. */
+typedef struct prsd_gp prsd_gp;
+int prsd_gp_create(prsd_ctx* ctx, int n, int ndim, const double* x, const double* x_mean, const double* x_scale,
+                   const double* metric, double amp, const double* alpha, double y_mean, double y_scale, prsd_gp** out);
+int prsd_gp_destroy(prsd_gp* gp);
+int prsd_gp_predict(prsd_gp* gp, int npred, const double* x, double* out, int device_ptrs);
+
+/* ---- BiasToMassRelation / BiasToSigmaRelation  [rsd/tools.py:393-649; the `sigma_sB` constraint of the default fit,
+ * rsdfit/theory/gal_defaults.py:174].  mass_out[w] in M_sun/h = root of bias_Tinker(rescale[w] Sigma(R(M)), delta_halo)
+ * = b1[w] for M in [mass_lo, mass_hi] (the reference brackets [1e5, 1e16]), R(M) = (3 M / (4 pi rho_bar))^(1/3),
+ * rescale = sigma8_z / cosmo.sigma8(), rho_bar = cosmo.rho_bar_z(0) in M_sun/h / (Mpc/h)^3.  One thread per (sigma8_z,
+ * b1) pair, Sigma(R) of every cosmology from one operator application; cmap NULL: walker w uses cosmology w (or 0 when
+ * the batch holds one).  sigma_out (may be NULL): Sigma(R) on numpy.logspace(-3, 4, 1000), [ncosmo][1000].  Host pointers. */
+int prsd_bias_to_mass(prsd_spectra* sp, int nw, const int* cmap, const double* rescale, const double* b1, double rho_bar,
+                      double delta_halo, double mass_lo, double mass_hi, double* mass_out, double* sigma_out);
 
 /* ---- measurement support (bench.py) -------------------------------------------------- */
 /* per-kernel-family CUDA-event timing on the context's stream; families: 0 I/K operator (DMMA contraction),

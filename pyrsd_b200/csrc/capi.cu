@@ -5,6 +5,8 @@
 #include "xilm.cuh"
 #include "discrete.cuh"
 #include "transfer.cuh"
+#include "biasrel.cuh"
+#include "gp.cuh"
 
 #include <cstring>
 #include <list>
@@ -28,6 +30,7 @@ struct prsd_window {
     DevBuf<double> din, dout;
     prsd_window(Context& c, int nk, const double* k, int nell, const int* ells, double q, int N) : op(c, nk, k, nell, ells, q, N) {}
 };
+struct prsd_gp { GPModel m; prsd_gp(Context& c, int n, int nd, const double* x, const double* xm, const double* xs, const double* met, double amp, const double* al, double ym, double ys) : m(c, n, nd, x, xm, xs, met, amp, al, ym, ys) {} };
 struct prsd_zelplan { ZelPlan z; Context* ctx = nullptr; };
 
 static thread_local std::string g_err;
@@ -84,6 +87,7 @@ static const Context* dev_of(const prsd_plan* h) { return h ? h->p.ctx : nullptr
 static const Context* dev_of(const prsd_result* h) { return h ? h->ctx : nullptr; }
 static const Context* dev_of(const prsd_galaxy* h) { return h ? h->g.ctx : nullptr; }
 static const Context* dev_of(const prsd_gridop* h) { return h ? h->op.ctx : nullptr; }
+static const Context* dev_of(const prsd_gp* h) { return h ? h->m.ctx : nullptr; }
 static const Context* dev_of(const prsd_window* h) { return h ? h->op.ctx : nullptr; }
 
 static QuadConfig cfg_from(const double* c)
@@ -698,6 +702,7 @@ static GalaxyConfig gal_cfg_from(const double* cfg)
         g.use_Pdv_model = cfg[5] != 0; g.use_Pvv_model = cfg[6] != 0; g.use_Phm_model = cfg[7] != 0;
         g.use_tidal_bias = cfg[8] != 0; g.use_so_correction = cfg[9] != 0;
         g.k0_low = cfg[10];
+        g.interpolate = cfg[11] != 0;
         for (int i = 0; i < 10; i++) g.hz00[i] = cfg[16 + i];
         for (int i = 0; i < 9; i++) g.hz11[i] = cfg[26 + i];
         for (int i = 0; i < 20; i++) g.hzhm[i] = cfg[35 + i];
@@ -715,7 +720,7 @@ int prsd_galaxy_config_default(double* cfg64)
         cfg64[0] = g.max_mu; cfg64[1] = g.fog_model;
         cfg64[2] = g.use_P00_model; cfg64[3] = g.use_P01_model; cfg64[4] = g.use_P11_model;
         cfg64[5] = g.use_Pdv_model; cfg64[6] = g.use_Pvv_model; cfg64[7] = g.use_Phm_model;
-        cfg64[8] = g.use_tidal_bias; cfg64[9] = g.use_so_correction; cfg64[10] = g.k0_low;
+        cfg64[8] = g.use_tidal_bias; cfg64[9] = g.use_so_correction; cfg64[10] = g.k0_low; cfg64[11] = g.interpolate;
         for (int i = 0; i < 10; i++) cfg64[16 + i] = g.hz00[i];
         for (int i = 0; i < 9; i++) cfg64[26 + i] = g.hz11[i];
         for (int i = 0; i < 20; i++) cfg64[35 + i] = g.hzhm[i];
@@ -1046,6 +1051,33 @@ int prsd_fp64_peak(prsd_ctx* ctx, int mode, double* tflops)
     return guarded(dev_of(ctx), [&] {
         PRSD_REQUIRE(ctx && tflops && (mode == 0 || mode == 1), "bad argument");
         *tflops = fp64_peak_tflops(ctx->c, mode);
+    });
+}
+
+int prsd_gp_create(prsd_ctx* ctx, int n, int ndim, const double* x, const double* x_mean, const double* x_scale, const double* metric,
+                   double amp, const double* alpha, double y_mean, double y_scale, prsd_gp** out)
+{
+    return guarded(dev_of(ctx), [&] {
+        PRSD_REQUIRE(ctx && x && x_mean && x_scale && metric && alpha && out, "null argument");
+        *out = new prsd_gp(ctx->c, n, ndim, x, x_mean, x_scale, metric, amp, alpha, y_mean, y_scale);
+    });
+}
+int prsd_gp_destroy(prsd_gp* gp) { return guarded(dev_of(gp), [&] { delete gp; }); }
+int prsd_gp_predict(prsd_gp* gp, int npred, const double* x, double* out, int device_ptrs)
+{
+    return guarded(dev_of(gp), [&] {
+        PRSD_REQUIRE(gp && (npred == 0 || (x && out)), "null argument");
+        if (device_ptrs) gp->m.predict_device(npred, x, out);
+        else gp->m.predict(npred, x, out);
+    });
+}
+
+int prsd_bias_to_mass(prsd_spectra* sp, int nw, const int* cmap, const double* rescale, const double* b1, double rho_bar,
+                      double delta_halo, double mass_lo, double mass_hi, double* mass_out, double* sigma_out)
+{
+    return guarded(dev_of(sp), [&] {
+        PRSD_REQUIRE(sp, "null argument");
+        bias_to_mass(sp->s, nw, cmap, rescale, b1, rho_bar, delta_halo, mass_lo, mass_hi, mass_out, sigma_out);
     });
 }
 

@@ -16,6 +16,7 @@ void galaxy_config_default(GalaxyConfig& c)
     c.use_tidal_bias = 0;
     c.use_so_correction = 0;
     c.k0_low = 5e-3;
+    c.interpolate = 0;
     // rsd/hzpt/__init__.py:66-92
     const double h00[10] = {707.8, 3.654, 31.76, 0.1257, 3.243, 0.3729, 3.768, -0.1043, 1.699, 0.4224};
     // rsd/hzpt/P11.py:33-61
@@ -602,6 +603,46 @@ __global__ void k_plin_model(int nspl, const PlinParams* __restrict__ params, co
     out[(size_t)c*nq + j] = plin_eval(params[c], spl + (size_t)c*5*nspl, q[j]);
 }
 
+// RegularGridInterpolator._find_indices (rsd/_interpolate.py:185-203): i = searchsorted(grid, x) - 1 clipped to
+// [0, n - 2], distance (x - grid[i]) / (grid[i + 1] - grid[i])
+__device__ __forceinline__ int grid_locate(const double* __restrict__ g, int n, double x, double& y)
+{
+    int lo = 0, hi = n;                    // first index with g[idx] >= x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    int i = lo - 1;
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    y = (x - g[i])/(g[i + 1] - g[i]);
+    return i;
+}
+
+// Zel'dovich terms of every walker from the sigma8 x k tables: which = 0 -> P00, P01, P11 at sigma8_z; which = 1 ->
+// P00 at sigma8_z / D.  A walker whose sigma8 lies outside the table keeps what `out` already holds (the direct value).
+__global__ void k_zel_table_read(int nkm, const double* __restrict__ km, int ns, const double* __restrict__ s8g, int nkt,
+                                 const double* __restrict__ kt, const double* __restrict__ ztab, const int* __restrict__ cmap,
+                                 const double* __restrict__ par, int which, double* __restrict__ out /*[n][3][nkm]*/)
+{
+    const int w = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= nkm) return;
+    const double* p = par + (size_t)w*GAL_NPAR;
+    const double s8 = which == 0 ? p[W_S8Z] : p[W_S8Z]/p[W_D];
+    if (!(s8 >= s8g[0] && s8 <= s8g[ns - 1])) return;
+    const double k = km[i];
+    if (!(k >= kt[0] && k <= kt[nkt - 1])) return;
+    double ys, yk;
+    const int is = grid_locate(s8g, ns, s8, ys), ik = grid_locate(kt, nkt, k, yk);
+    const double* T = ztab + (size_t)cmap[w]*ns*3*nkt;
+    const int nspec = which == 0 ? 3 : 1;
+    for (int t = 0; t < nspec; t++) {
+        const double* a = T + ((size_t)is*3 + t)*nkt + ik;
+        const double* b = a + (size_t)3*nkt;
+        out[((size_t)w*3 + t)*nkm + i] = (1.0 - ys)*(1.0 - yk)*a[0] + (1.0 - ys)*yk*a[1] + ys*(1.0 - yk)*b[0] + ys*yk*b[1];
+    }
+}
+
 // normalisation ratios of every walker: (sigma8_z / sigma8)^2 and the same at sigma8_z / D (Jennings fits)
 __global__ void k_gal_ratios(int nw, const double* __restrict__ par, double* __restrict__ r1, double* __restrict__ r2)
 {
@@ -671,6 +712,20 @@ GalaxyModel::GalaxyModel(Context& c, const GalaxyConfig& cfg_, const double* kmo
     h_kinterp.assign(k_interp, k_interp + nki);
     PRSD_REQUIRE(nki >= 4, "GalaxyModel: the PT interpolation grid needs at least 4 points");
     zel.build(c, km.data(), nkm);
+    if (cfg.interpolate) {
+        // InterpolationTable.grid (interpolated.py:27-29): numpy.linspace(0.3, 1.0, 100), numpy.logspace(log10(k_interp[0]),
+        // log10(k_interp[-1]), 300) -- the PT interpolation range INTERP_KMIN .. INTERP_KMAX
+        h_s8grid.resize(ZT_NS);
+        for (int i = 0; i < ZT_NS; i++) h_s8grid[i] = 0.3 + (1.0 - 0.3)/(ZT_NS - 1)*i;
+        h_s8grid[ZT_NS - 1] = 1.0;
+        h_ktab.resize(ZT_NK);
+        const double a0 = std::log10(k_interp[0]), a1 = std::log10(k_interp[nki - 1]);
+        for (int i = 0; i < ZT_NK; i++) h_ktab[i] = std::pow(10.0, a0 + (a1 - a0)/(ZT_NK - 1)*i);
+        h_ktab[ZT_NK - 1] = std::pow(10.0, a1);
+        d_s8grid.upload(h_s8grid, c.stream);
+        d_ktab.upload(h_ktab, c.stream);
+        zel_tab.build(c, h_ktab.data(), ZT_NK);
+    }
     {
         // E[i][j] = (not-a-knot spline through e_j on k_interp)(km[i]); band of rs_band columns around the interval of km[i]
         const int n = nki;
@@ -740,6 +795,43 @@ GalaxyModel::~GalaxyModel()
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }
 
+void GalaxyModel::ensure_zel_tables(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par)
+{
+    Context& c = *ctx;
+    cudaStream_t s = c.stream;
+    const int nc = sp.ncosmo;
+    // sigma8 of every cosmology at the normalisation of its P_L (the walkers carry it)
+    std::vector<double> s80(nc, 0.0);
+    for (int w = 0; w < nw; w++) s80[cmap ? cmap[w] : w] = par[(size_t)w*GAL_NPAR + W_S80];
+    bool same = ztab_uid == sp.uid && ztab_gen == sp.lin_gen && ztab_nc == nc && ztab_s80.size() == s80.size();
+    for (int i = 0; same && i < nc; i++) same = s80[i] == 0.0 || s80[i] == ztab_s80[i];
+    if (same) return;
+    for (int i = 0; i < nc; i++)
+        if (s80[i] == 0.0) s80[i] = (ztab_s80.size() == (size_t)nc && ztab_s80[i] > 0) ? ztab_s80[i] : 1.0;    // cosmology without a walker: never read
+    const int rows = nc*ZT_NS;
+    std::vector<int> hmap(rows);
+    std::vector<double> hratio(rows);
+    for (int ci = 0; ci < nc; ci++)
+        for (int i = 0; i < ZT_NS; i++) {
+            hmap[ci*ZT_NS + i] = ci;
+            const double r = h_s8grid[i]/s80[ci];
+            hratio[ci*ZT_NS + i] = r*r;
+        }
+    DevBuf<int> dmap;
+    DevBuf<double> dratio, plin_t((size_t)nc*ZT_NK), plin_rows((size_t)rows*ZT_NK);
+    dmap.upload(hmap, s);
+    dratio.upload(hratio, s);
+    k_plin_model<<<dim3((ZT_NK + 127)/128, nc), 128, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, ZT_NK, d_ktab.p, plin_t.p);
+    k_scale_rows<<<dim3((ZT_NK + 127)/128, rows), 128, 0, s>>>(ZT_NK, plin_t.p, dratio.p, dmap.p, plin_rows.p);
+    c.launches += 2;
+    d_ztab.ensure((size_t)rows*3*ZT_NK);
+    // the drivers of the tables have the low-k approximation on (HaloZeldovichBase.from_zeldovich, hzpt/__init__.py:60-63)
+    zeldovich_eval_map(c, zel_tab, rows, dmap.p, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, dratio.p, true, cfg.k0_low,
+                       plin_rows.p, pt.scalars.p + 2, 4, d_ztab.p);
+    PRSD_CUDA(cudaStreamSynchronize(s));           // the host vectors go out of scope
+    ztab_uid = sp.uid; ztab_gen = sp.lin_gen; ztab_nc = nc; ztab_s80 = s80;
+}
+
 void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par, const double* stoch,
                         int npts, const double* d_k, const double* d_mu, double* d_out, double* h_out, bool sync)
 {
@@ -784,6 +876,17 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
     // (in stream order this wait sits AFTER the PT stage of the current batch, which therefore overlaps that copy)
     if (copy_ticket > 0 && copy_done[(copy_ticket - 1) & 1]) PRSD_CUDA(cudaStreamWaitEvent(s, copy_done[(copy_ticket - 1) & 1], 0));
 
+    bool zel_direct = true;
+    if (cfg.interpolate) {
+        ensure_zel_tables(sp, pt, nw, cmap, par);
+        // the direct evaluation is only needed for walkers whose sigma8_z or sigma8_z / D leaves the table
+        zel_direct = false;
+        for (int w = 0; w < nw && !zel_direct; w++) {
+            const double* p = par + (size_t)w*GAL_NPAR;
+            const double a = p[W_S8Z], b = p[W_S8Z]/p[W_D];
+            zel_direct = !(a >= 0.3 && a <= 1.0 && b >= 0.3 && b <= 1.0) || !(km[0] >= h_ktab[0] && km[nkm - 1] <= h_ktab[ZT_NK - 1]);
+        }
+    }
     // ---- per-cosmology: every PT table splined on k_interp and read on the model grid (rsd/_cache.py:344-389)
     const int nk = nk_interp;
     ptspl.ensure((size_t)nc*PT_NROWS*nkm);
@@ -836,10 +939,18 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         k_scale_rows<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(nkm, plin_m.p, ratio1.p + w0, cm, pw1);
         k_scale_rows<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(nkm, plin_m.p, ratio2.p + w0, cm, pw2);
         c.launches += 2;
-        zeldovich_eval_map(c, zel, n, cm, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio1.p + w0, true, cfg.k0_low,
-                           pw1, pt.scalars.p + 2, 4, z1);
-        zeldovich_eval_map(c, zel, n, cm, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio2.p + w0, true, cfg.k0_low,
-                           pw2, pt.scalars.p + 2, 4, z2, true);             // only P00 is read at sigma8_z / D
+        if (zel_direct) {
+            zeldovich_eval_map(c, zel, n, cm, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio1.p + w0, true, cfg.k0_low,
+                               pw1, pt.scalars.p + 2, 4, z1);
+            zeldovich_eval_map(c, zel, n, cm, pt.X0.p, nullptr, pt.YY.p, pt.scalars.p, 4, ratio2.p + w0, true, cfg.k0_low,
+                               pw2, pt.scalars.p + 2, 4, z2, true);             // only P00 is read at sigma8_z / D
+        }
+        if (cfg.interpolate) {
+            for (int which = 0; which < 2; which++)
+                k_zel_table_read<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(nkm, d_km.p, ZT_NS, d_s8grid.p, ZT_NK, d_ktab.p, d_ztab.p,
+                                                                         cm, pr, which, which == 0 ? z1 : z2);
+            c.launches += 2;
+        }
         ProfScope prof_gal(c, PROF_GALAXY);
         k_gal_base<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(G, d_km.p, cm, pr, ptspl.p, plin_m.p, sp.oneloop_spl.p,
                                                             pt.scalars.p, z1, z2, bs);

@@ -27,6 +27,8 @@ struct GalaxyConfig {
     int use_P00_model, use_P01_model, use_P11_model, use_Pdv_model, use_Pvv_model, use_Phm_model;
     int use_tidal_bias, use_so_correction;
     double k0_low;              // low-k transition of the Zel'dovich drivers (5e-3)
+    int interpolate;            // 1: the Zel'dovich terms are read from sigma8 x k tables (InterpolatedHZPTModels, the
+                                // reference default), 0: evaluated exactly at every call
     double hz00[10];            // A0(amp, alpha) R R1 R1h R2h of HaloZeldovichBase.default_parameters
     double hz11[9];             // A0(amp, alpha, beta) R R1h of HaloZeldovichP11.default_parameters
     double hzhm[20];            // A0 R1 R1h R2h R (amp, alpha, beta, run) of HaloMatterBase.default_parameters
@@ -52,6 +54,18 @@ struct GalaxyModel {
     std::vector<double> km;             // model k grid (numpy.logspace(log10 kmin, log10 kmax, Nk))
     DevBuf<double> d_km, d_kstoch;
     ZelPlan zel;                        // Zel'dovich stencils for the model grid
+    // interpolate = 1 (rsd/hzpt/interpolated.py:8-72, 208-263): Zel'dovich P00 / P01 / P11 of every cosmology on
+    // 100 sigma8_z in [0.3, 1] x 300 k in [INTERP_KMIN, INTERP_KMAX] -- one batched k_zeldovich launch -- read
+    // bilinearly in (sigma8_z, k) as the reference's RegularGridInterpolator does; a sigma8 outside the table falls
+    // back to the direct evaluation (its InterpolationDomainError branch).  Rebuilt when the spectra change.
+    static const int ZT_NS = 100, ZT_NK = 300;
+    ZelPlan zel_tab;
+    std::vector<double> h_s8grid, h_ktab;
+    DevBuf<double> d_s8grid, d_ktab, d_ztab;   // d_ztab [ncosmo][ZT_NS][3][ZT_NK]
+    uint64_t ztab_uid = 0, ztab_gen = 0;
+    int ztab_nc = 0;
+    std::vector<double> ztab_s80;
+    void ensure_zel_tables(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap, const double* par);
     int nk_interp = 0;
     DevBuf<double> d_kinterp;
     // scratch

@@ -163,6 +163,24 @@ class Cosmology(PickalableSWIG):
     def f_z(self, z): return _lookup(self._params.get('f'), z, 'f')
     def H_z(self, z): return 100.*self.h() if (z == 0 and self._params.get('H') is None) else _lookup(self._params.get('H'), z, 'H')
     def Sigma8_z(self, z): return self._sigma8*self.D_z(z)
+    def H0(self): return 100.*self.h()
+
+    def Omega_m_z(self, z):
+        """ClassEngine.cpp:572-577"""
+        Ez = self.H_z(z)/self.H0()
+        return self.Omega0_m()*(1. + z)**3/Ez**2
+
+    def rho_crit_z(self, z):
+        """critical density in h^2 M_sun / Mpc^3 with the reference's constants (ClassEngine.cpp:552-570, Common.h:101-140)"""
+        G, M_sun, au = 6.67384e-8, 1.9891e33, 149597870700.*1e2
+        Mpc = 1e6*au/(np.pi/180./60./60.)
+        H = 100.*1e5/Mpc
+        rho = 3.*H**2/(8.*np.pi*G)/(M_sun/Mpc**3)
+        return rho*(self.H_z(z)/self.H0())**2
+
+    def rho_bar_z(self, z):
+        """mean matter density in h^2 M_sun / Mpc^3 (ClassEngine.cpp:579-582)"""
+        return self.Omega_m_z(z)*self.rho_crit_z(z)
     def rs_drag(self):
         if self._params.get('rs_drag') is None:
             raise ValueError("Cosmology: `rs_drag` was not supplied (CLASS is not run by this library)")

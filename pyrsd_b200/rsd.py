@@ -344,7 +344,7 @@ class PTStream(object):
 
 def galaxy_config(max_mu=4, fog_model='modified_lorentzian', use_P00_model=True, use_P01_model=True, use_P11_model=True,
                   use_Pdv_model=True, use_Pvv_model=True, use_Phm_model=True, use_tidal_bias=False,
-                  use_so_correction=False, k0_low=5e-3):
+                  use_so_correction=False, k0_low=5e-3, interpolate=False):
     cfg = np.empty(64)
     N.check(_L().prsd_galaxy_config_default(cfg))
     if fog_model not in FOG_MODELS:
@@ -355,6 +355,7 @@ def galaxy_config(max_mu=4, fog_model='modified_lorentzian', use_P00_model=True,
     cfg[2:10] = [use_P00_model, use_P01_model, use_P11_model, use_Pdv_model, use_Pvv_model, use_Phm_model,
                  use_tidal_bias, use_so_correction]
     cfg[10] = k0_low
+    cfg[11] = 1.0 if interpolate else 0.0
     return cfg
 
 
@@ -401,7 +402,7 @@ class GalaxySpectrum(object):
                'sigma_v2', 'sigma_bv2', 'sigma_bv4')
 
     def __init__(self, kmin=1e-3, kmax=0.5, Nk=200, z=0., params=None, include_2loop=False, transfer_fit="CLASS",
-                 max_mu=4, interpolate=False, k0_low=5e-3, Pdv_model_type='jennings', fog_model='modified_lorentzian',
+                 max_mu=4, interpolate=True, k0_low=5e-3, Pdv_model_type='jennings', fog_model='modified_lorentzian',
                  use_so_correction=False, use_tidal_bias=False, use_mean_bias=False, vel_disp_from_sims=False,
                  correct_mu2=False, correct_mu4=False, use_vlah_biasing=True, b2_00=None, b2_01=None,
                  stochasticity=None, engine=None, **kwargs):
@@ -409,14 +410,13 @@ class GalaxySpectrum(object):
             raise TypeError("`params` must be a pyrsd_b200.pygcl.Cosmology (the linear T(k) is a host input)")
         if include_2loop:
             raise ValueError("`include_2loop` is forced to False for biased tracers (power_biased.py:47)")
-        if interpolate:
-            raise NotImplementedError("interpolate=True (sigma8 x k Zel'dovich tables) is not needed: the Zel'dovich "
-                                      "terms are evaluated exactly at every call")
         if Pdv_model_type != 'jennings':
-            raise NotImplementedError("only Pdv_model_type='jennings' is available (the 'sims' model needs george)")
+            raise NotImplementedError("only Pdv_model_type='jennings' (the reference default) is available")
         if use_mean_bias or vel_disp_from_sims or correct_mu2 or correct_mu4:
-            raise NotImplementedError("use_mean_bias / vel_disp_from_sims / correct_mu2 / correct_mu4 need the "
-                                      "reference's Gaussian-process fits, which are host inputs not available here")
+            raise NotImplementedError("use_mean_bias / vel_disp_from_sims / correct_mu2 / correct_mu4 are not wired into the "
+                                      "assembly kernels; the Gaussian-process fits they read are available as "
+                                      "pyrsd_b200.simulation.VelocityDispersionFits / Pmu2ResidualCorrection / "
+                                      "Pmu4ResidualCorrection")
         if kmin < INTERP_KMIN:
             raise ValueError("kmin = %.2e h/Mpc below PT integrals interpolation lower bound" % kmin)
         if kmax > INTERP_KMAX:
@@ -426,7 +426,9 @@ class GalaxySpectrum(object):
         self.max_mu, self.fog_model, self.use_so_correction, self.use_tidal_bias = max_mu, fog_model, use_so_correction, use_tidal_bias
         self.k0_low = k0_low
         self.include_2loop = False
-        self.interpolate = False
+        # True (the reference's default, power_dm.py:34): Zel'dovich terms from the sigma8_z x k tables of
+        # rsd/hzpt/interpolated.py, built on the device in one batched launch; False: exact at every call
+        self.interpolate = bool(interpolate)
         self.transfer_fit = transfer_fit
         self.use_vlah_biasing = use_vlah_biasing
         self._models = {}
@@ -434,9 +436,13 @@ class GalaxySpectrum(object):
             self._models[kw] = bool(kwargs.pop(kw, True))
         if kwargs:
             raise TypeError("unexpected keyword arguments %s" % sorted(kwargs))
-        self.b2_00 = b2_00 if b2_00 is not None else default_b2_00
-        self.b2_01 = b2_01 if b2_01 is not None else default_b2_01
-        self.stochasticity = stochasticity
+        # the reference's defaults are its Gaussian-process simulation fits (use_vlah_biasing: one b2_00 and one b2_01
+        # for all terms, nonlinear_biasing.py:10-23; stochasticity: power_biased.py:342-366), predicted on the device
+        # from the shipped training data (pyrsd_b200/simulation.py); any callable with the same signature replaces them
+        from . import simulation as _sim
+        self.b2_00 = b2_00 if b2_00 is not None else _sim.b2_00
+        self.b2_01 = b2_01 if b2_01 is not None else _sim.b2_01
+        self.stochasticity = stochasticity if stochasticity is not None else _sim.stochasticity
         # defaults of DarkMatterSpectrum / GalaxySpectrum (power_dm.py:119-126, power_gal.py:103-123)
         self.sigma8_z = params.Sigma8_z(z)
         self.f = params.f_z(z)
@@ -505,7 +511,7 @@ class GalaxySpectrum(object):
             if k in self._models:
                 self._models[k] = bool(v)
             elif k in self._PARAMS or k in ('max_mu', 'fog_model', 'use_so_correction', 'use_tidal_bias', 'b2_00', 'b2_01',
-                                            'stochasticity'):
+                                            'stochasticity', 'interpolate', 'k0_low'):
                 setattr(self, k, v)
             else:
                 raise RuntimeError("failure to set parameter `%s` to value %s: unknown parameter" % (k, v))
@@ -559,7 +565,8 @@ class GalaxySpectrum(object):
 
     def _config(self):
         return galaxy_config(max_mu=self.max_mu, fog_model=self.fog_model, use_tidal_bias=self.use_tidal_bias,
-                             use_so_correction=self.use_so_correction, k0_low=self.k0_low, **self._models)
+                             use_so_correction=self.use_so_correction, k0_low=self.k0_low, interpolate=self.interpolate,
+                             **self._models)
 
     def power(self, k, mu, flatten=False):
         """P(k, mu) with the broadcasting rules of ``tools.broadcast_kmu`` (rsd/tools.py:225-266)"""

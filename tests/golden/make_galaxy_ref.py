@@ -273,11 +273,24 @@ def main():
         'z055_so_gauss': (0.55, dict(interpolate=False, use_so_correction=True, fog_model='gaussian', max_mu=6,
                                      use_tidal_bias=True),
                           dict(f_so=0.04, sigma_so=4.0, alpha_par=0.97, alpha_perp=1.02)),
+        # the reference's DEFAULT: Zel'dovich terms from its 100 x 300 sigma8_z x k interpolation tables
+        # (rsd/hzpt/interpolated.py), sigma8_z / D = 0.855 inside the table
+        'z055_interp': (0.55, dict(interpolate=True),
+                        dict(alpha_par=1.02, alpha_perp=0.99, sigma8_z=0.64, f=0.74, b1_cA=2.0, fs=0.11)),
+        # ... and with sigma8_z / D = 1.02 OUTSIDE the table: the reference falls back to the direct evaluation for
+        # that one call (InterpolationDomainError branch, interpolated.py:18-19)
+        'z055_interp_edge': (0.55, dict(interpolate=True), dict(sigma8_z=0.7636, f=0.74)),
     }
     names = ['sigma8_z', 'f', 'alpha_par', 'alpha_perp', 'alpha_drag', 'b1_cA', 'b1_cB', 'b1_sA', 'b1_sB', 'fs', 'fcB',
              'fsB', 'sigma_c', 'sigma_sA', 'sigma_sB', 'NcBs', 'NsBsB', 'f_so', 'sigma_so', 'sigma_v', 'D']
     global ZEL_SOURCE
-    runs = [(name, 'reference') for name in cases] + [(name, 'pi') for name in cases if name != 'z055_spt']
+    only = [a for a in sys.argv[1:] if a in cases]
+    runs = [(name, 'reference') for name in cases if not name.startswith('z055_interp')] \
+        + [(name, 'pi') for name in cases if name != 'z055_spt']
+    if only:
+        runs = [r for r in runs if r[0] in only]
+        old = np.load(os.path.join(HERE, 'galaxy_ref.npz'))
+        out.update({k: old[k] for k in old.files})
     for case_name, ZEL_SOURCE in runs:
         z, kw, upd = cases[case_name]
         name = case_name if ZEL_SOURCE == 'reference' else case_name + '_pi'

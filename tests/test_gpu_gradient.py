@@ -37,7 +37,7 @@ def models(golden):
     engine = rsd.PTEngine()
     out = {}
     for tag, (kw, upd) in CASES.items():
-        m = rsd.GalaxySpectrum(params=cosmo, z=0.55, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine, **kw)
+        m = rsd.GalaxySpectrum(params=cosmo, z=0.55, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine, interpolate=False, **kw)
         m.update(**upd)
         out[tag] = m
     return out
