@@ -70,7 +70,45 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     };
     // ---- one-loop tables: I00 I01 I11 I23 I32 I33 (all symmetric: 2 x the v > 0 half)
     {
-        auto geo = make_geometry(c, k_1loop.data(), ONELOOP_N, 1e5, cfg, grid);
+        // The 2-D integrals I00, I01, I11, I23, I32, I33 are smooth functions of k outside the BAO range: below k = 0.01
+        // (where they are < 1e-3 P_L anyway) only every 6th point of the reference's 1000-point grid is integrated, above
+        // k = 1.2 every 3rd, and the others are filled by 8-point Lagrange interpolation in ln k (k_oneloop_combine).  J_mn
+        // and P_L, one cheap matrix product, stay on the full grid.  482 of 1000 points carry 64 % of the nodes; the
+        // interpolation error is below the point-to-point noise of the quadrature itself (measured on the dense
+        // fixtures: tables unchanged to < 4e-6 for k <= 1, 3e-5 of |table| for k > 1 where 2 I + 6 k^2 J P_L cancels 140 x).
+        {
+            std::vector<char> keep(ONELOOP_N, 0);
+            int lo = 0, hi = ONELOOP_N - 1;
+            while (lo < ONELOOP_N - 1 && k_1loop[lo] < 0.01) lo++;
+            while (hi > 0 && k_1loop[hi] > 1.2) hi--;
+            for (int i = lo; i <= hi; i++) keep[i] = 1;
+            for (int i = lo; i >= 0; i -= 6) keep[i] = 1;
+            for (int i = hi; i < ONELOOP_N; i += 3) keep[i] = 1;
+            keep[0] = keep[ONELOOP_N - 1] = 1;
+            std::vector<double> ksub, xsub;
+            std::vector<int> pos;
+            for (int i = 0; i < ONELOOP_N; i++) if (keep[i]) { ksub.push_back(k_1loop[i]); xsub.push_back(std::log(k_1loop[i])); pos.push_back(i); }
+            n_1loop_sub = (int)ksub.size();
+            const int NP = 8;
+            std::vector<int> midx((size_t)ONELOOP_N*NP, 0);
+            std::vector<double> mw((size_t)ONELOOP_N*NP, 0.0);
+            for (int i = 0, j = 0; i < ONELOOP_N; i++) {
+                while (j < n_1loop_sub && pos[j] < i) j++;
+                if (keep[i]) { midx[(size_t)i*NP] = j; mw[(size_t)i*NP] = 1.0; continue; }
+                const double x = std::log(k_1loop[i]);
+                const int a = std::min(std::max(j - NP/2, 0), n_1loop_sub - NP);
+                for (int l = 0; l < NP; l++) {
+                    double w = 1.0;
+                    for (int m = 0; m < NP; m++) if (m != l) w *= (x - xsub[a + m])/(xsub[a + l] - xsub[a + m]);
+                    midx[(size_t)i*NP + l] = a + l;
+                    mw[(size_t)i*NP + l] = w;
+                }
+            }
+            d_olmap_idx.upload(midx, c.stream);
+            d_olmap_w.upload(mw, c.stream);
+            k_1loop_sub = ksub;
+        }
+        auto geo = make_geometry(c, k_1loop_sub.data(), n_1loop_sub, 1e5, cfg, grid);
         lap(0);
         std::vector<ColSpec> cols;
         for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
@@ -159,13 +197,24 @@ long long PTPlan::nodes_total() const
 }
 
 // ------------------------------------------------------------------ packing
-__global__ void k_oneloop_combine(int ncosmo, const double* __restrict__ op1 /*[c][1000][8]*/,
+__global__ void k_oneloop_combine(int ncosmo, int nsub, const double* __restrict__ op1 /*[c][nsub][8]*/,
+                                  const int* __restrict__ midx /*[1000][8]*/, const double* __restrict__ mw /*[1000][8]*/,
                                   const double* __restrict__ lin1 /*[c][3000]*/, const double* __restrict__ plk /*[c][1000]*/,
                                   const double* __restrict__ k1, double* __restrict__ ol /*[c][4][1000]*/)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
     if (i >= ONELOOP_N) return;
-    const double* a = op1 + ((size_t)c*ONELOOP_N + i)*8;
+    // the four 2-D integrals at k_i: computed there, or interpolated (8-point Lagrange in ln k) from the computed points
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* base = op1 + (size_t)c*nsub*8;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        const double w = mw[(size_t)i*8 + l];
+        if (w == 0.0) continue;
+        const double* r = base + (size_t)midx[(size_t)i*8 + l]*8;
+#pragma unroll
+        for (int t = 0; t < 4; t++) a[t] = fma(w, r[t], a[t]);
+    }
     const double* j = lin1 + (size_t)c*3*ONELOOP_N;
     const double k = k1[i], P = plk[(size_t)c*ONELOOP_N + i];
     double* o = ol + (size_t)c*4*ONELOOP_N;
@@ -250,7 +299,7 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
     }
 
     // ---- stage A: one-loop tables
-    s_op1.ensure((size_t)ntile*8*ONELOOP_N*8);
+    s_op1.ensure((size_t)(nc + 8)*n_1loop_sub*8);
     nodal_apply_diag(c, op_1loop, sp.tables.p, s_rowB.p, nc, s_op1.p);
     s_lin1.ensure((size_t)nc*3*ONELOOP_N);
     lin_1loop.apply(c, sp.tables.p, d_tabL.p, nc, s_lin1.p);
@@ -258,7 +307,8 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
     {
         dim3 g((ONELOOP_N + 255)/256, nc);
         k_plin_at<<<g, 256, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, ONELOOP_N, d_k1loop.p, s_plk.p);
-        k_oneloop_combine<<<g, 256, 0, s>>>(nc, s_op1.p, s_lin1.p, s_plk.p, d_k1loop.p, res.oneloop.p);
+        k_oneloop_combine<<<g, 256, 0, s>>>(nc, n_1loop_sub, s_op1.p, d_olmap_idx.p, d_olmap_w.p, s_lin1.p, s_plk.p, d_k1loop.p,
+                                            res.oneloop.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches += 2;
     }

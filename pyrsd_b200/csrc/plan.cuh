@@ -50,6 +50,11 @@ struct PTPlan {
     LinearOp lin_invq2_100;    // \int S/q^2 dq over [1e-5, 100] x 1/(10 pi^2)  (P_L^2 table)  -> Q3 / k^4
     LinearOp lin_kurt;         // 0.25/(2 pi^2) \int S/q^2 dq over [1e-5, 10]   (P22bar table)
     DevBuf<double> d_k1loop, d_kinterp;
+    // the subset of the one-loop grid on which the 2-D operator is integrated, and the interpolation map to all 1000 points
+    std::vector<double> k_1loop_sub;
+    int n_1loop_sub = 0;
+    DevBuf<int> d_olmap_idx;        // [1000][8]
+    DevBuf<double> d_olmap_w;       // [1000][8]
     // scratch
     DevBuf<double> s_op1, s_lin1, s_ik, s_mlp, s_mln, s_linmain, s_small, s_ol, s_plk;
     DevBuf<int> s_slot, s_rowA, s_rowB, s_tabidx;
