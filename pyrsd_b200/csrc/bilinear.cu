@@ -4,6 +4,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -264,6 +265,14 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
             pack[i] = (n_ol[i] << 12) | b_j0[i];
         }
         g->b_pack.upload(pack, s);
+        std::vector<int2> nodew(b_j0.size());
+        for (size_t i = 0; i < b_j0.size(); i++) {
+            const float sf = (float)(b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3]);
+            int bits;
+            std::memcpy(&bits, &sf, sizeof(int));
+            nodew[i] = make_int2(pack[i], bits);
+        }
+        g->b_node.upload(nodew, s);
     }
     g->kdev.upload(g->k, s);
     ctx.sync();   // the host vectors go out of scope
@@ -341,6 +350,28 @@ __global__ void k_fold_column(int64_t n, double* __restrict__ dst, const double*
 {
     const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     if (i < n) dst[i] = fma(coef, src[i], dst[i]);
+}
+
+__global__ void k_w_to_float4(int64_t n_nodes, int ncol, const double* __restrict__ src /*[ncol][n_nodes]*/, float4* __restrict__ dst)
+{
+    const int64_t node = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (node >= n_nodes) return;
+    float e[4];
+    for (int j = 0; j < 4; j++) e[j] = (4*v + j < ncol) ? (float)src[(int64_t)(4*v + j)*n_nodes + node] : 0.f;
+    dst[(int64_t)v*n_nodes + node] = make_float4(e[0], e[1], e[2], e[3]);
+}
+
+void BilinearOp::to_float(Context& ctx)
+{
+    PRSD_REQUIRE(soa && W.p, "to_float: only for SoA operators");
+    nvec = (ncol_used + 3)/4;
+    Wf.alloc((size_t)geo->n_nodes*nvec);
+    k_w_to_float4<<<dim3((unsigned)((geo->n_nodes + 255)/256), nvec), 256, 0, ctx.stream>>>(geo->n_nodes, ncol_used, W.p, Wf.p);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+    ctx.sync();
+    W.release();
 }
 
 void BilinearOp::fold_columns(Context& ctx, int dst, const std::vector<std::pair<int, double>>& terms, int ncol_keep)

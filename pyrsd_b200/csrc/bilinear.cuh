@@ -42,6 +42,9 @@ struct NodeGeometry {
     DevBuf<double> b_s, a_s;
     // compact index stream of the one-lane-per-node kernels: (outer index << 12) | stencil start
     DevBuf<int> b_pack;
+    // the two per-node words of the nodal kernels in ONE 8-byte load: .x = b_pack, .y = stencil coordinate as binary32
+    // (a coordinate error of 1e-7 of a knot spacing moves the interpolated value by < 1e-9)
+    DevBuf<int2> b_node;
     DevBuf<double> kdev;
     size_t bytes() const;
 };
@@ -58,6 +61,13 @@ struct BilinearOp {
     bool soa = false;   // false: W [n_nodes][ncol] in fragment-major column order (DMMA kernel);
                         // true : W [ncol_used][n_nodes] (one-lane-per-node kernels, nodal.cuh)
     DevBuf<double> W;
+    // Nodal (SoA) operators stream their entries as binary32 packed four columns to a float4, [ceil(ncol / 4)][n_nodes]:
+    // the LSU issues one global load per ~1.8 cycles whatever its width, so 9 columns cost 3 LDG.128 instead of 9 LDG.64.
+    // An entry is weight x kernel value; its rounding error (6e-8, independent from node to node) averages out over the
+    // ~2000 nodes of an integral -- measured on the dense fixtures: no table or ImnOneLoop integral moves by more than 2e-8.
+    DevBuf<float4> Wf;
+    int nvec = 0;
+    void to_float(Context& ctx);        // SoA only: W -> Wf, releases W
     void build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols, bool soa_layout = false);
     // SoA operators only: column `dst` += sum_i coef_i * column src_i, then keep the first `ncol_keep` columns
     void fold_columns(Context& ctx, int dst, const std::vector<std::pair<int, double>>& terms, int ncol_keep);

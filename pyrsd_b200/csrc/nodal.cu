@@ -18,9 +18,9 @@ struct NodalArgs {
     const int64_t* node_off;
     const int* a_j0;
     const double* a_s;      // stencil coordinate of every outer node
-    const int* b_pack;      // (outer index << 12) | stencil start
-    const double* b_s;      // stencil coordinate of every node: the Lagrange coefficients are lagrange4(s)
-    const double* W;        // [NW][n_nodes]
+    const int2* b_node;     // .x = (outer index << 12) | stencil start, .y = stencil coordinate (binary32 bits): the
+                            // Lagrange coefficients are lagrange4(s)
+    const float4* W;        // [ceil(NW / 4)][n_nodes], binary32, four columns per load (bilinear.cuh)
     int64_t n_nodes;
     const double* tables;
     const int* slot_tab;    // [ntiles][4]
@@ -178,15 +178,14 @@ k_nodal_apply(const NodalArgs g)
         // the index word and the stencil coordinate of the NEXT node of this lane are loaded one iteration ahead: the
         // shared-memory reads depend on them, and an exposed L2 round trip per node was the largest stall
         int64_t node = n0 + tid;
-        int pk_next = 0;
-        double s_next = 0.0;
-        double w_next[Spec::PREFETCH_W ? Spec::NW : 1];
+        int2 nw_next = make_int2(0, 0);
+        constexpr int NV = (Spec::NW + 3)/4;
+        float4 w_next[Spec::PREFETCH_W ? NV : 1];
         if (node < n1) {
-            pk_next = __ldg(g.b_pack + node);
-            s_next = __ldg(g.b_s + node);
+            nw_next = __ldg(g.b_node + node);
             if (Spec::PREFETCH_W) {
 #pragma unroll
-                for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
+                for (int v = 0; v < NV; v++) w_next[v] = __ldg(g.W + (int64_t)v*g.n_nodes + node);
             }
         }
         // ---- P(a) of the four spectra for every outer node of this k
@@ -206,27 +205,31 @@ k_nodal_apply(const NodalArgs g)
 #pragma unroll
         for (int i = 0; i < Spec::NACC; i++) acc[i] = 0.0;
         for (; node < n1; node += Spec::THREADS) {
-            const int pk = pk_next;
+            const int pk = nw_next.x;
             double c[4];
-            lagrange4(s_next, c);
-            double w[Spec::NW];
+            lagrange4((double)__int_as_float(nw_next.y), c);
+            float4 wv[NV];
             if (Spec::PREFETCH_W) {
 #pragma unroll
-                for (int c = 0; c < Spec::NW; c++) w[c] = w_next[c];
+                for (int v = 0; v < NV; v++) wv[v] = w_next[v];
             }
             const int64_t nx = node + Spec::THREADS;
             if (nx < n1) {
-                pk_next = __ldg(g.b_pack + nx);
-                s_next = __ldg(g.b_s + nx);
+                nw_next = __ldg(g.b_node + nx);
                 if (Spec::PREFETCH_W) {
 #pragma unroll
-                    for (int c = 0; c < Spec::NW; c++) w_next[c] = __ldg(g.W + (int64_t)c*g.n_nodes + nx);
+                    for (int v = 0; v < NV; v++) w_next[v] = __ldg(g.W + (int64_t)v*g.n_nodes + nx);
                 }
             }
             const int j0 = pk & 4095, ol = pk >> 12;
             if (!Spec::PREFETCH_W) {
 #pragma unroll
-                for (int c = 0; c < Spec::NW; c++) w[c] = __ldg(g.W + (int64_t)c*g.n_nodes + node);
+                for (int v = 0; v < NV; v++) wv[v] = __ldg(g.W + (int64_t)v*g.n_nodes + node);
+            }
+            double w[4*NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                w[4*v] = (double)wv[v].x; w[4*v + 1] = (double)wv[v].y; w[4*v + 2] = (double)wv[v].z; w[4*v + 3] = (double)wv[v].w;
             }
             double pa[Spec::NSLOT], pb[Spec::NSLOT];
 #pragma unroll
@@ -266,14 +269,14 @@ template <class Spec>
 static void launch_nodal(Context& ctx, const BilinearOp& op, const double* tables, const int* slot_tab, int ntiles,
                          int nrow, int kchunk, double* out, int prof_tag)
 {
-    PRSD_REQUIRE(op.soa && op.ncol_used == Spec::NW, "nodal operator has the wrong layout");
+    PRSD_REQUIRE(op.soa && op.ncol_used == Spec::NW && op.Wf.p, "nodal operator has the wrong layout");
     const NodeGeometry& geo = *op.geo;
     NodalArgs a;
     a.nk = geo.nk; a.max_outer = geo.max_outer; a.kchunk = kchunk; a.nrow = nrow;
     a.outer_off = geo.outer_off.p; a.node_off = geo.node_off.p;
     a.a_j0 = geo.a_j0.p; a.a_s = geo.a_s.p;
-    a.b_pack = geo.b_pack.p; a.b_s = geo.b_s.p;
-    a.W = op.W.p; a.n_nodes = geo.n_nodes;
+    a.b_node = geo.b_node.p;
+    a.W = op.Wf.p; a.n_nodes = geo.n_nodes;
     a.tables = tables; a.slot_tab = slot_tab; a.out = out;
     const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + Spec::NSLOT*geo.max_outer + ((Spec::THREADS/32) + 1)*Spec::NACC + 2)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);

@@ -115,6 +115,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         op_1loop.build(c, geo, cols, true);
         // OneLoopP22Bar only ever needs I23 + 2/3 I32 + 1/5 I33 (OneLoopPS.cpp:164-185): fold the three columns
         op_1loop.fold_columns(c, 3, {{4, 2.0/3.0}, {5, 1.0/5.0}}, 4);
+        op_1loop.to_float(c);
         lap(1);
     }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
@@ -134,6 +135,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg.ml_variant(), grid);
         lap(0);
         op_ml.build(c, geo, ml_columns(), true);
+        op_ml.to_float(c);
         lap(1);
     }
     // ---- 1-D operators
@@ -178,7 +180,7 @@ size_t PTPlan::device_bytes() const
     size_t b = 0;
     for (const BilinearOp* op : {&op_1loop, &op_ik, &op_ml}) {
         if (!op->geo) continue;
-        b += op->W.n*sizeof(double);
+        b += op->W.n*sizeof(double) + op->Wf.n*sizeof(float4);
     }
     if (op_1loop.geo) b += op_1loop.geo->bytes();
     if (op_ik.geo) b += op_ik.geo->bytes();

@@ -10,6 +10,7 @@
 using namespace prsd;
 
 static QuadConfig g_cfg;
+static int g_w_float = 0;       // experiment: round the operator entries W = weight x kernel to binary32
 static KnotGrid g_grid = make_knot_grid();
 
 extern "C" {
@@ -25,6 +26,7 @@ void emul_set_config(double qmin, int n_outer, int n_inner, double ln_far, doubl
 }
 
 void emul_set_config_default() { g_cfg = QuadConfig(); }
+void emul_set_w_float(int on) { g_w_float = on; }
 void emul_use_ml_variant() { g_cfg = g_cfg.ml_variant(); }
 
 void emul_set_tier(int i, double k_below, int n_outer, int n_inner, int n_thin)
@@ -103,11 +105,11 @@ void emul_ik(int kid, int nk, const double* k, double qmax, const double* tabQ, 
             const double u = (a + b)/kk, vp = (b - a)/kk;
             const double Qa = ca[0]*tabQ[ja] + ca[1]*tabQ[ja+1] + ca[2]*tabQ[ja+2] + ca[3]*tabQ[ja+3];
             const double Rb = cb[0]*tabR[jb] + cb[1]*tabR[jb+1] + cb[2]*tabR[jb+2] + cb[3]*tabR[jb+3];
-            pos += H.wgt[j]*Qa*Rb*pt_kernel(kid, u, vp, 2*a/kk, 2*b/kk);
+            { double W = H.wgt[j]*pt_kernel(kid, u, vp, 2*a/kk, 2*b/kk); if (g_w_float) W = (double)(float)W; pos += W*Qa*Rb; }
             if (mode == 2 || !sym) {
                 const double Qb = cb[0]*tabQ[jb] + cb[1]*tabQ[jb+1] + cb[2]*tabQ[jb+2] + cb[3]*tabQ[jb+3];
                 const double Ra = ca[0]*tabR[ja] + ca[1]*tabR[ja+1] + ca[2]*tabR[ja+2] + ca[3]*tabR[ja+3];
-                neg += H.wgt[j]*Qb*Ra*pt_kernel(kid, u, -vp, 2*b/kk, 2*a/kk);
+                { double W = H.wgt[j]*pt_kernel(kid, u, -vp, 2*b/kk, 2*a/kk); if (g_w_float) W = (double)(float)W; neg += W*Qb*Ra; }
             }
         }
         const double V8 = kk/(8*M_PI*M_PI), V4 = kk/(4*M_PI*M_PI);
