@@ -81,6 +81,10 @@ int prsd_spectra_get_oneloop(prsd_spectra* sp, double* out /*[ncosmo][4][1000]*/
  * domain (:362-367); y [batch][n] on shared x [n] */
 int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, const double* y, int nq,
                            const double* xq, double* out /*[batch][nq]*/);
+/* LinearSpline(x, y)(xq), and EvaluateDerivative when deriv != 0  [Spline.i:24, Spline.cpp:58-130]: y [batch][n] on shared
+ * abscissae, 0 outside the domain */
+int prsd_linear_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, const double* y, int nq, const double* xq,
+                            int deriv, double* out);
 
 /* ---- one-off evaluations with the call shapes of the pygcl drivers ------------------- */
 /* Imn(P_L)(k, m, n)  [Imn.i:8-14, Imn.cpp:142-189] */
@@ -129,6 +133,9 @@ int prsd_result_get(prsd_result* res, int what, double* out, long long n_expecte
 int prsd_fftlog(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
                 const double* a /*[batch][N]*/, double* out /*[batch][N]*/, double* kr_out);
 /* same with DEVICE pointers (asynchronous on the context's stream) */
+/* the same with FFTLog.Transform's direction argument: +1 forward, -1 backward (fftlog.f:523-527) */
+int prsd_fftlog_dir(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt, int direction,
+                    const double* a, double* out, double* kr_out);
 int prsd_fftlog_device(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
                        const double* d_in, double* d_out, double* kr_out);
 /* ComputeXiLM(l, m, k, pk, r, smoothing, FFTLOG) x scale  [CorrelationFunction.cpp:56-90];

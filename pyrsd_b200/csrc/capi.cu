@@ -560,6 +560,22 @@ int prsd_result_get(prsd_result* res, int what, double* out, long long n_expecte
 
 
 /* ------------------------------------------------------------------ FFTLog */
+int prsd_fftlog_dir(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt, int direction,
+                    const double* a, double* out, double* kr_out)
+{
+    return guarded(dev_of(ctx), [&] {
+        PRSD_REQUIRE(ctx && a && out, "null argument");
+        PRSD_REQUIRE(batch > 0, "FFTLog: empty batch");
+        auto plan = fftlog_plan(ctx->c, N, mu, q, dlnr, kr, kropt, direction);
+        DevBuf<double> din, dout((size_t)batch*N);
+        din.upload(a, (size_t)batch*N, ctx->c.stream);
+        fftlog_apply(ctx->c, *plan, batch, din.p, dout.p);
+        dout.download(out, (size_t)batch*N, ctx->c.stream);
+        ctx->c.sync();
+        if (kr_out) *kr_out = plan->kr;
+    });
+}
+
 int prsd_fftlog(prsd_ctx* ctx, int batch, int N, double mu, double q, double dlnr, double kr, int kropt,
                 const double* a, double* out, double* kr_out)
 {
@@ -1025,6 +1041,25 @@ int prsd_cubic_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, con
     });
 }
 
+
+/* LinearSpline(x, y)(xq) / EvaluateDerivative  [Spline.i:24, Spline.cpp:58-130] */
+int prsd_linear_spline_eval(prsd_ctx* ctx, int batch, int n, const double* x, const double* y, int nq, const double* xq, int deriv,
+                            double* out)
+{
+    return guarded(dev_of(ctx), [&] {
+        PRSD_REQUIRE(ctx && x && y && xq && out, "null argument");
+        PRSD_REQUIRE(batch > 0 && nq > 0 && n >= 2, "LinearSpline: empty request");
+        for (int i = 1; i < n; i++) PRSD_REQUIRE(x[i] > x[i - 1], "LinearSpline: abscissae must be increasing");
+        Context& c = ctx->c;
+        DevBuf<double> dx, dy, dq, dout((size_t)batch*nq);
+        dx.upload(x, n, c.stream);
+        dy.upload(y, (size_t)batch*n, c.stream);
+        dq.upload(xq, nq, c.stream);
+        linear_spline_dev(c, batch, n, dx.p, dy.p, nq, dq.p, deriv, dout.p);
+        dout.download(out, (size_t)batch*nq, c.stream);
+        c.sync();
+    });
+}
 
 /* ----------------------------------------------------- measurement support */
 int prsd_ctx_profile(prsd_ctx* ctx, int enable)

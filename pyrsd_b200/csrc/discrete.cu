@@ -120,6 +120,37 @@ k_xilm_discrete(int method, int l, int m, int nk, const double* __restrict__ k, 
     if (threadIdx.x == 0) out[(size_t)b*nr + ir] = scale*t;
 }
 
+// LinearSpline(X, Y)(x) / .EvaluateDerivative(x)  [Spline.i:24, Spline.cpp:58-130]: piecewise-linear interpolation by
+// binary search, 0 outside [X_0, X_{n-1}] like Spline::Evaluate (Spline.cpp:362-367)
+__global__ void __launch_bounds__(256)
+k_linear_spline(int n, const double* __restrict__ X, const double* __restrict__ Y, int nq, const double* __restrict__ xq,
+                int deriv, double* __restrict__ out)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= nq) return;
+    const double x = xq[i];
+    const double* y = Y + (size_t)b*n;
+    double v = 0.0;
+    if (x >= X[0] && x <= X[n - 1]) {
+        int lo = 0, hi = n - 1;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (X[mid] <= x) lo = mid; else hi = mid;
+        }
+        const double slope = (y[lo + 1] - y[lo])/(X[lo + 1] - X[lo]);
+        v = deriv ? slope : y[lo] + slope*(x - X[lo]);
+    }
+    out[(size_t)b*nq + i] = v;
+}
+
+void linear_spline_dev(Context& ctx, int batch, int n, const double* d_x, const double* d_y, int nq, const double* d_xq, int deriv,
+                       double* d_out)
+{
+    k_linear_spline<<<dim3((nq + 255)/256, batch), 256, 0, ctx.stream>>>(n, d_x, d_y, nq, d_xq, deriv, d_out);
+    PRSD_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
 void discrete_integrate_dev(Context& ctx, int method, int batch, int n, const double* d_x, const double* d_y, double* d_out)
 {
     PRSD_REQUIRE(method == 1 || method == 2, "discrete integration method must be 1 (Simpson) or 2 (trapezoid)");

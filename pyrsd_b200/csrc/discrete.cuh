@@ -11,4 +11,8 @@ void discrete_integrate_dev(Context& ctx, int method, int batch, int n, const do
 void xilm_discrete_dev(Context& ctx, int method, int batch, int l, int m, int nk, const double* d_k, const double* d_pk,
                        int nr, const double* d_r, double smoothing, double scale, double* d_out);
 
+// LinearSpline: y [batch][n] on shared abscissae x [n], queries xq [nq] -> out [batch][nq]; deriv != 0: the slope
+void linear_spline_dev(Context& ctx, int batch, int n, const double* d_x, const double* d_y, int nq, const double* d_xq, int deriv,
+                       double* d_out);
+
 } // namespace prsd

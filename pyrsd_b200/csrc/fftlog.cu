@@ -9,20 +9,21 @@
 namespace prsd {
 
 // --------------------------------------------------------------- plan cache
-struct FKey { int dev, N, kropt; double mu, q, dlnr, kr; };
+struct FKey { int dev, N, kropt, dir; double mu, q, dlnr, kr; };
 static bool operator==(const FKey& a, const FKey& b)
 {
-    return a.dev == b.dev && a.N == b.N && a.kropt == b.kropt && a.mu == b.mu && a.q == b.q && a.dlnr == b.dlnr && a.kr == b.kr;
+    return a.dev == b.dev && a.N == b.N && a.kropt == b.kropt && a.dir == b.dir && a.mu == b.mu && a.q == b.q && a.dlnr == b.dlnr && a.kr == b.kr;
 }
 static std::mutex g_mu;
 static std::list<std::pair<FKey, std::shared_ptr<FFTLogPlan>>> g_cache;
 
-std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt)
+std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt, int dir)
 {
+    PRSD_REQUIRE(dir == 1 || dir == -1, "FFTLog: direction must be +1 or -1");
     PRSD_REQUIRE(N >= 2 && N <= 8192, "FFTLog: N = %d outside [2, 8192]", N);
     PRSD_REQUIRE(dlnr != 0.0 && std::isfinite(dlnr), "FFTLog: dlnr must be non-zero");
     PRSD_REQUIRE(kr > 0, "FFTLog: kr must be positive");
-    FKey key{ctx.device, N, kropt, mu, q, dlnr, kr};
+    FKey key{ctx.device, N, kropt, dir, mu, q, dlnr, kr};
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto& e : g_cache) if (e.first == key) return e.second;
     auto p = std::make_shared<FFTLogPlan>();
@@ -31,6 +32,20 @@ std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q
     p->pow2 = (N & (N - 1)) == 0 && N >= 8;
     std::vector<double> re, im;
     fftlog_multipliers(N, mu, q, dlnr, p->kr, re, im);
+    if (dir == -1) {
+        // backward transform (fftlog.f:523-527, fhtq :644-784): the rotation by the phase of u_m is the SAME, its
+        // amplitude divides instead of multiplying (u_m -> u_m / |u_m|^2, m = 0 and the Nyquist term -> 1 / u, with
+        // 0 -> 0 for the singular m = 0 case), and both power-law biases change sign (q -> -q in the bias factors only)
+        const int nh = N/2;
+        re[0] = re[0] == 0.0 ? 0.0 : 1.0/re[0];
+        for (int m = 1; m <= nh; m++) {
+            if (m == nh && N % 2 == 0) { re[m] = 1.0/re[m]; im[m] = 0.0; continue; }
+            const double a2 = re[m]*re[m] + im[m]*im[m];
+            re[m] /= a2;
+            im[m] /= a2;
+        }
+        p->q = -q;
+    }
     p->ure.upload(re, ctx.stream);
     p->uim.upload(im, ctx.stream);
     ctx.sync();

@@ -17,7 +17,8 @@ namespace prsd {
 
 struct FFTLogPlan {
     int N = 0;
-    double mu = 0, q = 0, dlnr = 0, kr = 1;     // kr AFTER the optional low-ringing adjustment
+    double mu = 0, q = 0, dlnr = 0, kr = 1;     // kr AFTER the optional low-ringing adjustment; q = the exponent of the
+                                                // bias factors (-q of the multipliers for a backward plan)
     bool pow2 = false;
     DevBuf<double> ure, uim;     // multipliers, m = 0 .. N/2
     DevBuf<double> g;            // real-space circular kernel g[d], d = 0 .. N-1 (built on demand)
@@ -25,8 +26,8 @@ struct FFTLogPlan {
     void build_g(Context& ctx);
 };
 
-// cached per (device, N, mu, q, dlnr, kr, kropt)
-std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt);
+// cached per (device, N, mu, q, dlnr, kr, kropt, dir); dir = -1: the backward transform (FFTLog.Transform(a, -1))
+std::shared_ptr<FFTLogPlan> fftlog_plan(Context& ctx, int N, double mu, double q, double dlnr, double kr, int kropt, int dir = 1);
 
 // plan with caller-supplied multipliers U_m, m = 0 .. N/2 (U_{N/2} real), no bias: out[i] = (1/N) sum_m F_m U_m
 // exp(-2 pi i m (i + 1) / N) with F = DFT of the input -- the mcfit-style transforms of transfer.cu; not cached

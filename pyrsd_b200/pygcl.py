@@ -728,14 +728,18 @@ class FFTLog(object):
         self._kr = None
 
     def Transform(self, a, direction=1):
-        if direction != 1:
-            raise NotImplementedError("only the forward transform is used by the hot path")
+        if direction not in (1, -1):
+            raise ValueError("FFTLog.Transform: direction must be +1 or -1")
         a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
         batch = a.reshape(-1, self.N)
         out = np.empty_like(batch)
         kr = C.c_double()
-        N.check(_L().prsd_fftlog(N.default_context().ptr, batch.shape[0], self.N, self.mu, self.q, self.dlnr, self._kr_in,
-                                 self.kropt, batch, out, C.byref(kr)))
+        L = _L()
+        L.prsd_fftlog_dir.argtypes = [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                      N._dp, N._dp, C.POINTER(C.c_double)]
+        L.prsd_fftlog_dir.restype = C.c_int
+        N.check(L.prsd_fftlog_dir(N.default_context().ptr, batch.shape[0], self.N, self.mu, self.q, self.dlnr, self._kr_in,
+                                  self.kropt, int(direction), batch, out, C.byref(kr)))
         self._kr = kr.value
         return out.reshape(a.shape)
 
@@ -743,6 +747,32 @@ class FFTLog(object):
         if self._kr is None:
             self.Transform(np.zeros(self.N))
         return self._kr
+
+
+class LinearSpline(object):
+    """``LinearSpline(x, y)`` (Spline.i:24, Spline.cpp:58-130): piecewise-linear, zero outside the domain"""
+    def __init__(self, x, y):
+        self._x, self._y = N.as_f64(x), N.as_f64(y)
+        if len(self._x) != len(self._y) or len(self._x) < 2:
+            raise ValueError("LinearSpline needs two arrays of the same length >= 2")
+
+    def _eval(self, xq, deriv):
+        xa, scalar = _scalar_or_array(xq)
+        out = np.empty((1, len(xa)))
+        L = _L()
+        L.prsd_linear_spline_eval.argtypes = [_vp, C.c_int, C.c_int, N._dp, N._dp, C.c_int, N._dp, C.c_int, N._dp]
+        L.prsd_linear_spline_eval.restype = C.c_int
+        N.check(L.prsd_linear_spline_eval(N.default_context().ptr, 1, len(self._x), self._x, self._y.reshape(1, -1), len(xa), xa,
+                                          int(deriv), out))
+        return _ret(out[0], scalar)
+
+    def __call__(self, xq):
+        return self._eval(xq, 0)
+
+    Evaluate = __call__
+
+    def EvaluateDerivative(self, xq):
+        return self._eval(xq, 1)
 
 
 class CubicSpline(object):

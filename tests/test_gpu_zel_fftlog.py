@@ -162,3 +162,29 @@ def test_discrete_quadratures_vs_oracle(oracle):
         assert np.max(np.abs(mine - oracle.pk_to_xi(2, k, pk, r, 0.25, method))) < 1e-11*np.max(np.abs(mine))
     with pytest.raises(Exception):
         pygcl.ComputeXiLM(5, 2, k, pk, r, 0.5, pygcl.IntegrationMethods.SIMPS)     # l = 5 unsupported (:104-107)
+
+
+def test_fftlog_backward_and_linear_spline(oracle):
+    """FFTLog.Transform(a, -1) against the oracle's backward transform (fftlog.f:523-527), forward o backward = identity
+    for a biased transform, and LinearSpline (Spline.i:24) against its definition"""
+    from pyrsd_b200 import pygcl
+    rng = np.random.default_rng(8)
+    for (N, mu, q) in [(1024, 0.5, 0.0), (2048, 2.5, 0.4), (512, 1.5, -0.3), (300, 0.5, 0.2)]:
+        dlnr = np.log(1e7)/N
+        a = rng.normal(size=(2, N))
+        F = pygcl.FFTLog(N, dlnr, mu, q, 1.0, 1)
+        back = F.Transform(a, -1)
+        for i in range(2):
+            ref, _ = oracle.fftlog(a[i], dlnr, mu, q, 1.0, 1, direction=-1)
+            assert np.max(np.abs(back[i] - ref)) < 1e-10*np.max(np.abs(ref)), (N, mu, q)
+        rt = F.Transform(F.Transform(a), -1)
+        assert np.max(np.abs(rt - a)) < 1e-9*np.max(np.abs(a)), (N, mu, q)
+    x = np.sort(rng.uniform(0, 10, 40))
+    y = rng.normal(size=40)
+    S = pygcl.LinearSpline(x, y)
+    xq = rng.uniform(x[0], x[-1], 200)
+    assert np.max(np.abs(S(xq) - np.interp(xq, x, y))) < 1e-13
+    assert S(x[0] - 1.0) == 0.0 and S(x[-1] + 1.0) == 0.0
+    i = np.searchsorted(x, xq, side='right') - 1
+    assert np.allclose(S.EvaluateDerivative(xq), (y[i + 1] - y[i])/(x[i + 1] - x[i]), rtol=1e-12)
+    assert isinstance(S(0.5*(x[3] + x[4])), float)
