@@ -38,7 +38,7 @@ struct NodalArgs {
 //   10,11 (L,dv): h03 h04 | 12,13 (dv,dv) | 14..16 (L,vv): f23 f32 f33 | 17,18 (vv,vv): f23 f33
 struct SpecML {
     static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 9, NOUT = 21, THREADS = NL_THREADS;
-    static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
+    static const bool PREFETCH_W = false;    // W one iteration ahead: no gain here (1.453 vs 1.456 ms, 128 registers)
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
         const double La = pa[0], Da = pa[1], Va = pa[2], Wa = pa[3];
@@ -106,7 +106,7 @@ struct SpecDiag {
     static const int NC = 4;      // I00, I01, I11 and P22bar = I23 + 2/3 I32 + 1/5 I33 (combined in W at build time)
     static const int NSLOT = DIAG_R, MINB = DIAG_R <= 3 ? 3 : (DIAG_R <= 4 ? 2 : 1), NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
     static const int THREADS = DIAG_R <= 4 ? NL_THREADS : 2*NL_THREADS;
-    static const bool PREFETCH_W = false;     // measured slower (register pressure): ImnOneLoop 1.26 -> 1.55 ms, one-loop 1.22 -> 1.31 ms
+    static const bool PREFETCH_W = true;     // the float4 of W one iteration ahead: 0.935 -> 0.907 ms (one register quad)
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
 #pragma unroll
