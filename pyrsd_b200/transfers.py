@@ -407,7 +407,12 @@ class WindowFunctionTransfer(GriddedMultipoleTransfer):
         leading walker axis) on ``k_out`` if given, else on the zero-padded grid ``self.k_pad``; device tensors
         come back as [nw][nell][len(k)]"""
         if extrap:
-            raise NotImplementedError("only extrap=False (zero padding, the reference's default) is implemented")
+            # the reference passes `extrap` to mcfit, whose power-law padding is f[-1] (f[-1] / f[-2])^j (extern/mcfit/
+            # mcfit.py:170-178); this transfer zero-pads P_ell from kmax to 100 h/Mpc first (transfers/window.py:84-92), so
+            # f[-1] / f[-2] = 0 / 0 and every output of the reference is NaN (checked: profiles/r02_summary.md).  There is
+            # nothing to be equal to.
+            raise NotImplementedError("extrap=True is not meaningful for WindowFunctionTransfer: the reference's power-law "
+                                      "padding divides 0 / 0 on the zero-padded high-k tail and returns NaN everywhere")
         op = self._operator()
         p, multi, dev = _prepare(power, self.grid.shape)
         nw, nell, Nk, Npad = p.shape[0], len(self.ells), self.grid.Nk, len(self.k_pad)
