@@ -177,12 +177,13 @@ int prsd_zeldovich(prsd_ctx* ctx, int nrow, const double* X0, const double* XX, 
  *   [16..25] HZPT P00/P01 parameters, [26..34] HZPT P11, [35..54] HZPT Phm
  * kmodel: the model's spline grid self.k (numpy.logspace(log10 kmin, log10 kmax, Nk));
  * k_interp: the PT interpolation grid of the plan.
- * Walker parameters par [nw][48]:
+ * Walker parameters par [nw][56]:
  *   0 sigma8_z, 1 f, 2 alpha_par, 3 alpha_perp, 4 alpha_drag, 5..8 b1_cA b1_cB b1_sA b1_sB, 9 fs, 10 fcB,
  *   11 fsB, 12 sigma_c, 13 sigma_sA, 14 sigma_sB, 15 NcBs, 16 NsBsB, 17 f_so, 18 sigma_so,
  *   19 sigma_v (<= 0: sigma_lin), 20 D(z), 21 sigma8 (cosmo.sigma8()),
  *   22 + 4 kind + bias: nonlinear biases, kind = b2_00_a, b2_00_b, b2_00_c, b2_00_d, b2_01_a, b2_01_b
  *   evaluated at the four linear biases (host inputs: Gaussian-process fits in the reference).
+ *   46..49 sigma_v of the four biases (`vel_disp_from_sims`, power_biased.py:268-286; <= 0: sigma_v), 50..55 unused.
  * stoch [nw][10][20]: stochasticity Lambda(k) of the 10 (b1, b1_bar) pairs on 20 log-spaced k between
  *   the ends of kmodel (power_biased.py:342-366), pair order cAcA cAcB cBcB cAsA cAsB cBsA cBsB sAsA sAsB sBsB.
  * cmap [nw] (NULL = identity): cosmology (row of sp / res) each walker uses.
@@ -195,6 +196,16 @@ int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
                       const double* par, const double* stoch, int npts, const double* k, const double* mu,
                       double* out);
 /* k, mu, out are DEVICE pointers; returns after the kernels completed */
+/* correct_mu2 / correct_mu4 (power_biased.py:462-520): additive corrections of the P[mu^2], P[mu^4] spline knots,
+ * corr [nw][10 pairs][2][nkm] (host); used by the following calls with the same nw; corr == NULL clears */
+int prsd_galaxy_set_mu_corrections(prsd_galaxy* g, int nw, const double* corr);
+/* use_mean_bias (power_biased.py:219-237): both tracers of pair p of walker w carry ovr[w][p][0] = sqrt(b1 b1_bar);
+ * ovr[w][p][1..6] = b2_00_a, b2_00_b, b2_00_c, b2_00_d, b2_01_a, b2_01_b at that bias, [7] = halo sigma_v there (<= 0:
+ * sigma_v).  ovr [nw][10][8] (host); used by the following calls with the same nw; ovr == NULL clears */
+int prsd_galaxy_set_pair_overrides(prsd_galaxy* g, int nw, const double* ovr);
+/* SimLoaderMixin._load / _unload (rsd/sim_loader.py:44-75): loaded [4][nkm] (host) on the model grid kmodel, rows
+ * Pdv, P00_mu0, P01_mu2, P11_mu4; bit j of mask set = row j replaces the model's term for every walker; mask == 0 clears */
+int prsd_galaxy_set_loaded(prsd_galaxy* g, unsigned mask, const double* loaded);
 int prsd_galaxy_power_device(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,
                              const double* par, const double* stoch, int npts, const double* d_k,
                              const double* d_mu, double* d_out);

@@ -781,6 +781,25 @@ int prsd_galaxy_power_async(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, 
     });
 }
 
+int prsd_galaxy_set_mu_corrections(prsd_galaxy* g, int nw, const double* corr)
+{
+    return guarded(dev_of(g), [&] { PRSD_REQUIRE(g, "null argument"); g->g.set_mu_corrections(nw, corr); });
+}
+
+int prsd_galaxy_set_pair_overrides(prsd_galaxy* g, int nw, const double* ovr)
+{
+    return guarded(dev_of(g), [&] { PRSD_REQUIRE(g, "null argument"); g->g.set_pair_overrides(nw, ovr); });
+}
+
+int prsd_galaxy_set_loaded(prsd_galaxy* g, unsigned mask, const double* loaded)
+{
+    return guarded(dev_of(g), [&] {
+        PRSD_REQUIRE(g, "null argument");
+        PRSD_REQUIRE(mask < 16u, "mask: bits 0..3 = Pdv, P00_mu0, P01_mu2, P11_mu4");
+        g->g.set_loaded(mask, loaded);
+    });
+}
+
 int prsd_galaxy_wait(prsd_galaxy* g)
 {
     return guarded(dev_of(g), [&] { PRSD_REQUIRE(g, "null argument"); g->g.wait(); });

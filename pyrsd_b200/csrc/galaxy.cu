@@ -40,7 +40,8 @@ enum {
 // ---- walker parameter slots
 enum {
     W_S8Z = 0, W_F, W_APAR, W_APERP, W_ADRAG, W_B1 = 5 /* cA cB sA sB */, W_FS = 9, W_FCB, W_FSB, W_SIGC, W_SIGSA,
-    W_SIGSB, W_NCBS, W_NSBSB, W_FSO, W_SIGSO, W_SIGV, W_D, W_S80, W_B2 = 22 /* [6 kinds][4 biases] */, W_END = 46
+    W_SIGSB, W_NCBS, W_NSBSB, W_FSO, W_SIGSO, W_SIGV, W_D, W_S80, W_B2 = 22 /* [6 kinds][4 biases] */,
+    W_SIGVH = 46 /* sigma_v of the four biases (vel_disp_from_sims), <= 0: sigma_v */, W_END = 50
 };
 
 // ------------------------------------------------- PT tables on the model grid
@@ -114,6 +115,7 @@ __global__ void k_gal_base(GalDev G, const double* __restrict__ km, const int* _
                            const double* __restrict__ par, const double* __restrict__ ptspl,
                            const double* __restrict__ plin_m, const double* __restrict__ olspl,
                            const double* __restrict__ scal, const double* __restrict__ zel1, const double* __restrict__ zel2,
+                           const double* __restrict__ loaded /*[GAL_NLOAD][nkm] or NULL*/, unsigned loaded_mask,
                            double* __restrict__ base)
 {
     const int w = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -196,6 +198,13 @@ __global__ void k_gal_base(GalDev G, const double* __restrict__ km, const int* _
             Pvv = f*f*((g - P00_z0)/zs2 + P00_hz);
         } else Pvv = f*f*norm*(PL0 + norm*OL(2));
     }
+    // user-loaded terms replace the model's (SimLoaderMixin, rsd/sim_loader.py:44-75; dm/P00.py, P01.py, P11.py, power_dm.py:862-863)
+    if (loaded_mask) {
+        if (loaded_mask & 1u) Pdv = loaded[0*nkm + i];
+        if (loaded_mask & 2u) P00 = loaded[1*nkm + i];
+        if (loaded_mask & 4u) P01 = loaded[2*nkm + i];
+        if (loaded_mask & 8u) P11mu4 = loaded[3*nkm + i];
+    }
     double* o = base + (size_t)w*NB*nkm + i;
     const double f2 = f*f, f3 = f2*f, f4 = f2*f2;
     o[B_PLIN*nkm] = Plin;
@@ -234,7 +243,9 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
               int mband, const double* __restrict__ Mb /*[mband][nkm]*/, const int* __restrict__ mlo,
               const int* __restrict__ cmap,
               const double* __restrict__ par, const double* __restrict__ stoch, const double* __restrict__ scal,
-              const double* __restrict__ base, double* __restrict__ pairspl)
+              const double* __restrict__ base, const double* __restrict__ corr /*[nw][10][2][nkm] or NULL*/,
+              const double* __restrict__ pairovr /*[nw][10][GAL_NPAIROVR] or NULL*/,
+              double* __restrict__ pairspl)
 {
     extern __shared__ double sm_gm[];
     const int nkm = G.nkm;
@@ -247,13 +258,21 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
     const double* p = par + (size_t)w*GAL_NPAR;
     const double* B = base + (size_t)w*NB*nkm;
     const int ia = c_pair_a[pr], ib = c_pair_b[pr];
-    const double b1 = p[W_B1 + ia], b1b = p[W_B1 + ib];
-    auto b2 = [&](int kind, int which) { return p[W_B2 + kind*4 + which]; };   // kind: 00_a 00_b 00_c 00_d 01_a 01_b
+    // use_mean_bias (power_biased.py:219-237): both tracers of a pair carry the geometric-mean bias, and every quantity the
+    // reference evaluates at _ib1 / _ib1_bar (nonlinear biases, halo velocity dispersion) is handed in per pair
+    const double* ov = pairovr ? pairovr + ((size_t)w*GAL_NPAIR + pr)*GAL_NPAIROVR : nullptr;
+    const double b1 = ov ? ov[0] : p[W_B1 + ia], b1b = ov ? ov[0] : p[W_B1 + ib];
+    // kind: 00_a 00_b 00_c 00_d 01_a 01_b; which: bias index of the tracer
+    auto b2 = [&](int kind, int which) { return ov ? ov[1 + kind] : p[W_B2 + kind*4 + which]; };
     const double f = p[W_F], s8z = p[W_S8Z];
     const double norm = (s8z/p[W_S80])*(s8z/p[W_S80]);
     const double sig_lin = sqrt(norm*scal[(size_t)c*4 + 0]);
     const double sigv = p[W_SIGV] > 0.0 ? p[W_SIGV] : sig_lin;   // sigma_v defaults to sigma_lin (power_dm.py:454-460)
-    const double sig2 = sigv*sigv, sig2b = sigv*sigv;            // sigmav_halo = sigmav_halo_bar = sigma_v
+    // sigmav_halo / sigmav_halo_bar (power_biased.py:268-286): sigma_v, or -- vel_disp_from_sims -- the simulation fit at the
+    // bias of each tracer, handed in per bias
+    const double sva0 = ov ? ov[7] : p[W_SIGVH + ia], svb0 = ov ? ov[7] : p[W_SIGVH + ib];
+    const double sva = sva0 > 0.0 ? sva0 : sigv, svb = svb0 > 0.0 ? svb0 : sigv;
+    const double sig2 = sva*sva, sig2b = svb*svb;
     const double vkurt = norm*norm*scal[(size_t)c*4 + 1];
     const double bs = G.cfg.use_tidal_bias ? -2.0/7.0*(b1 - 1.0) : 0.0;
     const double bsb = G.cfg.use_tidal_bias ? -2.0/7.0*(b1b - 1.0) : 0.0;
@@ -327,7 +346,14 @@ k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict_
         const double mu4 = P11ss_mu4 + P02ss_mu4 + P12ss_mu4 + P03ss_mu4 + P22ss_mu4 + P13ss_mu4 + P04ss_mu4;
         // P[mu^6] (power_biased.py:522-528; biased/P12.py:24-45)
         const double mu6 = B[B_MU6A*nkm + i] - 0.5*(b1 + b1b)*B[B_I30F3*nkm + i];
-        Y[i] = mu0; Y[nkm + i] = mu2; Y[2*nkm + i] = mu4; Y[3*nkm + i] = mu6;
+        // correct_mu2 / correct_mu4 (power_biased.py:462-520): simulation-calibrated residuals added to the knots
+        double cm2 = 0.0, cm4 = 0.0;
+        if (corr) {
+            const double* cr = corr + ((size_t)w*GAL_NPAIR + pr)*2*nkm;
+            cm2 = cr[i];
+            cm4 = cr[nkm + i];
+        }
+        Y[i] = mu0; Y[nkm + i] = mu2 + cm2; Y[2*nkm + i] = mu4 + cm4; Y[3*nkm + i] = mu6;
     }
     __syncthreads();
     // not-a-knot splines of the four moments on the model grid (the reference's RSDSpline on self.k).  The second
@@ -953,9 +979,12 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         }
         ProfScope prof_gal(c, PROF_GALAXY);
         k_gal_base<<<dim3((nkm + 127)/128, n), 128, 0, s>>>(G, d_km.p, cm, pr, ptspl.p, plin_m.p, sp.oneloop_spl.p,
-                                                            pt.scalars.p, z1, z2, bs);
+                                                            pt.scalars.p, z1, z2, loaded_mask ? d_loaded.p : nullptr,
+                                                            loaded_mask, bs);
         k_gal_moments<<<dim3(GAL_NPAIR, n), 128, smem_mom, s>>>(G, d_km.p, d_stE.p, mom_band, d_momE.p, d_momJ.p, cm, pr, st,
-                                                                pt.scalars.p, bs, ps);
+                                                                pt.scalars.p, bs,
+                                                                (corr_nw == nw && d_corr.p) ? d_corr.p + (size_t)w0*GAL_NPAIR*2*nkm : nullptr,
+                                                                (ovr_nw == nw && d_ovr.p) ? d_ovr.p + (size_t)w0*GAL_NPAIR*GAL_NPAIROVR : nullptr, ps);
         k_gal_groups<<<dim3((16*nkm + 255)/256, n), 256, 0, s>>>(nkm, pr, ps, gs, gc);
         c.launches += 3;
         if (npts > 0) {
@@ -993,6 +1022,30 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         copy_ticket++;
     }
     if (sync) wait();
+}
+
+void GalaxyModel::set_mu_corrections(int nw, const double* h_corr)
+{
+    if (!h_corr || nw <= 0) { corr_nw = 0; return; }
+    d_corr.upload(h_corr, (size_t)nw*GAL_NPAIR*2*nkm, ctx->stream);
+    ctx->sync();
+    corr_nw = nw;
+}
+
+void GalaxyModel::set_pair_overrides(int nw, const double* h_ovr)
+{
+    if (!h_ovr || nw <= 0) { ovr_nw = 0; return; }
+    d_ovr.upload(h_ovr, (size_t)nw*GAL_NPAIR*GAL_NPAIROVR, ctx->stream);
+    ctx->sync();
+    ovr_nw = nw;
+}
+
+void GalaxyModel::set_loaded(unsigned mask, const double* h_loaded)
+{
+    if (!h_loaded || !mask) { loaded_mask = 0; return; }
+    d_loaded.upload(h_loaded, (size_t)GAL_NLOAD*nkm, ctx->stream);
+    ctx->sync();
+    loaded_mask = mask & 15u;
 }
 
 void GalaxyModel::wait()

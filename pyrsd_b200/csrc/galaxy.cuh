@@ -17,9 +17,11 @@
 
 namespace prsd {
 
-static const int GAL_NPAR = 48;        // doubles per walker, see include/pyrsd_b200.h
+static const int GAL_NPAR = 56;        // doubles per walker, see include/pyrsd_b200.h
 static const int GAL_NPAIR = 10;
 static const int GAL_NSTOCH = 20;      // GP_NK of power_biased.py:24
+static const int GAL_NPAIROVR = 8;     // per-pair overrides of use_mean_bias: mean b1, 6 nonlinear biases, halo sigma_v
+static const int GAL_NLOAD = 4;        // loadable dark-matter terms: Pdv, P00_mu0, P01_mu2, P11_mu4 (rsd/sim_loader.py:9)
 
 struct GalaxyConfig {
     int max_mu;                 // 0, 2, 4 or 6
@@ -81,6 +83,21 @@ struct GalaxyModel {
     DevBuf<double> d_stE, d_momE;
     DevBuf<int> d_momJ;
     int mom_band = 0;
+    // optional additive corrections of the P[mu^2], P[mu^4] knots of every (walker, pair): [nw][10][2][nkm], used by the
+    // power / poles calls with the same number of walkers until cleared (correct_mu2 / correct_mu4 of the reference)
+    DevBuf<double> d_corr;
+    int corr_nw = 0;
+    void set_mu_corrections(int nw, const double* h_corr);      // h_corr == NULL clears
+    // use_mean_bias (power_biased.py:219-237): [nw][10][GAL_NPAIROVR] = sqrt(b1 b1_bar), b2_00_{a,b,c,d}, b2_01_{a,b} and the
+    // halo sigma_v (<= 0: sigma_v) at that bias; same life cycle as the corrections
+    DevBuf<double> d_ovr;
+    int ovr_nw = 0;
+    void set_pair_overrides(int nw, const double* h_ovr);       // h_ovr == NULL clears
+    // user-loaded dark-matter terms on the model grid (SimLoaderMixin._load, rsd/sim_loader.py:56-66): [GAL_NLOAD][nkm],
+    // bit j of the mask = row j (Pdv, P00_mu0, P01_mu2, P11_mu4) replaces the model's term for every walker
+    DevBuf<double> d_loaded;
+    unsigned loaded_mask = 0;
+    void set_loaded(unsigned mask, const double* h_loaded);     // mask == 0 clears
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_event = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};      // end of the device-to-host copies of the last two power() calls

@@ -19,7 +19,9 @@ from . import pygcl
 
 INTERP_KMIN = 5e-6      # pyRSD/rsd/__init__.py:3-4
 INTERP_KMAX = 1.0
-NPAR = 48
+NPAR = 56
+NPAIROVR = 8
+LOADABLE = ('Pdv', 'P00_mu0', 'P01_mu2', 'P11_mu4')     # rows of prsd_galaxy_set_loaded
 NPAIR = 10
 NSTOCH = 20
 
@@ -47,6 +49,11 @@ def _L():
         L.prsd_galaxy_chi2.argtypes = [_vp, _vp, _vp, i, _vp, _dp, _dp, i, _dp, i, _ip, i, _dp, _dp, _dp, _vp]
         L.prsd_chi2.argtypes = [_vp, i, i, _vp, _dp, _dp, _dp, i]
         L.prsd_chi2.restype = i
+        L.prsd_galaxy_set_mu_corrections.argtypes = [_vp, i, _vp]
+        L.prsd_galaxy_set_pair_overrides.argtypes = [_vp, i, _vp]
+        L.prsd_galaxy_set_loaded.argtypes = [_vp, C.c_uint, _vp]
+        for name in ('prsd_galaxy_set_mu_corrections', 'prsd_galaxy_set_pair_overrides', 'prsd_galaxy_set_loaded'):
+            getattr(L, name).restype = i
         for name in ('prsd_galaxy_config_default', 'prsd_galaxy_create', 'prsd_galaxy_destroy', 'prsd_galaxy_power',
                      'prsd_galaxy_power_device', 'prsd_galaxy_moments', 'prsd_galaxy_poles', 'prsd_galaxy_poles_device',
                      'prsd_galaxy_chi2'):
@@ -151,6 +158,32 @@ class PTEngine(object):
             g.nkm = len(kmodel)
             self._galaxies[key] = g
         return self._galaxies[key]
+
+    def galaxy_options(self, gal, nw=0, mu_corrections=None, pair_overrides=None, loaded=None):
+        """optional inputs of the following galaxy_* calls on ``gal`` with ``nw`` walkers (None clears each):
+        ``mu_corrections`` [nw][10][2][nkm] added to the P[mu^2], P[mu^4] knots (correct_mu2 / correct_mu4),
+        ``pair_overrides`` [nw][10][8] (use_mean_bias), ``loaded`` dict name -> [nkm] of user-loaded dark-matter terms"""
+        L = _L()
+        if mu_corrections is None:
+            N.check(L.prsd_galaxy_set_mu_corrections(gal.ptr, 0, None))
+        else:
+            a = np.ascontiguousarray(mu_corrections, dtype=np.float64).reshape(nw, NPAIR, 2, gal.nkm)
+            N.check(L.prsd_galaxy_set_mu_corrections(gal.ptr, nw, a.ctypes.data_as(_vp)))
+        if pair_overrides is None:
+            N.check(L.prsd_galaxy_set_pair_overrides(gal.ptr, 0, None))
+        else:
+            a = np.ascontiguousarray(pair_overrides, dtype=np.float64).reshape(nw, NPAIR, NPAIROVR)
+            N.check(L.prsd_galaxy_set_pair_overrides(gal.ptr, nw, a.ctypes.data_as(_vp)))
+        if not loaded:
+            N.check(L.prsd_galaxy_set_loaded(gal.ptr, 0, None))
+        else:
+            a = np.zeros((len(LOADABLE), gal.nkm))
+            mask = 0
+            for name, v in loaded.items():
+                j = LOADABLE.index(name)
+                a[j] = v
+                mask |= 1 << j
+            N.check(L.prsd_galaxy_set_loaded(gal.ptr, mask, a.ctypes.data_as(_vp)))
 
     def galaxy_power(self, gal, spectra, result, par, stoch, k, mu, cmap=None):
         """P(k, mu) of nw walkers at paired (k, mu) points -> [nw][npts]"""
@@ -401,22 +434,23 @@ class GalaxySpectrum(object):
                'fsB', 'sigma_c', 'sigma_s', 'sigma_sA', 'sigma_sB', 'NcBs', 'NsBsB', 'N', 'f_so', 'sigma_so', 'sigma_v',
                'sigma_v2', 'sigma_bv2', 'sigma_bv4')
 
+    use_mean_bias = vel_disp_from_sims = correct_mu2 = correct_mu4 = False
+    Pdv_model_type = 'jennings'
+    vel_disp_fitter = Pmu2_correction = Pmu4_correction = Pdv_sim_cosmo = None
+    _loaded_data = {}
+
     def __init__(self, kmin=1e-3, kmax=0.5, Nk=200, z=0., params=None, include_2loop=False, transfer_fit="CLASS",
                  max_mu=4, interpolate=True, k0_low=5e-3, Pdv_model_type='jennings', fog_model='modified_lorentzian',
                  use_so_correction=False, use_tidal_bias=False, use_mean_bias=False, vel_disp_from_sims=False,
                  correct_mu2=False, correct_mu4=False, use_vlah_biasing=True, b2_00=None, b2_01=None,
-                 stochasticity=None, engine=None, **kwargs):
+                 stochasticity=None, vel_disp_fitter=None, Pmu2_correction=None, Pmu4_correction=None, Pdv_sim_cosmo=None,
+                 engine=None, **kwargs):
         if not isinstance(params, pygcl.Cosmology):
             raise TypeError("`params` must be a pyrsd_b200.pygcl.Cosmology (the linear T(k) is a host input)")
         if include_2loop:
             raise ValueError("`include_2loop` is forced to False for biased tracers (power_biased.py:47)")
-        if Pdv_model_type != 'jennings':
-            raise NotImplementedError("only Pdv_model_type='jennings' (the reference default) is available")
-        if use_mean_bias or vel_disp_from_sims or correct_mu2 or correct_mu4:
-            raise NotImplementedError("use_mean_bias / vel_disp_from_sims / correct_mu2 / correct_mu4 are not wired into the "
-                                      "assembly kernels; the Gaussian-process fits they read are available as "
-                                      "pyrsd_b200.simulation.VelocityDispersionFits / Pmu2ResidualCorrection / "
-                                      "Pmu4ResidualCorrection")
+        if Pdv_model_type not in ('jennings', 'sims'):
+            raise ValueError("`Pdv_model_type` must be one of ['jennings', 'sims']")       # power_dm.py:638-640
         if kmin < INTERP_KMIN:
             raise ValueError("kmin = %.2e h/Mpc below PT integrals interpolation lower bound" % kmin)
         if kmax > INTERP_KMAX:
@@ -431,6 +465,11 @@ class GalaxySpectrum(object):
         self.interpolate = bool(interpolate)
         self.transfer_fit = transfer_fit
         self.use_vlah_biasing = use_vlah_biasing
+        # simulation-calibrated options of HaloSpectrum (power_biased.py:26-52)
+        self.use_mean_bias, self.vel_disp_from_sims = bool(use_mean_bias), bool(vel_disp_from_sims)
+        self.correct_mu2, self.correct_mu4 = bool(correct_mu2), bool(correct_mu4)
+        self.Pdv_model_type = Pdv_model_type
+        self._loaded_data = {}              # SimLoaderMixin (rsd/sim_loader.py): name -> spline of the loaded term
         self._models = {}
         for kw in ('use_P00_model', 'use_P01_model', 'use_P11_model', 'use_Pdv_model', 'use_Pvv_model', 'use_Phm_model'):
             self._models[kw] = bool(kwargs.pop(kw, True))
@@ -443,6 +482,11 @@ class GalaxySpectrum(object):
         self.b2_00 = b2_00 if b2_00 is not None else _sim.b2_00
         self.b2_01 = b2_01 if b2_01 is not None else _sim.b2_01
         self.stochasticity = stochasticity if stochasticity is not None else _sim.stochasticity
+        # the fits behind vel_disp_from_sims / correct_mu2 / correct_mu4 (power_biased.py:181-200), keyword callables
+        # ``(b1=, sigma8_z=)`` and ``(f=, sigma8_z=, b1=, k=)``; None: the shipped Gaussian processes
+        self.vel_disp_fitter, self.Pmu2_correction, self.Pmu4_correction = vel_disp_fitter, Pmu2_correction, Pmu4_correction
+        # Pdv_model_type='sims': pygcl.Cosmology of the simulations (simulation.SimulationPdv); None: shipped normalisation
+        self.Pdv_sim_cosmo = Pdv_sim_cosmo
         # defaults of DarkMatterSpectrum / GalaxySpectrum (power_dm.py:119-126, power_gal.py:103-123)
         self.sigma8_z = params.Sigma8_z(z)
         self.f = params.f_z(z)
@@ -511,7 +555,8 @@ class GalaxySpectrum(object):
             if k in self._models:
                 self._models[k] = bool(v)
             elif k in self._PARAMS or k in ('max_mu', 'fog_model', 'use_so_correction', 'use_tidal_bias', 'b2_00', 'b2_01',
-                                            'stochasticity', 'interpolate', 'k0_low'):
+                                            'stochasticity', 'interpolate', 'k0_low', 'use_mean_bias', 'vel_disp_from_sims',
+                                            'correct_mu2', 'correct_mu4', 'Pdv_model_type'):
                 setattr(self, k, v)
             else:
                 raise RuntimeError("failure to set parameter `%s` to value %s: unknown parameter" % (k, v))
@@ -544,24 +589,130 @@ class GalaxySpectrum(object):
     def velocity_kurtosis(self):
         return self._power_norm**2*self.pt_table('scalars')[1]
 
+    def _pair_biases(self):
+        """(_ib1, _ib1_bar) of the ten sub-spectra (power_biased.py:219-237)"""
+        b1 = [self.b1_cA, self.b1_cB, self.b1_sA, self.b1_sB]
+        if not self.use_mean_bias:
+            return [(b1[a], b1[b]) for a, b in PAIRS]
+        return [((b1[a]*b1[b])**0.5,)*2 for a, b in PAIRS]
+
+    def _sigmav_halo(self, b1):
+        """sigmav_halo at a bias (power_biased.py:268-286); <= 0 stands for ``sigma_v``"""
+        from . import simulation as _sim
+        if not self.vel_disp_from_sims:
+            return -1.0
+        fit = self.vel_disp_fitter if self.vel_disp_fitter is not None else _sim._shared(_sim.VelocityDispersionFits)
+        return float(fit(b1=b1, sigma8_z=self.sigma8_z))
+
     def _walker(self):
         b1 = [self.b1_cA, self.b1_cB, self.b1_sA, self.b1_sB]
         b00 = [self.b2_00(b) for b in b1]
         b01 = [self.b2_01(b) for b in b1]
         b2 = [b00, b00, b00, b00, b01, b01]
-        return pack_walker(self.sigma8_z, self.f, self.alpha_par, self.alpha_perp, self.alpha_drag, b1, self.fs, self.fcB,
-                           self.fsB, self.sigma_c, self.sigma_sA, self.sigma_sB, self.NcBs, self.NsBsB, self.f_so,
-                           self.sigma_so, self.sigma_v, self.D, self.cosmo.sigma8(), b2)
+        p = pack_walker(self.sigma8_z, self.f, self.alpha_par, self.alpha_perp, self.alpha_drag, b1, self.fs, self.fcB,
+                        self.fsB, self.sigma_c, self.sigma_sA, self.sigma_sB, self.NcBs, self.NsBsB, self.f_so,
+                        self.sigma_so, self.sigma_v, self.D, self.cosmo.sigma8(), b2)
+        p[46:50] = [self._sigmav_halo(b) for b in b1]
+        return p
 
     def _stoch(self, kmodel):
         ks = stochasticity_grid(kmodel)
-        b1 = [self.b1_cA, self.b1_cB, self.b1_sA, self.b1_sB]
         out = np.zeros((NPAIR, NSTOCH))
         if self.stochasticity is not None:
-            for p, (a, b) in enumerate(PAIRS):
-                lo, hi = sorted([b1[a], b1[b]])
+            for p, (a, b) in enumerate(self._pair_biases()):
+                lo, hi = sorted([a, b])
                 out[p] = self.stochasticity(ks, self.sigma8_z, lo, hi)
         return out
+
+    def _pair_overrides(self):
+        """per-pair inputs of ``use_mean_bias``: the mean bias and everything evaluated at it"""
+        if not self.use_mean_bias:
+            return None
+        out = np.zeros((NPAIR, NPAIROVR))
+        for p, (bm, _) in enumerate(self._pair_biases()):
+            b00, b01 = self.b2_00(bm), self.b2_01(bm)
+            out[p] = [bm, b00, b00, b00, b00, b01, b01, self._sigmav_halo(bm)]
+        return out
+
+    def _mu_corrections(self, kmodel):
+        """mu2_model_correction / mu4_model_correction on the model grid (power_biased.py:462-480): the residual
+        fits at the geometric-mean bias of each pair"""
+        if not (self.correct_mu2 or self.correct_mu4):
+            return None
+        from . import simulation as _sim
+        out = np.zeros((NPAIR, 2, len(kmodel)))
+        bm = np.array([(a*b)**0.5 for a, b in self._pair_biases()])[:, None]
+        for j, (on, fit, cls) in enumerate(((self.correct_mu2, self.Pmu2_correction, _sim.Pmu2ResidualCorrection),
+                                            (self.correct_mu4, self.Pmu4_correction, _sim.Pmu4ResidualCorrection))):
+            if on:
+                fit = fit if fit is not None else _sim._shared(cls)
+                out[:, j] = fit(f=self.f, sigma8_z=self.sigma8_z, b1=bm, k=kmodel[None, :])
+        return out
+
+    # ---- SimLoaderMixin (rsd/sim_loader.py:44-75)
+    def _load(self, name, k, P):
+        """load data into a dark-matter term (``Pdv``, ``P00_mu0``, ``P01_mu2``, ``P11_mu4``): the term becomes the
+        cubic spline of (k, P), evaluated on the model grid"""
+        from scipy.interpolate import InterpolatedUnivariateSpline as spline
+        if name not in LOADABLE:
+            raise ValueError("`%s` not a valid term to be loaded; must be one of %s" % (name, list(LOADABLE)))
+        self._loaded_data[name] = spline(k, P)
+
+    def _unload(self, name):
+        self._loaded_data.pop(name, None)
+
+    def load_dm_sims(self, val):
+        """context manager: P00_mu0, P01_mu2, P11_mu4 and Pdv from the simulation snapshot ``teppei_lowz`` (z = 0),
+        ``teppei_midz`` (0.509) or ``teppei_highz`` (0.989) (power_dm.py:250-279)"""
+        import contextlib
+        from . import simulation as _sim
+        tags = {'teppei_lowz': 0, 'teppei_midz': 1, 'teppei_highz': 2}
+        if val not in tags:
+            raise ValueError("Allowed simulations to load are %s" % sorted(tags))
+
+        @contextlib.contextmanager
+        def cm():
+            d = _sim.dm_sims()
+            for name, key in (('P00_mu0', 'P00_mu0'), ('P01_mu2', 'P01_mu2'), ('P11_mu4', 'P11_mu4'), ('Pdv', 'Pdv_mu0')):
+                self._load(name, d['k'], d[key][tags[val]])
+            try:
+                yield
+            finally:
+                for name in ('P00_mu0', 'P01_mu2', 'P11_mu4', 'Pdv'):
+                    self._unload(name)
+        return cm()
+
+    def _loaded_knots(self, kmodel):
+        loaded = {n: s(kmodel) for n, s in self._loaded_data.items()}
+        if 'Pdv' not in loaded and self.Pdv_model_type == 'sims' and self._models['use_Pdv_model']:
+            from . import simulation as _sim
+            loaded['Pdv'] = _sim.SimulationPdv(self.cosmo, self.z, self.sigma8_z, self.f, self.Pdv_sim_cosmo)(kmodel)  # power_dm.py:869-870
+        return loaded
+
+    def _state(self, kmodel):
+        """everything one walker of the assembly kernels reads at the current attribute values"""
+        return dict(par=self._walker(), stoch=self._stoch(kmodel), corr=self._mu_corrections(kmodel), ovr=self._pair_overrides())
+
+    def _evaluate(self, states, kind, *args, **kw):
+        """run ``states`` as one batch of walkers of the engine's ``galaxy_<kind>`` on this model's tables"""
+        eng = self._ensure_tables()
+        kmodel = self.k
+        gal = eng.galaxy(kmodel, self._config())
+        nw = len(states)
+        par, stoch = np.array([s['par'] for s in states]), np.array([s['stoch'] for s in states])
+        corr = None if states[0]['corr'] is None else np.array([s['corr'] for s in states])
+        ovr = None if states[0]['ovr'] is None else np.array([s['ovr'] for s in states])
+        loaded = self._loaded_knots(kmodel)
+        opts = corr is not None or ovr is not None or bool(loaded)
+        if opts or getattr(gal, '_opts', False):
+            eng.galaxy_options(gal, nw, corr, ovr, loaded)
+            gal._opts = opts
+        out = getattr(eng, 'galaxy_' + kind)(gal, self._spectra, self._result, par, stoch, *args,
+                                             cmap=np.zeros(nw, dtype=np.int32), **kw)
+        if np.isnan(out).any():
+            raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
+                             "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+        return eng, gal, out
 
     def _config(self):
         return galaxy_config(max_mu=self.max_mu, fog_model=self.fog_model, use_tidal_bias=self.use_tidal_bias,
@@ -570,7 +721,6 @@ class GalaxySpectrum(object):
 
     def power(self, k, mu, flatten=False):
         """P(k, mu) with the broadcasting rules of ``tools.broadcast_kmu`` (rsd/tools.py:225-266)"""
-        eng = self._ensure_tables()
         k = np.atleast_1d(np.asarray(k, dtype=np.float64))
         mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
         if k.ndim == 1 and mu.ndim == 1:
@@ -583,27 +733,15 @@ class GalaxySpectrum(object):
         kb, mub = np.broadcast_arrays(k, mu)
         if kb.ndim > 2:
             raise ValueError("incompatible `k`, `mu` dimensions for broadcasted; arrays should have maximum dimension of 2")
-        kmodel = self.k
-        gal = eng.galaxy(kmodel, self._config())
-        P = eng.galaxy_power(gal, self._spectra, self._result, self._walker(), self._stoch(kmodel),
-                             np.ascontiguousarray(kb).ravel(), np.ascontiguousarray(mub).ravel())[0]
-        if np.isnan(P).any():
-            raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
-                             "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+        P = self._evaluate([self._state(self.k)], 'power', np.ascontiguousarray(kb).ravel(), np.ascontiguousarray(mub).ravel())[2][0]
         P = np.squeeze(P.reshape(kb.shape))
         return np.ravel(P, order='F') if flatten else P
 
 
 def _poles(self, k, ells, Nmu=40):
     """``GalaxySpectrum.poles(k, ells, Nmu=40)`` (power_dm.py:1016-1050): list of P_ell(k), one array per ell"""
-    eng = self._ensure_tables()
     scalar = np.isscalar(ells)
-    kmodel = self.k
-    gal = eng.galaxy(kmodel, self._config())
-    P = eng.galaxy_poles(gal, self._spectra, self._result, self._walker(), self._stoch(kmodel), k, ells, Nmu)[0]
-    if np.isnan(P).any():
-        raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
-                         "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+    P = self._evaluate([self._state(self.k)], 'poles', k, ells, Nmu)[2][0]
     return P[0] if scalar else [P[i] for i in range(P.shape[0])]
 
 
@@ -627,7 +765,6 @@ def _gradient(self, k, mu, names, epsilon=1e-4):
     below the 1e-5 target.  ``epsilon`` may be a scalar or one step per name; ``k`` and ``mu`` are paired points
     (or broadcast as in ``power``).  Constraints between parameters (rsdfit's ParameterSet) are the caller's
     chain rule."""
-    eng = self._ensure_tables()
     names = [names] if isinstance(names, str) else list(names)
     for n in names:
         if n not in _GRAD_PARAMS:
@@ -642,8 +779,7 @@ def _gradient(self, k, mu, names, epsilon=1e-4):
         k, mu = k[:, None], mu[None, :]
     kb, mub = np.broadcast_arrays(k, mu)
     kmodel = self.k
-    gal = eng.galaxy(kmodel, self._config())
-    wpar, stoch = [], []
+    states = []
     for n, e in zip(names, eps):
         x0 = getattr(self, n)
         if x0 is None:
@@ -651,16 +787,10 @@ def _gradient(self, k, mu, names, epsilon=1e-4):
         try:
             for sgn in (+1., -1.):
                 setattr(self, n, x0 + sgn*e)
-                wpar.append(self._walker())
-                stoch.append(self._stoch(kmodel))
+                states.append(self._state(kmodel))
         finally:
             setattr(self, n, x0)
-    P = eng.galaxy_power(gal, self._spectra, self._result, np.array(wpar), np.array(stoch),
-                         np.ascontiguousarray(kb).ravel(), np.ascontiguousarray(mub).ravel(),
-                         cmap=np.zeros(len(wpar), dtype=np.int32))
-    if np.isnan(P).any():
-        raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
-                         "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+    P = self._evaluate(states, 'power', np.ascontiguousarray(kb).ravel(), np.ascontiguousarray(mub).ravel())[2]
     P = P.reshape(len(names), 2, -1)
     return (P[:, 0] - P[:, 1])/(2.*eps[:, None])
 
@@ -673,28 +803,20 @@ def _components(self, k, mu):
     ``power = (1 - fs)^2 Pcc + 2 fs (1 - fs) Pcs + fs^2 Pss`` (power_gal.py:316-399, gal/__init__.py:24-40), each
     with the same AP treatment as ``power``.  Evaluated as ONE batch of three walkers of the assembly kernel at
     fs = 0, 1/2, 1 (fs enters nowhere else): Pcc = P(0), Pss = P(1), Pcs = 2 P(1/2) - (Pcc + Pss)/2."""
-    eng = self._ensure_tables()
     k = np.atleast_1d(np.asarray(k, dtype=np.float64))
     mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
     if k.ndim == 1 and mu.ndim == 1 and len(mu) != len(k):
         k, mu = k[:, None], mu[None, :]
     kb, mub = np.broadcast_arrays(k, mu)
-    kmodel = self.k
-    gal = eng.galaxy(kmodel, self._config())
     fs0 = self.fs
-    wpar = []
+    states = []
     try:
         for v in (0.0, 0.5, 1.0):
             self.fs = v
-            wpar.append(self._walker())
+            states.append(self._state(self.k))
     finally:
         self.fs = fs0
-    stoch = np.array([self._stoch(kmodel)]*3)
-    P = eng.galaxy_power(gal, self._spectra, self._result, np.array(wpar), stoch, np.ascontiguousarray(kb).ravel(),
-                         np.ascontiguousarray(mub).ravel(), cmap=np.zeros(3, dtype=np.int32))
-    if np.isnan(P).any():
-        raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
-                         "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
+    P = self._evaluate(states, 'power', np.ascontiguousarray(kb).ravel(), np.ascontiguousarray(mub).ravel())[2]
     shape = kb.shape
     Pcc, Pss = P[0], P[2]
     Pcs = 2.0*P[1] - 0.5*(Pcc + Pss)
@@ -710,10 +832,8 @@ def _dm_spectra(self):
     """the dark-matter building blocks on the model grid ``self.k`` at the current parameters: dict with
     P_lin (normed_power_lin), P00, P01, P11_mu4 (dm/P00.py, P01.py, P11.py totals), Pdd, Pdv, Pvv
     (power_dm.py:797-884 incl. the Jennings et al. fits of :676-718)"""
-    eng = self._ensure_tables()
     kmodel = self.k
-    gal = eng.galaxy(kmodel, self._config())
-    eng.galaxy_power(gal, self._spectra, self._result, self._walker(), self._stoch(kmodel), kmodel[:1], np.zeros(1))
+    eng, gal, _ = self._evaluate([self._state(kmodel)], 'power', kmodel[:1], np.zeros(1))
     base = eng.galaxy_base(gal, 1)[0]
     return {name: base[row].copy() for name, row in _DM_ROWS.items()}
 

@@ -166,3 +166,66 @@ def b2_00(b1):
 
 def b2_01(b1):
     return float(np.squeeze(_shared(NonlinearBiasFits)(b1=b1, select='b2_01_a')[0]))
+
+
+# ------------------------------------------------------------------------- dark-matter simulation measurements
+_DM_SIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'dm_sims.npz')
+
+
+def dm_sims():
+    """the measurements of ``pyRSD/data/dark_matter`` (see data/make_dm_sims.py): k, z, Pdv_mu0 / P00_mu0 / P01_mu2 / P11_mu4 [3][500]"""
+    if 'dm_sims' not in _cache:
+        _cache['dm_sims'] = dict(np.load(_DM_SIMS))
+    return _cache['dm_sims']
+
+
+def _lcdm_growth(Om, z):
+    """D(z) / D(0) and f(z) of flat LCDM (growth integral; matter + Lambda)"""
+    from scipy.integrate import quad
+    E = lambda a: np.sqrt(Om/a**3 + 1. - Om)
+    I = lambda a: quad(lambda x: 1./(x*E(x))**3, 0., a)[0]
+    a = 1./(1. + z)
+    D = E(a)*I(a)/(E(1.)*I(1.))
+    f = -1.5*Om/a**3/E(a)**2 + a/((a*E(a))**3*I(a))
+    return D, f
+
+
+class SimulationPdv(object):
+    """``SimulationPdv`` (rsd/simulation.py:550-660): the density -- velocity-divergence spectrum from the simulation
+    measurements at z = 0, 0.509, 0.989, each divided by D(z)^2 f(z) P_lin(k) of the simulation cosmology, interpolated
+    bilinearly in (z, k) (scipy RegularGridInterpolator, as the reference) and rescaled by f sigma8_z^2 P_lin(k) / sigma8^2
+    of the model cosmology; outside the redshift range the nearest snapshot's shape is rescaled by ``z`` itself, as the
+    reference's ``_extrapolate`` does.
+
+    ``sim_cosmo``: a ``pygcl.Cosmology`` of data/params/teppei_sims.ini with ``growth`` / ``f`` at the three redshifts (the
+    reference obtains it from CLASS).  None: the z = 0 linear spectrum the reference ships beside the measurements
+    (data/dark_matter/Plin_z_0.000.dat, log-log spline) with the flat-LCDM growth integral -- CLASS is not part of this
+    library, so this default normalisation is not pinned against the reference's."""
+
+    def __init__(self, cosmo, z, sigma8_z, f, sim_cosmo=None):
+        from scipy.interpolate import RegularGridInterpolator, InterpolatedUnivariateSpline
+        self.cosmo, self.z, self.sigma8_z, self.f = cosmo, z, sigma8_z, f
+        d = dm_sims()
+        self.zs, self.ks = d['z'], d['k']
+        if sim_cosmo is not None:
+            Plin = pygcl.LinearPS(sim_cosmo, 0.)(self.ks)
+            growth = [(sim_cosmo.D_z(zz), sim_cosmo.f_z(zz)) for zz in self.zs]
+        else:
+            spl = InterpolatedUnivariateSpline(np.log(d['plin_k']), np.log(d['plin_P']), k=3)
+            k0, ns = d['plin_k'][0], float(d['sim_n_s'])
+            # below the first tabulated k the spectrum is the primordial power law
+            Plin = np.where(self.ks >= k0, np.exp(spl(np.log(np.maximum(self.ks, k0)))), d['plin_P'][0]*(self.ks/k0)**ns)
+            Om = float(d['sim_Omega_b']) + float(d['sim_Omega_cdm'])
+            growth = [_lcdm_growth(Om, zz) for zz in self.zs]
+        vals = np.array([d['Pdv_mu0'][i]/(D**2*Plin*ff) for i, (D, ff) in enumerate(growth)])
+        self.interpolation_table = RegularGridInterpolator((self.zs, self.ks), vals)
+        self._power_lin = pygcl.LinearPS(cosmo, 0.)
+
+    def __call__(self, k):
+        k = np.atleast_1d(np.asarray(k, dtype=float))
+        normed = self._power_lin(k)/self.cosmo.sigma8()**2
+        if self.z < self.zs.min() or self.z > self.zs.max():
+            zz, factor = (self.zs.min() if self.z < self.zs.min() else self.zs.max()), self.z*normed      # simulation.py:620-641
+        else:
+            zz, factor = self.z, self.f*self.sigma8_z**2*normed
+        return self.interpolation_table(np.column_stack([np.full(len(k), zz), k]))*factor

@@ -24,6 +24,28 @@ def stochasticity(k, sigma8_z, b1a, b1b):
     return (sigma8_z/0.8)*(120.*b1a*b1b - 400.)*(1.0 + 0.3*np.log(k/0.1) - 0.05*np.log(k/0.1)**2)
 
 
+def vel_disp(b1, sigma8_z):
+    """smooth stand-in for VelocityDispersionFits (halo sigma_v in Mpc/h)"""
+    return 3.2 + 0.9*(b1 - 2.0) + 2.0*(sigma8_z - 0.6)
+
+
+def Pmu2_corr(f, sigma8_z, b1, k):
+    """smooth stand-in for Pmu2ResidualCorrection"""
+    return 900.*b1*(f/0.75)*(sigma8_z/0.6)**2*(k/0.1)/(1.0 + (k/0.15)**2)
+
+
+def Pmu4_corr(f, sigma8_z, b1, k):
+    """smooth stand-in for Pmu4ResidualCorrection"""
+    return -350.*b1*(f/0.75)**2*(sigma8_z/0.6)**2*(k/0.1)**2/(1.0 + (k/0.2)**3)
+
+
+def loaded_terms(k):
+    """smooth stand-ins for user-loaded dark-matter terms (SimLoaderMixin._load): name -> P(k)"""
+    shape = 2.2e4*(k/0.02)/(1.0 + (k/0.02)**2.3)
+    return {'Pdv': -0.78*shape*(1.0 - 0.8*k), 'P00_mu0': shape*(1.0 + 1.5*k), 'P01_mu2': 1.5*shape*(1.0 + 0.6*k),
+            'P11_mu4': 0.55*shape*(1.0 - 1.2*k)}
+
+
 def base_cosmology():
     """the reference's shipped Planck15 transfer function T(k) (500 samples, from docs/data/galaxy_power.npy) and the
     constants of its Eisenstein-Hu extrapolation; delta_H is the sigma8 = 0.8159 normalisation (data/planck15_transfer.npz,

@@ -234,6 +234,10 @@ def build_model(cosmo_mod, gcl_cosmo, z, **kwargs):
     model._cache['nonlinear_bias_fitter'] = fitter
     model._cache['auto_stochasticity_fits'] = lambda b1, sigma8_z, k: stochasticity(k, sigma8_z, b1, b1)
     model._cache['cross_stochasticity_fits'] = lambda b1_1, b1_2, sigma8_z, k: stochasticity(k, sigma8_z, b1_1, b1_2)
+    from pyrsd_b200 import synthetic as S
+    model._cache['vel_disp_fitter'] = S.vel_disp
+    model._cache['Pmu2_correction'] = S.Pmu2_corr
+    model._cache['Pmu4_correction'] = S.Pmu4_corr
     return model
 
 
@@ -280,12 +284,21 @@ def main():
         # ... and with sigma8_z / D = 1.02 OUTSIDE the table: the reference falls back to the direct evaluation for
         # that one call (InterpolationDomainError branch, interpolated.py:18-19)
         'z055_interp_edge': (0.55, dict(interpolate=True), dict(sigma8_z=0.7636, f=0.74)),
+        # the simulation-calibrated options of HaloSpectrum (power_biased.py:26-52); the fits behind them are the smooth
+        # stand-ins of pyrsd_b200/synthetic.py on both sides (build_model)
+        'z055_simopts': (0.55, dict(interpolate=False, use_mean_bias=True, vel_disp_from_sims=True, correct_mu2=True,
+                                    correct_mu4=True),
+                         dict(sigma8_z=0.62, f=0.77, b1_cA=1.95, b1_sB=3.4, fs=0.13)),
+        'z055_veldisp': (0.55, dict(interpolate=False, vel_disp_from_sims=True, correct_mu4=True), dict(sigma8_z=0.6)),
+        # user-loaded dark-matter terms (SimLoaderMixin._load, rsd/sim_loader.py:56-66)
+        'z055_loaded': (0.55, dict(interpolate=False), dict(sigma8_z=0.6, _load=True)),
     }
     names = ['sigma8_z', 'f', 'alpha_par', 'alpha_perp', 'alpha_drag', 'b1_cA', 'b1_cB', 'b1_sA', 'b1_sB', 'fs', 'fcB',
              'fsB', 'sigma_c', 'sigma_sA', 'sigma_sB', 'NcBs', 'NsBsB', 'f_so', 'sigma_so', 'sigma_v', 'D']
     global ZEL_SOURCE
     only = [a for a in sys.argv[1:] if a in cases]
-    runs = [(name, 'reference') for name in cases if not name.startswith('z055_interp')] \
+    new = ('z055_simopts', 'z055_veldisp', 'z055_loaded')
+    runs = [(name, 'reference') for name in cases if not name.startswith('z055_interp') and name not in new] \
         + [(name, 'pi') for name in cases if name != 'z055_spt']
     if only:
         runs = [r for r in runs if r[0] in only]
@@ -295,6 +308,12 @@ def main():
         z, kw, upd = cases[case_name]
         name = case_name if ZEL_SOURCE == 'reference' else case_name + '_pi'
         model = build_model(cosmo_mod, cosmo, z, **kw)
+        upd = dict(upd)
+        if upd.pop('_load', False):
+            from pyrsd_b200 import synthetic as S
+            kl = np.logspace(-3.2, 0., 400)
+            for term, Pl in S.loaded_terms(kl).items():
+                model._load(term, kl, Pl)
         model.update(**upd)
         k = kbench if ('alpha_par' not in upd) else kbench[kbench <= 0.48]
         out[name + '_k'] = k

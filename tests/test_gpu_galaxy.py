@@ -23,8 +23,15 @@ CASES = {
     # sigma8_z / D lies outside the table and that one call falls back to the direct evaluation
     'z055_interp': (0.55, dict(interpolate=True), dict()),
     'z055_interp_edge': (0.55, dict(interpolate=True), dict()),
+    # simulation-calibrated options of HaloSpectrum (power_biased.py:26-52, 219-286, 462-520): the fits behind them are
+    # the smooth stand-ins of pyrsd_b200/synthetic.py on both sides
+    'z055_simopts': (0.55, dict(use_mean_bias=True, vel_disp_from_sims=True, correct_mu2=True, correct_mu4=True), dict()),
+    'z055_veldisp': (0.55, dict(vel_disp_from_sims=True, correct_mu4=True), dict()),
+    # user-loaded dark-matter terms (SimLoaderMixin._load, rsd/sim_loader.py:56-66)
+    'z055_loaded': (0.55, dict(), dict(load=True)),
 }
 INTERP_CASES = ('z055_interp', 'z055_interp_edge')
+PI_ONLY = INTERP_CASES + ('z055_simopts', 'z055_veldisp', 'z055_loaded')
 
 
 @pytest.fixture(scope='module')
@@ -41,7 +48,9 @@ def engine():
 def make_model(cosmo, engine, z, **kw):
     from pyrsd_b200 import rsd
     kw.setdefault('interpolate', False)          # the fixtures' cases state interpolate=False (make_galaxy_ref.py) unless a test says otherwise
-    return rsd.GalaxySpectrum(params=cosmo, z=z, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine, **kw)
+    from pyrsd_b200 import synthetic as S
+    return rsd.GalaxySpectrum(params=cosmo, z=z, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine,
+                              vel_disp_fitter=S.vel_disp, Pmu2_correction=S.Pmu2_corr, Pmu4_correction=S.Pmu4_corr, **kw)
 
 
 # k0_low <= k' < 0.0075: the Zel'dovich transform amplifies errors of 1e-9 sigma_v^2 in Y(r > 1e4 Mpc/h) to 1e-4 in
@@ -51,7 +60,7 @@ def make_model(cosmo, engine, z, **kw):
 # state the bound in that band is the reference's noise (2.5e-4), 1e-5 elsewhere; against the reference fed with the
 # converged state ("_pi" cases) it is 1e-5 everywhere.
 ZEL_BAND = (4.5e-3, 8e-3)       # in OBSERVED k: the AP cases map k to k' = k / alpha (3 %), and the model's spline rings one knot below k0_low
-VARIANTS = [(c, '') for c in sorted(CASES) if c not in INTERP_CASES] + [(c, '_pi') for c in sorted(CASES) if c != 'z055_spt']
+VARIANTS = [(c, '') for c in sorted(CASES) if c not in PI_ONLY] + [(c, '_pi') for c in sorted(CASES) if c != 'z055_spt']
 
 
 def _record(tag, value):
@@ -70,8 +79,13 @@ def _record(tag, value):
 @pytest.mark.parametrize('case,variant', VARIANTS)
 def test_power_vs_reference_python(cosmo, engine, case, variant):
     ref = np.load(REF)
-    z, kw, _ = CASES[case]
+    z, kw, extra = CASES[case]
     model = make_model(cosmo, engine, z, **kw)
+    if extra.get('load'):
+        from pyrsd_b200 import synthetic as S
+        kl = np.logspace(-3.2, 0., 400)
+        for term, Pl in S.loaded_terms(kl).items():
+            model._load(term, kl, Pl)
     names = [str(n) for n in ref['par_names']]
     key = case + variant
     if key + '_P' not in ref.files:
@@ -255,8 +269,13 @@ def test_dm_blocks_vs_reference_python(cosmo, engine, case, variant):
     key = case + variant
     if key + '_dm' not in ref.files:
         pytest.skip("fixture has no dm blocks")
-    z, kw, _ = CASES[case]
+    z, kw, extra = CASES[case]
     model = make_model(cosmo, engine, z, **kw)
+    if extra.get('load'):
+        from pyrsd_b200 import synthetic as S
+        kl = np.logspace(-3.2, 0., 400)
+        for term, Pl in S.loaded_terms(kl).items():
+            model._load(term, kl, Pl)
     names = [str(n) for n in ref['par_names']]
     pars = dict(zip(names, ref[key + '_pars']))
     pars.pop('D')
@@ -274,3 +293,47 @@ def test_dm_blocks_vs_reference_python(cosmo, engine, case, variant):
         assert err[i] < TOL, (key, name, err[i], k[i])
         if band.any():
             assert err[band].max() < 2.5e-4, (key, name, err[band].max())
+
+
+def test_simulation_pdv_identity_and_default_fits(cosmo, engine):
+    """Pdv_model_type='sims' (power_dm.py:869-870, rsd/simulation.py:550-660): with the model cosmology standing in for the
+    simulation cosmology, at a snapshot redshift and the fiducial f, sigma8_z the normalisation cancels and the model
+    returns the measurement itself; the shipped Gaussian processes drive vel_disp_from_sims / correct_mu2 / correct_mu4
+    when no callable is given."""
+    from pyrsd_b200 import rsd, simulation as sim
+    d = sim.dm_sims()
+    zs = 0.509
+    c = cosmo.clone()
+    c._params['growth'] = {0.0: 1.0, 0.509: 0.77, 0.989: 0.61}
+    c._params['f'] = {0.0: 0.52, 0.509: 0.75, 0.989: 0.86}
+    m = sim.SimulationPdv(c, zs, c.Sigma8_z(zs), c.f_z(zs), sim_cosmo=c)
+    k = d['k'][200:480:7]
+    assert np.max(np.abs(m(k)/d['Pdv_mu0'][1][200:480:7] - 1)) < 1e-12
+    # default normalisation (shipped linear spectrum of the simulations + LCDM growth): Pdv ~ -f P_lin at low k
+    m0 = sim.SimulationPdv(cosmo, 0.55, cosmo.Sigma8_z(0.55), cosmo.f_z(0.55))
+    kl = np.array([2e-3, 5e-3])
+    from pyrsd_b200 import pygcl
+    PL = pygcl.LinearPS(cosmo, 0.55)(kl)
+    assert np.max(np.abs(m0(kl)/(-cosmo.f_z(0.55)*PL) - 1)) < 0.02
+    # through the model: the 'sims' Pdv replaces the Jennings fit on the model grid
+    model = rsd.GalaxySpectrum(params=cosmo, z=0.55, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity, engine=engine,
+                               interpolate=False, Pdv_model_type='sims')
+    dm = model.dm_spectra()
+    assert np.max(np.abs(dm['Pdv']/m0(model.k) - 1)) < 1e-13
+    with model.load_dm_sims('teppei_midz'):
+        dm2 = model.dm_spectra()
+    from scipy.interpolate import InterpolatedUnivariateSpline as spline
+    assert np.max(np.abs(dm2['P00']/spline(d['k'], d['P00_mu0'][1])(model.k) - 1)) < 1e-13
+    assert np.max(np.abs(model.dm_spectra()['P00']/dm['P00'] - 1)) < 1e-14          # unloaded again
+    # shipped Gaussian processes as the defaults of the simulation options
+    g = rsd.GalaxySpectrum(params=cosmo, z=0.55, engine=engine, interpolate=False, vel_disp_from_sims=True, correct_mu2=True,
+                           correct_mu4=True, use_mean_bias=True)
+    kk, mu = np.logspace(-2, np.log10(0.4), 30), np.linspace(0, 1, 5)
+    P1 = g.power(kk, mu)
+    g2 = rsd.GalaxySpectrum(params=cosmo, z=0.55, engine=engine, interpolate=False, vel_disp_from_sims=True, correct_mu2=True,
+                            correct_mu4=True, use_mean_bias=True, vel_disp_fitter=sim.VelocityDispersionFits(),
+                            Pmu2_correction=sim.Pmu2ResidualCorrection(), Pmu4_correction=sim.Pmu4ResidualCorrection())
+    assert np.all(np.isfinite(P1)) and np.array_equal(P1, g2.power(kk, mu))
+    g.update(correct_mu2=False, correct_mu4=False, vel_disp_from_sims=False, use_mean_bias=False)
+    P0 = g.power(kk, mu)
+    assert np.max(np.abs(P1/P0 - 1)) > 1e-3          # the options do act
