@@ -46,6 +46,33 @@ void PTResult::ensure(int ncosmo_, int nk_)
     YY.ensure(c*ZEL_NR);
 }
 
+// Interpolation map from the kept points of a k list to all of it: 8-point Lagrange in ln k for the points left out,
+// the identity for the kept ones.  idx / w [n][8]; ksub = the kept k.
+static void lagrange_fill_map(const std::vector<double>& kfull, const std::vector<char>& keep, std::vector<int>& idx,
+                              std::vector<double>& w, std::vector<double>& ksub)
+{
+    const int NP = 8, n = (int)kfull.size();
+    std::vector<double> xsub;
+    std::vector<int> pos;
+    ksub.clear();
+    for (int i = 0; i < n; i++) if (keep[i]) { ksub.push_back(kfull[i]); xsub.push_back(std::log(kfull[i])); pos.push_back(i); }
+    const int nsub = (int)ksub.size();
+    idx.assign((size_t)n*NP, 0);
+    w.assign((size_t)n*NP, 0.0);
+    for (int i = 0, j = 0; i < n; i++) {
+        while (j < nsub && pos[j] < i) j++;
+        if (keep[i]) { idx[(size_t)i*NP] = j; w[(size_t)i*NP] = 1.0; continue; }
+        const double x = std::log(kfull[i]);
+        const int a = std::min(std::max(j - NP/2, 0), nsub - NP);
+        for (int l = 0; l < NP; l++) {
+            double wl = 1.0;
+            for (int m = 0; m < NP; m++) if (m != l) wl *= (x - xsub[a + m])/(xsub[a + l] - xsub[a + m]);
+            idx[(size_t)i*NP + l] = a + l;
+            w[(size_t)i*NP + l] = wl;
+        }
+    }
+}
+
 static const double INV8PI2 = 1.0/(8.0*M_PI*M_PI);
 static const double INV4PI2 = 1.0/(4.0*M_PI*M_PI);
 static const int J_IDS[6] = {0, 1, 2, 3, 4, 6};                    // J00 J01 J02 J10 J11 J20 -> 3m+n
@@ -85,25 +112,10 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
             for (int i = lo; i >= 0; i -= 6) keep[i] = 1;
             for (int i = hi; i < ONELOOP_N; i += 3) keep[i] = 1;
             keep[0] = keep[ONELOOP_N - 1] = 1;
-            std::vector<double> ksub, xsub;
-            std::vector<int> pos;
-            for (int i = 0; i < ONELOOP_N; i++) if (keep[i]) { ksub.push_back(k_1loop[i]); xsub.push_back(std::log(k_1loop[i])); pos.push_back(i); }
+            std::vector<double> ksub, mw;
+            std::vector<int> midx;
+            lagrange_fill_map(k_1loop, keep, midx, mw, ksub);
             n_1loop_sub = (int)ksub.size();
-            const int NP = 8;
-            std::vector<int> midx((size_t)ONELOOP_N*NP, 0);
-            std::vector<double> mw((size_t)ONELOOP_N*NP, 0.0);
-            for (int i = 0, j = 0; i < ONELOOP_N; i++) {
-                while (j < n_1loop_sub && pos[j] < i) j++;
-                if (keep[i]) { midx[(size_t)i*NP] = j; mw[(size_t)i*NP] = 1.0; continue; }
-                const double x = std::log(k_1loop[i]);
-                const int a = std::min(std::max(j - NP/2, 0), n_1loop_sub - NP);
-                for (int l = 0; l < NP; l++) {
-                    double w = 1.0;
-                    for (int m = 0; m < NP; m++) if (m != l) w *= (x - xsub[a + m])/(xsub[a + l] - xsub[a + m]);
-                    midx[(size_t)i*NP + l] = a + l;
-                    mw[(size_t)i*NP + l] = w;
-                }
-            }
             d_olmap_idx.upload(midx, c.stream);
             d_olmap_w.upload(mw, c.stream);
             k_1loop_sub = ksub;
@@ -118,9 +130,38 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         op_1loop.to_float(c);
         lap(1);
     }
+    // ---- thinned k_interp.  Below k = 0.01 every mode-coupling integral is < 1e-3 P_L(k) and a smooth function of k (no
+    // BAO structure enters yet), but a k there costs as many CTA set-ups, P(a) passes and reductions as one at k = 0.3
+    // for 1/15 of the nodes: on a long ascending list (rsd's 250-point k_interp has 156 points below 0.01) the operators
+    // are integrated at points >= 0.29 apart in ln k there (every 6th of k_interp) and the others are filled by 8-point
+    // Lagrange interpolation in ln k (k_pack_ik, k_fill_ml).  Measured on the dense fixtures (tight reference on all 250
+    // k): the fill changes no I, K or ImnOneLoop value by more than 2.4e-7 of max(|value|, P_L).
+    if (!only_oneloop) {
+        std::vector<char> keep(nk, 1);
+        bool ascending = nk >= 64;
+        for (int i = 1; i < nk && ascending; i++) ascending = k_interp[i] > k_interp[i - 1];
+        if (ascending) {
+            int lo = 0;
+            while (lo < nk - 1 && k_interp[lo] < 0.01) lo++;
+            double last = std::log(k_interp[lo]);
+            for (int i = lo - 1; i > 0; i--) {
+                const double x = std::log(k_interp[i]);
+                if (last - x < 0.29) keep[i] = 0; else last = x;
+            }
+            int kept = 0;
+            for (int i = 0; i < nk; i++) kept += keep[i];
+            if (kept < 16) keep.assign(nk, 1);
+        }
+        std::vector<int> midx;
+        std::vector<double> mw;
+        lagrange_fill_map(k_interp, keep, midx, mw, k_sub);
+        nk_sub = (int)k_sub.size();
+        d_kmap_idx.upload(midx, c.stream);
+        d_kmap_w.upload(mw, c.stream);
+    }
     // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
     if (!only_oneloop) {
-        auto geo = make_geometry(c, k_interp.data(), nk, 1e5, cfg, grid, 4);     // DMMA lane layout: 4 nodes per k-step
+        auto geo = make_geometry(c, k_sub.data(), nk_sub, 1e5, cfg, grid, 4);     // DMMA lane layout: 4 nodes per k-step
         lap(0);
         std::vector<ColSpec> cols;
         // both spectra are P_L here, so P(a) P(b) is the same on the two halves of the v domain and the
@@ -132,7 +173,7 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     }
     // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
     if (with_ml && !only_oneloop) {
-        auto geo = make_geometry(c, k_interp.data(), nk, 10.0, cfg.ml_variant(), grid);
+        auto geo = make_geometry(c, k_sub.data(), nk_sub, 10.0, cfg.ml_variant(), grid);
         lap(0);
         op_ml.build(c, geo, ml_columns(), true);
         op_ml.to_float(c);
@@ -227,18 +268,45 @@ __global__ void k_oneloop_combine(int ncosmo, int nsub, const double* __restrict
     o[3*ONELOOP_N + i] = a[3];         // I23 + 2/3 I32 + 1/5 I33, combined in the operator (PTPlan ctor)
 }
 
-__global__ void k_pack_ik(int nk, const double* __restrict__ s /*[c][nk][32]*/, double* __restrict__ I, double* __restrict__ K)
+__global__ void k_pack_ik(int nk, int nsub, const double* __restrict__ s /*[c][nsub][32]*/, const int* __restrict__ midx /*[nk][8]*/,
+                          const double* __restrict__ mw /*[nk][8]*/, double* __restrict__ I, double* __restrict__ K)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
     if (i >= nk) return;
-    const double* r = s + ((size_t)c*nk + i)*32;
+    // computed at k_i, or interpolated from the computed points (PTPlan ctor)
     double v[29];
 #pragma unroll
-    for (int j = 0; j < 29; j++) v[j] = r[j];
+    for (int j = 0; j < 29; j++) v[j] = 0.0;
+#pragma unroll 1
+    for (int l = 0; l < 8; l++) {
+        const double w = mw[(size_t)i*8 + l];
+        if (w == 0.0) continue;
+        const double* r = s + ((size_t)c*nsub + midx[(size_t)i*8 + l])*32;
+#pragma unroll
+        for (int j = 0; j < 29; j++) v[j] = fma(w, r[j], v[j]);
+    }
 #pragma unroll
     for (int j = 0; j < 16; j++) I[((size_t)c*16 + j)*nk + i] = v[j];
 #pragma unroll
     for (int j = 0; j < 13; j++) K[((size_t)c*13 + j)*nk + i] = v[16 + j];
+}
+
+// ImnOneLoop parts on all of k_interp from the computed subset: ML [c][21][nk] <- s [c][21][nsub]
+__global__ void k_fill_ml(int nk, int nsub, const double* __restrict__ s, const int* __restrict__ midx, const double* __restrict__ mw,
+                          double* __restrict__ ML)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x, row = blockIdx.y;       // row = c*21 + t
+    if (i >= nk) return;
+    const double* r = s + (size_t)row*nsub;
+    double v = 0.0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        const double w = mw[(size_t)i*8 + l];
+        if (w == 0.0) continue;
+        const double x = r[midx[(size_t)i*8 + l]];
+        v = fma(w, x, v);
+    }
+    ML[(size_t)row*nk + i] = v;
 }
 
 __global__ void k_pack_lin(int nk, int nout, int with_zel, const double* __restrict__ s /*[c][nout]*/,
@@ -343,16 +411,26 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res, bool sync)
     }
 
     // ---- stage B: I_mn, K_mn
-    s_ik.ensure((size_t)ntile*8*nk*32);
+    s_ik.ensure((size_t)ntile*8*nk_sub*32);
     op_ik.apply(c, sp.tables.p, s_slot.p, s_rowA.p, s_rowA.p, ntile, s_ik.p);
     {
         dim3 g((nk + 127)/128, nc);
-        k_pack_ik<<<g, 128, 0, s>>>(nk, s_ik.p, res.I.p, res.K.p);
+        k_pack_ik<<<g, 128, 0, s>>>(nk, nk_sub, s_ik.p, d_kmap_idx.p, d_kmap_w.p, res.I.p, res.K.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches++;
     }
     // ---- stage B: ImnOneLoop (one tile = one cosmology, rows = spectrum pairs)
-    if (with_ml) nodal_apply_ml(c, op_ml, sp.tables.p, s_tabidx.p, nc, res.ML.p);
+    if (with_ml) {
+        if (nk_sub == nk) nodal_apply_ml(c, op_ml, sp.tables.p, s_tabidx.p, nc, res.ML.p);
+        else {
+            s_ml.ensure((size_t)nc*N_ML*3*nk_sub);
+            nodal_apply_ml(c, op_ml, sp.tables.p, s_tabidx.p, nc, s_ml.p);
+            dim3 g((nk + 127)/128, nc*N_ML*3);
+            k_fill_ml<<<g, 128, 0, s>>>(nk, nk_sub, s_ml.p, d_kmap_idx.p, d_kmap_w.p, res.ML.p);
+            PRSD_CUDA(cudaGetLastError());
+            c.launches++;
+        }
+    }
     // ---- 1-D functionals
     s_linmain.ensure((size_t)nc*lin_main.nout);
     lin_main.apply(c, sp.tables.p, d_tabL.p, nc, s_linmain.p);

@@ -55,6 +55,12 @@ struct PTPlan {
     int n_1loop_sub = 0;
     DevBuf<int> d_olmap_idx;        // [1000][8]
     DevBuf<double> d_olmap_w;       // [1000][8]
+    // the same for the I / K and ImnOneLoop operators on k_interp (PTPlan ctor): nk_sub == nk when the list is not thinned
+    std::vector<double> k_sub;
+    int nk_sub = 0;
+    DevBuf<int> d_kmap_idx;         // [nk][8]
+    DevBuf<double> d_kmap_w;        // [nk][8]
+    DevBuf<double> s_ml;            // [c][21][nk_sub]
     // scratch
     DevBuf<double> s_op1, s_lin1, s_ik, s_mlp, s_mln, s_linmain, s_small, s_ol, s_plk;
     DevBuf<int> s_slot, s_rowA, s_rowB, s_tabidx;

@@ -161,9 +161,13 @@ def test_plan_matches_one_off_calls_and_golden(plin, cosmo, golden, tight):
     I, K, J = eng.get(res, 'I')[0], eng.get(res, 'K')[0], eng.get(res, 'J')[0]
     k = eng.k_interp
     sel = np.arange(30, 250, 31)
-    assert np.max(np.abs(I[10][sel] - pygcl.Imn(plin)(k[sel], 2, 2))) <= 1e-12*np.max(np.abs(I[10]))
-    assert np.max(np.abs(K[6][sel] - pygcl.Kmn(plin)(k[sel], 1, 1))) <= 1e-12*np.max(np.abs(K[6]))
     Pk = plin(k)
+    # below k = 0.01 the plan integrates every 6th point of a long k list and fills the others by 8-point Lagrange
+    # interpolation in ln k (plan.cu, PTPlan ctor); a one-off call with a short list integrates every k it is given
+    direct = k[sel] >= 0.01
+    for tab, ref in ((I[10], pygcl.Imn(plin)(k[sel], 2, 2)), (K[6], pygcl.Kmn(plin)(k[sel], 1, 1))):
+        assert direct.sum() >= 3 and np.max(np.abs(tab[sel] - ref)[direct]) <= 1e-12*np.max(np.abs(tab))
+        assert relerr_floor(tab[sel], ref, Pk[sel]).max() < 1e-6
     # ImnOneLoop comes from the one-lane-per-node kernel in the plan and from the DMMA operator in the one-off pygcl
     # calls: same nodes, different kernels and summation orders
     ML = eng.get(res, 'ML')[0]
