@@ -39,6 +39,7 @@ struct NodalArgs {
 struct SpecML {
     static const int NSLOT = 4, MINB = 2, NACC = 19, NW = 9, NOUT = 21, THREADS = NL_THREADS;
     static const bool PREFETCH_W = false;    // W one iteration ahead: no gain here (1.453 vs 1.456 ms, 128 registers)
+    static const bool DOUBLE_BUF = true;     // P(a) and the per-warp partial sums ping-pong between two buffers: one barrier per k
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
         const double La = pa[0], Da = pa[1], Va = pa[2], Wa = pa[3];
@@ -107,6 +108,7 @@ struct SpecDiag {
     static const int NSLOT = DIAG_R, MINB = DIAG_R <= 3 ? 3 : (DIAG_R <= 4 ? 2 : 1), NACC = NC*DIAG_R, NW = NC, NOUT = NC*DIAG_R;
     static const int THREADS = DIAG_R <= 4 ? NL_THREADS : 2*NL_THREADS;
     static const bool PREFETCH_W = true;     // the float4 of W one iteration ahead: 0.935 -> 0.907 ms (one register quad)
+    static const bool DOUBLE_BUF = false;    // 2 x 4 x 752 outer nodes would not leave room for two CTAs per SM
     __device__ __forceinline__ static void accumulate(double* acc, const double* pa, const double* pb, const double* w)
     {
 #pragma unroll
@@ -126,6 +128,48 @@ struct SpecDiag {
     }
 };
 
+// Warp-wide sums of N per-lane accumulators, transposing as they go: at the step with lane mask M the lanes with the
+// bit clear keep the lower half of their array and receive the other lanes' lower half, the lanes with the bit set
+// the upper half -- N/2 + N/4 + ... + 1 ~ N 64-bit shuffles and additions in all (19 accumulators: 21) against 5 N for
+// a butterfly per accumulator and N tensor MMAs + 2 N shuffles + 3 N additions for the MMA-assisted form used before
+// (an FP64 MMA m8n8k4 holds the FP64 pipe as long as four DFMA).  On return a[0] of lane l is the total of
+// accumulator `idx` if `valid` (odd sizes are padded with zeros, whose sums land on the invalid lanes).
+template <int N, int MASK>
+struct WarpTransposeSum {
+    __device__ __forceinline__ static void run(double* a, int lane, int& idx, int& nv)
+    {
+        constexpr int H = (N + 1)/2;
+        const bool up = (lane & MASK) != 0;
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            const double lo = a[i], hi = (i + H < N) ? a[i + H] : 0.0;
+            const double send = up ? lo : hi, keep = up ? hi : lo;
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+        }
+        idx += up ? H : 0;
+        nv = up ? max(nv - H, 0) : min(nv, H);
+        WarpTransposeSum<H, MASK/2>::run(a, lane, idx, nv);
+    }
+};
+template <int N>
+struct WarpTransposeSum<N, 0> {
+    __device__ __forceinline__ static void run(double*, int, int&, int&) { static_assert(N == 1, "more than 32 accumulators"); }
+};
+template <int MASK>
+struct WarpTransposeSum<1, MASK> {
+    // one value left and lane bits to spare: plain exchange, both lanes end with the sum (the lower one reports it)
+    __device__ __forceinline__ static void run(double* a, int lane, int& idx, int& nv)
+    {
+        a[0] += __shfl_xor_sync(0xffffffffu, a[0], MASK);
+        if (lane & MASK) nv = 0;
+        WarpTransposeSum<1, MASK/2>::run(a, lane, idx, nv);
+    }
+};
+template <>
+struct WarpTransposeSum<1, 0> {
+    __device__ __forceinline__ static void run(double*, int, int&, int&) {}
+};
+
 // (Tried and rejected this round: staging the tables in binary32.  Rounding the TABLE is harmless -- the error of
 // a knot is common to every node that reads it and cancels wherever the kernels cancel -- and halves the table
 // wavefronts, but the kernel then runs into the P(a) reads and the global stream and gains only ~10 %; with the
@@ -135,11 +179,12 @@ __global__ void __launch_bounds__(Spec::THREADS, Spec::MINB)
 k_nodal_apply(const NodalArgs g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NBUF = Spec::DOUBLE_BUF ? 2 : 1;
+    constexpr int NWARP = Spec::THREADS/32;
     double* tabs = reinterpret_cast<double*>(smem_raw);                 // [4][TAB_MPAD]
-    double* PaS = tabs + Spec::NSLOT*TAB_MPAD;                             // [4][max_outer]
-    double* red = PaS + Spec::NSLOT*g.max_outer;                           // [(Spec::THREADS/32)][NACC]
-    double* fin = red + (Spec::THREADS/32)*Spec::NACC;                            // [NACC]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(fin + Spec::NACC + (Spec::NACC & 1));
+    double* PaS = tabs + Spec::NSLOT*TAB_MPAD;                             // [NBUF][4][max_outer]
+    double* red = PaS + NBUF*Spec::NSLOT*g.max_outer;                      // [NBUF][NWARP][NACC]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + NBUF*NWARP*Spec::NACC + ((NBUF*NWARP*Spec::NACC) & 1));
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -158,23 +203,40 @@ k_nodal_apply(const NodalArgs g)
         for (int s = 0; s < Spec::NSLOT; s++)
             bulk_copy_g2s(tabs + s*TAB_MPAD, g.tables + (size_t)g.slot_tab[tile*Spec::NSLOT + s]*TAB_MPAD, bytes, mbar);
     }
-    mbar_wait(mbar, 0);
 
     // the offsets of the NEXT k of this CTA are fetched during the current one, and the first node of a k is
-    // requested before the P(a) pass: the k loop starts without a chain of exposed L2 round trips
+    // requested before the P(a) pass: the k loop starts without a chain of exposed L2 round trips.  The same for the
+    // first outer node of this lane (stencil start and coordinate): the P(a) pass of the next k starts from registers.
     int ik = blockIdx.y;
     int64_t o0_next = 0, o1_next = 0, n0_next = 0, n1_next = 0;
+    int aj_next = 0;
+    double as_next = 0.0;
     if (ik < g.nk) {
         o0_next = g.outer_off[ik]; o1_next = g.outer_off[ik + 1];
         n0_next = g.node_off[ik];  n1_next = g.node_off[ik + 1];
+        if (tid < (int)(o1_next - o0_next)) { aj_next = g.a_j0[o0_next + tid]; as_next = g.a_s[o0_next + tid]; }
     }
-    for (; ik < g.nk; ik += k_stride) {
+    mbar_wait(mbar, 0);
+
+    // finish k: the outputs are formed straight from the per-warp partial sums
+    auto finish = [&](int k_done, const double* rbuf) {
+        if (tid < Spec::NOUT) {
+            double fac;
+            const int src = Spec::source(tid, fac);
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) s += rbuf[w*Spec::NACC + src];
+            Spec::store(g, tile, k_done, tid, fac*s);
+        }
+    };
+    int par = 0, ik_prev = -1;
+    for (; ik < g.nk; ik += k_stride, par ^= (NBUF - 1)) {
         const int64_t o0 = o0_next, n0 = n0_next, n1 = n1_next;
         const int n_out = (int)(o1_next - o0);
-        if (ik + k_stride < g.nk) {
-            o0_next = g.outer_off[ik + k_stride]; o1_next = g.outer_off[ik + k_stride + 1];
-            n0_next = g.node_off[ik + k_stride];  n1_next = g.node_off[ik + k_stride + 1];
-        }
+        const int aj_first = aj_next;
+        const double as_first = as_next;
+        double* Pa = PaS + par*Spec::NSLOT*g.max_outer;
+        double* rd = red + par*NWARP*Spec::NACC;
         // the index word and the stencil coordinate of the NEXT node of this lane are loaded one iteration ahead: the
         // shared-memory reads depend on them, and an exposed L2 round trip per node was the largest stall
         int64_t node = n0 + tid;
@@ -188,18 +250,29 @@ k_nodal_apply(const NodalArgs g)
                 for (int v = 0; v < NV; v++) w_next[v] = __ldg(g.W + (int64_t)v*g.n_nodes + node);
             }
         }
+        if (ik + k_stride < g.nk) {
+            o0_next = g.outer_off[ik + k_stride]; o1_next = g.outer_off[ik + k_stride + 1];
+            n0_next = g.node_off[ik + k_stride];  n1_next = g.node_off[ik + k_stride + 1];
+        }
         // ---- P(a) of the four spectra for every outer node of this k
         for (int o = tid; o < n_out; o += Spec::THREADS) {
-            const int j0 = g.a_j0[o0 + o];
+            const int j0 = (o == tid) ? aj_first : g.a_j0[o0 + o];
             double c[4];
-            lagrange4(__ldg(g.a_s + o0 + o), c);
+            lagrange4((o == tid) ? as_first : __ldg(g.a_s + o0 + o), c);
 #pragma unroll
             for (int s = 0; s < Spec::NSLOT; s++) {
                 const double* t = tabs + s*TAB_MPAD + j0;
-                PaS[s*g.max_outer + o] = fma(c[3], t[3], fma(c[2], t[2], fma(c[1], t[1], c[0]*t[0])));
+                Pa[s*g.max_outer + o] = fma(c[3], t[3], fma(c[2], t[2], fma(c[1], t[1], c[0]*t[0])));
             }
         }
+        if (ik + k_stride < g.nk && tid < (int)(o1_next - o0_next)) {
+            aj_next = g.a_j0[o0_next + tid];
+            as_next = g.a_s[o0_next + tid];
+        }
         __syncthreads();
+        // with two buffers the barrier above is the only one of a k: it also orders every warp's partial sums of the
+        // previous k before they are read here, and this k's P(a) / partial sums go to the other buffer
+        if (Spec::DOUBLE_BUF && ik_prev >= 0) finish(ik_prev, red + (par ^ 1)*NWARP*Spec::NACC);
 
         double acc[Spec::NACC];
 #pragma unroll
@@ -236,32 +309,26 @@ k_nodal_apply(const NodalArgs g)
             for (int s = 0; s < Spec::NSLOT; s++) {
                 const double* t = tabs + s*TAB_MPAD + j0;
                 pb[s] = fma(c[3], t[3], fma(c[2], t[2], fma(c[1], t[1], c[0]*t[0])));
-                pa[s] = PaS[s*g.max_outer + ol];
+                pa[s] = Pa[s*g.max_outer + ol];
             }
             Spec::accumulate(acc, pa, pb, w);
         }
-        // ---- reduce over the CTA.  Across the warp: one FP64 tensor MMA with A = 1 adds the four lanes of every
-        // quad (B[k][n] = value of lane 4 n + k, D[m][n] = sum_k B[k][n]: lane l receives the sums of quads
-        // 2 (l % 4) and 2 (l % 4) + 1), two shuffles add the four pairs -- 4 shuffles instead of 10 per accumulator.
-#pragma unroll
-        for (int i = 0; i < Spec::NACC; i++) {
-            double c0 = 0.0, c1 = 0.0;
-            dmma_m8n8k4(c0, c1, 1.0, acc[i]);
-            double v = c0 + c1;
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (lane == 0) red[warp*Spec::NACC + i] = v;
+        // ---- reduce over the CTA: transposing warp sums (WarpTransposeSum), then one partial per warp in shared memory
+        {
+            int idx = 0, nv = Spec::NACC;
+            WarpTransposeSum<Spec::NACC, 16>::run(acc, lane, idx, nv);
+            if (nv > 0) rd[warp*Spec::NACC + idx] = acc[0];
         }
+        if (!Spec::DOUBLE_BUF) {
+            __syncthreads();
+            finish(ik, rd);
+            // the next k's writes of PaS and red are ordered after this k's reads by the barrier after the next P(a) pass
+        }
+        ik_prev = ik;
+    }
+    if (Spec::DOUBLE_BUF && ik_prev >= 0) {
         __syncthreads();
-        if (tid < Spec::NOUT) {
-            double fac;
-            const int src = Spec::source(tid, fac);
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < (Spec::THREADS/32); w++) s += red[w*Spec::NACC + src];
-            Spec::store(g, tile, ik, tid, fac*s);
-        }
-        // the next k's writes of PaS and red are ordered after this k's reads by the barrier after the next P(a) pass
+        finish(ik_prev, red + (par ^ 1)*NWARP*Spec::NACC);
     }
 }
 
@@ -278,7 +345,8 @@ static void launch_nodal(Context& ctx, const BilinearOp& op, const double* table
     a.b_node = geo.b_node.p;
     a.W = op.Wf.p; a.n_nodes = geo.n_nodes;
     a.tables = tables; a.slot_tab = slot_tab; a.out = out;
-    const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + Spec::NSLOT*geo.max_outer + ((Spec::THREADS/32) + 1)*Spec::NACC + 2)*sizeof(double) + 16;
+    const int nbuf = Spec::DOUBLE_BUF ? 2 : 1;
+    const size_t smem = (size_t)(Spec::NSLOT*TAB_MPAD + nbuf*Spec::NSLOT*geo.max_outer + nbuf*(Spec::THREADS/32)*Spec::NACC + 2)*sizeof(double) + 16;
     PRSD_REQUIRE(smem <= ctx.smem_optin, "nodal apply needs %zu B shared memory (> %zu)", smem, ctx.smem_optin);
     PRSD_CUDA(cudaFuncSetAttribute(k_nodal_apply<Spec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // k chunks: few enough to amortise the table staging, enough CTAs to fill 148 SMs x 2 when the batch is small
