@@ -23,7 +23,7 @@ CU_SOURCES = ['context.cu', 'bilinear.cu', 'nodal.cu', 'linear.cu', 'spectra.cu'
 CXX_SOURCES = ['quad.cpp', 'fftlog_host.cpp']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('PRSD_NVCC_EXTRA', '').split()
 
 
 def _newer(target, deps):

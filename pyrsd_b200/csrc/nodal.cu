@@ -170,6 +170,10 @@ struct WarpTransposeSum<1, 0> {
     __device__ __forceinline__ static void run(double*, int, int&, int&) {}
 };
 
+// (Tried and rejected, round 2: streaming the Lagrange coefficients c_1..c_3 as binary32 in a 16-byte node word instead of
+// rebuilding them from the stencil coordinate -- 13 FP64 operations fewer per node, 8 bytes more: ImnOneLoop unchanged,
+// one-loop tables 2.6 % slower.  Reading three knots instead of four (not parity-clean, timing experiment only): -5.7 % /
+// -1.2 %.  Neither the FP64 pipe nor the shared-memory pipe alone sets the time of these kernels.)
 // (Tried and rejected this round: staging the tables in binary32.  Rounding the TABLE is harmless -- the error of
 // a knot is common to every node that reads it and cancels wherever the kernels cancel -- and halves the table
 // wavefronts, but the kernel then runs into the P(a) reads and the global stream and gains only ~10 %; with the
