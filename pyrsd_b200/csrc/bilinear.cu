@@ -171,8 +171,20 @@ void geometry_chunk(const double* k, int nk, double qmax, const QuadConfig& cfg,
 }
 } // namespace
 
-std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
-                                            const QuadConfig& cfg, const KnotGrid& grid, int bank_mod)
+// Host part of make_geometry: everything up to the arrays the device receives (pure CPU, thread-safe: PTPlan builds the
+// geometries of its three operators concurrently while the device integrates the 1-D operators).
+struct GeometryHost {
+    int nk = 0, max_outer = 0;
+    std::vector<double> k;
+    std::vector<int64_t> node_off, outer_off;
+    HalfNodes H;                                   // merged outer-node arrays
+    std::vector<int> b_j0, n_ol, pack;
+    std::vector<double> b, wgt, b_coef, bs, as;
+    std::vector<int2> nodew;
+};
+
+std::shared_ptr<GeometryHost> make_geometry_host(const double* k, int nk, double qmax, const QuadConfig& cfg,
+                                                 const KnotGrid& grid, int bank_mod)
 {
     PRSD_REQUIRE(bank_mod == 4 || bank_mod == 16 || bank_mod == 32, "make_geometry: bank_mod must be 4, 16 or 32");
     const int BM = bank_mod;
@@ -186,11 +198,13 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     std::vector<GeoChunk> chunks(nchunk);
     std::vector<int> lo(nchunk + 1);
     for (int c = 0; c <= nchunk; c++) lo[c] = (int)((int64_t)nk*c/nchunk);
+    // the node count per k grows with k: hand out the expensive chunks (high k) first
     std::atomic<int> next{0};
     std::string failure;
     std::mutex fmu;
     auto worker = [&]() {
-        for (int c = next++; c < nchunk; c = next++) {
+        for (int t = next++; t < nchunk; t = next++) {
+            const int c = nchunk - 1 - t;
             try {
                 geometry_chunk(k + lo[c], lo[c + 1] - lo[c], qmax, cfg, grid, BM, chunks[c]);
             } catch (const std::exception& e) {
@@ -207,14 +221,17 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     }
     PRSD_REQUIRE(failure.empty(), "make_geometry: %s", failure.c_str());
 
-    auto g = std::make_shared<NodeGeometry>();
+    auto g = std::make_shared<GeometryHost>();
     g->nk = nk;
     g->k.assign(k, k + nk);
-    HalfNodes H;                                   // merged outer-node arrays
-    std::vector<int> b_j0, n_ol;
-    std::vector<double> b, wgt, b_coef;
-    g->h_node_off.assign(1, 0);
-    g->h_outer_off.assign(1, 0);
+    HalfNodes& H = g->H;
+    std::vector<int>& b_j0 = g->b_j0;
+    std::vector<int>& n_ol = g->n_ol;
+    std::vector<double>& b = g->b;
+    std::vector<double>& wgt = g->wgt;
+    std::vector<double>& b_coef = g->b_coef;
+    g->node_off.assign(1, 0);
+    g->outer_off.assign(1, 0);
     size_t tot_nodes = 0, tot_outer = 0;
     for (const GeoChunk& c : chunks) { tot_nodes += c.b.size(); tot_outer += c.H.a.size(); }
     b_j0.reserve(tot_nodes); n_ol.reserve(tot_nodes); b.reserve(tot_nodes); wgt.reserve(tot_nodes); b_coef.reserve(4*tot_nodes);
@@ -222,8 +239,8 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
     for (int ci = 0; ci < nchunk; ci++) {
         GeoChunk& c = chunks[ci];
         const int64_t node_base = (int64_t)b.size(), outer_base = (int64_t)H.a.size();
-        for (size_t i = 1; i < c.node_off.size(); i++) g->h_node_off.push_back(node_base + c.node_off[i]);
-        for (size_t i = 1; i < c.H.outer_off.size(); i++) g->h_outer_off.push_back(outer_base + c.H.outer_off[i]);
+        for (size_t i = 1; i < c.node_off.size(); i++) g->node_off.push_back(node_base + c.node_off[i]);
+        for (size_t i = 1; i < c.H.outer_off.size(); i++) g->outer_off.push_back(outer_base + c.H.outer_off[i]);
         b_j0.insert(b_j0.end(), c.b_j0.begin(), c.b_j0.end());
         n_ol.insert(n_ol.end(), c.n_ol.begin(), c.n_ol.end());
         b.insert(b.end(), c.b.begin(), c.b.end());
@@ -236,46 +253,60 @@ std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int n
         g->max_outer = std::max(g->max_outer, c.max_outer);
         c = GeoChunk();                            // release the chunk's memory
     }
-    g->n_nodes = (int64_t)b.size();
-    g->n_outer = (int64_t)H.a.size();
+    // s = sum_m m c_m exactly reproduces the abscissa of a Lagrange rule of degree >= 1
+    g->bs.resize(b_j0.size());
+    g->as.resize(H.a_j0.size());
+    for (size_t i = 0; i < g->bs.size(); i++) g->bs[i] = b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3];
+    for (size_t i = 0; i < g->as.size(); i++) g->as[i] = H.a_coef[4*i + 1] + 2.0*H.a_coef[4*i + 2] + 3.0*H.a_coef[4*i + 3];
+    g->pack.resize(b_j0.size());
+    g->nodew.resize(b_j0.size());
+    for (size_t i = 0; i < b_j0.size(); i++) {
+        PRSD_REQUIRE(b_j0[i] >= 0 && b_j0[i] < 4096 && n_ol[i] >= 0 && n_ol[i] < (1 << 19), "node index does not fit the packed stream");
+        g->pack[i] = (n_ol[i] << 12) | b_j0[i];
+        const float sf = (float)g->bs[i];
+        int bits;
+        std::memcpy(&bits, &sf, sizeof(int));
+        g->nodew[i] = make_int2(g->pack[i], bits);
+    }
+    return g;
+}
+
+std::shared_ptr<NodeGeometry> upload_geometry(Context& ctx, const GeometryHost& h)
+{
+    auto g = std::make_shared<NodeGeometry>();
+    g->nk = h.nk;
+    g->k = h.k;
+    g->h_node_off = h.node_off;
+    g->h_outer_off = h.outer_off;
+    g->max_outer = h.max_outer;
+    g->n_nodes = (int64_t)h.b.size();
+    g->n_outer = (int64_t)h.H.a.size();
     cudaStream_t s = ctx.stream;
     g->outer_off.upload(g->h_outer_off, s);
     g->node_off.upload(g->h_node_off, s);
-    g->a_j0.upload(H.a_j0, s);
-    g->o_kid.upload(H.o_kid, s);
-    g->a.upload(H.a, s);
-    g->a_coef.upload(H.a_coef, s);
-    g->b_j0.upload(b_j0, s);
-    g->n_outer_local.upload(n_ol, s);
-    g->b.upload(b, s);
-    g->wgt.upload(wgt, s);
-    g->b_coef.upload(b_coef, s);
-    {
-        // s = sum_m m c_m exactly reproduces the abscissa of a Lagrange rule of degree >= 1
-        std::vector<double> bs(b_j0.size()), as(H.a_j0.size());
-        for (size_t i = 0; i < bs.size(); i++) bs[i] = b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3];
-        for (size_t i = 0; i < as.size(); i++) as[i] = H.a_coef[4*i + 1] + 2.0*H.a_coef[4*i + 2] + 3.0*H.a_coef[4*i + 3];
-        g->b_s.upload(bs, s);
-        g->a_s.upload(as, s);
-    }
-    {
-        std::vector<int> pack(b_j0.size());
-        for (size_t i = 0; i < b_j0.size(); i++) {
-            PRSD_REQUIRE(b_j0[i] >= 0 && b_j0[i] < 4096 && n_ol[i] >= 0 && n_ol[i] < (1 << 19), "node index does not fit the packed stream");
-            pack[i] = (n_ol[i] << 12) | b_j0[i];
-        }
-        g->b_pack.upload(pack, s);
-        std::vector<int2> nodew(b_j0.size());
-        for (size_t i = 0; i < b_j0.size(); i++) {
-            const float sf = (float)(b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3]);
-            int bits;
-            std::memcpy(&bits, &sf, sizeof(int));
-            nodew[i] = make_int2(pack[i], bits);
-        }
-        g->b_node.upload(nodew, s);
-    }
+    g->a_j0.upload(h.H.a_j0, s);
+    g->o_kid.upload(h.H.o_kid, s);
+    g->a.upload(h.H.a, s);
+    g->a_coef.upload(h.H.a_coef, s);
+    g->b_j0.upload(h.b_j0, s);
+    g->n_outer_local.upload(h.n_ol, s);
+    g->b.upload(h.b, s);
+    g->wgt.upload(h.wgt, s);
+    g->b_coef.upload(h.b_coef, s);
+    g->b_s.upload(h.bs, s);
+    g->a_s.upload(h.as, s);
+    g->b_pack.upload(h.pack, s);
+    g->b_node.upload(h.nodew, s);
     g->kdev.upload(g->k, s);
-    ctx.sync();   // the host vectors go out of scope
+    return g;       // copies from pageable memory are staged before cudaMemcpyAsync returns: h may be released
+}
+
+std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
+                                            const QuadConfig& cfg, const KnotGrid& grid, int bank_mod)
+{
+    auto h = make_geometry_host(k, nk, qmax, cfg, grid, bank_mod);
+    auto g = upload_geometry(ctx, *h);
+    ctx.sync();
     return g;
 }
 

@@ -54,6 +54,12 @@ struct NodeGeometry {
 std::shared_ptr<NodeGeometry> make_geometry(Context& ctx, const double* k, int nk, double qmax,
                                             const QuadConfig& cfg, const KnotGrid& grid, int bank_mod = 16);
 
+// the two halves of make_geometry: the host part touches no CUDA state and may run on any thread
+struct GeometryHost;
+std::shared_ptr<GeometryHost> make_geometry_host(const double* k, int nk, double qmax, const QuadConfig& cfg,
+                                                 const KnotGrid& grid, int bank_mod = 16);
+std::shared_ptr<NodeGeometry> upload_geometry(Context& ctx, const GeometryHost& h);
+
 struct BilinearOp {
     std::shared_ptr<NodeGeometry> geo;
     int ncol = 0;       // padded to a multiple of 8

@@ -82,7 +82,7 @@ k_linear_build(int nout, const LinOutDev* __restrict__ outs, ZonesDev Z, double*
     if (lane == 0) Omega[(size_t)o*TAB_MPAD + j] = total;
 }
 
-void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs)
+void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs, bool sync)
 {
     nout = (int)outs.size();
     PRSD_REQUIRE(nout > 0, "LinearOp: no outputs");
@@ -110,7 +110,9 @@ void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs)
     k_linear_build<<<grid, 256, 0, ctx.stream>>>(nout, dout.p, Z, Omega.p);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
-    ctx.sync();
+    // sync = false: the caller overlaps host work with the build; `dout` returns to the stream-ordered pool, which hands it
+    // out again only behind this kernel
+    if (sync) ctx.sync();
 }
 
 // ---------------------------------------------------------------- apply

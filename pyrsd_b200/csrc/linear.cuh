@@ -40,7 +40,7 @@ struct LinOutSpec {
 struct LinearOp {
     int nout = 0;
     DevBuf<double> Omega;      // [nout][TAB_MPAD]
-    void build(Context& ctx, const std::vector<LinOutSpec>& outs);
+    void build(Context& ctx, const std::vector<LinOutSpec>& outs, bool sync = true);
     // out[row][nout] = sum_j tables[tab_index[row]][j] * Omega[o][j]   (all device pointers)
     void apply(Context& ctx, const double* tables, const int* tab_index, int nrow, double* out) const;
 };

@@ -4,6 +4,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <future>
 
 namespace prsd {
 
@@ -95,42 +96,31 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         build_stage_ms[slot] += std::chrono::duration<double, std::milli>(now - t_lap).count();
         t_lap = now;
     };
-    // ---- one-loop tables: I00 I01 I11 I23 I32 I33 (all symmetric: 2 x the v > 0 half)
+    // ---- the k lists of the three 2-D operators
+    // The 2-D integrals I00, I01, I11, I23, I32, I33 are smooth functions of k outside the BAO range: below k = 0.01
+    // (where they are < 1e-3 P_L anyway) only every 6th point of the reference's 1000-point grid is integrated, above
+    // k = 1.2 every 3rd, and the others are filled by 8-point Lagrange interpolation in ln k (k_oneloop_combine).  J_mn
+    // and P_L, one cheap matrix product, stay on the full grid.  482 of 1000 points carry 64 % of the nodes; the
+    // interpolation error is below the point-to-point noise of the quadrature itself (measured on the dense
+    // fixtures: tables unchanged to < 4e-6 for k <= 1, 3e-5 of |table| for k > 1 where 2 I + 6 k^2 J P_L cancels 140 x).
     {
-        // The 2-D integrals I00, I01, I11, I23, I32, I33 are smooth functions of k outside the BAO range: below k = 0.01
-        // (where they are < 1e-3 P_L anyway) only every 6th point of the reference's 1000-point grid is integrated, above
-        // k = 1.2 every 3rd, and the others are filled by 8-point Lagrange interpolation in ln k (k_oneloop_combine).  J_mn
-        // and P_L, one cheap matrix product, stay on the full grid.  482 of 1000 points carry 64 % of the nodes; the
-        // interpolation error is below the point-to-point noise of the quadrature itself (measured on the dense
-        // fixtures: tables unchanged to < 4e-6 for k <= 1, 3e-5 of |table| for k > 1 where 2 I + 6 k^2 J P_L cancels 140 x).
-        {
-            std::vector<char> keep(ONELOOP_N, 0);
-            int lo = 0, hi = ONELOOP_N - 1;
-            while (lo < ONELOOP_N - 1 && k_1loop[lo] < 0.01) lo++;
-            while (hi > 0 && k_1loop[hi] > 1.2) hi--;
-            for (int i = lo; i <= hi; i++) keep[i] = 1;
-            for (int i = lo; i >= 0; i -= 6) keep[i] = 1;
-            for (int i = hi; i < ONELOOP_N; i += 3) keep[i] = 1;
-            keep[0] = keep[ONELOOP_N - 1] = 1;
-            std::vector<double> ksub, mw;
-            std::vector<int> midx;
-            lagrange_fill_map(k_1loop, keep, midx, mw, ksub);
-            n_1loop_sub = (int)ksub.size();
-            d_olmap_idx.upload(midx, c.stream);
-            d_olmap_w.upload(mw, c.stream);
-            k_1loop_sub = ksub;
-        }
-        auto geo = make_geometry(c, k_1loop_sub.data(), n_1loop_sub, 1e5, cfg, grid);
-        lap(0);
-        std::vector<ColSpec> cols;
-        for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
-        op_1loop.build(c, geo, cols, true);
-        // OneLoopP22Bar only ever needs I23 + 2/3 I32 + 1/5 I33 (OneLoopPS.cpp:164-185): fold the three columns
-        op_1loop.fold_columns(c, 3, {{4, 2.0/3.0}, {5, 1.0/5.0}}, 4);
-        op_1loop.to_float(c);
-        lap(1);
+        std::vector<char> keep(ONELOOP_N, 0);
+        int lo = 0, hi = ONELOOP_N - 1;
+        while (lo < ONELOOP_N - 1 && k_1loop[lo] < 0.01) lo++;
+        while (hi > 0 && k_1loop[hi] > 1.2) hi--;
+        for (int i = lo; i <= hi; i++) keep[i] = 1;
+        for (int i = lo; i >= 0; i -= 6) keep[i] = 1;
+        for (int i = hi; i < ONELOOP_N; i += 3) keep[i] = 1;
+        keep[0] = keep[ONELOOP_N - 1] = 1;
+        std::vector<double> ksub, mw;
+        std::vector<int> midx;
+        lagrange_fill_map(k_1loop, keep, midx, mw, ksub);
+        n_1loop_sub = (int)ksub.size();
+        d_olmap_idx.upload(midx, c.stream);
+        d_olmap_w.upload(mw, c.stream);
+        k_1loop_sub = ksub;
     }
-    // ---- thinned k_interp.  Below k = 0.01 every mode-coupling integral is < 1e-3 P_L(k) and a smooth function of k (no
+    // Thinned k_interp.  Below k = 0.01 every mode-coupling integral is < 1e-3 P_L(k) and a smooth function of k (no
     // BAO structure enters yet), but a k there costs as many CTA set-ups, P(a) passes and reductions as one at k = 0.3
     // for 1/15 of the nodes: on a long ascending list (rsd's 250-point k_interp has 156 points below 0.01) the operators
     // are integrated at points >= 0.29 apart in ln k there (every 6th of k_interp) and the others are filled by 8-point
@@ -159,57 +149,85 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         d_kmap_idx.upload(midx, c.stream);
         d_kmap_w.upload(mw, c.stream);
     }
-    // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
-    if (!only_oneloop) {
-        auto geo = make_geometry(c, k_sub.data(), nk_sub, 1e5, cfg, grid, 4);     // DMMA lane layout: 4 nodes per k-step
-        lap(0);
-        std::vector<ColSpec> cols;
-        // both spectra are P_L here, so P(a) P(b) is the same on the two halves of the v domain and the
-        // non-symmetric kernels simply use f(u, v) + f(u, -v) (ColSpec sign 0): 29 columns, 4 n-tiles
-        for (int id = 0; id < 16; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
-        for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
-        op_ik.build(c, geo, cols);
-        lap(1);
+    // ---- node geometry of the three operators on host threads (no CUDA state is touched there) ...
+    const bool want_ik = !only_oneloop, want_ml = with_ml && !only_oneloop;
+    const QuadConfig cfg_ml = cfg.ml_variant();
+    auto f_1loop = std::async(std::launch::async, [&] { return make_geometry_host(k_1loop_sub.data(), n_1loop_sub, 1e5, cfg, grid, 16); });
+    std::future<std::shared_ptr<GeometryHost>> f_ik, f_ml;
+    // DMMA lane layout for I / K: 4 nodes per k-step
+    if (want_ik) f_ik = std::async(std::launch::async, [&] { return make_geometry_host(k_sub.data(), nk_sub, 1e5, cfg, grid, 4); });
+    if (want_ml) f_ml = std::async(std::launch::async, [&] { return make_geometry_host(k_sub.data(), nk_sub, 10.0, cfg_ml, grid, 16); });
+    // ---- ... while the device integrates the 1-D operators (product integration, ~0.2 s of kernels, nothing waits on them)
+    try {
+        {
+            std::vector<LinOutSpec> o;
+            for (int id : {0, 1, 4})
+                for (int i = 0; i < ONELOOP_N; i++) o.push_back({LK_JMN, id, k_1loop[i], 1e-5, 1e5, 1.0});
+            lin_1loop.build(c, o, false);
+        }
+        if (!only_oneloop) {
+            std::vector<LinOutSpec> o;
+            for (int j = 0; j < 6; j++)
+                for (int i = 0; i < nk; i++) o.push_back({LK_JMN, J_IDS[j], k_interp[i], 1e-5, 1e5, 1.0});
+            // sigma_v^2(k) integrates from 1e-5 up to 0.5 k (PowerSpectrum.cpp:60-62)
+            for (int i = 0; i < nk; i++) {
+                // for 0.5 k < 1e-5 the reference integrates "backwards" and returns a negative number
+                const double hi = 0.5*k_interp[i];
+                if (hi >= 1e-5) o.push_back({LK_SIGV, 0, 0.0, 1e-5, hi, 1.0});
+                else            o.push_back({LK_SIGV, 0, 0.0, hi, 1e-5, -1.0});
+            }
+            o.push_back({LK_SIGV, 0, 0.0, 1e-5, 1e2, 1.0});
+            if (with_zel) {
+                for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_XZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
+                for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_YZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
+            }
+            lin_main.build(c, o, false);
+            lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}}, false);
+            lin_kurt.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}}, false);
+            d_kinterp.upload(k_interp, c.stream);
+        }
+        {
+            const auto now = std::chrono::steady_clock::now();      // host time to enqueue the 1-D builds
+            build_stage_ms[2] += std::chrono::duration<double, std::milli>(now - t_lap).count();
+            t_lap = now;
+        }
+        // ---- one-loop tables: I00 I01 I11 I23 I32 I33 (all symmetric: 2 x the v > 0 half)
+        {
+            auto geo = upload_geometry(c, *f_1loop.get());
+            std::vector<ColSpec> cols;
+            for (int id : {KID_F00, KID_F01, KID_F11, KID_F23, KID_F32, KID_F33}) cols.push_back({id, +1, 2.0*INV8PI2});
+            op_1loop.build(c, geo, cols, true);
+            // OneLoopP22Bar only ever needs I23 + 2/3 I32 + 1/5 I33 (OneLoopPS.cpp:164-185): fold the three columns
+            op_1loop.fold_columns(c, 3, {{4, 2.0/3.0}, {5, 1.0/5.0}}, 4);
+            op_1loop.to_float(c);
+        }
+        // ---- I_mn, K_mn on k_interp (Imn.cpp:120-140, Kmn.cpp:118-138 conventions)
+        if (want_ik) {
+            auto geo = upload_geometry(c, *f_ik.get());
+            std::vector<ColSpec> cols;
+            // both spectra are P_L here, so P(a) P(b) is the same on the two halves of the v domain and the
+            // non-symmetric kernels simply use f(u, v) + f(u, -v) (ColSpec sign 0): 29 columns, 4 n-tiles
+            for (int id = 0; id < 16; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? 2.0*INV8PI2 : INV8PI2});
+            for (int id = KID_K00; id <= KID_K20SB; id++) cols.push_back({id, kernel_is_symmetric(id) ? +1 : 0, kernel_is_symmetric(id) ? INV4PI2 : 0.5*INV4PI2});
+            op_ik.build(c, geo, cols);
+        }
+        // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
+        if (want_ml) {
+            auto geo = upload_geometry(c, *f_ml.get());
+            op_ml.build(c, geo, ml_columns(), true);
+            op_ml.to_float(c);
+        }
+    } catch (...) {
+        // the host tasks reference locals of this frame: let them finish before unwinding
+        if (f_1loop.valid()) f_1loop.wait();
+        if (f_ik.valid()) f_ik.wait();
+        if (f_ml.valid()) f_ml.wait();
+        throw;
     }
-    // ---- ImnOneLoop: QMAX = 10, v in [-1, 1] (ImnOneLoop.cpp:12-13, 82-93)
-    if (with_ml && !only_oneloop) {
-        auto geo = make_geometry(c, k_sub.data(), nk_sub, 10.0, cfg.ml_variant(), grid);
-        lap(0);
-        op_ml.build(c, geo, ml_columns(), true);
-        op_ml.to_float(c);
-        lap(1);
-    }
-    // ---- 1-D operators
     {
-        std::vector<LinOutSpec> o;
-        for (int id : {0, 1, 4})
-            for (int i = 0; i < ONELOOP_N; i++) o.push_back({LK_JMN, id, k_1loop[i], 1e-5, 1e5, 1.0});
-        lin_1loop.build(c, o);
-        lap(2);
-    }
-    if (!only_oneloop) {
-        std::vector<LinOutSpec> o;
-        for (int j = 0; j < 6; j++)
-            for (int i = 0; i < nk; i++) o.push_back({LK_JMN, J_IDS[j], k_interp[i], 1e-5, 1e5, 1.0});
-        // sigma_v^2(k) integrates from 1e-5 up to 0.5 k (PowerSpectrum.cpp:60-62)
-        for (int i = 0; i < nk; i++) {
-            // for 0.5 k < 1e-5 the reference integrates "backwards" and returns a negative number
-            const double hi = 0.5*k_interp[i];
-            if (hi >= 1e-5) o.push_back({LK_SIGV, 0, 0.0, 1e-5, hi, 1.0});
-            else            o.push_back({LK_SIGV, 0, 0.0, hi, 1e-5, -1.0});
-        }
-        o.push_back({LK_SIGV, 0, 0.0, 1e-5, 1e2, 1.0});
-        if (with_zel) {
-            for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_XZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
-            for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_YZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
-        }
-        lin_main.build(c, o);
-        lap(3);
-    }
-    if (!only_oneloop) {
-        lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}});
-        lin_kurt.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}});
-        d_kinterp.upload(k_interp, c.stream);
+        const auto now = std::chrono::steady_clock::now();          // host geometry (the longest of the three) + uploads
+        build_stage_ms[0] += std::chrono::duration<double, std::milli>(now - t_lap).count();
+        t_lap = now;
     }
     d_k1loop.upload(k_1loop, c.stream);
     lap(4);

@@ -68,7 +68,8 @@ struct PTPlan {
     DevBuf<int> d_tabL, d_tabSq, d_tab22;
     int idx_nc_a = -1, idx_nc_b = -1;
     double build_seconds = 0.0;
-    double build_stage_ms[8] = {0};    // 0 node geometry (host) + upload, 1 W operators, 2 J on the one-loop grid, 3 main 1-D operators, 4 rest
+    double build_stage_ms[8] = {0};    // host wall clock: 2 enqueue of the 1-D operator builds, 0 node geometry of the three 2-D
+                                       // operators (host threads, concurrent with those builds) + uploads + W builds, 4 drain
 
     PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool ml, bool zel, bool only1l = false);
     // stage A only: the four one-loop tables (left in sp and in res.oneloop)

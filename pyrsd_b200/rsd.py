@@ -111,7 +111,8 @@ class PTEngine(object):
         L.prsd_plan_build_profile.argtypes = [_vp, _dp]
         L.prsd_plan_build_profile.restype = C.c_int
         N.check(L.prsd_plan_build_profile(self.plan.ptr, out))
-        return dict(geometry_host_ms=out[0], w_operators_ms=out[1], j_oneloop_grid_ms=out[2], linear_main_ms=out[3], rest_ms=out[4])
+        # the host builds the node geometry of the three 2-D operators on threads while the device integrates the 1-D ones
+        return dict(geometry_uploads_w_operators_ms=out[0], enqueue_1d_operators_ms=out[2], drain_ms=out[4])
 
     # ------------------------------------------------------------------ spectra
     def spectra(self, k, T, n_s, amp, h, Omega0_m, Omega0_b, Tcmb=2.7255):
