@@ -319,7 +319,9 @@ int prsd_spectra_reload_device(prsd_spectra* sp, const double* d_k, const double
  *     prsd_spectra_reload(sp, k, T, pars);  prsd_plan_run_async(plan, sp, &res);
  *     prsd_galaxy_power_async(g, sp, res, ..., out_i, &ticket_i);
  * and out_i is complete after prsd_galaxy_wait_copy(g, ticket_i); its copy to the host runs on a second stream
- * under the PT kernels of step i + 1.  Same results as the blocking calls, bit for bit. */
+ * under the PT kernels of step i + 1, and the input copies of step i + 1 (k, T, pars, par, stoch) run on a third stream
+ * under the kernels of step i.  prsd_galaxy_power_async with k == mu == NULL reuses the evaluation points of the previous
+ * asynchronous call (same npts).  Same results as the blocking calls, bit for bit. */
 int prsd_spectra_reload(prsd_spectra* sp, const double* k, const double* T, const double* pars);   /* shapes of prsd_spectra_create */
 int prsd_plan_run_async(prsd_plan* plan, prsd_spectra* sp, prsd_result** res);
 int prsd_galaxy_power_async(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw, const int* cmap,

@@ -22,6 +22,7 @@ struct prsd_result { PTResult r; Context* ctx = nullptr; };
 struct prsd_galaxy {
     GalaxyModel g;
     DevBuf<double> dk, dmu, dout;
+    int async_npts = 0;             // evaluation points resident in dk / dmu from the last asynchronous call that passed them
     prsd_galaxy(Context& c, const GalaxyConfig& cfg, const double* km, int nkm, const double* ki, int nki) : g(c, cfg, km, nkm, ki, nki) {}
 };
 struct prsd_gridop { GridOp op; DevBuf<double> din, dout; prsd_gridop(Context& c, int nb, int nk, int nmu, const double* w) : op(c, nb, nk, nmu, w) {} };
@@ -757,10 +758,14 @@ int prsd_galaxy_power(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, int nw
                       const double* stoch, int npts, const double* k, const double* mu, double* out)
 {
     return guarded(dev_of(g), [&] {
-        PRSD_REQUIRE(g && sp && res && par && stoch && k && mu && out, "null argument");
+        PRSD_REQUIRE(g && sp && res && par && stoch && out, "null argument");
+        PRSD_REQUIRE((k == nullptr) == (mu == nullptr), "k and mu must both be given or both be NULL");
         Context& c = *g->g.ctx;
-        g->dk.upload(k, npts, c.stream);
-        g->dmu.upload(mu, npts, c.stream);
+        if (k) {
+            g->dk.upload(k, npts, c.stream);
+            g->dmu.upload(mu, npts, c.stream);
+            g->async_npts = npts;
+        } else PRSD_REQUIRE(g->async_npts == npts && npts > 0, "k == NULL reuses the points of the previous asynchronous call (%d), not %d", g->async_npts, npts);
         g->dout.ensure((size_t)nw*npts);
         g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p, out);
     });
@@ -771,10 +776,14 @@ int prsd_galaxy_power_async(prsd_galaxy* g, prsd_spectra* sp, prsd_result* res, 
                             const double* stoch, int npts, const double* k, const double* mu, double* out, long long* ticket)
 {
     return guarded(dev_of(g), [&] {
-        PRSD_REQUIRE(g && sp && res && par && stoch && k && mu && out, "null argument");
+        PRSD_REQUIRE(g && sp && res && par && stoch && out, "null argument");
+        PRSD_REQUIRE((k == nullptr) == (mu == nullptr), "k and mu must both be given or both be NULL");
         Context& c = *g->g.ctx;
-        g->dk.upload(k, npts, c.stream);
-        g->dmu.upload(mu, npts, c.stream);
+        if (k) {
+            g->dk.upload(k, npts, c.stream);
+            g->dmu.upload(mu, npts, c.stream);
+            g->async_npts = npts;
+        } else PRSD_REQUIRE(g->async_npts == npts && npts > 0, "k == NULL reuses the points of the previous asynchronous call (%d), not %d", g->async_npts, npts);
         if (g->dout.n < (size_t)nw*npts) { g->g.wait(); g->dout.ensure((size_t)nw*npts); }   // a copy may still read the old block
         g->g.power(sp->s, res->r, nw, cmap, par, stoch, npts, g->dk.p, g->dmu.p, g->dout.p, out, false);
         if (ticket) *ticket = g->g.last_ticket();

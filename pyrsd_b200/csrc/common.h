@@ -119,6 +119,10 @@ struct Context {
     explicit Context(int dev);
     ~Context();
     void sync() { PRSD_CUDA(cudaStreamSynchronize(stream)); }
+    // second stream for host -> device input copies of the asynchronous entry points: the inputs of batch i + 1 travel
+    // while the kernels of batch i run (created on first use)
+    cudaStream_t upload_stream = nullptr;
+    cudaStream_t uploads();
     cudaEvent_t prof_event();
     void prof_collect();           // sync + fold pending event pairs into prof_ms / prof_count
     void prof_reset();

@@ -180,8 +180,15 @@ Context::~Context()
     for (int t = 0; t < PROF_NTAGS; t++)
         for (auto& pr : prof_pending[t]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
+    if (upload_stream) { cudaStreamSynchronize(upload_stream); cudaStreamDestroy(upload_stream); }
     if (stream) cudaStreamDestroy(stream);
     pool_trim(device);
+}
+
+cudaStream_t Context::uploads()
+{
+    if (!upload_stream) PRSD_CUDA(cudaStreamCreateWithFlags(&upload_stream, cudaStreamNonBlocking));
+    return upload_stream;
 }
 
 cudaEvent_t Context::prof_event()

@@ -818,6 +818,7 @@ GalaxyModel::~GalaxyModel()
     if (copy_stream) cudaStreamSynchronize(copy_stream);
     for (cudaEvent_t e : copy_done) if (e) cudaEventDestroy(e);
     if (copy_event) cudaEventDestroy(copy_event);
+    if (ev_par_ready) { if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream); cudaEventDestroy(ev_par_ready); cudaEventDestroy(ev_par_free); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }
 
@@ -892,8 +893,28 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         ident_n = (int)id.size();
     }
     const int* d_map = cmap ? d_cmap.p : d_ident.p;
-    d_par.upload(par, (size_t)nw*GAL_NPAR, s);
-    d_stoch.upload(stoch, (size_t)nw*GAL_NPAIR*GAL_NSTOCH, s);
+    if (!sync) {
+        // one batch ahead of the kernels on the upload stream (see SpectraBatch::reload_host)
+        cudaStream_t up = c.uploads();
+        if (!ev_par_ready) {
+            PRSD_CUDA(cudaEventCreateWithFlags(&ev_par_ready, cudaEventDisableTiming));
+            PRSD_CUDA(cudaEventCreateWithFlags(&ev_par_free, cudaEventDisableTiming));
+            PRSD_CUDA(cudaEventRecord(ev_par_free, s));
+        }
+        if (d_par.n < (size_t)nw*GAL_NPAR || d_stoch.n < (size_t)nw*GAL_NPAIR*GAL_NSTOCH) {
+            PRSD_CUDA(cudaStreamSynchronize(s));      // growing: the old blocks may still be read (once per size)
+            d_par.ensure((size_t)nw*GAL_NPAR);
+            d_stoch.ensure((size_t)nw*GAL_NPAIR*GAL_NSTOCH);
+        }
+        PRSD_CUDA(cudaStreamWaitEvent(up, ev_par_free, 0));
+        d_par.upload(par, (size_t)nw*GAL_NPAR, up);
+        d_stoch.upload(stoch, (size_t)nw*GAL_NPAIR*GAL_NSTOCH, up);
+        PRSD_CUDA(cudaEventRecord(ev_par_ready, up));
+        PRSD_CUDA(cudaStreamWaitEvent(s, ev_par_ready, 0));
+    } else {
+        d_par.upload(par, (size_t)nw*GAL_NPAR, s);
+        d_stoch.upload(stoch, (size_t)nw*GAL_NPAIR*GAL_NSTOCH, s);
+    }
     ratio1.ensure(nw);
     ratio2.ensure(nw);
     k_gal_ratios<<<(nw + 127)/128, 128, 0, s>>>(nw, d_par.p, ratio1.p, ratio2.p);
@@ -1021,6 +1042,7 @@ void GalaxyModel::power(SpectraBatch& sp, PTResult& pt, int nw, const int* cmap,
         PRSD_CUDA(cudaEventRecord(done, copy_stream));
         copy_ticket++;
     }
+    if (!sync && ev_par_free) PRSD_CUDA(cudaEventRecord(ev_par_free, s));
     if (sync) wait();
 }
 

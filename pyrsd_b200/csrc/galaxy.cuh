@@ -98,6 +98,9 @@ struct GalaxyModel {
     DevBuf<double> d_loaded;
     unsigned loaded_mask = 0;
     void set_loaded(unsigned mask, const double* h_loaded);     // mask == 0 clears
+    // asynchronous mode: walker parameters (and evaluation points) go up on the context's upload stream behind ev_par_free
+    // (= the previous call's kernels have read them), the main stream waits for ev_par_ready
+    cudaEvent_t ev_par_ready = nullptr, ev_par_free = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_event = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};      // end of the device-to-host copies of the last two power() calls

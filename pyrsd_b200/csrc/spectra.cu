@@ -382,11 +382,34 @@ void SpectraBatch::reload_device(const double* d_k, const double* d_T, const dou
 
 void SpectraBatch::reload_host(const double* k, const double* T, const double* pars)
 {
-    cudaStream_t s = ctx->stream;
-    in_k.upload(k, (size_t)ncosmo*nspl, s);
-    in_T.upload(T, (size_t)ncosmo*nspl, s);
-    in_pars.upload(pars, (size_t)ncosmo*8, s);
+    // The copies run on the upload stream, one batch ahead of the kernels: they only wait until the previous batch's
+    // table build has read the staging (early in that batch), the main stream only waits for their end.
+    cudaStream_t s = ctx->stream, up = ctx->uploads();
+    if (!ev_in_ready) {
+        PRSD_CUDA(cudaEventCreateWithFlags(&ev_in_ready, cudaEventDisableTiming));
+        PRSD_CUDA(cudaEventCreateWithFlags(&ev_in_free, cudaEventDisableTiming));
+        in_k.ensure((size_t)ncosmo*nspl);
+        in_T.ensure((size_t)ncosmo*nspl);
+        in_pars.ensure((size_t)ncosmo*8);
+        PRSD_CUDA(cudaEventRecord(ev_in_free, s));       // whatever the main stream still does with fresh blocks comes first
+    }
+    PRSD_CUDA(cudaStreamWaitEvent(up, ev_in_free, 0));
+    in_k.upload(k, (size_t)ncosmo*nspl, up);
+    in_T.upload(T, (size_t)ncosmo*nspl, up);
+    in_pars.upload(pars, (size_t)ncosmo*8, up);
+    PRSD_CUDA(cudaEventRecord(ev_in_ready, up));
+    PRSD_CUDA(cudaStreamWaitEvent(s, ev_in_ready, 0));
     reload_device(in_k.p, in_T.p, in_pars.p);
+    PRSD_CUDA(cudaEventRecord(ev_in_free, s));
+}
+
+SpectraBatch::~SpectraBatch()
+{
+    if (ev_in_ready) {
+        if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
+        cudaEventDestroy(ev_in_ready);
+        cudaEventDestroy(ev_in_free);
+    }
 }
 
 void SpectraBatch::rescale_linear(const double* fac_host)

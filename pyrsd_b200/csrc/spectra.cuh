@@ -45,6 +45,10 @@ struct SpectraBatch {
     // run the host buffers must be page-locked, and they must stay unchanged until the stream has passed them.
     void reload_host(const double* k, const double* T, const double* pars);
     DevBuf<double> in_k, in_T, in_pars;
+    // reload_host copies on the context's upload stream: ev_in_ready = the staging holds the new inputs (the main stream
+    // waits for it), ev_in_free = the kernels reading the staging have run (the next upload waits for it)
+    cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr;
+    ~SpectraBatch();
     int table_index(int cosmo, int kind) const { return cosmo*SP_NKIND + kind; }
     const double* table_ptr(int cosmo, int kind) const { return tables.p + (size_t)table_index(cosmo, kind)*TAB_MPAD; }
     // multiply P_L (spline amplitude and tables) of cosmology c by fac

@@ -353,8 +353,10 @@ class PTStream(object):
             N.check(L.prsd_spectra_reload(self.sp.ptr, s['k'].ptr, s['T'].ptr, s['pars'].ptr))
         self.eng.run(self.sp, result=self.res, sync=False)
         t = C.c_longlong()
+        # the evaluation points go up with the first batch and stay on the device
+        kk, mm = (self.h_kk.ptr, self.h_mm.ptr) if self.n == 0 else (None, None)
         N.check(L.prsd_galaxy_power_async(self.gal.ptr, self.sp.ptr, self.res.ptr, self.nc, None, s['wpar'].ptr, s['stoch'].ptr,
-                                          self.npts, self.h_kk.ptr, self.h_mm.ptr, s['out'].ptr, C.byref(t)))
+                                          self.npts, kk, mm, s['out'].ptr, C.byref(t)))
         s['ticket'] = t.value
         self.n += 1
         return t.value
@@ -372,7 +374,8 @@ class PTStream(object):
 
     def bytes_per_step(self):
         s = self.slots[0]
-        h2d = sum(s[n].array.nbytes for n in ('k', 'T', 'pars', 'wpar', 'stoch')) + self.h_kk.array.nbytes + self.h_mm.array.nbytes
+        # per step: the spectra and the walker parameters; the evaluation points (k, mu) go up once with the first batch
+        h2d = sum(s[n].array.nbytes for n in ('k', 'T', 'pars', 'wpar', 'stoch'))
         return h2d, s['out'].array.nbytes
 
 
