@@ -360,8 +360,10 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e/e2e_steps, "steps": e2e_steps,
                 "how": "rsd.PTStream (prsd_spectra_reload / prsd_plan_run_async / prsd_galaxy_power_async): every step copies its "
-                       "inputs from NumPy arrays to page-locked slots and to the device and its P(k, mu) back to page-locked host "
-                       "memory; the device-to-host copy of step i runs on a second stream under the PT kernels of step i + 1; one "
+                       "inputs (spectra T(k), cosmological and walker parameters, stochasticity) from NumPy arrays to page-locked "
+                       "slots and to the device and its P(k, mu) back to page-locked host memory; the device-to-host copy of step i "
+                       "runs on a second stream under the PT kernels of step i + 1 and the input copies of step i + 1 on a third "
+                       "stream under the kernels of step i; the fixed (k, mu) evaluation grid goes up once with the first batch; one "
                        "CUDA-event pair around all steps including the final drain",
                 "blocking": {"value": world*B*blk_steps/(ms_blk*1e-3), "ms_per_step": ms_blk/blk_steps,
                              "how": "prsd_spectra_create / prsd_plan_run / prsd_galaxy_power with pageable host buffers, "
