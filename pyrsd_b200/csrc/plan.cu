@@ -4,6 +4,8 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <future>
 
 namespace prsd {
@@ -97,18 +99,21 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         t_lap = now;
     };
     // ---- the k lists of the three 2-D operators
-    // The 2-D integrals I00, I01, I11, I23, I32, I33 are smooth functions of k outside the BAO range: below k = 0.01
-    // (where they are < 1e-3 P_L anyway) only every 6th point of the reference's 1000-point grid is integrated, above
-    // k = 1.2 every 3rd, and the others are filled by 8-point Lagrange interpolation in ln k (k_oneloop_combine).  J_mn
-    // and P_L, one cheap matrix product, stay on the full grid.  482 of 1000 points carry 64 % of the nodes; the
-    // interpolation error is below the point-to-point noise of the quadrature itself (measured on the dense
-    // fixtures: tables unchanged to < 4e-6 for k <= 1, 3e-5 of |table| for k > 1 where 2 I + 6 k^2 J P_L cancels 140 x).
+    // The 2-D integrals I00, I01, I11, I23, I32, I33 and J00, J01, J11 are smooth functions of k outside the BAO range:
+    // below k = 0.01 (where the 2-D integrals are < 1e-3 P_L anyway) and above k = 1.2 only a subset of the reference's
+    // 1000-point grid is integrated and the others are filled by 8-point Lagrange interpolation in ln k
+    // (k_oneloop_combine); P_L is evaluated at every point.  The interpolation error is below the point-to-point noise
+    // of the quadrature itself (measured on the dense fixtures: tables unchanged to < 4e-6 for k <= 1, < 3e-5 of |table|
+    // for k > 1 where 2 I + 6 k^2 J P_L cancels 140 x).
     {
         std::vector<char> keep(ONELOOP_N, 0);
         int lo = 0, hi = ONELOOP_N - 1;
         while (lo < ONELOOP_N - 1 && k_1loop[lo] < 0.01) lo++;
         while (hi > 0 && k_1loop[hi] > 1.2) hi--;
         for (int i = lo; i <= hi; i++) keep[i] = 1;
+        // every 6th point below k = 0.01, every 3rd above 1.2: 482 of 1000 points carry 64 % of the nodes.  (Measured, round 2:
+        // every 12th / 6th would take another 9 % off the 2-D operator, but the tables above k = 1 then move by up to 7e-5
+        // of their value -- 2 I + 6 k^2 J P_L cancels 140 x there -- against 2e-5 with this choice.)
         for (int i = lo; i >= 0; i -= 6) keep[i] = 1;
         for (int i = hi; i < ONELOOP_N; i += 3) keep[i] = 1;
         keep[0] = keep[ONELOOP_N - 1] = 1;
@@ -119,6 +124,13 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         d_olmap_idx.upload(midx, c.stream);
         d_olmap_w.upload(mw, c.stream);
         k_1loop_sub = ksub;
+        // J00, J01, J11: the same subset below k = 1.2 (J_mn(k) is a smooth function of k: the BAO structure of P_L is
+        // integrated over), every point above -- 6 k^2 J P_L is one side of the 140-fold cancellation there and the fill
+        // would cost a third of the margin to the 5e-5 bound (measured: 1.9e-5 -> 2.6e-5 ... 3.6e-5)
+        for (int i = hi; i < ONELOOP_N; i++) keep[i] = 1;
+        lagrange_fill_map(k_1loop, keep, midx, mw, k_1loop_j);
+        d_jmap_idx.upload(midx, c.stream);
+        d_jmap_w.upload(mw, c.stream);
     }
     // Thinned k_interp.  Below k = 0.01 every mode-coupling integral is < 1e-3 P_L(k) and a smooth function of k (no
     // BAO structure enters yet), but a k there costs as many CTA set-ups, P(a) passes and reductions as one at k = 0.3
@@ -160,9 +172,10 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     // ---- ... while the device integrates the 1-D operators (product integration, ~0.2 s of kernels, nothing waits on them)
     try {
         {
+            // J00, J01, J11 on their subset of the one-loop grid (k_1loop_j), filled to all 1000 points in k_oneloop_combine
             std::vector<LinOutSpec> o;
             for (int id : {0, 1, 4})
-                for (int i = 0; i < ONELOOP_N; i++) o.push_back({LK_JMN, id, k_1loop[i], 1e-5, 1e5, 1.0});
+                for (double kj : k_1loop_j) o.push_back({LK_JMN, id, kj, 1e-5, 1e5, 1.0});
             lin_1loop.build(c, o, false);
         }
         if (!only_oneloop) {
@@ -260,29 +273,38 @@ long long PTPlan::nodes_total() const
 // ------------------------------------------------------------------ packing
 __global__ void k_oneloop_combine(int ncosmo, int nsub, const double* __restrict__ op1 /*[c][nsub][8]*/,
                                   const int* __restrict__ midx /*[1000][8]*/, const double* __restrict__ mw /*[1000][8]*/,
-                                  const double* __restrict__ lin1 /*[c][3000]*/, const double* __restrict__ plk /*[c][1000]*/,
+                                  int nj, const int* __restrict__ jidx /*[1000][8]*/, const double* __restrict__ jw /*[1000][8]*/,
+                                  const double* __restrict__ lin1 /*[c][3][nj]*/, const double* __restrict__ plk /*[c][1000]*/,
                                   const double* __restrict__ k1, double* __restrict__ ol /*[c][4][1000]*/)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
     if (i >= ONELOOP_N) return;
-    // the four 2-D integrals at k_i: computed there, or interpolated (8-point Lagrange in ln k) from the computed points
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    // the four 2-D integrals and J00, J01, J11 at k_i: computed there, or interpolated (8-point Lagrange in ln k) from the
+    // computed points
+    double a[4] = {0.0, 0.0, 0.0, 0.0}, j[3] = {0.0, 0.0, 0.0};
     const double* base = op1 + (size_t)c*nsub*8;
+    const double* jb = lin1 + (size_t)c*3*nj;
 #pragma unroll
     for (int l = 0; l < 8; l++) {
         const double w = mw[(size_t)i*8 + l];
-        if (w == 0.0) continue;
-        const double* r = base + (size_t)midx[(size_t)i*8 + l]*8;
+        if (w != 0.0) {
+            const double* r = base + (size_t)midx[(size_t)i*8 + l]*8;
 #pragma unroll
-        for (int t = 0; t < 4; t++) a[t] = fma(w, r[t], a[t]);
+            for (int t = 0; t < 4; t++) a[t] = fma(w, r[t], a[t]);
+        }
+        const double wj = jw[(size_t)i*8 + l];
+        if (wj != 0.0) {
+            const int m = jidx[(size_t)i*8 + l];
+#pragma unroll
+            for (int t = 0; t < 3; t++) j[t] = fma(wj, jb[(size_t)t*nj + m], j[t]);
+        }
     }
-    const double* j = lin1 + (size_t)c*3*ONELOOP_N;
     const double k = k1[i], P = plk[(size_t)c*ONELOOP_N + i];
     double* o = ol + (size_t)c*4*ONELOOP_N;
     // OneLoopPS.cpp:56-132: 2 I_ab + 6 k^2 J_ab P_L ; P22bar = I23 + 2/3 I32 + 1/5 I33 (:164-185)
-    o[i]               = 2.0*a[0] + 6.0*k*k*j[i]*P;
-    o[ONELOOP_N + i]   = 2.0*a[1] + 6.0*k*k*j[ONELOOP_N + i]*P;
-    o[2*ONELOOP_N + i] = 2.0*a[2] + 6.0*k*k*j[2*ONELOOP_N + i]*P;
+    o[i]               = 2.0*a[0] + 6.0*k*k*j[0]*P;
+    o[ONELOOP_N + i]   = 2.0*a[1] + 6.0*k*k*j[1]*P;
+    o[2*ONELOOP_N + i] = 2.0*a[2] + 6.0*k*k*j[2]*P;
     o[3*ONELOOP_N + i] = a[3];         // I23 + 2/3 I32 + 1/5 I33, combined in the operator (PTPlan ctor)
 }
 
@@ -389,13 +411,14 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
     // ---- stage A: one-loop tables
     s_op1.ensure((size_t)(nc + 8)*n_1loop_sub*8);
     nodal_apply_diag(c, op_1loop, sp.tables.p, s_rowB.p, nc, s_op1.p);
-    s_lin1.ensure((size_t)nc*3*ONELOOP_N);
+    s_lin1.ensure((size_t)nc*3*k_1loop_j.size());
     lin_1loop.apply(c, sp.tables.p, d_tabL.p, nc, s_lin1.p);
     s_plk.ensure((size_t)nc*ONELOOP_N);
     {
         dim3 g((ONELOOP_N + 255)/256, nc);
         k_plin_at<<<g, 256, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, ONELOOP_N, d_k1loop.p, s_plk.p);
-        k_oneloop_combine<<<g, 256, 0, s>>>(nc, n_1loop_sub, s_op1.p, d_olmap_idx.p, d_olmap_w.p, s_lin1.p, s_plk.p, d_k1loop.p,
+        k_oneloop_combine<<<g, 256, 0, s>>>(nc, n_1loop_sub, s_op1.p, d_olmap_idx.p, d_olmap_w.p, (int)k_1loop_j.size(),
+                                            d_jmap_idx.p, d_jmap_w.p, s_lin1.p, s_plk.p, d_k1loop.p,
                                             res.oneloop.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches += 2;

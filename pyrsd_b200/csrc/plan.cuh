@@ -55,6 +55,10 @@ struct PTPlan {
     int n_1loop_sub = 0;
     DevBuf<int> d_olmap_idx;        // [1000][8]
     DevBuf<double> d_olmap_w;       // [1000][8]
+    // ... and the (larger) subset on which J00, J01, J11 are integrated
+    std::vector<double> k_1loop_j;
+    DevBuf<int> d_jmap_idx;         // [1000][8]
+    DevBuf<double> d_jmap_w;        // [1000][8]
     // the same for the I / K and ImnOneLoop operators on k_interp (PTPlan ctor): nk_sub == nk when the list is not thinned
     std::vector<double> k_sub;
     int nk_sub = 0;
