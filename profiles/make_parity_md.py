@@ -5,7 +5,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 d = json.load(open(os.path.join(HERE, 'r02_parity.json')))
-out = ['# Parity, round 2 (B200, `pytest -m gpu`: 74 passed)', '',
+out = ['# Parity, round 2 (B200, `pytest -m gpu`: 82 passed)', '',
        'Worst error per family of the CUDA path (through the C-ABI) against the reference C++ at tight tolerance on ALL 250',
        '`k_interp` points and all 1000 one-loop grid points, for the golden Planck15 spectrum and four cosmologies of `bench.py`\'s',
        'own synthetic batch (seed 20261019: #0, #1, and the two extreme tilts of the 256) -- `tests/golden/make_tight_dense.py`,',

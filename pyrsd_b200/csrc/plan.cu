@@ -4,8 +4,6 @@
 
 #include <chrono>
 #include <cmath>
-#include <cstdio>
-#include <cstdlib>
 #include <future>
 
 namespace prsd {
@@ -51,6 +49,10 @@ void PTResult::ensure(int ncosmo_, int nk_)
 
 // Interpolation map from the kept points of a k list to all of it: 8-point Lagrange in ln k for the points left out,
 // the identity for the kept ones.  idx / w [n][8]; ksub = the kept k.
+// The stencil of a point is chosen QUASI-UNIFORM at the spacing h of the interval that brackets it -- the kept point
+// nearest to x_c + (m - 3.5) h, m = 0..7 -- and falls back to the 8 nearest kept points at the ends of the list.  Where
+// the kept set changes density abruptly, the 8 nearest kept points would be 4 coarse + 4 fine ones, and Lagrange
+// interpolation on such a stencil has a Lebesgue constant of up to 21 (see thin_graded).
 static void lagrange_fill_map(const std::vector<double>& kfull, const std::vector<char>& keep, std::vector<int>& idx,
                               std::vector<double>& w, std::vector<double>& ksub)
 {
@@ -66,14 +68,55 @@ static void lagrange_fill_map(const std::vector<double>& kfull, const std::vecto
         while (j < nsub && pos[j] < i) j++;
         if (keep[i]) { idx[(size_t)i*NP] = j; w[(size_t)i*NP] = 1.0; continue; }
         const double x = std::log(kfull[i]);
-        const int a = std::min(std::max(j - NP/2, 0), nsub - NP);
+        int sel[NP];
+        bool ok = j >= 1 && j < nsub && nsub >= NP;
+        if (ok) {
+            const double h = xsub[j] - xsub[j - 1], xc = 0.5*(xsub[j] + xsub[j - 1]);
+            ok = xc - 3.5*h >= xsub[0] - 1e-9 && xc + 3.5*h <= xsub[nsub - 1] + 1e-9;
+            int last = -1;
+            for (int m = 0; m < NP && ok; m++) {
+                const double t = xc + (m - 3.5)*h;
+                const int c = (int)(std::lower_bound(xsub.begin(), xsub.end(), t) - xsub.begin());
+                int best = c;
+                if (c >= nsub || (c > 0 && t - xsub[c - 1] <= xsub[c] - t)) best = c - 1;
+                if (best <= last) best = last + 1;
+                if (best >= nsub) { ok = false; break; }
+                sel[m] = last = best;
+            }
+        }
+        if (!ok) {
+            const int a = std::min(std::max(j - NP/2, 0), std::max(nsub - NP, 0));
+            for (int m = 0; m < NP; m++) sel[m] = std::min(a + m, nsub - 1);
+        }
         for (int l = 0; l < NP; l++) {
             double wl = 1.0;
-            for (int m = 0; m < NP; m++) if (m != l) wl *= (x - xsub[a + m])/(xsub[a + l] - xsub[a + m]);
-            idx[(size_t)i*NP + l] = a + l;
+            for (int m = 0; m < NP; m++) if (m != l) wl *= (x - xsub[sel[m]])/(xsub[sel[l]] - xsub[sel[m]]);
+            idx[(size_t)i*NP + l] = sel[l];
             w[(size_t)i*NP + l] = wl;
         }
     }
+}
+
+// Thin a uniformly (log-)spaced stretch of a k list away from index `from` (kept) in direction dir = -1 / +1 down to one
+// point in `max_gap`.  The gaps GROW gradually (1 2 2 3 3 4 5 6 7 8 10 12): where the kept set jumps from every point to
+// every 6th, the 8 nearest kept points of a left-out point are 4 fine + 4 coarse ones, and Lagrange interpolation on such a
+// stencil has a Lebesgue constant of 21 -- it amplified the point-to-point quadrature noise of the computed values (4e-7)
+// to 9e-6 in K01 at k = 0.0086.  Graded (and with the stencil choice of lagrange_fill_map) the constant is 3.2 and the
+// interpolation error of the tight reference values themselves is 1.4e-7 of max(|value|, P_L): the fine points sit where
+// the functions start to bend.  (A quasi-uniform stencil on the ungraded set: constant 1.5, but 1.7e-6.)
+static void thin_graded(std::vector<char>& keep, int from, int dir, int max_gap)
+{
+    static const int gaps[] = {1, 2, 2, 3, 3, 4, 5, 6, 7, 8, 10, 12};
+    const int n = (int)keep.size();
+    for (int i = from + dir; i >= 0 && i < n; i += dir) keep[i] = 0;
+    int i = from;
+    for (int s = 0;; s++) {
+        const int g = std::min(max_gap, gaps[std::min(s, 11)]);
+        i += dir*g;
+        if (i < 0 || i >= n) break;
+        keep[i] = 1;
+    }
+    keep[0] = keep[n - 1] = 1;
 }
 
 static const double INV8PI2 = 1.0/(8.0*M_PI*M_PI);
@@ -106,17 +149,20 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     // of the quadrature itself (measured on the dense fixtures: tables unchanged to < 4e-6 for k <= 1, < 3e-5 of |table|
     // for k > 1 where 2 I + 6 k^2 J P_L cancels 140 x).
     {
-        std::vector<char> keep(ONELOOP_N, 0);
+        std::vector<char> keep(ONELOOP_N, 1);
         int lo = 0, hi = ONELOOP_N - 1;
         while (lo < ONELOOP_N - 1 && k_1loop[lo] < 0.01) lo++;
         while (hi > 0 && k_1loop[hi] > 1.2) hi--;
-        for (int i = lo; i <= hi; i++) keep[i] = 1;
-        // every 6th point below k = 0.01, every 3rd above 1.2: 482 of 1000 points carry 64 % of the nodes.  (Measured, round 2:
-        // every 12th / 6th would take another 9 % off the 2-D operator, but the tables above k = 1 then move by up to 7e-5
-        // of their value -- 2 I + 6 k^2 J P_L cancels 140 x there -- against 2e-5 with this choice.)
-        for (int i = lo; i >= 0; i -= 6) keep[i] = 1;
-        for (int i = hi; i < ONELOOP_N; i += 3) keep[i] = 1;
-        keep[0] = keep[ONELOOP_N - 1] = 1;
+        // down to every 12th point below k = 0.01 (0.17 apart in ln k) and every 6th above 1.2 (0.08 apart), graded
+        // (thin_graded): ~390 of the 1000 points.  Measured on the dense fixtures
+        // (profiles/experiments/ol_thinning_exp.sh): tables unchanged for k <= 1 against (6, 3), 1.6e-5 ... 3.1e-5 of
+        // |table| above k = 1 (where 2 I + 6 k^2 J P_L cancels 140 x) against 1.7e-5 ... 3.1e-5; (12, 9) costs 3.8e-5 there
+        // for no further gain.
+        thin_graded(keep, lo, -1, 12);
+        // (no grading at the upper end: the quasi-uniform stencils of lagrange_fill_map on every 6th point measured 2.1e-5
+        // ... 3.1e-5 there, graded gaps 2.5e-5 ... 3.7e-5)
+        for (int i = hi + 1; i < ONELOOP_N; i++) keep[i] = ((i - hi) % 6 == 0) ? 1 : 0;
+        keep[ONELOOP_N - 1] = 1;
         std::vector<double> ksub, mw;
         std::vector<int> midx;
         lagrange_fill_map(k_1loop, keep, midx, mw, ksub);
@@ -135,9 +181,9 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     // Thinned k_interp.  Below k = 0.01 every mode-coupling integral is < 1e-3 P_L(k) and a smooth function of k (no
     // BAO structure enters yet), but a k there costs as many CTA set-ups, P(a) passes and reductions as one at k = 0.3
     // for 1/15 of the nodes: on a long ascending list (rsd's 250-point k_interp has 156 points below 0.01) the operators
-    // are integrated at points >= 0.29 apart in ln k there (every 6th of k_interp) and the others are filled by 8-point
-    // Lagrange interpolation in ln k (k_pack_ik, k_fill_ml).  Measured on the dense fixtures (tight reference on all 250
-    // k): the fill changes no I, K or ImnOneLoop value by more than 2.4e-7 of max(|value|, P_L).
+    // are integrated at points up to 0.29 apart in ln k there (every 6th of k_interp, graded: thin_graded) and the others are
+    // filled by 8-point Lagrange interpolation in ln k (k_pack_ik, k_fill_ml).  Measured on the dense fixtures (tight
+    // reference on all 250 k): the fill changes no I, K or ImnOneLoop value by more than 1.4e-7 of max(|value|, P_L).
     if (!only_oneloop) {
         std::vector<char> keep(nk, 1);
         bool ascending = nk >= 64;
@@ -145,11 +191,12 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         if (ascending) {
             int lo = 0;
             while (lo < nk - 1 && k_interp[lo] < 0.01) lo++;
-            double last = std::log(k_interp[lo]);
-            for (int i = lo - 1; i > 0; i--) {
-                const double x = std::log(k_interp[i]);
-                if (last - x < 0.29) keep[i] = 0; else last = x;
-            }
+            // the spacing of the list below the threshold decides how far it can be thinned: one point in >= 0.29 of ln k
+            const double dln = lo > 1 ? std::log(k_interp[lo]/k_interp[0])/lo : 1.0;
+            const int max_gap = std::max(1, (int)std::ceil(0.29/dln - 1e-9));
+            bool uniform = lo > 8;
+            for (int i = 1; i <= lo && uniform; i++) uniform = std::fabs(std::log(k_interp[i]/k_interp[i - 1])/dln - 1.0) < 1e-6;
+            if (uniform && max_gap > 1) thin_graded(keep, lo, -1, max_gap);
             int kept = 0;
             for (int i = 0; i < nk; i++) kept += keep[i];
             if (kept < 16) keep.assign(nk, 1);
