@@ -415,6 +415,9 @@ class WindowFunctionTransfer(GriddedMultipoleTransfer):
                                       "padding divides 0 / 0 on the zero-padded high-k tail and returns NaN everywhere")
         op = self._operator()
         p, multi, dev = _prepare(power, self.grid.shape)
+        if return_xi and dev:
+            raise ValueError("return_xi is only available for host (NumPy) inputs: the correlation functions are copied out "
+                             "through host buffers")
         nw, nell, Nk, Npad = p.shape[0], len(self.ells), self.grid.Nk, len(self.k_pad)
         with (_CtxStream(self._ctx) if (dev or k_out is not None) else _NoStream()):
             poles = _empty_like(p, (nw, nell, Nk), dev)
