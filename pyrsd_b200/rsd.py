@@ -752,6 +752,79 @@ def _poles(self, k, ells, Nmu=40):
 GalaxySpectrum.poles = _poles
 
 
+def _pole_method(ell):
+    def method(self, k, **kwargs):
+        """P_ell(k) by Simpson's rule over 41 mu in [0, 1] (the ``tools.monopole`` ... ``tetrahexadecapole`` decorators of
+        rsd/tools.py:268-325 around ``power``; they use 42 samples when len(k) == 41, which the device rule -- an odd
+        number of samples -- does not reproduce: 41 is used throughout)"""
+        return _poles(self, np.atleast_1d(np.asarray(k, dtype=float)), ell, Nmu=41)
+    return method
+
+
+GalaxySpectrum.monopole = _pole_method(0)
+GalaxySpectrum.quadrupole = _pole_method(2)
+GalaxySpectrum.hexadecapole = _pole_method(4)
+GalaxySpectrum.tetrahexadecapole = _pole_method(6)
+
+
+def _apply_transfer(self, transfer):
+    """the power spectrum on the grid of ``transfer`` (a transfers.* object) with the transfer applied: grid binning,
+    multipoles, wedges, window convolution (power_dm.py:1046-1077)"""
+    import warnings
+    from . import transfers as T
+    g = transfer.grid
+    if isinstance(transfer, T.WindowFunctionTransfer):
+        kmin, kmax = float(np.nanmin(g.k)), float(np.nanmax(g.k))
+        if kmin < self.kmin:
+            warnings.warn("min k of window transfer (%s) is less than model's kmin (%.2e)" % (kmin, self.kmin))
+        if kmax > self.kmax:
+            warnings.warn("max k of window transfer (%s) is greater than model's kmax (%.2e)" % (kmax, self.kmax))
+    # the model is evaluated on the cells that hold modes (transfer.flatk / flatmu of the reference); the others carry
+    # zero weight in every transfer
+    ok = g.notnull
+    P = np.zeros(g.shape)
+    P[ok] = self.power(np.ascontiguousarray(g.k[ok]), np.ascontiguousarray(g.mu[ok]))
+    return transfer(P)
+
+
+GalaxySpectrum.apply_transfer = _apply_transfer
+
+
+def _derivative(self, k, mu, wrt, rel=1e-4):
+    """d P / d k' or d P / d mu' at the Alcock-Paczynski coordinates (k', mu') of the observed (k, mu), with the volume and
+    sound-horizon factors of ``tools.alcock_paczynski`` (power_gal.py:427-441).  The reference chains analytic
+    derivatives of every term; here a central difference of the undistorted model (alpha = 1) at (k', mu'), one batch of
+    two point sets (truncation error ~ rel^2 = 1e-8 of the curvature scale)."""
+    k = np.atleast_1d(np.asarray(k, dtype=np.float64))
+    mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+    if k.ndim == 1 and mu.ndim == 1 and len(mu) != len(k):
+        k, mu = k[:, None], mu[None, :]
+    kb, mub = np.broadcast_arrays(k, mu)
+    F = self.alpha_par/self.alpha_perp
+    fac = np.sqrt(1. + mub**2*(1./F**2 - 1.))
+    kt, mut = (kb/self.alpha_perp*fac).ravel(), (mub/F/fac).ravel()
+    saved = self.alpha_par, self.alpha_perp, self.alpha_drag
+    try:
+        self.alpha_par = self.alpha_perp = self.alpha_drag = 1.
+        if wrt == 'k':
+            h = rel*kt
+            lo, hi = self.power(kt - h, mut), self.power(kt + h, mut)
+        else:
+            # one-sided where the step would leave [0, 1]
+            h = np.full(len(mut), rel)
+            up, dn = np.minimum(mut + h, 1.), np.maximum(mut - h, 0.)
+            lo, hi, h = self.power(kt, dn), self.power(kt, up), 0.5*(up - dn)
+    finally:
+        self.alpha_par, self.alpha_perp, self.alpha_drag = saved
+    d = (np.atleast_1d(hi) - np.atleast_1d(lo))/(2.*h)
+    d = d*self.alpha_drag**3/(self.alpha_perp**2*self.alpha_par)
+    return np.squeeze(d.reshape(kb.shape))
+
+
+GalaxySpectrum.derivative_k = lambda self, k, mu: _derivative(self, k, mu, 'k')
+GalaxySpectrum.derivative_mu = lambda self, k, mu: _derivative(self, k, mu, 'mu')
+
+
 # the parameters that enter a walker row (pack_walker)
 _GRAD_PARAMS = ('sigma8_z', 'f', 'alpha_par', 'alpha_perp', 'alpha_drag', 'b1_cA', 'b1_cB', 'b1_sA', 'b1_sB', 'fs', 'fcB', 'fsB',
                 'sigma_c', 'sigma_sA', 'sigma_sB', 'NcBs', 'NsBsB', 'f_so', 'sigma_so', 'sigma_v')

@@ -147,3 +147,22 @@ class BiasToSigmaRelation(BiasToMassRelation):
         if self.sigmav_0 is None or self.M_0 is None:
             return self.evrard_sigmav(M)
         return self.sigmav_0*(M/self.M_0)**(1./3.)
+
+
+def mass_from_bias(bias, z, linearPS):
+    """halo mass [M_sun / h] of a linear bias at redshift ``z`` from the Tinker et al. bias and Sigma(R) of ``linearPS``
+    (a ``pygcl.LinearPS`` at any redshift), rsd/tools.py:655-691: the mean density is the z = 0 one, the growth between the
+    spectrum's redshift and ``z`` rescales sigma, the root is bracketed by [1e-5, 1e5] x 1e13.  ``bias`` may be an array
+    (one launch for all of them)."""
+    cosmo = linearPS.GetCosmology()
+    z_P = linearPS.GetRedshift()
+    Dz = 1. if z_P == z else cosmo.D_z(z)/cosmo.D_z(z_P)
+    b = np.asarray(bias, dtype=float)
+    out = bias_to_mass(linearPS._sp, np.full(b.size, Dz), b.ravel(), cosmo.rho_bar_z(0.), 200., 1e-5*MASS_NORM, 1e5*MASS_NORM,
+                       cmap=np.zeros(b.size, dtype=np.int32))
+    return float(out[0]) if b.ndim == 0 else out.reshape(b.shape)
+
+
+def sigma_from_bias(bias, z, linearPS):
+    """sigma [Mpc/h] = 3.6 (M(bias) / 5.4903e13)^(1/3) (rsd/tools.py:713-720)"""
+    return 3.6*(np.asarray(mass_from_bias(bias, z, linearPS))/5.4903e13)**(1./3)

@@ -115,3 +115,57 @@ def test_component_spectra(ref, models):
     grid = models['ap'].Pgal_cs(np.logspace(-2, -1, 4), np.linspace(0, 1, 3))
     assert grid.shape == (4, 3)
     assert models['ap'].Pgal_cs(np.logspace(-2, -1, 4), np.linspace(0, 1, 3), flatten=True).shape == (12,)
+
+
+def test_derivative_k_mu_chain_rule_vs_reference_alpha_derivatives(ref, models):
+    """derivative_k / derivative_mu (power_gal.py:427-441) through the chain rule the reference's analytic alpha_par and
+    alpha_perp derivatives use (rsd/power/gal/derivatives/alpha_par.py, alpha_perp.py): dP_obs/d alpha = D_k dk'/d alpha +
+    D_mu dmu'/d alpha - (volume factor derivative) P_obs, compared with the reference's values"""
+    for tag in ('ap', 'so'):
+        m = models[tag]
+        k, mu = ref['k'], ref['mu']
+        P = m.power(k, mu)
+        Dk, Dmu = m.derivative_k(k, mu), m.derivative_mu(k, mu)
+        ap, ae = m.alpha_par, m.alpha_perp
+        F = ap/ae
+        A = 1. + mu**2*(1./F**2 - 1.)
+        kp, mup = k/ae*np.sqrt(A), mu/F/np.sqrt(A)
+        # d/d alpha_par at fixed alpha_perp
+        dA = mu**2*(-2./F**3)/ae
+        dk_par = k/(2.*ae)*dA/np.sqrt(A)
+        dmu_par = mu*(-1./F**2/ae/np.sqrt(A) - 0.5/F*dA/A**1.5)
+        d_par = Dk*dk_par + Dmu*dmu_par - P/ap
+        want = ref[tag + '_d_alpha_par']
+        assert np.max(np.abs(d_par - want))/np.max(np.abs(want)) < TOL, tag
+        # d/d alpha_perp at fixed alpha_par: F = ap / ae, dF/dae = -F / ae
+        dA = mu**2*(-2./F**3)*(-F/ae)
+        dk_perp = -kp/ae + k/(2.*ae)*dA/np.sqrt(A)
+        dmu_perp = mu*(1./(F*ae)/np.sqrt(A) - 0.5/F*dA/A**1.5)
+        d_perp = Dk*dk_perp + Dmu*dmu_perp - 2.*P/ae
+        want = ref[tag + '_d_alpha_perp']
+        assert np.max(np.abs(d_perp - want))/np.max(np.abs(want)) < TOL, tag
+        assert np.array_equal(m.power(k, mu), P)          # the model is left untouched
+
+
+def test_multipole_shortcuts_apply_transfer_and_bias_functions(models, golden):
+    from pyrsd_b200 import pygcl, tools, transfers
+    m = models['ap']
+    k = np.logspace(-2, np.log10(0.3), 12)
+    mus = np.linspace(0., 1., 41)
+    P = m.power(k, mus)
+    w = transfers.simpson_weights(mus)
+    for ell, fn, kern in ((0, m.monopole, np.ones(41)), (2, m.quadrupole, 2.5*(3*mus**2 - 1.)),
+                          (4, m.hexadecapole, 9./8.*(35*mus**4 - 30.*mus**2 + 3.))):
+        assert np.max(np.abs(fn(k)/(P*kern*w).sum(-1) - 1)) < 1e-12, ell      # tools.monopole ... (rsd/tools.py:268-310)
+    t = transfers.MultipoleTransfer(k, [0, 2], Nmu=40)
+    assert np.max(np.abs(m.apply_transfer(t)/np.array(m.poles(k, [0, 2], Nmu=40)).T - 1)) < 1e-12
+    # mass_from_bias / sigma_from_bias (rsd/tools.py:655-720): the Tinker bias of the mass that comes back is the bias that
+    # went in, at the growth of the requested redshift
+    cosmo = golden_pygcl_cosmology(golden)
+    PL = pygcl.LinearPS(cosmo, 0.)
+    b = np.array([1.4, 2.2, 3.1])
+    M = tools.mass_from_bias(b, 0.55, PL)
+    R = (3.*M/(4.*np.pi*cosmo.rho_bar_z(0.)))**(1./3.)
+    assert np.max(np.abs(tools.bias_Tinker(cosmo.D_z(0.55)*PL.Sigma(R)) - b)) < 1e-6
+    assert isinstance(tools.mass_from_bias(2.2, 0.55, PL), float) and abs(tools.mass_from_bias(2.2, 0.55, PL)/M[1] - 1) < 1e-12
+    assert np.allclose(tools.sigma_from_bias(b, 0.55, PL), 3.6*(M/5.4903e13)**(1./3), rtol=1e-14)
