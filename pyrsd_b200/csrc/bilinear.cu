@@ -356,6 +356,12 @@ __global__ void k_build_w(int64_t n_nodes, int ncol, int ncol_used, int soa, con
     }
 }
 
+__global__ void k_w_to_float(int64_t n, const double* __restrict__ src, float* __restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
 void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols, bool soa_layout)
 {
     geo = g;
@@ -374,7 +380,16 @@ void BilinearOp::build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std:
         g->node_off.p, g->nk, g->kdev.p, g->a.p, g->n_outer_local.p, g->b.p, g->wgt.p, W.p);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
+    if (!soa) {
+        // the DMMA operator streams its fragments as binary32 too (same lane order): half the bytes of the dominant
+        // stream through the LSU; the entries' rounding errors (6e-8, independent from node to node) average out
+        Wh.alloc(W.n);
+        k_w_to_float<<<(unsigned)((W.n + 255)/256), 256, 0, ctx.stream>>>((int64_t)W.n, W.p, Wh.p);
+        PRSD_CUDA(cudaGetLastError());
+        ctx.launches++;
+    }
     ctx.sync();
+    if (!soa) W.release();
 }
 
 __global__ void k_fold_column(int64_t n, double* __restrict__ dst, const double* __restrict__ src, double coef)
@@ -431,8 +446,7 @@ template <int NT>
 __global__ void __launch_bounds__(BL_THREADS, 1)
 k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, const int64_t* __restrict__ node_off,
                  const int* __restrict__ a_j0, const double* __restrict__ a_coef,
-                 const int* __restrict__ b_j0, const int* __restrict__ n_outer_local,
-                 const double* __restrict__ b_coef, const double* __restrict__ W,
+                 const int2* __restrict__ b_node, const float* __restrict__ W,
                  const double* __restrict__ tables, const int* __restrict__ slot_tab,
                  const int* __restrict__ rowA, const int* __restrict__ rowB, double* __restrict__ out)
 {
@@ -483,22 +497,28 @@ k_bilinear_apply(int nk, int max_outer, const int64_t* __restrict__ outer_off, c
     for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = 0.0;
 
     const int64_t n0 = node_off[ik], n1 = node_off[ik + 1];
+    // (an explicit one-step-ahead prefetch of the node word and the fragments with the loop unrolled twice: 0.51 -> 0.71 ms;
+    // unrolled four times the compiler keeps the loads of four steps in flight)
+    // measured: unrolled 2x 0.60 ms, 4x 0.51 ms, 8x 0.53 ms
 #pragma unroll 4
     for (int64_t base = n0 + 4*warp; base < n1; base += 4*BL_WARPS) {
         const int64_t node = base + sub;
-        const int j0 = __ldg(b_j0 + node);
-        const int ol = __ldg(n_outer_local + node);
-        const double2 c01 = __ldg(reinterpret_cast<const double2*>(b_coef + 4*node));
-        const double2 c23 = __ldg(reinterpret_cast<const double2*>(b_coef + 4*node) + 1);
+        // one 8-byte node word (packed outer index | stencil start, stencil coordinate as binary32: the Lagrange
+        // coefficients are lagrange4(s), 13 FP64 operations) and four binary32 fragments of W per step: 5 global loads
+        // of 24 bytes per lane where round 1 had 8 of 72 (0.537 -> 0.51 ms; the LSU data pipe was at 68 %)
+        const int2 nw = __ldg(b_node + node);
+        const int j0 = nw.x & 4095, ol = nw.x >> 12;
+        double c[4];
+        lagrange4((double)__int_as_float(nw.y), c);
         double wf[NT];
-        const double* wrow = W + (base >> 2)*(32*NT) + lane;      // base is a multiple of 4 (node lists are padded)
+        const float* wrow = W + (base >> 2)*(32*NT) + lane;       // base is a multiple of 4 (node lists are padded)
 #pragma unroll
-        for (int j = 0; j < NT; j++) wf[j] = __ldg(wrow + 32*j);
+        for (int j = 0; j < NT; j++) wf[j] = (double)__ldg(wrow + 32*j);
         const double* t = tb + j0;
-        double pb = c01.x*t[0];
-        pb = fma(c01.y, t[1], pb);
-        pb = fma(c23.x, t[2], pb);
-        pb = fma(c23.y, t[3], pb);
+        double pb = c[0]*t[0];
+        pb = fma(c[1], t[1], pb);
+        pb = fma(c[2], t[2], pb);
+        pb = fma(c[3], t[3], pb);
         const double pp = pa[ol]*pb;
 #pragma unroll
         for (int j = 0; j < NT; j++) dmma_m8n8k4(acc[j][0], acc[j][1], pp, wf[j]);
@@ -551,7 +571,7 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
     dim3 grid(ntiles, nchunks);
     ProfScope prof(ctx, PROF_BILINEAR);
     k_bilinear_apply<NT><<<grid, BL_THREADS, smem, ctx.stream>>>(g.nk, pas_stride, g.outer_off.p, g.node_off.p,
-        g.a_j0.p, g.a_coef.p, g.b_j0.p, g.n_outer_local.p, g.b_coef.p, op.W.p, tables, slot_tab, rowA, rowB, out);
+        g.a_j0.p, g.a_coef.p, g.b_node.p, op.Wh.p, tables, slot_tab, rowA, rowB, out);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
 }
@@ -559,7 +579,7 @@ static void launch_apply(Context& ctx, const BilinearOp& op, const double* table
 void BilinearOp::apply(Context& ctx, const double* tables, const int* slot_tab, const int* rowA,
                        const int* rowB, int ntiles, double* out) const
 {
-    PRSD_REQUIRE(!soa, "BilinearOp::apply: operator was built for the nodal kernels");
+    PRSD_REQUIRE(!soa && Wh.p, "BilinearOp::apply: operator was built for the nodal kernels");
     switch (ncol/8) {
         case 1: launch_apply<1>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;
         case 2: launch_apply<2>(ctx, *this, tables, slot_tab, rowA, rowB, ntiles, out); break;

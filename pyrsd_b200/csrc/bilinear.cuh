@@ -73,6 +73,8 @@ struct BilinearOp {
     // ~2000 nodes of an integral -- measured on the dense fixtures: no table or ImnOneLoop integral moves by more than 2e-8.
     DevBuf<float4> Wf;
     int nvec = 0;
+    // DMMA operator: the fragments of W as binary32 in the lane order of w_index (build() converts and releases W)
+    DevBuf<float> Wh;
     void to_float(Context& ctx);        // SoA only: W -> Wf, releases W
     void build(Context& ctx, std::shared_ptr<NodeGeometry> g, const std::vector<ColSpec>& cols, bool soa_layout = false);
     // SoA operators only: column `dst` += sum_i coef_i * column src_i, then keep the first `ncol_keep` columns

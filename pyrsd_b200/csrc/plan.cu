@@ -299,7 +299,7 @@ size_t PTPlan::device_bytes() const
     size_t b = 0;
     for (const BilinearOp* op : {&op_1loop, &op_ik, &op_ml}) {
         if (!op->geo) continue;
-        b += op->W.n*sizeof(double) + op->Wf.n*sizeof(float4);
+        b += op->W.n*sizeof(double) + op->Wf.n*sizeof(float4) + op->Wh.n*sizeof(float);
     }
     if (op_1loop.geo) b += op_1loop.geo->bytes();
     if (op_ik.geo) b += op_ik.geo->bytes();

@@ -166,7 +166,9 @@ def test_plan_matches_one_off_calls_and_golden(plin, cosmo, golden, tight):
     # interpolation in ln k (plan.cu, PTPlan ctor); a one-off call with a short list integrates every k it is given
     direct = k[sel] >= 0.01
     for tab, ref in ((I[10], pygcl.Imn(plin)(k[sel], 2, 2)), (K[6], pygcl.Kmn(plin)(k[sel], 1, 1))):
-        assert direct.sum() >= 3 and np.max(np.abs(tab[sel] - ref)[direct]) <= 1e-12*np.max(np.abs(tab))
+        # same nodes and tables; the operator entries are rounded to binary32 per column, and the plan's column of a
+        # non-symmetric kernel is f(u, v) + f(u, -v) where the one-off call sums two separately rounded operators
+        assert direct.sum() >= 3 and np.max(np.abs(tab[sel] - ref)[direct]) <= 1e-7*np.max(np.abs(tab))
         assert relerr_floor(tab[sel], ref, Pk[sel]).max() < 1e-6
     # ImnOneLoop comes from the one-lane-per-node kernel in the plan and from the DMMA operator in the one-off pygcl
     # calls: same nodes, different kernels and summation orders
