@@ -47,6 +47,22 @@ out += ['', '| dark-matter blocks on the 200-point model grid | ' + ' | '.join((
 for k, v in sorted(d.get('galaxy', {}).items()):
     if k.startswith('dm/'):
         out.append('| %s | ' % k[3:] + ' | '.join('%.1e' % v[n][0] if n in v else '' for n in ('P_lin', 'P00', 'P01', 'P11_mu4', 'Pdv', 'Pvv', 'Pdd')) + ' |')
+if d.get('dark_matter'):
+    out += ['', '## DarkMatterSpectrum term accessors vs the UNMODIFIED reference class (200-point model grid)', '',
+            'Metric: |mine - ref| / max(|ref|, 0.1 P_L(k)), sums over terms against their largest constituent (`tests/test_gpu_dm.py`).', '',
+            '| case | worst term | max error | all terms below |', '|---|---|---|---|']
+    for k, v in sorted(d['dark_matter'].items()):
+        w = max(v.items(), key=lambda kv: kv[1])
+        out.append('| %s | %s | %.1e | %s |' % (k, w[0], w[1], '1e-5 (%d terms)' % len(v)))
+if d.get('biased'):
+    out += ['', '| BiasedSpectrum / HaloSpectrum moments | ' + ' | '.join('P_mu%d' % (2*i) for i in range(4)) + ' |', '|---|' + '---|'*4]
+    for k, v in sorted(d['biased'].items()):
+        out.append('| %s | ' % k + ' | '.join('%.1e' % v['P_mu%d' % (2*i)] for i in range(4)) + ' |')
+if d.get('correlation'):
+    out += ['', '## ExtrapolatedPowerSpectrum / SmoothedXiMultipoles vs the reference classes (`tests/test_gpu_xi.py`)', '',
+            '| quantity | max error |', '|---|---|']
+    for k, v in sorted(d['correlation'].items()):
+        out.append('| %s | %.1e |' % (k, v))
 out += ['', open(os.path.join(HERE, 'r02_parity_notes.md')).read()]
 open(os.path.join(HERE, 'r02_parity.md'), 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out[:24]))

@@ -227,8 +227,10 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
         }
         if (!only_oneloop) {
             std::vector<LinOutSpec> o;
+            // J_mn on the same thinned list as the 2-D operators (filled in k_pack_lin); sigma_v^2(k), whose upper limit
+            // moves with k, on every point
             for (int j = 0; j < 6; j++)
-                for (int i = 0; i < nk; i++) o.push_back({LK_JMN, J_IDS[j], k_interp[i], 1e-5, 1e5, 1.0});
+                for (int i = 0; i < nk_sub; i++) o.push_back({LK_JMN, J_IDS[j], k_sub[i], 1e-5, 1e5, 1.0});
             // sigma_v^2(k) integrates from 1e-5 up to 0.5 k (PowerSpectrum.cpp:60-62)
             for (int i = 0; i < nk; i++) {
                 // for 0.5 k < 1e-5 the reference integrates "backwards" and returns a negative number
@@ -396,24 +398,38 @@ __global__ void k_fill_ml(int nk, int nsub, const double* __restrict__ s, const 
     ML[(size_t)row*nk + i] = v;
 }
 
-__global__ void k_pack_lin(int nk, int nout, int with_zel, const double* __restrict__ s /*[c][nout]*/,
+__global__ void k_pack_lin(int nk, int nsub, const int* __restrict__ midx /*[nk][8]*/, const double* __restrict__ mw /*[nk][8]*/,
+                           int nout, int with_zel, const double* __restrict__ s /*[c][nout]*/,
                            const double* __restrict__ q3, const double* __restrict__ kurt,
                            double* __restrict__ J, double* __restrict__ sigk, double* __restrict__ scal,
                            double* __restrict__ X0, double* __restrict__ YY)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
     const double* r = s + (size_t)c*nout;
-    if (i < 6*nk) J[(size_t)c*6*nk + i] = r[i];
-    if (i < nk) sigk[(size_t)c*nk + i] = r[6*nk + i];
+    if (i < 6*nk) {
+        // computed at k_i, or interpolated from the computed points (PTPlan ctor)
+        const int j = i/nk, ik = i - j*nk;
+        const double* rj = r + (size_t)j*nsub;
+        double v = 0.0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const double w = mw[(size_t)ik*8 + l];
+            if (w != 0.0) v = fma(w, rj[midx[(size_t)ik*8 + l]], v);
+        }
+        J[(size_t)c*6*nk + i] = v;
+    }
+    r += 6*nsub;
+    if (i < nk) sigk[(size_t)c*nk + i] = r[i];
+    r += nk;
     if (i == 0) {
-        scal[c*4 + 0] = r[7*nk];
+        scal[c*4 + 0] = r[0];
         scal[c*4 + 1] = kurt ? kurt[c] : 0.0;
         scal[c*4 + 2] = q3[c];
         scal[c*4 + 3] = 0.0;
     }
     if (with_zel && i < ZEL_NR) {
-        X0[(size_t)c*ZEL_NR + i] = r[7*nk + 1 + i];
-        YY[(size_t)c*ZEL_NR + i] = r[7*nk + 1 + ZEL_NR + i];
+        X0[(size_t)c*ZEL_NR + i] = r[1 + i];
+        YY[(size_t)c*ZEL_NR + i] = r[1 + ZEL_NR + i];
     }
 }
 
@@ -528,7 +544,7 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res, bool sync)
     {
         const int nmax = std::max(6*nk, ZEL_NR);
         dim3 g((nmax + 127)/128, nc);
-        k_pack_lin<<<g, 128, 0, s>>>(nk, lin_main.nout, with_zel ? 1 : 0, s_linmain.p, s_small.p, s_small.p + nc,
+        k_pack_lin<<<g, 128, 0, s>>>(nk, nk_sub, d_kmap_idx.p, d_kmap_w.p, lin_main.nout, with_zel ? 1 : 0, s_linmain.p, s_small.p, s_small.p + nc,
                                     res.J.p, res.sigmasq_k.p, res.scalars.p, res.X0.p, res.YY.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches++;

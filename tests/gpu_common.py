@@ -1,5 +1,20 @@
 """shared helpers for the GPU parity tests"""
+import json
+import os
+
 import numpy as np
+
+
+def record_parity(section, tag, value):
+    """worst errors of a GPU parity test -> gpurun_out/r02_parity.json[section][tag] (rendered by profiles/make_parity_md.py)"""
+    try:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'r02_parity.json')
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur.setdefault(section, {})[tag] = value
+        json.dump(cur, open(path, 'w'), indent=1, sort_keys=True)
+    except OSError:
+        pass
 
 
 def golden_pygcl_cosmology(golden, tight=None):

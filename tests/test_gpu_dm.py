@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity
+from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity, record_parity
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -71,6 +71,7 @@ def test_dark_matter_terms_vs_reference_python(cosmo, engine, case):
         err = np.abs(mine - r)/scale
         worst[name] = float(err.max())
         failures = failures + [(name, float(err.max()), float(km[np.argmax(err)]))] if err.max() >= TOL else failures
+    record_parity('dark_matter', case, worst)
     assert not failures, (case, failures)
     # integrals off the model grid: the spline over the k_interp table (rsd/pt_integrals.py)
     kq = ref['kq']
@@ -80,7 +81,9 @@ def test_dark_matter_terms_vs_reference_python(cosmo, engine, case):
     # P(k, mu) = sum of mu^2i P[mu^2i]: measured against the largest of the moments at that k (they cancel at high k)
     big = sum(np.abs(ref['mu'][None, :]**(2*i)*np.interp(kq, km, np.abs(terms[n]))[:, None])
               for i, n in enumerate(['P_mu0', 'P_mu2', 'P_mu4', 'P_mu6'][:m.max_mu//2 + 1]) if not np.isnan(terms[n]).any())
-    assert np.max(np.abs(P - ref[case + '_power'])/np.maximum(np.abs(ref[case + '_power']), big)) < TOL
+    e_pow = float(np.max(np.abs(P - ref[case + '_power'])/np.maximum(np.abs(ref[case + '_power']), big)))
+    record_parity('dark_matter', case + '/power(k, mu)', {'power': e_pow})
+    assert e_pow < TOL
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/dm_ref.npz not generated")
@@ -95,7 +98,9 @@ def test_biased_spectrum_vs_reference_python(cosmo, engine, tag):
     assert np.allclose(h.k, km, rtol=1e-14)
     mom = np.array([h.P_mu0(km), h.P_mu2(km), h.P_mu4(km), h.P_mu6(km)])
     scale = np.maximum(np.abs(ref[tag + '_moments']), 1e-3*np.abs(ref[tag + '_moments'][0]))
-    assert np.max(np.abs(mom - ref[tag + '_moments'])/scale) < TOL
+    e_mom = np.max(np.abs(mom - ref[tag + '_moments'])/scale, axis=1)
+    record_parity('biased', tag, {('P_mu%d' % (2*i)): float(e) for i, e in enumerate(e_mom)})
+    assert e_mom.max() < TOL
     kq = ref['kq']
     momq = np.array([h.P_mu0(kq), h.P_mu2(kq), h.P_mu4(kq), h.P_mu6(kq)])
     scale = np.maximum(np.abs(ref[tag + '_moments_kq']), 1e-3*np.abs(ref[tag + '_moments_kq'][0]))

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity
+from tests.gpu_common import golden_pygcl_cosmology, b2_00, b2_01, stochasticity, record_parity
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -45,11 +45,14 @@ def test_extrapolated_power_and_xi_multipoles(golden):
     r = ref['r']
     xi0 = SmoothedXiMultipoles(model, r, [0, 2, 4], R=0., **KW)
     xi3 = SmoothedXiMultipoles(model, r, [0, 2], R=3., **KW)
-    for mine, want in ((xi0, ref['xi_R0']), (xi3, ref['xi_R3'])):
+    for name, mine, want in (('xi_ell(s), R = 0', xi0, ref['xi_R0']), ('xi_ell(s), R = 3', xi3, ref['xi_R3'])):
         assert mine.shape == want.shape
         # scale: the monopole at that separation (the higher multipoles cross zero)
         scale = np.maximum(np.abs(want), np.abs(want[:, :1]))
+        record_parity('correlation', name, float(np.max(np.abs(mine - want)/scale)))
         assert np.max(np.abs(mine - want)/scale) < 2e-4
+    record_parity('correlation', 'P(k, mu) inside [k_lo, k_hi]', float(err[inside].max()))
+    record_parity('correlation', 'P(k, mu) extrapolated (to k = 9)', float(err[~inside].max()))
     # the default k_lo = kmin / k_hi = kmax lies outside the reference's own fit grid: same error as there
     with pytest.raises(ValueError):
         ExtrapolatedPowerSpectrum(model)(np.array([1e-4]), mu)
