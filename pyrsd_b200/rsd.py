@@ -708,11 +708,16 @@ class GalaxySpectrum(object):
         ovr = None if states[0]['ovr'] is None else np.array([s['ovr'] for s in states])
         loaded = self._loaded_knots(kmodel)
         opts = corr is not None or ovr is not None or bool(loaded)
-        if opts or getattr(gal, '_opts', False):
+        if opts:
             eng.galaxy_options(gal, nw, corr, ovr, loaded)
-            gal._opts = opts
-        out = getattr(eng, 'galaxy_' + kind)(gal, self._spectra, self._result, par, stoch, *args,
-                                             cmap=np.zeros(nw, dtype=np.int32), **kw)
+        try:
+            out = getattr(eng, 'galaxy_' + kind)(gal, self._spectra, self._result, par, stoch, *args,
+                                                 cmap=np.zeros(nw, dtype=np.int32), **kw)
+        finally:
+            # the handle is shared by every model of this engine with the same grid and configuration (and by the
+            # streaming path): the optional inputs never outlive the call that set them
+            if opts:
+                eng.galaxy_options(gal)
         if np.isnan(out).any():
             raise ValueError("wavenumber range outside interpolation domain: AP-distorted k outside [%.4e, %.4e]; "
                              "try adjusting `kmin` / `kmax`" % (kmodel[0], kmodel[-1]))
