@@ -130,4 +130,11 @@ struct HalfNodes {
 void build_half_nodes(const double* k, int nk, double qmax, const QuadConfig& cfg,
                       const KnotGrid& grid, HalfNodes& out);
 
+// ---- thinned k lists (PTPlan): which points of a list an operator is integrated on, and the 8-point Lagrange map (in
+// ln k) that fills the others; see quad.cpp
+void lagrange_fill_map(const std::vector<double>& kfull, const std::vector<char>& keep, std::vector<int>& idx,
+                       std::vector<double>& w, std::vector<double>& ksub);
+void thin_graded(std::vector<char>& keep, int from, int dir, int max_gap);
+std::vector<char> thin_k_list(const std::vector<double>& k);
+
 } // namespace prsd

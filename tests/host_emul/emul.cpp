@@ -189,3 +189,27 @@ extern "C" long long emul_nodes(int nk, const double* k, double qmax, long long 
     for (long long i = 0; i < n && i < cap; i++) { outer[i] = H.n_outer[i]; j0[i] = H.b_j0[i]; wgt[i] = H.wgt[i]; }
     return n;
 }
+
+// thinned k lists: keep mask and fill map of PTPlan (quad.cpp); which = 0: thin_k_list(k); 1 / 2: the one-loop grid rule with
+// (max_gap_lo, max_gap_hi) = (12, 6) for the 2-D integrals / the same with every point above 1.2 for J
+extern "C" int emul_fill_map(int which, int n, const double* k, char* keep_out, int* idx, double* w)
+{
+    std::vector<double> kk(k, k + n), ksub, mw;
+    std::vector<int> midx;
+    std::vector<char> keep;
+    if (which == 0) keep = thin_k_list(kk);
+    else {
+        keep.assign(n, 1);
+        int lo = 0, hi = n - 1;
+        while (lo < n - 1 && kk[lo] < 0.01) lo++;
+        while (hi > 0 && kk[hi] > 1.2) hi--;
+        thin_graded(keep, lo, -1, 12);
+        for (int i = hi + 1; i < n; i++) keep[i] = ((i - hi) % 6 == 0) ? 1 : 0;
+        keep[n - 1] = 1;
+        if (which == 2) for (int i = hi; i < n; i++) keep[i] = 1;
+    }
+    lagrange_fill_map(kk, keep, midx, mw, ksub);
+    for (int i = 0; i < n; i++) keep_out[i] = keep[i];
+    for (size_t i = 0; i < midx.size(); i++) { idx[i] = midx[i]; w[i] = mw[i]; }
+    return (int)ksub.size();
+}

@@ -38,6 +38,19 @@ class Emul(object):
         self.L.emul_plin_eval(len(k), np.ascontiguousarray(k), np.ascontiguousarray(T), ns, amp, h, Om, Ob, Tcmb, len(q), q, out)
         return out
 
+    def fill_map(self, which, k):
+        """keep mask [n], stencil indices [n][8] (into the kept points) and weights [n][8] of the thinned-list fill maps"""
+        k = np.ascontiguousarray(k, dtype='f8')
+        n = len(k)
+        keep = np.zeros(n, dtype=np.int8)
+        idx = np.zeros((n, 8), dtype=np.int32)
+        w = np.zeros((n, 8))
+        self.L.emul_fill_map.restype = C.c_int
+        self.L.emul_fill_map.argtypes = [C.c_int, C.c_int, dp, np.ctypeslib.ndpointer(dtype=np.int8, flags='C_CONTIGUOUS'),
+                                         np.ctypeslib.ndpointer(dtype=np.int32, flags='C_CONTIGUOUS'), dp]
+        nsub = self.L.emul_fill_map(which, n, k, keep, idx, w)
+        return keep.astype(bool), idx, w, nsub
+
     def table_read(self, tab, q):
         q = np.ascontiguousarray(q, dtype='f8')
         out = np.empty_like(q)

@@ -127,3 +127,42 @@ def test_banded_spline_operator_claim():
         # the decay itself: 40 knots away the influence is below 1e-17 of the diagonal
         i = n//2
         assert abs(op[i, i + 40]) < 1e-17*abs(op[i, i])
+
+
+def test_thinned_k_lists_and_fill_maps(emul, tight):
+    """the thinned k lists of PTPlan and their 8-point Lagrange fill maps (csrc/quad.cpp: thin_k_list, thin_graded,
+    lagrange_fill_map): kept points pass through exactly, the weights reproduce polynomials of degree 7 in ln k, the Lebesgue
+    constant stays small (it was 21 at the junction of an ungraded list: the point-to-point quadrature noise of the computed
+    values, 4e-7, became 9e-6), and smooth mode-coupling-like functions are filled to < 1e-6"""
+    k_interp = np.logspace(np.log10(5e-6), 0., 250)
+    k_1loop = np.exp(np.linspace(np.log(1e-5), np.log(10.), 1000))
+    for which, k, expect in ((0, k_interp, (110, 130)), (1, k_1loop, (400, 440)), (2, k_1loop, (520, 580))):
+        keep, idx, w, nsub = emul.fill_map(which, k)
+        assert keep.sum() == nsub and expect[0] <= nsub <= expect[1], (which, nsub)
+        assert keep[0] and keep[-1]
+        if which == 0:
+            assert keep[k >= 0.01].all() and not keep[k < 0.01].all()
+        else:
+            assert keep[(k >= 0.01) & (k <= 1.2)].all()
+        pos = np.where(keep)[0]
+        # kept points: identity
+        assert np.array_equal(idx[keep][:, 0], np.arange(nsub)) and np.all(w[keep][:, 0] == 1.) and np.all(w[keep][:, 1:] == 0.)
+        x = np.log(k)
+        xs = x[pos]
+        leb = np.abs(w).sum(axis=1)
+        inner = (k > 1e-4) & (k < 9.)
+        assert leb[inner].max() < 4.0, (which, leb[inner].max())
+        assert leb.max() < 8.0
+        assert np.allclose(w.sum(axis=1), 1., atol=1e-11)
+        for deg in (1, 3, 7):
+            f = (xs/5.)**deg
+            assert np.max(np.abs((w*f[idx]).sum(axis=1) - (x/5.)**deg)) < 1e-9, (which, deg)
+        # a smooth function with the shape of a low-k mode-coupling integral (power law x slow logarithmic running)
+        f = lambda q: q**3.2*(1. + 0.3*np.log(q) + 0.02*np.log(q)**2)/(1. + (q/0.05)**2)
+        filled = (w*f(k[pos])[idx]).sum(axis=1)
+        scale = np.maximum(np.abs(f(k)), 1e-3*k**0.96)
+        assert np.max(np.abs(filled - f(k))/scale) < 1e-6, which
+    # short, unsorted or non-uniform lists are not thinned
+    for kk in (np.logspace(-5, 0, 40), np.logspace(-5, 0, 200)[::-1].copy(), np.sort(np.random.default_rng(1).uniform(1e-5, 1., 200))):
+        keep, idx, w, nsub = emul.fill_map(0, kk)
+        assert nsub == len(kk) and keep.all()
