@@ -287,6 +287,18 @@ def run_gpu(args):
     ms_e2e, last = timed_block(lambda: run_e2e_pipelined(e2e_steps), lambda: run_e2e_pipelined(3))
     ms_blk, _, _ = timed_steps(step_e2e_blocking, max(2, args.steps//2), 1, flush_l2=True)
     blk_steps = max(2, args.steps//2)
+
+    # the box's device -> host ceiling for this step's result: every rank copies its 82 MB of P(k, mu) into its own
+    # page-locked buffer at the same time, nothing else running (one plain cudaMemcpyAsync per step).  On one GPU this is
+    # hidden under the next step's kernels; with 8 ranks on one host it is longer than a step and bounds e2e.
+    h_ceiling = torch.empty((B, npts), dtype=torch.float64, pin_memory=True)
+
+    def d2h_only(steps=4):
+        with torch.cuda.stream(stream):
+            for _ in range(steps):
+                h_ceiling.copy_(d_out, non_blocking=True)
+    ms_d2h, _ = timed_block(lambda: d2h_only(4), lambda: d2h_only(1))
+    ms_d2h /= 4
     sampler.stop_flag = True
 
     # in-run guards: the streaming and the blocking host paths return what the device-resident path returns
@@ -359,6 +371,9 @@ def run_gpu(args):
                        numa_node_of_rank0=numa),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e/e2e_steps, "steps": e2e_steps,
+                "d2h_only_ms_per_step": ms_d2h,
+                "d2h_only_note": "the device -> host copy of one step's P(k, mu) alone, all %d rank(s) copying at once (max over "
+                                 "ranks): the floor of the e2e step on this box whatever the kernels do" % world,
                 "how": "rsd.PTStream (prsd_spectra_reload / prsd_plan_run_async / prsd_galaxy_power_async): every step copies its "
                        "inputs (spectra T(k), cosmological and walker parameters, stochasticity) from NumPy arrays to page-locked "
                        "slots and to the device and its P(k, mu) back to page-locked host memory; the device-to-host copy of step i "
