@@ -174,6 +174,8 @@ struct WarpTransposeSum<1, 0> {
 // rebuilding them from the stencil coordinate -- 13 FP64 operations fewer per node, 8 bytes more: ImnOneLoop unchanged,
 // one-loop tables 2.6 % slower.  Reading three knots instead of four (not parity-clean, timing experiment only): -5.7 % /
 // -1.2 %.  Neither the FP64 pipe nor the shared-memory pipe alone sets the time of these kernels.)
+// (P(a) staged as binary32 -- half the wavefronts of the four P(a) reads, room for the second buffer of the one-loop
+// operator: ImnOneLoop 1.006 -> 1.025 ms, one-loop 0.776 -> 0.765 ms, parity unchanged, exact amplitude scaling lost.  Rejected.)
 // (Tried and rejected this round: staging the tables in binary32.  Rounding the TABLE is harmless -- the error of
 // a knot is common to every node that reads it and cancels wherever the kernels cancel -- and halves the table
 // wavefronts, but the kernel then runs into the P(a) reads and the global stream and gains only ~10 %; with the
