@@ -117,70 +117,98 @@ void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs, bool syn
 
 // ---------------------------------------------------------------- apply
 // out[row][o] = sum_j T[row][j] Omega[o][j] is a (rows x knots) . (knots x outputs) product: FP64 tensor-core MMAs
-// (DMMA m8n8k4).  One CTA owns 16 outputs x 32 rows; its 8 warps split the knots, so every warp streams a
-// contiguous 1/8 of 8 Omega rows and of 32 table rows with 16-byte loads (each lane's two values feed two
-// consecutive k-steps: the order of the knots inside a sum is free as long as both operands agree), and a
-// shared-memory pass adds the eight partial tiles.  Omega, the large operand, is read once per 32 rows.
-static const int LA_MT = 4;                            // row tiles (of 8) per CTA
-static const int LA_NT = 2;                            // output tiles (of 8) per CTA
-static const int LA_JS = ((TAB_MPAD + 63)/64)*8;      // knots per warp, a multiple of 8
+// (DMMA m8n8k4) in a shared-memory tiled GEMM.  A CTA owns 16 MT rows x 64 outputs (MT = 4, 2 or 1 by batch size), its 8
+// warps (2 x 4) own 8 MT x 16 each (MT x 2 MMA tiles); the knots are walked in chunks of 32 through a three-stage cp.async
+// pipeline (16-byte copies, zero-filled past the end of a row).  With MT = 4 each operand element is read from L2 once per
+// 64 x 64 tile -- 8 flop per byte against 2.7 for round 1's kernel (32 x 16 outputs per CTA, fragments straight from
+// global memory), whose 7.6 TB/s of L2 -> SM traffic was its limit -- and every fragment read from shared memory feeds
+// 2 - 4 MMAs.  Row stride 36 doubles (= 4 mod 16): the 16 fragment reads of a half-warp (4 rows x 4 knots) fall on distinct
+// bank pairs.  Every output element accumulates its knots in the same order whatever MT: results do not depend on the
+// batch size, bit for bit.
+static const int GM_BN = 64, GM_BK = 32, GM_LD = GM_BK + 4, GM_STAGES = 3;
 
-__global__ void __launch_bounds__(256)
-k_linear_apply(int nout, int nrow, const double* __restrict__ Omega, const double* __restrict__ tables,
-               const int* __restrict__ tab_index, double* __restrict__ out)
+template <int MT>
+__global__ void __launch_bounds__(256, 2)
+k_linear_gemm(int nout, int nrow, const double* __restrict__ Omega, const double* __restrict__ tables,
+              const int* __restrict__ tab_index, double* __restrict__ out)
 {
-    __shared__ double red[8][LA_NT*LA_MT][64];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int o0 = blockIdx.x*(8*LA_NT);
-    const int r0 = blockIdx.y*(8*LA_MT);
+    constexpr int BM = 16*MT;
+    extern __shared__ __align__(16) double gm_smem[];       // [STAGES][(BM + BN)][LD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = lane & 3, grp = lane >> 2;
-    const double* bp[LA_NT];
+    const int o0 = blockIdx.x*GM_BN, r0 = blockIdx.y*BM;
+    const int wm = warp >> 2, wn = warp & 3;                // warp tile: rows 8 MT wm .., outputs 16 wn ..
+
+    // global -> shared: 16 chunks of 16 bytes per row and stage; thread t copies chunk t % 16 of rows t / 16 + 16 i
+    const int c_chunk = tid & 15, c_row = tid >> 4;
+    const double* src_a[MT];
+    const double* src_b[4];
 #pragma unroll
-    for (int n = 0; n < LA_NT; n++) bp[n] = Omega + (size_t)min(o0 + 8*n + grp, nout - 1)*TAB_MPAD;
-    const double* ap[LA_MT];
+    for (int i = 0; i < MT; i++)
+        src_a[i] = tables + (size_t)tab_index[min(r0 + c_row + 16*i, nrow - 1)]*TAB_MPAD + 2*c_chunk;
 #pragma unroll
-    for (int m = 0; m < LA_MT; m++) ap[m] = tables + (size_t)tab_index[min(r0 + 8*m + grp, nrow - 1)]*TAB_MPAD;
-    double acc[LA_NT][LA_MT][2];
+    for (int i = 0; i < 4; i++) src_b[i] = Omega + (size_t)min(o0 + c_row + 16*i, nout - 1)*TAB_MPAD + 2*c_chunk;
+    auto load_stage = [&](int stage, int k0) {
+        double* As = gm_smem + (size_t)stage*(BM + GM_BN)*GM_LD;
+        double* Bs = As + BM*GM_LD;
+        const int bytes = (k0 + 2*c_chunk < TAB_MPAD) ? 16 : 0;       // TAB_MPAD is even: a chunk is inside a row or outside
 #pragma unroll
-    for (int n = 0; n < LA_NT; n++)
+        for (int i = 0; i < MT; i++) cp_async16(As + (c_row + 16*i)*GM_LD + 2*c_chunk, bytes ? src_a[i] + k0 : tables, bytes);
 #pragma unroll
-        for (int m = 0; m < LA_MT; m++) acc[n][m][0] = acc[n][m][1] = 0.0;
-    const int j_lo = warp*LA_JS, j_hi = min(j_lo + LA_JS, TAB_MPAD);
-#pragma unroll 2
-    for (int j = j_lo; j < j_hi; j += 8) {
-        const int idx = j + 2*sub;
-        const bool ok = idx < TAB_MPAD;
-        double2 b[LA_NT], a[LA_MT];
+        for (int i = 0; i < 4; i++) cp_async16(Bs + (c_row + 16*i)*GM_LD + 2*c_chunk, bytes ? src_b[i] + k0 : Omega, bytes);
+    };
+    constexpr int NCH = (TAB_MPAD + GM_BK - 1)/GM_BK;
 #pragma unroll
-        for (int n = 0; n < LA_NT; n++) b[n] = ok ? __ldg(reinterpret_cast<const double2*>(bp[n] + idx)) : make_double2(0.0, 0.0);
-#pragma unroll
-        for (int m = 0; m < LA_MT; m++) a[m] = ok ? __ldg(reinterpret_cast<const double2*>(ap[m] + idx)) : make_double2(0.0, 0.0);
-#pragma unroll
-        for (int n = 0; n < LA_NT; n++)
-#pragma unroll
-            for (int m = 0; m < LA_MT; m++) {
-                dmma_m8n8k4(acc[n][m][0], acc[n][m][1], a[m].x, b[n].x);
-                dmma_m8n8k4(acc[n][m][0], acc[n][m][1], a[m].y, b[n].y);
-            }
+    for (int s = 0; s < GM_STAGES - 1; s++) {
+        if (s < NCH) load_stage(s, s*GM_BK);
+        cp_async_commit();
     }
+    double acc[MT][2][2];
 #pragma unroll
-    for (int n = 0; n < LA_NT; n++)
+    for (int m = 0; m < MT; m++)
 #pragma unroll
-        for (int m = 0; m < LA_MT; m++) {
-            red[warp][n*LA_MT + m][grp*8 + 2*sub] = acc[n][m][0];
-            red[warp][n*LA_MT + m][grp*8 + 2*sub + 1] = acc[n][m][1];
+        for (int n = 0; n < 2; n++) acc[m][n][0] = acc[m][n][1] = 0.0;
+
+    for (int ch = 0; ch < NCH; ch++) {
+        cp_async_wait<GM_STAGES - 2>();
+        __syncthreads();                                     // chunk ch has landed; the stage refilled below was read in ch - 1
+        const int nx = ch + GM_STAGES - 1;
+        if (nx < NCH) load_stage(nx % GM_STAGES, nx*GM_BK);
+        cp_async_commit();
+        const double* As = gm_smem + (size_t)(ch % GM_STAGES)*(BM + GM_BN)*GM_LD + (8*MT*wm + grp)*GM_LD + sub;
+        const double* Bs = gm_smem + (size_t)(ch % GM_STAGES)*(BM + GM_BN)*GM_LD + (BM + 16*wn + grp)*GM_LD + sub;
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; kk += 4) {
+            double a[MT], b[2];
+#pragma unroll
+            for (int m = 0; m < MT; m++) a[m] = As[m*8*GM_LD + kk];
+#pragma unroll
+            for (int n = 0; n < 2; n++) b[n] = Bs[n*8*GM_LD + kk];
+#pragma unroll
+            for (int m = 0; m < MT; m++)
+#pragma unroll
+                for (int n = 0; n < 2; n++) dmma_m8n8k4(acc[m][n][0], acc[m][n][1], a[m], b[n]);
         }
-    __syncthreads();
-    // 64 elements per tile, LA_NT x LA_MT tiles
-    for (int idx = threadIdx.x; idx < LA_NT*LA_MT*64; idx += 256) {
-        const int t = idx >> 6, e = idx & 63;
-        const int n = t/LA_MT, m = t - n*LA_MT;
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) v += red[w][t][e];
-        const int row = r0 + 8*m + (e >> 3), col = o0 + 8*n + (e & 7);
-        if (row < nrow && col < nout) out[(size_t)row*nout + col] = v;
     }
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+            const int row = r0 + 8*MT*wm + 8*m + grp, col = o0 + 16*wn + 8*n + 2*sub;
+            if (row < nrow) {
+                if (col < nout) out[(size_t)row*nout + col] = acc[m][n][0];
+                if (col + 1 < nout) out[(size_t)row*nout + col + 1] = acc[m][n][1];
+            }
+        }
+}
+
+template <int MT>
+static void launch_gemm(Context& ctx, int nout, int nrow, const double* Omega, const double* tables, const int* tab_index, double* out)
+{
+    const size_t smem = (size_t)GM_STAGES*(16*MT + GM_BN)*GM_LD*sizeof(double);
+    PRSD_CUDA(cudaFuncSetAttribute(k_linear_gemm<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((nout + GM_BN - 1)/GM_BN, (nrow + 16*MT - 1)/(16*MT));
+    k_linear_gemm<MT><<<grid, 256, smem, ctx.stream>>>(nout, nrow, Omega, tables, tab_index, out);
 }
 
 // Operators with a handful of outputs (sigma_v^2-type scalars: one output per cosmology) leave the MMA kernel with
@@ -219,9 +247,10 @@ void LinearOp::apply(Context& ctx, const double* tables, const int* tab_index, i
         return;
     }
     static_assert(TAB_MPAD % 2 == 0, "table rows must be 16-byte multiples");
-    dim3 grid((nout + 8*LA_NT - 1)/(8*LA_NT), (nrow + 8*LA_MT - 1)/(8*LA_MT));
     ProfScope prof(ctx, PROF_LINEAR);
-    k_linear_apply<<<grid, 256, 0, ctx.stream>>>(nout, nrow, Omega.p, tables, tab_index, out);
+    if (nrow > 32) launch_gemm<4>(ctx, nout, nrow, Omega.p, tables, tab_index, out);
+    else if (nrow > 16) launch_gemm<2>(ctx, nout, nrow, Omega.p, tables, tab_index, out);
+    else launch_gemm<1>(ctx, nout, nrow, Omega.p, tables, tab_index, out);
     PRSD_CUDA(cudaGetLastError());
     ctx.launches++;
 }

@@ -135,35 +135,39 @@ PTPlan::PTPlan(Context& c, const double* k, int nk_, const QuadConfig& q, bool m
     // ---- ... while the device integrates the 1-D operators (product integration, ~0.2 s of kernels, nothing waits on them)
     try {
         {
-            // J00, J01, J11 on their subset of the one-loop grid (k_1loop_j), filled to all 1000 points in k_oneloop_combine
+            // ONE operator for every 1-D functional of P_L -- [J00, J01, J11 on their subset of the one-loop grid (k_1loop_j,
+            // filled to all 1000 points in k_oneloop_combine) | J_mn x 6, sigma_v^2(k), sigma_v^2, X(r), Y(r)] -- so that a
+            // batch is ONE GEMM launch of 73 x (ncosmo / 64) CTAs: two launches of 26 and 48 column tiles left half of the
+            // SMs idle
             std::vector<LinOutSpec> o;
             for (int id : {0, 1, 4})
                 for (double kj : k_1loop_j) o.push_back({LK_JMN, id, kj, 1e-5, 1e5, 1.0});
-            lin_1loop.build(c, o, false);
+            n_lin1 = (int)o.size();
+            if (!only_oneloop) {
+                // J_mn on the same thinned list as the 2-D operators (filled in k_pack_lin); sigma_v^2(k), whose upper
+                // limit moves with k, on every point
+                for (int j = 0; j < 6; j++)
+                    for (int i = 0; i < nk_sub; i++) o.push_back({LK_JMN, J_IDS[j], k_sub[i], 1e-5, 1e5, 1.0});
+                // sigma_v^2(k) integrates from 1e-5 up to 0.5 k (PowerSpectrum.cpp:60-62)
+                for (int i = 0; i < nk; i++) {
+                    // for 0.5 k < 1e-5 the reference integrates "backwards" and returns a negative number
+                    const double hi = 0.5*k_interp[i];
+                    if (hi >= 1e-5) o.push_back({LK_SIGV, 0, 0.0, 1e-5, hi, 1.0});
+                    else            o.push_back({LK_SIGV, 0, 0.0, hi, 1e-5, -1.0});
+                }
+                o.push_back({LK_SIGV, 0, 0.0, 1e-5, 1e2, 1.0});
+                if (with_zel) {
+                    // (X(r), Y(r) on a thinned r grid -- every 2nd point for 1 <= r <= 1000, every 4th outside, or the same
+                    // with every point in [10, 400] -- with an 8-point Lagrange fill in ln r: 1-D operators 0.29 -> 0.21 / 0.24
+                    // ms, but P(k, mu) moves by 6.8e-6 ... 1.35e-5 at k = 0.05: the Zel'dovich sum amplifies 1e-10 sigma_v^2
+                    // in X, Y.  Measured and reverted, round 2.)
+                    for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_XZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
+                    for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_YZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
+                }
+            }
+            lin_all.build(c, o, false);
         }
         if (!only_oneloop) {
-            std::vector<LinOutSpec> o;
-            // J_mn on the same thinned list as the 2-D operators (filled in k_pack_lin); sigma_v^2(k), whose upper limit
-            // moves with k, on every point
-            for (int j = 0; j < 6; j++)
-                for (int i = 0; i < nk_sub; i++) o.push_back({LK_JMN, J_IDS[j], k_sub[i], 1e-5, 1e5, 1.0});
-            // sigma_v^2(k) integrates from 1e-5 up to 0.5 k (PowerSpectrum.cpp:60-62)
-            for (int i = 0; i < nk; i++) {
-                // for 0.5 k < 1e-5 the reference integrates "backwards" and returns a negative number
-                const double hi = 0.5*k_interp[i];
-                if (hi >= 1e-5) o.push_back({LK_SIGV, 0, 0.0, 1e-5, hi, 1.0});
-                else            o.push_back({LK_SIGV, 0, 0.0, hi, 1e-5, -1.0});
-            }
-            o.push_back({LK_SIGV, 0, 0.0, 1e-5, 1e2, 1.0});
-            if (with_zel) {
-                // (X(r), Y(r) on a thinned r grid -- every 2nd point for 1 <= r <= 1000, every 4th outside, or the same with
-                // every point in [10, 400] -- with an 8-point Lagrange fill in ln r: 1-D operators 0.29 -> 0.21 / 0.24 ms, but
-                // P(k, mu) moves by 6.8e-6 ... 1.35e-5 at k = 0.05: the Zel'dovich sum amplifies 1e-10 sigma_v^2 in X, Y.
-                // Measured and reverted, round 2.)
-                for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_XZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
-                for (int i = 0; i < ZEL_NR; i++) o.push_back({LK_YZEL, 0, r_zel[i], 1e-5, 1e2, 1.0});
-            }
-            lin_main.build(c, o, false);
             lin_invq2_100.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e2, 1.0/(10.0*M_PI*M_PI)}}, false);
             lin_kurt.build(c, {{LK_INVQ2, 0, 0.0, 1e-5, 1e1, 0.25/(2.0*M_PI*M_PI)}}, false);
             d_kinterp.upload(k_interp, c.stream);
@@ -226,7 +230,7 @@ size_t PTPlan::device_bytes() const
     if (op_1loop.geo) b += op_1loop.geo->bytes();
     if (op_ik.geo) b += op_ik.geo->bytes();
     if (op_ml.geo) b += op_ml.geo->bytes();
-    for (const LinearOp* l : {&lin_1loop, &lin_main, &lin_invq2_100, &lin_kurt}) b += l->Omega.n*sizeof(double);
+    for (const LinearOp* l : {&lin_all, &lin_invq2_100, &lin_kurt}) b += l->Omega.n*sizeof(double);
     return b;
 }
 
@@ -243,7 +247,8 @@ long long PTPlan::nodes_total() const
 __global__ void k_oneloop_combine(int ncosmo, int nsub, const double* __restrict__ op1 /*[c][nsub][8]*/,
                                   const int* __restrict__ midx /*[1000][8]*/, const double* __restrict__ mw /*[1000][8]*/,
                                   int nj, const int* __restrict__ jidx /*[1000][8]*/, const double* __restrict__ jw /*[1000][8]*/,
-                                  const double* __restrict__ lin1 /*[c][3][nj]*/, const double* __restrict__ plk /*[c][1000]*/,
+                                  const double* __restrict__ lin1 /*[c][lin_stride]: 3 x nj first*/, int lin_stride,
+                                  const double* __restrict__ plk /*[c][1000]*/,
                                   const double* __restrict__ k1, double* __restrict__ ol /*[c][4][1000]*/)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
@@ -252,7 +257,7 @@ __global__ void k_oneloop_combine(int ncosmo, int nsub, const double* __restrict
     // computed points
     double a[4] = {0.0, 0.0, 0.0, 0.0}, j[3] = {0.0, 0.0, 0.0};
     const double* base = op1 + (size_t)c*nsub*8;
-    const double* jb = lin1 + (size_t)c*3*nj;
+    const double* jb = lin1 + (size_t)c*lin_stride;
 #pragma unroll
     for (int l = 0; l < 8; l++) {
         const double w = mw[(size_t)i*8 + l];
@@ -319,13 +324,13 @@ __global__ void k_fill_ml(int nk, int nsub, const double* __restrict__ s, const 
 }
 
 __global__ void k_pack_lin(int nk, int nsub, const int* __restrict__ midx /*[nk][8]*/, const double* __restrict__ mw /*[nk][8]*/,
-                           int nout, int with_zel, const double* __restrict__ s /*[c][nout]*/,
+                           int nout, int skip, int with_zel, const double* __restrict__ s /*[c][nout], the first `skip` belong to the one-loop stage*/,
                            const double* __restrict__ q3, const double* __restrict__ kurt,
                            double* __restrict__ J, double* __restrict__ sigk, double* __restrict__ scal,
                            double* __restrict__ X0, double* __restrict__ YY)
 {
     const int i = blockIdx.x*blockDim.x + threadIdx.x, c = blockIdx.y;
-    const double* r = s + (size_t)c*nout;
+    const double* r = s + (size_t)c*nout + skip;
     if (i < 6*nk) {
         // computed at k_i, or interpolated from the computed points (PTPlan ctor)
         const int j = i/nk, ik = i - j*nk;
@@ -394,14 +399,14 @@ void PTPlan::run_oneloop(SpectraBatch& sp, PTResult& res, bool sync)
     // ---- stage A: one-loop tables
     s_op1.ensure((size_t)(nc + 8)*n_1loop_sub*8);
     nodal_apply_diag(c, op_1loop, sp.tables.p, s_rowB.p, nc, s_op1.p);
-    s_lin1.ensure((size_t)nc*3*k_1loop_j.size());
-    lin_1loop.apply(c, sp.tables.p, d_tabL.p, nc, s_lin1.p);
+    s_lin.ensure((size_t)nc*lin_all.nout);
+    lin_all.apply(c, sp.tables.p, d_tabL.p, nc, s_lin.p);
     s_plk.ensure((size_t)nc*ONELOOP_N);
     {
         dim3 g((ONELOOP_N + 255)/256, nc);
         k_plin_at<<<g, 256, 0, s>>>(sp.nspl, sp.params.p, sp.spl.p, ONELOOP_N, d_k1loop.p, s_plk.p);
         k_oneloop_combine<<<g, 256, 0, s>>>(nc, n_1loop_sub, s_op1.p, d_olmap_idx.p, d_olmap_w.p, (int)k_1loop_j.size(),
-                                            d_jmap_idx.p, d_jmap_w.p, s_lin1.p, s_plk.p, d_k1loop.p,
+                                            d_jmap_idx.p, d_jmap_w.p, s_lin.p, lin_all.nout, s_plk.p, d_k1loop.p,
                                             res.oneloop.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches += 2;
@@ -456,15 +461,14 @@ void PTPlan::run(SpectraBatch& sp, PTResult& res, bool sync)
         }
     }
     // ---- 1-D functionals
-    s_linmain.ensure((size_t)nc*lin_main.nout);
-    lin_main.apply(c, sp.tables.p, d_tabL.p, nc, s_linmain.p);
+    // (the 1-D functionals of this batch were computed with the one-loop stage: lin_all)
     s_small.ensure((size_t)2*nc);
     lin_invq2_100.apply(c, sp.tables.p, d_tabSq.p, nc, s_small.p);
     lin_kurt.apply(c, sp.tables.p, d_tab22.p, nc, s_small.p + nc);
     {
         const int nmax = std::max(6*nk, ZEL_NR);
         dim3 g((nmax + 127)/128, nc);
-        k_pack_lin<<<g, 128, 0, s>>>(nk, nk_sub, d_kmap_idx.p, d_kmap_w.p, lin_main.nout, with_zel ? 1 : 0, s_linmain.p, s_small.p, s_small.p + nc,
+        k_pack_lin<<<g, 128, 0, s>>>(nk, nk_sub, d_kmap_idx.p, d_kmap_w.p, lin_all.nout, n_lin1, with_zel ? 1 : 0, s_lin.p, s_small.p, s_small.p + nc,
                                     res.J.p, res.sigmasq_k.p, res.scalars.p, res.X0.p, res.YY.p);
         PRSD_CUDA(cudaGetLastError());
         c.launches++;

@@ -45,8 +45,9 @@ struct PTPlan {
     int nk = 0;
     bool with_ml = true, with_zel = true, only_oneloop = false;
     BilinearOp op_1loop, op_ik, op_ml;
-    LinearOp lin_1loop;        // J00, J01, J11 on k_1loop                      (P_L table)
-    LinearOp lin_main;         // J x6 (nk each), sigmasq_k (nk), sigma_v^2, X (1024), Y (1024)   (P_L table)
+    LinearOp lin_all;          // [J00, J01, J11 on the one-loop subset (n_lin1 outputs) | J x6 on k_sub, sigmasq_k (nk), sigma_v^2,
+                               //  X (1024), Y (1024)]   (P_L table)
+    int n_lin1 = 0;
     LinearOp lin_invq2_100;    // \int S/q^2 dq over [1e-5, 100] x 1/(10 pi^2)  (P_L^2 table)  -> Q3 / k^4
     LinearOp lin_kurt;         // 0.25/(2 pi^2) \int S/q^2 dq over [1e-5, 10]   (P22bar table)
     DevBuf<double> d_k1loop, d_kinterp;
@@ -66,7 +67,7 @@ struct PTPlan {
     DevBuf<double> d_kmap_w;        // [nk][8]
     DevBuf<double> s_ml;            // [c][21][nk_sub]
     // scratch
-    DevBuf<double> s_op1, s_lin1, s_ik, s_mlp, s_mln, s_linmain, s_small, s_ol, s_plk;
+    DevBuf<double> s_op1, s_lin, s_ik, s_mlp, s_mln, s_small, s_ol, s_plk;
     DevBuf<int> s_slot, s_rowA, s_rowB, s_tabidx;
     // index arrays of the current batch size (rebuilt when it changes)
     DevBuf<int> d_tabL, d_tabSq, d_tab22;

@@ -46,6 +46,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     } while (!done);
 }
 
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 fills the destination with zeros (nothing is read)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // D(8x8) += A(8x4) * B(4x8), all FP64 (tensor pipe).  Fragment layout (PTX ISA, m8n8k4 .f64):
 //   a : A[lane/4][lane%4]        b : B[lane%4][lane/4]        c0,c1 : C[lane/4][2*(lane%4) + {0,1}]
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b)
