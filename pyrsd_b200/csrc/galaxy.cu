@@ -238,6 +238,9 @@ __constant__ int c_pair_a[GAL_NPAIR] = {0, 0, 1, 0, 0, 1, 1, 2, 2, 3};
 __constant__ int c_pair_b[GAL_NPAIR] = {0, 1, 1, 2, 3, 2, 3, 2, 3, 3};
 
 // ----------------------------------------------------------- halo moments + splines
+// (One CTA per (walker, pair), 128 threads.  Five pairs per CTA -- one load of a spline-operator entry feeding 20 splines
+// held in shared memory instead of 4 -- measured 0.175 -> 0.28 ms: the moment formulae, not the banded products, are the
+// cost, and 512 CTAs of 182 registers run them five pairs in sequence.  Rejected, round 2.)
 __global__ void __launch_bounds__(128)
 k_gal_moments(GalDev G, const double* __restrict__ km, const double* __restrict__ Es /*[GAL_NSTOCH][nkm]*/,
               int mband, const double* __restrict__ Mb /*[mband][nkm]*/, const int* __restrict__ mlo,
