@@ -9,34 +9,40 @@ namespace prsd {
 __constant__ double c_glx[GLN];
 __constant__ double c_glw[GLN];
 
-// One WARP per (output, knot): the lanes share the (sub-panel, Gauss point) pairs of every cell piece.  The outputs
-// with an oscillatory kernel (X(r), Y(r) at r up to 1e5 Mpc/h: omega dq / 10 = 2e4 sub-panels per cell near q = 100)
-// cost 1e6 kernel evaluations per weight; with one thread per weight (round 1) a handful of threads ran for 1.6 s
-// while the rest of the device idled.  Same arithmetic as linear_weight() (linear_math.cuh, the CPU emulation's
-// copy); only the order of the partial sums differs.
-__device__ double linear_weight_warp(const LinOutDev& S, const ZonesDev& Z, int j, int lane)
+// One WARP per (output, CELL of the knot grid): the lanes share the (sub-panel, Gauss point) pairs of every piece of the
+// cell and accumulate the integrals of all FOUR cardinal functions of the cell's stencil at once -- the kernel value and
+// log q, which are the cost, are computed once per point and not once per knot whose stencil holds the cell (4 x fewer
+// evaluations than one warp per (output, knot), which the first version of round 2 used).  The outputs with an
+// oscillatory kernel (X(r), Y(r) at r up to 1e5 Mpc/h: omega dq / 10 = 2e4 sub-panels per cell near q = 100) cost 3e5
+// kernel evaluations per cell; with one thread per weight (round 1) a handful of threads ran for 1.6 s while the rest of
+// the device idled.  Same arithmetic as linear_weight() (linear_math.cuh, the CPU emulation's copy); only the order of
+// the partial sums differs.  k_linear_gather then adds the <= 4 cell integrals of every knot in ascending cell order.
+struct CellsDev { int ncell; int cstart[8]; };      // cstart[z]: first global cell of zone z
+
+__global__ void __launch_bounds__(256)
+k_linear_cells(int o_first, const LinOutDev* __restrict__ outs, ZonesDev Z, CellsDev C, double* __restrict__ part /*[o][cell][4]*/)
 {
-    double total = 0.0;
+    const int o = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int gc = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gc >= C.ncell) return;
+    const LinOutDev S = outs[o_first + o];
     int z = 0;
-    while (z < Z.nz - 1 && j >= Z.start[z + 1]) ++z;
-    const int jl = j - Z.start[z];
+    while (z < Z.nz - 1 && gc >= C.cstart[z + 1]) ++z;
+    const int c = gc - C.cstart[z];
     const int n = Z.n[z];
     const double x0 = Z.x0[z], h = Z.h[z];
     const double xlo = log(S.lo), xhi = log(S.hi);
     const bool has_break = (S.type == LK_JMN || S.type == LK_SIGMA3);
     const double omega = lin_omega(S.type, S.param);
-    const int c_lo = jl - 3 > 0 ? jl - 3 : 0;
-    const int c_hi = jl + 3 < n - 1 ? jl + 3 : n - 1;
-    for (int c = c_lo; c <= c_hi; c++) {
-        int s0 = c - 1;
-        if (s0 < 0) s0 = 0;
-        if (s0 > n - 3) s0 = n - 3;
-        const int l = jl - s0;
-        if (l < 0 || l > 3) continue;
-        double xa = x0 + h*c, xb = x0 + h*(c + 1);
-        if (xa < xlo) xa = xlo;
-        if (xb > xhi) xb = xhi;
-        if (!(xb > xa)) continue;
+    int s0 = c - 1;
+    if (s0 < 0) s0 = 0;
+    if (s0 > n - 3) s0 = n - 3;
+    double total[4] = {0.0, 0.0, 0.0, 0.0};
+    double xa = x0 + h*c, xb = x0 + h*(c + 1);
+    if (xa < xlo) xa = xlo;
+    if (xb > xhi) xb = xhi;
+    if (xb > xa) {
         const double qa = exp(xa), qb = exp(xb);
         double pe[3];
         int np = 1;
@@ -51,7 +57,7 @@ __device__ double linear_weight_warp(const LinOutDev& S, const ZonesDev& Z, int 
                 if (ph > 10.0) nsub = (long long)ceil(ph/10.0);
             }
             const double dq = (p1 - p0)/(double)nsub, hw = 0.5*dq;
-            double acc = 0.0;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const long long npts = nsub*GLN;
             for (long long idx = lane; idx < npts; idx += 32) {
                 const long long is = idx/GLN;
@@ -60,26 +66,51 @@ __device__ double linear_weight_warp(const LinOutDev& S, const ZonesDev& Z, int 
                 const double s = (log(q) - x0)/h - (double)s0;
                 double Lg[4];
                 lagrange4(s, Lg);
-                acc += c_glw[g]*Lg[l]*lin_kernel(S.type, S.sub, S.param, q);
+                const double wk = c_glw[g]*lin_kernel(S.type, S.sub, S.param, q);
+#pragma unroll
+                for (int l = 0; l < 4; l++) acc[l] += wk*Lg[l];
             }
-            total += acc*hw;
+#pragma unroll
+            for (int l = 0; l < 4; l++) total[l] += acc[l]*hw;
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    return total*S.scale;
+    for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) total[l] += __shfl_xor_sync(0xffffffffu, total[l], sh);
+    if (lane == 0) {
+        double2* dst = reinterpret_cast<double2*>(part + ((size_t)o*C.ncell + gc)*4);
+        dst[0] = make_double2(total[0], total[1]);
+        dst[1] = make_double2(total[2], total[3]);
+    }
 }
 
 __global__ void __launch_bounds__(256)
-k_linear_build(int nout, const LinOutDev* __restrict__ outs, ZonesDev Z, double* __restrict__ Omega)
+k_linear_gather(int o_first, const LinOutDev* __restrict__ outs, ZonesDev Z, CellsDev C, const double* __restrict__ part,
+                double* __restrict__ Omega)
 {
     const int o = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int j = blockIdx.x*blockDim.x + threadIdx.x;
     if (j >= TAB_MPAD) return;
     double total = 0.0;
-    if (j < TAB_M) total = linear_weight_warp(outs[o], Z, j, lane);
-    if (lane == 0) Omega[(size_t)o*TAB_MPAD + j] = total;
+    if (j < TAB_M) {
+        int z = 0;
+        while (z < Z.nz - 1 && j >= Z.start[z + 1]) ++z;
+        const int jl = j - Z.start[z];
+        const int n = Z.n[z];
+        const int c_lo = jl - 3 > 0 ? jl - 3 : 0;
+        const int c_hi = jl + 3 < n - 1 ? jl + 3 : n - 1;
+        for (int c = c_lo; c <= c_hi; c++) {
+            int s0 = c - 1;
+            if (s0 < 0) s0 = 0;
+            if (s0 > n - 3) s0 = n - 3;
+            const int l = jl - s0;
+            if (l < 0 || l > 3) continue;
+            total += part[((size_t)o*C.ncell + C.cstart[z] + c)*4 + l];
+        }
+        total *= outs[o_first + o].scale;
+    }
+    Omega[(size_t)(o_first + o)*TAB_MPAD + j] = total;
 }
 
 void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs, bool sync)
@@ -106,12 +137,23 @@ void LinearOp::build(Context& ctx, const std::vector<LinOutSpec>& outs, bool syn
     DevBuf<LinOutDev> dout;
     dout.upload(ho, ctx.stream);
     Omega.alloc((size_t)nout*TAB_MPAD);
-    dim3 grid((TAB_MPAD + 7)/8, nout);
-    k_linear_build<<<grid, 256, 0, ctx.stream>>>(nout, dout.p, Z, Omega.p);
-    PRSD_CUDA(cudaGetLastError());
-    ctx.launches++;
-    // sync = false: the caller overlaps host work with the build; `dout` returns to the stream-ordered pool, which hands it
-    // out again only behind this kernel
+    CellsDev C;
+    C.ncell = 0;
+    for (int i = 0; i < Z.nz; i++) { C.cstart[i] = C.ncell; C.ncell += Z.n[i]; }
+    // the cell integrals of <= 2048 outputs at a time (160 MB of scratch)
+    const int o_batch = std::min(nout, 2048);
+    DevBuf<double> part;
+    part.alloc((size_t)o_batch*C.ncell*4);
+    for (int o0 = 0; o0 < nout; o0 += o_batch) {
+        const int no = std::min(o_batch, nout - o0);
+        k_linear_cells<<<dim3((C.ncell + 7)/8, no), 256, 0, ctx.stream>>>(o0, dout.p, Z, C, part.p);
+        PRSD_CUDA(cudaGetLastError());
+        k_linear_gather<<<dim3((TAB_MPAD + 255)/256, no), 256, 0, ctx.stream>>>(o0, dout.p, Z, C, part.p, Omega.p);
+        PRSD_CUDA(cudaGetLastError());
+        ctx.launches += 2;
+    }
+    // sync = false: the caller overlaps host work with the build; `dout` and `part` return to the stream-ordered pool,
+    // which hands them out again only behind these kernels
     if (sync) ctx.sync();
 }
 
