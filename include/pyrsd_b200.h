@@ -106,6 +106,10 @@ int prsd_eval_imn_oneloop(prsd_spectra* sp, int p1, int p2, int which, int m, in
  *       5 Sigma(R), 6 sigma3_squared(k) */
 int prsd_eval_ps_integral(prsd_spectra* sp, int what, int n, const double* x, double factor,
                           double* out /*[ncosmo][n]*/);
+/* CorrelationFunction(P, kmin = 1e-4, kmax = 10)(r) = 1/(2 pi^2 r) \int_kmin^kmax k sin(k r) P(k) dk
+ * [CorrelationFunction.i:39-55, CorrelationFunction.cpp:145-168] */
+int prsd_eval_correlation(prsd_spectra* sp, int n, const double* r, double kmin, double kmax,
+                          double* out /*[ncosmo][n]*/);
 /* OneLoopP22Bar::VelocityKurtosis  [OneLoopPS.cpp:187-193] */
 int prsd_eval_kurtosis(prsd_spectra* sp, double* out /*[ncosmo]*/);
 

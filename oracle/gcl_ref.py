@@ -42,6 +42,7 @@ def lib():
             'ref_ps_velocity_dispersion': (d, [vp]),
             'ref_ps_sigmasq_k': (None, [vp, d, i, _dp, _dp]),
             'ref_ps_sigma_R': (None, [vp, i, _dp, _dp]),
+            'ref_correlation': (None, [vp, d, d, i, _dp, _dp]),
             'ref_ps_xzel': (None, [vp, i, _dp, _dp]),
             'ref_ps_yzel': (None, [vp, i, _dp, _dp]),
             'ref_ps_q3zel': (None, [vp, i, _dp, _dp]),
@@ -176,6 +177,13 @@ class RefPower(object):
 
     def sigma3_squared(self, k):
         return self._vec('ref_ps_sigma3sq', k)
+
+    def correlation(self, r, kmin=1e-4, kmax=1e1):
+        """CorrelationFunction(P, kmin, kmax)(r)"""
+        r = _a(r)
+        out = np.empty_like(r)
+        lib().ref_correlation(self.ptr, kmin, kmax, len(r), r, out)
+        return out
 
 
 class RefLinearPS(RefPower):

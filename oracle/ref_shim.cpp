@@ -91,6 +91,12 @@ void ref_ps_q3zel(void* P, int n, const double* k, double* out)
 {
     for (int i = 0; i < n; i++) out[i] = ((PowerSpectrum*)P)->Q3_Zel(k[i]);
 }
+/* CorrelationFunction(P, kmin, kmax)(r)  [CorrelationFunction.cpp:145-168] */
+void ref_correlation(void* P, double kmin, double kmax, int n, const double* r, double* out)
+{
+    CorrelationFunction cf(*(PowerSpectrum*)P, kmin, kmax);
+    for (int i = 0; i < n; i++) out[i] = cf.Evaluate(r[i]);
+}
 void ref_ps_sigma3sq(void* P, int n, const double* k, double* out)
 {
     for (int i = 0; i < n; i++) out[i] = ((PowerSpectrum*)P)->sigma3_squared(k[i]);

@@ -57,6 +57,7 @@ def lib():
         'prsd_eval_imn_oneloop': (i, [vp, i, i, i, i, i, i, _dp, vp, _dp]),
         'prsd_eval_ps_integral': (i, [vp, i, i, _dp, d, _dp]),
         'prsd_eval_kurtosis': (i, [vp, _dp]),
+        'prsd_eval_correlation': (i, [vp, i, _dp, d, d, _dp]),
         'prsd_plan_create': (i, [vp, i, _dp, vp, i, pvp]),
         'prsd_plan_destroy': (i, [vp]),
         'prsd_plan_info': (i, [vp, _dp]),

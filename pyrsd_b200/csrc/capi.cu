@@ -470,6 +470,21 @@ int prsd_eval_ps_integral(prsd_spectra* sp, int what, int n, const double* x, do
     });
 }
 
+int prsd_eval_correlation(prsd_spectra* sp, int n, const double* r, double kmin, double kmax, double* out)
+{
+    return guarded(dev_of(sp), [&] {
+        PRSD_REQUIRE(sp && out && (n == 0 || r), "null argument");
+        PRSD_REQUIRE(kmin > 0 && kmax > kmin, "CorrelationFunction: need 0 < kmin < kmax (got %g, %g)", kmin, kmax);
+        if (n <= 0) return;
+        std::vector<LinOutSpec> o;
+        for (int i = 0; i < n; i++) {
+            PRSD_REQUIRE(std::isfinite(r[i]) && r[i] > 0, "r[%d] = %g must be positive", i, r[i]);
+            o.push_back({LK_XI, 0, r[i], kmin, kmax, 1.0});
+        }
+        eval_linear_generic(sp->s, o, SP_LIN, out);
+    });
+}
+
 int prsd_eval_kurtosis(prsd_spectra* sp, double* out)
 {
     return guarded(dev_of(sp), [&] {

@@ -27,6 +27,7 @@ enum LinKernel {
     LK_INVQ2,        // \int S / q^2 dq  (Q3 and the velocity kurtosis; scale carries the prefactor)
     LK_SIGMA_R,      // param = R : \int q^2 S W(qR)^2 dq / (2 pi^2)
     LK_SIGMA3,       // param = k : \int q^2 S I_R(q/k) dq / (2 pi^2)
+    LK_XI,           // param = r : \int q^2 S j0(q r) dq / (2 pi^2)  (CorrelationFunction::Evaluate)
 };
 
 struct LinOutSpec {

@@ -41,6 +41,7 @@ PRSD_HD double lin_kernel(int type, int sub, double p, double q)
             const double IR = (5.0/(512.0*r4*r))*(-4.0*r*(1.0 + r2)*(3.0 - 14.0*r2 + 3.0*r4) - 3.0*w2*w2*lg);
             return inv2pi2*q*q*IR;
         }
+        case LK_XI: return inv2pi2*q*q*sph_j0(q*p);      // = q sin(q r) / (2 pi^2 r), CorrelationFunction.cpp:151-157
         default: return 0.0;
     }
 }
@@ -48,7 +49,7 @@ PRSD_HD double lin_kernel(int type, int sub, double p, double q)
 // angular frequency of the kernel in q (for sub-panelling)
 PRSD_HD double lin_omega(int type, double p)
 {
-    if (type == LK_XZEL || type == LK_YZEL) return p;
+    if (type == LK_XZEL || type == LK_YZEL || type == LK_XI) return p;
     if (type == LK_SIGMA_R) return 2.0*p;
     return 0.0;
 }

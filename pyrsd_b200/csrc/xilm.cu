@@ -106,7 +106,7 @@ void compute_xilm_dev(Context& ctx, int batch, int l, int m, int nk, const doubl
                       int nr, const double* h_r, double smoothing, double scale, double* d_out)
 {
     // ComputeXiLM, FFTLOG branch (CorrelationFunction.cpp:56-90)
-    PRSD_REQUIRE(nk >= 4 && nk <= 8192, "ComputeXiLM: %d input samples unsupported (4..8192)", nk);
+    PRSD_REQUIRE(nk >= 4 && nk <= 4096, "ComputeXiLM: %d input samples unsupported (4..4096: the batched spline build)", nk);
     for (int i = 1; i < nk; i++) PRSD_REQUIRE(h_k[i] > h_k[i - 1] && h_k[0] > 0, "ComputeXiLM: abscissae must be positive and increasing");
     std::vector<double> kg, rg;
     double dlogr, logrc;

@@ -24,7 +24,7 @@ from . import _native as N
 __all__ = ['Cosmology', 'ClassParams', 'transfers', 'IntegrationMethods', 'LinearPS', 'Imn', 'Jmn', 'Kmn',
            'ImnOneLoop', 'OneLoopPdd', 'OneLoopPdv', 'OneLoopPvv', 'OneLoopP22Bar', 'ZeldovichPS', 'ZeldovichP00',
            'ZeldovichP01', 'ZeldovichP11', 'ZeldovichCF', 'pk_to_xi', 'xi_to_pk', 'ComputeXiLM', 'ComputeXiLM_fftlog',
-           'CubicSpline', 'FFTLog']
+           'CubicSpline', 'LinearSpline', 'FFTLog', 'CorrelationFunction', 'Kaiser', 'SimpsIntegrate', 'TrapzIntegrate']
 
 _vp = C.c_void_p
 _dp = N._dp
@@ -248,6 +248,12 @@ class _Spectra(N.Handle):
         x = N.as_f64(x)
         out = np.empty((self.ncosmo, max(len(x), 1)))
         N.check(_L().prsd_eval_ps_integral(self.ptr, what, len(x), x, factor, out))
+        return out
+
+    def correlation(self, r, kmin, kmax):
+        r = N.as_f64(r)
+        out = np.empty((self.ncosmo, max(len(r), 1)))
+        N.check(_L().prsd_eval_correlation(self.ptr, len(r), r, float(kmin), float(kmax), out))
         return out
 
     def ensure_oneloop(self):
@@ -711,13 +717,100 @@ def xi_to_pk(ell, r, xi, k, smoothing=0.005, method=IntegrationMethods.FFTLOG):
     return (-1.)**(ell//2)*8*np.pi**3*ComputeXiLM(ell, 2, r, xi, k, smoothing, method)
 
 
-def ComputeXiLM_fftlog(l, m, k, pk, q=0., smoothing=0.):
-    """log-spaced input; returns (r, xi) (``compute_xilm_fftlog`` of CorrelationFunction.i, .cpp:23-54)"""
+def ComputeXiLM_fftlog(l, m, k, pk, *args, **kwargs):
+    """log-spaced input (``compute_xilm_fftlog`` of CorrelationFunction.i:28-37, .cpp:23-54).  Two call forms:
+
+    * the reference's: ``ComputeXiLM_fftlog(l, m, k, pk, r, xi, q=0, smoothing=0)`` fills the caller's arrays ``r`` and ``xi``
+      (length ``len(k)``) in place and returns None (rsd/window.py:238, 251);
+    * ``ComputeXiLM_fftlog(l, m, k, pk, q=0, smoothing=0)`` returns ``(r, xi)``."""
+    inplace = len(args) >= 2 and isinstance(args[0], np.ndarray) and isinstance(args[1], np.ndarray)
+    if inplace:
+        r_out, xi_out, args = args[0], args[1], args[2:]
+        if r_out.shape != (len(k),) or xi_out.shape != (len(k),) or r_out.dtype != np.float64 or xi_out.dtype != np.float64:
+            raise ValueError("ComputeXiLM_fftlog: `r` and `xi` must be float64 arrays of the length of `k`")
+    q = args[0] if len(args) > 0 else kwargs.pop('q', 0.)
+    smoothing = args[1] if len(args) > 1 else kwargs.pop('smoothing', 0.)
+    if kwargs or len(args) > 2:
+        raise TypeError("ComputeXiLM_fftlog: unexpected arguments")
     k, pk = N.as_f64(k), N.as_f64(pk)
     r, xi = np.empty(len(k)), np.empty((1, len(k)))
     N.check(_L().prsd_compute_xilm_fftlog(N.default_context().ptr, 1, int(l), int(m), len(k), k, pk.reshape(1, -1),
                                           float(q), float(smoothing), r, xi))
+    if inplace:
+        r_out[...] = r
+        xi_out[...] = xi[0]
+        return None
     return r, xi[0]
+
+
+class CorrelationFunction(PickalableSWIG):
+    """``CorrelationFunction(P, kmin=1e-4, kmax=10)`` (CorrelationFunction.i:39-55): xi(r) = 1/(2 pi^2 r) int_kmin^kmax
+    k sin(k r) P(k) dk (CorrelationFunction.cpp:145-168, adaptive quadrature there).  For a ``LinearPS`` the integral is the
+    device's product-integration operator on the knot table of P_L (the oscillating factor is integrated exactly against
+    the interpolant, as for X(r), Y(r)); for any other spectrum P is sampled on 16384 log-spaced k and integrated by the
+    device Simpson rule of ``ComputeXiLM(0, 2, ..., method=SIMPS)``."""
+    def __init__(self, P, kmin=1e-4, kmax=1e1):
+        self.args = (P, kmin, kmax)
+        self._P, self._kmin, self._kmax = P, float(kmin), float(kmax)
+
+    def __getstate__(self):
+        return {'args': (self._P, self._kmin, self._kmax)}
+
+    def __call__(self, r):
+        ra, scalar = _scalar_or_array(r)
+        if isinstance(self._P, LinearPS):
+            return _ret(self._P._sp.correlation(ra, self._kmin, self._kmax)[0], scalar)
+        k = np.logspace(np.log10(self._kmin), np.log10(self._kmax), 16384)
+        return _ret(ComputeXiLM(0, 2, k, self._P(k), ra, 0., IntegrationMethods.SIMPS), scalar)
+
+    Evaluate = EvaluateMany = __call__
+
+    def GetPowerSpectrum(self): return self._P
+    def GetKmin(self): return self._kmin
+    def GetKmax(self): return self._kmax
+    def SetKmin(self, kmin): self._kmin = float(kmin)
+    def SetKmax(self, kmax): self._kmax = float(kmax)
+
+
+class Kaiser(PickalableSWIG):
+    """``Kaiser(P_L, f, b1=1)`` (Kaiser.i, Kaiser.cpp:9-62): linear redshift-space spectrum, its multipoles and theirs of
+    the correlation function.  (As the reference: ``P_s`` is (1 + f mu^2)^2 P(k) -- no b1 -- while the multipole
+    prefactors carry b1^2, Kaiser.cpp:14-31.)"""
+    def __init__(self, P_L, f, b1=1.0):
+        self.args = (P_L, f, b1)
+        self._P, self._f, self._b1 = P_L, float(f), float(b1)
+
+    def __getstate__(self):
+        return {'args': (self._P, self._f, self._b1)}
+
+    def P_s(self, k, mu):
+        return (1. + self._f*np.asarray(mu, dtype=float)**2)**2*self._P(k)
+
+    __call__ = P_s
+
+    def _prefactor(self, ell):
+        beta = self._f/self._b1
+        pre = {0: 1. + (2./3.)*beta + (1./5.)*beta**2, 2: (4./3.)*beta + (4./7.)*beta**2, 4: (8./35.)*beta**2}.get(int(ell), 0.)
+        return pre*self._b1**2
+
+    def P_ell(self, ell, k):
+        return self._prefactor(ell)*self._P(k)
+
+    def Xi_ell(self, ell, r, Nk=32768, kmin=1e-5, kmax=100):
+        ra, scalar = _scalar_or_array(r)
+        if int(Nk) > 4096:
+            raise ValueError("Kaiser.Xi_ell: the device ComputeXiLM takes at most 4096 samples (the reference's default is "
+                             "Nk = 32768); pass Nk <= 4096")
+        k = np.exp(np.linspace(np.log(kmin), np.log(kmax), int(Nk)))
+        k[0], k[-1] = kmin, kmax                                     # parray::logspace (parray.cpp:101-121)
+        xi = ComputeXiLM(int(ell), 2, k, self._P(k), ra, 0.)
+        return _ret((-1.)**(int(ell)//2)*self._prefactor(ell)*xi, scalar)
+
+    def SetGrowthRate(self, f): self._f = float(f)
+    def GetGrowthRate(self): return self._f
+    def SetLinearBias(self, b1): self._b1 = float(b1)
+    def GetLinearBias(self): return self._b1
+    def GetPowerSpectrum(self): return self._P
 
 
 class FFTLog(object):

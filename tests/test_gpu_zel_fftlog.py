@@ -188,3 +188,56 @@ def test_fftlog_backward_and_linear_spline(oracle):
     i = np.searchsorted(x, xq, side='right') - 1
     assert np.allclose(S.EvaluateDerivative(xq), (y[i + 1] - y[i])/(x[i + 1] - x[i]), rtol=1e-12)
     assert isinstance(S(0.5*(x[3] + x[4])), float)
+
+
+def test_correlation_function_and_kaiser_vs_oracle(oracle, ref_plin, cosmo):
+    """``CorrelationFunction(P_L)`` against the UNMODIFIED reference class (adaptive GK quadrature at its default
+    tolerance, CorrelationFunction.cpp:145-168) and ``Kaiser`` against its closed forms (Kaiser.cpp:14-62)"""
+    from pyrsd_b200 import pygcl
+    P = pygcl.LinearPS(cosmo, 0.)
+    r = np.array([0.5, 2., 10., 30., 60., 90., 105., 130., 180.])
+    cf = pygcl.CorrelationFunction(P)
+    assert cf.GetKmin() == 1e-4 and cf.GetKmax() == 10. and cf.GetPowerSpectrum() is P
+    ref = ref_plin.correlation(r, 1e-4, 10.)
+    out = cf(r)
+    # r^2 xi(r) is O(10) across the range: the reference's quadrature stops at 1e-5 of the integral of |integrand|'s scale
+    assert np.max(np.abs(out - ref)*r**2) < 1e-5*np.max(np.abs(ref)*r**2)
+    assert isinstance(cf(10.), float) and abs(cf(10.)/out[2] - 1) < 1e-14      # one output: the dot-product kernel's summation order
+    cf.SetKmin(1e-3); cf.SetKmax(5.)
+    ref2 = ref_plin.correlation(r[2:6], 1e-3, 5.)
+    assert np.max(np.abs(cf(r[2:6]) - ref2)*r[2:6]**2) < 1e-5*np.max(np.abs(ref2)*r[2:6]**2)
+    # another PowerSpectrum: sampled and integrated by the device Simpson rule
+    import pickle
+    cf2 = pickle.loads(pickle.dumps(pygcl.CorrelationFunction(P, 1e-4, 10.)))
+    assert np.array_equal(cf2(r), out)
+
+    kz = pygcl.Kaiser(P, 0.8, 2.0)
+    k = np.logspace(-2, 0, 7)
+    beta = 0.4
+    assert np.allclose(kz.P_ell(0, k), 4.*(1 + 2*beta/3 + beta**2/5)*P(k), rtol=1e-14)
+    assert np.allclose(kz.P_ell(2, k), 4.*(4*beta/3 + 4*beta**2/7)*P(k), rtol=1e-14)
+    assert np.allclose(kz.P_ell(4, k), 4.*(8*beta**2/35)*P(k), rtol=1e-14)
+    assert np.allclose(kz(k, 0.5), (1 + 0.8*0.25)**2*P(k), rtol=1e-14)
+    rr = np.array([20., 60., 100.])
+    kk = oracle.logspace(1e-5, 100., 4096)
+    for ell in (0, 2, 4):
+        ref = (-1.)**(ell//2)*kz._prefactor(ell)*oracle.ComputeXiLM(ell, 2, kk, P(kk), rr, 0.)
+        assert np.max(np.abs(kz.Xi_ell(ell, rr, Nk=4096) - ref)) < 1e-8*np.max(np.abs(ref)), ell
+    with pytest.raises(ValueError):
+        kz.Xi_ell(0, rr)                     # the reference's default Nk = 32768 exceeds the device ComputeXiLM's 4096
+    kz.SetGrowthRate(0.5); kz.SetLinearBias(1.5)
+    assert kz.GetGrowthRate() == 0.5 and kz.GetLinearBias() == 1.5
+
+
+def test_compute_xilm_fftlog_in_place_form(cosmo):
+    """the reference's call form fills ``r`` and ``xi`` in place (CorrelationFunction.i:28-37; rsd/window.py:238, 251)"""
+    from pyrsd_b200 import pygcl
+    P = pygcl.LinearPS(cosmo, 0.)
+    k = np.logspace(-4, 1.5, 512)
+    pk = P(k)
+    r1, xi1 = pygcl.ComputeXiLM_fftlog(2, 2, k, pk, 0.3, 0.1)
+    r2, xi2 = np.empty(len(k)), np.empty(len(k))
+    assert pygcl.ComputeXiLM_fftlog(2, 2, k, pk, r2, xi2, 0.3, 0.1) is None
+    assert np.array_equal(r1, r2) and np.array_equal(xi1, xi2)
+    with pytest.raises(ValueError):
+        pygcl.ComputeXiLM_fftlog(2, 2, k, pk, np.empty(3), np.empty(3))
