@@ -357,6 +357,54 @@ class WindowConvolution(object):
         return np.asarray([np.einsum('ij,ij->i', xi, self._get_kernel(ell, r)) for ell in ells]).T.copy(order=order)
 
 
+def convolve_multipoles(k, Pell, ells, convolver, qbias=0.7, dry_run=False, legacy=True):
+    """Window-convolved power multipoles, the older route of ``rsd/window.py:214-307`` (``WindowFunctionTransfer`` is the
+    current one).  ``Pell`` [Nk][Nell] on ``k``; ``convolver`` a ``WindowConvolution``.
+
+    * ``legacy=True``: multipoles with fewer than 500 k are first splined to 500 log-spaced points (FITPACK, as the
+      reference); xi_ell on the window's own separations by the trapezoid rule, the window kernels, and back to the input
+      k by the trapezoid rule -- the transforms are ``pygcl.pk_to_xi`` / ``xi_to_pk`` with ``method=TRAPZ`` (device).
+      Returns ``(k, Pell_conv)`` with Pell_conv [Nk][Nell].
+    * ``legacy=False``: biased FFTLog there and back on the input (log-spaced) ``k`` (``pygcl.ComputeXiLM_fftlog`` with
+      q = +-qbias).  Returns ``(k, Pell_conv)``."""
+    from . import pygcl
+    k = np.asarray(k, dtype=float)
+    Pell = np.asarray(Pell, dtype=float)
+    ells = [int(ell) for ell in ells]
+    sign = [(-1.)**(ell//2) for ell in ells]
+    if not legacy:
+        fwd = [pygcl.ComputeXiLM_fftlog(ell, 2, k, Pell[:, i], qbias) for i, ell in enumerate(ells)]
+        # Reference behaviour kept: every multipole's transform has its own low-ringing kr, hence its own output grid, but
+        # rsd/window.py:236-251 lets each call overwrite ONE `rr` (and `kk`) array -- the kernels are evaluated on, and the
+        # backward transforms start from, the grid of the LAST multipole (the grids differ by a factor ~1 +- 4e-4)
+        rr = fwd[-1][0]
+        xi = np.asfortranarray(np.array([sg*f[1] for sg, f in zip(sign, fwd)]).T)
+        xi_conv = xi.copy() if dry_run else convolver(ells, rr, xi, order='F')
+        back = [pygcl.ComputeXiLM_fftlog(ell, 2, rr, np.ascontiguousarray(xi_conv[:, i]), -qbias) for i, ell in enumerate(ells)]
+        return back[-1][0], np.asfortranarray(np.array([sg*(2*np.pi)**3*b[1] for sg, b in zip(sign, back)]).T)
+
+    if len(ells) != Pell.shape[-1]:
+        raise ValueError("shape mismatch between multipole numbers and number of multipoles provided")
+    if not all(ell in (0, 2, 4, 6) for ell in ells):
+        raise ValueError("valid `ell` values are [0,2,4,6]")
+    s = convolver.s
+    k_out = k if k.ndim == 2 else np.repeat(k[:, None], len(ells), axis=1)
+    if k_out.shape[-1] != len(ells):
+        raise ValueError("input `k_out` must have %d columns for ell=%s multipoles" % (len(ells), str(ells)))
+    if len(k) < 500:
+        from scipy import interpolate as _interp
+        k_hi = np.logspace(np.log10(k.min()), np.log10(k.max()), 500)
+        Pell = np.array([_interp.splev(k_hi, _interp.splrep(k, Pell[:, i], k=3, s=0)) for i in range(len(ells))]).T
+        k = k_hi
+    TRAPZ = pygcl.IntegrationMethods.TRAPZ
+    xi = np.array([pygcl.pk_to_xi(ell, k, np.ascontiguousarray(Pell[:, i]), s, smoothing=0., method=TRAPZ)
+                   for i, ell in enumerate(ells)]).T
+    xi_conv = xi.copy() if dry_run else convolver(ells, s, xi, order='F')
+    conv = np.array([pygcl.xi_to_pk(ell, s, np.ascontiguousarray(xi_conv[:, i]), np.ascontiguousarray(k_out[:, i]), smoothing=0.,
+                                    method=TRAPZ) for i, ell in enumerate(ells)]).T
+    return k_out[:, 0], conv
+
+
 class WindowFunctionTransfer(GriddedMultipoleTransfer):
     """Unconvolved P(k, mu) on the internal grid -> window-convolved multipoles
     (``rsd/transfers/window.py:9-132``).

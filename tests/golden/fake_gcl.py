@@ -277,7 +277,11 @@ def LinearSpline(x, y):
 def pk_to_xi(ell, k, pk, r, smoothing=0.5, method=0): return R.pk_to_xi(ell, k, pk, r, smoothing, method)
 def xi_to_pk(ell, r, xi, k, smoothing=0.005, method=0): return R.xi_to_pk(ell, r, xi, k, smoothing, method)
 def ComputeXiLM(l, m, k, pk, r, smoothing=0., method=0): return R.ComputeXiLM(l, m, k, pk, r, smoothing, method)
-def compute_xilm_fftlog(l, m, k, pk, q=0., smoothing=0.): return R.ComputeXiLM_fftlog(l, m, k, pk, q, smoothing)
+def compute_xilm_fftlog(l, m, k, pk, r, xi, q=0., smoothing=0.):
+    """SWIG's in-place form (CorrelationFunction.i:28-37): fills r, xi"""
+    rr, xx = R.ComputeXiLM_fftlog(l, m, k, pk, q, smoothing)
+    r[...] = rr
+    xi[...] = xx
 def SimpsIntegrate(x, y): return R.SimpsIntegrate(x, y)
 def TrapzIntegrate(x, y): return R.TrapzIntegrate(x, y)
 

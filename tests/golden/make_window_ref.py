@@ -115,6 +115,25 @@ def main():
                       ('wedges', wedges), ('poles', poles), ('bounds', np.array(bounds))):
         out['g_' + name] = val
 
+    # the older route, rsd/window.py:214-307 (convolve_multipoles), UNMODIFIED, both branches; its transforms go through the
+    # reference C++ (oracle/_ref: ComputeXiLM TRAPZ, ComputeXiLM_fftlog)
+    from pyRSD.rsd.window import convolve_multipoles
+    convolver = WindowConvolution(window[:, 0], window[:, 1:], max_ellprime=4, max_ell=4)
+    kc = np.logspace(-3, np.log10(0.6), 120)                    # < 500 points: the FITPACK refinement branch
+    mu_g = np.linspace(0.0125, 0.9875, 40)
+    Pg = synthetic_power(kc[:, None]*np.ones((1, 40)), np.ones((120, 1))*mu_g[None, :])
+    from scipy.special import legendre
+    Pell_c = np.array([(2*ell + 1)*np.mean(Pg*legendre(ell)(mu_g)[None, :], axis=1) for ell in ells]).T
+    out['c_k'], out['c_Pell'] = kc, Pell_c
+    out['c_legacy'] = np.asarray(convolve_multipoles(kc, Pell_c, ells, convolver, legacy=True)[1])
+    out['c_legacy_dry'] = np.asarray(convolve_multipoles(kc, Pell_c, ells, convolver, dry_run=True, legacy=True)[1])
+    kf = np.logspace(-4, 1, 1024)
+    Pgf = synthetic_power(kf[:, None]*np.ones((1, 40)), np.ones((1024, 1))*mu_g[None, :])
+    Pell_f = np.array([(2*ell + 1)*np.mean(Pgf*legendre(ell)(mu_g)[None, :], axis=1) for ell in ells]).T
+    kk, Pc = convolve_multipoles(kf, Pell_f, ells, convolver, qbias=0.7, legacy=False)
+    out['f_k'], out['f_Pell'], out['f_kout'], out['f_conv'] = kf, Pell_f, np.asarray(kk), np.asarray(Pc)
+    print('convolve_multipoles: legacy', out['c_legacy'].shape, 'fftlog', out['f_conv'].shape)
+
     path = os.path.join(HERE, 'window_ref.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, '%.1f kB' % (os.path.getsize(path)/1e3))

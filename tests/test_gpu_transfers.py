@@ -201,3 +201,25 @@ def test_continuous_multipole_and_wedge_transfers(oracle):
     for b, (lo, hi) in enumerate(bounds):
         sel = (mug >= lo) & (mug < (1.0005 if hi == 1.0 else hi))
         assert np.max(np.abs(got[:, b] - Pw[:, sel].mean(axis=1))) < 1e-12*np.max(np.abs(Pw))
+
+
+def test_convolve_multipoles_vs_reference():
+    """the older window route (rsd/window.py:214-307) vs the UNMODIFIED reference function run on the reference C++
+    transforms (tests/golden/make_window_ref.py): trapezoid branch with the FITPACK refinement, and biased FFTLog branch"""
+    from pyrsd_b200.transfers import WindowConvolution, convolve_multipoles
+    window = REF['window']
+    conv = WindowConvolution(window[:, 0], window[:, 1:], max_ellprime=4, max_ell=4)
+    ells = [0, 2, 4]
+    k, out = convolve_multipoles(REF['c_k'], REF['c_Pell'], ells, conv, legacy=True)
+    assert np.array_equal(k, REF['c_k']) and out.shape == REF['c_legacy'].shape
+    assert np.max(np.abs(out - REF['c_legacy'])) < 1e-9*np.max(np.abs(REF['c_legacy']))
+    _, dry = convolve_multipoles(REF['c_k'], REF['c_Pell'], ells, conv, dry_run=True, legacy=True)
+    assert np.max(np.abs(dry - REF['c_legacy_dry'])) < 1e-9*np.max(np.abs(REF['c_legacy_dry']))
+    kk, Pc = convolve_multipoles(REF['f_k'], REF['f_Pell'], ells, conv, qbias=0.7, legacy=False)
+    assert np.max(np.abs(kk/REF['f_kout'] - 1)) < 1e-12
+    for i in range(3):
+        assert np.max(np.abs(Pc[:, i] - REF['f_conv'][:, i])) < 1e-9*np.max(np.abs(REF['f_conv'][:, i])), i
+    with pytest.raises(ValueError):
+        convolve_multipoles(REF['c_k'], REF['c_Pell'], [0, 2], conv)
+    with pytest.raises(ValueError):
+        convolve_multipoles(REF['c_k'], REF['c_Pell'], [0, 2, 3], conv)
