@@ -97,10 +97,11 @@ class DarkMatterSpectrum(object):
     def _tables(self):
         g = self._g
         eng = g._ensure_tables()
-        if self._tabs is None or self._tabs[0] is not g._result:
+        tabs = g.__dict__.get('_dm_tabs')          # kept on the assembly model: every view of it shares one copy
+        if tabs is None or tabs[0] is not g._result:
             t = {n: eng.get(g._result, n)[0] for n in ('I', 'J', 'K', 'ML', 'sigmasq_k')}
-            self._tabs = (g._result, eng.k_interp, t, {})
-        return self._tabs
+            tabs = g.__dict__['_dm_tabs'] = (g._result, eng.k_interp, t, {})
+        return tabs
 
     def _spl(self, key, y):
         _, kint, _, cache = self._tables()
@@ -414,7 +415,7 @@ class BiasedSpectrum(object):
         try:
             g.b1_cA, g.b1_cB = self._pair()                  # pair 1 of the assembly kernel is (cA, cB)
             km = g.k
-            eng, gal, _ = g._evaluate([g._state(km)], 'power', km[:1], np.zeros(1))
+            eng, gal, _ = g._evaluate([g._state(km)], 'power', km[len(km)//2:len(km)//2 + 1], np.zeros(1))      # one point inside the grid whatever the AP parameters
             return km, eng.galaxy_moments(gal, 1)[0, 1], eng.galaxy_base(gal, 1)[0]
         finally:
             g.b1_cA, g.b1_cB = saved
@@ -436,21 +437,7 @@ class BiasedSpectrum(object):
     def P_mu6(self, k): return self._eval(3, k)
 
     def _phm(self, b1, k):
-        """power_biased.py:310-340; HZPT form: rsd/hzpt/Phm.py:24-68, 231-296 (Pade broadband + b1 x Zel'dovich P00)"""
-        g = self._g
-        km, _, base = self._moments()
-        R = self._BASE_ROWS
-        if g.use_Phm_model:
-            hm = np.asarray(_rsd.galaxy_config()[35:55]).reshape(5, 4)       # A0, R1, R1h, R2h, R x (amp, alpha, beta, run)
-            x, lb = g.sigma8_z/0.8, np.log(b1)
-            A0, R1, R1h, R2h, Rr = [a*b1**(al + run*lb)*x**be for a, al, be, run in hm]
-            k2 = km**2
-            F = 1. - 1./(1. + k2*Rr**2)
-            y = F*A0*(1. + k2*R1**2)/(1. + k2*R1h**2 + (km*R2h)**4) + b1*base[R['Z00']]
-        else:
-            bs = -2./7*(b1 - 1.) if g.use_tidal_bias else 0.
-            y = b1*base[R['P00']] + g.b2_00(b1)*base[R['K00']] + bs*base[R['K00s']]
-        return self._to_k(km, y, k)
+        return phm_from_base(self._g, self._moments()[2], b1, k)
 
     def Phm(self, k): return self._phm(self._pair()[0], k)
     def Phm_bar(self, k): return self._phm(self._pair()[1], k)
@@ -482,6 +469,24 @@ class BiasedSpectrum(object):
         return np.ravel(P, order='F') if flatten else P
 
 
+def phm_from_base(g, base, b1, k):
+    """the halo-matter spectrum of linear bias ``b1`` from the blocks of the assembly kernel's first stage
+    (power_biased.py:310-340; HZPT form: rsd/hzpt/Phm.py:24-68, 231-296 -- Pade broadband + b1 x Zel'dovich P00)"""
+    km = g.k
+    R = BiasedSpectrum._BASE_ROWS
+    if g.use_Phm_model:
+        hm = np.asarray(_rsd.galaxy_config()[35:55]).reshape(5, 4)       # A0, R1, R1h, R2h, R x (amp, alpha, beta, run)
+        x, lb = g.sigma8_z/0.8, np.log(b1)
+        A0, R1, R1h, R2h, Rr = [a*b1**(al + run*lb)*x**be for a, al, be, run in hm]
+        k2 = km**2
+        F = 1. - 1./(1. + k2*Rr**2)
+        y = F*A0*(1. + k2*R1**2)/(1. + k2*R1h**2 + (km*R2h)**4) + b1*base[R['Z00']]
+    else:
+        bs = -2./7*(b1 - 1.) if g.use_tidal_bias else 0.
+        y = b1*base[R['P00']] + g.b2_00(b1)*base[R['K00']] + bs*base[R['K00s']]
+    return BiasedSpectrum._to_k(km, y, k)
+
+
 class HaloSpectrum(BiasedSpectrum):
     """halos of one linear bias: ``b1_bar`` is ``b1`` (``power_halo.py:4-23``)"""
 
@@ -490,3 +495,6 @@ class HaloSpectrum(BiasedSpectrum):
 
     def _pair(self):
         return self.b1, self.b1
+
+
+from . import model_api  # noqa: E402,F401  (attaches the rest of the reference's model surface to the three classes)

@@ -117,8 +117,8 @@ class Cosmology(PickalableSWIG):
         if k is None or Tk is None or sigma8 is None:
             raise ValueError("pyrsd_b200.Cosmology needs the discrete transfer function: "
                              "Cosmology(params, tf, sigma8, k, Tk); CLASS is not run by this library")
-        if tf not in (transfers.CLASS, transfers.FromArrays):
-            raise ValueError("only tabulated transfer functions (transfers.CLASS) are supported")
+        if tf not in (transfers.CLASS, transfers.FromArrays, transfers.EH_NoWiggle):
+            raise ValueError("only tabulated transfer functions (transfers.CLASS) and their no-wiggle clones are supported")
         self._params = ClassParams(params)
         self._tf = int(tf)
         self._sigma8 = float(sigma8)
@@ -137,9 +137,33 @@ class Cosmology(PickalableSWIG):
         self.__init__(ClassParams.from_dict(a[0]), *a[1:])
 
     def clone(self, tf=None):
-        if tf is not None and tf != self._tf:
-            raise ValueError("only tabulated transfer functions are supported")
-        return Cosmology(*self.args)
+        """a copy; ``tf=transfers.EH_NoWiggle``: the same parameters with the Eisenstein-Hu no-wiggle transfer function
+        tabulated on the same k (Cosmology.cpp:233-246 on the grid of :270, as ``SetTransferFunction`` does)"""
+        if tf is None or tf == self._tf:
+            return Cosmology(*self.args)
+        if tf != transfers.EH_NoWiggle:
+            raise ValueError("only tabulated transfer functions and their Eisenstein-Hu no-wiggle clones are supported")
+        a = self.args
+        return Cosmology(a[0], transfers.EH_NoWiggle, a[2], a[3], self.GetNoWiggleTransfer(a[3]))
+
+    def GetNoWiggleTransfer(self, k):
+        """Eisenstein & Hu (1998) no-wiggle fit, eqs. 26, 28-31 (Cosmology.cpp:233-246 with the parameters of :311-362)"""
+        k = np.asarray(k, dtype=float)
+        h = self.h()
+        omh2, obh2 = self.Omega0_m()*h*h, self.Omega0_b()*h*h
+        fb = obh2/omh2
+        theta = self.Tcmb()/2.7
+        keq = 0.0746*omh2/theta**2
+        s = h*44.5*np.log(9.83/omh2)/np.sqrt(1. + 10.*obh2**0.75)
+        alpha_gamma = 1. - 0.328*np.log(431.*omh2)*fb + 0.38*np.log(22.3*omh2)*fb*fb
+        kk = k*h
+        ks = kk*s/h
+        q = kk/(13.41*keq)
+        geff = omh2*(alpha_gamma + (1. - alpha_gamma)/(1. + (0.43*ks)**4))
+        qeff = q*omh2/geff
+        L0 = np.log(2.*np.e + 1.8*qeff)
+        C0 = 14.2 + 731./(1. + 62.5*qeff)
+        return L0/(L0 + C0*qeff**2)
 
     # ---- accessors
     def GetParams(self): return self._params

@@ -513,6 +513,8 @@ class GalaxySpectrum(object):
         d = dict(self.__dict__)
         for k in ('_engine', '_spectra', '_result'):
             d[k] = None
+        for k in ('_dm_tabs', '_b2s', '_b2s_key'):
+            d.pop(k, None)
         return d
 
     def __setstate__(self, state):
@@ -915,7 +917,7 @@ def _dm_spectra(self):
     P_lin (normed_power_lin), P00, P01, P11_mu4 (dm/P00.py, P01.py, P11.py totals), Pdd, Pdv, Pvv
     (power_dm.py:797-884 incl. the Jennings et al. fits of :676-718)"""
     kmodel = self.k
-    eng, gal, _ = self._evaluate([self._state(kmodel)], 'power', kmodel[:1], np.zeros(1))
+    eng, gal, _ = self._evaluate([self._state(kmodel)], 'power', kmodel[len(kmodel)//2:len(kmodel)//2 + 1], np.zeros(1))
     base = eng.galaxy_base(gal, 1)[0]
     return {name: base[row].copy() for name, row in _DM_ROWS.items()}
 
@@ -934,3 +936,21 @@ def _new_result():
     r = _Result(None)
     r.ncosmo = 0
     return r
+
+
+def _z_setattr(self, name, value):
+    """``redshift_params`` (power_biased.py:128-146): setting ``z`` re-derives ``f`` and / or ``sigma8_z`` from the cosmology"""
+    object.__setattr__(self, name, value)
+    if name == 'z' and 'cosmo' in self.__dict__:
+        rp = getattr(self, 'redshift_params', ())
+        if any(par not in ('f', 'sigma8_z') for par in rp):
+            raise ValueError("valid parameters for redshift scaling: 'f' and 'sigma8_z'")
+        if 'f' in rp:
+            object.__setattr__(self, 'f', self.cosmo.f_z(value))
+        if 'sigma8_z' in rp:
+            object.__setattr__(self, 'sigma8_z', self.cosmo.Sigma8_z(value))
+
+
+GalaxySpectrum.__setattr__ = _z_setattr
+
+from . import dm as _dm_models  # noqa: E402,F401  (dm.py ends by importing model_api, which completes GalaxySpectrum)

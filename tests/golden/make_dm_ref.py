@@ -31,6 +31,11 @@ DM_CASES = {
 DM_UPDATE = dict(sigma8_z=0.61, f=0.77, sigma_v2=198., sigma_bv2=356., sigma_bv4=382., alpha_par=1.02, alpha_perp=0.99)
 
 
+HALO_TERMS = ['P00_ss.mu0', 'P00_ss_no_stoch.mu0', 'P01_ss.mu2', 'P11_ss.mu2', 'P11_ss.mu4', 'P02_ss.mu2', 'P02_ss.mu4',
+              'P12_ss.mu4', 'P12_ss.mu6', 'P22_ss.mu4', 'P22_ss.mu6', 'P03_ss.mu4', 'P13_ss.mu4', 'P13_ss.mu6', 'P04_ss.mu4',
+              'P04_ss.mu6']
+
+
 def main():
     t0 = time.time()
     G.ZEL_SOURCE = 'pi'
@@ -70,6 +75,7 @@ def main():
         print(name, 'done %.0fs' % (time.time() - t0), flush=True)
         G.save_cache()
     out['term_names'] = np.array([n for n, _ in DM_TERMS])
+    out['halo_term_names'] = np.array(HALO_TERMS)
     # BiasedSpectrum (b1, b1_bar free) and HaloSpectrum (b1_bar = b1) with the synthetic stand-ins of make_galaxy_ref.build_model
     from pyRSD.rsd import BiasedSpectrum
 
@@ -89,6 +95,13 @@ def main():
         out[tag + '_Phm'] = np.asarray(h.Phm(km))
         out[tag + '_Phm_bar'] = np.asarray(h.Phm_bar(km))
         out[tag + '_stochasticity'] = np.asarray(h.stochasticity(km))
+        # the nine halo-halo terms, piece by piece (biased/P00.py ... P22.py)
+        rows = []
+        for tname in HALO_TERMS:
+            term, piece = tname.split('.')
+            rows.append(np.asarray(getattr(getattr(h, term), piece)(km), dtype=float)*np.ones_like(km))
+        out[tag + '_halo_terms'] = np.array(rows)
+        out[tag + '_scalars'] = np.array([h.bs, h.bs_bar, h.sigmav_halo, h.sigmav_halo_bar])
         print(tag, 'done %.0fs' % (time.time() - t0), flush=True)
     path = os.path.join(HERE, 'dm_ref.npz')
     np.savez_compressed(path, **out)

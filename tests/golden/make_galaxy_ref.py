@@ -241,6 +241,9 @@ def build_model(cosmo_mod, gcl_cosmo, z, **kwargs):
     return model
 
 
+SUB_SPECTRA = ['cAcA', 'cAcB', 'cBcB', 'cAsA', 'cAsB', 'cBsA', 'cBsB', 'sAsA', 'sAsB', 'sBsB', 'cc', 'cs', 'ss']
+
+
 def main():
     t0 = time.time()
     cosmo_mod = install_stubs()
@@ -320,6 +323,13 @@ def main():
         P = np.asarray(model.power(k, mu))
         out[name + '_P'] = P
         out[name + '_pars'] = np.array([float(getattr(model, n)) for n in names])
+        if case_name in ('z055_ap', 'z055_so_gauss'):
+            # the ten sub-spectra and the three groups (power_gal.py:292-399) at paired points of a coarse grid
+            ks, mus = k[::25], mu[::8]
+            K, M = [a.ravel() for a in np.meshgrid(ks, mus, indexing='ij')]
+            out[name + '_sub_k'], out[name + '_sub_mu'] = ks, mus
+            out[name + '_sub'] = np.array([np.asarray(getattr(model, 'Pgal_' + n)(K, M)).reshape(len(ks), len(mus))
+                                           for n in SUB_SPECTRA])
         out[name + '_modelk'] = np.asarray(model.k)
         # the four moment splines of one bias pair, for a finer-grained check
         model.b1, model.b1_bar = model.b1_cB, model.b1_sA
@@ -334,6 +344,7 @@ def main():
         print(name, 'done  %.0fs' % (time.time() - t0), flush=True)
         save_cache()
     out['par_names'] = np.array(names)
+    out['sub_names'] = np.array(SUB_SPECTRA)
     path = os.path.join(HERE, 'galaxy_ref.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, '%.1f kB' % (os.path.getsize(path)/1e3))

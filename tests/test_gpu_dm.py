@@ -109,3 +109,80 @@ def test_biased_spectrum_vs_reference_python(cosmo, engine, tag):
     assert np.max(np.abs(h.Phm(km)/ref[tag + '_Phm'] - 1)) < TOL
     assert np.max(np.abs(h.Phm_bar(km)/ref[tag + '_Phm_bar'] - 1)) < TOL
     assert np.max(np.abs(h.stochasticity(km)/ref[tag + '_stochasticity'] - 1)) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/dm_ref.npz not generated")
+@pytest.mark.parametrize('tag', ['biased', 'halo'])
+def test_halo_terms_vs_reference_python(cosmo, engine, tag):
+    """the nine halo-halo terms, piece by piece (biased/P00.py ... P22.py), against the UNMODIFIED reference classes, and
+    their sums against the moments the assembly kernel builds itself (k_gal_moments)"""
+    from pyrsd_b200.dm import BiasedSpectrum, HaloSpectrum
+    ref = np.load(REF)
+    if 'halo_term_names' not in ref.files:
+        pytest.skip("dm_ref.npz predates the halo terms")
+    kw = dict(params=cosmo, z=0.55, interpolate=False, max_mu=6, engine=engine, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity)
+    h = BiasedSpectrum(**kw) if tag == 'biased' else HaloSpectrum(**kw)
+    h.update(sigma8_z=0.61, f=0.77, **(dict(b1=2.1, b1_bar=3.2) if tag == 'biased' else dict(b1=2.4)))
+    km = ref[tag + '_modelk']
+    P0 = np.abs(ref[tag + '_moments'][0])
+    mine, worst = {}, {}
+    for name, r in zip([str(n) for n in ref['halo_term_names']], ref[tag + '_halo_terms']):
+        term, piece = name.split('.')
+        mine[name] = np.asarray(getattr(getattr(h, term), piece)(km))
+        # same rule as for the dark-matter terms above: a term is measured against itself or, where it is small against
+        # the halo spectrum (k^2-suppressed velocity terms at low k, I + 2 k^2 J P_L combinations that cancel), 10 % of P_hh
+        worst[name] = float(np.max(np.abs(mine[name] - r)/np.maximum(np.abs(r), 0.1*P0)))
+    record_parity('biased', tag + '/halo terms', worst)
+    assert max(worst.values()) < TOL, worst
+    sc = ref[tag + '_scalars']
+    assert np.allclose([h.bs, h.bs_bar, h.sigmav_halo, h.sigmav_halo_bar], sc, rtol=1e-6, atol=1e-12)
+    # the terms add up to what the kernel assembles (power_biased.py:476-525)
+    sums = [mine['P00_ss.mu0'],
+            mine['P01_ss.mu2'] + mine['P11_ss.mu2'] + mine['P02_ss.mu2'],
+            mine['P11_ss.mu4'] + mine['P02_ss.mu4'] + mine['P12_ss.mu4'] + mine['P03_ss.mu4'] + mine['P22_ss.mu4']
+            + mine['P13_ss.mu4'] + mine['P04_ss.mu4'],
+            mine['P12_ss.mu6'] + 1./8*h.f**4*h.I32(km)]
+    kernel = [h.P_mu0(km), h.P_mu2(km), h.P_mu4(km), h.P_mu6(km)]
+    for i in range(4):
+        assert np.max(np.abs(sums[i] - kernel[i])/np.maximum(np.abs(kernel[i]), 1e-3*P0)) < 1e-9, i
+    # the dark-matter accessors of a biased spectrum (a BiasedSpectrum IS a DarkMatterSpectrum in the reference)
+    assert np.all(np.isfinite(h.P02.mu2.no_velocity(km))) and np.all(np.isfinite(h.K20_a(km)))
+
+
+def test_model_surface_of_the_reference(cosmo, engine):
+    """the generic methods on the dark-matter / biased classes and the state helpers"""
+    from pyrsd_b200.dm import DarkMatterSpectrum, HaloSpectrum
+    from pyrsd_b200 import pygcl
+    m = DarkMatterSpectrum(params=cosmo, z=0.55, engine=engine, interpolate=False)
+    m.update(sigma8_z=0.61, f=0.77)
+    k = np.logspace(-2, np.log10(0.4), 12)
+    mus = np.linspace(0., 1., 41)
+    P = m.power(k, mus)
+    from scipy.special import legendre
+    for ell, fn in ((0, m.monopole), (2, m.quadrupole), (4, m.hexadecapole)):
+        expect = pygcl.SimpsIntegrate(mus, (2*ell + 1.)*legendre(ell)(mus)[None, :]*P)
+        assert np.allclose(fn(k), expect, rtol=1e-12, atol=1e-9)
+    p0, p2 = m.poles(k, [0, 2])
+    assert np.allclose(p0, m.monopole(k), rtol=1e-12)
+    # derivative against a wider central difference
+    dk = m.derivative_k(k, 0.5)
+    h = 1e-3*k
+    assert np.allclose(dk, (m.power(k + h, 0.5) - m.power(k - h, 0.5))/(2*h), rtol=2e-4)
+    assert m.config['max_mu'] == m.max_mu and m.params is cosmo and len(m.k_interp) == 250
+    with m.use_spt():
+        assert not m.use_P00_model and not m.use_Pdv_model
+        spt = m.P00.mu0(k)
+    assert m.use_P00_model and np.max(np.abs(spt/m.P00.mu0(k) - 1)) > 1e-4
+    with m.preserve(f=0.5):
+        assert m.f == 0.5
+    assert m.f == 0.77
+    # the Jennings fits are the Pdv / Pvv blocks when the models are on (power_dm.py:676-718)
+    assert np.allclose(m.Pdv_jennings(k), m.Pdv(k), rtol=1e-13) and np.allclose(m.Pvv_jennings(k), m.Pvv(k), rtol=1e-13)
+    assert np.allclose(m.hzpt.P00(k), m.P00.mu0(k), rtol=1e-13)
+    assert np.allclose(m.normed_power_lin_nw(k)/m.normed_power_lin(k), 1., atol=0.12)      # BAO wiggles are ~ 5 %
+    hs = HaloSpectrum(params=cosmo, z=0.55, engine=engine, interpolate=False, b2_00=b2_00, b2_01=b2_01, stochasticity=stochasticity)
+    hs.update(b1=2.4, sigma8_z=0.61, f=0.77)
+    assert np.allclose(hs.monopole(k), pygcl.SimpsIntegrate(mus, hs.power(k, mus)), rtol=1e-12)
+    with hs.cache_override(b2_00=0.3):
+        assert hs.b2_00(5.) == 0.3
+    assert hs.b2_00(2.4) == b2_00(2.4)

@@ -337,3 +337,59 @@ def test_simulation_pdv_identity_and_default_fits(cosmo, engine):
     g.update(correct_mu2=False, correct_mu4=False, vel_disp_from_sims=False, use_mean_bias=False)
     P0 = g.power(kk, mu)
     assert np.max(np.abs(P1/P0 - 1)) > 1e-3          # the options do act
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/galaxy_ref.npz not generated")
+@pytest.mark.parametrize('case', ['z055_ap', 'z055_so_gauss'])
+def test_sub_spectra_vs_reference_python(cosmo, engine, case):
+    """Pgal_cAcA ... Pgal_sBsB and the three groups (power_gal.py:292-399) against the UNMODIFIED reference methods; the
+    ten recombine to ``power`` with the galaxy fractions"""
+    ref = np.load(REF)
+    key = case + '_pi'
+    if key + '_sub' not in ref.files:
+        pytest.skip("fixture has no sub-spectra for %s" % key)
+    z, kw, _ = CASES[case]
+    model = make_model(cosmo, engine, z, **kw)
+    pars = dict(zip([str(n) for n in ref['par_names']], ref[key + '_pars']))
+    pars.pop('D')
+    model.update(**pars)
+    ks, mus = ref[key + '_sub_k'], ref[key + '_sub_mu']
+    K, M = [a.ravel() for a in np.meshgrid(ks, mus, indexing='ij')]
+    worst = {}
+    got = {}
+    for name, r in zip([str(n) for n in ref['sub_names']], ref[key + '_sub']):
+        got[name] = np.asarray(getattr(model, 'Pgal_' + name)(K, M)).reshape(len(ks), len(mus))
+        worst[name] = float(np.max(np.abs(got[name]/r - 1)))
+    _record('sub_spectra/' + key, worst)
+    assert max(worst.values()) < TOL, worst
+    if not model.use_so_correction:
+        fs, fcB, fsB = model.fs, model.fcB, model.fsB
+        cc = (1 - fcB)**2*got['cAcA'] + 2*fcB*(1 - fcB)*got['cAcB'] + fcB**2*got['cBcB']
+        cs = (1 - fcB)*(1 - fsB)*got['cAsA'] + (1 - fcB)*fsB*got['cAsB'] + fcB*(1 - fsB)*got['cBsA'] + fcB*fsB*got['cBsB']
+        ss = (1 - fsB)**2*got['sAsA'] + 2*fsB*(1 - fsB)*got['sAsB'] + fsB**2*got['sBsB']
+        total = (1 - fs)**2*cc + 2*fs*(1 - fs)*cs + fs**2*ss
+        assert np.max(np.abs(total/model.power(K, M).reshape(total.shape) - 1)) < 1e-12
+        assert np.max(np.abs(cc/got['cc'] - 1)) < 1e-12 and np.max(np.abs(ss/got['ss'] - 1)) < 1e-12
+    # FOG kernels (gal/fog_kernels.py:40-84)
+    x = 0.2*0.5*4.0
+    expect = {'modified_lorentzian': 1/(1 + 0.5*x*x)**2, 'lorentzian': 1/(1 + 0.5*x*x), 'gaussian': np.exp(-0.5*x*x)}
+    assert abs(model.FOG(0.2, 0.5, 4.0) - expect[model.fog_model]) < 1e-15
+    # the halo-pair accessors of the model itself (a GalaxySpectrum IS a BiasedSpectrum in the reference): the moments of the
+    # pair (b1, b1_bar) against the fixture's, the terms behind them, and pickling with the table caches they leave behind
+    import pickle
+    model.b1, model.b1_bar = model.b1_cB, model.b1_sA
+    km = model.k
+    mom = np.array([model.P_mu0(km), model.P_mu2(km), model.P_mu4(km), model.P_mu6(km)])
+    rm = ref[key + '_moments_cBsA']
+    # (a moment is a sum of terms of either sign -- P[mu^2] crosses zero near k = 0.3 -- and enters P(k, mu) as
+    # mu^(2i) P[mu^(2i)]: where it is small it is measured against 10 % of P[mu^0], the rule of tests/test_gpu_dm.py)
+    e_rows = np.max(np.abs(mom - rm)/np.maximum(np.abs(rm), 0.1*np.abs(rm[0])), axis=1)
+    _record('pair_moments/' + key, [float(e) for e in e_rows])
+    assert e_rows.max() < TOL, e_rows
+    assert np.allclose(model.P01_ss.mu2(km) + model.P11_ss.mu2(km) + model.P02_ss.mu2(km), mom[1], rtol=1e-9, atol=1e-9*np.abs(mom[0]).max())
+    assert model.bs == (-2./7*(model.b1 - 1.) if model.use_tidal_bias else 0.) and model.sigmav_halo == model.sigma_v
+    clone = pickle.loads(pickle.dumps(model))
+    assert clone.b1 == model.b1 and clone._result is None and '_dm_tabs' not in clone.__dict__
+    model.redshift_params = ['f']
+    model.z = 0.55
+    assert model.f == cosmo.f_z(0.55)
