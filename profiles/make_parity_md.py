@@ -57,7 +57,21 @@ if d.get('dark_matter'):
 if d.get('biased'):
     out += ['', '| BiasedSpectrum / HaloSpectrum moments | ' + ' | '.join('P_mu%d' % (2*i) for i in range(4)) + ' |', '|---|' + '---|'*4]
     for k, v in sorted(d['biased'].items()):
-        out.append('| %s | ' % k + ' | '.join('%.1e' % v['P_mu%d' % (2*i)] for i in range(4)) + ' |')
+        if 'P_mu0' in v:
+            out.append('| %s | ' % k + ' | '.join('%.1e' % v['P_mu%d' % (2*i)] for i in range(4)) + ' |')
+    out += ['', 'Halo-halo terms P00_ss ... P04_ss piece by piece (16 pieces) vs the reference classes, |mine - ref| / max(|ref|, 0.1 P_hh[mu^0]):', '',
+            '| case | worst piece | max error |', '|---|---|---|']
+    for k, v in sorted(d['biased'].items()):
+        if 'P_mu0' not in v:
+            w = max(v.items(), key=lambda kv: kv[1])
+            out.append('| %s | %s | %.1e |' % (k, w[0], w[1]))
+subs = {k: v for k, v in d.get('galaxy', {}).items() if k.startswith('sub_spectra/')}
+if subs:
+    out += ['', 'Galaxy sub-spectra Pgal_cAcA ... Pgal_sBsB, Pgal_cc / cs / ss vs the reference methods (13 spectra, 20 k x 5 mu):', '',
+            '| case | worst spectrum | max rel. error |', '|---|---|---|']
+    for k, v in sorted(subs.items()):
+        w = max(v.items(), key=lambda kv: kv[1])
+        out.append('| %s | %s | %.1e |' % (k[12:], w[0], w[1]))
 if d.get('correlation'):
     out += ['', '## ExtrapolatedPowerSpectrum / SmoothedXiMultipoles vs the reference classes (`tests/test_gpu_xi.py`)', '',
             '| quantity | max error |', '|---|---|']
