@@ -170,27 +170,71 @@ def run_gpu(args):
     d_recv = torch.empty((world*B, NK_OUT), dtype=torch.float64, device=dev)
     flush = torch.empty(64*1024*1024, dtype=torch.float32, device=dev)      # L2 flush buffer (256 MB > 126 MB)
     torch.cuda.synchronize()
+    # the exchange over peer memory (NVLink / NVSwitch, CUDA IPC between the ranks); --exchange nccl or a box without peer
+    # access between its GPUs: the all-gather of torch.distributed
+    peer_x, exchange_kind = None, "none (one rank)"
+    if world > 1:
+        exchange_kind = "nccl all-gather (torch.distributed)"
+        if args.exchange == 'peer':
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                peer_x = parallel.PeerExchange(ctx, B*NK_OUT)
+            except Exception as e:                                    # noqa: BLE001 -- reported, every rank falls back together
+                ok[0] = 0
+                if rank == 0:
+                    print("peer exchange unavailable (%s): NCCL all-gather instead" % e, file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer_x = None
+            else:
+                exchange_kind = "grid-reduction kernel -> own slot of the receive buffer, push to every peer's slot over NVLink peer memory + flag exchange (csrc/exchange.cu)"
 
     sp = eng.spectra(data['k'], data['T'], data['pars'][:, 0], data['pars'][:, 1], data['pars'][:, 2], data['pars'][:, 3],
                      data['pars'][:, 4], data['pars'][:, 5])
     res = rsd._new_result()
 
-    def step_device():
+    def step_device(exchange=True, marks=None):
         """inputs resident in HBM, outputs left in HBM"""
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                marks.append(e)
+        mark()
         N.check(L.prsd_spectra_reload_device(sp.ptr, d_k.data_ptr(), d_T.data_ptr(), d_pars.data_ptr()))
         eng.run(sp, result=res, sync=False)
         N.check(gp_dev(gal.ptr, sp.ptr, res.ptr, B, None, h_wpar.data_ptr(), h_stoch.data_ptr(), npts,
                     d_kk.data_ptr(), d_mm.data_ptr(), d_out.data_ptr()))
-        if world > 1:
+        mark()
+        if world > 1 and exchange:
             # the ensemble step's exchange, enqueued behind the kernels on the library's own stream
-            N.check(L.prsd_gridop_apply(gop, B, d_out.data_ptr(), d_send.data_ptr(), 1))
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(d_recv, d_send)
+            if peer_x is not None:
+                # the grid-reduction kernel writes into this rank's slot of its receive buffer, a push kernel stores the slot
+                # into every peer's buffer over NVLink peer memory, a one-CTA flag exchange follows (csrc/exchange.cu)
+                peer_x.apply(gop, B, C.c_void_p(d_out.data_ptr()))
+            else:
+                N.check(L.prsd_gridop_apply(gop, B, d_out.data_ptr(), d_send.data_ptr(), 1))
+                mark()
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(d_recv, d_send)
+        mark()
 
     first0 = time.perf_counter()
     step_device()
     torch.cuda.synchronize()
     first_call_s = time.perf_counter() - first0
+    exchange_check = None
+    if peer_x is not None:
+        # untimed: what arrived over peer memory against the library all-gather of the same step
+        got = peer_x.received(check=True).reshape(world*B, NK_OUT).clone()
+        N.check(L.prsd_gridop_apply(gop, B, d_out.data_ptr(), d_send.data_ptr(), 1))
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(d_recv, d_send)
+        torch.cuda.synchronize()
+        same = torch.tensor([1 if torch.equal(got, d_recv) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert int(same.item()) == 1, "peer exchange differs from the NCCL all-gather"
+        exchange_check = "bit-identical to the NCCL all-gather of the same step on every rank"
 
     # ---- end to end through the public streaming API: every step copies its inputs host -> pinned -> device and its
     #      P(k, mu) device -> pinned host; the copy of step i runs under the PT kernels of step i + 1
@@ -242,6 +286,11 @@ def run_gpu(args):
             if flush_l2:
                 flush.zero_()                   # L2 flush between timed iterations (outside the event pair)
             torch.cuda.synchronize()
+            if world > 1:
+                # every timed step starts on all ranks together (the step ends in a collective: without this the event pair
+                # of a rank would also hold the other ranks' host-side drift through the L2 flush above)
+                dist.barrier()
+                torch.cuda.synchronize()
             e0.record(stream)
             fn()
             e1.record(stream)
@@ -249,6 +298,7 @@ def run_gpu(args):
         sampler.armed = False
         barrier()
         ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        timed_steps.last = [round(e0.elapsed_time(e1), 4) for e0, e1 in evs]
         launches = ctx.launches() - l0
         prof = None
         if profile:
@@ -282,7 +332,45 @@ def run_gpu(args):
 
     if rank == 0:
         sampler.start()
-    ms_dev, launches, prof = timed_steps(step_device, args.steps, args.warmup, profile=True)
+    # the timed steps run without instrumentation; a second pass of the same steps carries the library's per-kernel-family
+    # CUDA events (ProfScope: an event pair around every family on its stream, ~0.1 ms per step of overhead)
+    ms_dev, launches, _ = timed_steps(step_device, args.steps, args.warmup)
+    steps_rank0 = list(timed_steps.last)
+    ms_instr, _, prof = timed_steps(step_device, args.steps, 1, profile=True)
+    multi = None
+    if world > 1:
+        # where the N-GPU step differs from the 1-GPU one: the same steps without the exchange, per rank (GPUs of one box
+        # differ by a few per cent under load; the step with the exchange runs at the pace of the slowest)
+        ms_nox, _, _ = timed_steps(lambda: step_device(False), args.steps, 1)
+        own = torch.tensor([0.0], dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        per = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0.record(stream); step_device(False); e1.record(stream)
+            torch.cuda.synchronize()
+            per.append(e0.elapsed_time(e1))
+        own[0] = float(np.mean(per))
+        # where inside a step with the exchange the time goes (rank 0): kernels | [reduction |] exchange
+        split = []
+        for _ in range(4):
+            flush.zero_()
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            marks = []
+            step_device(True, marks)
+            torch.cuda.synchronize()
+            split.append([round(marks[i].elapsed_time(marks[i + 1]), 4) for i in range(len(marks) - 1)])
+        allr = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, own)
+        multi = {"ms_per_step_without_exchange_max_over_ranks": ms_nox/args.steps,
+                 "ms_per_step_without_exchange_per_rank": [round(float(x), 4) for x in allr.cpu().numpy()],
+                 "exchange": "%s; %d x %d doubles per rank and step" % (exchange_kind, B, NK_OUT),
+                 "exchange_check": exchange_check, "ms_of_every_timed_step_rank0": steps_rank0,
+                 "ms_split_of_4_steps_rank0": split}
+        if peer_x is not None:
+            peer_x.received(check=True)              # raises if any wait for a peer timed out during the timed steps
     e2e_steps = max(8, 2*args.steps)        # the final drain (one un-hidden copy) is amortised over the run
     ms_e2e, last = timed_block(lambda: run_e2e_pipelined(e2e_steps), lambda: run_e2e_pipelined(3))
     ms_blk, _, _ = timed_steps(step_e2e_blocking, max(2, args.steps//2), 1, flush_l2=True)
@@ -346,11 +434,11 @@ def run_gpu(args):
         kd['launches_per_step'] = n//args.steps
         kd['flops'] = float(kd['flops'])
         kd['achieved'] = kd['flops']/(kd['ms']*1e-3)/1e12 if kd['ms'] > 0 else None
-        kd['share'] = pms[kd['fam']]/ms_dev
+        kd['share'] = pms[kd['fam']]/ms_instr
     top = max(kern, key=lambda k: kern[k]['share'])
     peak = peak_dmma if 'DMMA' in kern[top]['pipe'] else peak_dfma
     fam = ['ik_dmma', 'linear_ops', 'zeldovich', 'galaxy', 'spline_builds', 'fftlog', 'imn_oneloop_nodal', 'oneloop_tables_nodal']
-    shares = {fam[i]: round(pms[i]/ms_dev, 4) for i in range(8)}
+    shares = {fam[i]: round(pms[i]/ms_instr, 4) for i in range(8)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -366,8 +454,8 @@ def run_gpu(args):
         "config": dict(workload_config(B), quadrature_nodes_per_cosmology=info['nodes'],
                        l2="value: L2 flushed between timed iterations (256 MB write); e2e: consecutive pipelined steps, each "
                           "streams 0.36 GB of quadrature operators + 82 MB of output (> 126 MB L2)",
-                       parallelism="walkers sharded over %d rank(s), no data-path collective; NCCL all-gather of the mu-averaged "
-                                   "P(k) (library epilogue -> persistent send buffer) inside the timed step" % world,
+                       parallelism="walkers sharded over %d rank(s), no data-path collective; the mu-averaged P(k) of every "
+                                   "walker reaches every rank inside the timed step (%s)" % (world, exchange_kind),
                        numa_node_of_rank0=numa),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e/e2e_steps, "steps": e2e_steps,
@@ -384,6 +472,7 @@ def run_gpu(args):
                              "how": "prsd_spectra_create / prsd_plan_run / prsd_galaxy_power with pageable host buffers, "
                                     "one step at a time (host waits for every result)"}},
         "gpu_launches": int(launches),
+        "multi_gpu": multi,
         "roofline": {"bound": "fp64 (DFMA pipe; ncu: the binding unit is the LSU / shared-memory data pipe, see ncu_pct_of_peak)",
                      "achieved": kern[top]['achieved'], "peak": peak, "unit": "TFLOP/s",
                      "frac": (kern[top]['achieved']/peak) if (kern[top]['achieved'] and peak) else None,
@@ -403,7 +492,10 @@ def run_gpu(args):
                      "other_kernels": {k: {"achieved": v['achieved'], "frac": (v['achieved']/(peak_dmma if 'DMMA' in v['pipe'] else peak_dfma))
                                            if v['achieved'] else None, "ms_per_launch": v['ms'], "traffic": traffic.get(k)}
                                        for k, v in kern.items() if k != top},
-                     "kernel_share_of_step": shares},
+                     "kernel_share_of_step": shares,
+                     "instrumented_ms_per_step": ms_instr/args.steps,
+                     "instrumentation": "kernel times and shares come from a second pass of the same steps with the library's "
+                                        "per-family CUDA-event pairs switched on; the timed steps behind `value` run without them"},
         "clocks": sampler.summary(),
         "cold_start": {"plan_build_s": info['build_seconds'], "engine_and_galaxy_ctor_wall_s": plan_wall_s,
                        "first_step_s": first_call_s, "process_start_to_first_result_s": first0 + first_call_s - t_cold0},
@@ -713,6 +805,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='cosmologies per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: how the per-walker results reach every rank (peer-memory stores, or torch.distributed all-gather)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip the other BASELINE configurations')
     args = ap.parse_args()

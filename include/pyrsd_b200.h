@@ -251,6 +251,29 @@ int prsd_gridop_destroy(prsd_gridop* op);
 /* power [nw][nk][nmu] -> out [nw][nbin][nk]; device_ptrs != 0: both are DEVICE pointers and the call does not
  * synchronise */
 int prsd_gridop_apply(prsd_gridop* op, int nw, const double* power, double* out, int device_ptrs);
+
+/* ---- the per-step exchange of an ensemble sharded over the GPUs of one box ------------------------------------------
+ * The reference gathers one likelihood per walker per ensemble step through emcee's MPI pool
+ * [rsdfit/util/mpi_manager.py, rsdfit/engines/mcmc.py].  Here every rank (one process per GPU) owns a receive buffer
+ * [2][world][n_per_rank] doubles and a flag word per peer; the ranks map each other's buffers (CUDA IPC: exchange the 128
+ * handle bytes by any means, e.g. torch.distributed.all_gather).  The producing kernel of a step writes this rank's
+ * n_per_rank results straight into its own slot of its receive buffer; a push kernel stores the slot into the same slot
+ * of EVERY peer's buffer over NVLink / NVSwitch peer memory; a one-CTA kernel then raises this rank's flag at every peer
+ * and waits (bounded: 2 s, then the status word is set) for theirs.  No staging copy, no library collective; consecutive
+ * steps alternate between the two halves of the buffer. */
+typedef struct prsd_exchange prsd_exchange;
+int prsd_exchange_create(prsd_ctx* ctx, int world, int rank, long long n_per_rank, prsd_exchange** out);
+int prsd_exchange_destroy(prsd_exchange* x);
+int prsd_exchange_handles(prsd_exchange* x, unsigned char* out128);
+/* all_handles [world][128] in rank order (this rank's own entry is ignored); call on every rank, then synchronise the
+ * ranks once before the first step */
+int prsd_exchange_open(prsd_exchange* x, const unsigned char* all_handles);
+/* gridded transfer of nw walkers (prsd_gridop_apply with device pointers) whose [nw][nbin][nk] results are this rank's
+ * contribution to the step: enqueued on the context's stream, returns at once */
+int prsd_gridop_apply_exchange(prsd_gridop* op, int nw, const double* power, prsd_exchange* x);
+/* device pointer to the [world][n_per_rank] results of the latest step (valid behind the step on the context's stream);
+ * status (may be NULL; synchronises): 0, or 1 if a wait for a peer timed out */
+int prsd_exchange_received(prsd_exchange* x, void** dev_ptr, int* status);
 /* WindowFunctionTransfer  [rsd/transfers/window.py:9-132] on the vendored mcfit transforms
  * [extern/mcfit/mcfit.py:86-176, cosmology.py:15-35, kernels.py:14-17].  k [nk]: the log-spaced grid of the
  * multipoles INCLUDING the zero-padded extension (window.py:84-93); ells [nell] even; q the mcfit tilt (1.5);

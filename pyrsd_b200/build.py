@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libpyrsd_b200.so')
 
 CU_SOURCES = ['context.cu', 'bilinear.cu', 'nodal.cu', 'linear.cu', 'spectra.cu', 'plan.cu', 'zeldovich.cu',
-              'fftlog.cu', 'xilm.cu', 'discrete.cu', 'transfer.cu', 'galaxy.cu', 'biasrel.cu', 'gp.cu', 'microbench.cu', 'capi.cu']
+              'fftlog.cu', 'xilm.cu', 'discrete.cu', 'transfer.cu', 'exchange.cu', 'galaxy.cu', 'biasrel.cu', 'gp.cu', 'microbench.cu', 'capi.cu']
 CXX_SOURCES = ['quad.cpp', 'fftlog_host.cpp']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -5,6 +5,7 @@
 #include "xilm.cuh"
 #include "discrete.cuh"
 #include "transfer.cuh"
+#include "exchange.cuh"
 #include "biasrel.cuh"
 #include "gp.cuh"
 
@@ -26,6 +27,7 @@ struct prsd_galaxy {
     prsd_galaxy(Context& c, const GalaxyConfig& cfg, const double* km, int nkm, const double* ki, int nki) : g(c, cfg, km, nkm, ki, nki) {}
 };
 struct prsd_gridop { GridOp op; DevBuf<double> din, dout; prsd_gridop(Context& c, int nb, int nk, int nmu, const double* w) : op(c, nb, nk, nmu, w) {} };
+struct prsd_exchange { Exchange x; prsd_exchange(Context& c, int world, int rank, size_t n) : x(c, world, rank, n) {} };
 struct prsd_window {
     WindowOp op;
     DevBuf<double> din, dout;
@@ -90,6 +92,7 @@ static const Context* dev_of(const prsd_galaxy* h) { return h ? h->g.ctx : nullp
 static const Context* dev_of(const prsd_gridop* h) { return h ? h->op.ctx : nullptr; }
 static const Context* dev_of(const prsd_gp* h) { return h ? h->m.ctx : nullptr; }
 static const Context* dev_of(const prsd_window* h) { return h ? h->op.ctx : nullptr; }
+static const Context* dev_of(const prsd_exchange* h) { return h ? h->x.ctx : nullptr; }
 
 static QuadConfig cfg_from(const double* c)
 {
@@ -916,6 +919,50 @@ int prsd_gridop_apply(prsd_gridop* g, int nw, const double* power, double* out, 
         op.apply(nw, g->din.p, g->dout.p);
         g->dout.download(out, nout, c.stream);
         c.sync();
+    });
+}
+
+int prsd_exchange_create(prsd_ctx* ctx, int world, int rank, long long n_per_rank, prsd_exchange** out)
+{
+    return guarded(dev_of(ctx), [&] {
+        PRSD_REQUIRE(ctx && out, "null argument");
+        PRSD_REQUIRE(n_per_rank > 0, "prsd_exchange_create: empty contribution");
+        *out = new prsd_exchange(ctx->c, world, rank, (size_t)n_per_rank);
+    });
+}
+
+int prsd_exchange_destroy(prsd_exchange* x) { return guarded(dev_of(x), [&] { delete x; }); }
+
+int prsd_exchange_handles(prsd_exchange* x, unsigned char* out128)
+{
+    return guarded(dev_of(x), [&] { PRSD_REQUIRE(x && out128, "null argument"); x->x.handles(out128); });
+}
+
+int prsd_exchange_open(prsd_exchange* x, const unsigned char* all_handles)
+{
+    return guarded(dev_of(x), [&] { PRSD_REQUIRE(x && all_handles, "null argument"); x->x.open(all_handles); });
+}
+
+int prsd_gridop_apply_exchange(prsd_gridop* g, int nw, const double* power, prsd_exchange* x)
+{
+    return guarded(dev_of(g), [&] {
+        PRSD_REQUIRE(g && power && x, "null argument");
+        PRSD_REQUIRE(g->op.ctx == x->x.ctx, "prsd_gridop_apply_exchange: the operator and the exchange belong to different contexts");
+        PRSD_REQUIRE((size_t)nw*g->op.nbin*g->op.nk == x->x.n_per_rank,
+                     "prsd_gridop_apply_exchange: %d walkers x %d bins x %d k do not fill the exchange's %zu doubles per rank",
+                     nw, g->op.nbin, g->op.nk, x->x.n_per_rank);
+        double* slot = x->x.begin_step();           // this rank's slot of its own receive buffer
+        g->op.apply(nw, power, slot);
+        x->x.finish_step();                         // push to the peers' slots + flag exchange
+    });
+}
+
+int prsd_exchange_received(prsd_exchange* x, void** dev_ptr, int* status)
+{
+    return guarded(dev_of(x), [&] {
+        PRSD_REQUIRE(x && dev_ptr, "null argument");
+        *dev_ptr = (void*)x->x.received();
+        if (status) *status = x->x.status();
     });
 }
 

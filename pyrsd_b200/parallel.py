@@ -56,3 +56,78 @@ def max_over_ranks(value, device=None, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class _DeviceArray(object):
+    """a device pointer as a ``__cuda_array_interface__`` holder (for ``torch.as_tensor``)"""
+    def __init__(self, ptr, shape, owner):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+        self._owner = owner
+
+
+class PeerExchange(object):
+    """The per-step exchange over NVLink / NVSwitch peer memory (``prsd_exchange_*``, csrc/exchange.cu): every rank's
+    gridded-transfer kernel writes its per-walker results into its slot of its own receive buffer, a push kernel stores the
+    slot into every peer's buffer, a flag exchange follows; no library collective on the data path.  ``torch.distributed`` carries the 128 handle bytes once at set-up.
+
+    ``n_per_rank`` doubles per rank and step (walkers x bins x k of the gridded transfer)."""
+
+    def __init__(self, context, n_per_rank, group=None):
+        import ctypes as C
+        import numpy as np
+        from . import _native as N
+        from . import transfers as _T
+        self._C, self._N, self._L = C, N, _T._L()
+        L = self._L
+        vp = C.c_void_p
+        L.prsd_exchange_create.argtypes = [vp, C.c_int, C.c_int, C.c_longlong, C.POINTER(vp)]
+        L.prsd_exchange_destroy.argtypes = [vp]
+        L.prsd_exchange_handles.argtypes = [vp, C.c_void_p]
+        L.prsd_exchange_open.argtypes = [vp, C.c_void_p]
+        L.prsd_gridop_apply_exchange.argtypes = [vp, C.c_int, vp, vp]
+        L.prsd_exchange_received.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
+        for f in ('prsd_exchange_create', 'prsd_exchange_destroy', 'prsd_exchange_handles', 'prsd_exchange_open',
+                  'prsd_gridop_apply_exchange', 'prsd_exchange_received'):
+            getattr(L, f).restype = C.c_int
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.n_per_rank = int(n_per_rank)
+        self._ctx = context
+        self.ptr = vp()
+        N.check(L.prsd_exchange_create(context.ptr, self.world, self.rank, self.n_per_rank, C.byref(self.ptr)))
+        if self.world > 1:
+            mine = np.zeros(128, dtype=np.uint8)
+            N.check(L.prsd_exchange_handles(self.ptr, mine.ctypes.data))
+            dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+            send = torch.from_numpy(mine).to(dev)
+            recv = torch.empty(self.world*128, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(recv, send, group=group)
+            allh = np.ascontiguousarray(recv.cpu().numpy())
+            N.check(L.prsd_exchange_open(self.ptr, allh.ctypes.data))
+            dist.barrier(group=group)              # every rank has mapped every buffer before the first step
+
+    def apply(self, gridop_ptr, nw, d_power_ptr):
+        """enqueue the gridded transfer of ``nw`` walkers + the exchange on the context's stream"""
+        self._N.check(self._L.prsd_gridop_apply_exchange(gridop_ptr, int(nw), d_power_ptr, self.ptr))
+
+    def received(self, check=False):
+        """torch tensor [world][n_per_rank] over the receive buffer of the latest step (valid behind the step on the
+        context's stream); ``check``: synchronise and raise if a wait for a peer timed out"""
+        C = self._C
+        p, st = C.c_void_p(), C.c_int(0)
+        self._N.check(self._L.prsd_exchange_received(self.ptr, C.byref(p), C.byref(st) if check else None))
+        if check and st.value != 0:
+            raise RuntimeError("PeerExchange: a rank did not deliver its step within 2 s")
+        return torch.as_tensor(_DeviceArray(p.value, (self.world, self.n_per_rank), self), device=torch.device('cuda', self._ctx.device))
+
+    def close(self):
+        if self.ptr:
+            self._L.prsd_exchange_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -223,3 +223,35 @@ def test_convolve_multipoles_vs_reference():
         convolve_multipoles(REF['c_k'], REF['c_Pell'], [0, 2], conv)
     with pytest.raises(ValueError):
         convolve_multipoles(REF['c_k'], REF['c_Pell'], [0, 2, 3], conv)
+
+
+def test_peer_exchange_single_rank_matches_gridop():
+    """the exchange path of the multi-GPU step (csrc/exchange.cu) with one rank: the gridded transfer written through the
+    peer table + flag kernel equals ``prsd_gridop_apply``, step after step, alternating buffer halves"""
+    import ctypes as C
+    import torch
+    from pyrsd_b200 import _native as N, transfers as T, parallel
+    L = T._L()
+    ctx = N.default_context()
+    nw, nk, nmu = 5, 37, 12
+    rng = np.random.default_rng(5)
+    w = rng.random((2, nk, nmu))
+    gop = C.c_void_p()
+    N.check(L.prsd_gridop_create(ctx.ptr, 2, nk, nmu, w, C.byref(gop)))
+    ex = parallel.PeerExchange(ctx, nw*2*nk)
+    dev = torch.device('cuda', ctx.device)
+    for step in range(3):
+        P = rng.random((nw, nk, nmu))
+        d_P = torch.from_numpy(P).to(dev)
+        d_ref = torch.empty((nw, 2, nk), dtype=torch.float64, device=dev)
+        N.check(L.prsd_gridop_apply(gop, nw, C.c_void_p(d_P.data_ptr()), C.c_void_p(d_ref.data_ptr()), 1))
+        ex.apply(gop, nw, C.c_void_p(d_P.data_ptr()))
+        got = ex.received(check=True)
+        ctx.sync()
+        assert got.shape == (1, nw*2*nk)
+        assert torch.equal(got.reshape(nw, 2, nk), d_ref)
+        assert np.allclose(d_ref.cpu().numpy(), np.einsum('wkm,bkm->wbk', P, w), rtol=1e-13)
+    with pytest.raises(N.NativeError):
+        ex.apply(gop, nw + 1, C.c_void_p(d_P.data_ptr()))
+    ex.close()
+    N.check(L.prsd_gridop_destroy(gop))
