@@ -176,17 +176,13 @@ def run_gpu(args):
     if world > 1:
         exchange_kind = "nccl all-gather (torch.distributed)"
         if args.exchange == 'peer':
-            ok = torch.ones(1, dtype=torch.int32, device=dev)
             try:
-                peer_x = parallel.PeerExchange(ctx, B*NK_OUT)
-            except Exception as e:                                    # noqa: BLE001 -- reported, every rank falls back together
-                ok[0] = 0
+                peer_x = parallel.PeerExchange(ctx, B*NK_OUT)      # raises on every rank or on none
+            except Exception as e:                                    # noqa: BLE001 -- reported; NCCL all-gather instead
+                peer_x = None
                 if rank == 0:
                     print("peer exchange unavailable (%s): NCCL all-gather instead" % e, file=sys.stderr)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                peer_x = None
-            else:
+            if peer_x is not None:
                 exchange_kind = "grid-reduction kernel -> own slot of the receive buffer, push to every peer's slot over NVLink peer memory + flag exchange (csrc/exchange.cu)"
 
     sp = eng.spectra(data['k'], data['T'], data['pars'][:, 0], data['pars'][:, 1], data['pars'][:, 2], data['pars'][:, 3],

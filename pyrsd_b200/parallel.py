@@ -95,16 +95,38 @@ class PeerExchange(object):
         self.n_per_rank = int(n_per_rank)
         self._ctx = context
         self.ptr = vp()
-        N.check(L.prsd_exchange_create(context.ptr, self.world, self.rank, self.n_per_rank, C.byref(self.ptr)))
+        # every phase that can fail on one rank alone is followed by an agreement, so that the ranks never sit in different
+        # collectives: either every rank owns a mapped exchange after this constructor or every rank raises
+        tdev = torch.device('cpu')
+        if on and dist.get_backend(group) == 'nccl':
+            tdev = torch.device('cuda', torch.cuda.current_device())
+
+        def agree(err, what):
+            flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=tdev)
+            if on:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()):
+                self.close()
+                raise RuntimeError("PeerExchange: %s failed on %s" % (what, "this rank: %s" % err if err is not None else "another rank"))
+
+        err = None
+        try:
+            N.check(L.prsd_exchange_create(context.ptr, self.world, self.rank, self.n_per_rank, C.byref(self.ptr)))
+        except Exception as e:                                             # noqa: BLE001
+            err = e
+        agree(err, "allocating the receive buffer")
         if self.world > 1:
             mine = np.zeros(128, dtype=np.uint8)
             N.check(L.prsd_exchange_handles(self.ptr, mine.ctypes.data))
-            dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
-            send = torch.from_numpy(mine).to(dev)
-            recv = torch.empty(self.world*128, dtype=torch.uint8, device=dev)
+            send = torch.from_numpy(mine).to(tdev)
+            recv = torch.empty(self.world*128, dtype=torch.uint8, device=tdev)
             dist.all_gather_into_tensor(recv, send, group=group)
             allh = np.ascontiguousarray(recv.cpu().numpy())
-            N.check(L.prsd_exchange_open(self.ptr, allh.ctypes.data))
+            try:
+                N.check(L.prsd_exchange_open(self.ptr, allh.ctypes.data))
+            except Exception as e:                                         # noqa: BLE001
+                err = e
+            agree(err, "mapping the peers' buffers (CUDA IPC)")
             dist.barrier(group=group)              # every rank has mapped every buffer before the first step
 
     def apply(self, gridop_ptr, nw, d_power_ptr):
@@ -122,7 +144,7 @@ class PeerExchange(object):
         return torch.as_tensor(_DeviceArray(p.value, (self.world, self.n_per_rank), self), device=torch.device('cuda', self._ctx.device))
 
     def close(self):
-        if self.ptr:
+        if getattr(self, 'ptr', None):
             self._L.prsd_exchange_destroy(self.ptr)
             self.ptr = None
 

@@ -66,3 +66,35 @@ def test_single_process_passthrough():
     assert parallel.max_over_ranks(2.5) == 2.5
     with pytest.raises(ValueError):
         parallel.gather_rows(x, 5)
+
+
+class _NoContext(object):
+    ptr = None
+    device = 0
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # without a device context the allocation fails on every rank; the agreement after it must turn that into an
+        # exception on every rank -- nobody is left waiting in the handle all-gather
+        try:
+            parallel.PeerExchange(_NoContext(), 16)
+            outcome = 'created'
+        except RuntimeError as e:
+            outcome = 'raised: ' + str(e)[:40]
+        dist.barrier()
+        with open(os.path.join(out_dir, 'x%d.txt' % rank), 'w') as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_fails_on_every_rank_together(tmp_path):
+    """host logic of the NVLink peer exchange (parallel.PeerExchange): a set-up failure is agreed upon by all ranks"""
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(tmp_path / ('x%d.txt' % r)).read().startswith('raised: PeerExchange: allocating')
