@@ -183,6 +183,13 @@ class Cosmology(PickalableSWIG):
             return float(p['Omega_m'])
         return float(p['Omega_b']) + float(p['Omega_cdm']) + float(p.get('m_ncdm', 0.0))/93.14/self.h()**2
 
+    def Omega0_k(self):
+        return float(self._params.get('Omega_k', 0.0))
+
+    def Omega0_lambda(self):
+        """dark-energy density today; flat LCDM (1 - Omega_m - Omega_k) unless ``Omega_Lambda`` is among the parameters"""
+        return float(self._params.get('Omega_Lambda', 1.0 - self.Omega0_m() - self.Omega0_k()))
+
     def D_z(self, z): return 1.0 if (z == 0 and self._params.get('growth') is None) else _lookup(self._params.get('growth'), z, 'growth')
     def f_z(self, z): return _lookup(self._params.get('f'), z, 'f')
     def H_z(self, z): return 100.*self.h() if (z == 0 and self._params.get('H') is None) else _lookup(self._params.get('H'), z, 'H')

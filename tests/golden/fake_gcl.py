@@ -29,7 +29,9 @@ IntegrationMethods = _IntegrationMethods()
 
 
 class Constants(object):
-    pass
+    # Common.i:36, 52 (cgs)
+    c_light = 2.99792458e10
+    km = 1e5
 
 
 class ClassParams(dict):
@@ -78,6 +80,21 @@ class Cosmology(object):
     def Sigma8_z(self, z): return self._sigma8*self.D_z(z)
     def rs_drag(self): return self._params.get('_rs_drag', 147.48679403288168)
     def SetTransferFunction(self, tf): raise NotImplementedError("only the CLASS-table transfer function is available")
+
+    # background densities CLASS would supply (ClassEngine.i:60-72); flat LCDM unless given in params
+    def Omega0_m(self):
+        p = self._params
+        return p['Omega_b'] + p['Omega_cdm'] + p.get('m_ncdm', 0.0)/93.14/p['h']**2
+    def Omega0_k(self): return self._params.get('Omega_k', 0.0)
+    def Omega0_lambda(self): return self._params.get('Omega_Lambda', 1.0 - self.Omega0_m() - self.Omega0_k())
+
+    def __getitem__(self, key):
+        # pygcl.py:91-95
+        if hasattr(self, key):
+            f = getattr(self, key)
+            if callable(f):
+                return f()
+        raise KeyError("Sorry, cannot return parameter '%s' in dict-like fashion" % key)
 
 
 class _PS(object):
