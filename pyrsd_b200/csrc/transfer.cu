@@ -56,16 +56,20 @@ k_grid_reduce(int nw, int nk, int nmu, int nbin, int KT, const double* __restric
 
 // nmu <= 64: one WARP per (walker, k) row.  The row's nmu values are one coalesced read (two elements per lane), kept in
 // registers for every bin; the weights come from L2 (the operator is a few hundred kB); a five-step butterfly finishes
-// the dot product.  Bandwidth-bound on the P(k, mu) read -- the staged kernel above does the dot products of a 32-row tile
-// on 32 of its 128 threads and measured 1.15 TB/s on the benchmark's 256 x 1000 x 40 grid.
+// the dot product.  Measured on the benchmark's 256 x 1000 x 40 grid (82 MB read, inputs > L2): 0.035 ms = 2.3 TB/s (0.047
+// with a 64-bit index division per warp -- ncu: 68 % of the issue slots at 22 % of the DRAM bandwidth,
+// profiles/r02_ncu_build_and_reduce.json); the staged kernel above, which does the dot products of a 32-row tile on 32 of its
+// 128 threads, 0.054 ms.
 __global__ void __launch_bounds__(256)
 k_grid_reduce_rows(int nw, int nk, int nmu, int nbin, const double* __restrict__ w, const double* __restrict__ power,
                    double* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row < (long long)nw*nk) {
-        const int wlk = (int)(row/nk), k = (int)(row - (long long)wlk*nk);
+    // blockIdx.y = walker, 8 consecutive k per CTA: no index division (a 64-bit division per warp made the first version
+    // issue-bound: ncu 68 % issue slots at 22 % of the DRAM bandwidth)
+    const int wlk = blockIdx.y, k = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k < nk) {
+        const size_t row = (size_t)wlk*nk + k;
         const double* P = power + (size_t)row*nmu;
         const bool has0 = lane < nmu, has1 = lane + 32 < nmu;
         const double p0 = has0 ? P[lane] : 0.0, p1 = has1 ? P[lane + 32] : 0.0;
@@ -98,9 +102,8 @@ void GridOp::apply(int nw, const double* d_power, double* d_out)
     if (nw <= 0) return;
     ProfScope prof(*ctx, PROF_GALAXY);
     if (nmu <= 64) {
-        const long long rows = (long long)nw*nk;
-        const unsigned blocks = (unsigned)((rows + 7)/8);
-        k_grid_reduce_rows<<<blocks, 256, 0, ctx->stream>>>(nw, nk, nmu, nbin, w.p, d_power, d_out);
+        PRSD_REQUIRE(nw <= 65535, "GridOp: at most 65535 walkers per call (%d)", nw);
+        k_grid_reduce_rows<<<dim3((nk + 7)/8, nw), 256, 0, ctx->stream>>>(nw, nk, nmu, nbin, w.p, d_power, d_out);
         PRSD_CUDA(cudaGetLastError());
         ctx->launches++;
         return;
