@@ -242,6 +242,34 @@ class Cosmology(PickalableSWIG):
         self._sigma8 = float(sigma8)
         self._delta_H = None
 
+    def NormalizeTransferFunction(self, sigma8):
+        """delta_H such that sigma(R = 8) = sigma8 (Cosmology.cpp:175-184); here the stored sigma8 follows"""
+        self.SetSigma8(sigma8)
+
+    @classmethod
+    def from_power(cls, params, k, Pk, sigma8=None, context=None):
+        """a cosmology whose transfer function is read off a linear power spectrum: T = sqrt(P / k^n_s), largest value
+        1e7 (``Cosmology::FromPower``, Cosmology.cpp:82-118).  CLASS supplies sigma8 in the reference; here it is the
+        argument or ``params['sigma8']``."""
+        p = ClassParams(params)
+        if sigma8 is None:
+            if 'sigma8' not in p:
+                raise ValueError("Cosmology.from_power: `sigma8` is needed (CLASS is not run by this library)")
+            sigma8 = p['sigma8']
+        k, Pk = np.asarray(k, dtype=float), np.asarray(Pk, dtype=float)
+        T = np.sqrt(Pk/k**float(p.get('n_s', 0.96)))
+        return cls(p, transfers.CLASS, sigma8, k, T/T.max()*1e7, context=context)
+
+    @classmethod
+    def from_file(cls, params, k, Tk, sigma8=None, context=None):
+        """``Cosmology(param_file, k, Tk)`` of pygcl.py:86-88 with the parameters as a mapping"""
+        p = ClassParams(params)
+        if sigma8 is None:
+            if 'sigma8' not in p:
+                raise ValueError("Cosmology.from_file: `sigma8` is needed (CLASS is not run by this library)")
+            sigma8 = p['sigma8']
+        return cls(p, transfers.CLASS, sigma8, k, Tk, context=context)
+
     def EvaluateTransfer(self, k):
         ka, scalar = _scalar_or_array(k)
         sp = self._make_spectra(1.0)
@@ -334,6 +362,18 @@ class PowerSpectrum(object):
 
     def NonlinearScale(self):
         return 1.0/np.sqrt(self.VelocityDispersion())
+
+    def Save(self, filename, kmin=1e-3, kmax=1., Nk=1001, log=False):
+        """two-column text file of (k, P(k)) (PowerSpectrum.i:17, PowerSpectrum.cpp:77-92)"""
+        import time
+        i = np.arange(int(Nk))
+        k = kmin*np.exp(i*np.log(kmax/kmin)/(Nk - 1)) if log else kmin + i*(kmax - kmin)/(Nk - 1)
+        P = np.atleast_1d(self(k))
+        with open(filename, 'w+') as fp:
+            fp.write("# Power spectrum saved at %s\n\n" % time.ctime())
+            fp.write("# k -- P(k)\n")
+            for a, b in zip(k, P):
+                fp.write("%e %e\n" % (a, b))
 
 
 class LinearPS(PowerSpectrum, PickalableSWIG):
@@ -527,6 +567,9 @@ class ImnOneLoop(PickalableSWIG):
     def EvaluateCross(self, k, m, n): return self._ev(1, k, m, n)
     def EvaluateOneLoop(self, k, m, n): return self._ev(2, k, m, n)
     def GetEpsrel(self): return self._eps
+    def GetOneLoopPS1(self): return self._P1
+    def GetOneLoopPS2(self): return self._P2 if self._P2 is not None else self._P1
+    def GetEqual(self): return self._P2 is None          # single-spectrum constructor (ImnOneLoop.cpp:14-22)
 
 
 # ------------------------------------------------------------------------------ Zel'dovich
@@ -873,6 +916,9 @@ class FFTLog(object):
         return self._kr
 
 
+Spline = object          # the SWIG base of LinearSpline / CubicSpline (Spline.i:5-22): both expose Evaluate / EvaluateDerivative
+
+
 class LinearSpline(object):
     """``LinearSpline(x, y)`` (Spline.i:24, Spline.cpp:58-130): piecewise-linear, zero outside the domain"""
     def __init__(self, x, y):
@@ -903,6 +949,9 @@ class CubicSpline(object):
     """``CubicSpline(x, y)`` (Spline.i; netlib spline of Spline.cpp:211-273, zero outside the domain)"""
     def __init__(self, x, y):
         self._x, self._y = N.as_f64(x), N.as_f64(y)
+
+    def Evaluate(self, xq):
+        return self(xq)
 
     def __call__(self, xq):
         xa, scalar = _scalar_or_array(xq)

@@ -284,3 +284,37 @@ def test_variant_cosmology_vs_tight_reference(golden):
         for j, o in enumerate([pygcl.OneLoopPdd(plin), pygcl.OneLoopPdv(plin), pygcl.OneLoopPvv(plin), pygcl.OneLoopP22Bar(plin)]):
             err = relerr_floor(o.GetOneLoopPower(), common[j], P1)
             assert err[k1 < 0.5].max() < TOL, ('one-loop table', j, err[k1 < 0.5].max())
+
+
+def test_pygcl_small_surface(golden, tmp_path):
+    """Cosmology.from_power / clone(tf=EH_NoWiggle) / NormalizeTransferFunction, PowerSpectrum.Save, ImnOneLoop getters"""
+    from pyrsd_b200 import pygcl
+    from tests.gpu_common import golden_pygcl_cosmology
+    cosmo = golden_pygcl_cosmology(golden)
+    P = pygcl.LinearPS(cosmo, 0.)
+    # a cosmology read off its own linear spectrum reproduces it (the transfer function is defined up to its amplitude)
+    k = cosmo.GetDiscreteK()
+    c2 = pygcl.Cosmology.from_power(cosmo.GetParams(), k, P(k), sigma8=cosmo.sigma8())
+    assert abs(c2.GetDiscreteTk().max() - 1e7) < 1e-3
+    kq = np.logspace(-3, 0, 30)
+    assert np.max(np.abs(pygcl.LinearPS(c2, 0.)(kq)/P(kq) - 1)) < 1e-9
+    with pytest.raises(ValueError):
+        pygcl.Cosmology.from_power(cosmo.GetParams(), k, P(k))
+    # no-wiggle clone: same sigma8, smooth spectrum within the BAO amplitude of the full one
+    nw = cosmo.clone(tf=pygcl.transfers.EH_NoWiggle)
+    Pnw = pygcl.LinearPS(nw, 0.)
+    assert abs(Pnw.Sigma(8.)/cosmo.sigma8() - 1) < 1e-6
+    assert np.max(np.abs(Pnw(kq)/P(kq) - 1)) < 0.15
+    assert np.allclose(nw.GetDiscreteTk(), cosmo.GetNoWiggleTransfer(k), rtol=1e-15)
+    c3 = cosmo.clone()
+    c3.NormalizeTransferFunction(0.5)
+    assert abs(pygcl.LinearPS(c3, 0.).Sigma(8.) - 0.5) < 1e-6
+    path = str(tmp_path / 'plin.dat')
+    P.Save(path, 1e-3, 1., 11, True)
+    tab = np.loadtxt(path)
+    assert tab.shape == (11, 2) and np.allclose(tab[:, 1], P(tab[:, 0]), rtol=1e-5)
+    Pdd, Pvv = pygcl.OneLoopPdd(P), pygcl.OneLoopPvv(P)
+    I = pygcl.ImnOneLoop(Pvv, Pdd, 1e-4)
+    assert I.GetOneLoopPS1() is Pvv and I.GetOneLoopPS2() is Pdd and not I.GetEqual()
+    assert pygcl.ImnOneLoop(Pdd).GetEqual() and Pdd.GetCosmology() is cosmo
+    assert pygcl.CubicSpline(k[:50], P(k[:50])).Evaluate(k[10]) == P(k[10])
