@@ -954,3 +954,21 @@ def _z_setattr(self, name, value):
 GalaxySpectrum.__setattr__ = _z_setattr
 
 from . import dm as _dm_models  # noqa: E402,F401  (dm.py ends by importing model_api, which completes GalaxySpectrum)
+
+
+def load_model(filename, show_warning=True):
+    """a model saved with ``to_npy`` (``pyRSD.rsd.load_model``, rsd/__init__.py:39-60)"""
+    return np.load(filename, allow_pickle=True).tolist()
+
+
+_LAZY = {'DarkMatterSpectrum': 'dm', 'BiasedSpectrum': 'dm', 'HaloSpectrum': 'dm', 'QuasarSpectrum': 'qso',
+         'ExtrapolatedPowerSpectrum': 'correlation', 'SmoothedXiMultipoles': 'correlation', 'transfers': 'transfers'}
+
+
+def __getattr__(name):
+    # the names ``pyRSD.rsd`` exports (rsd/__init__.py:21-29), resolved on first use
+    if name in _LAZY:
+        import importlib
+        mod = importlib.import_module('.' + _LAZY[name], __package__)
+        return mod if name == 'transfers' else getattr(mod, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

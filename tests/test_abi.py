@@ -68,3 +68,19 @@ def test_static_queries_work_without_gpu(lib):
     assert len(x) == 2457
     cfg = _native.quad_config_default()
     assert len(cfg) == 56 and cfg[0] == 1e-8 and cfg[21] == 12 and cfg[25] == 16 and cfg[29] == 12 and cfg[41] == 10 and cfg[42] == 7 and cfg[45] == 10 and cfg[46] == 9 and cfg[49] == 10 and cfg[50] == 8
+
+
+def test_rsd_module_exports_the_reference_names():
+    """``from pyRSD.rsd import ...`` (rsd/__init__.py:21-29) works against ``pyrsd_b200.rsd``; every model class answers the
+    reference's public methods that do not need a device to exist"""
+    from pyrsd_b200 import rsd
+    for name in ('GalaxySpectrum', 'DarkMatterSpectrum', 'BiasedSpectrum', 'HaloSpectrum', 'QuasarSpectrum',
+                 'ExtrapolatedPowerSpectrum', 'SmoothedXiMultipoles', 'transfers', 'load_model'):
+        assert getattr(rsd, name) is not None
+    for cls in (rsd.GalaxySpectrum, rsd.BiasedSpectrum, rsd.DarkMatterSpectrum, rsd.QuasarSpectrum):
+        for meth in ('power', 'poles', 'monopole', 'quadrupole', 'hexadecapole', 'derivative_k', 'derivative_mu', 'apply_transfer'):
+            assert callable(getattr(cls, meth)), (cls.__name__, meth)
+    for meth in ('Pgal_cAcA', 'Pgal_cBsA', 'Pgal_sBsB', 'Pgal_cc', 'preserve', 'use_spt', 'cache_override', 'to_npy', 'from_npy'):
+        assert hasattr(rsd.GalaxySpectrum, meth), meth
+    with pytest.raises(AttributeError):
+        rsd.no_such_name
