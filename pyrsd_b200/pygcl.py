@@ -105,6 +105,26 @@ def _lookup(table, z, what):
         raise ValueError("Cosmology: no `%s` value for z = %s" % (what, z))
 
 
+def eh_nowiggle_transfer(k, h, Omega0_m, Omega0_b, Tcmb=2.7255):
+    """Eisenstein & Hu (1998) no-wiggle transfer function, eqs. 26, 28-31, with the parameters of
+    ``Cosmology::SetEisensteinHuParameters`` (Cosmology.cpp:233-246, 311-362); k in h/Mpc"""
+    k = np.asarray(k, dtype=float)
+    omh2, obh2 = Omega0_m*h*h, Omega0_b*h*h
+    fb = obh2/omh2
+    theta = Tcmb/2.7
+    keq = 0.0746*omh2/theta**2
+    s = h*44.5*np.log(9.83/omh2)/np.sqrt(1. + 10.*obh2**0.75)
+    alpha_gamma = 1. - 0.328*np.log(431.*omh2)*fb + 0.38*np.log(22.3*omh2)*fb*fb
+    kk = k*h
+    ks = kk*s/h
+    q = kk/(13.41*keq)
+    geff = omh2*(alpha_gamma + (1. - alpha_gamma)/(1. + (0.43*ks)**4))
+    qeff = q*omh2/geff
+    L0 = np.log(2.*np.e + 1.8*qeff)
+    C0 = 14.2 + 731./(1. + 62.5*qeff)
+    return L0/(L0 + C0*qeff**2)
+
+
 class Cosmology(PickalableSWIG):
     """Host container of a linear transfer function and its normalisation.
 
@@ -147,23 +167,8 @@ class Cosmology(PickalableSWIG):
         return Cosmology(a[0], transfers.EH_NoWiggle, a[2], a[3], self.GetNoWiggleTransfer(a[3]))
 
     def GetNoWiggleTransfer(self, k):
-        """Eisenstein & Hu (1998) no-wiggle fit, eqs. 26, 28-31 (Cosmology.cpp:233-246 with the parameters of :311-362)"""
-        k = np.asarray(k, dtype=float)
-        h = self.h()
-        omh2, obh2 = self.Omega0_m()*h*h, self.Omega0_b()*h*h
-        fb = obh2/omh2
-        theta = self.Tcmb()/2.7
-        keq = 0.0746*omh2/theta**2
-        s = h*44.5*np.log(9.83/omh2)/np.sqrt(1. + 10.*obh2**0.75)
-        alpha_gamma = 1. - 0.328*np.log(431.*omh2)*fb + 0.38*np.log(22.3*omh2)*fb*fb
-        kk = k*h
-        ks = kk*s/h
-        q = kk/(13.41*keq)
-        geff = omh2*(alpha_gamma + (1. - alpha_gamma)/(1. + (0.43*ks)**4))
-        qeff = q*omh2/geff
-        L0 = np.log(2.*np.e + 1.8*qeff)
-        C0 = 14.2 + 731./(1. + 62.5*qeff)
-        return L0/(L0 + C0*qeff**2)
+        """Eisenstein & Hu (1998) no-wiggle fit at this cosmology's parameters (Cosmology.cpp:233-246)"""
+        return eh_nowiggle_transfer(k, self.h(), self.Omega0_m(), self.Omega0_b(), self.Tcmb())
 
     # ---- accessors
     def GetParams(self): return self._params

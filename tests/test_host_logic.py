@@ -166,3 +166,24 @@ def test_thinned_k_lists_and_fill_maps(emul, tight):
     for kk in (np.logspace(-5, 0, 40), np.logspace(-5, 0, 200)[::-1].copy(), np.sort(np.random.default_rng(1).uniform(1e-5, 1., 200))):
         keep, idx, w, nsub = emul.fill_map(0, kk)
         assert nsub == len(kk) and keep.all()
+
+
+def test_eh_nowiggle_host_formula_vs_reference_extrapolation(ref_cosmo, golden):
+    """``pygcl.eh_nowiggle_transfer`` (the table of ``Cosmology.clone(tf=EH_NoWiggle)``): outside the tabulated k the
+    reference's transfer function is its no-wiggle fit scaled to the table's end (Cosmology.cpp:187-199), so ratios of the
+    reference transfer there are ratios of the fit"""
+    from pyrsd_b200 import pygcl
+    a = ref_cosmo.args
+    h, Om, Ob, Tcmb = a[4], a[5], a[6], a[7]
+    for ks in (np.array([25., 40., 90., 300.]), np.array([1e-6, 3e-6, 8e-6])):
+        ref = ref_cosmo.transfer(ks)
+        mine = pygcl.eh_nowiggle_transfer(ks, h, Om, Ob, Tcmb)
+        assert np.max(np.abs((mine/mine[0])/(ref/ref[0]) - 1)) < 1e-13
+
+
+def test_quasar_growth_function_einstein_de_sitter():
+    """qso.growth_function (power_qso.py:32-46): E(a) int_0^a da' / (a' E)^3 = a / 2.5 for Omega_m = 1"""
+    from pyrsd_b200.qso import growth_function
+    eds = {'Omega0_m': 1.0, 'Omega0_lambda': 0.0, 'Omega0_k': 0.0}
+    for z in (0., 1., 100.):
+        assert abs(growth_function(eds, z)*2.5*(1 + z) - 1) < 1e-8
