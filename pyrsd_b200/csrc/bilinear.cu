@@ -76,12 +76,20 @@ void geometry_chunk(const double* k, int nk, double qmax, const QuadConfig& cfg,
     std::vector<double>& wgt = out.wgt;
     std::vector<double>& b_coef = out.b_coef;
     out.node_off.assign(1, 0);
+    {
+        // room for every padded node up front: the gather below appends ~1e6 times per operator
+        const int64_t pad_to = BM >= 16 ? 16 : 4;
+        size_t total = 0;
+        for (int ik = 0; ik < nk; ik++) total += (size_t)((H.node_off[ik + 1] - H.node_off[ik] + pad_to - 1)/pad_to*pad_to);
+        b.reserve(total); wgt.reserve(total); b_j0.reserve(total); n_ol.reserve(total); b_coef.reserve(4*total);
+    }
     std::vector<int64_t> src;                     // source node of every slot of this k (-1: padding)
     // an item = the nodes of one k that share the stencil start AND the outer node: every read of theirs is a
     // broadcast.  A group of BM lanes takes items whose stencil starts are distinct modulo BM (table reads) and,
     // where possible, whose outer indices are too (the P(a) reads of the nodal kernels).
     struct Item { int j0, ol; int64_t begin, end; };
-    std::vector<int64_t> sorted;
+    std::vector<int64_t> sorted, sort_tmp;
+    std::vector<int64_t> sort_cnt;
     std::vector<Item> items;
     std::vector<std::vector<int>> queue(BM);      // per stencil residue: item indices, ascending
     for (int ik = 0; ik < nk; ik++) {
@@ -97,8 +105,22 @@ void geometry_chunk(const double* k, int nk, double qmax, const QuadConfig& cfg,
         sorted.clear();
         for (int64_t j = n0; j < n1; j++) sorted.push_back(j);
         for (int64_t j = cnt; j < padded; j++) sorted.push_back(-1);       // padding reads stencil 0, outer node 0
-        std::stable_sort(sorted.begin(), sorted.end(), [&](int64_t x, int64_t y) {
-            return j0_of(x) != j0_of(y) ? j0_of(x) < j0_of(y) : ol_of(x) < ol_of(y); });
+        // stable order by (stencil start, outer node): two stable counting passes, least significant key first (the
+        // comparison sort this replaces took a third of the generator's time; same order, geometry_checksum unchanged)
+        {
+            const int n_ol_keys = (int)(H.outer_off[ik + 1] - o0) + 1;
+            int j0_max = 0;
+            for (int64_t x : sorted) j0_max = std::max(j0_max, j0_of(x));
+            sort_tmp.resize(sorted.size());
+            sort_cnt.assign((size_t)n_ol_keys + 1, 0);
+            for (int64_t x : sorted) sort_cnt[ol_of(x) + 1]++;
+            for (int i = 0; i < n_ol_keys; i++) sort_cnt[i + 1] += sort_cnt[i];
+            for (int64_t x : sorted) sort_tmp[sort_cnt[ol_of(x)]++] = x;
+            sort_cnt.assign((size_t)j0_max + 2, 0);
+            for (int64_t x : sort_tmp) sort_cnt[j0_of(x) + 1]++;
+            for (int i = 0; i <= j0_max; i++) sort_cnt[i + 1] += sort_cnt[i];
+            for (int64_t x : sort_tmp) sorted[sort_cnt[j0_of(x)]++] = x;
+        }
         items.clear();
         for (auto& q : queue) q.clear();
         for (int64_t i = 0; i < padded; ) {
@@ -269,6 +291,28 @@ std::shared_ptr<GeometryHost> make_geometry_host(const double* k, int nk, double
         g->nodew[i] = make_int2(g->pack[i], bits);
     }
     return g;
+}
+
+// FNV-1a over every array the device receives: pins the node order (tests, and any change of the host-side generator)
+uint64_t geometry_checksum(const GeometryHost& h)
+{
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t bytes) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < bytes; i++) { x ^= c[i]; x *= 1099511628211ull; }
+    };
+    mix(h.node_off.data(), h.node_off.size()*sizeof(int64_t));
+    mix(h.outer_off.data(), h.outer_off.size()*sizeof(int64_t));
+    mix(h.H.a.data(), h.H.a.size()*sizeof(double));
+    mix(h.H.a_j0.data(), h.H.a_j0.size()*sizeof(int32_t));
+    mix(h.H.a_coef.data(), h.H.a_coef.size()*sizeof(double));
+    mix(h.H.o_kid.data(), h.H.o_kid.size()*sizeof(int32_t));
+    mix(h.b.data(), h.b.size()*sizeof(double));
+    mix(h.wgt.data(), h.wgt.size()*sizeof(double));
+    mix(h.b_coef.data(), h.b_coef.size()*sizeof(double));
+    mix(h.pack.data(), h.pack.size()*sizeof(int));
+    mix(h.nodew.data(), h.nodew.size()*sizeof(int2));
+    return x;
 }
 
 std::shared_ptr<NodeGeometry> upload_geometry(Context& ctx, const GeometryHost& h)

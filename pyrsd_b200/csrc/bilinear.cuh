@@ -59,6 +59,7 @@ struct GeometryHost;
 std::shared_ptr<GeometryHost> make_geometry_host(const double* k, int nk, double qmax, const QuadConfig& cfg,
                                                  const KnotGrid& grid, int bank_mod = 16);
 std::shared_ptr<NodeGeometry> upload_geometry(Context& ctx, const GeometryHost& h);
+uint64_t geometry_checksum(const GeometryHost& h);
 
 struct BilinearOp {
     std::shared_ptr<NodeGeometry> geo;
