@@ -252,44 +252,62 @@ std::shared_ptr<GeometryHost> make_geometry_host(const double* k, int nk, double
     std::vector<double>& b = g->b;
     std::vector<double>& wgt = g->wgt;
     std::vector<double>& b_coef = g->b_coef;
-    g->node_off.assign(1, 0);
-    g->outer_off.assign(1, 0);
-    size_t tot_nodes = 0, tot_outer = 0;
-    for (const GeoChunk& c : chunks) { tot_nodes += c.b.size(); tot_outer += c.H.a.size(); }
-    b_j0.reserve(tot_nodes); n_ol.reserve(tot_nodes); b.reserve(tot_nodes); wgt.reserve(tot_nodes); b_coef.reserve(4*tot_nodes);
-    H.a.reserve(tot_outer); H.a_j0.reserve(tot_outer); H.a_coef.reserve(4*tot_outer); H.o_kid.reserve(tot_outer);
-    for (int ci = 0; ci < nchunk; ci++) {
-        GeoChunk& c = chunks[ci];
-        const int64_t node_base = (int64_t)b.size(), outer_base = (int64_t)H.a.size();
-        for (size_t i = 1; i < c.node_off.size(); i++) g->node_off.push_back(node_base + c.node_off[i]);
-        for (size_t i = 1; i < c.H.outer_off.size(); i++) g->outer_off.push_back(outer_base + c.H.outer_off[i]);
-        b_j0.insert(b_j0.end(), c.b_j0.begin(), c.b_j0.end());
-        n_ol.insert(n_ol.end(), c.n_ol.begin(), c.n_ol.end());
-        b.insert(b.end(), c.b.begin(), c.b.end());
-        wgt.insert(wgt.end(), c.wgt.begin(), c.wgt.end());
-        b_coef.insert(b_coef.end(), c.b_coef.begin(), c.b_coef.end());
-        H.a.insert(H.a.end(), c.H.a.begin(), c.H.a.end());
-        H.a_j0.insert(H.a_j0.end(), c.H.a_j0.begin(), c.H.a_j0.end());
-        H.a_coef.insert(H.a_coef.end(), c.H.a_coef.begin(), c.H.a_coef.end());
-        for (int32_t kid : c.H.o_kid) H.o_kid.push_back(kid + lo[ci]);
-        g->max_outer = std::max(g->max_outer, c.max_outer);
-        c = GeoChunk();                            // release the chunk's memory
+    // concatenate the chunks: offsets first, then every chunk copies itself into place on the worker threads, which also
+    // derive the packed per-node words (done serially this step was as long as the chunk generation of the largest operator)
+    std::vector<size_t> node_base(nchunk + 1, 0), outer_base(nchunk + 1, 0);
+    for (int c = 0; c < nchunk; c++) {
+        node_base[c + 1] = node_base[c] + chunks[c].b.size();
+        outer_base[c + 1] = outer_base[c] + chunks[c].H.a.size();
+        g->max_outer = std::max(g->max_outer, chunks[c].max_outer);
     }
-    // s = sum_m m c_m exactly reproduces the abscissa of a Lagrange rule of degree >= 1
-    g->bs.resize(b_j0.size());
-    g->as.resize(H.a_j0.size());
-    for (size_t i = 0; i < g->bs.size(); i++) g->bs[i] = b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3];
-    for (size_t i = 0; i < g->as.size(); i++) g->as[i] = H.a_coef[4*i + 1] + 2.0*H.a_coef[4*i + 2] + 3.0*H.a_coef[4*i + 3];
-    g->pack.resize(b_j0.size());
-    g->nodew.resize(b_j0.size());
-    for (size_t i = 0; i < b_j0.size(); i++) {
-        PRSD_REQUIRE(b_j0[i] >= 0 && b_j0[i] < 4096 && n_ol[i] >= 0 && n_ol[i] < (1 << 19), "node index does not fit the packed stream");
-        g->pack[i] = (n_ol[i] << 12) | b_j0[i];
-        const float sf = (float)g->bs[i];
-        int bits;
-        std::memcpy(&bits, &sf, sizeof(int));
-        g->nodew[i] = make_int2(g->pack[i], bits);
+    const size_t tot_nodes = node_base[nchunk], tot_outer = outer_base[nchunk];
+    g->node_off.assign(nk + 1, 0);
+    g->outer_off.assign(nk + 1, 0);
+    b_j0.resize(tot_nodes); n_ol.resize(tot_nodes); b.resize(tot_nodes); wgt.resize(tot_nodes); b_coef.resize(4*tot_nodes);
+    H.a.resize(tot_outer); H.a_j0.resize(tot_outer); H.a_coef.resize(4*tot_outer); H.o_kid.resize(tot_outer);
+    g->bs.resize(tot_nodes); g->as.resize(tot_outer); g->pack.resize(tot_nodes); g->nodew.resize(tot_nodes);
+    next = 0;
+    auto merger = [&]() {
+        for (int ci = next++; ci < nchunk; ci = next++) {
+            GeoChunk& c = chunks[ci];
+            const size_t nb = node_base[ci], ob = outer_base[ci];
+            try {
+                for (size_t i = 1; i < c.node_off.size(); i++) g->node_off[lo[ci] + i] = (int64_t)nb + c.node_off[i];
+                for (size_t i = 1; i < c.H.outer_off.size(); i++) g->outer_off[lo[ci] + i] = (int64_t)ob + c.H.outer_off[i];
+                std::copy(c.b_j0.begin(), c.b_j0.end(), b_j0.begin() + nb);
+                std::copy(c.n_ol.begin(), c.n_ol.end(), n_ol.begin() + nb);
+                std::copy(c.b.begin(), c.b.end(), b.begin() + nb);
+                std::copy(c.wgt.begin(), c.wgt.end(), wgt.begin() + nb);
+                std::copy(c.b_coef.begin(), c.b_coef.end(), b_coef.begin() + 4*nb);
+                std::copy(c.H.a.begin(), c.H.a.end(), H.a.begin() + ob);
+                std::copy(c.H.a_j0.begin(), c.H.a_j0.end(), H.a_j0.begin() + ob);
+                std::copy(c.H.a_coef.begin(), c.H.a_coef.end(), H.a_coef.begin() + 4*ob);
+                for (size_t i = 0; i < c.H.o_kid.size(); i++) H.o_kid[ob + i] = c.H.o_kid[i] + lo[ci];
+                // s = sum_m m c_m exactly reproduces the abscissa of a Lagrange rule of degree >= 1
+                for (size_t i = ob; i < ob + c.H.a.size(); i++) g->as[i] = H.a_coef[4*i + 1] + 2.0*H.a_coef[4*i + 2] + 3.0*H.a_coef[4*i + 3];
+                for (size_t i = nb; i < nb + c.b.size(); i++) {
+                    g->bs[i] = b_coef[4*i + 1] + 2.0*b_coef[4*i + 2] + 3.0*b_coef[4*i + 3];
+                    PRSD_REQUIRE(b_j0[i] >= 0 && b_j0[i] < 4096 && n_ol[i] >= 0 && n_ol[i] < (1 << 19), "node index does not fit the packed stream");
+                    g->pack[i] = (n_ol[i] << 12) | b_j0[i];
+                    const float sf = (float)g->bs[i];
+                    int bits;
+                    std::memcpy(&bits, &sf, sizeof(int));
+                    g->nodew[i] = make_int2(g->pack[i], bits);
+                }
+                c = GeoChunk();                        // release the chunk's memory
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lk(fmu);
+                failure = e.what();
+            }
+        }
+    };
+    if (nthreads == 1) merger();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++) pool.emplace_back(merger);
+        for (auto& t : pool) t.join();
     }
+    PRSD_REQUIRE(failure.empty(), "make_geometry: %s", failure.c_str());
     return g;
 }
 
