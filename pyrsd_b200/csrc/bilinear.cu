@@ -14,7 +14,8 @@ namespace prsd {
 
 size_t NodeGeometry::bytes() const
 {
-    return n_nodes*(sizeof(int)*3 + sizeof(double)*6) + n_outer*(sizeof(int)*2 + sizeof(double)*5);
+    // inner nodes: b, wgt, n_outer_local, b_node; outer nodes: a, a_j0, a_coef, a_s
+    return n_nodes*(sizeof(double)*2 + sizeof(int) + sizeof(int2)) + n_outer*(sizeof(int) + sizeof(double)*6);
 }
 
 // Host part of the geometry for a contiguous range of k: nodes, padding and lane ordering.  Every k is independent,
@@ -344,20 +345,17 @@ std::shared_ptr<NodeGeometry> upload_geometry(Context& ctx, const GeometryHost& 
     g->n_nodes = (int64_t)h.b.size();
     g->n_outer = (int64_t)h.H.a.size();
     cudaStream_t s = ctx.stream;
+    // (the stencil starts, Lagrange coefficients, coordinates and index words of the inner nodes stay on the host: the
+    // kernels read them packed in b_node; 48 bytes per node less to upload and to hold)
     g->outer_off.upload(g->h_outer_off, s);
     g->node_off.upload(g->h_node_off, s);
     g->a_j0.upload(h.H.a_j0, s);
-    g->o_kid.upload(h.H.o_kid, s);
     g->a.upload(h.H.a, s);
     g->a_coef.upload(h.H.a_coef, s);
-    g->b_j0.upload(h.b_j0, s);
     g->n_outer_local.upload(h.n_ol, s);
     g->b.upload(h.b, s);
     g->wgt.upload(h.wgt, s);
-    g->b_coef.upload(h.b_coef, s);
-    g->b_s.upload(h.bs, s);
     g->a_s.upload(h.as, s);
-    g->b_pack.upload(h.pack, s);
     g->b_node.upload(h.nodew, s);
     g->kdev.upload(g->k, s);
     return g;       // copies from pageable memory are staged before cudaMemcpyAsync returns: h may be released
